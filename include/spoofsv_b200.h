@@ -1,0 +1,115 @@
+/* spoofsv_b200 -- C ABI of the B200-native Text2Mel + SSRN synthesis hot path.
+ *
+ * The reference (MingruiYuan/SpoofSV) has no FFI layer: its boundary for this path is the
+ * Python nn.Module API of models/TTSModel.py plus the state_dict layout.  The
+ * entry points below are what the `forward()` shims of the drop-in `melSyn` / `SSRN` classes
+ * (spoofsv_b200/models/TTSModel.py) bind through ctypes; each one names the reference code
+ * it replaces.  Plain pointers and sizes only: no torch types, no C++ in the signatures.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error (SSV_E*); ssv_last_error() gives
+ *     the message for the calling thread;
+ *   - "dev" pointers are CUDA device pointers on the current device, "host" pointers are
+ *     ordinary (ideally pinned) host memory; tensors are fp32, contiguous unless strides are
+ *     given, in the reference's channels-first layout (B, C, T);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *     asynchronous on that stream unless stated otherwise;
+ *   - parameters are passed by state_dict key: parallel arrays of names, device pointers and
+ *     element counts (order irrelevant, every key of SURVEY.md Appendix B required).  The
+ *     library keeps repacked private copies; the caller's tensors may be freed afterwards.
+ */
+#ifndef SPOOFSV_B200_H_
+#define SPOOFSV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSV_OK 0
+#define SSV_EINVAL 1   /* bad argument / unsupported shape */
+#define SSV_ECUDA 2    /* a CUDA runtime call failed */
+#define SSV_ENOMEM 3
+#define SSV_ESTATE 4   /* call sequence error, decode kernel aborted */
+
+#define SSV_PREC_FP32 0   /* CUDA-core FP32 FMA, <= 1e-4 max-abs vs the reference */
+#define SSV_PREC_BF16 1   /* tcgen05 BF16 tensor cores, FP32 accumulate, <= 2e-2 rel-L2 */
+
+typedef struct ssv_text2mel ssv_text2mel;   /* packed Text2Mel weights (melSyn) */
+typedef struct ssv_decoder ssv_decoder;     /* incremental AR decode state */
+typedef struct ssv_ssrn ssv_ssrn;           /* packed SSRN weights + workspace */
+
+int ssv_version(void);
+const char* ssv_last_error(void);
+/* SM count and compute capability of the current device. */
+int ssv_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Kernels launched by the calling thread since the last reset (bench "gpu_launches"). */
+long ssv_launch_count(int reset);
+
+/* ---- single highwayConv, replaces highwayConv.forward (models/TTSModel.py:63-84) ----------
+ * x, y: dev (B, d, T).  conv_w (2d, d, k), conv_b (2d), ln*_w/b (d): dev.  k in {1,3};
+ * d in {256, 512}. */
+int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_b,
+                         const float* ln1_w, const float* ln1_b, const float* ln2_w, const float* ln2_b,
+                         int B, int d, int T, int k, int dilation, int causal,
+                         float* y, int precision, void* stream);
+
+/* ---- Text2Mel ------------------------------------------------------------------------------
+ * replaces melSyn.__init__ + load_state_dict (models/TTSModel.py:236-251): 214 tensors. */
+int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, const int64_t* numels,
+                        int n_params, int vocab_len, int spkemb_dim, int textemb_dim, int freq_bins,
+                        int hidden_dim, ssv_text2mel** out);
+int ssv_text2mel_destroy(ssv_text2mel* m);
+
+/* replaces textEncoder.forward (models/TTSModel.py:126-140).  textid: dev int64 (B, 1, N);
+ * K, V: dev (B, hidden, N). */
+int ssv_text_encoder_fwd(ssv_text2mel* m, const int64_t* textid, int B, int N, float* K, float* V,
+                         int precision, void* stream);
+
+/* Incremental decoder: replaces the eval branch of melSyn.forward (models/TTSModel.py:275-300)
+ * as driven by the AR loops (generate_test_utterances.py:105-116, synthesize.py:103-109). */
+int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_frames, ssv_decoder** out);
+int ssv_decoder_destroy(ssv_decoder* d);
+/* Start a new batch of utterances (the reference's T == 1 call).  K, V: dev (B, hidden, N);
+ * spkemb: dev (B, E, 1).  Y (B, F, t_cap), A (B, N, t_cap), pma_traj int64 (t_cap, B) are
+ * caller-owned dev buffers the decoder fills column by column; A is zeroed here. */
+int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const float* spkemb, int B, int N,
+                      float* Y, float* A, int64_t* pma_traj, int t_cap, void* stream);
+/* One frame, caller-driven (drop-in protocol): x = the newest column of the caller's melspec,
+ * element (b, f) at x[b*x_stride_b + f*x_stride_f]; pma_in: dev int64 (B,) or NULL to chain the
+ * decoder's own argmax.  Writes Y[:, :, t], A[:, :, t], pma_traj[t]; advances t. */
+int ssv_decoder_step(ssv_decoder* d, const float* x, long x_stride_b, long x_stride_f,
+                     const int64_t* pma_in, void* stream);
+/* n_steps frames free-running in one launch: x_0 = 0 (or Y[:, :, t-1] when continuing),
+ * x_t = y_{t-1}. */
+int ssv_decoder_run(ssv_decoder* d, int n_steps, void* stream);
+/* Frames decoded since begin. */
+int ssv_decoder_frames(const ssv_decoder* d);
+/* Synchronise `stream` and report a decode-kernel abort (barrier timeout) if one happened. */
+int ssv_decoder_check(ssv_decoder* d, void* stream);
+
+/* ---- SSRN -----------------------------------------------------------------------------------
+ * replaces SSRN.__init__ + load_state_dict (models/TTSModel.py:321-340): 76 tensors. */
+int ssv_ssrn_create(const char* const* names, const float* const* dev_ptrs, const int64_t* numels,
+                    int n_params, int freq_bins, int output_bins, int ssrn_dim, ssv_ssrn** out);
+int ssv_ssrn_destroy(ssv_ssrn* m);
+/* replaces SSRN.forward (models/TTSModel.py:342-362).  mel: dev (B, F, T) with element strides;
+ * out: dev (B, O, 4T) contiguous. */
+int ssv_ssrn_fwd(ssv_ssrn* m, const float* mel, long stride_b, long stride_f, long stride_t, int B, int T,
+                 float* out, int precision, void* stream);
+
+/* ---- whole utterance batch with HOST buffers -----------------------------------------------
+ * replaces generate_test_utterances.py:105-124 (AR loop, SSRN, .cpu()).  Copies textid (B, N)
+ * int64 and spkemb (B, E) fp32 from the host, runs TextEnc + n_frames of decode + SSRN, copies
+ * lin (B, O, 4*n_frames) and, when non-NULL, mel (B, F, n_frames), A (B, N, n_frames) and
+ * pma_traj (n_frames, B) back, and synchronises the stream. */
+int ssv_synthesize_host(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* s, const int64_t* textid_host,
+                        const float* spkemb_host, int B, int N, int n_frames, float* lin_host,
+                        float* mel_host, float* A_host, int64_t* pma_traj_host,
+                        int t2m_precision, int ssrn_precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPOOFSV_B200_H_ */

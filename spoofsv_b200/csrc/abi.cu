@@ -1,0 +1,734 @@
+// C-ABI entry points (include/spoofsv_b200.h): handles, weight repacking, layer schedules.
+#include "../../include/spoofsv_b200.h"
+
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace ssv {
+
+thread_local std::string g_err;
+thread_local long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+namespace {
+
+struct Arena {
+  std::vector<void*> ptrs;
+  ~Arena() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  int alloc(size_t count, T** out) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, count * sizeof(T) + 256) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc of %zu bytes failed", count * sizeof(T));
+      return kNoMem;
+    }
+    ptrs.push_back(p);
+    *out = static_cast<T*>(p);
+    return kOk;
+  }
+};
+
+struct ParamMap {
+  std::map<std::string, std::pair<const float*, int64_t>> m;
+  int get(const std::string& name, int64_t numel, const float** out) const {
+    auto it = m.find(name);
+    if (it == m.end()) {
+      set_error("state_dict key '%s' missing", name.c_str());
+      return kInval;
+    }
+    if (it->second.second != numel) {
+      set_error("state_dict key '%s' has %lld elements, expected %lld", name.c_str(),
+                (long long)it->second.second, (long long)numel);
+      return kInval;
+    }
+    *out = it->second.first;
+    return kOk;
+  }
+};
+
+int build_param_map(const char* const* names, const float* const* ptrs, const int64_t* numels, int n,
+                    ParamMap* pm) {
+  SSV_CHECK(names && ptrs && numels && n > 0, "empty parameter list");
+  for (int i = 0; i < n; ++i) {
+    SSV_CHECK(names[i] && ptrs[i], "null parameter entry %d", i);
+    pm->m[names[i]] = {ptrs[i], numels[i]};
+  }
+  return kOk;
+}
+
+int copy_vec(Arena& ar, const ParamMap& pm, const std::string& name, int n, float** out, cudaStream_t s) {
+  const float* src;
+  SSV_TRY(pm.get(name, n, &src));
+  SSV_TRY(ar.alloc<float>(n, out));
+  SSV_CUDA(cudaMemcpyAsync(*out, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  return kOk;
+}
+
+// A conv layer packed for the tiled kernels (fp32 [k*cin_p][n_pad], bf16 [n_pad][k*cin_p]).
+struct ConvPack {
+  float* W = nullptr;
+  float* bias = nullptr;
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+  void* Wtc = nullptr;    // bf16 copy for the tensor-core path (optional)
+  int cin = 0, cin_p = 0, k = 1, n = 0, n_pad = 0;
+};
+
+int pack_conv(Arena& ar, const ParamMap& pm, const std::string& name, int n, int cin, int k, ConvPack* c,
+              cudaStream_t s) {
+  const float *w, *b;
+  SSV_TRY(pm.get(name + ".weight", (int64_t)n * cin * k, &w));
+  SSV_TRY(pm.get(name + ".bias", n, &b));
+  c->cin = cin;
+  c->cin_p = round_up(cin, 16);
+  c->k = k;
+  c->n = n;
+  c->n_pad = round_up(n, 64);
+  SSV_TRY(ar.alloc<float>((size_t)k * c->cin_p * c->n_pad, &c->W));
+  SSV_TRY(ar.alloc<float>(c->n_pad, &c->bias));
+  SSV_TRY(launch_pack_conv_w(w, n, cin, k, c->cin_p, c->n_pad, c->W, s));
+  SSV_TRY(launch_pad_vec(b, n, c->n_pad, c->bias, s));
+  return kOk;
+}
+
+int pack_ln(Arena& ar, const ParamMap& pm, const std::string& name, int n, float** g, float** b, cudaStream_t s) {
+  SSV_TRY(copy_vec(ar, pm, name + ".weight", n, g, s));
+  SSV_TRY(copy_vec(ar, pm, name + ".bias", n, b, s));
+  return kOk;
+}
+
+int pack_highway(Arena& ar, const ParamMap& pm, const std::string& prefix, int d, int k, ConvPack* c,
+                 cudaStream_t s) {
+  SSV_TRY(pack_conv(ar, pm, prefix + ".conv", 2 * d, d, k, c, s));
+  SSV_TRY(pack_ln(ar, pm, prefix + ".ln1", d, &c->g1, &c->b1, s));
+  SSV_TRY(pack_ln(ar, pm, prefix + ".ln2", d, &c->g2, &c->b2, s));
+  return kOk;
+}
+
+int pack_conv_ln(Arena& ar, const ParamMap& pm, const std::string& conv, const std::string& ln, int n, int cin,
+                 ConvPack* c, cudaStream_t s) {
+  SSV_TRY(pack_conv(ar, pm, conv, n, cin, 1, c, s));
+  SSV_TRY(pack_ln(ar, pm, ln, n, &c->g1, &c->b1, s));
+  return kOk;
+}
+
+// Run one packed layer over B x [t0, t0+t_rows) rows of a channels-last activation.
+int run_conv(const ConvPack& c, int epi, int dil, int causal, const float* X, int x_ld, int T, int B, float* Y,
+             int y_ld, cudaStream_t s, const float* bias_b = nullptr, long bias_b_ld = 0) {
+  ConvArgs a{};
+  a.X = X;
+  a.x_sb = (long)T * x_ld;
+  a.x_st = x_ld;
+  a.t_in = T;
+  a.t0 = 0;
+  a.t_rows = T;
+  a.M = B * T;
+  a.W = c.W;
+  a.bias = c.bias;
+  a.bias_b = bias_b;
+  a.bias_b_ld = bias_b_ld;
+  a.g1 = c.g1; a.b1 = c.b1; a.g2 = c.g2; a.b2 = c.b2;
+  a.cin_p = c.cin_p;
+  a.ktaps = c.k;
+  a.dil = dil;
+  a.causal = causal;
+  a.n = c.n;
+  a.epi = epi;
+  a.Y = Y;
+  a.y_sb = (long)T * y_ld;
+  a.y_st = y_ld;
+  a.y_cols = y_ld < c.n_pad ? y_ld : c.n_pad;
+  SSV_CHECK(x_ld >= c.cin_p, "activation row stride %d smaller than padded Cin %d", x_ld, c.cin_p);
+  return launch_conv_f32(a, s);
+}
+
+cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+int device_sm_count() {
+  static int sm = 0;
+  if (sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sm;
+}
+
+struct Workspace {
+  float* buf[2] = {nullptr, nullptr};
+  size_t floats = 0;
+  int ensure(size_t need) {
+    if (need <= floats) return kOk;
+    for (int i = 0; i < 2; ++i) {
+      if (buf[i]) cudaFree(buf[i]);
+      buf[i] = nullptr;
+    }
+    floats = 0;
+    for (int i = 0; i < 2; ++i) {
+      if (cudaMalloc((void**)&buf[i], need * sizeof(float) + 256) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("workspace cudaMalloc of %zu bytes failed", need * sizeof(float));
+        return kNoMem;
+      }
+    }
+    floats = need;
+    return kOk;
+  }
+  ~Workspace() {
+    for (int i = 0; i < 2; ++i)
+      if (buf[i]) cudaFree(buf[i]);
+  }
+};
+
+}  // namespace
+}  // namespace ssv
+
+using namespace ssv;
+
+// ================================================================================================
+struct ssv_text2mel {
+  Arena arena;
+  int vocab, E, temb, F, H;
+  // text encoder (tiled kernels)
+  float* emb_wt = nullptr;    // [vocab][temb]
+  float* emb_b = nullptr;
+  ConvPack te_conv1, te_conv2;
+  ConvPack te_hc[12];
+  int te_dil[12];
+  // speaker projections
+  float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+  // decode stage table
+  DecStage stages[DEC_STAGES];
+  DecStage* stages_dev = nullptr;
+  float *fin_g, *fin_b;
+  Workspace ws;
+  int* err_flag = nullptr;
+};
+
+struct ssv_decoder {
+  ssv_text2mel* m;
+  Arena arena;
+  int maxB, maxN, maxT;
+  float *raw, *hist, *Kt, *Vt, *s1, *s2;
+  int* pma_state;
+  unsigned* bar;
+  int* abort_flag;
+  // per-batch state
+  bool begun = false;
+  int B = 0, N = 0, t_cap = 0, t = 0;
+  float *Y = nullptr, *A = nullptr;
+  long long* traj = nullptr;
+  // staging for ssv_synthesize_host
+  Arena host_arena;
+  size_t hs_key = 0;
+  int64_t* h_textid = nullptr;
+  float *h_spk = nullptr, *h_K = nullptr, *h_V = nullptr, *h_Y = nullptr, *h_A = nullptr, *h_lin = nullptr;
+  long long* h_traj = nullptr;
+};
+
+struct ssv_ssrn {
+  Arena arena;
+  int F, O, D;
+  ConvPack conv1, hc1, hc2, dc1, u1h1, u1h2, dc2, u2h1, u2h2, conv2, hc3, hc4, conv3, conv4, conv5, conv6;
+  Workspace ws;
+};
+
+extern "C" {
+
+int ssv_version(void) { return 100; }
+
+const char* ssv_last_error(void) { return g_err.c_str(); }
+
+int ssv_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  SSV_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SSV_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return kOk;
+}
+
+long ssv_launch_count(int reset) {
+  long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
+                         const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
+                         int dilation, int causal, float* y, int precision, void* stream) {
+  SSV_CHECK(x && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b && y, "highway_conv: null pointer");
+  SSV_CHECK(B > 0 && T > 0, "highway_conv: empty input");
+  SSV_CHECK(d == 256 || d == 512, "highway_conv: dimension %d unsupported (256 or 512)", d);
+  SSV_CHECK(k == 1 || k == 3, "highway_conv: kernel_size %d unsupported (1 or 3)", k);
+  SSV_CHECK(dilation >= 1, "highway_conv: dilation must be >= 1");
+  cudaStream_t s = as_stream(stream);
+  Arena ar;
+  ParamMap pm;
+  pm.m["conv.weight"] = {conv_w, (int64_t)2 * d * d * k};
+  pm.m["conv.bias"] = {conv_b, 2 * d};
+  pm.m["ln1.weight"] = {ln1_w, d};
+  pm.m["ln1.bias"] = {ln1_b, d};
+  pm.m["ln2.weight"] = {ln2_w, d};
+  pm.m["ln2.bias"] = {ln2_b, d};
+  ConvPack c;
+  SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
+  SSV_TRY(pack_ln(ar, pm, "ln1", d, &c.g1, &c.b1, s));
+  SSV_TRY(pack_ln(ar, pm, "ln2", d, &c.g2, &c.b2, s));
+  float *xin, *yout;
+  SSV_TRY(ar.alloc<float>((size_t)B * T * d, &xin));
+  SSV_TRY(ar.alloc<float>((size_t)B * T * d, &yout));
+  SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
+  SSV_CHECK(precision == SSV_PREC_FP32, "highway_conv: precision %d not implemented", precision);
+  SSV_TRY(run_conv(c, EPI_HIGHWAY, dilation, causal, xin, d, T, B, yout, d, s));
+  SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
+  SSV_CUDA(cudaStreamSynchronize(s));   // arena is freed on return
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int fill_stage(ssv_text2mel* m, const ParamMap& pm, int idx, const std::string& conv, int n, int cin, int k,
+                      int dil, int pro, const float* g1, const float* b1, const float* g2, const float* b2,
+                      int hist_in, int res_hist, int bias_b, cudaStream_t s) {
+  const float *w, *b;
+  SSV_TRY(pm.get(conv + ".weight", (int64_t)n * cin * k, &w));
+  SSV_TRY(pm.get(conv + ".bias", n, &b));
+  float *wd, *bd;
+  SSV_TRY(m->arena.alloc<float>((size_t)n * cin * k, &wd));
+  SSV_TRY(m->arena.alloc<float>(n, &bd));
+  SSV_TRY(launch_pack_rowmajor_w(w, n, cin, k, wd, s));
+  SSV_CUDA(cudaMemcpyAsync(bd, b, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  DecStage& st = m->stages[idx];
+  st.W = wd; st.bias = bd;
+  st.g1 = g1; st.b1 = b1; st.g2 = g2; st.b2 = b2;
+  st.n = n; st.k_seg = cin; st.ntaps = k; st.dil = dil; st.pro = pro;
+  st.n_prev = 0; st.hist_in = hist_in; st.res_hist = res_hist; st.bias_b = bias_b;
+  return kOk;
+}
+
+int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, const int64_t* numels,
+                        int n_params, int vocab_len, int spkemb_dim, int textemb_dim, int freq_bins,
+                        int hidden_dim, ssv_text2mel** out) {
+  SSV_CHECK(out, "text2mel_create: null out");
+  SSV_CHECK(hidden_dim == 256, "text2mel_create: hidden_dim %d unsupported (256)", hidden_dim);
+  SSV_CHECK(textemb_dim % 16 == 0 && textemb_dim <= 512, "text2mel_create: textemb_dim must be a multiple of 16");
+  SSV_CHECK(freq_bins % 16 == 0 && freq_bins <= 96, "text2mel_create: freq_bins must be a multiple of 16, <= 96");
+  SSV_CHECK(vocab_len > 0 && spkemb_dim > 0, "text2mel_create: bad dims");
+  ParamMap pm;
+  SSV_TRY(build_param_map(names, dev_ptrs, numels, n_params, &pm));
+  ssv_text2mel* m = new ssv_text2mel();
+  m->vocab = vocab_len; m->E = spkemb_dim; m->temb = textemb_dim; m->F = freq_bins; m->H = hidden_dim;
+  cudaStream_t s = nullptr;
+  const int H = hidden_dim, D2 = 2 * hidden_dim;
+  auto fail = [&](int code) { delete m; return code; };
+#define T2M_TRY(expr) do { int _s = (expr); if (_s != kOk) return fail(_s); } while (0)
+  // ---- text encoder
+  {
+    const float *w, *b;
+    T2M_TRY(pm.get("text_encoder.textemb_layer.W.weight", (int64_t)textemb_dim * vocab_len, &w));
+    T2M_TRY(pm.get("text_encoder.textemb_layer.W.bias", textemb_dim, &b));
+    T2M_TRY(m->arena.alloc<float>((size_t)vocab_len * textemb_dim, &m->emb_wt));
+    T2M_TRY(m->arena.alloc<float>(textemb_dim, &m->emb_b));
+    // (E, vocab) -> [vocab][E]: a k=1 "rowmajor" pack of w viewed as [n=E][cin=vocab] gives [E][vocab];
+    // we need the transpose, which pack_conv_w provides: dst[kk=ci][col] with n=E, cin=vocab.
+    T2M_TRY(launch_pack_conv_w(w, textemb_dim, vocab_len, 1, vocab_len, textemb_dim, m->emb_wt, s));
+    if (cudaMemcpyAsync(m->emb_b, b, sizeof(float) * textemb_dim, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return fail(kCuda);
+    T2M_TRY(m->arena.alloc<int>(1, &m->err_flag));
+    cudaMemsetAsync(m->err_flag, 0, sizeof(int), s);
+  }
+  T2M_TRY(pack_conv_ln(m->arena, pm, "text_encoder.conv1", "text_encoder.ln1", D2, textemb_dim, &m->te_conv1, s));
+  T2M_TRY(pack_conv_ln(m->arena, pm, "text_encoder.conv2", "text_encoder.ln2", D2, D2, &m->te_conv2, s));
+  {
+    const char* nm[12] = {"hci1.hc1", "hci1.hc2", "hci1.hc3", "hci1.hc4", "hci2.hc1", "hci2.hc2",
+                          "hci2.hc3", "hci2.hc4", "hc1", "hc2", "hc3", "hc4"};
+    const int dil[12] = {1, 3, 9, 27, 1, 3, 9, 27, 1, 1, 1, 1};
+    const int ks[12] = {3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 1, 1};
+    for (int i = 0; i < 12; ++i) {
+      T2M_TRY(pack_highway(m->arena, pm, std::string("text_encoder.") + nm[i], D2, ks[i], &m->te_hc[i], s));
+      m->te_dil[i] = dil[i];
+    }
+  }
+  // ---- speaker projections
+  T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc1.weight", H * spkemb_dim, &m->fc1_w, s));
+  T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc1.bias", H, &m->fc1_b, s));
+  T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc2.weight", H * spkemb_dim, &m->fc2_w, s));
+  T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc2.bias", H, &m->fc2_b, s));
+  // ---- decode stage table
+  {
+    struct Ln { float *g, *b; };
+    auto ln = [&](const std::string& name, int n, Ln* o) { return pack_ln(m->arena, pm, name, n, &o->g, &o->b, s); };
+    const std::string ae = "audio_encoder.", ad = "audio_decoder.";
+    Ln e1, e2, e3, d1, d2, d3, d4, d5;
+    T2M_TRY(ln(ae + "ln1", H, &e1)); T2M_TRY(ln(ae + "ln2", H, &e2)); T2M_TRY(ln(ae + "ln3", H, &e3));
+    T2M_TRY(ln(ad + "ln1", H, &d1)); T2M_TRY(ln(ad + "ln2", H, &d2)); T2M_TRY(ln(ad + "ln3", H, &d3));
+    T2M_TRY(ln(ad + "ln4", H, &d4)); T2M_TRY(ln(ad + "ln5", freq_bins, &d5));
+    m->fin_g = d5.g; m->fin_b = d5.b;
+    const char* enc_hc[10] = {"hci1.hc1", "hci1.hc2", "hci1.hc3", "hci1.hc4", "hci2.hc1",
+                              "hci2.hc2", "hci2.hc3", "hci2.hc4", "hc1", "hc2"};
+    const int enc_dil[10] = {1, 3, 9, 27, 1, 3, 9, 27, 3, 3};
+    const char* dec_hc[6] = {"hci.hc1", "hci.hc2", "hci.hc3", "hci.hc4", "hc1", "hc2"};
+    const int dec_dil[6] = {1, 3, 9, 27, 1, 1};
+    Ln eh1[10], eh2[10], dh1[6], dh2[6];
+    for (int i = 0; i < 10; ++i) {
+      T2M_TRY(ln(ae + enc_hc[i] + ".ln1", H, &eh1[i]));
+      T2M_TRY(ln(ae + enc_hc[i] + ".ln2", H, &eh2[i]));
+    }
+    for (int i = 0; i < 6; ++i) {
+      T2M_TRY(ln(ad + dec_hc[i] + ".ln1", H, &dh1[i]));
+      T2M_TRY(ln(ad + dec_hc[i] + ".ln2", H, &dh2[i]));
+    }
+    int si = 0;
+    T2M_TRY(fill_stage(m, pm, si++, ae + "conv1", H, freq_bins, 1, 1, PRO_X, nullptr, nullptr, nullptr, nullptr, -1, -1, 1, s));
+    T2M_TRY(fill_stage(m, pm, si++, ae + "conv2", H, H, 1, 1, PRO_LN_RELU, e1.g, e1.b, nullptr, nullptr, -1, -1, 0, s));
+    T2M_TRY(fill_stage(m, pm, si++, ae + "conv3", H, H, 1, 1, PRO_LN_RELU, e2.g, e2.b, nullptr, nullptr, -1, -1, 2, s));
+    for (int i = 0; i < 10; ++i) {
+      if (i == 0)
+        T2M_TRY(fill_stage(m, pm, si++, ae + enc_hc[i] + ".conv", D2, H, 3, enc_dil[i], PRO_LN, e3.g, e3.b, nullptr, nullptr, 0, -1, 0, s));
+      else
+        T2M_TRY(fill_stage(m, pm, si++, ae + enc_hc[i] + ".conv", D2, H, 3, enc_dil[i], PRO_HWY, eh1[i - 1].g, eh1[i - 1].b,
+                           eh2[i - 1].g, eh2[i - 1].b, i, i - 1, 0, s));
+    }
+    T2M_TRY(fill_stage(m, pm, si++, ad + "conv1", H, D2, 1, 1, PRO_ATT, eh1[9].g, eh1[9].b, eh2[9].g, eh2[9].b, -1, 9, 0, s));
+    for (int i = 0; i < 6; ++i) {
+      if (i == 0)
+        T2M_TRY(fill_stage(m, pm, si++, ad + dec_hc[i] + ".conv", D2, H, 3, dec_dil[i], PRO_LN, d1.g, d1.b, nullptr, nullptr, 10, -1, 0, s));
+      else
+        T2M_TRY(fill_stage(m, pm, si++, ad + dec_hc[i] + ".conv", D2, H, 3, dec_dil[i], PRO_HWY, dh1[i - 1].g, dh1[i - 1].b,
+                           dh2[i - 1].g, dh2[i - 1].b, 10 + i, 10 + i - 1, 0, s));
+    }
+    T2M_TRY(fill_stage(m, pm, si++, ad + "conv2", H, H, 1, 1, PRO_HWY, dh1[5].g, dh1[5].b, dh2[5].g, dh2[5].b, -1, 15, 0, s));
+    T2M_TRY(fill_stage(m, pm, si++, ad + "conv3", H, H, 1, 1, PRO_LN_RELU, d2.g, d2.b, nullptr, nullptr, -1, -1, 0, s));
+    T2M_TRY(fill_stage(m, pm, si++, ad + "conv4", H, H, 1, 1, PRO_LN_RELU, d3.g, d3.b, nullptr, nullptr, -1, -1, 0, s));
+    T2M_TRY(fill_stage(m, pm, si++, ad + "conv5", freq_bins, H, 1, 1, PRO_LN_RELU, d4.g, d4.b, nullptr, nullptr, -1, -1, 0, s));
+    if (si != DEC_STAGES) { set_error("internal: stage table has %d entries", si); return fail(kState); }
+    T2M_TRY(m->arena.alloc<DecStage>(DEC_STAGES, &m->stages_dev));
+    if (cudaMemcpyAsync(m->stages_dev, m->stages, sizeof(DecStage) * DEC_STAGES, cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return fail(kCuda);
+  }
+#undef T2M_TRY
+  if (cudaStreamSynchronize(s) != cudaSuccess) {
+    set_error("text2mel_create: %s", cudaGetErrorString(cudaGetLastError()));
+    delete m;
+    return kCuda;
+  }
+  *out = m;
+  return kOk;
+}
+
+int ssv_text2mel_destroy(ssv_text2mel* m) {
+  if (m) {
+    cudaDeviceSynchronize();
+    delete m;
+  }
+  return kOk;
+}
+
+// Text encoder on channels-last buffers; result (B, N, 2H) left in *out_cl.
+static int text_encoder_cl(ssv_text2mel* m, const int64_t* textid, int B, int N, float** out_cl, cudaStream_t s) {
+  const int D2 = 2 * m->H;
+  SSV_TRY(m->ws.ensure((size_t)B * N * D2));
+  float* P = m->ws.buf[0];
+  float* Q = m->ws.buf[1];
+  const int e_ld = round_up(m->temb, 16);
+  SSV_TRY(launch_embed(textid, B, N, m->emb_wt, m->emb_b, m->vocab, m->temb, P, e_ld, m->err_flag, s));
+  SSV_TRY(run_conv(m->te_conv1, EPI_LN_RELU, 1, 0, P, e_ld, N, B, Q, D2, s));
+  SSV_TRY(run_conv(m->te_conv2, EPI_LN, 1, 0, Q, D2, N, B, P, D2, s));
+  float* cur = P;
+  float* nxt = Q;
+  for (int i = 0; i < 12; ++i) {
+    SSV_TRY(run_conv(m->te_hc[i], EPI_HIGHWAY, m->te_dil[i], 0, cur, D2, N, B, nxt, D2, s));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  *out_cl = cur;
+  return kOk;
+}
+
+int ssv_text_encoder_fwd(ssv_text2mel* m, const int64_t* textid, int B, int N, float* K, float* V, int precision,
+                         void* stream) {
+  SSV_CHECK(m && textid && K && V, "text_encoder: null pointer");
+  SSV_CHECK(B > 0 && N > 0, "text_encoder: empty input");
+  SSV_CHECK(precision == SSV_PREC_FP32, "text_encoder: only SSV_PREC_FP32 is implemented");
+  cudaStream_t s = as_stream(stream);
+  float* x;
+  SSV_TRY(text_encoder_cl(m, textid, B, N, &x, s));
+  SSV_TRY(launch_transpose_out2(x, 2 * m->H, 0, B, m->H, N, K, s));
+  SSV_TRY(launch_transpose_out2(x, 2 * m->H, m->H, B, m->H, N, V, s));
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_frames, ssv_decoder** out) {
+  SSV_CHECK(m && out, "decoder_create: null pointer");
+  SSV_CHECK(max_batch >= 1 && max_text >= 1 && max_frames >= 1, "decoder_create: bad capacity");
+  ssv_decoder* d = new ssv_decoder();
+  d->m = m;
+  d->maxB = max_batch; d->maxN = max_text; d->maxT = max_frames;
+  const int H = m->H;
+  int st = kOk;
+  if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_STAGES * max_batch * DEC_RAW_LD, &d->raw);
+  if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_HIST * max_batch * max_frames * H, &d->hist);
+  if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * max_text * H, &d->Kt);
+  if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * max_text * H, &d->Vt);
+  if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * H, &d->s1);
+  if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * H, &d->s2);
+  if (st == kOk) st = d->arena.alloc<int>(max_batch, &d->pma_state);
+  if (st == kOk) st = d->arena.alloc<unsigned>(1, &d->bar);
+  if (st == kOk) st = d->arena.alloc<int>(1, &d->abort_flag);
+  if (st != kOk) { delete d; return st; }
+  cudaMemset(d->abort_flag, 0, sizeof(int));
+  *out = d;
+  return kOk;
+}
+
+int ssv_decoder_destroy(ssv_decoder* d) {
+  if (d) {
+    cudaDeviceSynchronize();
+    delete d;
+  }
+  return kOk;
+}
+
+int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const float* spkemb, int B, int N, float* Y,
+                      float* A, int64_t* pma_traj, int t_cap, void* stream) {
+  SSV_CHECK(d && K && V && spkemb && Y && A && pma_traj, "decoder_begin: null pointer");
+  SSV_CHECK(B >= 1 && B <= d->maxB, "decoder_begin: batch %d outside [1, %d]", B, d->maxB);
+  SSV_CHECK(N >= 1 && N <= d->maxN, "decoder_begin: text length %d outside [1, %d]", N, d->maxN);
+  SSV_CHECK(t_cap >= 1 && t_cap <= d->maxT, "decoder_begin: frame capacity %d outside [1, %d]", t_cap, d->maxT);
+  cudaStream_t s = as_stream(stream);
+  ssv_text2mel* m = d->m;
+  const int H = m->H;
+  SSV_TRY(launch_transpose_in(K, (long)H * N, N, 1, B, H, N, d->Kt, H, s));
+  SSV_TRY(launch_transpose_in(V, (long)H * N, N, 1, B, H, N, d->Vt, H, s));
+  SSV_TRY(launch_linear_small(spkemb, m->E, m->fc1_w, m->fc1_b, B, m->E, H, d->s1, H, s));
+  SSV_TRY(launch_linear_small(spkemb, m->E, m->fc2_w, m->fc2_b, B, m->E, H, d->s2, H, s));
+  SSV_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * (size_t)B * N * t_cap, s));
+  SSV_CUDA(cudaMemsetAsync(d->pma_state, 0, sizeof(int) * B, s));
+  d->B = B; d->N = N; d->t_cap = t_cap; d->t = 0;
+  d->Y = Y; d->A = A; d->traj = reinterpret_cast<long long*>(pma_traj);
+  d->begun = true;
+  return kOk;
+}
+
+static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long x_sb, long x_sf,
+                          const int64_t* pma_in, cudaStream_t s) {
+  SSV_CHECK(d && d->begun, "decoder: begin() has not been called");
+  if (d->t + n_steps > d->t_cap) {
+    set_error("decoder: %d + %d frames exceed capacity %d", d->t, n_steps, d->t_cap);
+    return kState;
+  }
+  ssv_text2mel* m = d->m;
+  DecParams p{};
+  p.stages = m->stages_dev;
+  p.fin_g = m->fin_g; p.fin_b = m->fin_b;
+  p.raw = d->raw; p.hist = d->hist;
+  p.Kt = d->Kt; p.Vt = d->Vt; p.s1 = d->s1; p.s2 = d->s2;
+  p.Y = d->Y; p.A = d->A; p.pma_traj = d->traj;
+  p.pma_in = reinterpret_cast<const long long*>(pma_in);
+  p.pma_state = d->pma_state;
+  p.x_ext = x_ext; p.x_sb = x_sb; p.x_sf = x_sf;
+  p.B = d->B; p.N = d->N; p.t_cap = d->t_cap; p.F = m->F; p.H = m->H;
+  p.t_start = d->t; p.n_steps = n_steps;
+  p.RG = 1;
+  p.bar_counter = d->bar;
+  p.abort_flag = d->abort_flag;
+  const int sms = device_sm_count();
+  SSV_CHECK(sms > 0, "decoder: no CUDA device");
+  SSV_TRY(launch_decode(p, sms, s));
+  d->t += n_steps;
+  return kOk;
+}
+
+int ssv_decoder_step(ssv_decoder* d, const float* x, long x_stride_b, long x_stride_f, const int64_t* pma_in,
+                     void* stream) {
+  return decoder_launch(d, 1, x, x_stride_b, x_stride_f, pma_in, as_stream(stream));
+}
+
+int ssv_decoder_run(ssv_decoder* d, int n_steps, void* stream) {
+  SSV_CHECK(n_steps >= 1, "decoder_run: n_steps must be >= 1");
+  return decoder_launch(d, n_steps, nullptr, 0, 0, nullptr, as_stream(stream));
+}
+
+int ssv_decoder_frames(const ssv_decoder* d) { return d ? d->t : 0; }
+
+int ssv_decoder_check(ssv_decoder* d, void* stream) {
+  SSV_CHECK(d, "decoder_check: null decoder");
+  SSV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  int flag = 0;
+  SSV_CUDA(cudaMemcpy(&flag, d->abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag != 0) {
+    set_error("decode kernel aborted (grid barrier timeout, code %d)", flag);
+    cudaMemset(d->abort_flag, 0, sizeof(int));
+    return kState;
+  }
+  int eflag = 0;
+  SSV_CUDA(cudaMemcpy(&eflag, d->m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (eflag != 0) {
+    set_error("text id outside [0, vocab_len)");
+    cudaMemset(d->m->err_flag, 0, sizeof(int));
+    return kInval;
+  }
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+int ssv_ssrn_create(const char* const* names, const float* const* dev_ptrs, const int64_t* numels, int n_params,
+                    int freq_bins, int output_bins, int ssrn_dim, ssv_ssrn** out) {
+  SSV_CHECK(out, "ssrn_create: null out");
+  SSV_CHECK(ssrn_dim == 256, "ssrn_create: ssrn_dim %d unsupported (256)", ssrn_dim);
+  SSV_CHECK(freq_bins % 16 == 0 && freq_bins <= 128, "ssrn_create: freq_bins must be a multiple of 16, <= 128");
+  SSV_CHECK(output_bins > 512 && output_bins <= 576, "ssrn_create: output_bins %d unsupported (513..576)", output_bins);
+  ParamMap pm;
+  SSV_TRY(build_param_map(names, dev_ptrs, numels, n_params, &pm));
+  ssv_ssrn* m = new ssv_ssrn();
+  m->F = freq_bins; m->O = output_bins; m->D = ssrn_dim;
+  cudaStream_t s = nullptr;
+  const int D = ssrn_dim, O = output_bins;
+  int st = kOk;
+  auto deconv = [&](const std::string& name, ConvPack* c) -> int {
+    const float *w, *b;
+    SSV_TRY(pm.get(name + ".weight", (int64_t)D * D * 2, &w));
+    SSV_TRY(pm.get(name + ".bias", D, &b));
+    c->cin = D; c->cin_p = D; c->k = 1; c->n = 2 * D; c->n_pad = 2 * D;
+    SSV_TRY(m->arena.alloc<float>((size_t)D * 2 * D, &c->W));
+    SSV_TRY(m->arena.alloc<float>(2 * D, &c->bias));
+    return launch_pack_deconv_w(w, b, D, D, c->W, c->bias, s);
+  };
+#define S_TRY(expr) do { if (st == kOk) st = (expr); } while (0)
+  S_TRY(pack_conv_ln(m->arena, pm, "conv1", "ln1", D, freq_bins, &m->conv1, s));
+  S_TRY(pack_highway(m->arena, pm, "hc1", D, 3, &m->hc1, s));
+  S_TRY(pack_highway(m->arena, pm, "hc2", D, 3, &m->hc2, s));
+  S_TRY(deconv("ups1.deconv", &m->dc1));
+  S_TRY(pack_highway(m->arena, pm, "ups1.hc1", D, 3, &m->u1h1, s));
+  S_TRY(pack_highway(m->arena, pm, "ups1.hc2", D, 3, &m->u1h2, s));
+  S_TRY(deconv("ups2.deconv", &m->dc2));
+  S_TRY(pack_highway(m->arena, pm, "ups2.hc1", D, 3, &m->u2h1, s));
+  S_TRY(pack_highway(m->arena, pm, "ups2.hc2", D, 3, &m->u2h2, s));
+  S_TRY(pack_conv_ln(m->arena, pm, "conv2", "ln2", 2 * D, D, &m->conv2, s));
+  S_TRY(pack_highway(m->arena, pm, "hc3", 2 * D, 3, &m->hc3, s));
+  S_TRY(pack_highway(m->arena, pm, "hc4", 2 * D, 3, &m->hc4, s));
+  S_TRY(pack_conv_ln(m->arena, pm, "conv3", "ln3", O, 2 * D, &m->conv3, s));
+  S_TRY(pack_conv_ln(m->arena, pm, "conv4", "ln4", O, O, &m->conv4, s));
+  S_TRY(pack_conv_ln(m->arena, pm, "conv5", "ln5", O, O, &m->conv5, s));
+  S_TRY(pack_conv_ln(m->arena, pm, "conv6", "ln6", O, O, &m->conv6, s));
+#undef S_TRY
+  if (st == kOk && cudaStreamSynchronize(s) != cudaSuccess) {
+    set_error("ssrn_create: %s", cudaGetErrorString(cudaGetLastError()));
+    st = kCuda;
+  }
+  if (st != kOk) { delete m; return st; }
+  *out = m;
+  return kOk;
+}
+
+int ssv_ssrn_destroy(ssv_ssrn* m) {
+  if (m) {
+    cudaDeviceSynchronize();
+    delete m;
+  }
+  return kOk;
+}
+
+static int ssrn_fwd_f32(ssv_ssrn* m, const float* mel, long sb, long sf, long st_, int B, int T, float* out,
+                        cudaStream_t s) {
+  const int D = m->D, O = m->O;
+  const int o_ld = round_up(O, 64);
+  const int f_ld = round_up(m->F, 64);
+  SSV_TRY(m->ws.ensure((size_t)B * 4 * T * o_ld));
+  float* P = m->ws.buf[0];
+  float* Q = m->ws.buf[1];
+  SSV_TRY(launch_transpose_in(mel, sb, sf, st_, B, m->F, T, P, f_ld, s));
+  SSV_TRY(run_conv(m->conv1, EPI_LN, 1, 0, P, f_ld, T, B, Q, D, s));
+  SSV_TRY(run_conv(m->hc1, EPI_HIGHWAY, 1, 0, Q, D, T, B, P, D, s));
+  SSV_TRY(run_conv(m->hc2, EPI_HIGHWAY, 3, 0, P, D, T, B, Q, D, s));
+  // ConvTranspose1d(k=2, s=2) == 1x1 GEMM to 2*D columns; (B, T, 2D) is (B, 2T, D) in memory.
+  SSV_TRY(run_conv(m->dc1, EPI_NONE, 1, 0, Q, D, T, B, P, 2 * D, s));
+  SSV_TRY(run_conv(m->u1h1, EPI_HIGHWAY, 1, 0, P, D, 2 * T, B, Q, D, s));
+  SSV_TRY(run_conv(m->u1h2, EPI_HIGHWAY, 3, 0, Q, D, 2 * T, B, P, D, s));
+  SSV_TRY(run_conv(m->dc2, EPI_NONE, 1, 0, P, D, 2 * T, B, Q, 2 * D, s));
+  SSV_TRY(run_conv(m->u2h1, EPI_HIGHWAY, 1, 0, Q, D, 4 * T, B, P, D, s));
+  SSV_TRY(run_conv(m->u2h2, EPI_HIGHWAY, 3, 0, P, D, 4 * T, B, Q, D, s));
+  SSV_TRY(run_conv(m->conv2, EPI_LN, 1, 0, Q, D, 4 * T, B, P, 2 * D, s));
+  SSV_TRY(run_conv(m->hc3, EPI_HIGHWAY, 1, 0, P, 2 * D, 4 * T, B, Q, 2 * D, s));
+  SSV_TRY(run_conv(m->hc4, EPI_HIGHWAY, 1, 0, Q, 2 * D, 4 * T, B, P, 2 * D, s));
+  SSV_TRY(run_conv(m->conv3, EPI_LN, 1, 0, P, 2 * D, 4 * T, B, Q, o_ld, s));
+  SSV_TRY(run_conv(m->conv4, EPI_LN_RELU, 1, 0, Q, o_ld, 4 * T, B, P, o_ld, s));
+  SSV_TRY(run_conv(m->conv5, EPI_LN_RELU, 1, 0, P, o_ld, 4 * T, B, Q, o_ld, s));
+  SSV_TRY(run_conv(m->conv6, EPI_LN_SIGMOID, 1, 0, Q, o_ld, 4 * T, B, P, o_ld, s));
+  SSV_TRY(launch_transpose_out(P, o_ld, B, O, 4 * T, out, s));
+  return kOk;
+}
+
+int ssv_ssrn_fwd(ssv_ssrn* m, const float* mel, long stride_b, long stride_f, long stride_t, int B, int T,
+                 float* out, int precision, void* stream) {
+  SSV_CHECK(m && mel && out, "ssrn_fwd: null pointer");
+  SSV_CHECK(B > 0 && T > 0, "ssrn_fwd: empty input");
+  cudaStream_t s = as_stream(stream);
+  if (precision == SSV_PREC_FP32) return ssrn_fwd_f32(m, mel, stride_b, stride_f, stride_t, B, T, out, s);
+  set_error("ssrn_fwd: unknown precision %d", precision);
+  return kInval;
+}
+
+// ------------------------------------------------------------------------------------------------
+int ssv_synthesize_host(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const int64_t* textid_host,
+                        const float* spkemb_host, int B, int N, int n_frames, float* lin_host, float* mel_host,
+                        float* A_host, int64_t* pma_traj_host, int t2m_precision, int ssrn_precision,
+                        void* stream) {
+  SSV_CHECK(m && d && sr && textid_host && spkemb_host && lin_host, "synthesize_host: null pointer");
+  SSV_CHECK(d->m == m, "synthesize_host: decoder belongs to another model");
+  SSV_CHECK(B >= 1 && B <= d->maxB && N >= 1 && N <= d->maxN && n_frames >= 1 && n_frames <= d->maxT,
+            "synthesize_host: shape (B=%d, N=%d, T=%d) exceeds decoder capacity (%d, %d, %d)", B, N, n_frames,
+            d->maxB, d->maxN, d->maxT);
+  cudaStream_t s = as_stream(stream);
+  const int H = m->H, F = m->F, O = sr->O, T = n_frames;
+  const size_t key = ((size_t)B << 40) ^ ((size_t)N << 20) ^ (size_t)T;
+  if (d->hs_key != key) {
+    SSV_CUDA(cudaStreamSynchronize(s));
+    d->host_arena.~Arena();
+    new (&d->host_arena) Arena();
+    SSV_TRY(d->host_arena.alloc<int64_t>((size_t)B * N, &d->h_textid));
+    SSV_TRY(d->host_arena.alloc<float>((size_t)B * m->E, &d->h_spk));
+    SSV_TRY(d->host_arena.alloc<float>((size_t)B * H * N, &d->h_K));
+    SSV_TRY(d->host_arena.alloc<float>((size_t)B * H * N, &d->h_V));
+    SSV_TRY(d->host_arena.alloc<float>((size_t)B * F * T, &d->h_Y));
+    SSV_TRY(d->host_arena.alloc<float>((size_t)B * N * T, &d->h_A));
+    SSV_TRY(d->host_arena.alloc<long long>((size_t)T * B, &d->h_traj));
+    SSV_TRY(d->host_arena.alloc<float>((size_t)B * O * 4 * T, &d->h_lin));
+    d->hs_key = key;
+  }
+  SSV_CUDA(cudaMemcpyAsync(d->h_textid, textid_host, sizeof(int64_t) * B * N, cudaMemcpyHostToDevice, s));
+  SSV_CUDA(cudaMemcpyAsync(d->h_spk, spkemb_host, sizeof(float) * B * m->E, cudaMemcpyHostToDevice, s));
+  SSV_TRY(ssv_text_encoder_fwd(m, d->h_textid, B, N, d->h_K, d->h_V, t2m_precision, s));
+  SSV_TRY(ssv_decoder_begin(d, d->h_K, d->h_V, d->h_spk, B, N, d->h_Y, d->h_A,
+                            reinterpret_cast<int64_t*>(d->h_traj), T, s));
+  SSV_TRY(ssv_decoder_run(d, T, s));
+  SSV_TRY(ssv_ssrn_fwd(sr, d->h_Y, (long)F * T, T, 1, B, T, d->h_lin, ssrn_precision, s));
+  SSV_CUDA(cudaMemcpyAsync(lin_host, d->h_lin, sizeof(float) * (size_t)B * O * 4 * T, cudaMemcpyDeviceToHost, s));
+  if (mel_host) SSV_CUDA(cudaMemcpyAsync(mel_host, d->h_Y, sizeof(float) * (size_t)B * F * T, cudaMemcpyDeviceToHost, s));
+  if (A_host) SSV_CUDA(cudaMemcpyAsync(A_host, d->h_A, sizeof(float) * (size_t)B * N * T, cudaMemcpyDeviceToHost, s));
+  if (pma_traj_host)
+    SSV_CUDA(cudaMemcpyAsync(pma_traj_host, d->h_traj, sizeof(long long) * (size_t)T * B, cudaMemcpyDeviceToHost, s));
+  return ssv_decoder_check(d, s);
+}
+
+}  // extern "C"

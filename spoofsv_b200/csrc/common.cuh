@@ -1,0 +1,97 @@
+// Shared declarations for the spoofsv_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace ssv {
+
+// ---- error plumbing (C-ABI returns an int status; message via ssv_last_error) ----
+enum Status { kOk = 0, kInval = 1, kCuda = 2, kNoMem = 3, kState = 4 };
+void set_error(const char* fmt, ...);
+extern thread_local long g_launches;     // kernels launched by this thread (bench "gpu_launches")
+
+#define SSV_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ssv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                           \
+      return ssv::kCuda;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define SSV_CHECK(cond, ...)                                                        \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      ssv::set_error(__VA_ARGS__);                                                  \
+      return ssv::kInval;                                                           \
+    }                                                                               \
+  } while (0)
+
+#define SSV_TRY(expr)                                                               \
+  do {                                                                              \
+    int _s = (expr);                                                                \
+    if (_s != ssv::kOk) return _s;                                                   \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- epilogue kinds of the fused conv kernels ----
+enum Epilogue {
+  EPI_NONE = 0,        // conv + bias                     (ConvTranspose1d as 1x1 GEMM)
+  EPI_LN = 1,          // LayerNorm over channels
+  EPI_LN_RELU = 2,     // LayerNorm, ReLU (the ReLU the reference applies to the next conv's input)
+  EPI_LN_SIGMOID = 3,  // LayerNorm, sigmoid (final layer)
+  EPI_HIGHWAY = 4      // split, LN1/LN2, sigma(H1)*H2 + (1-sigma(H1))*x
+};
+
+// One fused "conv1d (k taps, dilation, causal|same) -> epilogue" over channels-last rows.
+// Rows are (b, t) pairs: row r -> b = r / t_rows, t = t0 + r % t_rows.
+struct ConvArgs {
+  const float* X;      // input activations, channels-last
+  long x_sb, x_st;     // element strides between batch items / time steps
+  int t_in;            // taps outside [0, t_in) read as zero
+  int t0, t_rows;      // computed time range per batch item
+  int M;               // total rows = B * t_rows
+  const float* W;      // packed [k*cin_p][n_pad], tap-major
+  const float* bias;   // [n_pad]
+  const float* bias_b; // optional per-batch additive term [B][bias_b_ld] (speaker projection)
+  long bias_b_ld;
+  const float* g1; const float* b1;   // LN affine (LN1 of highway / the only LN)
+  const float* g2; const float* b2;   // LN2 of highway
+  int cin_p;           // input channels rounded up to 16
+  int ktaps, dil, causal;
+  int n;               // real output columns (<= n_pad)
+  int epi;
+  float* Y;            // output, channels-last
+  long y_sb, y_st;
+  int y_cols;          // columns written per row (real ones computed, rest zero)
+};
+
+int launch_conv_f32(const ConvArgs& a, cudaStream_t s);
+
+// bf16 tensor-core (tcgen05) highway / LN conv.  Same contract; activations bf16.
+struct ConvTcArgs;   // defined in conv_tc.cuh
+
+// ---- small utility kernels (misc.cu) ----
+int launch_transpose_in(const float* src, long sb, long sc, long st, int B, int C, int T,
+                        float* dst, int ld, cudaStream_t s);          // (B,C,T) strided -> (B,T,ld) zero padded
+int launch_transpose_out(const float* src, int ld, int B, int C, int T,
+                         float* dst, cudaStream_t s);                  // (B,T,ld) -> (B,C,T) contiguous
+int launch_transpose_out2(const float* src, int ld, int c_off, int B, int C, int T,
+                          float* dst, cudaStream_t s);                 // same, reading channels [c_off, c_off+C)
+int launch_embed(const int64_t* ids, int B, int N, const float* Wt /*[vocab][E]*/, const float* bias,
+                 int vocab, int E, float* dst, int ld, int* err_flag, cudaStream_t s);
+int launch_pack_conv_w(const float* w /*[n][cin][k]*/, int n, int cin, int k, int cin_p, int n_pad,
+                       float* dst /*[k*cin_p][n_pad]*/, cudaStream_t s);
+int launch_pack_deconv_w(const float* w /*[cin][cout][2]*/, const float* b, int cin, int cout,
+                         float* dst /*[cin][2*cout]*/, float* bias_dst, cudaStream_t s);
+int launch_pack_rowmajor_w(const float* w /*[n][cin][k]*/, int n, int cin, int k,
+                           float* dst /*[n][k*cin]*/, cudaStream_t s);
+int launch_pad_vec(const float* src, int n, int n_pad, float* dst, cudaStream_t s);
+int launch_linear_small(const float* x, long x_ld, const float* w, const float* b, int B, int in_f, int out_f,
+                        float* y, int y_ld, cudaStream_t s);          // y[b] = W x[b] + b (speaker projections)
+
+}  // namespace ssv

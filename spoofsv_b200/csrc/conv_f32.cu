@@ -1,0 +1,315 @@
+// FP32 (CUDA-core FFMA) fused conv1d + LayerNorm / highway-gate kernel.
+//
+// This is the FP32-exact arm of the hot path (north_star: 1e-4 max-abs vs the
+// reference): every highwayConv (models/TTSModel.py:63-84), every 1x1 conv +
+// LayerNorm (+ReLU / +sigmoid) and the ConvTranspose1d (as a 1x1 GEMM whose 2*C
+// output columns are the two interleaved output frames) of TextEnc and SSRN run
+// through this one kernel.  Implicit GEMM: M = (b,t) rows, K = taps*Cin, N = Cout;
+// a CTA owns BM complete rows so the channel LayerNorm and the gate are done in
+// registers before anything is written.
+//
+// Tiling: 256 threads = 64 column-threads x 4 row-groups; thread tile RPT x CPT
+// with columns tx + 64*j (so H1[c] and H2[c] of a highway layer live in the same
+// thread).  K is streamed in chunks of 16 through a cp.async ring (3 stages):
+// the weight chunk is one contiguous KC*N block, the activation chunk is a row
+// gather whose tap shift / zero padding is resolved per row (zero-fill cp.async).
+#include "common.cuh"
+
+namespace ssv {
+
+namespace {
+
+constexpr int KC = 16;
+constexpr int NT = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Sum v[0..CNT) over the 64 column-threads that share a row group (two warps).
+template <int CNT>
+__device__ __forceinline__ void rowgroup_sum(float (&v)[CNT], float* red /*[8][CNT]*/, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, ty = tid >> 6;
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) red[warp * CNT + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) v[i] = red[(2 * ty) * CNT + i] + red[(2 * ty + 1) * CNT + i];
+  __syncthreads();
+}
+
+template <int BM, int CPT, int STAGES>
+__global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
+  constexpr int NP = 64 * CPT;
+  constexpr int RPT = BM / 4;
+  extern __shared__ __align__(16) float smem[];
+  float* Ws = smem;                        // [STAGES][KC][NP]
+  float* As = smem + STAGES * KC * NP;     // [STAGES][BM][KC]
+  __shared__ float red[8 * 2 * RPT];
+  __shared__ int row_b[BM], row_t[BM];
+
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  const int row0 = blockIdx.x * BM;
+  if (tid < BM) {
+    int r = row0 + tid;
+    if (r < a.M) {
+      row_b[tid] = r / a.t_rows;
+      row_t[tid] = a.t0 + r % a.t_rows;
+    } else {
+      row_b[tid] = -1;
+      row_t[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  const int chunks_per_tap = a.cin_p / KC;
+  const int nchunks = a.ktaps * chunks_per_tap;
+  const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
+
+  auto load_stage = [&](int q, int st) {
+    const float4* src = reinterpret_cast<const float4*>(a.W + (size_t)q * KC * NP);
+    float4* dst = reinterpret_cast<float4*>(Ws + st * KC * NP);
+#pragma unroll
+    for (int i = tid; i < KC * NP / 4; i += NT) cp_async16(dst + i, src + i, true);
+    if (tid < BM * 4) {
+      const int j = q / chunks_per_tap;
+      const int c0 = (q - j * chunks_per_tap) * KC;
+      const int off = (tap_base + j) * a.dil;
+      const int r = tid >> 2, seg = tid & 3;
+      const int b = row_b[r];
+      const int t = row_t[r] + off;
+      const bool ok = (b >= 0) && (t >= 0) && (t < a.t_in);
+      const float* p = ok ? a.X + (long)b * a.x_sb + (long)t * a.x_st + c0 + seg * 4 : a.X;
+      cp_async16(As + (st * BM + r) * KC + seg * 4, p, ok);
+    }
+  };
+
+  float acc[RPT][CPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i)
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  for (int q = 0; q < nchunks; ++q) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int qn = q + STAGES - 1;
+      if (qn < nchunks) load_stage(qn, qn % STAGES);
+      cp_async_commit();
+    }
+    const int st = q % STAGES;
+    const float* Wst = Ws + st * KC * NP + tx;
+    const float* Ast = As + (st * BM + ty * RPT) * KC;
+#pragma unroll
+    for (int k4 = 0; k4 < KC / 4; ++k4) {
+      float4 av[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) av[i] = *reinterpret_cast<const float4*>(Ast + i * KC + k4 * 4);
+#pragma unroll
+      for (int kq = 0; kq < 4; ++kq) {
+        float w[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) w[j] = Wst[(k4 * 4 + kq) * NP + 64 * j];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const float x = kq == 0 ? av[i].x : kq == 1 ? av[i].y : kq == 2 ? av[i].z : av[i].w;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(x, w[j], acc[i][j]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---------------- epilogue ----------------
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    const float bv = a.bias[tx + 64 * j];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i][j] += bv;
+  }
+  if (a.bias_b != nullptr) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int b = row_b[ty * RPT + i];
+      if (b >= 0) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[i][j] += a.bias_b[(long)b * a.bias_b_ld + tx + 64 * j];
+      }
+    }
+  }
+
+  if (a.epi == EPI_NONE) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int b = row_b[ty * RPT + i];
+      if (b < 0) continue;
+      float* y = a.Y + (long)b * a.y_sb + (long)row_t[ty * RPT + i] * a.y_st;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = tx + 64 * j;
+        if (c < a.y_cols) y[c] = c < a.n ? acc[i][j] : 0.f;
+      }
+    }
+    return;
+  }
+
+  if (a.epi == EPI_HIGHWAY) {
+    if constexpr (CPT % 2 == 0) {
+      constexpr int H = CPT / 2;
+      const float inv_d = 1.0f / (float)(a.n / 2);
+      float s[2 * RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) { s1 += acc[i][j]; s2 += acc[i][j + H]; }
+        s[2 * i] = s1; s[2 * i + 1] = s2;
+      }
+      rowgroup_sum<2 * RPT>(s, red, tid);
+      float mean[2 * RPT];
+#pragma unroll
+      for (int i = 0; i < 2 * RPT; ++i) mean[i] = s[i] * inv_d;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          const float d1 = acc[i][j] - mean[2 * i], d2 = acc[i][j + H] - mean[2 * i + 1];
+          q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2);
+        }
+        s[2 * i] = q1; s[2 * i + 1] = q2;
+      }
+      rowgroup_sum<2 * RPT>(s, red, tid);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int b = row_b[ty * RPT + i];
+        if (b < 0) continue;
+        const int t = row_t[ty * RPT + i];
+        const float r1 = 1.0f / sqrtf(s[2 * i] * inv_d + 1e-5f);
+        const float r2 = 1.0f / sqrtf(s[2 * i + 1] * inv_d + 1e-5f);
+        const float* xr = a.X + (long)b * a.x_sb + (long)t * a.x_st;
+        float* y = a.Y + (long)b * a.y_sb + (long)t * a.y_st;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          const int c = tx + 64 * j;
+          const float h1 = (acc[i][j] - mean[2 * i]) * r1 * a.g1[c] + a.b1[c];
+          const float h2 = (acc[i][j + H] - mean[2 * i + 1]) * r2 * a.g2[c] + a.b2[c];
+          const float g = sigmoidf_(h1);
+          y[c] = g * h2 + (1.0f - g) * xr[c];
+        }
+      }
+    }
+    return;
+  }
+
+  // EPI_LN / EPI_LN_RELU / EPI_LN_SIGMOID over the first a.n columns
+  {
+    const float inv_n = 1.0f / (float)a.n;
+    float s[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) v += (tx + 64 * j < a.n) ? acc[i][j] : 0.f;
+      s[i] = v;
+    }
+    rowgroup_sum<RPT>(s, red, tid);
+    float mean[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) mean[i] = s[i] * inv_n;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const float d = acc[i][j] - mean[i];
+        v += (tx + 64 * j < a.n) ? d * d : 0.f;
+      }
+      s[i] = v;
+    }
+    rowgroup_sum<RPT>(s, red, tid);
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int b = row_b[ty * RPT + i];
+      if (b < 0) continue;
+      const float rstd = 1.0f / sqrtf(s[i] * inv_n + 1e-5f);
+      float* y = a.Y + (long)b * a.y_sb + (long)row_t[ty * RPT + i] * a.y_st;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = tx + 64 * j;
+        if (c >= a.y_cols) continue;
+        float o = 0.f;
+        if (c < a.n) {
+          o = (acc[i][j] - mean[i]) * rstd * a.g1[c] + a.b1[c];
+          if (a.epi == EPI_LN_RELU) o = fmaxf(o, 0.f);
+          else if (a.epi == EPI_LN_SIGMOID) o = sigmoidf_(o);
+        }
+        y[c] = o;
+      }
+    }
+  }
+}
+
+template <int BM, int CPT, int STAGES>
+int launch_inst(const ConvArgs& a, cudaStream_t s) {
+  constexpr int NP = 64 * CPT;
+  constexpr size_t smem = (size_t)STAGES * (KC * NP + BM * KC) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    SSV_CUDA(cudaFuncSetAttribute(conv_f32_kernel<BM, CPT, STAGES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int grid = (a.M + BM - 1) / BM;
+  conv_f32_kernel<BM, CPT, STAGES><<<grid, NT, smem, s>>>(a);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace
+
+int launch_conv_f32(const ConvArgs& a, cudaStream_t s) {
+  SSV_CHECK(a.M > 0 && a.cin_p % KC == 0 && a.ktaps >= 1 && a.ktaps <= 3, "conv_f32: bad shape");
+  const int n_pad = round_up(a.n, 64);
+  if (a.epi == EPI_HIGHWAY) SSV_CHECK(a.n == n_pad && (a.n / 64) % 2 == 0, "conv_f32: highway needs n %% 128 == 0");
+  switch (n_pad / 64) {
+    case 2:  return launch_inst<32, 2, 3>(a, s);
+    case 4:  return launch_inst<32, 4, 3>(a, s);
+    case 8:  return launch_inst<32, 8, 3>(a, s);
+    case 9:  return launch_inst<32, 9, 3>(a, s);
+    case 16: return launch_inst<16, 16, 3>(a, s);
+    default: break;
+  }
+  set_error("conv_f32: unsupported output width %d (padded %d)", a.n, n_pad);
+  return kInval;
+}
+
+}  // namespace ssv

@@ -1,0 +1,186 @@
+// Layout / packing helpers: module-boundary transposes (reference tensors are
+// (B, C, T) channels-first, models/TTSModel.py; kernels work on channels-last rows),
+// the text-embedding gather (models/TTSModel.py:25-35), weight repacking and the
+// hoisted speaker projections (models/TTSModel.py:174,179).
+#include "common.cuh"
+
+namespace ssv {
+
+namespace {
+
+// (B, C, T) with arbitrary element strides -> (B, T, ld) channels-last, zero padded to ld.
+__global__ void transpose_in_kernel(const float* __restrict__ src, long sb, long sc, long st, int C, int T,
+                                    float* __restrict__ dst, int ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? src[b * sb + c * sc + t * st] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < ld) dst[((long)b * T + t) * ld + c] = tile[tx][i];
+  }
+}
+
+// (B, T, ld) channels-last, channels [c_off, c_off + C) -> (B, C, T) contiguous.
+__global__ void transpose_out_kernel(const float* __restrict__ src, int ld, int c_off, int C, int T,
+                                     float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (t < T && c < C) ? src[((long)b * T + t) * ld + c_off + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < C && t < T) dst[((long)b * C + c) * T + t] = tile[tx][i];
+  }
+}
+
+__global__ void embed_kernel(const int64_t* __restrict__ ids, int rows, const float* __restrict__ Wt,
+                             const float* __restrict__ bias, int vocab, int E, float* __restrict__ dst, int ld,
+                             int* err_flag) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  long id = ids[r];
+  if (id < 0 || id >= vocab) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    id = 0;
+  }
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) dst[(long)r * ld + c] = c < E ? Wt[id * E + c] + bias[c] : 0.f;
+}
+
+// w [n][cin][k] -> dst [k*cin_p][n_pad] (tap-major rows), zero padded.
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, int n, int cin, int k, int cin_p, int n_pad,
+                                   float* __restrict__ dst) {
+  const long total = (long)k * cin_p * n_pad;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % n_pad);
+    const int kk = (int)(i / n_pad);
+    const int j = kk / cin_p, ci = kk % cin_p;
+    dst[i] = (col < n && ci < cin) ? w[((long)col * cin + ci) * k + j] : 0.f;
+  }
+}
+
+// ConvTranspose1d weight [cin][cout][2] -> [cin][2*cout] with column j*cout + co; bias duplicated.
+__global__ void pack_deconv_w_kernel(const float* __restrict__ w, const float* __restrict__ b, int cin, int cout,
+                                     float* __restrict__ dst, float* __restrict__ bias_dst) {
+  const long total = (long)cin * 2 * cout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % (2 * cout));
+    const int ci = (int)(i / (2 * cout));
+    const int j = col / cout, co = col % cout;
+    dst[i] = w[((long)ci * cout + co) * 2 + j];
+    if (ci == 0) bias_dst[col] = b[co];
+  }
+}
+
+// w [n][cin][k] -> dst [n][k*cin] (per-output-column contiguous K, tap-major) for the decode GEMVs.
+__global__ void pack_rowmajor_w_kernel(const float* __restrict__ w, int n, int cin, int k, float* __restrict__ dst) {
+  const long total = (long)n * cin * k;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % ((long)cin * k));
+    const int col = (int)(i / ((long)cin * k));
+    const int j = kk / cin, ci = kk % cin;
+    dst[i] = w[((long)col * cin + ci) * k + j];
+  }
+}
+
+__global__ void pad_vec_kernel(const float* __restrict__ src, int n, int n_pad, float* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+    dst[i] = i < n ? src[i] : 0.f;
+}
+
+// y[b][o] = sum_i w[o][i] x[b][i] + bias[o]; one warp per (b, o).
+__global__ void linear_small_kernel(const float* __restrict__ x, long x_ld, const float* __restrict__ w,
+                                    const float* __restrict__ bias, int B, int in_f, int out_f,
+                                    float* __restrict__ y, int y_ld) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * out_f) return;
+  const int b = gw / out_f, o = gw % out_f;
+  float acc = 0.f;
+  for (int i = lane; i < in_f; i += 32) acc = fmaf(w[(long)o * in_f + i], x[b * x_ld + i], acc);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) y[(long)b * y_ld + o] = acc + bias[o];
+}
+
+inline int grid_for(long total, int block = 256) {
+  long g = (total + block - 1) / block;
+  return (int)(g > 4096 ? 4096 : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+
+int launch_transpose_in(const float* src, long sb, long sc, long st, int B, int C, int T, float* dst, int ld,
+                        cudaStream_t s) {
+  dim3 grid((T + 31) / 32, (ld + 31) / 32, B), block(32, 8);
+  transpose_in_kernel<<<grid, block, 0, s>>>(src, sb, sc, st, C, T, dst, ld);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_transpose_out2(const float* src, int ld, int c_off, int B, int C, int T, float* dst, cudaStream_t s) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_out_kernel<<<grid, block, 0, s>>>(src, ld, c_off, C, T, dst);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_transpose_out(const float* src, int ld, int B, int C, int T, float* dst, cudaStream_t s) {
+  return launch_transpose_out2(src, ld, 0, B, C, T, dst, s);
+}
+
+int launch_embed(const int64_t* ids, int B, int N, const float* Wt, const float* bias, int vocab, int E, float* dst,
+                 int ld, int* err_flag, cudaStream_t s) {
+  embed_kernel<<<B * N, 128, 0, s>>>(ids, B * N, Wt, bias, vocab, E, dst, ld, err_flag);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_pack_conv_w(const float* w, int n, int cin, int k, int cin_p, int n_pad, float* dst, cudaStream_t s) {
+  pack_conv_w_kernel<<<grid_for((long)k * cin_p * n_pad), 256, 0, s>>>(w, n, cin, k, cin_p, n_pad, dst);
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_pack_deconv_w(const float* w, const float* b, int cin, int cout, float* dst, float* bias_dst,
+                         cudaStream_t s) {
+  pack_deconv_w_kernel<<<grid_for((long)cin * 2 * cout), 256, 0, s>>>(w, b, cin, cout, dst, bias_dst);
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_pack_rowmajor_w(const float* w, int n, int cin, int k, float* dst, cudaStream_t s) {
+  pack_rowmajor_w_kernel<<<grid_for((long)n * cin * k), 256, 0, s>>>(w, n, cin, k, dst);
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_pad_vec(const float* src, int n, int n_pad, float* dst, cudaStream_t s) {
+  pad_vec_kernel<<<grid_for(n_pad), 256, 0, s>>>(src, n, n_pad, dst);
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_linear_small(const float* x, long x_ld, const float* w, const float* b, int B, int in_f, int out_f,
+                        float* y, int y_ld, cudaStream_t s) {
+  const long threads = (long)B * out_f * 32;
+  linear_small_kernel<<<(int)((threads + 255) / 256), 256, 0, s>>>(x, x_ld, w, b, B, in_f, out_f, y, y_ld);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace ssv

@@ -1,0 +1,349 @@
+"""Drop-in ``melSyn`` / ``SSRN`` / ``highwayConv`` backed by the sm_100a CUDA library.
+
+Same constructor arguments, forward signatures, return tuples and ``state_dict``
+key layout as the reference ``models/TTSModel.py`` (melSyn :234-300, SSRN :319-362,
+highwayConv :37-84), so ``*.tar.pth`` checkpoints load with
+``load_state_dict(ckp['model_state_dict'])`` unchanged.  The ``torch.nn`` submodules
+below only *hold parameters* (and reproduce the reference's construction order, so
+``torch.manual_seed(s)`` yields identical random-init weights); no torch math runs in
+``forward`` -- it hands raw device pointers to the C ABI (include/spoofsv_b200.h).
+
+There is no CPU fallback: a CPU tensor, a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+__all__ = ["melSyn", "SSRN", "highwayConv"]
+
+
+class _Bag(nn.Module):
+    """Ordered parameter container; children are registered in keyword order."""
+
+    def __init__(self, **children: nn.Module):
+        super().__init__()
+        for name, child in children.items():
+            self.add_module(name, child)
+
+    def forward(self, *a, **k):  # pragma: no cover - containers are never called
+        raise RuntimeError("parameter container; call the owning model instead")
+
+
+def _hc(d: int, k: int) -> _Bag:
+    return _Bag(conv=nn.Conv1d(d, 2 * d, k), ln1=nn.LayerNorm(d), ln2=nn.LayerNorm(d))
+
+
+def _hci(d: int) -> _Bag:
+    return _Bag(hc1=_hc(d, 3), hc2=_hc(d, 3), hc3=_hc(d, 3), hc4=_hc(d, 3))
+
+
+def _prec(name: str) -> int:
+    try:
+        return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[name]
+    except KeyError:
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {name!r}") from None
+
+
+class _Native(nn.Module):
+    """Owns a native handle built from the module's parameters; rebuilt when they change."""
+
+    _create_name = ""
+    _destroy_name = ""
+
+    def __init__(self):
+        super().__init__()
+        self._handle: Optional[int] = None
+        self._stamp = None
+
+    def _dims(self):  # pragma: no cover
+        raise NotImplementedError
+
+    def _param_stamp(self):
+        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+
+    def _release(self):
+        if self._handle is not None:
+            try:
+                getattr(_lib.load(False), self._destroy_name)(C.c_void_p(self._handle))
+            except Exception:
+                pass
+            self._handle = None
+
+    def _native(self) -> C.c_void_p:
+        stamp = self._param_stamp()
+        if self._handle is None or stamp != self._stamp:
+            self._release()
+            self._on_rebuild()
+            lib = _lib.load()
+            names, ptrs, numels, n, keep = _lib.pack_params(self.state_dict())
+            out = C.c_void_p()
+            _lib.check(getattr(lib, self._create_name)(names, ptrs, numels, n, *self._dims(), C.byref(out)))
+            del keep
+            self._handle = out.value
+            self._stamp = stamp
+        return C.c_void_p(self._handle)
+
+    def _on_rebuild(self):
+        pass
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:   # interpreter shutdown: torch internals may already be gone
+            pass
+
+
+class highwayConv(nn.Module):
+    """reference models/TTSModel.py:37-84 -- same ctor, same parameters, CUDA forward."""
+
+    def __init__(self, dimension, kernel_size, dilation, causal=False):
+        super().__init__()
+        self.dimension, self.kernel_size, self.dilation, self.causal = dimension, kernel_size, dilation, causal
+        self.pad = dilation * (kernel_size - 1) // 2
+        self.conv = nn.Conv1d(dimension, 2 * dimension, kernel_size, padding=0 if causal else self.pad,
+                              dilation=dilation)
+        self.ln1 = nn.LayerNorm(dimension)
+        self.ln2 = nn.LayerNorm(dimension)
+        self.precision = "fp32"
+
+    def forward(self, inputs):
+        _lib.require_cuda(inputs, "highwayConv.forward")
+        if inputs.dim() != 3 or inputs.shape[1] != self.dimension:
+            raise ValueError(f"highwayConv expects (B, {self.dimension}, T), got {tuple(inputs.shape)}")
+        x = inputs.detach().to(torch.float32).contiguous()
+        B, d, T = x.shape
+        y = torch.empty_like(x)
+        if x.numel() == 0:
+            return y
+        ps = [self.conv.weight, self.conv.bias, self.ln1.weight, self.ln1.bias, self.ln2.weight, self.ln2.bias]
+        ps = [p.detach().contiguous() for p in ps]
+        for p in ps:
+            _lib.require_cuda(p, "highwayConv parameter")
+        _lib.check(_lib.load().ssv_highway_conv_fwd(
+            x.data_ptr(), *[p.data_ptr() for p in ps], B, d, T, self.kernel_size, self.dilation, int(self.causal),
+            y.data_ptr(), _prec(self.precision), _lib.current_stream_ptr()))
+        return y
+
+
+class melSyn(_Native):
+    """Text2Mel.  reference models/TTSModel.py:234-300."""
+
+    _create_name = "ssv_text2mel_create"
+    _destroy_name = "ssv_text2mel_destroy"
+
+    def __init__(self, vocab_len, condition, spkemb_dim, textemb_dim=128, freq_bins=80, hidden_dim=256):
+        super().__init__()
+        if not condition:
+            raise NotImplementedError("spoofsv_b200 implements the speaker-conditioned model (condition=True)")
+        h, h2 = hidden_dim, 2 * hidden_dim
+        self.vocab_len, self.spkemb_dim, self.textemb_dim = vocab_len, spkemb_dim, textemb_dim
+        self.freq_bins, self.hidden_dim = freq_bins, hidden_dim
+        pw = lambda i, o: nn.Conv1d(i, o, 1)
+        # construction order == reference order (fixes the RNG stream and the state_dict key order)
+        self.text_encoder = _Bag(
+            textemb_layer=_Bag(W=nn.Linear(vocab_len, textemb_dim)),
+            conv1=pw(textemb_dim, h2), ln1=nn.LayerNorm(h2), conv2=pw(h2, h2), ln2=nn.LayerNorm(h2),
+            hci1=_hci(h2), hci2=_hci(h2), hc1=_hc(h2, 3), hc2=_hc(h2, 3), hc3=_hc(h2, 1), hc4=_hc(h2, 1))
+        self.audio_encoder = _Bag(
+            fc1=nn.Linear(spkemb_dim, h), fc2=nn.Linear(spkemb_dim, h),
+            conv1=pw(freq_bins, h), ln1=nn.LayerNorm(h), conv2=pw(h, h), ln2=nn.LayerNorm(h),
+            conv3=pw(h, h), ln3=nn.LayerNorm(h),
+            hci1=_hci(h), hci2=_hci(h), hc1=_hc(h, 3), hc2=_hc(h, 3))
+        self.audio_decoder = _Bag(
+            conv1=pw(h2, h), ln1=nn.LayerNorm(h), hci=_hci(h), hc1=_hc(h, 3), hc2=_hc(h, 3),
+            conv2=pw(h, h), ln2=nn.LayerNorm(h), conv3=pw(h, h), ln3=nn.LayerNorm(h),
+            conv4=pw(h, h), ln4=nn.LayerNorm(h), conv5=pw(h, freq_bins), ln5=nn.LayerNorm(freq_bins))
+        self.precision = "fp32"
+        self.max_frames = 1024      # decoder capacity (reference MAX_FRAME_NUM is 325)
+        self._dec: Optional[int] = None
+        self._dec_cap = (0, 0, 0)
+        self._state = None
+
+    # ---- native handles ------------------------------------------------------------------
+    def _dims(self):
+        return (self.vocab_len, self.spkemb_dim, self.textemb_dim, self.freq_bins, self.hidden_dim)
+
+    def _drop_decoder(self):
+        if self._dec is not None:
+            try:
+                _lib.load(False).ssv_decoder_destroy(C.c_void_p(self._dec))
+            except Exception:
+                pass
+            self._dec = None
+            self._dec_cap = (0, 0, 0)
+        self._state = None
+
+    def _on_rebuild(self):
+        self._drop_decoder()
+
+    def _release(self):
+        self._drop_decoder()
+        super()._release()
+
+    def _decoder(self, B: int, N: int, T: int) -> C.c_void_p:
+        h = self._native()
+        cb, cn, ct = self._dec_cap
+        if self._dec is None or B > cb or N > cn or T > ct:
+            self._drop_decoder()
+            cap = (max(B, cb), max(N, cn), max(T, ct))
+            out = C.c_void_p()
+            _lib.check(_lib.load().ssv_decoder_create(h, *cap, C.byref(out)))
+            self._dec, self._dec_cap = out.value, cap
+        return C.c_void_p(self._dec)
+
+    # ---- pieces --------------------------------------------------------------------------
+    def encode_text(self, textid: torch.Tensor):
+        """textEncoder.forward (reference :126-140): (B, 1, N) int -> K, V (B, hidden, N)."""
+        _lib.require_cuda(textid, "melSyn text ids")
+        ids = textid.detach().to(torch.int64).contiguous()
+        if ids.dim() != 3 or ids.shape[1] != 1:
+            raise ValueError(f"textid must be (B, 1, N), got {tuple(ids.shape)}")
+        B, _, N = ids.shape
+        if B == 0 or N == 0:
+            raise ValueError("textid is empty")
+        if int(ids.min()) < 0 or int(ids.max()) >= self.vocab_len:
+            raise ValueError(f"text ids must lie in [0, {self.vocab_len})")
+        K = torch.empty((B, self.hidden_dim, N), device=ids.device, dtype=torch.float32)
+        V = torch.empty_like(K)
+        _lib.check(_lib.load().ssv_text_encoder_fwd(self._native(), ids.data_ptr(), B, N, K.data_ptr(), V.data_ptr(),
+                                                    _prec(self.precision), _lib.current_stream_ptr()))
+        return K, V
+
+    def _begin(self, K, V, spkemb, t_cap: int):
+        B, _, N = K.shape
+        spk = spkemb.detach().to(torch.float32).contiguous()
+        if spk.shape != (B, self.spkemb_dim, 1):
+            raise ValueError(f"spkemb must be ({B}, {self.spkemb_dim}, 1), got {tuple(spk.shape)}")
+        dec = self._decoder(B, N, t_cap)
+        dev = K.device
+        Y = torch.empty((B, self.freq_bins, t_cap), device=dev, dtype=torch.float32)
+        A = torch.empty((B, N, t_cap), device=dev, dtype=torch.float32)
+        traj = torch.empty((t_cap, B), device=dev, dtype=torch.int64)
+        Kc, Vc = K.detach().contiguous(), V.detach().contiguous()
+        _lib.check(_lib.load().ssv_decoder_begin(dec, Kc.data_ptr(), Vc.data_ptr(), spk.data_ptr(), B, N,
+                                                 Y.data_ptr(), A.data_ptr(), traj.data_ptr(), t_cap,
+                                                 _lib.current_stream_ptr()))
+        self._state = dict(Y=Y, A=A, traj=traj, B=B, N=N, t=0, cap=t_cap, keep=(Kc, Vc, spk))
+        return dec
+
+    def synthesize(self, textid, spkemb, n_frames: int):
+        """Whole AR loop of generate_test_utterances.py:105-116 in one launch.
+
+        Returns (Y (B,F,T), A (B,N,T), pma trajectory (T,B), K, V)."""
+        if n_frames < 1:
+            raise ValueError("n_frames must be >= 1")
+        K, V = self.encode_text(textid)
+        dec = self._begin(K, V, spkemb, n_frames)
+        lib = _lib.load()
+        _lib.check(lib.ssv_decoder_run(dec, n_frames, _lib.current_stream_ptr()))
+        _lib.check(lib.ssv_decoder_check(dec, _lib.current_stream_ptr()))
+        st = self._state
+        st["t"] = n_frames
+        return st["Y"], st["A"], st["traj"], K, V
+
+    # ---- reference protocol --------------------------------------------------------------
+    def forward(self, melspec, textid, spkemb, K=None, V=None, A_last=None, pma=None):
+        """Eval-mode protocol of the reference (:275-300).
+
+        Call 1: melspec (B,F,1) -> (Y, A, max_att, K, V).  Call t: melspec (B,F,t) whose newest
+        column is the next input frame -> (Y (B,F,t), A (B,N,t), max_att).  Y and A are views of
+        decoder-owned buffers.  ``A_last`` is not read (its columns are already held here)."""
+        if self.training:
+            raise NotImplementedError(
+                "melSyn.forward in train() mode (teacher-forced training) is outside the CUDA hot path; "
+                "call .eval() for synthesis")
+        _lib.require_cuda(melspec, "melSyn.forward melspec")
+        if melspec.dim() != 3 or melspec.shape[1] != self.freq_bins:
+            raise ValueError(f"melspec must be (B, {self.freq_bins}, T), got {tuple(melspec.shape)}")
+        B, _, T = melspec.shape
+        if T < 1 or B < 1:
+            raise ValueError("melspec is empty")
+        lib = _lib.load()
+        first = T == 1
+        if first:
+            if textid is None:
+                raise ValueError("the first call (T == 1) needs textid")
+            K, V = self.encode_text(textid)
+            if K.shape[0] != B:
+                raise ValueError("batch size of textid and melspec differ")
+            dec = self._begin(K, V, spkemb, self.max_frames)
+        else:
+            st = self._state
+            if st is None or st["B"] != B or st["t"] != T - 1:
+                have = None if st is None else st["t"]
+                raise RuntimeError(
+                    f"melSyn.forward: incremental decoder holds {have} frame(s) but was called with T={T}; "
+                    "the reference protocol appends exactly one frame per call after a T == 1 call")
+            if T > st["cap"]:
+                raise RuntimeError(f"melSyn.forward: T={T} exceeds max_frames={st['cap']}; raise model.max_frames")
+            dec = C.c_void_p(self._dec)
+        st = self._state
+        x = melspec.detach()
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        xl = x[:, :, T - 1]
+        pma_t = None
+        if pma is not None:
+            _lib.require_cuda(pma, "melSyn.forward pma")
+            pma_t = pma.detach().to(torch.int64).contiguous()
+            if pma_t.shape != (B,):
+                raise ValueError(f"pma must be ({B},), got {tuple(pma_t.shape)}")
+        _lib.check(lib.ssv_decoder_step(dec, xl.data_ptr(), xl.stride(0), xl.stride(1),
+                                        None if pma_t is None else pma_t.data_ptr(), _lib.current_stream_ptr()))
+        st["t"] = T
+        st["last_in"] = (x, pma_t)
+        Y, A, max_att = st["Y"][:, :, :T], st["A"][:, :, :T], st["traj"][T - 1]
+        if first:
+            return Y, A, max_att, K, V
+        return Y, A, max_att
+
+    def check(self):
+        """Synchronise and raise if the decode kernel aborted."""
+        if self._dec is not None:
+            _lib.check(_lib.load().ssv_decoder_check(C.c_void_p(self._dec), _lib.current_stream_ptr()))
+
+
+class SSRN(_Native):
+    """reference models/TTSModel.py:319-362."""
+
+    _create_name = "ssv_ssrn_create"
+    _destroy_name = "ssv_ssrn_destroy"
+
+    def __init__(self, freq_bins, output_bins, ssrn_dim):
+        super().__init__()
+        self.freq_bins, self.output_bins, self.ssrn_dim = freq_bins, output_bins, ssrn_dim
+        d, d2, o = ssrn_dim, 2 * ssrn_dim, output_bins
+        pw = lambda i, o_: nn.Conv1d(i, o_, 1)
+        ups = lambda: _Bag(deconv=nn.ConvTranspose1d(d, d, 2, stride=2), hc1=_hc(d, 3), hc2=_hc(d, 3))
+        for name, mod in (
+                ("conv1", pw(freq_bins, d)), ("ln1", nn.LayerNorm(d)), ("hc1", _hc(d, 3)), ("hc2", _hc(d, 3)),
+                ("ups1", ups()), ("ups2", ups()),
+                ("conv2", pw(d, d2)), ("ln2", nn.LayerNorm(d2)), ("hc3", _hc(d2, 3)), ("hc4", _hc(d2, 3)),
+                ("conv3", pw(d2, o)), ("ln3", nn.LayerNorm(o)), ("conv4", pw(o, o)), ("ln4", nn.LayerNorm(o)),
+                ("conv5", pw(o, o)), ("ln5", nn.LayerNorm(o)), ("conv6", pw(o, o)), ("ln6", nn.LayerNorm(o))):
+            self.add_module(name, mod)
+        self.precision = "fp32"
+
+    def _dims(self):
+        return (self.freq_bins, self.output_bins, self.ssrn_dim)
+
+    def forward(self, inputs):
+        _lib.require_cuda(inputs, "SSRN.forward")
+        if inputs.dim() != 3 or inputs.shape[1] != self.freq_bins:
+            raise ValueError(f"SSRN expects (B, {self.freq_bins}, T), got {tuple(inputs.shape)}")
+        x = inputs.detach()
+        if x.dtype != torch.float32:
+            x = x.to(torch.float32)
+        B, _, T = x.shape
+        out = torch.empty((B, self.output_bins, 4 * T), device=x.device, dtype=torch.float32)
+        if B == 0 or T == 0:
+            return out
+        _lib.check(_lib.load().ssv_ssrn_fwd(self._native(), x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
+                                            B, T, out.data_ptr(), _prec(self.precision), _lib.current_stream_ptr()))
+        return out

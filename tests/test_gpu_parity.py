@@ -1,0 +1,266 @@
+"""GPU parity: the CUDA path (through the drop-in modules -> C ABI) against the CPU oracle and the
+committed known-answer vectors of the unmodified reference.
+
+Tolerances (BASELINE.json north_star): FP32 path max-abs <= 1e-4 on mel / linear / attention with
+identical alignment (pma) trajectories; BF16 path relative-L2 <= 2e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ttsmodel_oracle as O
+from oracle import weights as W
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _maxabs(a, b):
+    return float((a.detach().cpu().float() - b.detach().cpu().float()).abs().max())
+
+
+def _rel_l2(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / b.norm())
+
+
+# --------------------------------------------------------------------------- highwayConv
+def test_highway_conv_all_classes_fp32(golden_dir):
+    from spoofsv_b200.models import highwayConv
+    z = np.load(golden_dir / "highway_cases.npz")
+    for i, (d, k, dil, causal) in enumerate(z["cases"].tolist()):
+        hc = highwayConv(dimension=d, kernel_size=k, dilation=dil, causal=bool(causal))
+        hc.load_state_dict(W.highway_params(d, k, 100 + i), strict=True)
+        hc = hc.cuda().eval()
+        x = torch.randn((2, d, 45), generator=torch.Generator().manual_seed(200 + i))
+        y = hc(x.cuda())
+        assert y.shape == x.shape
+        assert _maxabs(y, _t(z[f"y{i}"])) <= FP32_TOL, (d, k, dil, causal)
+
+
+@pytest.mark.parametrize("T", [1, 2, 31, 33, 130])
+def test_highway_conv_ragged_lengths(T):
+    """T smaller than the dilation reach, tile-straddling, and multi-tile."""
+    from spoofsv_b200.models import highwayConv
+    for (d, k, dil, causal) in [(256, 3, 27, 1), (256, 3, 3, 0), (512, 3, 9, 0)]:
+        p = W.highway_params(d, k, 5)
+        hc = highwayConv(d, k, dil, bool(causal))
+        hc.load_state_dict(p, strict=True)
+        x = torch.randn((3, d, T), generator=torch.Generator().manual_seed(T))
+        want = O.highway_conv(x, {"." + kk: v for kk, v in p.items()}, "", dil, bool(causal))
+        assert _maxabs(hc.cuda()(x.cuda()), want) <= FP32_TOL, (d, k, dil, causal, T)
+
+
+def test_highway_conv_empty_and_bad_shape():
+    from spoofsv_b200.models import highwayConv
+    hc = highwayConv(256, 3, 1).cuda()
+    assert hc(torch.zeros(0, 256, 5, device="cuda")).shape == (0, 256, 5)
+    with pytest.raises(ValueError):
+        hc(torch.zeros(1, 128, 5, device="cuda"))
+
+
+# --------------------------------------------------------------------------- SSRN
+def test_ssrn_golden_fp32(golden_dir, cuda_models_k):
+    _, m2, _, _ = cuda_models_k
+    z = np.load(golden_dir / "ssrn_seed7.npz")
+    lin = m2(_t(z["mel"]).cuda())
+    assert lin.shape == (2, 513, 148)
+    assert _maxabs(lin, _t(z["lin"])) <= FP32_TOL
+
+
+def test_ssrn_noncontiguous_input_and_cfg1(golden_dir, cuda_models):
+    _, m2, _, _ = cuda_models
+    z = np.load(golden_dir / "cfg1_seed0.npz")
+    Y = _t(z["Y"]).cuda()
+    buf = torch.zeros((1, 80, 300), device="cuda")
+    buf[:, :, :217] = Y
+    lin = m2(buf[:, :, :217])                       # a view, like the decoder-owned Y buffer
+    assert lin.shape == (1, 513, 868)
+    assert _maxabs(lin[:, :, ::4], _t(z["lin_t4"])) <= FP32_TOL
+    assert _maxabs(lin[:, :, :16], _t(z["lin_first"])) <= FP32_TOL
+
+
+def test_ssrn_full_size_properties(cuda_models):
+    """BASELINE config 2 size (32 x 217): range, determinism, batch independence."""
+    _, m2, _, sd2 = cuda_models
+    mel = torch.rand((32, 80, 217), generator=torch.Generator().manual_seed(0)).cuda()
+    a = m2(mel)
+    assert a.shape == (32, 513, 868)
+    assert bool(torch.isfinite(a).all()) and float(a.min()) > 0 and float(a.max()) < 1
+    assert torch.equal(a, m2(mel))
+    perm = torch.randperm(32, generator=torch.Generator().manual_seed(1)).cuda()
+    assert torch.equal(m2(mel[perm]), a[perm])
+    want = O.ssrn(mel[5:6].cpu(), sd2)
+    assert _maxabs(a[5:6], want) <= FP32_TOL
+
+
+# --------------------------------------------------------------------------- text encoder
+def test_text_encoder_golden(golden_dir, cuda_models_k):
+    m1, _, _, _ = cuda_models_k
+    z = np.load(golden_dir / "small_seed7.npz")
+    K, V = m1.encode_text(_t(z["textid"]).cuda())
+    assert _maxabs(K, _t(z["K"])) <= FP32_TOL and _maxabs(V, _t(z["V"])) <= FP32_TOL
+
+
+def test_text_encoder_rejects_bad_ids(cuda_models):
+    m1, _, _, _ = cuda_models
+    with pytest.raises(ValueError):
+        m1.encode_text(torch.full((1, 1, 4), 34, device="cuda"))
+    with pytest.raises(ValueError):
+        m1.encode_text(torch.zeros((1, 4), dtype=torch.int64, device="cuda"))
+
+
+# --------------------------------------------------------------------------- decode
+def test_decode_cfg1_217_frames(golden_dir, cuda_models):
+    """BASELINE config 1: identical alignment trajectory over 217 frames, mel within 1e-4."""
+    m1, m2, _, _ = cuda_models
+    z = np.load(golden_dir / "cfg1_seed0.npz")
+    Y, A, traj, K, V = m1.synthesize(_t(z["textid"]).cuda(), _t(z["spk"]).cuda(), 217)
+    assert np.array_equal(traj.cpu().numpy(), z["traj"])
+    assert _maxabs(K, _t(z["K"])) <= FP32_TOL
+    assert _maxabs(Y, _t(z["Y"])) <= FP32_TOL
+    assert _maxabs(A, _t(z["A"])) <= FP32_TOL
+    lin = m2(Y)
+    assert _maxabs(lin[:, :, ::4], _t(z["lin_t4"])) <= FP32_TOL
+
+
+def test_decode_small_batch_run_and_protocol(golden_dir, cuda_models_k):
+    """Ragged batch of 3; the one-launch run and the reference's call-per-frame protocol agree."""
+    m1, m2, _, _ = cuda_models_k
+    z = np.load(golden_dir / "small_seed7.npz")
+    ids, spk = _t(z["textid"]).cuda(), _t(z["spk"]).cuda()
+    T = z["Y"].shape[-1]
+    Y, A, traj, _, _ = m1.synthesize(ids, spk, T)
+    assert np.array_equal(traj.cpu().numpy(), z["traj"])
+    assert _maxabs(Y, _t(z["Y"])) <= FP32_TOL and _maxabs(A, _t(z["A"])) <= FP32_TOL
+    assert _maxabs(m2(Y), _t(z["lin"])) <= FP32_TOL
+    Y_run, A_run = Y.clone(), A.clone()
+
+    # generate_test_utterances.py:105-116, verbatim call pattern
+    init = torch.zeros((3, 80, 1), device="cuda")
+    Yp, Ap, pma, K, V = m1(melspec=init, textid=ids, spkemb=spk, pma=torch.zeros((3,), device="cuda").long())
+    assert Yp.shape == (3, 80, 1) and Ap.shape == (3, ids.shape[-1], 1) and pma.dtype == torch.int64
+    inputs = torch.cat((init, Yp), dim=-1)
+    for _ in range(T - 1):
+        Yp, Ap, pma = m1(melspec=inputs, textid=None, spkemb=spk, K=K, V=V, A_last=Ap, pma=pma)
+        inputs = torch.cat((inputs, Yp[:, :, -1:]), dim=-1)
+    m1.check()
+    assert Yp.shape == (3, 80, T) and Ap.shape == (3, ids.shape[-1], T)
+    assert torch.equal(Yp, Y_run) and torch.equal(Ap, A_run)
+    assert np.array_equal(pma.cpu().numpy(), z["traj"][-1])
+
+
+def test_decode_protocol_violation_raises(cuda_models):
+    m1, _, _, _ = cuda_models
+    ids = W.synthetic_text(2, 12, seed=2).cuda()
+    spk = torch.full((2, 200, 1), 0.05, device="cuda")
+    m1(melspec=torch.zeros((2, 80, 1), device="cuda"), textid=ids, spkemb=spk, pma=torch.zeros(2, device="cuda").long())
+    with pytest.raises(RuntimeError, match="one frame per call"):
+        m1(melspec=torch.zeros((2, 80, 5), device="cuda"), textid=None, spkemb=spk, pma=torch.zeros(2, device="cuda").long())
+
+
+@pytest.mark.parametrize("B", [1, 2, 4, 5, 16, 17, 64])
+def test_decode_batch_sizes_vs_oracle(B, cuda_models):
+    """Every row-group configuration of the decode kernel (1 / 4 / 16 rows, 1..4 groups), N = 58."""
+    m1, _, sd1, _ = cuda_models
+    names, emb, _ = W.load_fixtures()
+    ids = W.synthetic_text(B, 58, seed=B)
+    spk = torch.from_numpy(emb[:B].copy())[:, :, None]
+    T = 30
+    Y, A, traj, _, _ = m1.synthesize(ids.cuda(), spk.cuda(), T)
+    with torch.no_grad():
+        oY, oA, otraj = O.ar_loop_incremental(sd1, ids, spk, T)
+    assert np.array_equal(traj.cpu().numpy(), otraj.numpy())
+    assert _maxabs(Y, oY) <= FP32_TOL and _maxabs(A, oA) <= FP32_TOL
+
+
+def test_decode_teacher_forced_frames(cuda_models):
+    """The step API takes the newest column of the caller's melspec (not its own y) and the caller's pma."""
+    m1, _, sd1, _ = cuda_models
+    ids = W.synthetic_text(2, 20, seed=3)
+    spk = torch.full((2, 200, 1), 0.06)
+    mel = torch.rand((2, 80, 6), generator=torch.Generator().manual_seed(4))
+    mel[:, :, 0] = 0
+    with torch.no_grad():
+        K, V = O.text_encoder(ids, sd1)
+        pma = torch.zeros(2, dtype=torch.int64)
+        A_last = None
+        want = []
+        for t in range(1, 7):
+            if t == 1:
+                Y, A_last, pma, _, _ = O.melsyn_eval_call(sd1, mel[:, :, :1], ids, spk, pma=pma)
+            else:
+                Y, A_last, pma = O.melsyn_eval_call(sd1, mel[:, :, :t], None, spk, K=K, V=V, A_last=A_last, pma=pma)
+            want.append((Y.clone(), pma.clone()))
+    melc, spkc = mel.cuda(), spk.cuda()
+    pm = torch.zeros(2, dtype=torch.int64, device="cuda")
+    for t in range(1, 7):
+        if t == 1:
+            Y, A, pm, Kc, Vc = m1(melspec=melc[:, :, :1], textid=ids.cuda(), spkemb=spkc, pma=pm)
+        else:
+            Y, A, pm = m1(melspec=melc[:, :, :t], textid=None, spkemb=spkc, K=Kc, V=Vc, A_last=A, pma=pm)
+        assert _maxabs(Y, want[t - 1][0]) <= FP32_TOL
+        assert torch.equal(pm.cpu(), want[t - 1][1])
+    m1.check()
+
+
+def test_decode_continuation_equals_single_run(cuda_models):
+    """run(T) == step-wise continuation; chunked launches leave the same state."""
+    m1, _, _, _ = cuda_models
+    from spoofsv_b200 import _lib
+    import ctypes as C
+    ids = W.synthetic_text(4, 33, seed=5).cuda()
+    spk = torch.full((4, 200, 1), 0.05, device="cuda")
+    Y, A, traj, K, V = m1.synthesize(ids, spk, 60)
+    Y, A, traj = Y.clone(), A.clone(), traj.clone()
+    dec = m1._begin(K, V, spk, 60)
+    lib = _lib.load()
+    for n in (1, 7, 30, 22):
+        _lib.check(lib.ssv_decoder_run(dec, n, _lib.current_stream_ptr()))
+    _lib.check(lib.ssv_decoder_check(dec, _lib.current_stream_ptr()))
+    st = m1._state
+    assert torch.equal(st["Y"], Y) and torch.equal(st["A"], A) and torch.equal(st["traj"], traj)
+    with pytest.raises(_lib.SsvError, match="capacity"):
+        _lib.check(lib.ssv_decoder_run(dec, 1, _lib.current_stream_ptr()))
+
+
+def test_full_size_decode_properties(cuda_models):
+    """BASELINE config 3 size (B=64, N=58, 217 frames): determinism, batch independence, ranges,
+    monotone window constraint of the alignment."""
+    m1, _, _, _ = cuda_models
+    names, emb, _ = W.load_fixtures()
+    ids = W.synthetic_text(64, 58, seed=11).cuda()
+    spk = torch.from_numpy(emb[:64].copy())[:, :, None].cuda()
+    Y, A, traj, _, _ = m1.synthesize(ids, spk, 217)
+    Y, A, traj = Y.clone(), A.clone(), traj.clone()
+    assert bool(torch.isfinite(Y).all()) and float(Y.min()) > 0 and float(Y.max()) < 1
+    assert torch.allclose(A.sum(1), torch.ones_like(A.sum(1)), atol=1e-5)
+    assert int((A > 0).sum(1).max()) <= 3
+    step = traj[1:] - traj[:-1]
+    assert int(step.min()) >= 0 and int(step.max()) <= 2          # argmax stays inside [pma, pma+2]
+    Y2, A2, traj2, _, _ = m1.synthesize(ids, spk, 217)
+    assert torch.equal(Y2, Y) and torch.equal(traj2, traj)
+    sub = [3, 40, 63]
+    Ys, As, trajs, _, _ = m1.synthesize(ids[sub], spk[sub], 217)
+    assert torch.equal(trajs, traj[:, sub])
+    assert _maxabs(Ys, Y[sub]) <= 1e-5
+
+
+# --------------------------------------------------------------------------- host-buffer entry point
+def test_synthesize_host_matches_module_path(cuda_models):
+    from spoofsv_b200.synth import Synthesizer
+    m1, m2, _, _ = cuda_models
+    names, emb, _ = W.load_fixtures()
+    ids = W.synthetic_text(3, 25, seed=8)
+    spk = emb[:3].copy()
+    syn = Synthesizer(m1, m2)
+    out = syn.synthesize_host(ids[:, 0, :].numpy(), spk, 20, want_mel=True, want_att=True)
+    Y, A, traj, _, _ = m1.synthesize(ids.cuda(), torch.from_numpy(spk)[:, :, None].cuda(), 20)
+    lin = m2(Y)
+    assert np.array_equal(out["traj"], traj.cpu().numpy())
+    assert np.array_equal(out["mel"], Y.cpu().numpy()) and np.array_equal(out["lin"], lin.cpu().numpy())
+    assert np.array_equal(out["att"], A.cpu().numpy())
