@@ -1,0 +1,330 @@
+"""Benchmark of the Text2Mel + SSRN synthesis hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic utterances shaped like
+generate_test_utterances.py's workload (BASELINE config 4 = configs 2+3 back to back): B utterances
+(Harvard sentences x VCTK speaker embeddings, all padded to N = 58), TextEnc once, T = 217 frames
+of incremental decode, SSRN on the result.  Frames are REDUCED MEL FRAMES (decode steps; one mel
+frame = 4 linear-spectrogram frames).
+
+  value     frames/s with inputs resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e       the same through the C ABI's host-buffer call (ssv_synthesize_host): H2D of ids +
+            embeddings and D2H of the linear spectrogram inside the timed region
+  roofline  the dominant kernel (the persistent decode kernel), algorithmic bytes / CUDA-event time
+            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference
+            the reference algorithm (re-encoding O(T^2) AR loop + SSRN) as restated in oracle/ on the
+            host cores, on a bounded sample of the same workload.  /root/reference is a Python repo
+            that does not exist on the GPU box, so the port is what can be timed there.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Text2Mel+SSRN synthesized frames/s"
+UNIT = "reduced mel frames/s"
+N_TEXT = 58
+T_FRAMES = 217
+BATCH = 64
+# SURVEY.md 8(d) cfg 3: algorithmic bytes per decode step = AudioEnc+AudioDec weights (fc1/fc2 hoisted)
+DECODE_WEIGHT_BYTES = 6_821_360 * 4
+DECODE_STATE_BYTES_PER_UTT = 16 * 3 * 256 * 4 + 6 * 1024 + 640       # taps r/w, K/V window, x/y  (~56 KB)
+SSRN_FLOP_PER_FRAME = 46_469_144
+TEXTENC_FLOP_PER_CHAR = 34_218_496
+DECODE_FLOP_PER_FRAME = 13_630_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--frames", type=int, default=T_FRAMES)
+    ap.add_argument("--ssrn-precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sustained=float(d["bf16_tflops_sustained"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(batch: int, rank: int):
+    """Rank r takes units [r*B, (r+1)*B) of the speaker-major corpus (108 speakers x 720 sentences)."""
+    import numpy as np
+    from oracle import weights as W
+    from spoofsv_b200.synth import corpus_units
+    from spoofsv_b200.text import encode_lines, pad_batch
+    names, emb, lines = W.load_fixtures()
+    sent = encode_lines(lines)
+    units = corpus_units(len(names), len(lines))
+    # stride through the corpus so a batch mixes speakers and sentences
+    stride = 1201
+    pick = [units[((rank * batch + i) * stride) % len(units)] for i in range(batch)]
+    ids = pad_batch([sent[u.sentence] for u in pick], N_TEXT)
+    spk = np.stack([emb[u.speaker] for u in pick]).astype(np.float32)
+    return ids, spk
+
+
+def cpu_reference_step(sd1, sd2, ids, spk, frames):
+    """One step of the reference algorithm on the CPU (oracle port): re-encoding AR loop + SSRN."""
+    import torch
+    from oracle import ttsmodel_oracle as O
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        Y, A, traj, lin = O.synthesize(sd1, sd2, torch.from_numpy(ids)[:, None, :], torch.from_numpy(spk)[:, :, None], frames)
+        return time.perf_counter() - t0, lin
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import weights as W
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd1, sd2 = W.state_dicts(0)
+    nb = max(1, min(args.cpu_sample, args.batch))
+    ids, spk = workload(args.batch, 0)
+    ids, spk = ids[:nb], spk[:nb]
+    for _ in range(args.warmup):
+        cpu_reference_step(sd1, sd2, ids, spk, min(args.frames, 8))       # short warm-up: thread pools, oneDNN primitives
+    times = [cpu_reference_step(sd1, sd2, ids, spk, args.frames)[0] for _ in range(args.steps)]
+    total = sum(times)
+    value = nb * args.frames * args.steps / total
+    sample = (f"{nb} of the {args.batch} utterances per step, all {args.frames} frames, reference re-encoding AR loop + SSRN "
+              f"(oracle port of models/TTSModel.py, torch {torch.__version__} CPU fp32)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": config_dict(args, args.batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, batch):
+    return {"workload": f"generate_test_utterances batch: {batch} utterances (Harvard sentences x VCTK speaker embeddings, "
+                        f"N={N_TEXT} padded ids), TextEnc + {args.frames}-frame incremental Text2Mel decode + SSRN "
+                        f"-> ({batch}, 513, {4 * args.frames})",
+            "batch_per_gpu": batch, "text_len": N_TEXT, "frames": args.frames, "weights": "random-init seed 0",
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"utterance-sharded x{args.gpus}, no collective"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import weights as W
+    from spoofsv_b200 import _lib
+    from spoofsv_b200.synth import Synthesizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = _lib.load()
+    B, T = args.batch, args.frames
+    m1, m2 = W.build_models(0)
+    sd1 = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+    sd2 = {k: v.detach().clone() for k, v in m2.state_dict().items()}
+    m1, m2 = m1.cuda(), m2.cuda()
+    m2.precision = args.ssrn_precision
+    ids_np, spk_np = workload(B, rank)
+    ids_d = torch.from_numpy(ids_np)[:, None, :].cuda()
+    spk_d = torch.from_numpy(spk_np)[:, :, None].cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    syn = Synthesizer(m1, m2, ssrn_precision=args.ssrn_precision)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def device_step(parts=None):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        K, V = m1.encode_text(ids_d)
+        dec = m1._begin(K, V, spk_d, T)
+        e[1].record()
+        _lib.check(lib.ssv_decoder_run(dec, T, _lib.current_stream_ptr()))
+        e[2].record()
+        lin = m2(m1._state["Y"])
+        e[3].record()
+        return e, lin
+
+    # ---- warm-up (also builds the native handles and the decoder)
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        device_step()
+        syn.synthesize_host(ids_np, spk_np, T)
+    m1.check()
+
+    # ---- device-resident arm
+    barrier()
+    lib.ssv_launch_count(1)
+    step_ms, parts = [], []
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e, lin = device_step()
+            torch.cuda.synchronize()
+            step_ms.append(e[0].elapsed_time(e[3]))
+            parts.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])))
+        barrier()
+        launches = int(lib.ssv_launch_count(0))
+        m1.check()
+        total_ms = max_over_ranks(sum(step_ms))
+        # ---- end-to-end arm: host buffers in, host buffers out, through ssv_synthesize_host
+        e2e_s = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            syn.synthesize_host(ids_np, spk_np, T)
+            e2e_s.append(time.perf_counter() - t0)
+        barrier()
+        e2e_total = max_over_ranks(sum(e2e_s))
+    clocks = clk.summary()
+
+    frames_total = world * B * T * args.steps
+    value = frames_total / (total_ms * 1e-3)
+    e2e_value = frames_total / e2e_total
+    te_ms, dec_ms, ssrn_ms = (statistics.mean(p[i] for p in parts) for i in range(3))
+
+    peaks = measured_peaks()
+    dec_bytes = T * (DECODE_WEIGHT_BYTES + B * DECODE_STATE_BYTES_PER_UTT)
+    dec_gbs = dec_bytes / (dec_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get("decode_kernel_dram_bytes_per_launch")
+    ssrn_tflops = B * T * SSRN_FLOP_PER_FRAME / (ssrn_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32" if args.ssrn_precision == "fp32" else "fp32 Text2Mel + bf16 SSRN", "data": "synthetic",
+        "config": config_dict(args, B),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(syn.h2d_bytes),
+                "d2h_bytes_per_step": int(syn.d2h_bytes), "ms_per_step": 1e3 * e2e_total / args.steps,
+                "api": "ssv_synthesize_host (C ABI, pinned host buffers)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "phases_ms": {"text_encoder+begin": te_ms, "decode": dec_ms, "ssrn": ssrn_ms},
+        "roofline": {"kernel": "decode_kernel (persistent incremental Text2Mel decode)", "bound": "hbm",
+                     "achieved": dec_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm"],
+                     "traffic": traffic, "peak_source": peaks["source"],
+                     "algorithmic_bytes_per_launch": dec_bytes, "us_per_frame": 1e3 * dec_ms / T},
+        "roofline_ssrn": {"bound": "tensor", "achieved": ssrn_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                          "frac": ssrn_tflops / peaks["bf16_sustained"], "precision": args.ssrn_precision},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        nb = max(1, min(args.cpu_sample, B))
+        cpu_reference_step(sd1, sd2, ids_np[:nb], spk_np[:nb], 8)
+        sec, olin = cpu_reference_step(sd1, sd2, ids_np[:nb], spk_np[:nb], T)
+        got = syn.synthesize_host(ids_np, spk_np, T)["lin"][:nb]
+        line["cpu_baseline"] = {
+            "value": nb * T / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nb} of the {B} utterances, all {T} frames, reference re-encoding AR loop + SSRN (oracle port, torch CPU fp32)",
+            "max_abs_err_vs_gpu_lin": float(np.abs(got - olin.numpy()).max())}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

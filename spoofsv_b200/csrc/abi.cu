@@ -2,6 +2,7 @@
 #include "../../include/spoofsv_b200.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -230,6 +231,7 @@ struct ssv_decoder {
   int* pma_state;
   unsigned* bar;
   int* abort_flag;
+  long long* prof = nullptr;
   // per-batch state
   bool begun = false;
   int B = 0, N = 0, t_cap = 0, t = 0;
@@ -493,8 +495,9 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * H, &d->s1);
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * H, &d->s2);
   if (st == kOk) st = d->arena.alloc<int>(max_batch, &d->pma_state);
-  if (st == kOk) st = d->arena.alloc<unsigned>(1, &d->bar);
+  if (st == kOk) st = d->arena.alloc<unsigned>(DEC_MAX_GRID, &d->bar);
   if (st == kOk) st = d->arena.alloc<int>(1, &d->abort_flag);
+  if (st == kOk && getenv("SSV_DECODE_PROF")) st = d->arena.alloc<long long>((size_t)DEC_MAX_GRID * 8, &d->prof);
   if (st != kOk) { delete d; return st; }
   cudaMemset(d->abort_flag, 0, sizeof(int));
   *out = d;
@@ -552,9 +555,27 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.RG = 1;
   p.bar_counter = d->bar;
   p.abort_flag = d->abort_flag;
+  p.prof = d->prof;
   const int sms = device_sm_count();
   SSV_CHECK(sms > 0, "decoder: no CUDA device");
+  if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 8, s));
   SSV_TRY(launch_decode(p, sms, s));
+  if (d->prof) {   // development aid: per-phase SM cycles, mean / max over CTAs, per stage
+    SSV_CUDA(cudaStreamSynchronize(s));
+    std::vector<long long> h((size_t)DEC_MAX_GRID * 8);
+    SSV_CUDA(cudaMemcpy(h.data(), d->prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    const char* nm[7] = {"loop-top", "arrive+prefetch-issue", "barrier-wait", "prologue", "cp.async-wait+sync", "gemv", "tail-sync"};
+    fprintf(stderr, "[decode prof] B=%d steps=%d (cycles per stage: mean / max over CTAs)\n", d->B, n_steps);
+    for (int i = 0; i < 7; ++i) {
+      double sum = 0, mx = 0; int cnt = 0;
+      for (int c = 0; c < sms; ++c) {
+        if (h[(size_t)c * 8 + 7] == 0) continue;
+        const double v = (double)h[(size_t)c * 8 + i] / (double)h[(size_t)c * 8 + 7];
+        sum += v; mx = v > mx ? v : mx; ++cnt;
+      }
+      fprintf(stderr, "  %-24s %9.0f / %9.0f\n", nm[i], cnt ? sum / cnt : 0.0, mx);
+    }
+  }
   d->t += n_steps;
   return kOk;
 }

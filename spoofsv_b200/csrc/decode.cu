@@ -21,20 +21,27 @@ namespace ssv {
 
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 512;
 constexpr int NW = NT / 32;
 constexpr int HD = 256;              // hidden width (validated on the host)
 constexpr int NE = HD / 32;          // elements per lane of a hidden vector
+constexpr int KMAX = DEC_XS_LD;      // longest GEMV reduction (3 taps x 256)
 constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_u32(unsigned* p) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -55,25 +62,38 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
   return fmaf(a.w, b.w, acc);
 }
 
-// Grid-wide barrier on a monotonically increasing counter.  Returns false on timeout/abort.
-__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned target, int* abort_flag, int* s_abort) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    red_release_u32(counter);
+// Barrier among the `members` CTAs of one row group: every CTA publishes the generation it has
+// finished in its own flag word (plain release store -- no atomics to serialise in L2) and ONE warp
+// polls all member flags with coalesced relaxed loads (<= 5 cache lines per round; a thread-per-flag
+// poll issues ~150x the L2 requests and delays the very stores it waits for).
+__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void group_arrive(int* flags, int my_index, int gen) {
+  // caller has just executed __syncthreads(): every store of this CTA precedes the release
+  if (threadIdx.x == 0) st_release_s32(flags + my_index, gen);
+}
+__device__ __forceinline__ bool group_wait(int* flags, int members, int gen, int* abort_flag) {
+  int bad = 0;
+  if (threadIdx.x < 32) {
     const long long t0 = clock64();
-    int bad = 0;
-    while (ld_acquire_u32(counter) < target) {
-      if (*reinterpret_cast<volatile int*>(abort_flag) != 0) { bad = 1; break; }
-      if (clock64() - t0 > SPIN_LIMIT) {
-        atomicExch(abort_flag, 2);
-        bad = 1;
-        break;
+    unsigned spins = 0;
+    for (;;) {
+      int ok = 1;
+      for (int i = threadIdx.x; i < members; i += 32) ok &= ld_relaxed_s32(flags + i) >= gen;
+      if (__all_sync(0xffffffffu, ok)) break;
+      if ((++spins & 1023u) == 0) {
+        if (clock64() - t0 > SPIN_LIMIT) atomicExch(abort_flag, 2);
+        if (*reinterpret_cast<volatile int*>(abort_flag) != 0) { bad = 1; break; }
       }
     }
-    *s_abort = bad;
+    // acquire: re-read the (now final) flags with acquire semantics so the data loads that follow
+    // the CTA barrier are ordered after them; no MEMBAR that would drain the in-flight prefetch
+    for (int i = threadIdx.x; i < members; i += 32) (void)ld_acquire_s32(flags + i);
   }
-  __syncthreads();
-  return *s_abort == 0;
+  return __syncthreads_or(bad) == 0;
 }
 
 // Sum V per-lane values across the warp; lane L ends up holding the total of value index
@@ -107,8 +127,7 @@ __device__ __forceinline__ int fold_index(int lane) {
 }
 template <int V>
 __device__ __forceinline__ bool fold_writer(int lane) {
-  // after folding log2(V) levels the remaining low bits are replicas
-  constexpr int rep = 32 / V;
+  constexpr int rep = 32 / V;      // after log2(V) folding levels the low lane bits hold replicas
   return (lane & (rep - 1)) == 0;
 }
 
@@ -136,92 +155,129 @@ __device__ __forceinline__ void final_row(const DecParams& p, const float* raw_r
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int f = lane + 32 * i;
-    y[i] = f < p.F ? sigmoidf_((v[i] - mean) * rstd * p.fin_g[f] + p.fin_b[f]) : 0.f;
+    y[i] = f < p.F ? sigmoidf_((v[i] - mean) * rstd * __ldg(p.fin_g + f) + __ldg(p.fin_b + f)) : 0.f;
   }
 }
 
-template <int ROWS>
+// ROWS: utterances per row group.  RC: rows per GEMV task (ROWS / RC warps share a column pair).
+template <int ROWS, int RC>
 __global__ void __launch_bounds__(NT, 1) decode_kernel(const DecParams p) {
-  extern __shared__ __align__(16) float xs[];   // [ROWS][DEC_XS_LD]
+  constexpr int CHUNKS = ROWS / RC;           // row chunks per column pair
+  constexpr int PAIRS = NW / CHUNKS;          // column pairs per CTA per stage
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                            // [ROWS][DEC_XS_LD]   stage input rows (taps | current)
+  float* ws = smem + ROWS * DEC_XS_LD;         // [2][PAIRS][KMAX]    weights of this CTA's column pairs
+  float* ps = ws + 2 * PAIRS * KMAX;           // [4][HD]: g1 b1 g2 b2 of the prologue
   __shared__ int pma_s[ROWS];
-  __shared__ int s_abort;
+  __shared__ DecStage stab[DEC_STAGES];        // stage table (global copies sit behind an L1 that every
+                                               // acquire load invalidates)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x;
   const int rg = blockIdx.x % p.RG;
   const int slot_cta = blockIdx.x / p.RG;
   const int Gr = G / p.RG;
-  const bool active = slot_cta < Gr;
+  if (slot_cta >= Gr) return;                  // leftover CTAs take no part (barriers are per row group)
   const int row0 = rg * ROWS;
   const int nrows = min(ROWS, p.B - row0);
-  const bool designated = active && slot_cta == 0;
+  const bool designated = slot_cta == 0;
+  int* flags = reinterpret_cast<int*>(p.bar_counter) + rg * Gr;
 
   for (int i = tid; i < ROWS * DEC_XS_LD; i += NT) xs[i] = 0.f;
+  for (int i = tid; i < (int)(DEC_STAGES * sizeof(DecStage) / sizeof(int)); i += NT)
+    reinterpret_cast<int*>(stab)[i] = reinterpret_cast<const int*>(p.stages)[i];
   if (tid < ROWS) {
     int v = 0;
     if (tid < nrows) v = p.pma_in ? (int)p.pma_in[row0 + tid] : p.pma_state[row0 + tid];
     pma_s[tid] = max(0, min(v, p.N - 1));
   }
-  if (tid == 0) s_abort = 0;
   __syncthreads();
 
+  long long prof_last = 0;
+  long long prof_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const bool prof_on = p.prof != nullptr && tid == 0;
+  if (prof_on) prof_last = clock64();
+#define PROF_T(i)                                  \
+  if (prof_on) {                                   \
+    const long long now_ = clock64();              \
+    prof_acc[i] += now_ - prof_last;               \
+    prof_last = now_;                              \
+  }
   const int total = p.n_steps * DEC_STAGES + 1;
   const size_t raw_stage = (size_t)p.B * DEC_RAW_LD;
   const size_t hist_buf = (size_t)p.B * p.t_cap * HD;
+  const int pair_local = warp / CHUNKS;
+  const int chunk = warp % CHUNKS;
 
   for (int gs = 0; gs < total; ++gs) {
     const bool final_stage = gs == total - 1;
     const int step = gs / DEC_STAGES;
     const int s = final_stage ? 0 : gs - step * DEC_STAGES;
     const int t = p.t_start + step;           // for the final stage: t == t_last + 1
-    const DecStage st = p.stages[s];
-    const int K = st.ntaps * st.k_seg;
+    const DecStage* sp = stab + s;
+    const int n = sp->n, k_seg = sp->k_seg, ntaps = sp->ntaps, dil = sp->dil;
+    const int K = ntaps * k_seg;
+    const int half = n / 2;
+    const int ppc = min(PAIRS, (half + Gr - 1) / Gr);     // column pairs this stage gives each CTA
+    const int pair0 = slot_cta * ppc;
+    PROF_T(0);
 
-    // ---- 1. prefetch (independent of the previous stage): weights -> registers, old taps -> smem
-    const int task = slot_cta * NW + warp;
-    const bool has_task = active && !final_stage && task < st.n / 2;
-    float4 w0[6], w1[6];
-    if (has_task) {
-      const float* wa = st.W + (size_t)task * K;
-      const float* wb = st.W + (size_t)(task + st.n / 2) * K;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int k = lane * 4 + 128 * i;
-        if (k < K) {
-          w0[i] = __ldg(reinterpret_cast<const float4*>(wa + k));
-          w1[i] = __ldg(reinterpret_cast<const float4*>(wb + k));
-        } else {
-          w0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          w1[i] = w0[i];
+    // ---- 0. publish completion of the previous stage BEFORE starting new memory traffic
+    if (gs > 0) group_arrive(flags, slot_cta, gs);
+
+    // ---- 1. prefetch (independent of the previous stage): weights and old taps -> smem (cp.async)
+    if (!final_stage) {
+      const float* Wg = sp->W;
+      const int k4 = K / 4;
+      for (int row = warp; row < 2 * ppc; row += NW) {       // row = h * ppc + pr
+        const int h = row >= ppc ? 1 : 0;
+        const int pr = row - h * ppc;
+        const int col = pair0 + pr;
+        const bool ok = col < half;
+        const float* src = ok ? Wg + (size_t)(col + h * half) * K : Wg;
+        float* dst = ws + (h * PAIRS + pr) * KMAX;
+        for (int c4 = lane; c4 < k4; c4 += 32) cp_async16(dst + c4 * 4, src + (ok ? c4 * 4 : 0), ok);
+      }
+      if (ntaps == 3) {
+        const float* hb = p.hist + (size_t)sp->hist_in * hist_buf;
+        for (int rj = warp; rj < nrows * 2; rj += NW) {
+          const int r = rj >> 1, j = rj & 1;
+          const int tt = t - (2 - j) * dil;
+          const bool ok = tt >= 0;
+          const float* src = ok ? hb + ((size_t)(row0 + r) * p.t_cap + tt) * HD : hb;
+          float* dst = xs + r * DEC_XS_LD + j * HD;
+          for (int c4 = lane; c4 < HD / 4; c4 += 32) cp_async16(dst + c4 * 4, src + (ok ? c4 * 4 : 0), ok);
         }
       }
-    }
-    if (active && !final_stage && st.ntaps == 3) {
-      const float* hb = p.hist + (size_t)st.hist_in * hist_buf;
-      for (int i = tid; i < nrows * 2 * (HD / 4); i += NT) {
-        const int c4 = i % (HD / 4);
-        const int j = (i / (HD / 4)) & 1;
-        const int r = i / (2 * (HD / 4));
-        const int tt = t - (2 - j) * st.dil;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tt >= 0) v = __ldcg(reinterpret_cast<const float4*>(hb + ((size_t)(row0 + r) * p.t_cap + tt) * HD) + c4);
-        *reinterpret_cast<float4*>(xs + r * DEC_XS_LD + j * HD + c4 * 4) = v;
+      // LayerNorm affine parameters the prologue of this stage applies
+      if (tid < 4 * (HD / 4)) {
+        const int which = tid / (HD / 4), c4 = tid % (HD / 4);
+        const float* src = which == 0 ? sp->g1 : which == 1 ? sp->b1 : which == 2 ? sp->g2 : sp->b2;
+        if (src != nullptr) cp_async16(ps + which * HD + c4 * 4, src + c4 * 4, true);
       }
     }
 
-    // ---- 2. wait for the previous stage of every CTA
+    PROF_T(1);
     if (gs > 0) {
-      if (!grid_barrier(p.bar_counter, (unsigned)G * (unsigned)gs, p.abort_flag, &s_abort)) return;
+      if (!group_wait(flags, Gr, gs, p.abort_flag)) return;
     }
-    if (!active) continue;
+    PROF_T(2);
 
     // ---- 3. prologue: u_t for my rows -> xs[r][(ntaps-1)*k_seg ...]
     const int prev = (s + DEC_STAGES - 1) % DEC_STAGES;
     const float* rawp = p.raw + (size_t)prev * raw_stage;
-    const int pro = final_stage ? PRO_X : st.pro;
+    const int pro = final_stage ? PRO_X : sp->pro;
+    const float* g1 = ps;
+    const float* b1 = ps + HD;
+    const float* g2 = ps + 2 * HD;
+    const float* b2 = ps + 3 * HD;
+    if (pro != PRO_X) {            // the prologue reads the cp.async'ed LayerNorm parameters
+      cp_async_wait_all();
+      __syncthreads();
+    }
     for (int r = warp; r < nrows; r += NW) {
       const int b = row0 + r;
-      float* xrow = xs + r * DEC_XS_LD + (st.ntaps - 1) * st.k_seg;
+      float* xrow = xs + r * DEC_XS_LD + (ntaps - 1) * k_seg;
       if (pro == PRO_X) {
         float y[3];
         if (gs == 0) {
@@ -268,13 +324,13 @@ __global__ void __launch_bounds__(NT, 1) decode_kernel(const DecParams p) {
 #pragma unroll
         for (int i = 0; i < NE; ++i) {
           const int c = lane + 32 * i;
-          float o = (v[i] - mean) * rstd * st.g1[c] + st.b1[c];
+          float o = (v[i] - mean) * rstd * g1[c] + b1[c];
           if (pro == PRO_LN_RELU) o = fmaxf(o, 0.f);
           xrow[c] = o;
         }
       } else {   // PRO_HWY / PRO_ATT
         const float* R = rawp + (size_t)b * DEC_RAW_LD;
-        const float* res = p.hist + (size_t)st.res_hist * hist_buf + ((size_t)b * p.t_cap + t) * HD;
+        const float* res = p.hist + (size_t)sp->res_hist * hist_buf + ((size_t)b * p.t_cap + t) * HD;
         float h1[NE], h2[NE], xr[NE];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -302,8 +358,8 @@ __global__ void __launch_bounds__(NT, 1) decode_kernel(const DecParams p) {
 #pragma unroll
         for (int i = 0; i < NE; ++i) {
           const int c = lane + 32 * i;
-          const float a = (h1[i] - m1) * r1 * st.g1[c] + st.b1[c];
-          const float bb = (h2[i] - m2) * r2 * st.g2[c] + st.b2[c];
+          const float a = (h1[i] - m1) * r1 * g1[c] + b1[c];
+          const float bb = (h2[i] - m2) * r2 * g2[c] + b2[c];
           const float g = sigmoidf_(a);
           u[i] = g * bb + (1.0f - g) * xr[i];
         }
@@ -364,62 +420,93 @@ __global__ void __launch_bounds__(NT, 1) decode_kernel(const DecParams p) {
         }
       }
       // the designated CTA of the row group publishes the stage input to its history buffer
-      if (!final_stage && designated && st.hist_in >= 0) {
+      if (!final_stage && designated && sp->hist_in >= 0) {
         __syncwarp();
-        float* hrow = p.hist + (size_t)st.hist_in * hist_buf + ((size_t)b * p.t_cap + t) * HD;
+        float* hrow = p.hist + (size_t)sp->hist_in * hist_buf + ((size_t)b * p.t_cap + t) * HD;
 #pragma unroll
         for (int i = 0; i < NE; ++i) hrow[lane + 32 * i] = xrow[lane + 32 * i];
       }
     }
     if (final_stage) break;
+    PROF_T(3);
+    cp_async_wait_all();
     __syncthreads();
+    PROF_T(4);
 
-    // ---- 4. GEMV: two output columns per warp over all rows of the group
-    if (has_task) {
-      float acc[2 * ROWS];
+    // ---- 4. GEMV: one column pair x RC rows per warp
+    const int col = pair0 + pair_local;
+    if (pair_local < ppc && col < half) {
+      float4 w0[6], w1[6];
+      const float* wa = ws + pair_local * KMAX;
+      const float* wb = ws + (PAIRS + pair_local) * KMAX;
 #pragma unroll
-      for (int i = 0; i < 2 * ROWS; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 6; ++i) {
+        const int k = lane * 4 + 128 * i;
+        if (k < K) {
+          w0[i] = *reinterpret_cast<const float4*>(wa + k);
+          w1[i] = *reinterpret_cast<const float4*>(wb + k);
+        } else {
+          w0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          w1[i] = w0[i];
+        }
+      }
+      // the lane that will own output (row r, column oc) after the fold fetches its bias now,
+      // so the load's L2 latency hides behind the FMA loop
+      const int vi = fold_index<2 * RC>(lane);
+      const int r_out = chunk * RC + vi % RC, hsel = vi / RC;
+      const int oc = col + hsel * half;
+      const bool writer = fold_writer<2 * RC>(lane) && r_out < nrows;
+      float bias_v = 0.f;
+      if (writer) {
+        bias_v = __ldg(sp->bias + oc);
+        if (sp->bias_b == 1) bias_v += __ldg(p.s1 + (size_t)(row0 + r_out) * HD + oc);
+        else if (sp->bias_b == 2) bias_v += __ldg(p.s2 + (size_t)(row0 + r_out) * HD + oc);
+      }
+      float acc[2 * RC];
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        const float* xr = xs + r * DEC_XS_LD;
+      for (int i = 0; i < 2 * RC; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        const float* xr = xs + (chunk * RC + r) * DEC_XS_LD;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const int k = lane * 4 + 128 * i;
           if (k < K) {
             const float4 x = *reinterpret_cast<const float4*>(xr + k);
             acc[r] = dot4(w0[i], x, acc[r]);
-            acc[ROWS + r] = dot4(w1[i], x, acc[ROWS + r]);
+            acc[RC + r] = dot4(w1[i], x, acc[RC + r]);
           }
         }
       }
-      const float tot = fold_reduce<2 * ROWS>(acc, lane);
-      const int vi = fold_index<2 * ROWS>(lane);
-      const int r = vi % ROWS, half = vi / ROWS;
-      if (fold_writer<2 * ROWS>(lane) && r < nrows) {
-        const int b = row0 + r;
-        const int col = task + half * (st.n / 2);
-        float v = tot + st.bias[col];
-        if (st.bias_b == 1) v += p.s1[(size_t)b * HD + col];
-        else if (st.bias_b == 2) v += p.s2[(size_t)b * HD + col];
-        __stcg(p.raw + (size_t)s * raw_stage + (size_t)b * DEC_RAW_LD + col, v);
-      }
+      const float tot = fold_reduce<2 * RC>(acc, lane);
+      if (writer)
+        __stcg(p.raw + (size_t)s * raw_stage + (size_t)(row0 + r_out) * DEC_RAW_LD + oc, tot + bias_v);
     }
-    // xs is rewritten by the next stage's tap prefetch only after every warp passed this point
+    // xs / ws are rewritten by the next stage's prefetch only after every warp passed this point
+    PROF_T(5);
     __syncthreads();
+    PROF_T(6);
   }
+  if (prof_on) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 8 + i] = prof_acc[i];
+    p.prof[(size_t)blockIdx.x * 8 + 7] = total;
+  }
+#undef PROF_T
 }
 
-template <int ROWS>
+template <int ROWS, int RC>
 int launch_rows(const DecParams& p, int grid, cudaStream_t s) {
-  constexpr size_t smem = (size_t)ROWS * DEC_XS_LD * sizeof(float);
+  constexpr int PAIRS = NW / (ROWS / RC);
+  constexpr size_t smem = ((size_t)ROWS * DEC_XS_LD + 2 * (size_t)PAIRS * KMAX + 5 * HD) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    SSV_CUDA(cudaFuncSetAttribute(decode_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSV_CUDA(cudaFuncSetAttribute(decode_kernel<ROWS, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   DecParams pl = p;
   void* args[] = {&pl};
-  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_kernel<ROWS>, dim3(grid), dim3(NT), args, smem, s));
+  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_kernel<ROWS, RC>, dim3(grid), dim3(NT), args, smem, s));
   ++g_launches;
   return kOk;
 }
@@ -430,13 +517,15 @@ int launch_decode(const DecParams& p, int sm_count, cudaStream_t s) {
   SSV_CHECK(p.H == HD, "decode: hidden_dim must be %d", HD);
   SSV_CHECK(p.F <= 96 && p.F % 4 == 0, "decode: freq_bins must be <= 96 and a multiple of 4");
   SSV_CHECK(p.B >= 1 && p.n_steps >= 1, "decode: empty launch");
-  SSV_CUDA(cudaMemsetAsync(p.bar_counter, 0, sizeof(unsigned), s));
+  SSV_CHECK(sm_count <= DEC_MAX_GRID, "decode: more than %d SMs", DEC_MAX_GRID);
+  // per-CTA barrier flags (generation numbers restart at 1 every launch)
+  SSV_CUDA(cudaMemsetAsync(p.bar_counter, 0, sizeof(int) * DEC_MAX_GRID, s));
   DecParams q = p;
-  if (p.B == 1) { q.RG = 1; return launch_rows<1>(q, sm_count, s); }
-  if (p.B <= 4) { q.RG = 1; return launch_rows<4>(q, sm_count, s); }
+  if (p.B == 1) { q.RG = 1; return launch_rows<1, 1>(q, sm_count, s); }
+  if (p.B <= 4) { q.RG = 1; return launch_rows<4, 4>(q, sm_count, s); }
   q.RG = (p.B + 15) / 16;
   SSV_CHECK(q.RG <= sm_count, "decode: batch too large for one launch");
-  return launch_rows<16>(q, sm_count, s);
+  return launch_rows<16, 8>(q, sm_count, s);
 }
 
 }  // namespace ssv

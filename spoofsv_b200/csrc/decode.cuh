@@ -33,6 +33,7 @@ constexpr int DEC_STAGES = 24;
 constexpr int DEC_HIST = 16;
 constexpr int DEC_RAW_LD = 512;
 constexpr int DEC_XS_LD = 768;
+constexpr int DEC_MAX_GRID = 1024;   // barrier flag words
 
 struct DecParams {
   const DecStage* stages;       // [DEC_STAGES]
@@ -50,8 +51,9 @@ struct DecParams {
   int B, N, t_cap, F, H;
   int t_start, n_steps;
   int RG;                       // row groups
-  unsigned* bar_counter;
+  unsigned* bar_counter;      // [DEC_MAX_GRID] per-CTA barrier flags
   int* abort_flag;
+  long long* prof;              // optional [grid][8] phase cycle counters (SSV_DECODE_PROF=1), else nullptr
 };
 
 int launch_decode(const DecParams& p, int sm_count, cudaStream_t s);
