@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "decode.cuh"
 
 namespace ssv {
@@ -160,6 +161,47 @@ int run_conv(const ConvPack& c, int epi, int dil, int causal, const float* X, in
   return launch_conv_f32(a, s);
 }
 
+
+// ---- tensor-core (bf16) packing: reuses the fp32 pack's bias / LayerNorm copies ----
+int tc_pack_layer(Arena& ar, const ParamMap& pm, const std::string& wname, const ConvPack& c, int rows, int cin, int k,
+                  TcLayer* L, cudaStream_t s) {
+  const float* w;
+  SSV_TRY(pm.get(wname, (int64_t)rows * cin * k, &w));
+  L->rows = rows;
+  L->cin = cin;
+  L->cin_p = round_up(cin, TC_BK);
+  L->k = k;
+  L->bias = c.bias;
+  L->g1 = c.g1; L->b1 = c.b1; L->g2 = c.g2; L->b2 = c.b2;
+  SSV_TRY(ar.alloc<__nv_bfloat16>((size_t)L->rows_pad * k * L->cin_p, &L->W));
+  return tc_pack_weights(w, rows, cin, k, L->cin_p, L->rows_pad, L->W, s);
+}
+
+// column split of a layer over accumulator blocks / cluster ranks
+void tc_shape_highway(TcLayer* L, int d) {          // rows = 2d
+  L->rows_pad = 2 * d;
+  L->n_real = d;
+  L->n0 = L->n1 = 256;
+  L->cluster_n = d / 256;
+  L->w0_base = 0; L->w0_rank = 256;
+  L->w1_base = d; L->w1_rank = 256;
+}
+void tc_shape_plain(TcLayer* L, int n) {            // LN-only / no-epilogue layer with n output columns
+  L->n_real = n;
+  if (n <= 256) {
+    L->rows_pad = round_up(n, 16); L->cluster_n = 1; L->n0 = L->rows_pad; L->n1 = 0;
+    L->w0_base = 0; L->w0_rank = 0; L->w1_base = 0; L->w1_rank = 0;
+  } else if (n <= 512) {
+    L->rows_pad = round_up(n, 32); L->cluster_n = 1; L->n0 = L->rows_pad / 2; L->n1 = L->rows_pad / 2;
+    L->w0_base = 0; L->w0_rank = 0; L->w1_base = L->n0; L->w1_rank = 0;
+  } else {                                           // 513..1024: two CTAs, each n_loc columns in blocks (256, rest)
+    const int n_loc = round_up((n + 1) / 2, 16);
+    L->rows_pad = 2 * n_loc; L->cluster_n = 2;
+    L->n0 = n_loc > 256 ? 256 : n_loc; L->n1 = n_loc - L->n0;
+    L->w0_base = 0; L->w0_rank = n_loc; L->w1_base = L->n0; L->w1_rank = n_loc;
+  }
+}
+
 cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 int device_sm_count() {
@@ -249,7 +291,15 @@ struct ssv_ssrn {
   Arena arena;
   int F, O, D;
   ConvPack conv1, hc1, hc2, dc1, u1h1, u1h2, dc2, u2h1, u2h2, conv2, hc3, hc4, conv3, conv4, conv5, conv6;
+  TcLayer t_conv1, t_hc1, t_hc2, t_dc1, t_u1h1, t_u1h2, t_dc2, t_u2h1, t_u2h2, t_conv2, t_hc3, t_hc4, t_conv3, t_conv4,
+      t_conv5, t_conv6;
   Workspace ws;
+  __nv_bfloat16* tws[2] = {nullptr, nullptr};
+  size_t tws_elems = 0;
+  ~ssv_ssrn() {
+    for (int i = 0; i < 2; ++i)
+      if (tws[i]) cudaFree(tws[i]);
+  }
 };
 
 extern "C" {
@@ -301,10 +351,21 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
   SSV_TRY(ar.alloc<float>((size_t)B * T * d, &xin));
   SSV_TRY(ar.alloc<float>((size_t)B * T * d, &yout));
   SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
-  SSV_CHECK(precision == SSV_PREC_FP32, "highway_conv: precision %d not implemented", precision);
-  SSV_TRY(run_conv(c, EPI_HIGHWAY, dilation, causal, xin, d, T, B, yout, d, s));
+  if (precision == SSV_PREC_BF16) {
+    TcLayer L;
+    tc_shape_highway(&L, d);
+    SSV_TRY(tc_pack_layer(ar, pm, "conv.weight", c, 2 * d, d, k, &L, s));
+    __nv_bfloat16* xb;
+    SSV_TRY(ar.alloc<__nv_bfloat16>((size_t)B * T * d, &xb));
+    SSV_TRY(launch_cast_f32_to_bf16(xin, xb, (size_t)B * T * d, s));
+    SSV_TRY(tc_launch(L, EPI_HIGHWAY, dilation, causal, xb, d, T, B, yout, d, true, s));
+  } else {
+    SSV_CHECK(precision == SSV_PREC_FP32, "highway_conv: unknown precision %d", precision);
+    SSV_TRY(run_conv(c, EPI_HIGHWAY, dilation, causal, xin, d, T, B, yout, d, s));
+  }
   SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
   SSV_CUDA(cudaStreamSynchronize(s));   // arena is freed on return
+  if (precision == SSV_PREC_BF16) SSV_TRY(tc_check_error());
   return kOk;
 }
 
@@ -652,6 +713,40 @@ int ssv_ssrn_create(const char* const* names, const float* const* dev_ptrs, cons
   S_TRY(pack_conv_ln(m->arena, pm, "conv4", "ln4", O, O, &m->conv4, s));
   S_TRY(pack_conv_ln(m->arena, pm, "conv5", "ln5", O, O, &m->conv5, s));
   S_TRY(pack_conv_ln(m->arena, pm, "conv6", "ln6", O, O, &m->conv6, s));
+  {  // bf16 copies for the tcgen05 path
+    auto hw = [&](const char* name, const ConvPack& c, int d, TcLayer* L) -> int {
+      tc_shape_highway(L, d);
+      return tc_pack_layer(m->arena, pm, std::string(name) + ".conv.weight", c, 2 * d, d, 3, L, s);
+    };
+    auto pl = [&](const char* name, const ConvPack& c, int n, int cin, TcLayer* L) -> int {
+      tc_shape_plain(L, n);
+      return tc_pack_layer(m->arena, pm, std::string(name) + ".weight", c, n, cin, 1, L, s);
+    };
+    auto dc = [&](const char* name, const ConvPack& c, TcLayer* L) -> int {
+      const float* w;
+      SSV_TRY(pm.get(std::string(name) + ".weight", (int64_t)D * D * 2, &w));
+      tc_shape_plain(L, 2 * D);
+      L->rows = 2 * D; L->cin = D; L->cin_p = D; L->k = 1; L->bias = c.bias;
+      SSV_TRY(m->arena.alloc<__nv_bfloat16>((size_t)2 * D * D, &L->W));
+      return tc_pack_deconv(w, D, D, L->W, s);
+    };
+    S_TRY(pl("conv1", m->conv1, D, freq_bins, &m->t_conv1));
+    S_TRY(hw("hc1", m->hc1, D, &m->t_hc1));
+    S_TRY(hw("hc2", m->hc2, D, &m->t_hc2));
+    S_TRY(dc("ups1.deconv", m->dc1, &m->t_dc1));
+    S_TRY(hw("ups1.hc1", m->u1h1, D, &m->t_u1h1));
+    S_TRY(hw("ups1.hc2", m->u1h2, D, &m->t_u1h2));
+    S_TRY(dc("ups2.deconv", m->dc2, &m->t_dc2));
+    S_TRY(hw("ups2.hc1", m->u2h1, D, &m->t_u2h1));
+    S_TRY(hw("ups2.hc2", m->u2h2, D, &m->t_u2h2));
+    S_TRY(pl("conv2", m->conv2, 2 * D, D, &m->t_conv2));
+    S_TRY(hw("hc3", m->hc3, 2 * D, &m->t_hc3));
+    S_TRY(hw("hc4", m->hc4, 2 * D, &m->t_hc4));
+    S_TRY(pl("conv3", m->conv3, O, 2 * D, &m->t_conv3));
+    S_TRY(pl("conv4", m->conv4, O, O, &m->t_conv4));
+    S_TRY(pl("conv5", m->conv5, O, O, &m->t_conv5));
+    S_TRY(pl("conv6", m->conv6, O, O, &m->t_conv6));
+  }
 #undef S_TRY
   if (st == kOk && cudaStreamSynchronize(s) != cudaSuccess) {
     set_error("ssrn_create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -700,12 +795,57 @@ static int ssrn_fwd_f32(ssv_ssrn* m, const float* mel, long sb, long sf, long st
   return kOk;
 }
 
+static int ssrn_fwd_bf16(ssv_ssrn* m, const float* mel, long sb, long sf, long st_, int B, int T, float* out,
+                         cudaStream_t s) {
+  const int D = m->D, O = m->O;
+  const int o_ld = round_up(O, 64);
+  const int f_ld = round_up(m->F, 64);
+  const size_t need = (size_t)B * 4 * T * o_ld;
+  SSV_TRY(m->ws.ensure(need));
+  if (need > m->tws_elems) {
+    for (int i = 0; i < 2; ++i) {
+      if (m->tws[i]) cudaFree(m->tws[i]);
+      m->tws[i] = nullptr;
+      if (cudaMalloc((void**)&m->tws[i], need * sizeof(__nv_bfloat16) + 256) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("bf16 workspace cudaMalloc of %zu bytes failed", need * 2);
+        m->tws_elems = 0;
+        return kNoMem;
+      }
+    }
+    m->tws_elems = need;
+  }
+  __nv_bfloat16* P = m->tws[0];
+  __nv_bfloat16* Q = m->tws[1];
+  SSV_TRY(launch_transpose_in_bf16(mel, sb, sf, st_, B, m->F, T, P, f_ld, s));
+  SSV_TRY(tc_launch(m->t_conv1, EPI_LN, 1, 0, P, f_ld, T, B, Q, D, false, s));
+  SSV_TRY(tc_launch(m->t_hc1, EPI_HIGHWAY, 1, 0, Q, D, T, B, P, D, false, s));
+  SSV_TRY(tc_launch(m->t_hc2, EPI_HIGHWAY, 3, 0, P, D, T, B, Q, D, false, s));
+  SSV_TRY(tc_launch(m->t_dc1, EPI_NONE, 1, 0, Q, D, T, B, P, 2 * D, false, s));           // (B,T,2D) == (B,2T,D)
+  SSV_TRY(tc_launch(m->t_u1h1, EPI_HIGHWAY, 1, 0, P, D, 2 * T, B, Q, D, false, s));
+  SSV_TRY(tc_launch(m->t_u1h2, EPI_HIGHWAY, 3, 0, Q, D, 2 * T, B, P, D, false, s));
+  SSV_TRY(tc_launch(m->t_dc2, EPI_NONE, 1, 0, P, D, 2 * T, B, Q, 2 * D, false, s));
+  SSV_TRY(tc_launch(m->t_u2h1, EPI_HIGHWAY, 1, 0, Q, D, 4 * T, B, P, D, false, s));
+  SSV_TRY(tc_launch(m->t_u2h2, EPI_HIGHWAY, 3, 0, P, D, 4 * T, B, Q, D, false, s));
+  SSV_TRY(tc_launch(m->t_conv2, EPI_LN, 1, 0, Q, D, 4 * T, B, P, 2 * D, false, s));
+  SSV_TRY(tc_launch(m->t_hc3, EPI_HIGHWAY, 1, 0, P, 2 * D, 4 * T, B, Q, 2 * D, false, s));
+  SSV_TRY(tc_launch(m->t_hc4, EPI_HIGHWAY, 1, 0, Q, 2 * D, 4 * T, B, P, 2 * D, false, s));
+  SSV_TRY(tc_launch(m->t_conv3, EPI_LN, 1, 0, P, 2 * D, 4 * T, B, Q, o_ld, false, s));
+  SSV_TRY(tc_launch(m->t_conv4, EPI_LN_RELU, 1, 0, Q, o_ld, 4 * T, B, P, o_ld, false, s));
+  SSV_TRY(tc_launch(m->t_conv5, EPI_LN_RELU, 1, 0, P, o_ld, 4 * T, B, Q, o_ld, false, s));
+  float* F32 = m->ws.buf[0];
+  SSV_TRY(tc_launch(m->t_conv6, EPI_LN_SIGMOID, 1, 0, Q, o_ld, 4 * T, B, F32, o_ld, true, s));
+  SSV_TRY(launch_transpose_out(F32, o_ld, B, O, 4 * T, out, s));
+  return kOk;
+}
+
 int ssv_ssrn_fwd(ssv_ssrn* m, const float* mel, long stride_b, long stride_f, long stride_t, int B, int T,
                  float* out, int precision, void* stream) {
   SSV_CHECK(m && mel && out, "ssrn_fwd: null pointer");
   SSV_CHECK(B > 0 && T > 0, "ssrn_fwd: empty input");
   cudaStream_t s = as_stream(stream);
   if (precision == SSV_PREC_FP32) return ssrn_fwd_f32(m, mel, stride_b, stride_f, stride_t, B, T, out, s);
+  if (precision == SSV_PREC_BF16) return ssrn_fwd_bf16(m, mel, stride_b, stride_f, stride_t, B, T, out, s);
   set_error("ssrn_fwd: unknown precision %d", precision);
   return kInval;
 }
@@ -749,7 +889,9 @@ int ssv_synthesize_host(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const int
   if (A_host) SSV_CUDA(cudaMemcpyAsync(A_host, d->h_A, sizeof(float) * (size_t)B * N * T, cudaMemcpyDeviceToHost, s));
   if (pma_traj_host)
     SSV_CUDA(cudaMemcpyAsync(pma_traj_host, d->h_traj, sizeof(long long) * (size_t)T * B, cudaMemcpyDeviceToHost, s));
-  return ssv_decoder_check(d, s);
+  SSV_TRY(ssv_decoder_check(d, s));
+  if (ssrn_precision == SSV_PREC_BF16) SSV_TRY(tc_check_error());
+  return kOk;
 }
 
 }  // extern "C"

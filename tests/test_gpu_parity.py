@@ -264,3 +264,57 @@ def test_synthesize_host_matches_module_path(cuda_models):
     assert np.array_equal(out["traj"], traj.cpu().numpy())
     assert np.array_equal(out["mel"], Y.cpu().numpy()) and np.array_equal(out["lin"], lin.cpu().numpy())
     assert np.array_equal(out["att"], A.cpu().numpy())
+
+
+# --------------------------------------------------------------------------- BF16 tensor-core (tcgen05) path
+BF16_TOL = 2e-2   # relative L2 (BASELINE.json north_star)
+
+
+def test_highway_conv_all_classes_bf16(golden_dir):
+    from spoofsv_b200.models import highwayConv
+    z = np.load(golden_dir / "highway_cases.npz")
+    for i, (d, k, dil, causal) in enumerate(z["cases"].tolist()):
+        hc = highwayConv(dimension=d, kernel_size=k, dilation=dil, causal=bool(causal))
+        hc.load_state_dict(W.highway_params(d, k, 100 + i), strict=True)
+        hc = hc.cuda().eval()
+        hc.precision = "bf16"
+        x = torch.randn((2, d, 45), generator=torch.Generator().manual_seed(200 + i))
+        y = hc(x.cuda())
+        assert _rel_l2(y, _t(z[f"y{i}"])) <= BF16_TOL, (d, k, dil, causal)
+
+
+@pytest.mark.parametrize("T", [1, 127, 128, 129, 300])
+def test_highway_conv_bf16_tile_edges(T):
+    """Rows beyond T inside the last 128-row tile, taps reaching outside [0, T) (TMA zero fill)."""
+    from spoofsv_b200.models import highwayConv
+    for (d, k, dil, causal) in [(256, 3, 27, 1), (256, 3, 3, 0), (512, 3, 1, 0)]:
+        p = W.highway_params(d, k, 6)
+        hc = highwayConv(d, k, dil, bool(causal))
+        hc.load_state_dict(p, strict=True)
+        hc.precision = "bf16"
+        x = torch.randn((3, d, T), generator=torch.Generator().manual_seed(T))
+        want = O.highway_conv(x, {"." + kk: v for kk, v in p.items()}, "", dil, bool(causal))
+        assert _rel_l2(hc.cuda()(x.cuda()), want) <= BF16_TOL, (d, k, dil, causal, T)
+
+
+def test_ssrn_bf16(golden_dir, cuda_models_k, cuda_models):
+    _, m2, _, _ = cuda_models_k
+    z = np.load(golden_dir / "ssrn_seed7.npz")
+    m2.precision = "bf16"
+    try:
+        lin = m2(_t(z["mel"]).cuda())
+    finally:
+        m2.precision = "fp32"
+    assert lin.shape == (2, 513, 148)
+    assert _rel_l2(lin, _t(z["lin"])) <= BF16_TOL
+    _, m2b, _, sd2 = cuda_models
+    mel = torch.rand((32, 80, 217), generator=torch.Generator().manual_seed(0)).cuda()
+    m2b.precision = "bf16"
+    try:
+        a = m2b(mel)
+        assert torch.equal(a, m2b(mel))
+    finally:
+        m2b.precision = "fp32"
+    ref = m2b(mel)
+    assert _rel_l2(a, ref) <= BF16_TOL
+    assert float(a.min()) >= 0 and float(a.max()) <= 1
