@@ -8,7 +8,7 @@
 namespace ssv {
 
 constexpr int TC_BM = 128;       // rows (time steps of one utterance) per CTA tile == UMMA M
-constexpr int TC_BK = 64;        // bf16 elements per k-block == one 128-byte swizzle row
+constexpr int TC_BK = 64;        // K padding granule (largest k-block: one 128-byte swizzle row)
 
 // Kernel argument block (passed as a __grid_constant__ parameter; holds the TMA descriptors).
 struct alignas(64) ConvTcArgs {
@@ -26,12 +26,16 @@ struct alignas(64) ConvTcArgs {
   int n_real;             // LayerNorm width (real output columns; d for a highway layer)
   int epi;                // Epilogue
   int nstages;
+  int bk;                 // k-block: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) bf16 elements
   const float* bias;      // [padded N] fp32, indexed by global column
   const float* g1; const float* b1; const float* g2; const float* b2;
   const __nv_bfloat16* Xres; long x_sb, x_st;     // residual input (highway), channels-last bf16
   void* Y; long y_sb, y_st;                       // output, channels-last (bf16 or fp32)
   int y_cols;             // columns to write per row (>= real columns: the tail is zero-filled)
   int out_fp32;
+  int stage_out;          // epilogue writes through a smem staging tile + coalesced copy-out
+  int stage_res;          // highway residual rows are copied to smem during the mainloop
+  long long* prof;        // optional per-CTA cycle counters (SSV_TC_PROF=1)
 };
 
 // Host-side description of one packed layer for the tensor-core path.
