@@ -625,11 +625,11 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
     SSV_CUDA(cudaStreamSynchronize(s));
     std::vector<long long> h((size_t)DEC_MAX_GRID * 8);
     SSV_CUDA(cudaMemcpy(h.data(), d->prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
-    const char* nm[7] = {"loop-top", "arrive+prefetch-issue", "barrier-wait", "prologue", "cp.async-wait+sync", "gemv", "tail-sync"};
+    const char* nm[7] = {"loop-top", "arm/arrive+prefetch-issue", "wait", "prologue", "cp.async-wait+sync", "gemv", "tail (sync / bulk-copy issue)"};
     fprintf(stderr, "[decode prof] B=%d steps=%d (cycles per stage: mean / max over CTAs)\n", d->B, n_steps);
     for (int i = 0; i < 7; ++i) {
       double sum = 0, mx = 0; int cnt = 0;
-      for (int c = 0; c < sms; ++c) {
+      for (int c = 0; c < DEC_MAX_GRID; ++c) {
         if (h[(size_t)c * 8 + 7] == 0) continue;
         const double v = (double)h[(size_t)c * 8 + i] / (double)h[(size_t)c * 8 + 7];
         sum += v; mx = v > mx ? v : mx; ++cnt;

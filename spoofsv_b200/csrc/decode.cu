@@ -17,6 +17,8 @@
 // Batch rows are split into row groups of <=16 utterances; CTAs are dealt round-robin to row groups.
 #include "decode.cuh"
 
+#include <cstdlib>
+
 namespace ssv {
 
 namespace {
@@ -514,6 +516,13 @@ int launch_rows(const DecParams& p, int grid, cudaStream_t s) {
 }  // namespace
 
 int launch_decode(const DecParams& p, int sm_count, cudaStream_t s) {
+  // default: the cluster kernel (decode_cluster.cu); SSV_DECODE_IMPL=grid selects this file's grid-barrier kernel
+  static int use_cluster = -1;
+  if (use_cluster < 0) {
+    const char* e = getenv("SSV_DECODE_IMPL");
+    use_cluster = (e && e[0] == 'g') ? 0 : (decode_cluster_capacity() > 0 ? 1 : 0);
+  }
+  if (use_cluster) return launch_decode_cluster(p, s);
   SSV_CHECK(p.H == HD, "decode: hidden_dim must be %d", HD);
   SSV_CHECK(p.F <= 96 && p.F % 4 == 0, "decode: freq_bins must be <= 96 and a multiple of 4");
   SSV_CHECK(p.B >= 1 && p.n_steps >= 1, "decode: empty launch");

@@ -57,6 +57,8 @@ struct DecParams {
 };
 
 int launch_decode(const DecParams& p, int sm_count, cudaStream_t s);
+int launch_decode_cluster(const DecParams& p, cudaStream_t s);     // decode_cluster.cu
+int decode_cluster_capacity();
 int decode_max_grid(int* out);
 
 }  // namespace ssv

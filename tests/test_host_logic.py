@@ -1,0 +1,86 @@
+"""CPU: host-side logic of the drivers -- text front-end, batching, utterance sharding (incl. a
+world_size-2 gloo run of the N>1 path)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ttsmodel_oracle as O
+from oracle import weights as W
+from spoofsv_b200 import text as T
+from spoofsv_b200.synth import Unit, corpus_units, plan_batches, shard_range
+
+
+def test_text2id_agrees_with_oracle_on_all_lines():
+    _, _, lines = W.load_fixtures()
+    enc = T.encode_lines(lines)
+    for s, ids in zip(lines, enc):
+        assert np.array_equal(ids, O.text2id(s))
+    assert T.vocab_len() == 34
+
+
+def test_pad_batch():
+    rows = [np.array([[3, 4, 1]]), np.array([[5, 1]])]
+    out = T.pad_batch(rows)
+    assert out.shape == (2, 3) and out.dtype == np.int64 and out[1].tolist() == [5, 1, 0]
+    assert T.pad_batch(rows, 58).shape == (2, 58)
+    with pytest.raises(ValueError):
+        T.pad_batch(rows, 2)
+
+
+def test_shard_range_partitions_exactly():
+    for n, w in [(77760, 8), (77760, 1), (10, 4), (3, 8), (0, 2)]:
+        spans = [shard_range(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert [hi - lo for lo, hi in (shard_range(77760, 8, r) for r in range(8))] == [9720] * 8
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_corpus_units_and_batches():
+    units = corpus_units(108, 720)
+    assert len(units) == 77760 and units[0] == Unit(0, 0) and units[720] == Unit(1, 0)
+    batches = plan_batches(units[:130], 64)
+    assert [len(b) for b in batches] == [64, 64, 2]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n_units, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(n_units, world, rank)
+    # what bench.py does across ranks: barrier, per-rank work, MAX-reduce of the time, SUM of units
+    dist.barrier()
+    mine = torch.zeros(n_units, dtype=torch.int64)
+    mine[lo:hi] = 1
+    dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([hi - lo], dtype=torch.int64)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        torch.save({"cover": mine, "tmax": t, "count": cnt}, os.path.join(out_dir, "r0.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    import torch.multiprocessing as mp
+    n_units = 1001
+    mp.spawn(_gloo_worker, args=(2, _free_port(), n_units, str(tmp_path)), nprocs=2, join=True)
+    r = torch.load(tmp_path / "r0.pt")
+    assert bool((r["cover"] == 1).all())          # every unit owned by exactly one rank, no collective on data
+    assert float(r["tmax"]) == 2.0 and int(r["count"]) == n_units
