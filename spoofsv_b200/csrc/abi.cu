@@ -261,6 +261,10 @@ struct ssv_text2mel {
   DecStage stages[DEC_STAGES];
   DecStage* stages_dev = nullptr;
   float *fin_g, *fin_b;
+  // weight-stationary pipeline (decode_ws.cu): stage -> CTA-group table and the weight-slice images
+  WsStage ws_stages[DEC_STAGES];
+  WsStage* ws_stages_dev = nullptr;
+  int ws_hist_blocks = 0;
   Workspace ws;
   int* err_flag = nullptr;
 };
@@ -274,6 +278,11 @@ struct ssv_decoder {
   unsigned* bar;
   int* abort_flag;
   long long* prof = nullptr;
+  int impl = DEC_IMPL_GRID;
+  unsigned long long* ws_raw = nullptr;
+  int* ws_sent = nullptr;
+  float* ws_hist = nullptr;
+  int seq_base = 0, R = 1, G = 1;
   // per-batch state
   bool begun = false;
   int B = 0, N = 0, t_cap = 0, t = 0;
@@ -488,6 +497,24 @@ int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, 
     T2M_TRY(m->arena.alloc<DecStage>(DEC_STAGES, &m->stages_dev));
     if (cudaMemcpyAsync(m->stages_dev, m->stages, sizeof(DecStage) * DEC_STAGES, cudaMemcpyHostToDevice, s) != cudaSuccess)
       return fail(kCuda);
+    // weight-stationary layout: CTA groups, weight-slice images, private-history ring blocks
+    int cta = 0, blk = 0;
+    for (int i = 0; i < DEC_STAGES; ++i) {
+      WsStage& w = m->ws_stages[i];
+      ws_stage_layout(i, m->stages[i], &w);
+      if (i == 0) { w.g1 = m->fin_g; w.b1 = m->fin_b; }     // PRO_X finishes the previous frame: sigmoid(LN5(.))
+      w.cta0 = cta; cta += w.parts;
+      w.hist_blk0 = blk; blk += w.parts * w.hist_depth;
+      float* img;
+      T2M_TRY(m->arena.alloc<float>((size_t)w.parts * w.K * w.ncol, &img));
+      T2M_TRY(ws_pack_image(m->stages[i].W, w, img, s));
+      w.img = img;
+    }
+    if (cta != WS_GRID) { set_error("internal: weight-stationary layout uses %d CTAs, expected %d", cta, WS_GRID); return fail(kState); }
+    m->ws_hist_blocks = blk;
+    T2M_TRY(m->arena.alloc<WsStage>(DEC_STAGES, &m->ws_stages_dev));
+    if (cudaMemcpyAsync(m->ws_stages_dev, m->ws_stages, sizeof(WsStage) * DEC_STAGES, cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return fail(kCuda);
   }
 #undef T2M_TRY
   if (cudaStreamSynchronize(s) != cudaSuccess) {
@@ -549,8 +576,21 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
   d->maxB = max_batch; d->maxN = max_text; d->maxT = max_frames;
   const int H = m->H;
   int st = kOk;
-  if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_STAGES * max_batch * DEC_RAW_LD, &d->raw);
-  if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_HIST * max_batch * max_frames * H, &d->hist);
+  d->impl = decode_select_impl(device_sm_count());
+  if (d->impl == DEC_IMPL_WS && max_batch > WS_MAX_BATCH) d->impl = DEC_IMPL_GRID;
+  if (d->impl == DEC_IMPL_WS) {
+    const size_t bp = (size_t)round_up(max_batch, 4);
+    const size_t raw_words = (size_t)DEC_STAGES * max_batch * WS_WORDS;
+    const size_t sent_ints = (size_t)DEC_STAGES * max_batch * WS_MAX_PARTS;
+    if (st == kOk) st = d->arena.alloc<unsigned long long>(raw_words, &d->ws_raw);
+    if (st == kOk) st = d->arena.alloc<int>(sent_ints, &d->ws_sent);
+    if (st == kOk) st = d->arena.alloc<float>((size_t)m->ws_hist_blocks * bp * H, &d->ws_hist);
+    if (st == kOk && cudaMemset(d->ws_raw, 0, raw_words * sizeof(unsigned long long)) != cudaSuccess) st = kCuda;
+    if (st == kOk && cudaMemset(d->ws_sent, 0, sent_ints * sizeof(int)) != cudaSuccess) st = kCuda;
+  } else {
+    if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_STAGES * max_batch * DEC_RAW_LD, &d->raw);
+    if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_HIST * max_batch * max_frames * H, &d->hist);
+  }
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * max_text * H, &d->Kt);
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * max_text * H, &d->Vt);
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * H, &d->s1);
@@ -588,6 +628,18 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
   SSV_TRY(launch_linear_small(spkemb, m->E, m->fc2_w, m->fc2_b, B, m->E, H, d->s2, H, s));
   SSV_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * (size_t)B * N * t_cap, s));
   SSV_CUDA(cudaMemsetAsync(d->pma_state, 0, sizeof(int) * B, s));
+  if (d->impl == DEC_IMPL_WS) {
+    // tags of this batch: seq_base + t + 1, strictly above every tag of earlier batches
+    d->seq_base += d->t_cap + 2;
+    if (d->seq_base > (1 << 30)) {
+      SSV_CUDA(cudaMemsetAsync(d->ws_raw, 0, (size_t)DEC_STAGES * d->maxB * WS_WORDS * sizeof(unsigned long long), s));
+      SSV_CUDA(cudaMemsetAsync(d->ws_sent, 0, (size_t)DEC_STAGES * d->maxB * WS_MAX_PARTS * sizeof(int), s));
+      d->seq_base = 0;
+    }
+    // rows per micro-batch: as many micro-batches in flight as the 24-stage pipeline can hold
+    d->R = B <= DEC_STAGES ? 1 : (B <= 2 * DEC_STAGES ? 2 : 4);
+    d->G = (B + d->R - 1) / d->R;
+  }
   d->B = B; d->N = N; d->t_cap = t_cap; d->t = 0;
   d->Y = Y; d->A = A; d->traj = reinterpret_cast<long long*>(pma_traj);
   d->begun = true;
@@ -617,16 +669,21 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.bar_counter = d->bar;
   p.abort_flag = d->abort_flag;
   p.prof = d->prof;
+  p.ws_stages = m->ws_stages_dev;
+  p.ws_raw = d->ws_raw; p.ws_sent = d->ws_sent; p.ws_hist = d->ws_hist;
+  p.seq_base = d->seq_base; p.R = d->R; p.G = d->G;
   const int sms = device_sm_count();
   SSV_CHECK(sms > 0, "decoder: no CUDA device");
   if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 8, s));
-  SSV_TRY(launch_decode(p, sms, s));
+  SSV_TRY(launch_decode(p, sms, d->impl, s));
   if (d->prof) {   // development aid: per-phase SM cycles, mean / max over CTAs, per stage
     SSV_CUDA(cudaStreamSynchronize(s));
     std::vector<long long> h((size_t)DEC_MAX_GRID * 8);
     SSV_CUDA(cudaMemcpy(h.data(), d->prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
-    const char* nm[7] = {"loop-top", "arm/arrive+prefetch-issue", "wait", "prologue", "cp.async-wait+sync", "gemv", "tail (sync / bulk-copy issue)"};
-    fprintf(stderr, "[decode prof] B=%d steps=%d (cycles per stage: mean / max over CTAs)\n", d->B, n_steps);
+    const char* nm_old[7] = {"loop-top", "arm/arrive+prefetch-issue", "wait", "prologue", "cp.async-wait+sync", "gemv", "tail (sync / bulk-copy issue)"};
+    const char* nm_ws[7] = {"loop-top", "tap prefetch issue", "wait + prologue (warp 0)", "cp.async-wait + sync", "ring write + gemv", "reduce + publish", "-"};
+    const char* const* nm = d->impl == DEC_IMPL_WS ? nm_ws : nm_old;
+    fprintf(stderr, "[decode prof] impl=%d B=%d R=%d steps=%d (cycles per stage visit: mean / max over CTAs)\n", d->impl, d->B, d->R, n_steps);
     for (int i = 0; i < 7; ++i) {
       double sum = 0, mx = 0; int cnt = 0;
       for (int c = 0; c < DEC_MAX_GRID; ++c) {

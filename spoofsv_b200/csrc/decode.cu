@@ -515,14 +515,16 @@ int launch_rows(const DecParams& p, int grid, cudaStream_t s) {
 
 }  // namespace
 
-int launch_decode(const DecParams& p, int sm_count, cudaStream_t s) {
-  // default: the cluster kernel (decode_cluster.cu); SSV_DECODE_IMPL=grid selects this file's grid-barrier kernel
-  static int use_cluster = -1;
-  if (use_cluster < 0) {
-    const char* e = getenv("SSV_DECODE_IMPL");
-    use_cluster = (e && e[0] == 'g') ? 0 : (decode_cluster_capacity() > 0 ? 1 : 0);
-  }
-  if (use_cluster) return launch_decode_cluster(p, s);
+int decode_select_impl(int sm_count) {
+  const char* e = getenv("SSV_DECODE_IMPL");
+  if (e && e[0] == 'g') return DEC_IMPL_GRID;
+  if (e && e[0] == 'c') return decode_cluster_capacity() > 0 ? DEC_IMPL_CLUSTER : DEC_IMPL_GRID;
+  return decode_ws_supported(sm_count) ? DEC_IMPL_WS : DEC_IMPL_GRID;
+}
+
+int launch_decode(const DecParams& p, int sm_count, int impl, cudaStream_t s) {
+  if (impl == DEC_IMPL_WS) return launch_decode_ws(p, s);
+  if (impl == DEC_IMPL_CLUSTER) return launch_decode_cluster(p, s);
   SSV_CHECK(p.H == HD, "decode: hidden_dim must be %d", HD);
   SSV_CHECK(p.F <= 96 && p.F % 4 == 0, "decode: freq_bins must be <= 96 and a multiple of 4");
   SSV_CHECK(p.B >= 1 && p.n_steps >= 1, "decode: empty launch");

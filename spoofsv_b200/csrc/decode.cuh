@@ -35,6 +35,27 @@ constexpr int DEC_RAW_LD = 512;
 constexpr int DEC_XS_LD = 768;
 constexpr int DEC_MAX_GRID = 1024;   // barrier flag words
 
+// ---- weight-stationary pipeline (decode_ws.cu): one CTA group per stage, weights resident in shared memory
+struct WsStage {
+  const float* img;    // [parts][K][ncol] shared-memory images of the weight slices
+  const float* bias;   // [n]
+  const float* g1; const float* b1;   // LayerNorm affine of the prologue (as DecStage)
+  const float* g2; const float* b2;
+  int n, K, k_seg, ntaps, dil, pro, bias_b;
+  int parts;           // CTAs of this stage
+  int ncol;            // columns per CTA (64 / 128 / 256; padded past n with zero weights)
+  int cg;              // ncol / 4: column groups of the thread tiling
+  int hwy;             // 1: outputs are (H1 | H2) and the CTA owns matching slices; its input row travels along as residual
+  int cta0;            // first CTA of the group
+  int hist_depth;      // ring depth 2*dil + 1 of the private input history (3-tap stages), else 0
+  int hist_blk0;       // first ring block of the stage (block = [G][256][RT] floats)
+};
+constexpr int WS_WORDS = 768;        // tagged 8-byte words per (stage, utterance): 512 outputs + 256 residual
+constexpr int WS_MAX_PARTS = 8;
+constexpr int WS_GRID = 144;         // 16 highway layers x 8 + 16 CTAs for the eight 1x1 stages
+constexpr int WS_MAX_BATCH = 1024;
+enum DecodeImpl { DEC_IMPL_WS = 0, DEC_IMPL_CLUSTER = 1, DEC_IMPL_GRID = 2 };
+
 struct DecParams {
   const DecStage* stages;       // [DEC_STAGES]
   const float* fin_g; const float* fin_b;   // LN5 of the decoder (80)
@@ -54,11 +75,23 @@ struct DecParams {
   unsigned* bar_counter;      // [DEC_MAX_GRID] per-CTA barrier flags
   int* abort_flag;
   long long* prof;              // optional [grid][8] phase cycle counters (SSV_DECODE_PROF=1), else nullptr
+  // weight-stationary pipeline only
+  const WsStage* ws_stages;     // device [DEC_STAGES]
+  unsigned long long* ws_raw;   // [DEC_STAGES][B][WS_WORDS] tagged words {float, tag}
+  int* ws_sent;                 // [DEC_STAGES][G][WS_MAX_PARTS] sentinel tags
+  float* ws_hist;               // private input-history rings, [blocks][G][256][R]
+  int seq_base;                 // tag of frame t is seq_base + t + 1 (advanced by every begin())
+  int R, G;                     // rows per micro-batch (1, 2, 4), micro-batches
 };
 
-int launch_decode(const DecParams& p, int sm_count, cudaStream_t s);
+int launch_decode(const DecParams& p, int sm_count, int impl, cudaStream_t s);
 int launch_decode_cluster(const DecParams& p, cudaStream_t s);     // decode_cluster.cu
 int decode_cluster_capacity();
+int launch_decode_ws(const DecParams& p, cudaStream_t s);          // decode_ws.cu
+bool decode_ws_supported(int sm_count);
+void ws_stage_layout(int s, const DecStage& d, WsStage* w);
+int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStream_t s);
+int decode_select_impl(int sm_count);                              // SSV_DECODE_IMPL=ws|cluster|grid overrides
 int decode_max_grid(int* out);
 
 }  // namespace ssv
