@@ -501,12 +501,12 @@ int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, 
     int cta = 0, blk = 0;
     for (int i = 0; i < DEC_STAGES; ++i) {
       WsStage& w = m->ws_stages[i];
-      ws_stage_layout(i, m->stages[i], &w);
+      ws_stage_layout(m->stages[i], &w);
       if (i == 0) { w.g1 = m->fin_g; w.b1 = m->fin_b; }     // PRO_X finishes the previous frame: sigmoid(LN5(.))
       w.cta0 = cta; cta += w.parts;
       w.hist_blk0 = blk; blk += w.parts * w.hist_depth;
       float* img;
-      T2M_TRY(m->arena.alloc<float>((size_t)w.parts * w.K * w.ncol, &img));
+      T2M_TRY(m->arena.alloc<float>(ws_image_floats(w), &img));
       T2M_TRY(ws_pack_image(m->stages[i].W, w, img, s));
       w.img = img;
     }
@@ -598,7 +598,7 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
   if (st == kOk) st = d->arena.alloc<int>(max_batch, &d->pma_state);
   if (st == kOk) st = d->arena.alloc<unsigned>(DEC_MAX_GRID, &d->bar);
   if (st == kOk) st = d->arena.alloc<int>(1, &d->abort_flag);
-  if (st == kOk && getenv("SSV_DECODE_PROF")) st = d->arena.alloc<long long>((size_t)DEC_MAX_GRID * 8, &d->prof);
+  if (st == kOk && getenv("SSV_DECODE_PROF")) st = d->arena.alloc<long long>((size_t)DEC_MAX_GRID * 16, &d->prof);
   if (st != kOk) { delete d; return st; }
   cudaMemset(d->abort_flag, 0, sizeof(int));
   *out = d;
@@ -638,6 +638,10 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
     }
     // rows per micro-batch: as many micro-batches in flight as the 24-stage pipeline can hold
     d->R = B <= DEC_STAGES ? 1 : (B <= 2 * DEC_STAGES ? 2 : 4);
+    if (const char* e = getenv("SSV_DECODE_R")) {          // development knob
+      const int r = atoi(e);
+      if (r == 1 || r == 2 || r == 4) d->R = r;
+    }
     d->G = (B + d->R - 1) / d->R;
   }
   d->B = B; d->N = N; d->t_cap = t_cap; d->t = 0;
@@ -674,24 +678,29 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.seq_base = d->seq_base; p.R = d->R; p.G = d->G;
   const int sms = device_sm_count();
   SSV_CHECK(sms > 0, "decoder: no CUDA device");
-  if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 8, s));
+  if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 16, s));
   SSV_TRY(launch_decode(p, sms, d->impl, s));
-  if (d->prof) {   // development aid: per-phase SM cycles, mean / max over CTAs, per stage
+  if (d->prof) {   // development aid: per-phase SM cycles, mean / max over CTAs, per stage visit
     SSV_CUDA(cudaStreamSynchronize(s));
-    std::vector<long long> h((size_t)DEC_MAX_GRID * 8);
+    const bool ws = d->impl == DEC_IMPL_WS;
+    const int stride = ws ? 16 : 8, cnt_slot = ws ? 15 : 7, n_ph = ws ? 15 : 7;
+    std::vector<long long> h((size_t)DEC_MAX_GRID * 16);
     SSV_CUDA(cudaMemcpy(h.data(), d->prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     const char* nm_old[7] = {"loop-top", "arm/arrive+prefetch-issue", "wait", "prologue", "cp.async-wait+sync", "gemv", "tail (sync / bulk-copy issue)"};
-    const char* nm_ws[7] = {"loop-top", "tap prefetch issue", "wait + prologue (warp 0)", "cp.async-wait + sync", "ring write + gemv", "reduce + publish", "-"};
-    const char* const* nm = d->impl == DEC_IMPL_WS ? nm_ws : nm_old;
+    const char* nm_ws[15] = {"FE loop-top", "FE wait X buffer empty", "FE tap prefetch issue", "FE wait for producer sentinel", "FE row load (tags verified)", "FE barrier + ring write", "FE prologue math + X stores", "-",
+                             "MV wait taps", "MV old taps (2/3)", "MV wait current tap", "MV current tap + k-slice store", "MV reduce + publish",
+                             "sentinel seen -> my sentinel out", "curfull arrive -> MV awake (highway)"};
+    const char* const* nm = ws ? nm_ws : nm_old;
     fprintf(stderr, "[decode prof] impl=%d B=%d R=%d steps=%d (cycles per stage visit: mean / max over CTAs)\n", d->impl, d->B, d->R, n_steps);
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < n_ph; ++i) {
+      if (nm[i][0] == '-') continue;
       double sum = 0, mx = 0; int cnt = 0;
       for (int c = 0; c < DEC_MAX_GRID; ++c) {
-        if (h[(size_t)c * 8 + 7] == 0) continue;
-        const double v = (double)h[(size_t)c * 8 + i] / (double)h[(size_t)c * 8 + 7];
+        if (h[(size_t)c * stride + cnt_slot] == 0) continue;
+        const double v = (double)h[(size_t)c * stride + i] / (double)h[(size_t)c * stride + cnt_slot];
         sum += v; mx = v > mx ? v : mx; ++cnt;
       }
-      fprintf(stderr, "  %-24s %9.0f / %9.0f\n", nm[i], cnt ? sum / cnt : 0.0, mx);
+      fprintf(stderr, "  %-32s %9.0f / %9.0f\n", nm[i], cnt ? sum / cnt : 0.0, mx);
     }
   }
   d->t += n_steps;

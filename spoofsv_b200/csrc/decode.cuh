@@ -35,16 +35,18 @@ constexpr int DEC_RAW_LD = 512;
 constexpr int DEC_XS_LD = 768;
 constexpr int DEC_MAX_GRID = 1024;   // barrier flag words
 
-// ---- weight-stationary pipeline (decode_ws.cu): one CTA group per stage, weights resident in shared memory
+// ---- weight-stationary pipeline (decode_ws.cu): one CTA group per stage, weights resident in registers / shared memory
 struct WsStage {
-  const float* img;    // [parts][K][ncol] shared-memory images of the weight slices
+  const float* img;    // [parts][njt][384] float4: thread-major images of the weight slices
   const float* bias;   // [n]
   const float* g1; const float* b1;   // LayerNorm affine of the prologue (as DecStage)
   const float* g2; const float* b2;
   int n, K, k_seg, ntaps, dil, pro, bias_b;
   int parts;           // CTAs of this stage
-  int ncol;            // columns per CTA (64 / 128 / 256; padded past n with zero weights)
+  int ncol;            // columns per CTA (64 / 128; padded past n with zero weights)
   int cg;              // ncol / 4: column groups of the thread tiling
+  int nj;              // k iterations a mat-vec thread holds in registers (<= 22)
+  int njt;             // k iterations in the image (highway: 33 = tap 0 for shared memory + nj)
   int hwy;             // 1: outputs are (H1 | H2) and the CTA owns matching slices; its input row travels along as residual
   int cta0;            // first CTA of the group
   int hist_depth;      // ring depth 2*dil + 1 of the private input history (3-tap stages), else 0
@@ -52,7 +54,9 @@ struct WsStage {
 };
 constexpr int WS_WORDS = 768;        // tagged 8-byte words per (stage, utterance): 512 outputs + 256 residual
 constexpr int WS_MAX_PARTS = 8;
-constexpr int WS_GRID = 144;         // 16 highway layers x 8 + 16 CTAs for the eight 1x1 stages
+constexpr int WS_GRID = 145;         // 16 highway layers x 8 + 17 CTAs for the eight 1x1 stages
+constexpr int WS_GEMV_THREADS = 384; // warps 4-15 of a CTA
+constexpr int WS_TAP_ROWS = 264;     // 256 input channels of a tap, padded to a multiple of 24 k-slices
 constexpr int WS_MAX_BATCH = 1024;
 enum DecodeImpl { DEC_IMPL_WS = 0, DEC_IMPL_CLUSTER = 1, DEC_IMPL_GRID = 2 };
 
@@ -74,7 +78,7 @@ struct DecParams {
   int RG;                       // row groups
   unsigned* bar_counter;      // [DEC_MAX_GRID] per-CTA barrier flags
   int* abort_flag;
-  long long* prof;              // optional [grid][8] phase cycle counters (SSV_DECODE_PROF=1), else nullptr
+  long long* prof;              // optional [grid][8] ([grid][16]: decode_ws) phase cycle counters (SSV_DECODE_PROF=1)
   // weight-stationary pipeline only
   const WsStage* ws_stages;     // device [DEC_STAGES]
   unsigned long long* ws_raw;   // [DEC_STAGES][B][WS_WORDS] tagged words {float, tag}
@@ -89,7 +93,8 @@ int launch_decode_cluster(const DecParams& p, cudaStream_t s);     // decode_clu
 int decode_cluster_capacity();
 int launch_decode_ws(const DecParams& p, cudaStream_t s);          // decode_ws.cu
 bool decode_ws_supported(int sm_count);
-void ws_stage_layout(int s, const DecStage& d, WsStage* w);
+void ws_stage_layout(const DecStage& d, WsStage* w);
+size_t ws_image_floats(const WsStage& w);
 int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStream_t s);
 int decode_select_impl(int sm_count);                              // SSV_DECODE_IMPL=ws|cluster|grid overrides
 int decode_max_grid(int* out);

@@ -5,25 +5,32 @@
 // highwayConv keeps the history of its own input, so frame t costs O(1) instead of O(t).
 //
 // What is different here is WHERE the work lives.  The 24 mat-vec stages of a frame (AudioEnc 13,
-// attention + AudioDec 11) own 6.8 M fp32 weights = 27.3 MB; the 148 SMs of a B200 have 33 MB of shared
-// memory between them.  So every stage gets a fixed group of CTAs (8 per highway layer, 1-4 per 1x1 conv,
-// 144 in total), each CTA loads its [K][ncol] weight slice into shared memory ONCE per launch, and the
-// utterances flow through the stage groups as micro-batches of RT rows:
+// attention + AudioDec 11) own 6.8 M fp32 weights = 27.3 MB; a B200 has 37 MB of registers and 33 MB of
+// shared memory spread over its 148 SMs.  So every stage gets a fixed group of CTAs (8 per highway layer,
+// 1-4 per 1x1 conv, 145 in total), each CTA loads its weight slice ONCE per launch -- 88 weights per thread
+// into REGISTERS, the remaining tap of a highway layer into shared memory -- and the utterances flow
+// through the stage groups as micro-batches of RT rows:
 //
 //     stage s, micro-batch g, frame t   needs   stage s-1, g, t      (stage 0: stage 23, g, t-1)
 //
-// which is a software pipeline over (frame, micro-batch): up to 24 micro-batches are in flight, HBM/L2 see
-// only activations, and there is no grid-wide barrier anywhere.
+// a software pipeline over (frame, micro-batch): up to 24 micro-batches are in flight, HBM/L2 see only
+// activations, and there is no grid-wide barrier anywhere.
+//
+// Inside a CTA the work is warp-specialised.  Warps 0-3 are the front end: they prefetch the taps t-2d, t-d
+// from the CTA's private history ring, wait for the producer stage, redo the cheap LayerNorm / highway gate /
+// windowed attention of the input row (redundantly per consumer CTA, as decode.cu does), and fill one of two
+// X buffers.  Warps 4-15 hold the weights and do the mat-vec: the two OLD taps (2/3 of a highway layer's
+// work) do not depend on the producer stage and run while the front end is still waiting for it; only the
+// current tap sits on the frame's critical path.  The two halves hand X buffers back and forth through
+// mbarriers, so with enough micro-batches the wait for stage s-1 overlaps the mat-vec of the previous one.
 //
 // Cross-CTA hand-off: every value a CTA publishes is an 8-byte word {float value, int tag} written with one
 // 64-bit store (single-copy atomic); tag = seq_base + frame + 1.  A consumer first polls one sentinel word
 // per producer CTA (cheap: 32 B per round), then loads the row and checks every tag, re-loading until all
 // match -- so no fences and no release/acquire chains sit on the critical path, and a word that has not
-// landed yet can never be mistaken for data.  Everything else a CTA touches is private to it: its weight
-// slice, its LayerNorm parameters, and its own ring of past stage inputs (taps t-d, t-2d), so the only
-// cross-CTA traffic is the tagged words.  Consumers redo the cheap LayerNorm / highway gate / windowed
-// attention of their input row redundantly (as decode.cu does), which is what lets a stage boundary be a
-// single hand-off.
+// landed yet can never be mistaken for data.  Everything else a CTA touches is private to it (weights,
+// LayerNorm parameters, its own ring of past stage inputs), so the tagged words are the only cross-CTA
+// traffic.
 #include "decode.cuh"
 
 #include <cstdlib>
@@ -33,16 +40,21 @@ namespace ssv {
 namespace {
 
 constexpr int NT = 512;
+constexpr int FE_T = 128;                // front-end threads (warps 0-3)
+constexpr int GV_T = WS_GEMV_THREADS;    // mat-vec threads (warps 4-15)
 constexpr int HD = 256;
+constexpr int TAPP = WS_TAP_ROWS;        // rows of one tap in X (256 padded to a multiple of 24)
 constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks
 constexpr unsigned FULL = 0xffffffffu;
 
-// fixed shared-memory carve-up (floats)
-constexpr int SM_W = 768 * 64;             // weight slice, at most [768][64]
-constexpr int SM_SCRATCH_MAX = 4096;       // highway CTA: X [768][RT<=4] (3072) | partials [16][RT][64] (4096)
-constexpr int SM_LN = SM_W + SM_SCRATCH_MAX;   // [4][256] LayerNorm parameters of my prologue
-constexpr int SM_BIAS = SM_LN + 4 * HD;    // [256] bias of my columns
-constexpr int SM_PMA = SM_BIAS + 256;      // [WS_MAX_BATCH] ints (attention stage only)
+// shared-memory carve-up (floats)
+constexpr int XBUF = 3 * TAPP * 4;                 // one X buffer: [rows <= 792][RT <= 4]
+constexpr int SM_WSM = 0;                          // [11][384] float4: tap-0 weights of a highway CTA
+constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [2][XBUF]
+constexpr int SM_PART = SM_X + 2 * XBUF;           // [12][RT][ncol <= 128] k-slice partial sums
+constexpr int SM_LN = SM_PART + 12 * 4 * 128;      // [4][256] LayerNorm parameters of my prologue
+constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
+constexpr int SM_PMA = SM_BIAS + 128;              // [WS_MAX_BATCH] ints (attention stage only)
 constexpr int SM_TOTAL = SM_PMA + WS_MAX_BATCH;
 
 struct __align__(8) Word { float v; int tag; };
@@ -74,12 +86,50 @@ __device__ __forceinline__ int ld_relaxed_s32(const int* p) {
 __device__ __forceinline__ void st_relaxed_s32(int* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// ---- mbarriers (CTA-local producer / consumer hand-off of the X buffers)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrival that fires when all cp.async of the executing thread issued so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait; false: the launch was aborted (some CTA timed out), leave
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int* abort_flag) {
+  unsigned spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > SPIN_LIMIT) atomicExch(abort_flag, 9);
+      if (*reinterpret_cast<volatile int*>(abort_flag) != 0) return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -93,6 +143,10 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b) {
   }
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Highway gate / LayerNorm scale on the frame's critical path: MUFU-based, branch-free (2 ulp), so the eight
+// per-lane chains interleave instead of serialising on the slow-path calls of IEEE division / sqrt.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float rstd_fast(float var) { return rsqrtf(var + 1e-5f); }
 
 template <int RT> struct XVec;
 template <> struct XVec<1> {
@@ -111,165 +165,223 @@ template <> struct XVec<4> {
   }
 };
 
-// Partial products of the CTA's [K][4*CG] weight slice with the RT input rows X[K][RT].
-// Thread (cg, ks) owns 4 columns and the k indices ks + KS*i; partial sums of every k-slice go to
-// part[slice][r][col] (aliases X: the caller's data in X is dead after the barrier inside).
-template <int RT, int CG>
-__device__ __forceinline__ void gemv_partials(const float* __restrict__ Ws, float* __restrict__ Xs, int K, int tid) {
-  constexpr int NCOL = 4 * CG;
-  constexpr int KS = NT / CG;
-  const int cg = tid % CG, ks = tid / CG;
-  const int iters = K / KS;
-  float acc[RT][4];
+template <int RT>
+__device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, const float* xp) {
+  float x[RT];
+  XVec<RT>::ld(xp, x);
 #pragma unroll
-  for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-  const float* wp = Ws + ks * NCOL + cg * 4;
-  const float* xp = Xs + ks * RT;
-#pragma unroll 8
-  for (int i = 0; i < iters; ++i) {
-    const float4 w = *reinterpret_cast<const float4*>(wp + (size_t)i * KS * NCOL);
-    float x[RT];
-    XVec<RT>::ld(xp + i * KS * RT, x);
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      acc[r][0] = fmaf(x[r], w.x, acc[r][0]);
-      acc[r][1] = fmaf(x[r], w.y, acc[r][1]);
-      acc[r][2] = fmaf(x[r], w.z, acc[r][2]);
-      acc[r][3] = fmaf(x[r], w.w, acc[r][3]);
-    }
+  for (int r = 0; r < RT; ++r) {
+    acc[r][0] = fmaf(x[r], w.x, acc[r][0]);
+    acc[r][1] = fmaf(x[r], w.y, acc[r][1]);
+    acc[r][2] = fmaf(x[r], w.z, acc[r][2]);
+    acc[r][3] = fmaf(x[r], w.w, acc[r][3]);
   }
-  int slice;
-  bool writer = true;
-  if (CG == 16) {               // the two half-warps hold adjacent k-slices of the same columns
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] += __shfl_xor_sync(FULL, acc[r][c], 16);
-    slice = tid >> 5;
-    writer = (tid & 16) == 0;
-  } else {
-    slice = ks;
-  }
-  __syncthreads();              // every thread is done reading X
-  if (writer) {
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-      *reinterpret_cast<float4*>(Xs + ((size_t)slice * RT + r) * NCOL + cg * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-  }
-  __syncthreads();
 }
 
-template <int RT>
-__global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ int s_bad;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+struct Ctx {                 // per-CTA constants shared by both roles
+  int s, prev, part, prev_parts, G, B;
+  float* smem;
+  uint64_t* tapsfull;        // [2] old taps of the X buffer have landed (cp.async)
+  uint64_t* curfull;         // [2] current tap (prologue output) is in the X buffer
+  uint64_t* empty;           // [2] mat-vec warps are done reading the X buffer
+  int* s_bad;
+  volatile long long* t_seen;   // profiling: SM clock at which the front end saw the producer's sentinel
+};
 
-  // ---- which stage / column slice am I?
-  int s = -1;
-#pragma unroll 1
-  for (int i = 0; i < DEC_STAGES; ++i) {
-    const int c0 = p.ws_stages[i].cta0;
-    if ((int)blockIdx.x >= c0 && (int)blockIdx.x < c0 + p.ws_stages[i].parts) s = i;
-  }
-  if (s < 0) return;
-  const int prev = (s + DEC_STAGES - 1) % DEC_STAGES;
-  const WsStage st = p.ws_stages[s];
-  const int prev_parts = p.ws_stages[prev].parts;
-  const int part = (int)blockIdx.x - st.cta0;
-  const bool designated = part == 0;
-  const int K = st.K, ncol = st.ncol, half = ncol / 2;
-  const int G = p.G, B = p.B;
+// global column (= tagged word index) of local column lc; highway CTAs own matching H1 / H2 slices
+__device__ __forceinline__ int gcol(const WsStage& st, int part, int lc) {
+  const int half = st.ncol / 2;
+  return st.hwy ? (lc < half ? part * half + lc : HD + part * half + (lc - half)) : part * st.ncol + lc;
+}
 
-  float* Ws = smem;
-  float* Xs = smem + (size_t)K * ncol;     // scratch: X [K][RT], later partials [slices][RT][ncol]
-  float* lnp = smem + SM_LN;
-  float* bias_s = smem + SM_BIAS;
-  int* pma_s = reinterpret_cast<int*>(smem + SM_PMA);
-  const float* g1 = lnp;
-  const float* b1 = lnp + HD;
-  const float* g2 = lnp + 2 * HD;
-  const float* b2 = lnp + 3 * HD;
+// ------------------------------------------------------------------------------------------------------
+// Mat-vec role (warps 4-15).  Thread (cg, ks) owns 4 columns and the k rows ks + KS*j of every tap.
+template <int RT, int CG, bool HWY, bool PROF>
+__device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st, const Ctx& c, int gtid) {
+  constexpr int KS = GV_T / CG;            // k-slices: 24 (64 columns) or 12 (128 columns)
+  constexpr int NCOL = 4 * CG;
+  const int cg = gtid % CG, ks = gtid / CG;
+  const int lane = gtid & 31, gwarp = gtid >> 5;
+  float* parts = c.smem + SM_PART;
+  const float* bias_s = c.smem + SM_BIAS;
+  const float4* wsm = reinterpret_cast<const float4*>(c.smem + SM_WSM) + gtid;
 
-  // global column (= tagged word index) of local column lc; highway stages own matching H1 / H2 slices
-  auto gcol = [&](int lc) { return st.hwy ? (lc < half ? part * half + lc : HD + part * half + (lc - half)) : part * ncol + lc; };
-
-  // ---- one-time loads: weight slice, LayerNorm parameters, bias, alignment state
+  // my weights -> registers (image is thread-major: [j][384] float4); highway CTAs: tap 1 and tap 2
+  float4 w[22];
   {
-    const float* img = st.img + (size_t)part * K * ncol;
-    const int n4 = K * ncol / 4;
-    for (int i = tid; i < n4; i += NT) cp_async16(Ws + (size_t)i * 4, img + (size_t)i * 4, true);
-    for (int i = tid; i < 4 * HD; i += NT) {
-      const int which = i / HD, c = i % HD;
-      const float* src = which == 0 ? st.g1 : which == 1 ? st.b1 : which == 2 ? st.g2 : st.b2;
-      const int len = st.pro == PRO_X ? p.F : HD;
-      lnp[i] = (src != nullptr && c < len) ? src[c] : 0.f;
-    }
-    for (int i = tid; i < 256; i += NT) {
-      float v = 0.f;
-      if (i < ncol) { const int gc = gcol(i); if (gc < st.n) v = st.bias[gc]; }
-      bias_s[i] = v;
-    }
-    if (st.pro == PRO_ATT) {
-      for (int i = tid; i < B; i += NT) {
-        const int v = p.pma_in ? (int)p.pma_in[i] : p.pma_state[i];
-        pma_s[i] = max(0, min(v, p.N - 1));
-      }
-    }
-    if (tid == 0) s_bad = 0;
-    cp_async_wait_all();
-    __syncthreads();
+    const float4* img = reinterpret_cast<const float4*>(st.img) + (size_t)c.part * st.njt * GV_T + gtid;
+    const int j0 = HWY ? 11 : 0;
+#pragma unroll
+    for (int j = 0; j < 22; ++j) w[j] = j < st.nj ? __ldg(img + (size_t)(j0 + j) * GV_T) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
-  long long prof_last = 0;
-  long long prof_acc[7] = {0, 0, 0, 0, 0, 0, 0};
-  const bool prof_on = p.prof != nullptr && tid == 0;
+  long long prof_last = 0, prof_acc[5] = {0, 0, 0, 0, 0}, lat_acc = 0, wake_acc = 0;
+  const bool prof_on = PROF && p.prof != nullptr && gtid == 0;
   if (prof_on) prof_last = clock64();
-#define PROF_T(i)                                  \
+#define PROF_G(i)                                  \
   if (prof_on) {                                   \
     const long long now_ = clock64();              \
     prof_acc[i] += now_ - prof_last;               \
     prof_last = now_;                              \
   }
 
-  const Word* raw_in = reinterpret_cast<const Word*>(p.ws_raw) + (size_t)prev * B * WS_WORDS;
-  Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)s * B * WS_WORDS;
-  const int koff = (st.ntaps - 1) * st.k_seg;               // X row of the current tap
-  const int n_visits = p.n_steps + (s == 0 ? 1 : 0);        // stage 0 also finishes the last frame (y = sigmoid(LN5))
-  long visits = 0;
+  Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)c.s * c.B * WS_WORDS;
+  long v = 0;                               // visit counter (same sequence as the front end)
+  for (int step = 0; step < p.n_steps; ++step) {
+    const int tag = p.seq_base + p.t_start + step + 1;
+    for (int g = 0; g < c.G; ++g, ++v) {
+      const int q = (int)(v & 1);
+      const unsigned par = (unsigned)(v >> 1) & 1u;
+      const float* X = c.smem + SM_X + q * XBUF + ks * RT;
+      float acc[RT][4];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+      if (HWY) {
+        // old taps: independent of the producer stage, overlaps the front end's wait
+        mbar_wait(&c.tapsfull[q], par, p.abort_flag);     // on abort: fall through, the uniform exit is below
+        PROF_G(0);
+#pragma unroll
+        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, wsm[j * GV_T], X + (size_t)(KS * j) * RT);
+#pragma unroll
+        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[j], X + (size_t)(TAPP + KS * j) * RT);
+        PROF_G(1);
+        mbar_wait(&c.curfull[q], par, p.abort_flag);
+        PROF_G(2);
+        if (PROF && prof_on) wake_acc += prof_last - c.t_seen[1];
+#pragma unroll
+        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[11 + j], X + (size_t)(2 * TAPP + KS * j) * RT);
+      } else {
+        mbar_wait(&c.curfull[q], par, p.abort_flag);
+        PROF_G(2);
+#pragma unroll
+        for (int j = 0; j < 22; ++j)
+          if (j < st.nj) fma_tile<RT>(acc, w[j], X + (size_t)(KS * j) * RT);
+      }
+      // k-slices -> shared memory
+      bool writer = true;
+      if (CG == 16) {               // the two half-warps hold adjacent k-slices of the same columns
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) acc[r][cc] += __shfl_xor_sync(FULL, acc[r][cc], 16);
+        writer = lane < 16;
+      }
+      if (writer) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          *reinterpret_cast<float4*>(parts + ((size_t)gwarp * RT + r) * NCOL + cg * 4) =
+              make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      }
+      named_bar(1, GV_T);
+      if (gtid == 0) mbar_arrive(&c.empty[q]);     // X buffer q may be refilled
+      PROF_G(3);
+      // reduce the 12 k-slices, add bias (+ hoisted speaker projection), publish tagged words
+      const int row0 = g * RT;
+      for (int o = gtid; o < RT * NCOL; o += GV_T) {
+        const int r = o / NCOL, lc = o - r * NCOL;
+        float sum = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < 12; ++sl) sum += parts[((size_t)sl * RT + r) * NCOL + lc];
+        const int gc = gcol(st, c.part, lc);
+        const int b = row0 + r;
+        if (b < c.B && gc < st.n) {
+          sum += bias_s[lc];
+          if (st.bias_b == 1) sum += __ldg(p.s1 + (size_t)b * HD + gc);
+          else if (st.bias_b == 2) sum += __ldg(p.s2 + (size_t)b * HD + gc);
+          st_word(raw_out + (size_t)b * WS_WORDS + gc, sum, tag);
+        }
+      }
+      named_bar(1, GV_T);
+      if (*reinterpret_cast<volatile int*>(c.s_bad) == 2) return;     // uniform: written before the barrier
+      if (gtid == 0) {
+        st_relaxed_s32(p.ws_sent + ((size_t)c.s * c.G + g) * WS_MAX_PARTS + c.part, tag);
+        if ((v & 15) == 15 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) *c.s_bad = 2;   // seen at the next barrier
+      }
+      PROF_G(4);
+      if (PROF && prof_on) lat_acc += prof_last - *c.t_seen;
+    }
+  }
+  if (prof_on) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) p.prof[(size_t)blockIdx.x * 16 + 8 + i] = prof_acc[i];
+    p.prof[(size_t)blockIdx.x * 16 + 13] = lat_acc;
+    p.prof[(size_t)blockIdx.x * 16 + 14] = wake_acc;
+  }
+#undef PROF_G
+}
 
+// ------------------------------------------------------------------------------------------------------
+// Front-end role (warps 0-3): taps, wait for the producer stage, prologue -> X buffer.
+template <int RT, bool PROF>
+__device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st, const Ctx& c, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int s = c.s, part = c.part, G = c.G, B = c.B;
+  const bool designated = part == 0;
+  const float* lnp = c.smem + SM_LN;
+  const float* g1 = lnp;
+  const float* b1 = lnp + HD;
+  const float* g2 = lnp + 2 * HD;
+  const float* b2 = lnp + 3 * HD;
+  int* pma_s = reinterpret_cast<int*>(c.smem + SM_PMA);
+  const Word* raw_in = reinterpret_cast<const Word*>(p.ws_raw) + (size_t)c.prev * B * WS_WORDS;
+  Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)s * B * WS_WORDS;
+  const int koff = st.hwy ? 2 * TAPP : 0;                   // X row of the current tap
+  const int n_visits = p.n_steps + (s == 0 ? 1 : 0);        // stage 0 also finishes the last frame (y = sigmoid(LN5))
+
+  long long prof_last = 0, prof_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const bool prof_on = PROF && p.prof != nullptr && tid == 0;
+  if (prof_on) prof_last = clock64();
+#define PROF_F(i)                                  \
+  if (prof_on) {                                   \
+    const long long now_ = clock64();              \
+    prof_acc[i] += now_ - prof_last;               \
+    prof_last = now_;                              \
+  }
+
+  __shared__ volatile int s_fe_bad;
+  if (tid == 0) s_fe_bad = 0;
+  named_bar(2, FE_T);
+  long v = 0;
   for (int step = 0; step < n_visits; ++step) {
     const int t = p.t_start + step;
     const bool final_visit = s == 0 && step == p.n_steps;
     const int tag = p.seq_base + t + 1;                     // tag of everything produced for frame t
     const int tag_in = s == 0 ? tag - 1 : tag;              // stage 0 consumes frame t-1 of stage 23
     const bool need_wait = !(s == 0 && step == 0);
-    for (int g = 0; g < G; ++g, ++visits) {
+    for (int g = 0; g < G; ++g, ++v) {
+      const int q = (int)(v & 1);
+      const long u = v >> 1;
+      float* X = c.smem + SM_X + q * XBUF;
       const int row0 = g * RT;
       const int nrows = min(RT, B - row0);
-      PROF_T(0);
+      PROF_F(0);
+      if (!final_visit && u >= 1) {
+        mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag);   // on abort: fall through to the uniform exit
+      }
+      PROF_F(1);
 
-      // ---- 1. old taps t-2d, t-d of this micro-batch from my private ring -> X[0 .. 2*256)  (independent of the wait)
+      // ---- 1. old taps t-2d, t-d of this micro-batch from my private ring -> X rows [0, 256) and [264, 520)
       if (st.ntaps == 3) {
         const int chunks = HD * RT / 4;                      // 16-byte chunks per tap block
-        for (int i = tid; i < 2 * chunks; i += NT) {
+        for (int i = tid; i < 2 * chunks; i += FE_T) {
           const int j = i / chunks, c4 = i - j * chunks;
           const int tt = t - (2 - j) * st.dil;
           const bool ok = tt >= 0;
           const int slot = ok ? tt % st.hist_depth : 0;
           const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT) + c4 * 4;
-          cp_async16(Xs + (size_t)j * HD * RT + c4 * 4, src, ok);
+          cp_async16(X + (size_t)j * TAPP * RT + c4 * 4, src, ok);
         }
+        cp_async_mbar_arrive(&c.tapsfull[q]);
       }
-      PROF_T(1);
+      PROF_F(2);
 
       // ---- 2./3. wait for the producers of my input row, then the prologue: u_t -> X[koff ..][r]
       if (warp < RT) {
         const int r = warp, b = row0 + r;
-        float* xcur = Xs + (size_t)koff * RT + r;            // channel c at xcur[c * RT]
+        float* xcur = X + (size_t)koff * RT + r;             // channel ch at xcur[ch * RT]
         if (r >= nrows) {
           if (!final_visit)
-            for (int c = lane; c < st.k_seg; c += 32) xcur[(size_t)c * RT] = 0.f;
+            for (int ch = lane; ch < st.k_seg; ch += 32) xcur[(size_t)ch * RT] = 0.f;
         } else {
           bool bad = false;
           long long t0 = 0;
@@ -282,14 +394,15 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
             }
           };
           if (need_wait) {
-            const int* sp = p.ws_sent + ((size_t)prev * G + g) * WS_MAX_PARTS;
+            const int* sp = p.ws_sent + ((size_t)c.prev * G + g) * WS_MAX_PARTS;
             for (;;) {
-              const int v = lane < prev_parts ? ld_relaxed_s32(sp + lane) : tag_in;
-              if (__all_sync(FULL, v - tag_in >= 0)) break;
+              const int sv = lane < c.prev_parts ? ld_relaxed_s32(sp + lane) : tag_in;
+              if (__all_sync(FULL, sv - tag_in >= 0)) break;
               spin_check();
               if (__any_sync(FULL, bad)) { bad = true; break; }
             }
           }
+          if (PROF && prof_on) { PROF_F(3); *c.t_seen = prof_last; }
           const Word* R = raw_in + (size_t)b * WS_WORDS;
           const int pro = st.pro;
           if (pro == PRO_X) {
@@ -298,43 +411,43 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
 #pragma unroll
               for (int i = 0; i < 3; ++i) {
                 const int f = lane + 32 * i;
-                float v = 0.f;
+                float xv = 0.f;
                 if (f < p.F) {
-                  if (p.x_ext) v = p.x_ext[(long)b * p.x_sb + (long)f * p.x_sf];
-                  else if (t > 0) v = __ldcg(p.Y + ((size_t)b * p.F + f) * p.t_cap + (t - 1));
+                  if (p.x_ext) xv = p.x_ext[(long)b * p.x_sb + (long)f * p.x_sf];
+                  else if (t > 0) xv = __ldcg(p.Y + ((size_t)b * p.F + f) * p.t_cap + (t - 1));
                 }
-                y[i] = v;
+                y[i] = xv;
               }
             } else {
-              float v[3] = {0.f, 0.f, 0.f};
+              float vv[3] = {0.f, 0.f, 0.f};
               while (!bad) {
                 bool ok = true;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                   const int f = lane + 32 * i;
-                  v[i] = 0.f;
-                  if (f < p.F) { int tg; ld_word(R + f, v[i], tg); ok &= tg == tag_in; }
+                  vv[i] = 0.f;
+                  if (f < p.F) { int tg; ld_word(R + f, vv[i], tg); ok &= tg == tag_in; }
                 }
                 if (__all_sync(FULL, ok)) break;
                 spin_check();
                 if (__any_sync(FULL, bad)) bad = true;
               }
-              float sm = v[0] + v[1] + v[2];
+              float sm = vv[0] + vv[1] + vv[2];
               sm = warp_sum(sm);
               const float mean = sm / (float)p.F;
-              float q = 0.f;
+              float qq = 0.f;
 #pragma unroll
               for (int i = 0; i < 3; ++i) {
-                const float d = v[i] - mean;
-                q += lane + 32 * i < p.F ? d * d : 0.f;
+                const float d = vv[i] - mean;
+                qq += lane + 32 * i < p.F ? d * d : 0.f;
               }
-              q = warp_sum(q);
-              const float rstd = 1.0f / sqrtf(q / (float)p.F + 1e-5f);
+              qq = warp_sum(qq);
+              const float rstd = 1.0f / sqrtf(qq / (float)p.F + 1e-5f);
 #pragma unroll
               for (int i = 0; i < 3; ++i) {
                 const int f = lane + 32 * i;
-                y[i] = f < p.F ? sigmoidf_((v[i] - mean) * rstd * g1[f] + b1[f]) : 0.f;
-                if (f < p.F && !bad) p.Y[((size_t)b * p.F + f) * p.t_cap + (t - 1)] = y[i];
+                y[i] = f < p.F ? sigmoidf_((vv[i] - mean) * rstd * g1[f] + b1[f]) : 0.f;
+                if (f < p.F && !bad && designated) p.Y[((size_t)b * p.F + f) * p.t_cap + (t - 1)] = y[i];
               }
             }
             if (!final_visit) {
@@ -345,42 +458,43 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
               }
             }
           } else if (pro == PRO_LN || pro == PRO_LN_RELU) {
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float vv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             while (!bad) {
               bool ok = true;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 int ta, tb;
-                ld_word2(R + 2 * lane + 64 * i, v[2 * i], ta, v[2 * i + 1], tb);
+                ld_word2(R + 2 * lane + 64 * i, vv[2 * i], ta, vv[2 * i + 1], tb);
                 ok &= ta == tag_in && tb == tag_in;
               }
               if (__all_sync(FULL, ok)) break;
               spin_check();
               if (__any_sync(FULL, bad)) bad = true;
             }
+            if (PROF && prof_on) PROF_F(4);
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sum += v[i];
+            for (int i = 0; i < 8; ++i) sum += vv[i];
             sum = warp_sum(sum);
             const float mean = sum / (float)HD;
-            float q = 0.f;
+            float qq = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-            q = warp_sum(q);
-            const float rstd = 1.0f / sqrtf(q / (float)HD + 1e-5f);
+            for (int i = 0; i < 8; ++i) { const float d = vv[i] - mean; qq = fmaf(d, d, qq); }
+            qq = warp_sum(qq);
+            const float rstd = rstd_fast(qq / (float)HD);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int c = 2 * lane + 64 * (i >> 1) + (i & 1);
-              float o = (v[i] - mean) * rstd * g1[c] + b1[c];
+              const int ch = 2 * lane + 64 * (i >> 1) + (i & 1);
+              float o = (vv[i] - mean) * rstd * g1[ch] + b1[ch];
               if (pro == PRO_LN_RELU) o = fmaxf(o, 0.f);
-              v[i] = o;
-              xcur[(size_t)c * RT] = o;
+              vv[i] = o;
+              xcur[(size_t)ch * RT] = o;
             }
             if (st.hwy && (lane >> 4) == (part & 1)) {       // my residual slice travels with my outputs
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 if (i == (part >> 1))
-                  st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + 2 * lane + 64 * i, v[2 * i], v[2 * i + 1], tag);
+                  st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + 2 * lane + 64 * i, vv[2 * i], vv[2 * i + 1], tag);
             }
           } else {   // PRO_HWY / PRO_ATT: the producer is a highway layer: H1 | H2 | its input (my residual)
             float h1[8] = {}, h2[8] = {}, xr[8] = {};
@@ -389,18 +503,19 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 int ta, tb;
-                const Word* w = R + 2 * lane + 64 * i;
-                ld_word2(w, h1[2 * i], ta, h1[2 * i + 1], tb);
+                const Word* wp = R + 2 * lane + 64 * i;
+                ld_word2(wp, h1[2 * i], ta, h1[2 * i + 1], tb);
                 ok &= ta == tag_in && tb == tag_in;
-                ld_word2(w + HD, h2[2 * i], ta, h2[2 * i + 1], tb);
+                ld_word2(wp + HD, h2[2 * i], ta, h2[2 * i + 1], tb);
                 ok &= ta == tag_in && tb == tag_in;
-                ld_word2(w + 2 * HD, xr[2 * i], ta, xr[2 * i + 1], tb);
+                ld_word2(wp + 2 * HD, xr[2 * i], ta, xr[2 * i + 1], tb);
                 ok &= ta == tag_in && tb == tag_in;
               }
               if (__all_sync(FULL, ok)) break;
               spin_check();
               if (__any_sync(FULL, bad)) bad = true;
             }
+            if (PROF && prof_on) PROF_F(4);
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { s1 += h1[i]; s2 += h2[i]; }
@@ -414,25 +529,25 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
               q2 = fmaf(d2, d2, q2);
             }
             warp_sum2(q1, q2);
-            const float r1 = 1.0f / sqrtf(q1 / (float)HD + 1e-5f);
-            const float r2 = 1.0f / sqrtf(q2 / (float)HD + 1e-5f);
-            float u[8];
+            const float r1 = rstd_fast(q1 / (float)HD);
+            const float r2 = rstd_fast(q2 / (float)HD);
+            float uu[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int c = 2 * lane + 64 * (i >> 1) + (i & 1);
-              const float a = (h1[i] - m1) * r1 * g1[c] + b1[c];
-              const float bb = (h2[i] - m2) * r2 * g2[c] + b2[c];
-              const float gt = sigmoidf_(a);
-              u[i] = gt * bb + (1.0f - gt) * xr[i];
+              const int ch = 2 * lane + 64 * (i >> 1) + (i & 1);
+              const float a = (h1[i] - m1) * r1 * g1[ch] + b1[ch];
+              const float bb = (h2[i] - m2) * r2 * g2[ch] + b2[ch];
+              const float gt = sigmoid_fast(a);
+              uu[i] = gt * bb + (1.0f - gt) * xr[i];
             }
             if (pro == PRO_HWY) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) xcur[(size_t)(2 * lane + 64 * (i >> 1) + (i & 1)) * RT] = u[i];
+              for (int i = 0; i < 8; ++i) xcur[(size_t)(2 * lane + 64 * (i >> 1) + (i & 1)) * RT] = uu[i];
               if (st.hwy && (lane >> 4) == (part & 1)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                   if (i == (part >> 1))
-                    st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + 2 * lane + 64 * i, u[2 * i], u[2 * i + 1], tag);
+                    st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + 2 * lane + 64 * i, uu[2 * i], uu[2 * i + 1], tag);
               }
             } else {
               // windowed attention, models/TTSModel.py:281-295: logits over [pma, min(pma+2, N-1)];
@@ -444,27 +559,27 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
               float l0 = 0.f, l1 = 0.f, l2 = 0.f;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const int c = 2 * lane + 64 * i;
-                const float2 k0 = __ldg(reinterpret_cast<const float2*>(kp + c));
-                l0 = fmaf(k0.x, u[2 * i], l0); l0 = fmaf(k0.y, u[2 * i + 1], l0);
+                const int ch = 2 * lane + 64 * i;
+                const float2 k0 = __ldg(reinterpret_cast<const float2*>(kp + ch));
+                l0 = fmaf(k0.x, uu[2 * i], l0); l0 = fmaf(k0.y, uu[2 * i + 1], l0);
                 if (cnt > 1) {
-                  const float2 k1 = __ldg(reinterpret_cast<const float2*>(kp + HD + c));
-                  l1 = fmaf(k1.x, u[2 * i], l1); l1 = fmaf(k1.y, u[2 * i + 1], l1);
+                  const float2 k1 = __ldg(reinterpret_cast<const float2*>(kp + HD + ch));
+                  l1 = fmaf(k1.x, uu[2 * i], l1); l1 = fmaf(k1.y, uu[2 * i + 1], l1);
                 }
                 if (cnt > 2) {
-                  const float2 k2 = __ldg(reinterpret_cast<const float2*>(kp + 2 * HD + c));
-                  l2 = fmaf(k2.x, u[2 * i], l2); l2 = fmaf(k2.y, u[2 * i + 1], l2);
+                  const float2 k2 = __ldg(reinterpret_cast<const float2*>(kp + 2 * HD + ch));
+                  l2 = fmaf(k2.x, uu[2 * i], l2); l2 = fmaf(k2.y, uu[2 * i + 1], l2);
                 }
               }
               warp_sum2(l0, l1);
               l2 = warp_sum(l2);
               l0 *= 0.0625f; l1 *= 0.0625f; l2 *= 0.0625f;    // 1/sqrt(256)
-              float m = l0;
-              if (cnt > 1) m = fmaxf(m, l1);
-              if (cnt > 2) m = fmaxf(m, l2);
-              const float e0 = expf(l0 - m);
-              const float e1 = cnt > 1 ? expf(l1 - m) : 0.f;
-              const float e2 = cnt > 2 ? expf(l2 - m) : 0.f;
+              float mx = l0;
+              if (cnt > 1) mx = fmaxf(mx, l1);
+              if (cnt > 2) mx = fmaxf(mx, l2);
+              const float e0 = expf(l0 - mx);
+              const float e1 = cnt > 1 ? expf(l1 - mx) : 0.f;
+              const float e2 = cnt > 2 ? expf(l2 - mx) : 0.f;
               const float den = e0 + e1 + e2;
               const float a0 = e0 / den, a1 = e1 / den, a2 = e2 / den;
               int best = 0;
@@ -473,21 +588,21 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
               if (cnt > 2 && a2 > bv) { best = 2; bv = a2; }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const int c = 2 * lane + 64 * i;
-                const float2 v0 = __ldg(reinterpret_cast<const float2*>(vp + c));
+                const int ch = 2 * lane + 64 * i;
+                const float2 v0 = __ldg(reinterpret_cast<const float2*>(vp + ch));
                 float rx = a0 * v0.x, ry = a0 * v0.y;
                 if (cnt > 1) {
-                  const float2 v1 = __ldg(reinterpret_cast<const float2*>(vp + HD + c));
+                  const float2 v1 = __ldg(reinterpret_cast<const float2*>(vp + HD + ch));
                   rx = fmaf(a1, v1.x, rx); ry = fmaf(a1, v1.y, ry);
                 }
                 if (cnt > 2) {
-                  const float2 v2 = __ldg(reinterpret_cast<const float2*>(vp + 2 * HD + c));
+                  const float2 v2 = __ldg(reinterpret_cast<const float2*>(vp + 2 * HD + ch));
                   rx = fmaf(a2, v2.x, rx); ry = fmaf(a2, v2.y, ry);
                 }
-                xcur[(size_t)c * RT] = rx;                    // R
-                xcur[(size_t)(c + 1) * RT] = ry;
-                xcur[(size_t)(HD + c) * RT] = u[2 * i];       // Q
-                xcur[(size_t)(HD + c + 1) * RT] = u[2 * i + 1];
+                xcur[(size_t)ch * RT] = rx;                    // R
+                xcur[(size_t)(ch + 1) * RT] = ry;
+                xcur[(size_t)(HD + ch) * RT] = uu[2 * i];      // Q
+                xcur[(size_t)(HD + ch + 1) * RT] = uu[2 * i + 1];
               }
               if (lane == 0 && !bad) {
                 pma_s[b] = p0 + best;
@@ -502,113 +617,182 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
               }
             }
           }
-          if (bad && lane == 0) s_bad = 1;
+          if (bad && lane == 0) s_fe_bad = 1;
         }
       }
-      if (final_visit) continue;                 // stage 0 after the last frame: prologue only (uniform per CTA)
-      PROF_T(2);
-      cp_async_wait_all();
-      __syncthreads();
-      PROF_T(3);
-      if (s_bad) break;
+      if (final_visit) continue;                 // stage 0 after the last frame: prologue only
+      PROF_F(6);
+      named_bar(2, FE_T);                        // every row of the micro-batch is in X
+      if (tid == 0) { mbar_arrive(&c.curfull[q]); if (PROF && prof_on) c.t_seen[1] = clock64(); }
+      if (s_fe_bad) return;                      // uniform: written before the barrier
+      if (tid == 0 && (v & 15) == 15 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) s_fe_bad = 1;   // seen at the next barrier
 
       // ---- 4. my stage input of frame t joins my private ring (taps of later frames)
       if (st.ntaps == 3) {
         const int slot = t % st.hist_depth;
         float* dst = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT);
-        for (int i = tid; i < HD * RT / 4; i += NT)
-          __stcg(reinterpret_cast<float4*>(dst) + i, *reinterpret_cast<const float4*>(Xs + (size_t)koff * RT + (size_t)i * 4));
+        for (int i = tid; i < HD * RT / 4; i += FE_T)
+          __stcg(reinterpret_cast<float4*>(dst) + i, *reinterpret_cast<const float4*>(X + (size_t)koff * RT + (size_t)i * 4));
       }
-
-      // ---- 5. mat-vec on the resident weight slice
-      if (st.cg == 16) gemv_partials<RT, 16>(Ws, Xs, K, tid);
-      else if (st.cg == 32) gemv_partials<RT, 32>(Ws, Xs, K, tid);
-      else gemv_partials<RT, 64>(Ws, Xs, K, tid);
-      PROF_T(4);
-
-      // ---- 6. reduce the k-slices, add bias (+ hoisted speaker projection), publish tagged words
-      {
-        const int slices = st.cg == 64 ? 8 : 16;
-        for (int o = tid; o < RT * ncol; o += NT) {
-          const int r = o / ncol, lc = o - r * ncol;
-          float v = 0.f;
-          for (int sl = 0; sl < slices; ++sl) v += Xs[((size_t)sl * RT + r) * ncol + lc];
-          const int gc = gcol(lc);
-          if (r < nrows && gc < st.n) {
-            const int b = row0 + r;
-            v += bias_s[lc];
-            if (st.bias_b == 1) v += __ldg(p.s1 + (size_t)b * HD + gc);
-            else if (st.bias_b == 2) v += __ldg(p.s2 + (size_t)b * HD + gc);
-            st_word(raw_out + (size_t)b * WS_WORDS + gc, v, tag);
-          }
-        }
-      }
-      __syncthreads();
-      if (tid == 0) st_relaxed_s32(p.ws_sent + ((size_t)s * G + g) * WS_MAX_PARTS + part, tag);
-      PROF_T(5);
+      PROF_F(5);
     }
-    if (s_bad) break;
   }
   if (prof_on) {
 #pragma unroll
-    for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 8 + i] = prof_acc[i];
-    p.prof[(size_t)blockIdx.x * 8 + 7] = visits > 0 ? visits : 1;
+    for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 16 + i] = prof_acc[i];
+    p.prof[(size_t)blockIdx.x * 16 + 15] = v > 0 ? v : 1;
   }
-#undef PROF_T
+#undef PROF_F
 }
 
-// dst[part][kk][lc] = W[gcol(lc)][kk] (W row-major [n][K]), zero for padded columns.
-__global__ void ws_pack_image_kernel(const float* __restrict__ W, int n, int K, int parts, int ncol, int hwy,
-                                     float* __restrict__ dst) {
-  const long total = (long)parts * K * ncol;
-  const int half = ncol / 2;
+template <int RT, bool PROF>
+__global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ __align__(8) uint64_t bars[6];
+  __shared__ int s_bad;
+  __shared__ long long s_t_seen[2];
+  const int tid = threadIdx.x;
+
+  // ---- which stage / column slice am I?
+  int s = -1;
+#pragma unroll 1
+  for (int i = 0; i < DEC_STAGES; ++i) {
+    const int c0 = p.ws_stages[i].cta0;
+    if ((int)blockIdx.x >= c0 && (int)blockIdx.x < c0 + p.ws_stages[i].parts) s = i;
+  }
+  if (s < 0) return;
+  const WsStage st = p.ws_stages[s];
+  Ctx c;
+  c.s = s;
+  c.prev = (s + DEC_STAGES - 1) % DEC_STAGES;
+  c.part = (int)blockIdx.x - st.cta0;
+  c.prev_parts = p.ws_stages[c.prev].parts;
+  c.G = p.G;
+  c.B = p.B;
+  c.smem = smem;
+  c.tapsfull = bars;
+  c.curfull = bars + 2;
+  c.empty = bars + 4;
+  c.s_bad = &s_bad;
+  c.t_seen = s_t_seen;
+
+  // ---- one-time loads: tap-0 weights of a highway CTA, LayerNorm parameters, bias, alignment state
+  {
+    float* lnp = smem + SM_LN;
+    if (st.hwy) {
+      const float4* img = reinterpret_cast<const float4*>(st.img) + (size_t)c.part * st.njt * GV_T;
+      float4* dst = reinterpret_cast<float4*>(smem + SM_WSM);
+      for (int i = tid; i < 11 * GV_T; i += NT) dst[i] = __ldg(img + i);
+    }
+    for (int i = tid; i < 2 * XBUF; i += NT) smem[SM_X + i] = 0.f;      // padding rows of X stay zero for good
+    for (int i = tid; i < 4 * HD; i += NT) {
+      const int which = i / HD, ch = i % HD;
+      const float* src = which == 0 ? st.g1 : which == 1 ? st.b1 : which == 2 ? st.g2 : st.b2;
+      const int len = st.pro == PRO_X ? p.F : HD;
+      lnp[i] = (src != nullptr && ch < len) ? src[ch] : 0.f;
+    }
+    for (int i = tid; i < 128; i += NT) {
+      float bv = 0.f;
+      if (i < st.ncol) { const int gc = gcol(st, c.part, i); if (gc < st.n) bv = st.bias[gc]; }
+      smem[SM_BIAS + i] = bv;
+    }
+    if (st.pro == PRO_ATT) {
+      int* pma_s = reinterpret_cast<int*>(smem + SM_PMA);
+      for (int i = tid; i < p.B; i += NT) {
+        const int pv = p.pma_in ? (int)p.pma_in[i] : p.pma_state[i];
+        pma_s[i] = max(0, min(pv, p.N - 1));
+      }
+    }
+    if (tid == 0) {
+      s_bad = 0;
+      mbar_init(&bars[0], FE_T); mbar_init(&bars[1], FE_T);     // tapsfull: one cp.async arrival per front-end thread
+      mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);           // curfull
+      mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);           // empty
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+
+  if (tid < FE_T) {
+    front_role<RT, PROF>(p, st, c, tid);
+  } else {
+    const int gtid = tid - FE_T;
+    if (st.hwy) gemv_role<RT, 16, true, PROF>(p, st, c, gtid);
+    else if (st.cg == 16) gemv_role<RT, 16, false, PROF>(p, st, c, gtid);
+    else gemv_role<RT, 32, false, PROF>(p, st, c, gtid);
+  }
+}
+
+// Weight images, thread-major: dst[part][j][gtid][c] with thread (cg, ks) = (gtid % CG, gtid / CG), column
+// lc = 4 cg + c.  Highway layers: j = tap * 11 + jj covers k = tap * 256 + ks + 24 jj (zero past 256);
+// plain layers: k = ks + KS j (zero past K).  W is row-major [n][K].
+__global__ void ws_pack_image_kernel(const float* __restrict__ W, WsStage w, float* __restrict__ dst) {
+  const long total = (long)w.parts * w.njt * GV_T * 4;
+  const int KS = GV_T / w.cg;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int lc = (int)(i % ncol);
-    const int kk = (int)((i / ncol) % K);
-    const int part = (int)(i / ((long)ncol * K));
-    const int gc = hwy ? (lc < half ? part * half + lc : HD + part * half + (lc - half)) : part * ncol + lc;
-    dst[i] = gc < n ? W[(long)gc * K + kk] : 0.f;
+    const int cc = (int)(i & 3);
+    const int gtid = (int)((i >> 2) % GV_T);
+    const int j = (int)(((i >> 2) / GV_T) % w.njt);
+    const int part = (int)((i >> 2) / ((long)GV_T * w.njt));
+    const int cg = gtid % w.cg, ks = gtid / w.cg;
+    const int gc = gcol(w, part, cg * 4 + cc);
+    int kk;
+    bool ok;
+    if (w.hwy) {
+      const int tap = j / 11, kin = ks + KS * (j % 11);
+      ok = kin < HD;
+      kk = tap * HD + kin;
+    } else {
+      kk = ks + KS * j;
+      ok = kk < w.K;
+    }
+    dst[i] = (ok && gc < w.n) ? W[(long)gc * w.K + kk] : 0.f;
   }
 }
 
-template <int RT>
+template <int RT, bool PROF>
 int launch_rt(const DecParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)SM_TOTAL * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   DecParams pl = p;
   void* args[] = {&pl};
-  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT>, dim3(WS_GRID), dim3(NT), args, smem, s));
+  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT, PROF>, dim3(WS_GRID), dim3(NT), args, smem, s));
   ++g_launches;
   return kOk;
 }
 
 }  // namespace
 
-// Stage -> CTA-group layout (static).  Highway layers: 8 CTAs x 64 columns (32 H1 + the matching 32 H2).
-void ws_stage_layout(int s, const DecStage& d, WsStage* w) {
+// Stage -> CTA-group layout (static).  Highway layers: 8 CTAs x 64 columns (32 H1 + the matching 32 H2);
+// 1x1 convs: 128 columns per CTA, except AudioDec conv1 (K = 512): 64 columns so that a thread's weights
+// still fit its registers.
+void ws_stage_layout(const DecStage& d, WsStage* w) {
   w->n = d.n; w->k_seg = d.k_seg; w->ntaps = d.ntaps; w->dil = d.dil; w->pro = d.pro; w->bias_b = d.bias_b;
   w->K = d.ntaps * d.k_seg;
   w->bias = d.bias; w->g1 = d.g1; w->b1 = d.b1; w->g2 = d.g2; w->b2 = d.b2;
-  w->hwy = d.n == 2 * HD ? 1 : 0;
+  w->hwy = (d.n == 2 * HD && d.ntaps == 3) ? 1 : 0;
   if (w->hwy) { w->parts = 8; w->ncol = 64; }
-  else if (w->K > 256) { w->parts = 4; w->ncol = 64; }              // AudioDec conv1 (512 -> 256)
-  else if (w->K < 256) { w->parts = 1; w->ncol = 256; }             // AudioEnc conv1 (80 -> 256)
-  else if (d.n < 256) { w->parts = 1; w->ncol = 128; }              // AudioDec conv5 (256 -> 80), columns padded
-  else { w->parts = 2; w->ncol = 128; }                             // 256 -> 256
+  else if (w->K > 256) { w->parts = (d.n + 63) / 64; w->ncol = 64; }
+  else { w->parts = (d.n + 127) / 128; w->ncol = 128; }
   w->cg = w->ncol / 4;
+  const int ks = GV_T / w->cg;
+  w->nj = w->hwy ? 22 : (w->K + ks - 1) / ks;       // k iterations held in registers (<= 22)
+  w->njt = w->hwy ? 33 : w->nj;
   w->hist_depth = d.ntaps == 3 ? 2 * d.dil + 1 : 0;
-  (void)s;
 }
 
+size_t ws_image_floats(const WsStage& w) { return (size_t)w.parts * w.njt * GV_T * 4; }
+
 int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStream_t s) {
-  const long total = (long)w.parts * w.K * w.ncol;
+  SSV_CHECK(w.nj <= 22 && (w.hwy == 0 || w.K == 3 * HD), "decode: stage shape (n=%d, K=%d) does not fit the weight-stationary tiling", w.n, w.K);
+  const long total = (long)ws_image_floats(w);
   long g = (total + 255) / 256;
   if (g > 4096) g = 4096;
-  ws_pack_image_kernel<<<(int)g, 256, 0, s>>>(W_rowmajor, w.n, w.K, w.parts, w.ncol, w.hwy, dst);
+  ws_pack_image_kernel<<<(int)g, 256, 0, s>>>(W_rowmajor, w, dst);
   SSV_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -633,10 +817,9 @@ int launch_decode_ws(const DecParams& p, cudaStream_t s) {
   SSV_CHECK(p.B >= 1 && p.n_steps >= 1, "decode: empty launch");
   SSV_CHECK(p.B <= WS_MAX_BATCH, "decode: batch %d exceeds %d", p.B, WS_MAX_BATCH);
   SSV_CHECK(p.ws_stages && p.ws_raw && p.ws_sent && p.ws_hist, "decode: weight-stationary buffers missing");
-  if (p.R == 1) return launch_rt<1>(p, s);
-  if (p.R == 2) return launch_rt<2>(p, s);
-  SSV_CHECK(p.R == 4, "decode: micro-batch rows must be 1, 2 or 4");
-  return launch_rt<4>(p, s);
+  SSV_CHECK(p.R == 1 || p.R == 2 || p.R == 4, "decode: micro-batch rows must be 1, 2 or 4");
+  if (p.prof) return p.R == 1 ? launch_rt<1, true>(p, s) : p.R == 2 ? launch_rt<2, true>(p, s) : launch_rt<4, true>(p, s);
+  return p.R == 1 ? launch_rt<1, false>(p, s) : p.R == 2 ? launch_rt<2, false>(p, s) : launch_rt<4, false>(p, s);
 }
 
 }  // namespace ssv
