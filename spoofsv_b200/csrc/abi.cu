@@ -636,8 +636,10 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
       SSV_CUDA(cudaMemsetAsync(d->ws_sent, 0, (size_t)DEC_STAGES * d->maxB * WS_MAX_PARTS * sizeof(int), s));
       d->seq_base = 0;
     }
-    // rows per micro-batch: as many micro-batches in flight as the 24-stage pipeline can hold
-    d->R = B <= DEC_STAGES ? 1 : (B <= 2 * DEC_STAGES ? 2 : 4);
+    // rows per micro-batch: small batches are latency-bound (one row per micro-batch keeps most micro-batches in
+    // flight over the 24 stages); larger ones amortise the per-visit cost over 2 / 4 rows (measured on B200:
+    // B=32 R=1 51 us/frame vs R=2 63; B=64 R=2 63 vs R=1 72, R=4 84; B=128 R=2 117, R=4 118)
+    d->R = B <= 40 ? 1 : (B <= 128 ? 2 : 4);
     if (const char* e = getenv("SSV_DECODE_R")) {          // development knob
       const int r = atoi(e);
       if (r == 1 || r == 2 || r == 4) d->R = r;

@@ -48,11 +48,14 @@ constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks
 constexpr unsigned FULL = 0xffffffffu;
 
 // shared-memory carve-up (floats)
-constexpr int XBUF = 3 * TAPP * 4;                 // one X buffer: [rows <= 792][RT <= 4]
+constexpr int XROWS = 3 * TAPP;                    // rows of one X buffer ([rows][RT] floats)
+constexpr int XREGION = 8 * XROWS;                 // 8 / RT buffers: 8 (RT = 1), 4 (RT = 2), 2 (RT = 4)
+constexpr int MAXBUF = 8;
 constexpr int SM_WSM = 0;                          // [11][384] float4: tap-0 weights of a highway CTA
-constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [2][XBUF]
-constexpr int SM_PART = SM_X + 2 * XBUF;           // [12][RT][ncol <= 128] k-slice partial sums
-constexpr int SM_LN = SM_PART + 12 * 4 * 128;      // [4][256] LayerNorm parameters of my prologue
+constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [8 / RT][XROWS][RT]
+constexpr int SM_PART = SM_X + XREGION;            // [12][RT][ncol <= 128] k-slice partial sums
+constexpr int SM_REC = SM_PART + 12 * 4 * 128;     // [24 / RT][RT][256] stage inputs of the most recent visits (short-distance taps)
+constexpr int SM_LN = SM_REC + 24 * HD;            // [4][256] LayerNorm parameters of my prologue
 constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
 constexpr int SM_PMA = SM_BIAS + 128;              // [WS_MAX_BATCH] ints (attention stage only)
 constexpr int SM_TOTAL = SM_PMA + WS_MAX_BATCH;
@@ -181,11 +184,12 @@ __device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, c
 struct Ctx {                 // per-CTA constants shared by both roles
   int s, prev, part, prev_parts, G, B;
   float* smem;
-  uint64_t* tapsfull;        // [2] old taps of the X buffer have landed (cp.async)
-  uint64_t* curfull;         // [2] current tap (prologue output) is in the X buffer
-  uint64_t* empty;           // [2] mat-vec warps are done reading the X buffer
+  uint64_t* tapsfull;        // [8] old taps of the X buffer have landed (cp.async)
+  uint64_t* curfull;         // [8] current tap (prologue output) is in the X buffer
+  uint64_t* empty;           // [8] mat-vec warps are done reading the X buffer
   int* s_bad;
-  volatile long long* t_seen;   // profiling: SM clock at which the front end saw the producer's sentinel
+  volatile int* fe_done;      // [4] progress counters of the front-end warps
+  volatile long long* t_seen;   // profiling, [2][8]: SM clock at which the front end saw the producer's sentinel / handed X over
 };
 
 // global column (= tagged word index) of local column lc; highway CTAs own matching H1 / H2 slices
@@ -200,6 +204,7 @@ template <int RT, int CG, bool HWY, bool PROF>
 __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st, const Ctx& c, int gtid) {
   constexpr int KS = GV_T / CG;            // k-slices: 24 (64 columns) or 12 (128 columns)
   constexpr int NCOL = 4 * CG;
+  constexpr int NBUF = MAXBUF / RT;
   const int cg = gtid % CG, ks = gtid / CG;
   const int lane = gtid & 31, gwarp = gtid >> 5;
   float* parts = c.smem + SM_PART;
@@ -230,9 +235,9 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
   for (int step = 0; step < p.n_steps; ++step) {
     const int tag = p.seq_base + p.t_start + step + 1;
     for (int g = 0; g < c.G; ++g, ++v) {
-      const int q = (int)(v & 1);
-      const unsigned par = (unsigned)(v >> 1) & 1u;
-      const float* X = c.smem + SM_X + q * XBUF + ks * RT;
+      const int q = (int)(v % NBUF);
+      const unsigned par = (unsigned)(v / NBUF) & 1u;
+      const float* X = c.smem + SM_X + q * (XROWS * RT) + ks * RT;
       float acc[RT][4];
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
@@ -247,7 +252,7 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
         PROF_G(1);
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);
-        if (PROF && prof_on) wake_acc += prof_last - c.t_seen[1];
+        if (PROF && prof_on) wake_acc += prof_last - c.t_seen[8 + q];
 #pragma unroll
         for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[11 + j], X + (size_t)(2 * TAPP + KS * j) * RT);
       } else {
@@ -298,7 +303,7 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
         if ((v & 15) == 15 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) *c.s_bad = 2;   // seen at the next barrier
       }
       PROF_G(4);
-      if (PROF && prof_on) lat_acc += prof_last - *c.t_seen;
+      if (PROF && prof_on) lat_acc += prof_last - c.t_seen[q];
     }
   }
   if (prof_on) {
@@ -338,52 +343,89 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     prof_last = now_;                              \
   }
 
-  __shared__ volatile int s_fe_bad;
-  if (tid == 0) s_fe_bad = 0;
-  named_bar(2, FE_T);
-  long v = 0;
-  for (int step = 0; step < n_visits; ++step) {
+  // One warp per row; 4 / RT micro-batches are in flight in the front end (warp w: visit slot w / RT, row w % RT),
+  // so the wait for one producer overlaps the prologue of another micro-batch.
+  constexpr int NV = 4 / RT;
+  constexpr int NBUF = MAXBUF / RT;
+  constexpr int NREC = 3 * NBUF;           // a visit slot runs at most NBUF visits ahead of the slowest one
+  float* rec = c.smem + SM_REC;
+  volatile int* fe_done = c.fe_done;       // [4] visits completed by each front-end warp
+  const int vs = warp / RT, r = warp % RT;
+  const long total_visits = (long)n_visits * G;
+  long my_visits = 0;
+  for (long v = vs; v < total_visits; v += NV, ++my_visits) {
+    const int step = (int)(v / G), g = (int)(v - (long)step * G);
     const int t = p.t_start + step;
     const bool final_visit = s == 0 && step == p.n_steps;
     const int tag = p.seq_base + t + 1;                     // tag of everything produced for frame t
     const int tag_in = s == 0 ? tag - 1 : tag;              // stage 0 consumes frame t-1 of stage 23
     const bool need_wait = !(s == 0 && step == 0);
-    for (int g = 0; g < G; ++g, ++v) {
-      const int q = (int)(v & 1);
-      const long u = v >> 1;
-      float* X = c.smem + SM_X + q * XBUF;
-      const int row0 = g * RT;
-      const int nrows = min(RT, B - row0);
+    const int q = (int)(v % NBUF);
+    const long u = v / NBUF;
+    float* X = c.smem + SM_X + q * (XROWS * RT);
+    const int row0 = g * RT;
+    const int nrows = min(RT, B - row0);
+    bool bad = false;
+    {
       PROF_F(0);
-      if (!final_visit && u >= 1) {
-        mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag);   // on abort: fall through to the uniform exit
-      }
-      PROF_F(1);
 
-      // ---- 1. old taps t-2d, t-d of this micro-batch from my private ring -> X rows [0, 256) and [264, 520)
+      // ---- 1. my row of the old taps t-2d, t-d -> X rows [0, 256) and [264, 520).  A tap that one of the last
+      //         NBUF + NV visits produced is still in the CTA's recent-row ring (shared memory; the warp that wrote
+      //         it publishes its progress in fe_done).  Older ones come from my private ring in global memory: their
+      //         writes precede my previous visit's "empty" wait through the curfull -> mat-vec -> empty barrier chain
+      //         (a row is overwritten in the recent ring only by a visit 3 NBUF later, which cannot start before this
+      //         visit has been consumed).
       if (st.ntaps == 3) {
-        const int chunks = HD * RT / 4;                      // 16-byte chunks per tap block
-        for (int i = tid; i < 2 * chunks; i += FE_T) {
-          const int j = i / chunks, c4 = i - j * chunks;
-          const int tt = t - (2 - j) * st.dil;
-          const bool ok = tt >= 0;
-          const int slot = ok ? tt % st.hist_depth : 0;
-          const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT) + c4 * 4;
-          cp_async16(X + (size_t)j * TAPP * RT + c4 * 4, src, ok);
+        float tp[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int back = (2 - j) * st.dil;                 // frames back
+          const int tt = t - back;
+          const long dist = (long)back * G;                  // visits back
+          if (tt < 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tp[j][i] = 0.f;
+          } else if (tt >= p.t_start && dist < NBUF + NV) {
+            const long d = v - dist;
+            const int dw = (int)(d % NV) * RT + r;           // the warp that produced row r of visit d
+            const int need = (int)(d / NV) + 1;
+            unsigned spins = 0;
+            while (fe_done[dw] < need) {
+              if ((++spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) { bad = true; break; }
+            }
+            __threadfence_block();
+            const float* src = rec + ((size_t)(d % NREC) * RT + r) * HD;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tp[j][i] = src[lane + 32 * i];
+          } else {
+            const int slot = tt % st.hist_depth;
+            const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT) + r;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tp[j][i] = __ldcg(src + (size_t)(lane + 32 * i) * RT);
+          }
         }
-        cp_async_mbar_arrive(&c.tapsfull[q]);
+        if (u >= 1) {
+          if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) X[((size_t)j * TAPP + lane + 32 * i) * RT + r] = tp[j][i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c.tapsfull[q]);
+      } else if (!final_visit && u >= 1) {
+        if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
       }
       PROF_F(2);
 
       // ---- 2./3. wait for the producers of my input row, then the prologue: u_t -> X[koff ..][r]
-      if (warp < RT) {
-        const int r = warp, b = row0 + r;
+      {
+        const int b = row0 + r;
         float* xcur = X + (size_t)koff * RT + r;             // channel ch at xcur[ch * RT]
         if (r >= nrows) {
           if (!final_visit)
             for (int ch = lane; ch < st.k_seg; ch += 32) xcur[(size_t)ch * RT] = 0.f;
         } else {
-          bool bad = false;
           long long t0 = 0;
           unsigned spins = 0;
           auto spin_check = [&]() {        // bounded spinning: flag the abort and leave
@@ -402,7 +444,8 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
               if (__any_sync(FULL, bad)) { bad = true; break; }
             }
           }
-          if (PROF && prof_on) { PROF_F(3); *c.t_seen = prof_last; }
+          PROF_F(3);
+          if (PROF && p.prof != nullptr && r == 0 && lane == 0) c.t_seen[q] = clock64();
           const Word* R = raw_in + (size_t)b * WS_WORDS;
           const int pro = st.pro;
           if (pro == PRO_X) {
@@ -617,22 +660,37 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
               }
             }
           }
-          if (bad && lane == 0) s_fe_bad = 1;
         }
       }
       if (final_visit) continue;                 // stage 0 after the last frame: prologue only
       PROF_F(6);
-      named_bar(2, FE_T);                        // every row of the micro-batch is in X
-      if (tid == 0) { mbar_arrive(&c.curfull[q]); if (PROF && prof_on) c.t_seen[1] = clock64(); }
-      if (s_fe_bad) return;                      // uniform: written before the barrier
-      if (tid == 0 && (v & 15) == 15 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) s_fe_bad = 1;   // seen at the next barrier
-
-      // ---- 4. my stage input of frame t joins my private ring (taps of later frames)
+      __syncwarp();                              // my row of the micro-batch is in X
+      // ---- 4. my stage input of frame t joins the recent-row ring and my private ring (taps of later frames)
       if (st.ntaps == 3) {
         const int slot = t % st.hist_depth;
-        float* dst = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT);
-        for (int i = tid; i < HD * RT / 4; i += FE_T)
-          __stcg(reinterpret_cast<float4*>(dst) + i, *reinterpret_cast<const float4*>(X + (size_t)koff * RT + (size_t)i * 4));
+        float* dst = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT) + r;
+        float* rdst = rec + ((size_t)(v % NREC) * RT + r) * HD;
+        const float* xcur = X + (size_t)koff * RT + r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ch = lane + 32 * i;
+          const float xv = xcur[(size_t)ch * RT];
+          rdst[ch] = xv;
+          __stcg(dst + (size_t)ch * RT, xv);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        mbar_arrive(&c.curfull[q]);              // release: X row, recent row and ring stores precede it
+        if (PROF && p.prof != nullptr && r == 0) c.t_seen[8 + q] = clock64();
+        __threadfence_block();
+        fe_done[warp] = (int)my_visits + 1;
+      }
+      if (__any_sync(FULL, bad)) return;         // aborted launch: the mat-vec warps leave through their own bounded waits
+      if ((my_visits & 15) == 15) {               // a launch aborted elsewhere: leave
+        int ab = 0;
+        if (lane == 0) ab = *reinterpret_cast<volatile int*>(p.abort_flag);
+        if (__shfl_sync(FULL, ab, 0) != 0) return;
       }
       PROF_F(5);
     }
@@ -640,7 +698,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
   if (prof_on) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 16 + i] = prof_acc[i];
-    p.prof[(size_t)blockIdx.x * 16 + 15] = v > 0 ? v : 1;
+    p.prof[(size_t)blockIdx.x * 16 + 15] = my_visits > 0 ? my_visits : 1;
   }
 #undef PROF_F
 }
@@ -648,9 +706,10 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 template <int RT, bool PROF>
 __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t bars[6];
+  __shared__ __align__(8) uint64_t bars[3 * MAXBUF];
   __shared__ int s_bad;
-  __shared__ long long s_t_seen[2];
+  __shared__ int s_fe_done[4];
+  __shared__ long long s_t_seen[2 * MAXBUF];
   const int tid = threadIdx.x;
 
   // ---- which stage / column slice am I?
@@ -671,9 +730,10 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   c.B = p.B;
   c.smem = smem;
   c.tapsfull = bars;
-  c.curfull = bars + 2;
-  c.empty = bars + 4;
+  c.curfull = bars + MAXBUF;
+  c.empty = bars + 2 * MAXBUF;
   c.s_bad = &s_bad;
+  c.fe_done = s_fe_done;
   c.t_seen = s_t_seen;
 
   // ---- one-time loads: tap-0 weights of a highway CTA, LayerNorm parameters, bias, alignment state
@@ -684,7 +744,7 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
       float4* dst = reinterpret_cast<float4*>(smem + SM_WSM);
       for (int i = tid; i < 11 * GV_T; i += NT) dst[i] = __ldg(img + i);
     }
-    for (int i = tid; i < 2 * XBUF; i += NT) smem[SM_X + i] = 0.f;      // padding rows of X stay zero for good
+    for (int i = tid; i < XREGION; i += NT) smem[SM_X + i] = 0.f;       // padding rows of X stay zero for good
     for (int i = tid; i < 4 * HD; i += NT) {
       const int which = i / HD, ch = i % HD;
       const float* src = which == 0 ? st.g1 : which == 1 ? st.b1 : which == 2 ? st.g2 : st.b2;
@@ -705,9 +765,12 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
     }
     if (tid == 0) {
       s_bad = 0;
-      mbar_init(&bars[0], FE_T); mbar_init(&bars[1], FE_T);     // tapsfull: one cp.async arrival per front-end thread
-      mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);           // curfull
-      mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);           // empty
+      s_fe_done[0] = s_fe_done[1] = s_fe_done[2] = s_fe_done[3] = 0;
+      for (int i = 0; i < MAXBUF; ++i) {
+        mbar_init(&bars[i], RT);                   // tapsfull: one arrival per row
+        mbar_init(&bars[MAXBUF + i], RT);          // curfull: one arrival per row
+        mbar_init(&bars[2 * MAXBUF + i], 1);       // empty
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
