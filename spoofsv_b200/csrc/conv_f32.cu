@@ -305,7 +305,10 @@ int launch_conv_f32(const ConvArgs& a, cudaStream_t s) {
     case 4:  return launch_inst<32, 4, 3>(a, s);
     case 8:  return launch_inst<32, 8, 3>(a, s);
     case 9:  return launch_inst<32, 9, 3>(a, s);
-    case 16: return launch_inst<16, 16, 3>(a, s);
+    case 16:
+      // d = 512 layers stream a 6.3 MB weight matrix per CTA from L2: 32-row tiles halve that traffic and make the
+      // inner loop FMA-bound (16 weight loads per 128 FMAs); small problems keep 16-row tiles for more CTAs
+      return a.M >= 32 * 96 ? launch_inst<32, 16, 3>(a, s) : launch_inst<16, 16, 3>(a, s);
     default: break;
   }
   set_error("conv_f32: unsupported output width %d (padded %d)", a.n, n_pad);
