@@ -689,8 +689,8 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
     std::vector<long long> h((size_t)DEC_MAX_GRID * 16);
     SSV_CUDA(cudaMemcpy(h.data(), d->prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     const char* nm_old[7] = {"loop-top", "arm/arrive+prefetch-issue", "wait", "prologue", "cp.async-wait+sync", "gemv", "tail (sync / bulk-copy issue)"};
-    const char* nm_ws[15] = {"FE loop-top", "FE wait X buffer empty", "FE tap prefetch issue", "FE wait for producer sentinel", "FE row load (tags verified)", "FE barrier + ring write", "FE prologue math + X stores", "-",
-                             "MV wait taps", "MV old taps (2/3)", "MV wait current tap", "MV current tap + k-slice store", "MV reduce + publish",
+    const char* nm_ws[15] = {"FE loop-top", "FE wait X buffer empty", "FE tap prefetch issue", "FE wait for producer sentinel", "FE row load (tags verified)", "FE ring write + tap prefetch", "FE prologue math + X stores", "MV reducer: wait for the 12 k-slices",
+                             "MV wait taps", "MV old taps (2/3)", "MV wait current tap", "MV current tap + k-slice store", "MV reducer: reduce + publish",
                              "sentinel seen -> my sentinel out", "curfull arrive -> MV awake (highway)"};
     const char* const* nm = ws ? nm_ws : nm_old;
     fprintf(stderr, "[decode prof] impl=%d B=%d R=%d steps=%d (cycles per stage visit: mean / max over CTAs)\n", d->impl, d->B, d->R, n_steps);
@@ -699,7 +699,8 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
       double sum = 0, mx = 0; int cnt = 0;
       for (int c = 0; c < DEC_MAX_GRID; ++c) {
         if (h[(size_t)c * stride + cnt_slot] == 0) continue;
-        const double v = (double)h[(size_t)c * stride + i] / (double)h[(size_t)c * stride + cnt_slot];
+        double v = (double)h[(size_t)c * stride + i] / (double)h[(size_t)c * stride + cnt_slot];
+        if (ws && i >= 7) v /= 4.0 / d->R;          // mat-vec slots cover all visits, the count is front-end warp 0's share
         sum += v; mx = v > mx ? v : mx; ++cnt;
       }
       fprintf(stderr, "  %-32s %9.0f / %9.0f\n", nm[i], cnt ? sum / cnt : 0.0, mx);

@@ -110,11 +110,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // suspend-time hint: sleep in hardware, do not spin
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
       : "memory");
   return ok != 0;
 }
@@ -187,6 +187,9 @@ struct Ctx {                 // per-CTA constants shared by both roles
   uint64_t* tapsfull;        // [8] old taps of the X buffer have landed (cp.async)
   uint64_t* curfull;         // [8] current tap (prologue output) is in the X buffer
   uint64_t* empty;           // [8] mat-vec warps are done reading the X buffer
+  uint64_t* pfull;           // [2] k-slice partial sums of all 12 mat-vec warps are in shared memory
+  uint64_t* pfree;           // [2] the reducer warp(s) are done with the partial-sum buffer
+  uint64_t* rdone;           // [2] second reducer warp has published its half (wide tiles)
   int* s_bad;
   volatile int* fe_done;      // [4] progress counters of the front-end warps
   volatile long long* t_seen;   // profiling, [2][8]: SM clock at which the front end saw the producer's sentinel / handed X over
@@ -353,6 +356,8 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
   const int vs = warp / RT, r = warp % RT;
   const long total_visits = (long)n_visits * G;
   long my_visits = 0;
+  float tp[2][8];                          // my row of the two old taps (global-ring ones are prefetched a visit ahead)
+  bool have_pref = false;
   for (long v = vs; v < total_visits; v += NV, ++my_visits) {
     const int step = (int)(v / G), g = (int)(v - (long)step * G);
     const int t = p.t_start + step;
@@ -376,7 +381,6 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
       //         (a row is overwritten in the recent ring only by a visit 3 NBUF later, which cannot start before this
       //         visit has been consumed).
       if (st.ntaps == 3) {
-        float tp[2][8];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int back = (2 - j) * st.dil;                 // frames back
@@ -390,19 +394,20 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
             const int dw = (int)(d % NV) * RT + r;           // the warp that produced row r of visit d
             const int need = (int)(d / NV) + 1;
             unsigned spins = 0;
-            while (fe_done[dw] < need) {
+            while (fe_done[dw] < need) {          // sleep between looks: a spinning warp steals issue slots from the mat-vec warps
+              __nanosleep(100);
               if ((++spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) { bad = true; break; }
             }
             __threadfence_block();
             const float* src = rec + ((size_t)(d % NREC) * RT + r) * HD;
 #pragma unroll
             for (int i = 0; i < 8; ++i) tp[j][i] = src[lane + 32 * i];
-          } else {
+          } else if (!have_pref) {
             const int slot = tt % st.hist_depth;
             const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT) + r;
 #pragma unroll
             for (int i = 0; i < 8; ++i) tp[j][i] = __ldcg(src + (size_t)(lane + 32 * i) * RT);
-          }
+          }                                                  // else: prefetched at the end of my previous visit
         }
         if (u >= 1) {
           if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
@@ -687,6 +692,27 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
         fe_done[warp] = (int)my_visits + 1;
       }
       if (__any_sync(FULL, bad)) return;         // aborted launch: the mat-vec warps leave through their own bounded waits
+      // ---- 5. global-ring taps of my next visit: issue the loads now, they land while I wait for its producer.
+      //         (Rows at least NBUF + NV visits old: written before the "empty" wait this visit has passed.)
+      have_pref = false;
+      if (st.ntaps == 3 && v + NV < total_visits) {
+        const long v2 = v + NV;
+        const int step2 = (int)(v2 / G), g2 = (int)(v2 - (long)step2 * G);
+        const int t2 = p.t_start + step2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int back = (2 - j) * st.dil;
+          const int tt = t2 - back;
+          const long dist = (long)back * G;
+          if (tt >= 0 && !(tt >= p.t_start && dist < NBUF + NV)) {
+            const int slot = tt % st.hist_depth;
+            const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g2) * (HD * RT) + r;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tp[j][i] = __ldcg(src + (size_t)(lane + 32 * i) * RT);
+          }
+        }
+        have_pref = true;
+      }
       if ((my_visits & 15) == 15) {               // a launch aborted elsewhere: leave
         int ab = 0;
         if (lane == 0) ab = *reinterpret_cast<volatile int*>(p.abort_flag);
@@ -706,7 +732,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 template <int RT, bool PROF>
 __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t bars[3 * MAXBUF];
+  __shared__ __align__(8) uint64_t bars[3 * MAXBUF + 6];
   __shared__ int s_bad;
   __shared__ int s_fe_done[4];
   __shared__ long long s_t_seen[2 * MAXBUF];
@@ -732,6 +758,9 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   c.tapsfull = bars;
   c.curfull = bars + MAXBUF;
   c.empty = bars + 2 * MAXBUF;
+  c.pfull = bars + 3 * MAXBUF;
+  c.pfree = bars + 3 * MAXBUF + 2;
+  c.rdone = bars + 3 * MAXBUF + 4;
   c.s_bad = &s_bad;
   c.fe_done = s_fe_done;
   c.t_seen = s_t_seen;
@@ -770,6 +799,12 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
         mbar_init(&bars[i], RT);                   // tapsfull: one arrival per row
         mbar_init(&bars[MAXBUF + i], RT);          // curfull: one arrival per row
         mbar_init(&bars[2 * MAXBUF + i], 1);       // empty
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars[3 * MAXBUF + i], 12);                            // pfull
+        const int nrw = RT * st.ncol > 128 ? RT * st.ncol / 128 : 1;     // reducer warps (as in gemv_role)
+        mbar_init(&bars[3 * MAXBUF + 2 + i], nrw);                       // pfree
+        mbar_init(&bars[3 * MAXBUF + 4 + i], nrw > 1 ? nrw - 1 : 1);     // rdone
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
