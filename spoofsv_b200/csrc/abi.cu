@@ -294,6 +294,13 @@ struct ssv_decoder {
   int64_t* h_textid = nullptr;
   float *h_spk = nullptr, *h_K = nullptr, *h_V = nullptr, *h_Y = nullptr, *h_A = nullptr, *h_lin = nullptr;
   long long* h_traj = nullptr;
+  cudaStream_t copy_stream = nullptr;     // D2H of finished SSRN chunks
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  ~ssv_decoder() {
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (int i = 0; i < 2; ++i)
+      if (copy_ev[i]) cudaEventDestroy(copy_ev[i]);
+  }
 };
 
 struct ssv_ssrn {
@@ -952,13 +959,32 @@ int ssv_synthesize_host(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const int
   SSV_TRY(ssv_decoder_begin(d, d->h_K, d->h_V, d->h_spk, B, N, d->h_Y, d->h_A,
                             reinterpret_cast<int64_t*>(d->h_traj), T, s));
   SSV_TRY(ssv_decoder_run(d, T, s));
-  SSV_TRY(ssv_ssrn_fwd(sr, d->h_Y, (long)F * T, T, 1, B, T, d->h_lin, ssrn_precision, s));
-  SSV_CUDA(cudaMemcpyAsync(lin_host, d->h_lin, sizeof(float) * (size_t)B * O * 4 * T, cudaMemcpyDeviceToHost, s));
+  // SSRN in utterance chunks: the D2H of chunk i (114 MB in all at B = 64) runs on a second stream under the SSRN of
+  // chunk i + 1
+  if (d->copy_stream == nullptr) {
+    SSV_CUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) SSV_CUDA(cudaEventCreateWithFlags(&d->copy_ev[i], cudaEventDisableTiming));
+  }
+  {
+    const int chunk = B >= 32 ? (B + 1) / 2 : B;
+    const size_t lin_per_utt = (size_t)O * 4 * T;
+    int ci = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
+      const int nb = B - b0 < chunk ? B - b0 : chunk;
+      SSV_TRY(ssv_ssrn_fwd(sr, d->h_Y + (size_t)b0 * F * T, (long)F * T, T, 1, nb, T, d->h_lin + b0 * lin_per_utt,
+                           ssrn_precision, s));
+      SSV_CUDA(cudaEventRecord(d->copy_ev[ci & 1], s));
+      SSV_CUDA(cudaStreamWaitEvent(d->copy_stream, d->copy_ev[ci & 1], 0));
+      SSV_CUDA(cudaMemcpyAsync(lin_host + b0 * lin_per_utt, d->h_lin + b0 * lin_per_utt, sizeof(float) * nb * lin_per_utt,
+                               cudaMemcpyDeviceToHost, d->copy_stream));
+    }
+  }
   if (mel_host) SSV_CUDA(cudaMemcpyAsync(mel_host, d->h_Y, sizeof(float) * (size_t)B * F * T, cudaMemcpyDeviceToHost, s));
   if (A_host) SSV_CUDA(cudaMemcpyAsync(A_host, d->h_A, sizeof(float) * (size_t)B * N * T, cudaMemcpyDeviceToHost, s));
   if (pma_traj_host)
     SSV_CUDA(cudaMemcpyAsync(pma_traj_host, d->h_traj, sizeof(long long) * (size_t)T * B, cudaMemcpyDeviceToHost, s));
   SSV_TRY(ssv_decoder_check(d, s));
+  SSV_CUDA(cudaStreamSynchronize(d->copy_stream));
   if (ssrn_precision == SSV_PREC_BF16) SSV_TRY(tc_check_error());
   return kOk;
 }

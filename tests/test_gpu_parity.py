@@ -353,3 +353,35 @@ def test_ssrn_bf16(golden_dir, cuda_models_k, cuda_models):
     ref = m2b(mel)
     assert _rel_l2(a, ref) <= BF16_TOL
     assert float(a.min()) >= 0 and float(a.max()) <= 1
+
+
+# --------------------------------------------------------------------------- corpus driver
+def test_corpus_driver_matches_per_speaker_reference_loop(tmp_path, write_driver_cfg):
+    """generate_test_utterances driver (K/V hoisted out of the speaker loop, units batched across speakers)
+    == the reference's per-speaker AR loop + SSRN, as restated by the oracle."""
+    import json
+    from spoofsv_b200 import generate_test_utterances as G
+    path, cfg = write_driver_cfg(tmp_path, n_lines=3, speakers=("p225", "p226"))
+    args = G.build_parser().parse_args(["-C", str(path), "-T", "t", "--eval_utt_num", "3", "--batch", "4",
+                                        "--ssrn_precision", "fp32", "--random_init", "0",
+                                        "--save_spectrogram", str(tmp_path / "out")])
+    got = {}
+
+    def on_batch(group, lin, state):
+        for u, spec, y in zip(group, lin, state["Y"].cpu()):
+            got[(u.speaker, u.sentence)] = (spec.copy(), y.clone())
+
+    stats = G.run(args, on_batch)
+    assert stats["utterances"] == 6 and stats["frames"] == 10
+    sd1, sd2 = W.state_dicts(0)
+    names, emb, lines = W.load_fixtures()
+    ids = O.pad_text_ids([O.text2id(s) for s in lines[:3]])
+    for si, spk in enumerate(("p225", "p226")):
+        e = torch.from_numpy(emb[names.index(spk)])[None, :, None].repeat(3, 1, 1)
+        with torch.no_grad():
+            oY, oA, otraj, olin = O.synthesize(sd1, sd2, ids, e, 10)
+        for k in range(3):
+            spec, y = got[(si, k)]
+            assert _maxabs(y, oY[k]) <= FP32_TOL and _maxabs(_t(spec), olin[k]) <= FP32_TOL
+            saved = np.load(tmp_path / "out" / f"s{spk[1:]}" / f"s{spk[1:]}_{k + 1:03d}.npy")
+            assert np.array_equal(saved, spec)

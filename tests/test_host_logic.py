@@ -84,3 +84,35 @@ def test_two_rank_gloo_sharding(tmp_path):
     r = torch.load(tmp_path / "r0.pt")
     assert bool((r["cover"] == 1).all())          # every unit owned by exactly one rank, no collective on data
     assert float(r["tmax"]) == 2.0 and int(r["count"]) == n_units
+
+
+# --------------------------------------------------------------------------- corpus driver (CLI surface)
+def test_driver_cli_flags_match_the_reference():
+    from spoofsv_b200 import generate_test_utterances as G
+    ps = G.build_parser()
+    a = ps.parse_args(["-C", "config.json", "-T", "19-08-17_13-05-42"])            # reference defaults (:46-50)
+    assert (a.train_spk_num, a.enroll_utt_num, a.eval_utt_num) == (88, 3, 20)
+    a = ps.parse_args(["--configuration", "c.json", "--current_time", "x", "--eval_utt_num", "5"])
+    assert a.configuration == "c.json" and a.current_time == "x" and a.eval_utt_num == 5
+    with pytest.raises(SystemExit):
+        ps.parse_args(["-C", "c.json"])                                             # -T is required, as in the reference
+
+
+def test_driver_texts_speakers_plan(tmp_path, write_driver_cfg):
+    from spoofsv_b200 import generate_test_utterances as G
+    path, cfg = write_driver_cfg(tmp_path)
+    cfg2 = G.load_config(str(path))
+    ids = G.read_texts(cfg2, 4)
+    _, _, lines = W.load_fixtures()
+    want = O.pad_text_ids([O.text2id(s) for s in lines[:4]])                       # reference padding: batch maximum
+    assert np.array_equal(ids, want[:, 0, :].numpy())
+    with pytest.raises(ValueError):
+        G.read_texts(cfg2, 7)
+    assert G.list_speakers(cfg2) == ["p225", "p226", "p227"]
+    (tmp_path / "no_corpus" / "wav22" / "p300").mkdir(parents=True)                 # with the corpus: its directory listing
+    assert G.list_speakers(cfg2) == ["p300"]
+    assert G.output_name("p225", 0) == "s225/s225_001"                              # reference wav naming (:139)
+    # two ranks cover every (speaker, sentence) unit exactly once, speaker-major
+    seen = [u for r in range(2) for b in G.plan(3, 4, 2, r, 5) for u in b]
+    assert seen == [Unit(s, k) for s in range(3) for k in range(4)]
+    assert [len(b) for b in G.plan(3, 4, 1, 0, 5)] == [5, 5, 2]
