@@ -308,7 +308,15 @@ int launch_conv_f32(const ConvArgs& a, cudaStream_t s) {
     case 16:
       // d = 512 layers stream a 6.3 MB weight matrix per CTA from L2: 32-row tiles halve that traffic and make the
       // inner loop FMA-bound (16 weight loads per 128 FMAs); small problems keep 16-row tiles for more CTAs
-      return a.M >= 32 * 96 ? launch_inst<32, 16, 3>(a, s) : launch_inst<16, 16, 3>(a, s);
+      if (a.M < 32 * 96) return launch_inst<16, 16, 3>(a, s);
+      {
+        // one CTA per SM: pick the tile height that wastes the least of the last wave (TextEnc at B = 64 is
+        // 3712 rows: 116 CTAs of 32 rows leave 32 of 148 SMs idle, 133 CTAs of 28 rows do not)
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        auto cost = [&](int bm) { const long ctas = (a.M + bm - 1) / bm; return ((ctas + sms - 1) / sms) * bm; };
+        return cost(28) < cost(32) ? launch_inst<28, 16, 3>(a, s) : launch_inst<32, 16, 3>(a, s);
+      }
     default: break;
   }
   set_error("conv_f32: unsupported output width %d (padded %d)", a.n, n_pad);

@@ -530,8 +530,9 @@ __global__ void __launch_bounds__(NT, 1) conv_tc_kernel(const __grid_constant__ 
           norm(c, ra);
           if (two) { tmem_wait16(ra2); norm(c + 16, ra2); }
         }
-        // zero the tail of the padded row that no CTA's columns cover (e.g. 544..575 of a 576-wide row)
-        if (row_ok && hsel == 1 && rank == (uint32_t)(a.cluster_n - 1)) {
+        // zero the tail of the padded row that no CTA's columns cover (e.g. 544..575 of a 576-wide row); with a
+        // staged output the coalesced copy-out below does it
+        if (!staged && row_ok && hsel == 1 && rank == (uint32_t)(a.cluster_n - 1)) {
           for (int c = a.cluster_n * NL; c < a.y_cols; ++c) {
             if (f32) static_cast<float*>(a.Y)[yoff + c] = 0.f;
             else static_cast<__nv_bfloat16*>(a.Y)[yoff + c] = __float2bfloat16_rn(0.f);
@@ -552,6 +553,12 @@ __global__ void __launch_bounds__(NT, 1) conv_tc_kernel(const __grid_constant__ 
         const uint8_t* src = out_s + (size_t)r * out_rs;
         for (int ch = lane; ch < chunks; ch += 32)
           *reinterpret_cast<uint4*>(dst + ch * 16) = *reinterpret_cast<const uint4*>(src + ch * 16);
+        // last CTA of the row: zero the padded tail no CTA's columns cover (e.g. 544..575 of a 576-wide row)
+        if (!hwy && a.epi != EPI_NONE && rank == (uint32_t)(a.cluster_n - 1)) {
+          const int tail_bytes = (a.y_cols - a.cluster_n * NL) * (int)esz;
+          for (int o = lane * 16; o < tail_bytes; o += 32 * 16)
+            *reinterpret_cast<uint4*>(dst + (size_t)chunks * 16 + o) = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
     }
     if (ptime) {

@@ -58,7 +58,8 @@ constexpr int SM_REC = SM_PART + 12 * 4 * 128;     // [24 / RT][RT][256] stage i
 constexpr int SM_LN = SM_REC + 24 * HD;            // [4][256] LayerNorm parameters of my prologue
 constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
 constexpr int SM_PMA = SM_BIAS + 128;              // [WS_MAX_BATCH] ints (attention stage only)
-constexpr int SM_TOTAL = SM_PMA + WS_MAX_BATCH;
+constexpr int SM_KV = SM_PMA + WS_MAX_BATCH;        // [4 warps][K window 3 | V window 3][256]: attention rows prefetched by cp.async
+constexpr int SM_TOTAL = SM_KV + 4 * 6 * HD;
 
 struct __align__(8) Word { float v; int tag; };
 
@@ -234,11 +235,11 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
   }
 
   Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)c.s * c.B * WS_WORDS;
-  long v = 0;                               // visit counter (same sequence as the front end)
+  int v = 0;                                // visit counter (same sequence as the front end; < 2^31: checked at launch)
   for (int step = 0; step < p.n_steps; ++step) {
     const int tag = p.seq_base + p.t_start + step + 1;
     for (int g = 0; g < c.G; ++g, ++v) {
-      const int q = (int)(v % NBUF);
+      const int q = v % NBUF;
       const unsigned par = (unsigned)(v / NBUF) & 1u;
       const float* X = c.smem + SM_X + q * (XROWS * RT) + ks * RT;
       float acc[RT][4];
@@ -354,19 +355,21 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
   float* rec = c.smem + SM_REC;
   volatile int* fe_done = c.fe_done;       // [4] visits completed by each front-end warp
   const int vs = warp / RT, r = warp % RT;
-  const long total_visits = (long)n_visits * G;
-  long my_visits = 0;
+  const int total_visits = n_visits * G;
+  int my_visits = 0;
+  int step = 0, g = vs;                    // (frame, micro-batch) of visit v, advanced incrementally
+  while (g >= G) { g -= G; ++step; }
   float tp[2][8];                          // my row of the two old taps (global-ring ones are prefetched a visit ahead)
   bool have_pref = false;
-  for (long v = vs; v < total_visits; v += NV, ++my_visits) {
-    const int step = (int)(v / G), g = (int)(v - (long)step * G);
+  for (int v = vs; v < total_visits; v += NV, ++my_visits, g += NV) {
+    while (g >= G) { g -= G; ++step; }
     const int t = p.t_start + step;
     const bool final_visit = s == 0 && step == p.n_steps;
     const int tag = p.seq_base + t + 1;                     // tag of everything produced for frame t
     const int tag_in = s == 0 ? tag - 1 : tag;              // stage 0 consumes frame t-1 of stage 23
     const bool need_wait = !(s == 0 && step == 0);
-    const int q = (int)(v % NBUF);
-    const long u = v / NBUF;
+    const int q = v % NBUF;
+    const int u = v / NBUF;
     float* X = c.smem + SM_X + q * (XROWS * RT);
     const int row0 = g * RT;
     const int nrows = min(RT, B - row0);
@@ -385,14 +388,14 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
         for (int j = 0; j < 2; ++j) {
           const int back = (2 - j) * st.dil;                 // frames back
           const int tt = t - back;
-          const long dist = (long)back * G;                  // visits back
+          const int dist = back * G;                         // visits back
           if (tt < 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) tp[j][i] = 0.f;
           } else if (tt >= p.t_start && dist < NBUF + NV) {
-            const long d = v - dist;
-            const int dw = (int)(d % NV) * RT + r;           // the warp that produced row r of visit d
-            const int need = (int)(d / NV) + 1;
+            const int d = v - dist;
+            const int dw = (d % NV) * RT + r;                // the warp that produced row r of visit d
+            const int need = d / NV + 1;
             unsigned spins = 0;
             while (fe_done[dw] < need) {          // sleep between looks: a spinning warp steals issue slots from the mat-vec warps
               __nanosleep(100);
@@ -422,6 +425,32 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
         if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
       }
       PROF_F(2);
+
+      // ---- 1b. attention stage: the K / V rows of this utterance's 3-character window are known as soon as the
+      //          previous frame of the micro-batch has updated pma -- fetch them (cp.async -> shared memory) under the
+      //          wait for the producer instead of after it (two dependent L2 round trips off the critical path)
+      bool kv_pref = false;
+      float* kvs = c.smem + SM_KV + warp * (6 * HD);
+      if (st.pro == PRO_ATT && r < nrows) {
+        const int d = v - G;                                 // the visit that wrote pma of this row last
+        bool ready = d < 0;
+        if (!ready && G < NBUF + NV) ready = fe_done[(d % NV) * RT + r] >= d / NV + 1;
+        else if (!ready) ready = true;                       // at least NBUF + NV visits back: consumed long ago
+        if (ready) {
+          __threadfence_block();
+          const int bq = row0 + r;
+          const int p0 = pma_s[bq];
+          const int cnt = min(p0 + 2, p.N - 1) - p0 + 1;
+          const float* kp = p.Kt + ((size_t)bq * p.N + p0) * HD;
+          const float* vp = p.Vt + ((size_t)bq * p.N + p0) * HD;
+          for (int i = lane; i < cnt * (HD / 4); i += 32) {
+            cp_async16(kvs + i * 4, kp + i * 4, true);
+            cp_async16(kvs + 3 * HD + i * 4, vp + i * 4, true);
+          }
+          asm volatile("cp.async.commit_group;\n" ::: "memory");
+          kv_pref = true;
+        }
+      }
 
       // ---- 2./3. wait for the producers of my input row, then the prologue: u_t -> X[koff ..][r]
       {
@@ -604,18 +633,24 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
               const int cnt = min(p0 + 2, p.N - 1) - p0 + 1;
               const float* kp = p.Kt + ((size_t)b * p.N + p0) * HD;
               const float* vp = p.Vt + ((size_t)b * p.N + p0) * HD;
+              if (kv_pref) {                                  // window rows already in shared memory
+                asm volatile("cp.async.wait_all;\n" ::: "memory");
+                __syncwarp();
+                kp = kvs;
+                vp = kvs + 3 * HD;
+              }
               float l0 = 0.f, l1 = 0.f, l2 = 0.f;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int ch = 2 * lane + 64 * i;
-                const float2 k0 = __ldg(reinterpret_cast<const float2*>(kp + ch));
+                const float2 k0 = *reinterpret_cast<const float2*>(kp + ch);
                 l0 = fmaf(k0.x, uu[2 * i], l0); l0 = fmaf(k0.y, uu[2 * i + 1], l0);
                 if (cnt > 1) {
-                  const float2 k1 = __ldg(reinterpret_cast<const float2*>(kp + HD + ch));
+                  const float2 k1 = *reinterpret_cast<const float2*>(kp + HD + ch);
                   l1 = fmaf(k1.x, uu[2 * i], l1); l1 = fmaf(k1.y, uu[2 * i + 1], l1);
                 }
                 if (cnt > 2) {
-                  const float2 k2 = __ldg(reinterpret_cast<const float2*>(kp + 2 * HD + ch));
+                  const float2 k2 = *reinterpret_cast<const float2*>(kp + 2 * HD + ch);
                   l2 = fmaf(k2.x, uu[2 * i], l2); l2 = fmaf(k2.y, uu[2 * i + 1], l2);
                 }
               }
@@ -637,14 +672,14 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int ch = 2 * lane + 64 * i;
-                const float2 v0 = __ldg(reinterpret_cast<const float2*>(vp + ch));
+                const float2 v0 = *reinterpret_cast<const float2*>(vp + ch);
                 float rx = a0 * v0.x, ry = a0 * v0.y;
                 if (cnt > 1) {
-                  const float2 v1 = __ldg(reinterpret_cast<const float2*>(vp + HD + ch));
+                  const float2 v1 = *reinterpret_cast<const float2*>(vp + HD + ch);
                   rx = fmaf(a1, v1.x, rx); ry = fmaf(a1, v1.y, ry);
                 }
                 if (cnt > 2) {
-                  const float2 v2 = __ldg(reinterpret_cast<const float2*>(vp + 2 * HD + ch));
+                  const float2 v2 = *reinterpret_cast<const float2*>(vp + 2 * HD + ch);
                   rx = fmaf(a2, v2.x, rx); ry = fmaf(a2, v2.y, ry);
                 }
                 xcur[(size_t)ch * RT] = rx;                    // R
@@ -689,21 +724,21 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
         mbar_arrive(&c.curfull[q]);              // release: X row, recent row and ring stores precede it
         if (PROF && p.prof != nullptr && r == 0) c.t_seen[8 + q] = clock64();
         __threadfence_block();
-        fe_done[warp] = (int)my_visits + 1;
+        fe_done[warp] = my_visits + 1;
       }
       if (__any_sync(FULL, bad)) return;         // aborted launch: the mat-vec warps leave through their own bounded waits
       // ---- 5. global-ring taps of my next visit: issue the loads now, they land while I wait for its producer.
       //         (Rows at least NBUF + NV visits old: written before the "empty" wait this visit has passed.)
       have_pref = false;
       if (st.ntaps == 3 && v + NV < total_visits) {
-        const long v2 = v + NV;
-        const int step2 = (int)(v2 / G), g2 = (int)(v2 - (long)step2 * G);
+        int step2 = step, g2 = g + NV;
+        while (g2 >= G) { g2 -= G; ++step2; }
         const int t2 = p.t_start + step2;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int back = (2 - j) * st.dil;
           const int tt = t2 - back;
-          const long dist = (long)back * G;
+          const int dist = back * G;
           if (tt >= 0 && !(tt >= p.t_start && dist < NBUF + NV)) {
             const int slot = tt % st.hist_depth;
             const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g2) * (HD * RT) + r;
