@@ -109,6 +109,17 @@ int ssv_synthesize_host(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* s, const int6
                         float* mel_host, float* A_host, int64_t* pma_traj_host,
                         int t2m_precision, int ssrn_precision, void* stream);
 
+/* Pipelined form of the same call for corpus runs: submit enqueues one batch and returns a ticket (0 or 1) without
+ * waiting for the GPU; wait blocks until that batch's host buffers are filled and reports its errors.  Two
+ * batches may be in flight, so the device->host copy of batch i (114 MB at B = 64) overlaps TextEnc / decode of
+ * batch i + 1.  The host buffers of an in-flight batch must stay valid and distinct until its wait returns; all
+ * batches in flight must have the same (B, N, n_frames). */
+int ssv_synthesize_host_submit(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* s, const int64_t* textid_host,
+                               const float* spkemb_host, int B, int N, int n_frames, float* lin_host,
+                               float* mel_host, float* A_host, int64_t* pma_traj_host,
+                               int t2m_precision, int ssrn_precision, void* stream, int* ticket);
+int ssv_synthesize_host_wait(ssv_decoder* d, int ticket);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,10 @@ SIGNATURES = {
                                C.c_int, C.c_void_p]),
     "ssv_synthesize_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _c_i64p, _c_f32p, C.c_int, C.c_int, C.c_int,
                                       _c_f32p, _c_f32p, _c_f32p, _c_i64p, C.c_int, C.c_int, C.c_void_p]),
+    "ssv_synthesize_host_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _c_i64p, _c_f32p, C.c_int, C.c_int, C.c_int,
+                                             _c_f32p, _c_f32p, _c_f32p, _c_i64p, C.c_int, C.c_int, C.c_void_p,
+                                             C.POINTER(C.c_int)]),
+    "ssv_synthesize_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 _lib: Optional[C.CDLL] = None

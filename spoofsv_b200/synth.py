@@ -50,6 +50,7 @@ class Synthesizer:
         self.m1, self.m2 = text2mel, ssrn
         self.ssrn_precision = ssrn_precision
         self._pinned: Dict[str, torch.Tensor] = {}
+        self._next_buf = 0
 
     def _pin(self, key: str, shape, dtype) -> torch.Tensor:
         t = self._pinned.get(key)
@@ -64,6 +65,15 @@ class Synthesizer:
 
         Everything between the host buffers (H2D, TextEnc, n_frames of decode, SSRN, D2H, sync)
         happens inside one C call, ssv_synthesize_host."""
+        return self.collect(self.submit(textid, spkemb, n_frames, want_mel, want_att, _sync=True))
+
+    def submit(self, textid: np.ndarray, spkemb: np.ndarray, n_frames: int, want_mel: bool = False,
+               want_att: bool = False, _sync: bool = False):
+        """Pipelined form (ssv_synthesize_host_submit): enqueue one batch and return a ticket for `collect`.
+
+        Two batches may be in flight: the device->host copy of batch i then overlaps TextEnc / decode of batch
+        i + 1.  Each in-flight batch has its own pinned host buffers, which `collect` returns (valid until the
+        second-next submit)."""
         ids = np.ascontiguousarray(textid, dtype=np.int64)
         spk = np.ascontiguousarray(spkemb, dtype=np.float32)
         if ids.ndim != 2 or spk.ndim != 2 or ids.shape[0] != spk.shape[0]:
@@ -73,20 +83,26 @@ class Synthesizer:
         B, N = ids.shape
         T = int(n_frames)
         F, O = self.m1.freq_bins, self.m2.output_bins
-        h_ids = self._pin("ids", (B, N), torch.int64)
-        h_spk = self._pin("spk", (B, spk.shape[1]), torch.float32)
+        k = self._next_buf                                  # host buffer set of this batch (two sets alternate)
+        self._next_buf ^= 1
+        h_ids = self._pin(f"ids{k}", (B, N), torch.int64)
+        h_spk = self._pin(f"spk{k}", (B, spk.shape[1]), torch.float32)
         h_ids.numpy()[...] = ids
         h_spk.numpy()[...] = spk
-        h_lin = self._pin("lin", (B, O, 4 * T), torch.float32)
-        h_traj = self._pin("traj", (T, B), torch.int64)
-        h_mel = self._pin("mel", (B, F, T), torch.float32) if want_mel else None
-        h_att = self._pin("att", (B, N, T), torch.float32) if want_att else None
+        h_lin = self._pin(f"lin{k}", (B, O, 4 * T), torch.float32)
+        h_traj = self._pin(f"traj{k}", (T, B), torch.int64)
+        h_mel = self._pin(f"mel{k}", (B, F, T), torch.float32) if want_mel else None
+        h_att = self._pin(f"att{k}", (B, N, T), torch.float32) if want_att else None
         dec = self.m1._decoder(B, N, T)
         ptr = lambda t: None if t is None else t.data_ptr()
-        _lib.check(_lib.load().ssv_synthesize_host(
-            self.m1._native(), dec, self.m2._native(), h_ids.data_ptr(), h_spk.data_ptr(), B, N, T,
-            h_lin.data_ptr(), ptr(h_mel), ptr(h_att), h_traj.data_ptr(),
-            _prec(self.m1.precision), _prec(self.ssrn_precision), _lib.current_stream_ptr()))
+        ticket = C.c_int(-1)
+        args = (self.m1._native(), dec, self.m2._native(), h_ids.data_ptr(), h_spk.data_ptr(), B, N, T,
+                h_lin.data_ptr(), ptr(h_mel), ptr(h_att), h_traj.data_ptr(),
+                _prec(self.m1.precision), _prec(self.ssrn_precision), _lib.current_stream_ptr())
+        if _sync:                   # the one-call form: returns with the host buffers filled
+            _lib.check(_lib.load().ssv_synthesize_host(*args))
+        else:
+            _lib.check(_lib.load().ssv_synthesize_host_submit(*args, C.byref(ticket)))
         self.m1._state = None       # the decoder's buffers now belong to the C side
         out = {"lin": h_lin.numpy(), "traj": h_traj.numpy()}
         if want_mel:
@@ -96,6 +112,13 @@ class Synthesizer:
         self.h2d_bytes = ids.nbytes + spk.nbytes
         self.d2h_bytes = h_lin.numel() * 4 + h_traj.numel() * 8 + (h_mel.numel() * 4 if want_mel else 0) + (
             h_att.numel() * 4 if want_att else 0)
+        return (dec, ticket.value, out)
+
+    def collect(self, pending) -> Dict[str, np.ndarray]:
+        """Wait for a submitted batch (ssv_synthesize_host_wait) and return its host arrays."""
+        dec, ticket, out = pending
+        if ticket >= 0:
+            _lib.check(_lib.load().ssv_synthesize_host_wait(dec, ticket))
         return out
 
     def synthesize_units(self, units: Sequence[Unit], sentence_ids: Sequence[np.ndarray], speaker_emb: np.ndarray,
@@ -106,7 +129,16 @@ class Synthesizer:
         the reference pads every sentence of its batch to the batch maximum."""
         from .text import pad_batch
         n = pad_to or max(int(np.asarray(r).size) for r in sentence_ids)
+        prev = None                      # one batch ahead: batch i + 1 computes while batch i copies back
         for group in plan_batches(units, batch):
             ids = pad_batch([sentence_ids[u.sentence] for u in group], n)
             spk = np.stack([speaker_emb[u.speaker] for u in group]).astype(np.float32)
-            yield group, self.synthesize_host(ids, spk, n_frames)
+            if prev is not None and prev[2] != ids.shape:       # shape change (last, smaller batch): drain first
+                yield prev[0], self.collect(prev[1])
+                prev = None
+            cur = (group, self.submit(ids, spk, n_frames), ids.shape)
+            if prev is not None:
+                yield prev[0], self.collect(prev[1])
+            prev = cur
+        if prev is not None:
+            yield prev[0], self.collect(prev[1])

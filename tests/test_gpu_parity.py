@@ -385,3 +385,31 @@ def test_corpus_driver_matches_per_speaker_reference_loop(tmp_path, write_driver
             assert _maxabs(y, oY[k]) <= FP32_TOL and _maxabs(_t(spec), olin[k]) <= FP32_TOL
             saved = np.load(tmp_path / "out" / f"s{spk[1:]}" / f"s{spk[1:]}_{k + 1:03d}.npy")
             assert np.array_equal(saved, spec)
+
+
+def test_pipelined_submit_wait_matches_sync(cuda_models):
+    """ssv_synthesize_host_submit / _wait with two batches in flight == the synchronous call, batch by batch."""
+    from spoofsv_b200 import _lib
+    from spoofsv_b200.synth import Synthesizer
+    m1, m2, _, _ = cuda_models
+    names, emb, _ = W.load_fixtures()
+    syn = Synthesizer(m1, m2)
+    batches = [(W.synthetic_text(4, 25, seed=30 + i).numpy()[:, 0, :], emb[4 * i:4 * i + 4].copy()) for i in range(3)]
+    want = [{k: v.copy() for k, v in syn.synthesize_host(ids, spk, 12, want_mel=True).items()} for ids, spk in batches]
+    pend, got = None, []
+    for ids, spk in batches:
+        cur = syn.submit(ids, spk, 12, want_mel=True)
+        if pend is not None:
+            got.append({k: v.copy() for k, v in syn.collect(pend).items()})
+        pend = cur
+    got.append({k: v.copy() for k, v in syn.collect(pend).items()})
+    for w, g in zip(want, got):
+        assert np.array_equal(w["lin"], g["lin"]) and np.array_equal(w["mel"], g["mel"]) and np.array_equal(w["traj"], g["traj"])
+    # protocol errors: a third submit while two are in flight, waiting twice for the same ticket
+    a = syn.submit(*batches[0], 12)
+    b = syn.submit(*batches[1], 12)
+    with pytest.raises(ValueError, match="in flight"):
+        syn.submit(*batches[2], 12)
+    syn.collect(a); syn.collect(b)
+    with pytest.raises(ValueError, match="no batch in flight"):
+        syn.collect(a)
