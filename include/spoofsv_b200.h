@@ -120,6 +120,12 @@ int ssv_synthesize_host_submit(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* s, con
                                int t2m_precision, int ssrn_precision, void* stream, int* ticket);
 int ssv_synthesize_host_wait(ssv_decoder* d, int ticket);
 
+/* ---- waveform stage (next row of the scope table) -------------------------------------------
+ * De-emphasis of B waveforms of n samples each, y[n] = x[n] + coeff * y[n-1]: replaces
+ * scipy.signal.lfilter([1], [1, -PREEMPH], time_signal) (generate_test_utterances.py:136,
+ * synthesize.py:144).  x, y: dev (B, n) contiguous; in place (y == x) is allowed. */
+int ssv_deemphasis(const float* x, float* y, int B, long n, float coeff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1058,4 +1058,13 @@ int ssv_synthesize_host_submit(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, co
 
 int ssv_synthesize_host_wait(ssv_decoder* d, int ticket) { return synth_wait(d, ticket); }
 
+// ------------------------------------------------------------------------------------------------
+int ssv_deemphasis(const float* x, float* y, int B, long n, float coeff, void* stream) {
+  SSV_CHECK(x && y, "deemphasis: null pointer");
+  SSV_CHECK(B >= 0 && n >= 0, "deemphasis: negative size");
+  SSV_CHECK(coeff > -1.f && coeff < 1.f, "deemphasis: |coeff| must be < 1");
+  if (B == 0 || n == 0) return kOk;
+  return launch_deemphasis(x, y, B, n, coeff, as_stream(stream));
+}
+
 }  // extern "C"

@@ -113,6 +113,43 @@ __global__ void linear_small_kernel(const float* __restrict__ x, long x_ld, cons
   if (lane == 0) y[(long)b * y_ld + o] = acc + bias[o];
 }
 
+// De-emphasis y[n] = x[n] + c y[n-1] (scipy.signal.lfilter([1], [1, -c]) at generate_test_utterances.py:136) of one
+// waveform per block: 1024 threads filter contiguous chunks from zero state, one warp-free serial pass chains the
+// 1024 chunk ends (carry_t = end_{t-1} + c^L carry_{t-1}), and a second pass adds c^(i+1) * carry to every sample.
+constexpr int DEEMPH_T = 1024;
+__global__ void __launch_bounds__(DEEMPH_T) deemphasis_kernel(const float* x, float* y, long n, float c) {
+  __shared__ float ends[DEEMPH_T];
+  __shared__ float carry[DEEMPH_T];
+  const float* xr = x + (long)blockIdx.x * n;
+  float* yr = y + (long)blockIdx.x * n;
+  const long L = (n + DEEMPH_T - 1) / DEEMPH_T;
+  const long lo = (long)threadIdx.x * L, hi = lo + L < n ? lo + L : n;
+  float acc = 0.f;
+  for (long i = lo; i < hi; ++i) {
+    acc = fmaf(c, acc, xr[i]);
+    yr[i] = acc;
+  }
+  ends[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float cL = powf(c, (float)L);
+    float cin = 0.f;
+    for (int t = 0; t < DEEMPH_T; ++t) {
+      carry[t] = cin;
+      cin = fmaf(cL, cin, ends[t]);        // a short last chunk only matters for threads past the end
+    }
+  }
+  __syncthreads();
+  const float cin = carry[threadIdx.x];
+  if (cin != 0.f) {
+    float p = c;
+    for (long i = lo; i < hi; ++i) {
+      yr[i] = fmaf(p, cin, yr[i]);
+      p *= c;
+    }
+  }
+}
+
 inline int grid_for(long total, int block = 256) {
   long g = (total + block - 1) / block;
   return (int)(g > 4096 ? 4096 : (g < 1 ? 1 : g));
@@ -178,6 +215,13 @@ int launch_linear_small(const float* x, long x_ld, const float* w, const float* 
                         float* y, int y_ld, cudaStream_t s) {
   const long threads = (long)B * out_f * 32;
   linear_small_kernel<<<(int)((threads + 255) / 256), 256, 0, s>>>(x, x_ld, w, b, B, in_f, out_f, y, y_ld);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_deemphasis(const float* x, float* y, int B, long n, float coeff, cudaStream_t s) {
+  deemphasis_kernel<<<B, DEEMPH_T, 0, s>>>(x, y, n, coeff);
   ++g_launches;
   SSV_CUDA(cudaGetLastError());
   return kOk;

@@ -13,9 +13,10 @@ SPK_EMB_DIR for MAX_FRAME_NUM + 1 frames (:105-116), then SSRN (:120).  What is 
     contiguously over the ranks (one process per GPU, no collective on the data path);
   * the AR loop is one launch of the incremental decode kernel per batch.
 
-The waveform stage of the reference (:126-139: Griffin-Lim, de-emphasis, trim, wav files) and the Kaldi / GE2E
-directory shuffling (:141-259) are the next rows of the scope table; this driver stops at the linear
-spectrogram and, with --save_spectrogram DIR, writes `s<spk>/s<spk>_<nnn>.npy` named like the reference's wavs.
+With --save_spectrogram DIR it writes the linear spectrograms as `s<spk>/s<spk>_<nnn>.npy`; with --save_wav DIR it
+also runs the waveform stage of the reference (:126-139: Griffin-Lim, de-emphasis, trim, wav files) batched on
+the GPU (spoofsv_b200/vocoder.py) and writes `s<spk>/s<spk>_<nnn>.wav`.  The Kaldi / GE2E directory shuffling
+(:141-259) is a later row of the scope table.
 """
 from __future__ import annotations
 
@@ -46,6 +47,11 @@ def build_parser() -> argparse.ArgumentParser:
     ps.add_argument("--speakers", type=int, default=None, help="only the first N speakers (dry runs)")
     ps.add_argument("--ssrn_precision", default="bf16", choices=["fp32", "bf16"])
     ps.add_argument("--save_spectrogram", type=str, default=None, help="directory for s<spk>/s<spk>_<nnn>.npy")
+    ps.add_argument("--save_wav", type=str, default=None,
+                    help="directory for s<spk>/s<spk>_<nnn>.wav: batched GPU Griffin-Lim (64 iterations), de-emphasis, "
+                         "trim, 9 s cap, peak 0.75, as generate_test_utterances.py:130-139 (default there: "
+                         "SRC_ROOT_DIR/test/<current_time>/spoof_data/)")
+    ps.add_argument("--gl_iters", type=int, default=64)
     ps.add_argument("--random_init", type=int, default=None, metavar="SEED",
                     help="random-init weights instead of the INFERENCE_* checkpoints (no checkpoints are vendored)")
     return ps
@@ -130,7 +136,15 @@ def run(args, on_batch=None) -> Dict[str, float]:
             spk = emb_d[torch.tensor([u.speaker for u in group], device="cuda")][:, :, None]
             dec = m1._begin(K[sent].contiguous(), V[sent].contiguous(), spk, frames)
             _lib.check(lib.ssv_decoder_run(dec, frames, _lib.current_stream_ptr()))
-            lin = m2(m1._state["Y"]).cpu().numpy()                          # (B, 513, 4T), the reference's pred_lin
+            lin_d = m2(m1._state["Y"])                                      # (B, 513, 4T), the reference's pred_lin
+            if args.save_wav:
+                from . import vocoder
+                waves = vocoder.postprocess(lin_d, cfg, n_iter=args.gl_iters)
+                for u, w in zip(group, waves):
+                    path = Path(args.save_wav) / (output_name(speakers[u.speaker], u.sentence) + ".wav")
+                    path.parent.mkdir(parents=True, exist_ok=True)
+                    vocoder.write_wav(path, w, cfg["SAMPLING_RATE"])
+            lin = lin_d.cpu().numpy()
             m1.check()
             n_utt += len(group)
             if on_batch is not None:

@@ -1,0 +1,101 @@
+"""Waveform stage of the reference drivers on the GPU (next row of the scope table).
+
+generate_test_utterances.py:130-139 / synthesize.py:134-147 run, per utterance and on one CPU thread:
+max-normalise, `** (RECONSTRUCTION / ANALYSIS)`, 64 iterations of librosa's fast Griffin-Lim (n_fft 1024, hop 256),
+de-emphasis, trim (30 dB), 9 s cap, peak 0.75, wav.  Here the whole batch is processed at once: batched
+STFT / ISTFT (cuFFT through torch.stft / torch.istft -- library FFTs, as librosa's are), the phase update in torch
+element-wise ops, de-emphasis in the library's own scan kernel (`ssv_deemphasis`), trim bounds from framed RMS.
+librosa seeds the phases from numpy's global RNG, so a reference run is not reproducible sample by sample;
+`angles0` makes this implementation comparable with the CPU restatement in oracle/vocoder_oracle.py.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def griffin_lim(S: torch.Tensor, n_iter: int = 64, hop: int = 256, win_length: int = 1024, momentum: float = 0.99,
+                angles0: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """(B, 1 + n_fft/2, frames) magnitudes on the GPU -> (B, hop * (frames - 1)) samples.
+    librosa.core.griffinlim (0.7): momentum 0.99, hann window, centred reflect-padded frames."""
+    _lib.require_cuda(S, "griffin_lim")
+    B, F, T = S.shape
+    n_fft = 2 * (F - 1)
+    window = torch.hann_window(win_length, periodic=True, device=S.device, dtype=torch.float32)
+    if angles0 is None:
+        ph = torch.rand((B, F, T), device=S.device, generator=generator) * (2.0 * np.pi)
+        angles = torch.polar(torch.ones_like(ph), ph)
+    else:
+        angles = angles0.to(device=S.device, dtype=torch.complex64)
+    S = S.to(torch.float32)
+    length = hop * (T - 1)
+    istft = lambda D: torch.istft(D, n_fft, hop_length=hop, win_length=win_length, window=window, center=True, length=length)
+    rebuilt = None
+    c = momentum / (1.0 + momentum)
+    for _ in range(n_iter):
+        tprev = rebuilt
+        inverse = istft(S * angles)
+        rebuilt = torch.stft(inverse, n_fft, hop_length=hop, win_length=win_length, window=window, center=True,
+                             pad_mode="reflect", return_complex=True)
+        angles = rebuilt if tprev is None else rebuilt - c * tprev
+        angles = angles / (angles.abs() + 1e-16)
+    return istft(S * angles)
+
+
+def deemphasis(x: torch.Tensor, coeff: float) -> torch.Tensor:
+    """scipy.signal.lfilter([1], [1, -coeff]) over the last axis of a (B, n) CUDA tensor (ssv_deemphasis kernel)."""
+    _lib.require_cuda(x, "deemphasis")
+    x = x.to(torch.float32).contiguous()
+    y = torch.empty_like(x)
+    B, n = x.shape
+    _lib.check(_lib.load().ssv_deemphasis(x.data_ptr(), y.data_ptr(), B, n, float(coeff), _lib.current_stream_ptr()))
+    return y
+
+
+def trim_bounds(y: torch.Tensor, top_db: float = 30.0, frame_length: int = 2048, hop_length: int = 512):
+    """librosa.effects.trim bounds for every row of (B, n): lists of start / end sample indices."""
+    B, n = y.shape
+    yp = torch.nn.functional.pad(y[:, None, :], (frame_length // 2, frame_length // 2), mode="reflect")[:, 0, :]
+    fr = yp.unfold(1, frame_length, hop_length)                     # (B, frames, frame_length)
+    rms = fr.pow(2).mean(-1).sqrt()
+    db = 20.0 * torch.log10(rms.clamp_min(1e-5)) - 20.0 * torch.log10(rms.max(dim=1, keepdim=True).values.clamp_min(1e-5))
+    keep = (db > -top_db).cpu().numpy()
+    starts, ends = [], []
+    for k in range(B):
+        nz = np.flatnonzero(keep[k])
+        if nz.size == 0:
+            starts.append(0); ends.append(0)
+        else:
+            starts.append(int(nz[0]) * hop_length); ends.append(int(min(n, (int(nz[-1]) + 1) * hop_length)))
+    return starts, ends
+
+
+def postprocess(pred_lin: torch.Tensor, cfg: dict, n_iter: int = 64, angles0: Optional[torch.Tensor] = None,
+                generator: Optional[torch.Generator] = None) -> List[np.ndarray]:
+    """generate_test_utterances.py:130-139 (LOG_FEATURE false) for a whole batch: (B, 513, 4T) in (0, 1) on the GPU
+    -> one float32 waveform per utterance (peak 0.75, trimmed, at most 9 s)."""
+    if cfg.get("LOG_FEATURE", False):
+        raise NotImplementedError("LOG_FEATURE spectrograms are not used by the vendored config.json")
+    _lib.require_cuda(pred_lin, "postprocess")
+    x = pred_lin.to(torch.float32)
+    spec = (x / x.amax(dim=(1, 2), keepdim=True)).pow(cfg["NORM_POWER"]["RECONSTRUCTION"] / cfg["NORM_POWER"]["ANALYSIS"])
+    sig = griffin_lim(spec, n_iter, cfg["STFT"]["HOP_LENGTH"], cfg["STFT"]["FFT_LENGTH"], angles0=angles0, generator=generator)
+    sig = deemphasis(sig, cfg["PREEMPH"])
+    starts, ends = trim_bounds(sig, 30.0)
+    cap = 9 * cfg["SAMPLING_RATE"]
+    host = sig.cpu().numpy()
+    out = []
+    for k in range(host.shape[0]):
+        w = host[k, starts[k]:ends[k]][:cap]
+        out.append((w / np.max(w) * 0.75).astype(np.float32) if w.size else w.astype(np.float32))
+    return out
+
+
+def write_wav(path, samples: np.ndarray, sampling_rate: int) -> None:
+    """librosa.output.write_wav(norm=False) of 0.7 == scipy.io.wavfile.write of the float32 samples."""
+    from scipy.io import wavfile
+    wavfile.write(str(path), int(sampling_rate), np.asarray(samples, dtype=np.float32))

@@ -413,3 +413,21 @@ def test_pipelined_submit_wait_matches_sync(cuda_models):
     syn.collect(a); syn.collect(b)
     with pytest.raises(ValueError, match="no batch in flight"):
         syn.collect(a)
+
+
+def test_corpus_driver_writes_wavs(tmp_path, write_driver_cfg):
+    """--save_wav: the reference's file naming and sample format (float32 wav at SAMPLING_RATE, peak 0.75, <= 9 s)."""
+    import json
+    from scipy.io import wavfile
+    from spoofsv_b200 import generate_test_utterances as G
+    path, cfg = write_driver_cfg(tmp_path, n_lines=2, speakers=("p225",))
+    cfg.update({"NORM_POWER": {"ANALYSIS": 0.6, "RECONSTRUCTION": 1.3}, "PREEMPH": 0.97, "SAMPLING_RATE": 22050,
+                "LOG_FEATURE": False, "MAX_FRAME_NUM": 19})
+    path.write_text(json.dumps(cfg))
+    args = G.build_parser().parse_args(["-C", str(path), "-T", "t", "--eval_utt_num", "2", "--random_init", "0",
+                                        "--save_wav", str(tmp_path / "wav"), "--gl_iters", "8"])
+    assert G.run(args)["utterances"] == 2
+    for k in (1, 2):
+        sr, w = wavfile.read(tmp_path / "wav" / "s225" / f"s225_{k:03d}.wav")
+        assert sr == 22050 and w.dtype == np.float32 and 0 < len(w) <= 9 * 22050
+        assert abs(float(w.max()) - 0.75) < 1e-6 and np.isfinite(w).all()
