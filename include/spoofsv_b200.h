@@ -67,6 +67,13 @@ int ssv_text2mel_destroy(ssv_text2mel* m);
 int ssv_text_encoder_fwd(ssv_text2mel* m, const int64_t* textid, int B, int N, float* K, float* V,
                          int precision, void* stream);
 
+/* replaces the train branch of melSyn.forward (models/TTSModel.py:263-273; teacher-forced, as the training loops
+ * call it: train/adversarial_wasserstein_gp.py:277-278): full-sequence forward, unmasked attention.  melspec: dev
+ * (B, F, T); textid: dev int64 (B, 1, N); spkemb: dev (B, E, 1); Y: dev (B, F, T); A: dev (B, N, T).  Forward only:
+ * the backward pass / optimiser / gradient allreduce of the training step is the next row of the scope table. */
+int ssv_text2mel_train_fwd(ssv_text2mel* m, const float* melspec, const int64_t* textid, const float* spkemb,
+                           int B, int N, int T, float* Y, float* A, int precision, void* stream);
+
 /* Incremental decoder: replaces the eval branch of melSyn.forward (models/TTSModel.py:275-300)
  * as driven by the AR loops (generate_test_utterances.py:105-116, synthesize.py:103-109). */
 int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_frames, ssv_decoder** out);

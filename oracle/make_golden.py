@@ -73,8 +73,35 @@ def close(a, b, tol, what):
     return err
 
 
+def golden_train(R, ref_ids, emb):
+    """Known answer for the train branch: the reference module in train() mode (TTSModel.py has no dropout, so
+    train() only selects the branch), kaiming init + jittered LayerNorm affine, B = 3, T = 29."""
+    k1, k2 = W.state_dicts(7, init="kaiming", ln_jitter=True)
+    r1, _ = ref_models(R, k1, k2)
+    r1.train()
+    ids = O.pad_text_ids([ref_ids[2], ref_ids[10], ref_ids[5]])
+    spk = torch.from_numpy(emb[[0, 17, 55]])[:, :, None]
+    g = torch.Generator().manual_seed(9)
+    mel = torch.rand((3, W.CFG["freq_bins"], 29), generator=g)
+    mel[:, :, 0] = 0                                           # teacher forcing: [0, mel_gt[:, :, :-1]]
+    with torch.no_grad():
+        Y, A = r1(mel, ids, spk)
+        oY, oA = O.melsyn_train_forward(k1, mel, ids, spk)
+    print("train oracle-vs-ref  Y %.2e  A %.2e" % (close(oY, Y, 2e-5, "train Y"), close(oA, A, 2e-5, "train A")))
+    np.savez_compressed(GOLDEN / "train_seed7.npz", mel=mel.numpy(), textid=ids.numpy(), spk=spk.numpy(),
+                        Y=Y.numpy(), A=A.numpy())
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    if "--train-only" in sys.argv:                             # add the train-branch vector without rewriting the rest
+        R = import_reference()
+        torch.set_num_threads(8)
+        lines = [ln.strip() for ln in (REF / "havard.txt").read_text().splitlines()]
+        names = sorted(p.stem for p in (REF / "spk_emb").glob("*.npy"))
+        emb = np.stack([np.load(REF / "spk_emb" / f"{n}.npy").astype(np.float32) for n in names])
+        golden_train(R, [O.text2id(s) for s in lines], emb)
+        return
     R = import_reference()
     torch.set_num_threads(8)
 
@@ -174,6 +201,9 @@ def main():
             out[f"y{i}"] = y.numpy()
         out["cases"] = np.array(cases, dtype=np.int64)
         np.savez_compressed(GOLDEN / "highway_cases.npz", **out)
+
+        # ---- 3f. train-mode (teacher-forced) forward of melSyn (models/TTSModel.py:263-273), ragged texts
+        golden_train(R, ref_ids, emb)
 
     (GOLDEN / "digests.txt").write_text("".join(f"{k} {v}\n" for k, v in sorted(digests.items())))
     np.save(GOLDEN / "havard_id_lens.npy", id_lens)

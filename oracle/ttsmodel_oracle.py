@@ -141,6 +141,17 @@ def audio_decoder(rq: torch.Tensor, sd: SD, p: str = "audio_decoder") -> torch.T
     return torch.sigmoid(x)
 
 
+# --------------------------------------------------------------------------- Text2Mel train-mode (teacher-forced) forward
+def melsyn_train_forward(sd: SD, melspec: torch.Tensor, textid: torch.Tensor, spkemb: torch.Tensor):
+    """melSyn.forward in train() mode, models/TTSModel.py:263-273: full-sequence teacher-forced forward with
+    unmasked attention over all characters.  Returns (Y_prob (B, F, T), A (B, N, T))."""
+    K, V = text_encoder(textid, sd)
+    Q = audio_encoder(melspec, spkemb, sd)
+    A = F.softmax(torch.matmul(K.transpose(1, 2), Q) / math.sqrt(K.shape[1]), dim=1)
+    R = torch.cat((torch.matmul(V, A), Q), dim=1)
+    return audio_decoder(R, sd), A
+
+
 # --------------------------------------------------------------------------- Text2Mel eval protocol
 def melsyn_eval_call(sd: SD, melspec, textid, spkemb, K=None, V=None, A_last=None, pma=None):
     """One eval-mode call of melSyn.forward, models/TTSModel.py:275-300.

@@ -30,6 +30,8 @@ SIGNATURES = {
                             + [C.c_int] * 6 + [C.POINTER(C.c_void_p)]),
     "ssv_text2mel_destroy": (C.c_int, [C.c_void_p]),
     "ssv_text_encoder_fwd": (C.c_int, [C.c_void_p, _c_i64p, C.c_int, C.c_int, _c_f32p, _c_f32p, C.c_int, C.c_void_p]),
+    "ssv_text2mel_train_fwd": (C.c_int, [C.c_void_p, _c_f32p, _c_i64p, _c_f32p, C.c_int, C.c_int, C.c_int, _c_f32p, _c_f32p,
+                                         C.c_int, C.c_void_p]),
     "ssv_decoder_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ssv_decoder_destroy": (C.c_int, [C.c_void_p]),
     "ssv_decoder_begin": (C.c_int, [C.c_void_p, _c_f32p, _c_f32p, _c_f32p, C.c_int, C.c_int, _c_f32p, _c_f32p,

@@ -257,6 +257,12 @@ struct ssv_text2mel {
   int te_dil[12];
   // speaker projections
   float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+  // AudioEnc / AudioDec packed for the tiled kernels (train-mode full-sequence forward)
+  ConvPack ae_conv1, ae_conv2, ae_conv3, ae_hc[10], ad_conv1, ad_hc[6], ad_conv2, ad_conv3, ad_conv4, ad_conv5;
+  int ae_dil[10], ad_dil[6];
+  Workspace tws;      // train-mode activations
+  float *ts1 = nullptr, *ts2 = nullptr;
+  int ts_cap = 0;
   // decode stage table
   DecStage stages[DEC_STAGES];
   DecStage* stages_dev = nullptr;
@@ -461,6 +467,30 @@ int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, 
   T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc1.bias", H, &m->fc1_b, s));
   T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc2.weight", H * spkemb_dim, &m->fc2_w, s));
   T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc2.bias", H, &m->fc2_b, s));
+  // ---- AudioEnc / AudioDec for the tiled kernels (train branch)
+  {
+    const std::string ae = "audio_encoder.", ad = "audio_decoder.";
+    T2M_TRY(pack_conv_ln(m->arena, pm, ae + "conv1", ae + "ln1", H, freq_bins, &m->ae_conv1, s));
+    T2M_TRY(pack_conv_ln(m->arena, pm, ae + "conv2", ae + "ln2", H, H, &m->ae_conv2, s));
+    T2M_TRY(pack_conv_ln(m->arena, pm, ae + "conv3", ae + "ln3", H, H, &m->ae_conv3, s));
+    const char* eh[10] = {"hci1.hc1", "hci1.hc2", "hci1.hc3", "hci1.hc4", "hci2.hc1", "hci2.hc2", "hci2.hc3", "hci2.hc4", "hc1", "hc2"};
+    const int ed[10] = {1, 3, 9, 27, 1, 3, 9, 27, 3, 3};
+    for (int i = 0; i < 10; ++i) {
+      T2M_TRY(pack_highway(m->arena, pm, ae + eh[i], H, 3, &m->ae_hc[i], s));
+      m->ae_dil[i] = ed[i];
+    }
+    T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv1", ad + "ln1", H, D2, &m->ad_conv1, s));
+    const char* dh[6] = {"hci.hc1", "hci.hc2", "hci.hc3", "hci.hc4", "hc1", "hc2"};
+    const int dd[6] = {1, 3, 9, 27, 1, 1};
+    for (int i = 0; i < 6; ++i) {
+      T2M_TRY(pack_highway(m->arena, pm, ad + dh[i], H, 3, &m->ad_hc[i], s));
+      m->ad_dil[i] = dd[i];
+    }
+    T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv2", ad + "ln2", H, H, &m->ad_conv2, s));
+    T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv3", ad + "ln3", H, H, &m->ad_conv3, s));
+    T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv4", ad + "ln4", H, H, &m->ad_conv4, s));
+    T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv5", ad + "ln5", freq_bins, H, &m->ad_conv5, s));
+  }
   // ---- decode stage table
   {
     struct Ln { float *g, *b; };
@@ -579,6 +609,57 @@ int ssv_text_encoder_fwd(ssv_text2mel* m, const int64_t* textid, int B, int N, f
   SSV_TRY(text_encoder_cl(m, textid, B, N, &x, s));
   SSV_TRY(launch_transpose_out2(x, 2 * m->H, 0, B, m->H, N, K, s));
   SSV_TRY(launch_transpose_out2(x, 2 * m->H, m->H, B, m->H, N, V, s));
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Train-mode (teacher-forced) forward of melSyn, models/TTSModel.py:263-273: full-sequence AudioEnc, unmasked
+// attention over all characters, AudioDec -- the same fused conv kernels as TextEnc / SSRN with causal taps.
+int ssv_text2mel_train_fwd(ssv_text2mel* m, const float* melspec, const int64_t* textid, const float* spkemb, int B,
+                           int N, int T, float* Y, float* A, int precision, void* stream) {
+  SSV_CHECK(m && melspec && textid && spkemb && Y && A, "text2mel_train_fwd: null pointer");
+  SSV_CHECK(B > 0 && N > 0 && T > 0, "text2mel_train_fwd: empty input");
+  SSV_CHECK(precision == SSV_PREC_FP32, "text2mel_train_fwd: only SSV_PREC_FP32 is implemented");
+  cudaStream_t s = as_stream(stream);
+  const int H = m->H, D2 = 2 * H, F = m->F;
+  float* kx;                                                   // (B, N, 512): K | V, channels-last, in m->ws
+  SSV_TRY(text_encoder_cl(m, textid, B, N, &kx, s));
+  SSV_TRY(m->tws.ensure((size_t)B * T * D2));
+  if (m->ts_cap < B) {
+    SSV_TRY(m->arena.alloc<float>((size_t)B * H, &m->ts1));
+    SSV_TRY(m->arena.alloc<float>((size_t)B * H, &m->ts2));
+    m->ts_cap = B;
+  }
+  float* P = m->tws.buf[0];
+  float* Q = m->tws.buf[1];
+  SSV_TRY(launch_linear_small(spkemb, m->E, m->fc1_w, m->fc1_b, B, m->E, H, m->ts1, H, s));
+  SSV_TRY(launch_linear_small(spkemb, m->E, m->fc2_w, m->fc2_b, B, m->E, H, m->ts2, H, s));
+  const int f_ld = round_up(F, 16);
+  SSV_TRY(launch_transpose_in(melspec, (long)F * T, T, 1, B, F, T, P, f_ld, s));
+  // AudioEnc (:172-184): conv1 + fc1(e) -> LN -> ReLU -> conv2 -> LN -> ReLU -> conv3 + fc2(e) -> LN -> 10 causal highway convs
+  SSV_TRY(run_conv(m->ae_conv1, EPI_LN_RELU, 1, 0, P, f_ld, T, B, Q, H, s, m->ts1, H));
+  SSV_TRY(run_conv(m->ae_conv2, EPI_LN_RELU, 1, 0, Q, H, T, B, P, H, s));
+  SSV_TRY(run_conv(m->ae_conv3, EPI_LN, 1, 0, P, H, T, B, Q, H, s, m->ts2, H));
+  float* cur = Q;
+  float* nxt = P;
+  for (int i = 0; i < 10; ++i) {
+    SSV_TRY(run_conv(m->ae_hc[i], EPI_HIGHWAY, m->ae_dil[i], 1, cur, H, T, B, nxt, H, s));
+    float* t_ = cur; cur = nxt; nxt = t_;
+  }
+  // attention (:266-270) -> A (B, N, T), [R ; Q] (B, T, 512)
+  SSV_TRY(launch_train_attention(kx, cur, B, N, T, A, nxt, s));
+  // AudioDec (:217-232)
+  SSV_TRY(run_conv(m->ad_conv1, EPI_LN, 1, 0, nxt, D2, T, B, cur, H, s));
+  for (int i = 0; i < 6; ++i) {
+    SSV_TRY(run_conv(m->ad_hc[i], EPI_HIGHWAY, m->ad_dil[i], 1, cur, H, T, B, nxt, H, s));
+    float* t_ = cur; cur = nxt; nxt = t_;
+  }
+  SSV_TRY(run_conv(m->ad_conv2, EPI_LN_RELU, 1, 0, cur, H, T, B, nxt, H, s));
+  SSV_TRY(run_conv(m->ad_conv3, EPI_LN_RELU, 1, 0, nxt, H, T, B, cur, H, s));
+  SSV_TRY(run_conv(m->ad_conv4, EPI_LN_RELU, 1, 0, cur, H, T, B, nxt, H, s));
+  const int y_ld = round_up(F, 64);
+  SSV_TRY(run_conv(m->ad_conv5, EPI_LN_SIGMOID, 1, 0, nxt, H, T, B, cur, y_ld, s));
+  SSV_TRY(launch_transpose_out(cur, y_ld, B, F, T, Y, s));
   return kOk;
 }
 

@@ -94,6 +94,8 @@ int launch_pad_vec(const float* src, int n, int n_pad, float* dst, cudaStream_t 
 int launch_linear_small(const float* x, long x_ld, const float* w, const float* b, int B, int in_f, int out_f,
                         float* y, int y_ld, cudaStream_t s);          // y[b] = W x[b] + b (speaker projections)
 
+int launch_train_attention(const float* Kx /*(B,N,512)*/, const float* Q /*(B,T,256)*/, int B, int N, int T,
+                           float* A /*(B,N,T)*/, float* RQ /*(B,T,512)*/, cudaStream_t s);
 int launch_deemphasis(const float* x, float* y, int B, long n, float coeff, cudaStream_t s);   // y[n] = x[n] + c y[n-1] per row
 
 }  // namespace ssv

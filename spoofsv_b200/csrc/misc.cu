@@ -150,6 +150,81 @@ __global__ void __launch_bounds__(DEEMPH_T) deemphasis_kernel(const float* x, fl
   }
 }
 
+// Unmasked attention of the train branch (models/TTSModel.py:266-270): A = softmax_n(K^T Q / 16), R = V A, output
+// [R ; Q].  One warp per (utterance, time step): lane n-strided dot products against the query held in shared
+// memory, warp softmax, then a coalesced weighted sum of the V rows.  Kx: (B, N, 512) channels-last text-encoder
+// output (K = channels 0..255, V = 256..511); Q: (B, T, 256); A: (B, N, T) reference layout; RQ: (B, T, 512).
+constexpr int ATT_W = 8;            // warps (time steps) per block
+constexpr int ATT_NMAX = 192;       // MAX_TEXT_LEN of the reference config is 186
+__global__ void __launch_bounds__(ATT_W * 32) train_attention_kernel(const float* __restrict__ Kx, const float* __restrict__ Q,
+                                                                     int N, int T, float* __restrict__ A, float* __restrict__ RQ) {
+  __shared__ __align__(16) float qs[ATT_W][256];
+  __shared__ float ps[ATT_W][ATT_NMAX];
+  const int b = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * ATT_W + w;
+  if (t >= T) return;
+  const float* q = Q + ((long)b * T + t) * 256;
+  float* rq = RQ + ((long)b * T + t) * 512;
+  {
+    const float4 a = *reinterpret_cast<const float4*>(q + lane * 8), c = *reinterpret_cast<const float4*>(q + lane * 8 + 4);
+    *reinterpret_cast<float4*>(&qs[w][lane * 8]) = a;
+    *reinterpret_cast<float4*>(&qs[w][lane * 8 + 4]) = c;
+    *reinterpret_cast<float4*>(rq + 256 + lane * 8) = a;
+    *reinterpret_cast<float4*>(rq + 256 + lane * 8 + 4) = c;
+  }
+  __syncwarp();
+  float lg[ATT_NMAX / 32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < ATT_NMAX / 32; ++i) {
+    const int n = lane + 32 * i;
+    float d = -INFINITY;
+    if (n < N) {
+      const float4* kr = reinterpret_cast<const float4*>(Kx + ((long)b * N + n) * 512);
+      const float4* qv = reinterpret_cast<const float4*>(qs[w]);
+      float acc = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < 64; ++c) {
+        const float4 kk = kr[c], qq = qv[c];
+        acc = fmaf(kk.x, qq.x, acc); acc = fmaf(kk.y, qq.y, acc); acc = fmaf(kk.z, qq.z, acc); acc = fmaf(kk.w, qq.w, acc);
+      }
+      d = acc * 0.0625f;                       // 1 / sqrt(256)
+    }
+    lg[i] = d;
+    mx = fmaxf(mx, d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < ATT_NMAX / 32; ++i) {
+    lg[i] = lane + 32 * i < N ? expf(lg[i] - mx) : 0.f;
+    sum += lg[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+  for (int i = 0; i < ATT_NMAX / 32; ++i) {
+    const int n = lane + 32 * i;
+    if (n < N) {
+      const float pv = lg[i] / sum;
+      ps[w][n] = pv;
+      A[((long)b * N + n) * T + t] = pv;
+    }
+  }
+  __syncwarp();
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+  for (int n = 0; n < N; ++n) {
+    const float pv = ps[w][n];
+    const float* vr = Kx + ((long)b * N + n) * 512 + 256 + lane * 8;
+    const float4 v0 = *reinterpret_cast<const float4*>(vr), v1 = *reinterpret_cast<const float4*>(vr + 4);
+    r0.x = fmaf(pv, v0.x, r0.x); r0.y = fmaf(pv, v0.y, r0.y); r0.z = fmaf(pv, v0.z, r0.z); r0.w = fmaf(pv, v0.w, r0.w);
+    r1.x = fmaf(pv, v1.x, r1.x); r1.y = fmaf(pv, v1.y, r1.y); r1.z = fmaf(pv, v1.z, r1.z); r1.w = fmaf(pv, v1.w, r1.w);
+  }
+  *reinterpret_cast<float4*>(rq + lane * 8) = r0;
+  *reinterpret_cast<float4*>(rq + lane * 8 + 4) = r1;
+}
+
 inline int grid_for(long total, int block = 256) {
   long g = (total + block - 1) / block;
   return (int)(g > 4096 ? 4096 : (g < 1 ? 1 : g));
@@ -222,6 +297,15 @@ int launch_linear_small(const float* x, long x_ld, const float* w, const float* 
 
 int launch_deemphasis(const float* x, float* y, int B, long n, float coeff, cudaStream_t s) {
   deemphasis_kernel<<<B, DEEMPH_T, 0, s>>>(x, y, n, coeff);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_train_attention(const float* Kx, const float* Q, int B, int N, int T, float* A, float* RQ, cudaStream_t s) {
+  SSV_CHECK(N >= 1 && N <= ATT_NMAX, "train attention: text length %d outside [1, %d]", N, ATT_NMAX);
+  dim3 grid((T + ATT_W - 1) / ATT_W, B);
+  train_attention_kernel<<<grid, ATT_W * 32, 0, s>>>(Kx, Q, N, T, A, RQ);
   ++g_launches;
   SSV_CUDA(cudaGetLastError());
   return kOk;

@@ -255,9 +255,7 @@ class melSyn(_Native):
         column is the next input frame -> (Y (B,F,t), A (B,N,t), max_att).  Y and A are views of
         decoder-owned buffers.  ``A_last`` is not read (its columns are already held here)."""
         if self.training:
-            raise NotImplementedError(
-                "melSyn.forward in train() mode (teacher-forced training) is outside the CUDA hot path; "
-                "call .eval() for synthesis")
+            return self._train_forward(melspec, textid, spkemb)
         _lib.require_cuda(melspec, "melSyn.forward melspec")
         if melspec.dim() != 3 or melspec.shape[1] != self.freq_bins:
             raise ValueError(f"melspec must be (B, {self.freq_bins}, T), got {tuple(melspec.shape)}")
@@ -302,6 +300,37 @@ class melSyn(_Native):
         if first:
             return Y, A, max_att, K, V
         return Y, A, max_att
+
+    def _train_forward(self, melspec, textid, spkemb):
+        """Train branch of the reference (:263-273): teacher-forced full-sequence forward, unmasked attention.
+
+        Returns (Y_prob (B, F, T), A (B, N, T)) like the reference.  Forward only: the outputs carry no autograd
+        graph (the backward pass of the training step is the next row of the scope table)."""
+        _lib.require_cuda(melspec, "melSyn.forward melspec")
+        if textid is None:
+            raise ValueError("melSyn.forward in train() mode needs textid")
+        _lib.require_cuda(textid, "melSyn.forward textid")
+        if melspec.dim() != 3 or melspec.shape[1] != self.freq_bins:
+            raise ValueError(f"melspec must be (B, {self.freq_bins}, T), got {tuple(melspec.shape)}")
+        ids = textid.detach().to(torch.int64).contiguous()
+        if ids.dim() != 3 or ids.shape[1] != 1 or ids.shape[0] != melspec.shape[0]:
+            raise ValueError(f"textid must be ({melspec.shape[0]}, 1, N), got {tuple(ids.shape)}")
+        B, _, T = melspec.shape
+        N = ids.shape[-1]
+        if B == 0 or T == 0 or N == 0:
+            raise ValueError("empty input")
+        if int(ids.min()) < 0 or int(ids.max()) >= self.vocab_len:
+            raise ValueError(f"text ids must lie in [0, {self.vocab_len})")
+        x = melspec.detach().to(torch.float32).contiguous()
+        spk = spkemb.detach().to(torch.float32).contiguous()
+        if spk.shape != (B, self.spkemb_dim, 1):
+            raise ValueError(f"spkemb must be ({B}, {self.spkemb_dim}, 1), got {tuple(spk.shape)}")
+        Y = torch.empty((B, self.freq_bins, T), device=x.device, dtype=torch.float32)
+        A = torch.empty((B, N, T), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().ssv_text2mel_train_fwd(self._native(), x.data_ptr(), ids.data_ptr(), spk.data_ptr(), B, N, T,
+                                                      Y.data_ptr(), A.data_ptr(), _prec(self.precision),
+                                                      _lib.current_stream_ptr()))
+        return Y, A
 
     def check(self):
         """Synchronise and raise if the decode kernel aborted."""

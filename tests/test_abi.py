@@ -88,6 +88,6 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.SsvError, match="no CPU path"):
         m1(melspec=torch.zeros(1, 80, 1), textid=torch.zeros(1, 1, 5).long(), spkemb=torch.zeros(1, 200, 1),
            pma=torch.zeros(1).long())
-    m1.train()
-    with pytest.raises(NotImplementedError):
+    m1.train()                       # the train branch (teacher-forced forward) is CUDA-only as well
+    with pytest.raises(_lib.SsvError, match="no CPU path"):
         m1(torch.zeros(1, 80, 4), torch.zeros(1, 1, 5).long(), torch.zeros(1, 200, 1))

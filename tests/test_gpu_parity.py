@@ -431,3 +431,37 @@ def test_corpus_driver_writes_wavs(tmp_path, write_driver_cfg):
         sr, w = wavfile.read(tmp_path / "wav" / "s225" / f"s225_{k:03d}.wav")
         assert sr == 22050 and w.dtype == np.float32 and 0 < len(w) <= 9 * 22050
         assert abs(float(w.max()) - 0.75) < 1e-6 and np.isfinite(w).all()
+
+
+# --------------------------------------------------------------------------- train branch (teacher-forced forward)
+def test_train_mode_forward_golden(golden_dir, cuda_models_k):
+    """melSyn.forward in train() mode (models/TTSModel.py:263-273) against the reference's own output."""
+    m1, _, sd1, _ = cuda_models_k
+    z = np.load(golden_dir / "train_seed7.npz")
+    m1.train()
+    try:
+        Y, A = m1(_t(z["mel"]).cuda(), _t(z["textid"]).cuda(), _t(z["spk"]).cuda())      # positional, as the training loops call it
+    finally:
+        m1.eval()
+    assert Y.shape == z["Y"].shape and A.shape == z["A"].shape
+    assert _maxabs(Y, _t(z["Y"])) <= FP32_TOL and _maxabs(A, _t(z["A"])) <= FP32_TOL
+    assert torch.allclose(A.sum(1), torch.ones_like(A.sum(1)), atol=1e-5)
+
+
+def test_train_mode_forward_config5_shape_vs_oracle(cuda_models):
+    """BASELINE config 5 shape (B = 32, N = 64, T = 217) against the oracle; teacher forcing makes the train forward
+    and the incremental decode agree on the first frame."""
+    m1, _, sd1, _ = cuda_models
+    names, emb, _ = W.load_fixtures()
+    ids = W.synthetic_text(32, 64, seed=41)
+    spk = torch.from_numpy(emb[:32].copy())[:, :, None]
+    mel = torch.rand((32, 80, 217), generator=torch.Generator().manual_seed(42))
+    mel[:, :, 0] = 0
+    m1.train()
+    try:
+        Y, A = m1(mel.cuda(), ids.cuda(), spk.cuda())
+    finally:
+        m1.eval()
+    with torch.no_grad():
+        oY, oA = O.melsyn_train_forward(sd1, mel, ids, spk)
+    assert _maxabs(Y, oY) <= FP32_TOL and _maxabs(A, oA) <= FP32_TOL

@@ -128,3 +128,13 @@ def test_window_mask_edges():
                 inside[p:min(p + 2, 8) + 1] = True
                 assert torch.all(col[~inside] == 0) and abs(float(col.sum()) - 1) < 1e-6
                 assert p <= int(mx[b]) <= min(p + 2, 8)
+
+
+def test_oracle_train_forward_against_reference_golden(golden_dir):
+    """Train branch of melSyn.forward (models/TTSModel.py:263-273): oracle == reference output, bit for bit."""
+    z = np.load(golden_dir / "train_seed7.npz")
+    sd1, _ = W.state_dicts(7, init="kaiming", ln_jitter=True)
+    with torch.no_grad():
+        Y, A = O.melsyn_train_forward(sd1, torch.from_numpy(z["mel"]), torch.from_numpy(z["textid"]), torch.from_numpy(z["spk"]))
+    assert float((Y - torch.from_numpy(z["Y"])).abs().max()) <= 2e-6
+    assert float((A - torch.from_numpy(z["A"])).abs().max()) <= 2e-6
