@@ -327,6 +327,15 @@ def main():
         ms = ea.elapsed_time(eb)
         best1 = ms if best1 is None else min(best1, ms)
     m1.check()
+    # BASELINE config 1 shape end to end (one utterance, host buffers in and out): TextEnc + decode + SSRN
+    for _ in range(2):
+        syn.synthesize_host(ids_np[:1], spk_np[:1], T)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        syn.synthesize_host(ids_np[:1], spk_np[:1], T)
+    extra["synthesize_batch1_e2e_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+    for _ in range(2):
+        syn.synthesize_host(ids_np, spk_np, T)          # back to the headline shape (re-creates the staging buffers)
     extra["decode_batch1"] = {"ms": best1, "us_per_frame": 1e3 * best1 / T, "frames_per_s": T / (best1 * 1e-3),
                               "hbm_roofline_frac": T * (DECODE_WEIGHT_BYTES + DECODE_STATE_BYTES_PER_UTT) / (best1 * 1e-3) / 1e9 / measured_peaks()["hbm"]}
 

@@ -279,6 +279,217 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
   }
 }
 
+// ---- few rows (batch-1 TextEnc: 58 rows): split K and N over the whole GPU ----------------------------------------
+// With one CTA per row tile a 58-row problem runs on 4 SMs and every one of them streams the whole weight matrix
+// (TextEnc at B = 1: 3.0 ms, 25 % of a batch-1 synthesis).  Here the weight matrix is cut into (64-column, K / ks)
+// slabs, one per CTA (~128 CTAs); each CTA multiplies its slab with all rows and writes a partial product, and a
+// second kernel (one warp per row) adds the ks partials in a fixed order and applies bias / LayerNorm / gate.
+constexpr int SPL_MAXM = 128;
+constexpr int SPL_T = 256;
+
+__global__ void __launch_bounds__(SPL_T) conv_f32_split_kernel(const ConvArgs a, int klen, int n_pad, float* __restrict__ part) {
+  extern __shared__ __align__(16) float xs[];                 // [klen][Mp] rows contiguous, Mp = M rounded up to 16 / 32 / 64 / 128
+  const int Mp = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
+  const int col0 = blockIdx.x * 64, ks = blockIdx.y;
+  const int K = a.ktaps * a.cin_p;
+  const int k0 = ks * klen, k1 = min(K, k0 + klen);
+  const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
+  // stage my K range of every row: thread (r, q) copies the float4s q, q + T/Mp, ... of row r (channels are contiguous
+  // in X; k0 and cin_p are multiples of 16, so a float4 never straddles a tap), transposed into xs[k][r]
+  {
+    const int r = threadIdx.x % Mp, q0 = threadIdx.x / Mp, qs = SPL_T / Mp;       // Mp in {16, 32, 64, 128} divides 256
+    const int b = r < a.M ? r / a.t_rows : 0, tr = r < a.M ? a.t0 + r % a.t_rows : 0;
+    for (int k4 = q0; k4 < (k1 - k0) / 4; k4 += qs) {
+      const int k = k0 + 4 * k4, j = k / a.cin_p, c = k - j * a.cin_p;
+      const int t = tr + (tap_base + j) * a.dil;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < a.M && t >= 0 && t < a.t_in) v = *reinterpret_cast<const float4*>(a.X + (long)b * a.x_sb + (long)t * a.x_st + c);
+      float* d = xs + (4 * k4) * Mp + r;
+      d[0] = v.x; d[Mp] = v.y; d[2 * Mp] = v.z; d[3 * Mp] = v.w;
+    }
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;     // column, row quarter
+  const int rq = Mp / 4;                                      // rows per thread (multiple of 4, <= 32)
+  float acc[SPL_MAXM / 4];
+#pragma unroll
+  for (int i = 0; i < SPL_MAXM / 4; ++i) acc[i] = 0.f;
+  const float* wp = a.W + (size_t)k0 * n_pad + col0 + tx;
+  // weights in batches of 16 rows: the 16 loads are in flight together (klen is a multiple of 16; rows past K read
+  // as zero), otherwise every k step would wait a full L2 round trip
+  for (int kb = 0; kb < klen; kb += 16) {
+    float w[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) w[u] = k0 + kb + u < K ? __ldg(wp + (size_t)(kb + u) * n_pad) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (k0 + kb + u >= k1) break;
+      const float4* xr = reinterpret_cast<const float4*>(xs + (kb + u) * Mp + ty * rq);
+#pragma unroll
+      for (int i = 0; i < SPL_MAXM / 16; ++i) {
+        if (4 * i < rq) {
+          const float4 x = xr[i];
+          acc[4 * i] = fmaf(x.x, w[u], acc[4 * i]);
+          acc[4 * i + 1] = fmaf(x.y, w[u], acc[4 * i + 1]);
+          acc[4 * i + 2] = fmaf(x.z, w[u], acc[4 * i + 2]);
+          acc[4 * i + 3] = fmaf(x.w, w[u], acc[4 * i + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SPL_MAXM / 4; ++i) {
+    const int r = ty * rq + i;
+    if (i < rq && r < a.M) part[((size_t)ks * a.M + r) * n_pad + col0 + tx] = acc[i];
+  }
+}
+
+// One 256-thread block per row: sum the ks partials (fixed order), bias, then the epilogue of the fused kernels.
+// Thread tid owns columns tid + 256 i, so H1[c] and H2[c] of a highway layer (d = 256 or 512) sit in one thread.
+template <int CNT>
+__device__ __forceinline__ void block_sum(float (&v)[CNT], float* red /*[8][CNT]*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) red[warp * CNT + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w * CNT + i];
+    v[i] = t;
+  }
+}
+
+template <int NPT>      // columns per thread = n_pad / 256
+__global__ void __launch_bounds__(256) conv_f32_split_epilogue(const ConvArgs a, int nks, const float* __restrict__ part) {
+  constexpr int n_pad = 256 * NPT;
+  __shared__ float red[8 * 2];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int b = r / a.t_rows, t = a.t0 + r % a.t_rows;
+  float* y = a.Y + (long)b * a.y_sb + (long)t * a.y_st;
+  float v[NPT];
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) v[i] = 0.f;
+  for (int ks = 0; ks < nks; ++ks) {                          // fixed order; the loads of a step are independent
+    const float* pr = part + ((size_t)ks * a.M + r) * n_pad + tid;
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) v[i] += pr[256 * i];
+  }
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) {
+    const int c = tid + 256 * i;
+    v[i] += a.bias[c];
+    if (a.bias_b != nullptr && c < a.n) v[i] += a.bias_b[(long)b * a.bias_b_ld + c];
+  }
+  if (a.epi == EPI_NONE) {
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+      const int c = tid + 256 * i;
+      if (c < a.y_cols) y[c] = c < a.n ? v[i] : 0.f;
+    }
+    return;
+  }
+  if (a.epi == EPI_HIGHWAY) {
+    if constexpr (NPT >= 2) {
+      constexpr int H = NPT / 2;
+      const int d = a.n / 2;
+      float s[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < H; ++i) { s[0] += v[i]; s[1] += v[i + H]; }
+      block_sum<2>(s, red);
+      const float m1 = s[0] / (float)d, m2 = s[1] / (float)d;
+      float q[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float d1 = v[i] - m1, d2 = v[i + H] - m2;
+        q[0] = fmaf(d1, d1, q[0]); q[1] = fmaf(d2, d2, q[1]);
+      }
+      block_sum<2>(q, red);
+      const float r1 = 1.0f / sqrtf(q[0] / (float)d + 1e-5f), r2 = 1.0f / sqrtf(q[1] / (float)d + 1e-5f);
+      const float* xr = a.X + (long)b * a.x_sb + (long)t * a.x_st;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const int c = tid + 256 * i;
+        const float h1 = (v[i] - m1) * r1 * a.g1[c] + a.b1[c];
+        const float h2 = (v[i + H] - m2) * r2 * a.g2[c] + a.b2[c];
+        const float g = sigmoidf_(h1);
+        y[c] = g * h2 + (1.0f - g) * xr[c];
+      }
+    }
+    return;
+  }
+  float s1[1] = {0.f};
+#pragma unroll
+  for (int i = 0; i < NPT; ++i)
+    if (tid + 256 * i < a.n) s1[0] += v[i];
+  block_sum<1>(s1, red);
+  const float mean = s1[0] / (float)a.n;
+  float q1[1] = {0.f};
+#pragma unroll
+  for (int i = 0; i < NPT; ++i)
+    if (tid + 256 * i < a.n) { const float dd = v[i] - mean; q1[0] = fmaf(dd, dd, q1[0]); }
+  block_sum<1>(q1, red);
+  const float rstd = 1.0f / sqrtf(q1[0] / (float)a.n + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NPT; ++i) {
+    const int c = tid + 256 * i;
+    if (c >= a.y_cols) continue;
+    float o = 0.f;
+    if (c < a.n) {
+      o = (v[i] - mean) * rstd * a.g1[c] + a.b1[c];
+      if (a.epi == EPI_LN_RELU) o = fmaxf(o, 0.f);
+      else if (a.epi == EPI_LN_SIGMOID) o = sigmoidf_(o);
+    }
+    y[c] = o;
+  }
+}
+
+int launch_split(const ConvArgs& a, int n_pad, cudaStream_t s) {
+  static float* part = nullptr;
+  static size_t part_floats = 0;
+  const int K = a.ktaps * a.cin_p;
+  const int slabs = n_pad / 64;
+  int nks = 128 / slabs;
+  if (nks < 1) nks = 1;
+  int klen = (K + nks - 1) / nks;
+  klen = (klen + 15) / 16 * 16;
+  nks = (K + klen - 1) / klen;
+  const size_t need = (size_t)nks * a.M * n_pad;
+  if (need > part_floats) {
+    if (part) cudaFree(part);
+    part = nullptr;
+    if (cudaMalloc((void**)&part, need * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      part_floats = 0;
+      set_error("conv_f32: cannot allocate %zu bytes of split-K partials", need * sizeof(float));
+      return kNoMem;
+    }
+    part_floats = need;
+  }
+  const int Mp = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
+  const size_t smem = (size_t)klen * Mp * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    SSV_CUDA(cudaFuncSetAttribute(conv_f32_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    configured = 200 * 1024;
+  }
+  SSV_CHECK(smem <= 200 * 1024, "conv_f32: split tile does not fit shared memory");
+  conv_f32_split_kernel<<<dim3(slabs, nks), SPL_T, smem, s>>>(a, klen, n_pad, part);
+  SSV_CUDA(cudaGetLastError());
+  if (n_pad == 256) conv_f32_split_epilogue<1><<<a.M, 256, 0, s>>>(a, nks, part);
+  else if (n_pad == 512) conv_f32_split_epilogue<2><<<a.M, 256, 0, s>>>(a, nks, part);
+  else conv_f32_split_epilogue<4><<<a.M, 256, 0, s>>>(a, nks, part);
+  SSV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return kOk;
+}
+
 template <int BM, int CPT, int STAGES>
 int launch_inst(const ConvArgs& a, cudaStream_t s) {
   constexpr int NP = 64 * CPT;
@@ -302,6 +513,9 @@ int launch_conv_f32(const ConvArgs& a, cudaStream_t s) {
   SSV_CHECK(a.M > 0 && a.cin_p % KC == 0 && a.ktaps >= 1 && a.ktaps <= 3, "conv_f32: bad shape");
   const int n_pad = round_up(a.n, 64);
   if (a.epi == EPI_HIGHWAY) SSV_CHECK(a.n == n_pad && (a.n / 64) % 2 == 0, "conv_f32: highway needs n %% 128 == 0");
+  // few rows: cut the weight matrix over the whole GPU instead of streaming all of it through a handful of CTAs
+  if (a.M <= SPL_MAXM && (n_pad == 256 || n_pad == 512 || n_pad == 1024) && (a.epi != EPI_HIGHWAY || (a.n == n_pad && n_pad >= 512)))
+    return launch_split(a, n_pad, s);
   switch (n_pad / 64) {
     case 2:  return launch_inst<32, 2, 3>(a, s);
     case 4:  return launch_inst<32, 4, 3>(a, s);
