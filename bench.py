@@ -361,7 +361,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "phases_ms": {"text_encoder+begin": te_ms, "decode": dec_ms, "ssrn": ssrn_ms},
-        "step_ms": [round(x, 3) for x in step_ms], "e2e_step_ms": [round(1e3 * x, 3) for x in e2e_s],
+        "step_ms": [round(x, 3) for x in step_ms], "e2e_sync_step_ms": [round(1e3 * x, 3) for x in e2e_s],
         "roofline": {"kernel": "decode_ws_kernel (weight-stationary pipelined incremental Text2Mel decode)", "bound": "hbm",
                      "achieved": dec_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm"],
                      "traffic": traffic, "peak_source": peaks["source"],
