@@ -732,10 +732,11 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
       SSV_CUDA(cudaMemsetAsync(d->ws_sent, 0, (size_t)DEC_STAGES * d->maxB * WS_MAX_PARTS * sizeof(int), s));
       d->seq_base = 0;
     }
-    // rows per micro-batch: small batches are latency-bound (one row per micro-batch keeps most micro-batches in
-    // flight over the 24 stages); larger ones amortise the per-visit cost over 2 / 4 rows (measured on B200:
-    // B=32 R=1 51 us/frame vs R=2 63; B=64 R=2 63 vs R=1 72, R=4 84; B=128 R=2 117, R=4 118)
-    d->R = B <= 40 ? 1 : (B <= 128 ? 2 : 4);
+    // rows per micro-batch (measured on B200, us/frame).  Up to 16 micro-batches the
+    // cooperative front end (the warps of a row split its channels) wins: B <= 16 R=1 31-36, B <= 32 R=2 42.
+    // Past that one warp per row with 4 / R micro-batches in flight: B=40 R=1 49 (R=2 51); B=64 R=2 56 (R=1 74,
+    // R=4 61); B=128 R=2 108 (R=4 111); B=256 R=4 225.
+    d->R = B <= 16 ? 1 : B <= 32 ? 2 : B <= 40 ? 1 : (B <= 128 ? 2 : 4);
     if (const char* e = getenv("SSV_DECODE_R")) {          // development knob
       const int r = atoi(e);
       if (r == 1 || r == 2 || r == 4) d->R = r;

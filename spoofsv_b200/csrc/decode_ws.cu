@@ -34,6 +34,7 @@
 #include "decode.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace ssv {
 
@@ -59,7 +60,8 @@ constexpr int SM_LN = SM_REC + 24 * HD;            // [4][256] LayerNorm paramet
 constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
 constexpr int SM_PMA = SM_BIAS + 128;              // [WS_MAX_BATCH] ints (attention stage only)
 constexpr int SM_KV = SM_PMA + WS_MAX_BATCH;        // [4 warps][K window 3 | V window 3][256]: attention rows prefetched by cp.async
-constexpr int SM_TOTAL = SM_KV + 4 * 6 * HD;
+constexpr int SM_RED = SM_KV + 4 * 6 * HD;          // [4 rounds][4 warps] float4: cross-warp LayerNorm / logit sums (cooperative front end)
+constexpr int SM_TOTAL = SM_RED + 4 * 4 * 4;
 
 struct __align__(8) Word { float v; int tag; };
 
@@ -469,7 +471,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
               if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) bad = true;
             }
           };
-          if (need_wait) {
+          if (need_wait && !(p.ws_flags & WS_FLAG_ROWPOLL)) {
             const int* sp = p.ws_sent + ((size_t)c.prev * G + g) * WS_MAX_PARTS;
             for (;;) {
               const int sv = lane < c.prev_parts ? ld_relaxed_s32(sp + lane) : tag_in;
@@ -764,7 +766,455 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 #undef PROF_F
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Cooperative front end (warps 0-3): the 4 / RT warps of a row split its 256 channels, so the dependent chain of
+// one stage -- tagged-word loads, two LayerNorm reductions, gate, X stores -- is 2 * RT channels per lane instead
+// of 8.  One micro-batch is in the front end at a time; a warp reads only taps that it wrote itself (its channel
+// slice), so the taps need no cross-warp synchronisation at all.
+template <int WPR>
+__device__ __forceinline__ void row_reduce(float& a, float& b, float& c3, bool& bad, float* red, int round, int warp, int r, int lane) {
+  warp_sum2(a, b);
+  c3 = warp_sum(c3);
+  if (WPR > 1) {
+    float4* slot = reinterpret_cast<float4*>(red) + round * 4;
+    if (lane == 0) slot[warp] = make_float4(a, b, c3, bad ? 1.f : 0.f);
+    named_bar(2 + r, WPR * 32);
+    float sa = 0.f, sb = 0.f, sc = 0.f, sf = 0.f;
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) {          // fixed order: every warp of the row gets bit-identical sums
+      const float4 x = slot[r * WPR + w];
+      sa += x.x; sb += x.y; sc += x.z; sf += x.w;
+    }
+    a = sa; b = sb; c3 = sc;
+    bad = sf != 0.f;                          // row-uniform from here on
+  }
+}
+
 template <int RT, bool PROF>
+__device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStage& st, const Ctx& c, int tid) {
+  constexpr int WPR = 4 / RT;               // warps per row
+  constexpr int NP = RT;                    // channel pairs per lane
+  constexpr int CW = HD / WPR;              // channels per warp
+  constexpr int NBUF = MAXBUF / RT;
+  constexpr int NREC = 24 / RT;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int r = warp / WPR, sub = warp % WPR;
+  const int cb = sub * CW + 2 * lane;       // pair i: channels cb + 64 i, cb + 64 i + 1
+  const int s = c.s, part = c.part, G = c.G, B = c.B;
+  const bool designated = part == 0;
+  const float* lnp = c.smem + SM_LN;
+  const float* g1 = lnp;
+  const float* b1 = lnp + HD;
+  const float* g2 = lnp + 2 * HD;
+  const float* b2 = lnp + 3 * HD;
+  int* pma_w = reinterpret_cast<int*>(c.smem + SM_PMA) + sub * B;     // my warp's own copy of the alignment state
+  float* red = c.smem + SM_RED;
+  float* rec = c.smem + SM_REC;
+  float* kvs = c.smem + SM_KV + r * (6 * HD);
+  const Word* raw_in = reinterpret_cast<const Word*>(p.ws_raw) + (size_t)c.prev * B * WS_WORDS;
+  Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)s * B * WS_WORDS;
+  const int koff = st.hwy ? 2 * TAPP : 0;
+  const int n_visits = p.n_steps + (s == 0 ? 1 : 0);
+  const int total_visits = n_visits * G;
+  const int pro = st.pro;
+
+  long long prof_last = 0, prof_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const bool prof_on = PROF && p.prof != nullptr && tid == 0;
+  if (prof_on) prof_last = clock64();
+#define PROF_F(i)                                  \
+  if (prof_on) {                                   \
+    const long long now_ = clock64();              \
+    prof_acc[i] += now_ - prof_last;               \
+    prof_last = now_;                              \
+  }
+
+  float2 tp[2][NP];
+  bool have_pref = false, bad = false;
+  int step = 0, g = 0;
+  for (int v = 0; v < total_visits; ++v, ++g) {
+    if (g == G) { g = 0; ++step; }
+    const int t = p.t_start + step;
+    const bool final_visit = s == 0 && step == p.n_steps;
+    const int tag = p.seq_base + t + 1;
+    const int tag_in = s == 0 ? tag - 1 : tag;
+    const bool need_wait = !(s == 0 && step == 0);
+    const int q = v % NBUF;
+    const int u = v / NBUF;
+    float* X = c.smem + SM_X + q * (XROWS * RT);
+    const int row0 = g * RT;
+    const bool live = row0 + r < B;
+    const int b = row0 + r;
+    PROF_F(0);
+    if ((v & 15) == 15) {                    // a launch aborted elsewhere: becomes row-uniform in the next reduction
+      int ab = 0;
+      if (lane == 0) ab = *reinterpret_cast<volatile int*>(p.abort_flag);
+      if (__shfl_sync(FULL, ab, 0) != 0) bad = true;
+    }
+
+    // ---- 1. my slice of the old taps t-2d, t-d -> X rows [0, 256) and [264, 520): from the recent-row ring in
+    //         shared memory when one of the last NREC visits produced it, else from my private ring in global
+    //         memory (prefetched at the end of the previous visit).  Both were written by this very warp.
+    if (st.ntaps == 3) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int back = (2 - j) * st.dil;
+        const int tt = t - back;
+        const int dist = back * G;
+        if (tt < 0 || !live) {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) tp[j][i] = make_float2(0.f, 0.f);
+        } else if (tt >= p.t_start && dist < NREC) {
+          const float* src = rec + ((size_t)((v - dist) % NREC) * RT + r) * HD + cb;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) tp[j][i] = *reinterpret_cast<const float2*>(src + 64 * i);
+        } else if (!have_pref) {
+          const int slot = tt % st.hist_depth;
+          const float* src = p.ws_hist + ((((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * RT + r) * HD + cb;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) tp[j][i] = __ldcg(reinterpret_cast<const float2*>(src + 64 * i));
+        }
+      }
+      if (u >= 1) {
+        if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          float* xp = X + ((size_t)j * TAPP + cb + 64 * i) * RT + r;
+          if (RT == 1) *reinterpret_cast<float2*>(xp) = tp[j][i];
+          else { xp[0] = tp[j][i].x; xp[RT] = tp[j][i].y; }
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c.tapsfull[q]);
+    } else if (!final_visit && u >= 1) {
+      if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
+    }
+    PROF_F(2);
+
+    // ---- 1b. attention stage: fetch my slice of the K / V window rows (cp.async) under the wait for the producer
+    int p0 = 0, cnt = 1;
+    if (pro == PRO_ATT && live) {
+      p0 = pma_w[b];
+      cnt = min(p0 + 2, p.N - 1) - p0 + 1;
+      const float* kp = p.Kt + ((size_t)b * p.N + p0) * HD + sub * CW;
+      const float* vp = p.Vt + ((size_t)b * p.N + p0) * HD + sub * CW;
+      float* kd = kvs + sub * CW;
+      for (int i = lane; i < cnt * (CW / 4); i += 32) {
+        const int row = i / (CW / 4), cc = (i % (CW / 4)) * 4;
+        cp_async16(kd + row * HD + cc, kp + (size_t)row * HD + cc, true);
+        cp_async16(kd + (3 + row) * HD + cc, vp + (size_t)row * HD + cc, true);
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+
+    // ---- 2./3. wait for the producers of my input row, then the prologue: u_t -> X[koff ..][r]
+    float2 o[NP];                                          // my slice of the stage input (joins the rings below)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) o[i] = make_float2(0.f, 0.f);
+    float* xcur = X + (size_t)koff * RT + r;               // channel ch at xcur[ch * RT]
+    auto xstore = [&](int ch, float2 val) {
+      float* xp = xcur + (size_t)ch * RT;
+      if (RT == 1) *reinterpret_cast<float2*>(xp) = val;
+      else { xp[0] = val.x; xp[RT] = val.y; }
+    };
+    if (!live) {
+      if (!final_visit)
+        for (int ch = lane + 32 * sub; ch < st.k_seg; ch += 32 * WPR) xcur[(size_t)ch * RT] = 0.f;
+    } else if (pro == PRO_X && sub != 0) {
+      // 80 mel channels: the first warp of the row does them alone
+    } else {
+      long long t0 = 0;
+      unsigned spins = 0;
+      auto spin_check = [&]() {
+        if ((++spins & 255u) == 0) {
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > SPIN_LIMIT) atomicExch(p.abort_flag, 8);
+          if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) bad = true;
+        }
+      };
+      if (need_wait && !(p.ws_flags & WS_FLAG_ROWPOLL)) {
+        const int* sp = p.ws_sent + ((size_t)c.prev * G + g) * WS_MAX_PARTS;
+        for (;;) {
+          const int sv = lane < c.prev_parts ? ld_relaxed_s32(sp + lane) : tag_in;
+          if (__all_sync(FULL, sv - tag_in >= 0)) break;
+          spin_check();
+          if (__any_sync(FULL, bad)) { bad = true; break; }
+        }
+      }
+      PROF_F(3);
+      if (PROF && p.prof != nullptr && tid == 0) c.t_seen[q] = clock64();
+      const Word* R = raw_in + (size_t)b * WS_WORDS;
+      if (pro == PRO_X) {
+        float y[3];
+        if (!need_wait) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int f = lane + 32 * i;
+            float xv = 0.f;
+            if (f < p.F) {
+              if (p.x_ext) xv = p.x_ext[(long)b * p.x_sb + (long)f * p.x_sf];
+              else if (t > 0) xv = __ldcg(p.Y + ((size_t)b * p.F + f) * p.t_cap + (t - 1));
+            }
+            y[i] = xv;
+          }
+        } else {
+          float vv[3] = {0.f, 0.f, 0.f};
+          while (!bad) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const int f = lane + 32 * i;
+              vv[i] = 0.f;
+              if (f < p.F) { int tg; ld_word(R + f, vv[i], tg); ok &= tg == tag_in; }
+            }
+            if (__all_sync(FULL, ok)) break;
+            spin_check();
+            if (__any_sync(FULL, bad)) bad = true;
+          }
+          float sm = vv[0] + vv[1] + vv[2];
+          sm = warp_sum(sm);
+          const float mean = sm / (float)p.F;
+          float qq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float d = vv[i] - mean;
+            qq += lane + 32 * i < p.F ? d * d : 0.f;
+          }
+          qq = warp_sum(qq);
+          const float rstd = 1.0f / sqrtf(qq / (float)p.F + 1e-5f);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int f = lane + 32 * i;
+            y[i] = f < p.F ? sigmoidf_((vv[i] - mean) * rstd * g1[f] + b1[f]) : 0.f;
+            if (f < p.F && !bad && designated) p.Y[((size_t)b * p.F + f) * p.t_cap + (t - 1)] = y[i];
+          }
+        }
+        if (!final_visit) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int f = lane + 32 * i;
+            if (f < p.F) xcur[(size_t)f * RT] = y[i];
+          }
+        }
+      } else if (pro == PRO_LN || pro == PRO_LN_RELU) {
+        float2 vv[NP];
+        while (!bad) {
+          bool ok = true;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            int ta, tb;
+            ld_word2(R + cb + 64 * i, vv[i].x, ta, vv[i].y, tb);
+            ok &= ta == tag_in && tb == tag_in;
+          }
+          if (__all_sync(FULL, ok)) break;
+          spin_check();
+          if (__any_sync(FULL, bad)) bad = true;
+        }
+        if (PROF && prof_on) PROF_F(4);
+        float sum = 0.f, z0 = 0.f, z1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) sum += vv[i].x + vv[i].y;
+        row_reduce<WPR>(sum, z0, z1, bad, red, 0, warp, r, lane);
+        const float mean = sum / (float)HD;
+        float qq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const float d0 = vv[i].x - mean, d1 = vv[i].y - mean;
+          qq = fmaf(d0, d0, qq);
+          qq = fmaf(d1, d1, qq);
+        }
+        z0 = z1 = 0.f;
+        row_reduce<WPR>(qq, z0, z1, bad, red, 1, warp, r, lane);
+        const float rstd = rstd_fast(qq / (float)HD);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const int ch = cb + 64 * i;
+          float o0 = (vv[i].x - mean) * rstd * g1[ch] + b1[ch];
+          float o1 = (vv[i].y - mean) * rstd * g1[ch + 1] + b1[ch + 1];
+          if (pro == PRO_LN_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+          o[i] = make_float2(o0, o1);
+          xstore(ch, o[i]);
+          if (st.hwy && (ch >> 5) == part)                 // my residual slice travels with my outputs
+            st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + ch, o0, o1, tag);
+        }
+      } else {   // PRO_HWY / PRO_ATT: the producer is a highway layer: H1 | H2 | its input (my residual)
+        float2 h1[NP], h2[NP], xr[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) h1[i] = h2[i] = xr[i] = make_float2(0.f, 0.f);
+        while (!bad) {
+          bool ok = true;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            int ta, tb;
+            const Word* wp = R + cb + 64 * i;
+            ld_word2(wp, h1[i].x, ta, h1[i].y, tb);
+            ok &= ta == tag_in && tb == tag_in;
+            ld_word2(wp + HD, h2[i].x, ta, h2[i].y, tb);
+            ok &= ta == tag_in && tb == tag_in;
+            ld_word2(wp + 2 * HD, xr[i].x, ta, xr[i].y, tb);
+            ok &= ta == tag_in && tb == tag_in;
+          }
+          if (__all_sync(FULL, ok)) break;
+          spin_check();
+          if (__any_sync(FULL, bad)) bad = true;
+        }
+        if (PROF && prof_on) PROF_F(4);
+        float s1 = 0.f, s2 = 0.f, z = 0.f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) { s1 += h1[i].x + h1[i].y; s2 += h2[i].x + h2[i].y; }
+        row_reduce<WPR>(s1, s2, z, bad, red, 0, warp, r, lane);
+        const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
+        float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          float d = h1[i].x - m1; q1 = fmaf(d, d, q1);
+          d = h1[i].y - m1; q1 = fmaf(d, d, q1);
+          d = h2[i].x - m2; q2 = fmaf(d, d, q2);
+          d = h2[i].y - m2; q2 = fmaf(d, d, q2);
+        }
+        z = 0.f;
+        row_reduce<WPR>(q1, q2, z, bad, red, 1, warp, r, lane);
+        const float r1 = rstd_fast(q1 / (float)HD);
+        const float r2 = rstd_fast(q2 / (float)HD);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const int ch = cb + 64 * i;
+          const float a0 = (h1[i].x - m1) * r1 * g1[ch] + b1[ch];
+          const float a1 = (h1[i].y - m1) * r1 * g1[ch + 1] + b1[ch + 1];
+          const float c0 = (h2[i].x - m2) * r2 * g2[ch] + b2[ch];
+          const float c1 = (h2[i].y - m2) * r2 * g2[ch + 1] + b2[ch + 1];
+          const float gt0 = sigmoid_fast(a0), gt1 = sigmoid_fast(a1);
+          o[i] = make_float2(gt0 * c0 + (1.0f - gt0) * xr[i].x, gt1 * c1 + (1.0f - gt1) * xr[i].y);
+        }
+        if (pro == PRO_HWY) {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            const int ch = cb + 64 * i;
+            xstore(ch, o[i]);
+            if (st.hwy && (ch >> 5) == part) st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + ch, o[i].x, o[i].y, tag);
+          }
+        } else {
+          // windowed attention, models/TTSModel.py:281-295: logits over [pma, min(pma+2, N-1)];
+          // every other character is masked to -2^32 and gets softmax weight exactly 0.
+          asm volatile("cp.async.wait_all;\n" ::: "memory");
+          __syncwarp();
+          const float* kp = kvs;
+          const float* vp = kvs + 3 * HD;
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            const int ch = cb + 64 * i;
+            const float2 k0 = *reinterpret_cast<const float2*>(kp + ch);
+            l0 = fmaf(k0.x, o[i].x, l0); l0 = fmaf(k0.y, o[i].y, l0);
+            if (cnt > 1) {
+              const float2 k1 = *reinterpret_cast<const float2*>(kp + HD + ch);
+              l1 = fmaf(k1.x, o[i].x, l1); l1 = fmaf(k1.y, o[i].y, l1);
+            }
+            if (cnt > 2) {
+              const float2 k2 = *reinterpret_cast<const float2*>(kp + 2 * HD + ch);
+              l2 = fmaf(k2.x, o[i].x, l2); l2 = fmaf(k2.y, o[i].y, l2);
+            }
+          }
+          row_reduce<WPR>(l0, l1, l2, bad, red, 2, warp, r, lane);
+          l0 *= 0.0625f; l1 *= 0.0625f; l2 *= 0.0625f;    // 1/sqrt(256)
+          float mx = l0;
+          if (cnt > 1) mx = fmaxf(mx, l1);
+          if (cnt > 2) mx = fmaxf(mx, l2);
+          const float e0 = expf(l0 - mx);
+          const float e1 = cnt > 1 ? expf(l1 - mx) : 0.f;
+          const float e2 = cnt > 2 ? expf(l2 - mx) : 0.f;
+          const float den = e0 + e1 + e2;
+          const float a0 = e0 / den, a1 = e1 / den, a2 = e2 / den;
+          int best = 0;
+          float bv = a0;
+          if (cnt > 1 && a1 > bv) { best = 1; bv = a1; }
+          if (cnt > 2 && a2 > bv) { best = 2; bv = a2; }
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            const int ch = cb + 64 * i;
+            const float2 v0 = *reinterpret_cast<const float2*>(vp + ch);
+            float rx = a0 * v0.x, ry = a0 * v0.y;
+            if (cnt > 1) {
+              const float2 v1 = *reinterpret_cast<const float2*>(vp + HD + ch);
+              rx = fmaf(a1, v1.x, rx); ry = fmaf(a1, v1.y, ry);
+            }
+            if (cnt > 2) {
+              const float2 v2 = *reinterpret_cast<const float2*>(vp + 2 * HD + ch);
+              rx = fmaf(a2, v2.x, rx); ry = fmaf(a2, v2.y, ry);
+            }
+            xstore(ch, make_float2(rx, ry));              // R
+            xstore(HD + ch, o[i]);                         // Q
+          }
+          __syncwarp();                                    // every lane has read the window before the next prefetch
+          if (lane == 0 && !bad) {
+            pma_w[b] = p0 + best;
+            if (designated && sub == 0) {
+              float* Ab = p.A + ((size_t)b * p.N + p0) * p.t_cap + t;
+              Ab[0] = a0;
+              if (cnt > 1) Ab[p.t_cap] = a1;
+              if (cnt > 2) Ab[2 * (size_t)p.t_cap] = a2;
+              p.pma_traj[(size_t)t * B + b] = p0 + best;
+              p.pma_state[b] = p0 + best;
+            }
+          }
+        }
+      }
+    }
+    if (final_visit) continue;                 // stage 0 after the last frame: prologue only
+    PROF_F(6);
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&c.curfull[q]);              // release: my slice of the micro-batch is in X
+      if (PROF && p.prof != nullptr && tid == 0) c.t_seen[8 + q] = clock64();
+    }
+    // ---- 4. my slice of the stage input joins the recent-row ring and my private global ring (later frames' taps)
+    if (st.ntaps == 3 && live) {
+      const int slot = t % st.hist_depth;
+      float* dst = p.ws_hist + ((((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * RT + r) * HD + cb;
+      float* rdst = rec + ((size_t)(v % NREC) * RT + r) * HD + cb;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        *reinterpret_cast<float2*>(rdst + 64 * i) = o[i];
+        __stcg(reinterpret_cast<float2*>(dst + 64 * i), o[i]);
+      }
+    }
+    // leave an aborted launch only where every warp of my row agrees (after a reduction, or where there is none)
+    if (bad && (WPR == 1 || pro == PRO_X || live)) return;
+    // ---- 5. global-ring taps of the next visit: issue the loads now, they land while I wait for its producer
+    have_pref = false;
+    if (st.ntaps == 3 && v + 1 < total_visits) {
+      int step2 = step, g2 = g + 1;
+      if (g2 == G) { g2 = 0; ++step2; }
+      const int t2 = p.t_start + step2;
+      if (g2 * RT + r < B) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int back = (2 - j) * st.dil;
+          const int tt = t2 - back;
+          const int dist = back * G;
+          if (tt >= 0 && !(tt >= p.t_start && dist < NREC)) {
+            const int slot = tt % st.hist_depth;
+            const float* src = p.ws_hist + ((((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g2) * RT + r) * HD + cb;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) tp[j][i] = __ldcg(reinterpret_cast<const float2*>(src + 64 * i));
+          }
+        }
+        have_pref = true;
+      }
+    }
+    PROF_F(5);
+  }
+  if (prof_on) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 16 + i] = prof_acc[i];
+    p.prof[(size_t)blockIdx.x * 16 + 15] = total_visits > 0 ? total_visits : 1;
+  }
+#undef PROF_F
+}
+
+template <int RT, bool PROF, bool COOP>
 __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t bars[3 * MAXBUF + 6];
@@ -822,17 +1272,18 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
     }
     if (st.pro == PRO_ATT) {
       int* pma_s = reinterpret_cast<int*>(smem + SM_PMA);
+      const int copies = COOP ? 4 / RT : 1;               // cooperative front end: one copy per warp of a row
       for (int i = tid; i < p.B; i += NT) {
         const int pv = p.pma_in ? (int)p.pma_in[i] : p.pma_state[i];
-        pma_s[i] = max(0, min(pv, p.N - 1));
+        for (int w = 0; w < copies; ++w) pma_s[w * p.B + i] = max(0, min(pv, p.N - 1));
       }
     }
     if (tid == 0) {
       s_bad = 0;
       s_fe_done[0] = s_fe_done[1] = s_fe_done[2] = s_fe_done[3] = 0;
       for (int i = 0; i < MAXBUF; ++i) {
-        mbar_init(&bars[i], RT);                   // tapsfull: one arrival per row
-        mbar_init(&bars[MAXBUF + i], RT);          // curfull: one arrival per row
+        mbar_init(&bars[i], COOP ? 4 : RT);              // tapsfull: one arrival per front-end warp of the visit
+        mbar_init(&bars[MAXBUF + i], COOP ? 4 : RT);     // curfull: likewise
         mbar_init(&bars[2 * MAXBUF + i], 1);       // empty
       }
       for (int i = 0; i < 2; ++i) {
@@ -847,7 +1298,8 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   }
 
   if (tid < FE_T) {
-    front_role<RT, PROF>(p, st, c, tid);
+    if (COOP) front_role_coop<RT, PROF>(p, st, c, tid);
+    else front_role<RT, PROF>(p, st, c, tid);
   } else {
     const int gtid = tid - FE_T;
     if (st.hwy) gemv_role<RT, 16, true, PROF>(p, st, c, gtid);
@@ -883,19 +1335,25 @@ __global__ void ws_pack_image_kernel(const float* __restrict__ W, WsStage w, flo
   }
 }
 
-template <int RT, bool PROF>
+template <int RT, bool PROF, bool COOP>
 int launch_rt(const DecParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)SM_TOTAL * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT, PROF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   DecParams pl = p;
   void* args[] = {&pl};
-  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT, PROF>, dim3(WS_GRID), dim3(NT), args, smem, s));
+  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT, PROF, COOP>, dim3(WS_GRID), dim3(NT), args, smem, s));
   ++g_launches;
   return kOk;
+}
+
+template <bool COOP>
+int launch_fe(const DecParams& p, cudaStream_t s) {
+  if (p.prof) return p.R == 1 ? launch_rt<1, true, COOP>(p, s) : p.R == 2 ? launch_rt<2, true, COOP>(p, s) : launch_rt<4, true, COOP>(p, s);
+  return p.R == 1 ? launch_rt<1, false, COOP>(p, s) : p.R == 2 ? launch_rt<2, false, COOP>(p, s) : launch_rt<4, false, COOP>(p, s);
 }
 
 }  // namespace
@@ -951,8 +1409,20 @@ int launch_decode_ws(const DecParams& p, cudaStream_t s) {
   SSV_CHECK(p.B <= WS_MAX_BATCH, "decode: batch %d exceeds %d", p.B, WS_MAX_BATCH);
   SSV_CHECK(p.ws_stages && p.ws_raw && p.ws_sent && p.ws_hist, "decode: weight-stationary buffers missing");
   SSV_CHECK(p.R == 1 || p.R == 2 || p.R == 4, "decode: micro-batch rows must be 1, 2 or 4");
-  if (p.prof) return p.R == 1 ? launch_rt<1, true>(p, s) : p.R == 2 ? launch_rt<2, true>(p, s) : launch_rt<4, true>(p, s);
-  return p.R == 1 ? launch_rt<1, false>(p, s) : p.R == 2 ? launch_rt<2, false>(p, s) : launch_rt<4, false>(p, s);
+  // Front end: "coop" = the 4 / R warps of a row split its channels (one micro-batch in the front end at a time);
+  // "warp" = one warp per row, 4 / R micro-batches in flight.  (SSV_WS_FE picks one for A/B runs.)
+  static int fe = -1, rowpoll = 1;
+  if (fe < 0) {
+    const char* e = getenv("SSV_WS_FE");
+    fe = !e ? 2 : !strcmp(e, "warp") ? 0 : !strcmp(e, "coop") ? 1 : 2;
+    const char* q = getenv("SSV_WS_POLL");
+    rowpoll = !(q && !strcmp(q, "sentinel"));
+  }
+  bool coop = fe == 1 || (fe == 2 && p.G <= 16);      // the cooperative front end serves one micro-batch at a time
+  coop = coop && (4 / p.R) * p.B <= WS_MAX_BATCH;     // per-warp copies of the alignment state must fit
+  DecParams pl = p;
+  pl.ws_flags = rowpoll ? WS_FLAG_ROWPOLL : 0;
+  return coop ? launch_fe<true>(pl, s) : launch_fe<false>(pl, s);
 }
 
 }  // namespace ssv
