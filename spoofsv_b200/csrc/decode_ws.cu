@@ -60,8 +60,8 @@ constexpr int SM_LN = SM_REC + 24 * HD;            // [4][256] LayerNorm paramet
 constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
 constexpr int SM_PMA = SM_BIAS + 128;              // [WS_MAX_BATCH] ints (attention stage only)
 constexpr int SM_KV = SM_PMA + WS_MAX_BATCH;        // [4 warps][K window 3 | V window 3][256]: attention rows prefetched by cp.async
-constexpr int SM_RED = SM_KV + 4 * 6 * HD;          // [4 rounds][4 warps] float4: cross-warp LayerNorm / logit sums (cooperative front end)
-constexpr int SM_TOTAL = SM_RED + 4 * 4 * 4;
+constexpr int SM_RED = SM_KV + 4 * 6 * HD;          // [4 rounds][4 warps][8]: cross-warp LayerNorm statistics / logit sums (cooperative front end)
+constexpr int SM_TOTAL = SM_RED + 4 * 4 * 8;
 
 struct __align__(8) Word { float v; int tag; };
 
@@ -148,6 +148,38 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b) {
     b += __shfl_xor_sync(FULL, b, o);
   }
 }
+// One-pass LayerNorm statistics: every lane holds (sum, M2 = sum of squared deviations from its own mean) of N0
+// values; the butterfly merges equal-sized groups with Chan's update M2 = M2a + M2b + (sa - sb)^2 / (2 n), which is
+// symmetric, so all lanes end with bit-identical totals -- one dependent shuffle chain instead of two (mean, then
+// variance).  Two independent channels (H1 | H2) ride the same chain.
+template <int N0>
+__device__ __forceinline__ void warp_stats2(float& s1, float& m1, float& s2, float& m2) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int off = 16 >> k;
+    const float c = 0.5f / (float)(N0 << k);
+    const float sp1 = __shfl_xor_sync(FULL, s1, off), mp1 = __shfl_xor_sync(FULL, m1, off);
+    const float sp2 = __shfl_xor_sync(FULL, s2, off), mp2 = __shfl_xor_sync(FULL, m2, off);
+    const float d1 = s1 - sp1, d2 = s2 - sp2;
+    m1 = (m1 + mp1) + d1 * d1 * c;
+    m2 = (m2 + mp2) + d2 * d2 * c;
+    s1 += sp1;
+    s2 += sp2;
+  }
+}
+template <int N0>
+__device__ __forceinline__ void warp_stats1(float& s1, float& m1) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int off = 16 >> k;
+    const float c = 0.5f / (float)(N0 << k);
+    const float sp1 = __shfl_xor_sync(FULL, s1, off), mp1 = __shfl_xor_sync(FULL, m1, off);
+    const float d1 = s1 - sp1;
+    m1 = (m1 + mp1) + d1 * d1 * c;
+    s1 += sp1;
+  }
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 // Highway gate / LayerNorm scale on the frame's critical path: MUFU-based, branch-free (2 ulp), so the eight
 // per-lane chains interleave instead of serialising on the slow-path calls of IEEE division / sqrt.
@@ -551,15 +583,16 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
               if (__any_sync(FULL, bad)) bad = true;
             }
             if (PROF && prof_on) PROF_F(4);
-            float sum = 0.f;
+            float sum = 0.f, qq = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) sum += vv[i];
-            sum = warp_sum(sum);
-            const float mean = sum / (float)HD;
-            float qq = 0.f;
+            {
+              const float lm = sum * 0.125f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = vv[i] - mean; qq = fmaf(d, d, qq); }
-            qq = warp_sum(qq);
+              for (int i = 0; i < 8; ++i) { const float d = vv[i] - lm; qq = fmaf(d, d, qq); }
+            }
+            warp_stats1<8>(sum, qq);
+            const float mean = sum / (float)HD;
             const float rstd = rstd_fast(qq / (float)HD);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -598,16 +631,18 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { s1 += h1[i]; s2 += h2[i]; }
-            warp_sum2(s1, s2);
-            const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
             float q1 = 0.f, q2 = 0.f;
+            {
+              const float l1 = s1 * 0.125f, l2 = s2 * 0.125f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float d1 = h1[i] - m1, d2 = h2[i] - m2;
-              q1 = fmaf(d1, d1, q1);
-              q2 = fmaf(d2, d2, q2);
+              for (int i = 0; i < 8; ++i) {
+                const float d1 = h1[i] - l1, d2 = h2[i] - l2;
+                q1 = fmaf(d1, d1, q1);
+                q2 = fmaf(d2, d2, q2);
+              }
             }
-            warp_sum2(q1, q2);
+            warp_stats2<8>(s1, q1, s2, q2);
+            const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
             const float r1 = rstd_fast(q1 / (float)HD);
             const float r2 = rstd_fast(q2 / (float)HD);
             float uu[8];
@@ -777,17 +812,52 @@ __device__ __forceinline__ void row_reduce(float& a, float& b, float& c3, bool& 
   warp_sum2(a, b);
   c3 = warp_sum(c3);
   if (WPR > 1) {
-    float4* slot = reinterpret_cast<float4*>(red) + round * 4;
-    if (lane == 0) slot[warp] = make_float4(a, b, c3, bad ? 1.f : 0.f);
+    float4* slot = reinterpret_cast<float4*>(red) + round * 8;
+    if (lane == 0) slot[2 * warp] = make_float4(a, b, c3, bad ? 1.f : 0.f);
     named_bar(2 + r, WPR * 32);
     float sa = 0.f, sb = 0.f, sc = 0.f, sf = 0.f;
 #pragma unroll
     for (int w = 0; w < WPR; ++w) {          // fixed order: every warp of the row gets bit-identical sums
-      const float4 x = slot[r * WPR + w];
+      const float4 x = slot[2 * (r * WPR + w)];
       sa += x.x; sb += x.y; sc += x.z; sf += x.w;
     }
     a = sa; b = sb; c3 = sc;
     bad = sf != 0.f;                          // row-uniform from here on
+  }
+}
+
+// (sum, M2) of two channels over the whole row: per-warp butterfly, then the WPR warp totals (CW values each) are
+// merged pairwise in a fixed order by every warp.
+template <int WPR, int N0>
+__device__ __forceinline__ void row_stats2(float& s1, float& m1, float& s2, float& m2, bool& bad, float* red, int round, int warp, int r, int lane) {
+  warp_stats2<N0>(s1, m1, s2, m2);
+  if (WPR > 1) {
+    constexpr int CW = HD / WPR;
+    float4* slot = reinterpret_cast<float4*>(red) + round * 8;
+    if (lane == 0) {
+      slot[2 * warp] = make_float4(s1, m1, s2, m2);
+      slot[2 * warp + 1] = make_float4(bad ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    }
+    named_bar(2 + r, WPR * 32);
+    float4 e[WPR];
+    float sf = 0.f;
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) {
+      e[w] = slot[2 * (r * WPR + w)];
+      sf += slot[2 * (r * WPR + w) + 1].x;
+    }
+#pragma unroll
+    for (int n = CW, cnt = WPR; cnt > 1; cnt >>= 1, n <<= 1) {
+      const float c = 0.5f / (float)n;
+#pragma unroll
+      for (int w = 0; w < cnt / 2; ++w) {
+        const float4 x = e[2 * w], y = e[2 * w + 1];
+        const float d1 = x.x - y.x, d2 = x.z - y.z;
+        e[w] = make_float4(x.x + y.x, (x.y + y.y) + d1 * d1 * c, x.z + y.z, (x.w + y.w) + d2 * d2 * c);
+      }
+    }
+    s1 = e[0].x; m1 = e[0].y; s2 = e[0].z; m2 = e[0].w;
+    bad = sf != 0.f;
   }
 }
 
@@ -1013,20 +1083,20 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
           if (__any_sync(FULL, bad)) bad = true;
         }
         if (PROF && prof_on) PROF_F(4);
-        float sum = 0.f, z0 = 0.f, z1 = 0.f;
+        float sum = 0.f, qq = 0.f, z0 = 0.f, z1 = 0.f;
 #pragma unroll
         for (int i = 0; i < NP; ++i) sum += vv[i].x + vv[i].y;
-        row_reduce<WPR>(sum, z0, z1, bad, red, 0, warp, r, lane);
-        const float mean = sum / (float)HD;
-        float qq = 0.f;
+        {
+          const float lm = sum * (1.0f / (float)(2 * NP));
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          const float d0 = vv[i].x - mean, d1 = vv[i].y - mean;
-          qq = fmaf(d0, d0, qq);
-          qq = fmaf(d1, d1, qq);
+          for (int i = 0; i < NP; ++i) {
+            const float d0 = vv[i].x - lm, d1 = vv[i].y - lm;
+            qq = fmaf(d0, d0, qq);
+            qq = fmaf(d1, d1, qq);
+          }
         }
-        z0 = z1 = 0.f;
-        row_reduce<WPR>(qq, z0, z1, bad, red, 1, warp, r, lane);
+        row_stats2<WPR, 2 * NP>(sum, qq, z0, z1, bad, red, 2 * (v & 1), warp, r, lane);
+        const float mean = sum / (float)HD;
         const float rstd = rstd_fast(qq / (float)HD);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
@@ -1061,21 +1131,21 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
           if (__any_sync(FULL, bad)) bad = true;
         }
         if (PROF && prof_on) PROF_F(4);
-        float s1 = 0.f, s2 = 0.f, z = 0.f;
+        float s1 = 0.f, s2 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NP; ++i) { s1 += h1[i].x + h1[i].y; s2 += h2[i].x + h2[i].y; }
-        row_reduce<WPR>(s1, s2, z, bad, red, 0, warp, r, lane);
-        const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
-        float q1 = 0.f, q2 = 0.f;
+        {
+          const float l1 = s1 * (1.0f / (float)(2 * NP)), l2 = s2 * (1.0f / (float)(2 * NP));
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          float d = h1[i].x - m1; q1 = fmaf(d, d, q1);
-          d = h1[i].y - m1; q1 = fmaf(d, d, q1);
-          d = h2[i].x - m2; q2 = fmaf(d, d, q2);
-          d = h2[i].y - m2; q2 = fmaf(d, d, q2);
+          for (int i = 0; i < NP; ++i) {
+            float d = h1[i].x - l1; q1 = fmaf(d, d, q1);
+            d = h1[i].y - l1; q1 = fmaf(d, d, q1);
+            d = h2[i].x - l2; q2 = fmaf(d, d, q2);
+            d = h2[i].y - l2; q2 = fmaf(d, d, q2);
+          }
         }
-        z = 0.f;
-        row_reduce<WPR>(q1, q2, z, bad, red, 1, warp, r, lane);
+        row_stats2<WPR, 2 * NP>(s1, q1, s2, q2, bad, red, 2 * (v & 1), warp, r, lane);
+        const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
         const float r1 = rstd_fast(q1 / (float)HD);
         const float r2 = rstd_fast(q2 / (float)HD);
 #pragma unroll
@@ -1117,7 +1187,7 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
               l2 = fmaf(k2.x, o[i].x, l2); l2 = fmaf(k2.y, o[i].y, l2);
             }
           }
-          row_reduce<WPR>(l0, l1, l2, bad, red, 2, warp, r, lane);
+          row_reduce<WPR>(l0, l1, l2, bad, red, 2 * (v & 1) + 1, warp, r, lane);
           l0 *= 0.0625f; l1 *= 0.0625f; l2 *= 0.0625f;    // 1/sqrt(256)
           float mx = l0;
           if (cnt > 1) mx = fmaxf(mx, l1);
