@@ -786,7 +786,7 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
     std::vector<long long> h((size_t)DEC_MAX_GRID * 16);
     SSV_CUDA(cudaMemcpy(h.data(), d->prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     const char* nm_old[7] = {"loop-top", "arm/arrive+prefetch-issue", "wait", "prologue", "cp.async-wait+sync", "gemv", "tail (sync / bulk-copy issue)"};
-    const char* nm_ws[15] = {"FE loop-top", "FE wait X buffer empty", "FE tap prefetch issue", "FE wait for producer sentinel", "FE row load (tags verified)", "FE ring write + tap prefetch", "FE prologue math + X stores", "MV reducer: wait for the 12 k-slices",
+    const char* nm_ws[15] = {"FE loop-top", "FE wait X buffer empty", "FE tap prefetch issue", "FE wait for producer sentinel", "FE row poll / load (tags verified)", "FE ring write + tap prefetch", "FE prologue math + X stores", "-",
                              "MV wait taps", "MV old taps (2/3)", "MV wait current tap", "MV current tap + k-slice store", "MV reducer: reduce + publish",
                              "sentinel seen -> my sentinel out", "curfull arrive -> MV awake (highway)"};
     const char* const* nm = ws ? nm_ws : nm_old;
@@ -796,8 +796,9 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
       double sum = 0, mx = 0; int cnt = 0;
       for (int c = 0; c < DEC_MAX_GRID; ++c) {
         if (h[(size_t)c * stride + cnt_slot] == 0) continue;
-        double v = (double)h[(size_t)c * stride + i] / (double)h[(size_t)c * stride + cnt_slot];
-        if (ws && i >= 7) v /= 4.0 / d->R;          // mat-vec slots cover all visits, the count is front-end warp 0's share
+        const int cs = (ws && i >= 8) ? 7 : cnt_slot;       // mat-vec slots carry their own visit count
+        if (h[(size_t)c * stride + cs] == 0) continue;
+        const double v = (double)h[(size_t)c * stride + i] / (double)h[(size_t)c * stride + cs];
         sum += v; mx = v > mx ? v : mx; ++cnt;
       }
       fprintf(stderr, "  %-32s %9.0f / %9.0f\n", nm[i], cnt ? sum / cnt : 0.0, mx);

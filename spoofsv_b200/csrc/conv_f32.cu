@@ -8,11 +8,14 @@
 // a CTA owns BM complete rows so the channel LayerNorm and the gate are done in
 // registers before anything is written.
 //
-// Tiling: 256 threads = 64 column-threads x 4 row-groups; thread tile RPT x CPT
-// with columns tx + 64*j (so H1[c] and H2[c] of a highway layer live in the same
-// thread).  K is streamed in chunks of 16 through a cp.async ring (3 stages):
-// the weight chunk is one contiguous KC*N block, the activation chunk is a row
-// gather whose tap shift / zero padding is resolved per row (zero-fill cp.async).
+// Tiling: 256 threads = 64 column-threads x 4 row-groups; thread tile RPT x CPT.
+// Wide layers (CPT % 8 == 0) give a thread 4 consecutive columns per 256-column
+// block (4 tx + 256 j'), so the weight fragment is read with LDS.128 (5.75 shared
+// loads per 112 FMAs instead of 17.75); narrow ones keep columns tx + 64 j.  Either
+// way H1[c] and H2[c] of a highway layer live in the same thread.  K is streamed in chunks of 16 through a cp.async ring (3 stages):
+// the weight chunk is one contiguous KC*N block (one bulk copy, cp.async.bulk ->
+// mbarrier complete_tx), the activation chunk is a row gather whose tap shift /
+// zero padding is resolved per row (zero-fill cp.async arriving on the same mbarrier).
 #include "common.cuh"
 
 namespace ssv {
@@ -57,10 +60,17 @@ __device__ __forceinline__ void rowgroup_sum(float (&v)[CNT], float* red /*[8][C
   __syncthreads();
 }
 
+// column of accumulator j of column-thread tx
+template <int CPT>
+__device__ __forceinline__ int col_of(int tx, int j) {
+  return CPT % 8 == 0 ? 4 * tx + (j & 3) + 256 * (j >> 2) : tx + 64 * j;
+}
+
 template <int BM, int CPT, int STAGES>
 __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
   constexpr int NP = 64 * CPT;
   constexpr int RPT = BM / 4;
+  constexpr bool VEC = CPT % 8 == 0;
   extern __shared__ __align__(16) float smem[];
   float* Ws = smem;                        // [STAGES][KC][NP]
   float* As = smem + STAGES * KC * NP;     // [STAGES][BM][KC]
@@ -85,21 +95,61 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
   const int nchunks = a.ktaps * chunks_per_tap;
   const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
 
-  auto load_stage = [&](int q, int st) {
-    const float4* src = reinterpret_cast<const float4*>(a.W + (size_t)q * KC * NP);
-    float4* dst = reinterpret_cast<float4*>(Ws + st * KC * NP);
+  // One mbarrier per ring stage collects both halves of a chunk: the weight block (KC x NP floats, contiguous) comes
+  // as one bulk copy issued by thread 0 (complete_tx), the activation rows as per-thread zero-fill cp.async whose
+  // completion arrives on the same barrier -- no per-thread address arithmetic for 16 weight copies, no wait_group.
+  __shared__ __align__(8) unsigned long long full[STAGES];
+  if (tid == 0) {
 #pragma unroll
-    for (int i = tid; i < KC * NP / 4; i += NT) cp_async16(dst + i, src + i, true);
+    for (int s = 0; s < STAGES; ++s) {
+      const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&full[s]));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1 + BM * 4));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // loader state of this thread's activation segment: (tap, channel offset) of the next chunk to fetch
+  int ld_j = 0, ld_c0 = 0;
+  const int ld_r = tid >> 2, ld_seg = tid & 3;
+  int ld_b = -1, ld_t = 0;
+  if (tid < BM * 4) { ld_b = row_b[ld_r]; ld_t = row_t[ld_r]; }
+  const float* ld_row = a.X + (long)(ld_b < 0 ? 0 : ld_b) * a.x_sb + ld_seg * 4;
+
+  auto load_stage = [&](int q, int st) {
+    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&full[st]));
+    if (tid == 0) {
+      constexpr unsigned bytes = KC * NP * sizeof(float);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(Ws + st * KC * NP));
+      const float* src = a.W + (size_t)q * KC * NP;
+      constexpr unsigned piece = bytes / 4;        // 4 bulk copies of 2-16 KB
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + i * piece), "l"(reinterpret_cast<const char*>(src) + i * piece), "r"(piece), "r"(bar) : "memory");
+    }
     if (tid < BM * 4) {
-      const int j = q / chunks_per_tap;
-      const int c0 = (q - j * chunks_per_tap) * KC;
-      const int off = (tap_base + j) * a.dil;
-      const int r = tid >> 2, seg = tid & 3;
-      const int b = row_b[r];
-      const int t = row_t[r] + off;
-      const bool ok = (b >= 0) && (t >= 0) && (t < a.t_in);
-      const float* p = ok ? a.X + (long)b * a.x_sb + (long)t * a.x_st + c0 + seg * 4 : a.X;
-      cp_async16(As + (st * BM + r) * KC + seg * 4, p, ok);
+      const int t = ld_t + (tap_base + ld_j) * a.dil;
+      const bool ok = (ld_b >= 0) && (t >= 0) && (t < a.t_in);
+      const float* p = ok ? ld_row + (long)t * a.x_st + ld_c0 : a.X;
+      cp_async16(As + (st * BM + ld_r) * KC + ld_seg * 4, p, ok);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+      ld_c0 += KC;
+      if (ld_c0 == a.cin_p) { ld_c0 = 0; ++ld_j; }
+    }
+  };
+  auto wait_stage = [&](int st, unsigned parity) {
+    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&full[st]));
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
   };
 
@@ -110,21 +160,18 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
     for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
 
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
+  for (int s = 0; s < STAGES - 1; ++s)
     if (s < nchunks) load_stage(s, s);
-    cp_async_commit();
-  }
 
   for (int q = 0; q < nchunks; ++q) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
+    wait_stage(q % STAGES, (unsigned)(q / STAGES) & 1u);
+    __syncthreads();                       // every warp is done with chunk q - 1: its stage may be refilled
     {
       const int qn = q + STAGES - 1;
       if (qn < nchunks) load_stage(qn, qn % STAGES);
-      cp_async_commit();
     }
     const int st = q % STAGES;
-    const float* Wst = Ws + st * KC * NP + tx;
+    const float* Wst = Ws + st * KC * NP + (VEC ? 4 * tx : tx);
     const float* Ast = As + (st * BM + ty * RPT) * KC;
     // two of the four k-quads per trip: the fully unrolled 16-k body (38 KB of SASS) missed the instruction cache
     // (ncu: stall_no_instruction 0.24 per issue); measured TextEnc 4.78 -> 4.34 ms, SSRN fp32 19.8 -> 17.9 ms
@@ -136,8 +183,16 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
 #pragma unroll
       for (int kq = 0; kq < 4; ++kq) {
         float w[CPT];
+        if constexpr (VEC) {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) w[j] = Wst[(k4 * 4 + kq) * NP + 64 * j];
+          for (int j = 0; j < CPT / 4; ++j) {
+            const float4 wv = *reinterpret_cast<const float4*>(Wst + (k4 * 4 + kq) * NP + 256 * j);
+            w[4 * j] = wv.x; w[4 * j + 1] = wv.y; w[4 * j + 2] = wv.z; w[4 * j + 3] = wv.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) w[j] = Wst[(k4 * 4 + kq) * NP + 64 * j];
+        }
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const float x = kq == 0 ? av[i].x : kq == 1 ? av[i].y : kq == 2 ? av[i].z : av[i].w;
@@ -147,12 +202,11 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
       }
     }
   }
-  cp_async_wait<0>();
 
   // ---------------- epilogue ----------------
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
-    const float bv = a.bias[tx + 64 * j];
+    const float bv = a.bias[col_of<CPT>(tx, j)];
 #pragma unroll
     for (int i = 0; i < RPT; ++i) acc[i][j] += bv;
   }
@@ -162,7 +216,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
       const int b = row_b[ty * RPT + i];
       if (b >= 0) {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[i][j] += a.bias_b[(long)b * a.bias_b_ld + tx + 64 * j];
+        for (int j = 0; j < CPT; ++j) acc[i][j] += a.bias_b[(long)b * a.bias_b_ld + col_of<CPT>(tx, j)];
       }
     }
   }
@@ -175,7 +229,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
       float* y = a.Y + (long)b * a.y_sb + (long)row_t[ty * RPT + i] * a.y_st;
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
-        const int c = tx + 64 * j;
+        const int c = col_of<CPT>(tx, j);
         if (c < a.y_cols) y[c] = c < a.n ? acc[i][j] : 0.f;
       }
     }
@@ -220,7 +274,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
         float* y = a.Y + (long)b * a.y_sb + (long)t * a.y_st;
 #pragma unroll
         for (int j = 0; j < H; ++j) {
-          const int c = tx + 64 * j;
+          const int c = col_of<CPT>(tx, j);
           const float h1 = (acc[i][j] - mean[2 * i]) * r1 * a.g1[c] + a.b1[c];
           const float h2 = (acc[i][j + H] - mean[2 * i + 1]) * r2 * a.g2[c] + a.b2[c];
           const float g = sigmoidf_(h1);
@@ -239,7 +293,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
     for (int i = 0; i < RPT; ++i) {
       float v = 0.f;
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) v += (tx + 64 * j < a.n) ? acc[i][j] : 0.f;
+      for (int j = 0; j < CPT; ++j) v += (col_of<CPT>(tx, j) < a.n) ? acc[i][j] : 0.f;
       s[i] = v;
     }
     rowgroup_sum<RPT>(s, red, tid);
@@ -252,7 +306,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const float d = acc[i][j] - mean[i];
-        v += (tx + 64 * j < a.n) ? d * d : 0.f;
+        v += (col_of<CPT>(tx, j) < a.n) ? d * d : 0.f;
       }
       s[i] = v;
     }
@@ -265,7 +319,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
       float* y = a.Y + (long)b * a.y_sb + (long)row_t[ty * RPT + i] * a.y_st;
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
-        const int c = tx + 64 * j;
+        const int c = col_of<CPT>(tx, j);
         if (c >= a.y_cols) continue;
         float o = 0.f;
         if (c < a.n) {

@@ -347,6 +347,7 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
   if (prof_on) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) p.prof[(size_t)blockIdx.x * 16 + 8 + i] = prof_acc[i];
+    p.prof[(size_t)blockIdx.x * 16 + 7] = v > 0 ? v : 1;       // mat-vec visit count (the front end's is slot 15)
     p.prof[(size_t)blockIdx.x * 16 + 13] = lat_acc;
     p.prof[(size_t)blockIdx.x * 16 + 14] = wake_acc;
   }
