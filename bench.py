@@ -74,30 +74,75 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 500 ms while the timed region runs."""
+    """SM clock / throttle reasons sampled every 100 ms while the timed region runs.
+
+    In-process NVML (nvidia_ml_py): a query is a few microseconds of driver work.  A looping `nvidia-smi` child
+    (the fallback when NVML cannot be imported) stalled kernel launches for ~160 ms whenever a sample fell into a
+    step, which showed up as one 180 ms step among 17 ms ones."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, uuid: str | None = None):
+        self.index, self.uuid, self.rows, self.proc = index, uuid, [], None
+        self.nvml, self.handle, self.stop = None, None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            self.handle = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = [(n.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                (n.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+        while not self.stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append([sm, self.max_sm, [name for bit, name in bits if mask & bit]])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            c = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append([float(c[0]), float(c[1]),
+                                  [n for n, v in zip(self.NAMES, c[3:7]) if v.lower().startswith("active")]])
+            except (ValueError, IndexError):
+                continue
 
     def __enter__(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
@@ -106,19 +151,12 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+        sm = [r[0] for r in self.rows]
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted({n for r in self.rows for n in r[2]})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(r[1] for r in self.rows), "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def workload(batch: int, rank: int):
@@ -247,6 +285,12 @@ def main():
         e[3].record()
         return e, lin
 
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid)          # NVML is initialised here, outside the timed region
+
     # ---- warm-up (also builds the native handles and the decoder)
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
@@ -258,7 +302,7 @@ def main():
     barrier()
     lib.ssv_launch_count(1)
     step_ms, parts = [], []
-    with ClockSampler(local) as clk:
+    with sampler as clk:
         for _ in range(args.steps):
             flush.fill_(1)
             e, lin = device_step()

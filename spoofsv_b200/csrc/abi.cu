@@ -288,7 +288,7 @@ struct ssv_decoder {
   unsigned long long* ws_raw = nullptr;
   int* ws_sent = nullptr;
   float* ws_hist = nullptr;
-  int seq_base = 0, R = 1, G = 1;
+  int seq_base = 0, R = 1, G = 1, W = 4;
   // per-batch state
   bool begun = false;
   int B = 0, N = 0, t_cap = 0, t = 0;
@@ -677,7 +677,7 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
   if (d->impl == DEC_IMPL_WS) {
     const size_t bp = (size_t)round_up(max_batch, 4);
     const size_t raw_words = (size_t)DEC_STAGES * max_batch * WS_WORDS;
-    const size_t sent_ints = (size_t)DEC_STAGES * max_batch * WS_MAX_PARTS;
+    const size_t sent_ints = (size_t)DEC_STAGES * bp * WS_MAX_PARTS;      // micro-batch count may be padded by up to 3
     if (st == kOk) st = d->arena.alloc<unsigned long long>(raw_words, &d->ws_raw);
     if (st == kOk) st = d->arena.alloc<int>(sent_ints, &d->ws_sent);
     if (st == kOk) st = d->arena.alloc<float>((size_t)m->ws_hist_blocks * bp * H, &d->ws_hist);
@@ -729,19 +729,10 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
     d->seq_base += d->t_cap + 2;
     if (d->seq_base > (1 << 30)) {
       SSV_CUDA(cudaMemsetAsync(d->ws_raw, 0, (size_t)DEC_STAGES * d->maxB * WS_WORDS * sizeof(unsigned long long), s));
-      SSV_CUDA(cudaMemsetAsync(d->ws_sent, 0, (size_t)DEC_STAGES * d->maxB * WS_MAX_PARTS * sizeof(int), s));
+      SSV_CUDA(cudaMemsetAsync(d->ws_sent, 0, (size_t)DEC_STAGES * round_up(d->maxB, 4) * WS_MAX_PARTS * sizeof(int), s));
       d->seq_base = 0;
     }
-    // rows per micro-batch (measured on B200, us/frame).  Up to 16 micro-batches the
-    // cooperative front end (the warps of a row split its channels) wins: B <= 16 R=1 31-36, B <= 32 R=2 42.
-    // Past that one warp per row with 4 / R micro-batches in flight: B=40 R=1 49 (R=2 51); B=64 R=2 56 (R=1 74,
-    // R=4 61); B=128 R=2 108 (R=4 111); B=256 R=4 225.
-    d->R = B <= 16 ? 1 : B <= 32 ? 2 : B <= 40 ? 1 : (B <= 128 ? 2 : 4);
-    if (const char* e = getenv("SSV_DECODE_R")) {          // development knob
-      const int r = atoi(e);
-      if (r == 1 || r == 2 || r == 4) d->R = r;
-    }
-    d->G = (B + d->R - 1) / d->R;
+    ws_plan(B, &d->R, &d->W, &d->G);
   }
   d->B = B; d->N = N; d->t_cap = t_cap; d->t = 0;
   d->Y = Y; d->A = A; d->traj = reinterpret_cast<long long*>(pma_traj);
@@ -774,7 +765,7 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.prof = d->prof;
   p.ws_stages = m->ws_stages_dev;
   p.ws_raw = d->ws_raw; p.ws_sent = d->ws_sent; p.ws_hist = d->ws_hist;
-  p.seq_base = d->seq_base; p.R = d->R; p.G = d->G;
+  p.seq_base = d->seq_base; p.R = d->R; p.G = d->G; p.W = d->W;
   const int sms = device_sm_count();
   SSV_CHECK(sms > 0, "decoder: no CUDA device");
   if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 16, s));
@@ -790,7 +781,7 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
                              "MV wait taps", "MV old taps (2/3)", "MV wait current tap", "MV current tap + k-slice store", "MV reducer: reduce + publish",
                              "sentinel seen -> my sentinel out", "curfull arrive -> MV awake (highway)"};
     const char* const* nm = ws ? nm_ws : nm_old;
-    fprintf(stderr, "[decode prof] impl=%d B=%d R=%d steps=%d (cycles per stage visit: mean / max over CTAs)\n", d->impl, d->B, d->R, n_steps);
+    fprintf(stderr, "[decode prof] impl=%d B=%d R=%d W=%d G=%d steps=%d (cycles per stage visit: mean / max over CTAs)\n", d->impl, d->B, d->R, d->W, d->G, n_steps);
     for (int i = 0; i < n_ph; ++i) {
       if (nm[i][0] == '-') continue;
       double sum = 0, mx = 0; int cnt = 0;

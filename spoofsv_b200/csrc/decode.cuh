@@ -86,7 +86,7 @@ struct DecParams {
   int* ws_sent;                 // [DEC_STAGES][G][WS_MAX_PARTS] sentinel tags
   float* ws_hist;               // private input-history rings, [blocks][G][256][R]
   int seq_base;                 // tag of frame t is seq_base + t + 1 (advanced by every begin())
-  int R, G;                     // rows per micro-batch (1, 2, 4), micro-batches
+  int R, G, W;                  // rows per micro-batch (1, 2, 4), micro-batches, front-end warps per row (1, 2, 4)
   int ws_flags;                 // WS_FLAG_* (set by launch_decode_ws)
 };
 
@@ -95,6 +95,7 @@ int launch_decode_cluster(const DecParams& p, cudaStream_t s);     // decode_clu
 int decode_cluster_capacity();
 int launch_decode_ws(const DecParams& p, cudaStream_t s);          // decode_ws.cu
 bool decode_ws_supported(int sm_count);
+void ws_plan(int B, int* R, int* W, int* G);                      // front-end shape for a batch
 void ws_stage_layout(const DecStage& d, WsStage* w);
 size_t ws_image_floats(const WsStage& w);
 int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStream_t s);

@@ -16,21 +16,28 @@
 // a software pipeline over (frame, micro-batch): up to 24 micro-batches are in flight, HBM/L2 see only
 // activations, and there is no grid-wide barrier anywhere.
 //
-// Inside a CTA the work is warp-specialised.  Warps 0-3 are the front end: they prefetch the taps t-2d, t-d
-// from the CTA's private history ring, wait for the producer stage, redo the cheap LayerNorm / highway gate /
-// windowed attention of the input row (redundantly per consumer CTA, as decode.cu does), and fill one of two
-// X buffers.  Warps 4-15 hold the weights and do the mat-vec: the two OLD taps (2/3 of a highway layer's
-// work) do not depend on the producer stage and run while the front end is still waiting for it; only the
-// current tap sits on the frame's critical path.  The two halves hand X buffers back and forth through
-// mbarriers, so with enough micro-batches the wait for stage s-1 overlaps the mat-vec of the previous one.
+// Inside a CTA the work is warp-specialised.  Warps 0-3 are the front end: they fetch the taps t-2d, t-d from the
+// CTA's private history ring, wait for the producer stage, redo the cheap LayerNorm / highway gate / windowed
+// attention of the input row (redundantly per consumer CTA, as decode.cu does), and fill an X buffer.  How the
+// four warps are dealt is a launch-time shape (ws_plan): W warps share one row (each owns 256 / W channels, the
+// LayerNorm sums cross warps through shared memory and a named barrier), R rows make a micro-batch, and
+// 4 / (R W) micro-batches are in the front end at a time.  Few utterances: W = 4 or 2, the dependent chain of a
+// stage is 2-4 channels per lane; many: W = 1 and two micro-batches in flight, so that the wait for one producer
+// hides behind the prologue of the other.  A warp only ever reads history it wrote itself (its channel slice of
+// its visit slot), so the taps need no cross-warp synchronisation.
+// Warps 4-15 hold the weights and do the mat-vec: the two OLD taps (2/3 of a highway layer's work) do not depend
+// on the producer stage and run while the front end is still waiting for it; only the current tap sits on the
+// frame's critical path.  The two halves hand X buffers back and forth through mbarriers.
 //
 // Cross-CTA hand-off: every value a CTA publishes is an 8-byte word {float value, int tag} written with one
-// 64-bit store (single-copy atomic); tag = seq_base + frame + 1.  A consumer first polls one sentinel word
-// per producer CTA (cheap: 32 B per round), then loads the row and checks every tag, re-loading until all
-// match -- so no fences and no release/acquire chains sit on the critical path, and a word that has not
-// landed yet can never be mistaken for data.  Everything else a CTA touches is private to it (weights,
-// LayerNorm parameters, its own ring of past stage inputs), so the tagged words are the only cross-CTA
-// traffic.
+// 64-bit store (single-copy atomic); tag = seq_base + frame + 1.  A consumer polls the tagged words of its own
+// row slice directly -- it loads them, checks every tag and re-loads until all match -- so there is exactly one
+// L2 round trip between "the producer's store landed" and "the consumer has the data", no fences and no
+// release/acquire chain on the critical path, and a word that has not landed yet can never be mistaken for data.
+// (Polling a per-CTA sentinel first and loading the row afterwards costs a second dependent round trip per stage:
+// 43 vs 31 us/frame at B = 1; SSV_WS_POLL=sentinel keeps that mode for A/B runs.)  Everything else a CTA touches
+// is private to it (weights, LayerNorm parameters, its own ring of past stage inputs), so the tagged words are
+// the only cross-CTA traffic.
 #include "decode.cuh"
 
 #include <cstdlib>
@@ -226,7 +233,6 @@ struct Ctx {                 // per-CTA constants shared by both roles
   uint64_t* pfree;           // [2] the reducer warp(s) are done with the partial-sum buffer
   uint64_t* rdone;           // [2] second reducer warp has published its half (wide tiles)
   int* s_bad;
-  volatile int* fe_done;      // [4] progress counters of the front-end warps
   volatile long long* t_seen;   // profiling, [2][8]: SM clock at which the front end saw the producer's sentinel / handed X over
 };
 
@@ -355,471 +361,22 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Front-end role (warps 0-3): taps, wait for the producer stage, prologue -> X buffer.
-template <int RT, bool PROF>
-__device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st, const Ctx& c, int tid) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int s = c.s, part = c.part, G = c.G, B = c.B;
-  const bool designated = part == 0;
-  const float* lnp = c.smem + SM_LN;
-  const float* g1 = lnp;
-  const float* b1 = lnp + HD;
-  const float* g2 = lnp + 2 * HD;
-  const float* b2 = lnp + 3 * HD;
-  int* pma_s = reinterpret_cast<int*>(c.smem + SM_PMA);
-  const Word* raw_in = reinterpret_cast<const Word*>(p.ws_raw) + (size_t)c.prev * B * WS_WORDS;
-  Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)s * B * WS_WORDS;
-  const int koff = st.hwy ? 2 * TAPP : 0;                   // X row of the current tap
-  const int n_visits = p.n_steps + (s == 0 ? 1 : 0);        // stage 0 also finishes the last frame (y = sigmoid(LN5))
-
-  long long prof_last = 0, prof_acc[7] = {0, 0, 0, 0, 0, 0, 0};
-  const bool prof_on = PROF && p.prof != nullptr && tid == 0;
-  if (prof_on) prof_last = clock64();
-#define PROF_F(i)                                  \
-  if (prof_on) {                                   \
-    const long long now_ = clock64();              \
-    prof_acc[i] += now_ - prof_last;               \
-    prof_last = now_;                              \
-  }
-
-  // One warp per row; 4 / RT micro-batches are in flight in the front end (warp w: visit slot w / RT, row w % RT),
-  // so the wait for one producer overlaps the prologue of another micro-batch.
-  constexpr int NV = 4 / RT;
-  constexpr int NBUF = MAXBUF / RT;
-  constexpr int NREC = 3 * NBUF;           // a visit slot runs at most NBUF visits ahead of the slowest one
-  float* rec = c.smem + SM_REC;
-  volatile int* fe_done = c.fe_done;       // [4] visits completed by each front-end warp
-  const int vs = warp / RT, r = warp % RT;
-  const int total_visits = n_visits * G;
-  int my_visits = 0;
-  int step = 0, g = vs;                    // (frame, micro-batch) of visit v, advanced incrementally
-  while (g >= G) { g -= G; ++step; }
-  float tp[2][8];                          // my row of the two old taps (global-ring ones are prefetched a visit ahead)
-  bool have_pref = false;
-  for (int v = vs; v < total_visits; v += NV, ++my_visits, g += NV) {
-    while (g >= G) { g -= G; ++step; }
-    const int t = p.t_start + step;
-    const bool final_visit = s == 0 && step == p.n_steps;
-    const int tag = p.seq_base + t + 1;                     // tag of everything produced for frame t
-    const int tag_in = s == 0 ? tag - 1 : tag;              // stage 0 consumes frame t-1 of stage 23
-    const bool need_wait = !(s == 0 && step == 0);
-    const int q = v % NBUF;
-    const int u = v / NBUF;
-    float* X = c.smem + SM_X + q * (XROWS * RT);
-    const int row0 = g * RT;
-    const int nrows = min(RT, B - row0);
-    bool bad = false;
-    {
-      PROF_F(0);
-
-      // ---- 1. my row of the old taps t-2d, t-d -> X rows [0, 256) and [264, 520).  A tap that one of the last
-      //         NBUF + NV visits produced is still in the CTA's recent-row ring (shared memory; the warp that wrote
-      //         it publishes its progress in fe_done).  Older ones come from my private ring in global memory: their
-      //         writes precede my previous visit's "empty" wait through the curfull -> mat-vec -> empty barrier chain
-      //         (a row is overwritten in the recent ring only by a visit 3 NBUF later, which cannot start before this
-      //         visit has been consumed).
-      if (st.ntaps == 3) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int back = (2 - j) * st.dil;                 // frames back
-          const int tt = t - back;
-          const int dist = back * G;                         // visits back
-          if (tt < 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tp[j][i] = 0.f;
-          } else if (tt >= p.t_start && dist < NBUF + NV) {
-            const int d = v - dist;
-            const int dw = (d % NV) * RT + r;                // the warp that produced row r of visit d
-            const int need = d / NV + 1;
-            unsigned spins = 0;
-            while (fe_done[dw] < need) {          // sleep between looks: a spinning warp steals issue slots from the mat-vec warps
-              __nanosleep(100);
-              if ((++spins & 1023u) == 0 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) { bad = true; break; }
-            }
-            __threadfence_block();
-            const float* src = rec + ((size_t)(d % NREC) * RT + r) * HD;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tp[j][i] = src[lane + 32 * i];
-          } else if (!have_pref) {
-            const int slot = tt % st.hist_depth;
-            const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT) + r;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tp[j][i] = __ldcg(src + (size_t)(lane + 32 * i) * RT);
-          }                                                  // else: prefetched at the end of my previous visit
-        }
-        if (u >= 1) {
-          if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) X[((size_t)j * TAPP + lane + 32 * i) * RT + r] = tp[j][i];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&c.tapsfull[q]);
-      } else if (!final_visit && u >= 1) {
-        if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
-      }
-      PROF_F(2);
-
-      // ---- 1b. attention stage: the K / V rows of this utterance's 3-character window are known as soon as the
-      //          previous frame of the micro-batch has updated pma -- fetch them (cp.async -> shared memory) under the
-      //          wait for the producer instead of after it (two dependent L2 round trips off the critical path)
-      bool kv_pref = false;
-      float* kvs = c.smem + SM_KV + warp * (6 * HD);
-      if (st.pro == PRO_ATT && r < nrows) {
-        const int d = v - G;                                 // the visit that wrote pma of this row last
-        bool ready = d < 0;
-        if (!ready && G < NBUF + NV) ready = fe_done[(d % NV) * RT + r] >= d / NV + 1;
-        else if (!ready) ready = true;                       // at least NBUF + NV visits back: consumed long ago
-        if (ready) {
-          __threadfence_block();
-          const int bq = row0 + r;
-          const int p0 = pma_s[bq];
-          const int cnt = min(p0 + 2, p.N - 1) - p0 + 1;
-          const float* kp = p.Kt + ((size_t)bq * p.N + p0) * HD;
-          const float* vp = p.Vt + ((size_t)bq * p.N + p0) * HD;
-          for (int i = lane; i < cnt * (HD / 4); i += 32) {
-            cp_async16(kvs + i * 4, kp + i * 4, true);
-            cp_async16(kvs + 3 * HD + i * 4, vp + i * 4, true);
-          }
-          asm volatile("cp.async.commit_group;\n" ::: "memory");
-          kv_pref = true;
-        }
-      }
-
-      // ---- 2./3. wait for the producers of my input row, then the prologue: u_t -> X[koff ..][r]
-      {
-        const int b = row0 + r;
-        float* xcur = X + (size_t)koff * RT + r;             // channel ch at xcur[ch * RT]
-        if (r >= nrows) {
-          if (!final_visit)
-            for (int ch = lane; ch < st.k_seg; ch += 32) xcur[(size_t)ch * RT] = 0.f;
-        } else {
-          long long t0 = 0;
-          unsigned spins = 0;
-          auto spin_check = [&]() {        // bounded spinning: flag the abort and leave
-            if ((++spins & 255u) == 0) {
-              if (t0 == 0) t0 = clock64();
-              else if (clock64() - t0 > SPIN_LIMIT) atomicExch(p.abort_flag, 8);
-              if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) bad = true;
-            }
-          };
-          if (need_wait && !(p.ws_flags & WS_FLAG_ROWPOLL)) {
-            const int* sp = p.ws_sent + ((size_t)c.prev * G + g) * WS_MAX_PARTS;
-            for (;;) {
-              const int sv = lane < c.prev_parts ? ld_relaxed_s32(sp + lane) : tag_in;
-              if (__all_sync(FULL, sv - tag_in >= 0)) break;
-              spin_check();
-              if (__any_sync(FULL, bad)) { bad = true; break; }
-            }
-          }
-          PROF_F(3);
-          if (PROF && p.prof != nullptr && r == 0 && lane == 0) c.t_seen[q] = clock64();
-          const Word* R = raw_in + (size_t)b * WS_WORDS;
-          const int pro = st.pro;
-          if (pro == PRO_X) {
-            float y[3];
-            if (!need_wait) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const int f = lane + 32 * i;
-                float xv = 0.f;
-                if (f < p.F) {
-                  if (p.x_ext) xv = p.x_ext[(long)b * p.x_sb + (long)f * p.x_sf];
-                  else if (t > 0) xv = __ldcg(p.Y + ((size_t)b * p.F + f) * p.t_cap + (t - 1));
-                }
-                y[i] = xv;
-              }
-            } else {
-              float vv[3] = {0.f, 0.f, 0.f};
-              while (!bad) {
-                bool ok = true;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                  const int f = lane + 32 * i;
-                  vv[i] = 0.f;
-                  if (f < p.F) { int tg; ld_word(R + f, vv[i], tg); ok &= tg == tag_in; }
-                }
-                if (__all_sync(FULL, ok)) break;
-                spin_check();
-                if (__any_sync(FULL, bad)) bad = true;
-              }
-              float sm = vv[0] + vv[1] + vv[2];
-              sm = warp_sum(sm);
-              const float mean = sm / (float)p.F;
-              float qq = 0.f;
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const float d = vv[i] - mean;
-                qq += lane + 32 * i < p.F ? d * d : 0.f;
-              }
-              qq = warp_sum(qq);
-              const float rstd = 1.0f / sqrtf(qq / (float)p.F + 1e-5f);
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const int f = lane + 32 * i;
-                y[i] = f < p.F ? sigmoidf_((vv[i] - mean) * rstd * g1[f] + b1[f]) : 0.f;
-                if (f < p.F && !bad && designated) p.Y[((size_t)b * p.F + f) * p.t_cap + (t - 1)] = y[i];
-              }
-            }
-            if (!final_visit) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const int f = lane + 32 * i;
-                if (f < p.F) xcur[(size_t)f * RT] = y[i];
-              }
-            }
-          } else if (pro == PRO_LN || pro == PRO_LN_RELU) {
-            float vv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            while (!bad) {
-              bool ok = true;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                int ta, tb;
-                ld_word2(R + 2 * lane + 64 * i, vv[2 * i], ta, vv[2 * i + 1], tb);
-                ok &= ta == tag_in && tb == tag_in;
-              }
-              if (__all_sync(FULL, ok)) break;
-              spin_check();
-              if (__any_sync(FULL, bad)) bad = true;
-            }
-            if (PROF && prof_on) PROF_F(4);
-            float sum = 0.f, qq = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sum += vv[i];
-            {
-              const float lm = sum * 0.125f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { const float d = vv[i] - lm; qq = fmaf(d, d, qq); }
-            }
-            warp_stats1<8>(sum, qq);
-            const float mean = sum / (float)HD;
-            const float rstd = rstd_fast(qq / (float)HD);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int ch = 2 * lane + 64 * (i >> 1) + (i & 1);
-              float o = (vv[i] - mean) * rstd * g1[ch] + b1[ch];
-              if (pro == PRO_LN_RELU) o = fmaxf(o, 0.f);
-              vv[i] = o;
-              xcur[(size_t)ch * RT] = o;
-            }
-            if (st.hwy && (lane >> 4) == (part & 1)) {       // my residual slice travels with my outputs
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i == (part >> 1))
-                  st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + 2 * lane + 64 * i, vv[2 * i], vv[2 * i + 1], tag);
-            }
-          } else {   // PRO_HWY / PRO_ATT: the producer is a highway layer: H1 | H2 | its input (my residual)
-            float h1[8] = {}, h2[8] = {}, xr[8] = {};
-            while (!bad) {
-              bool ok = true;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                int ta, tb;
-                const Word* wp = R + 2 * lane + 64 * i;
-                ld_word2(wp, h1[2 * i], ta, h1[2 * i + 1], tb);
-                ok &= ta == tag_in && tb == tag_in;
-                ld_word2(wp + HD, h2[2 * i], ta, h2[2 * i + 1], tb);
-                ok &= ta == tag_in && tb == tag_in;
-                ld_word2(wp + 2 * HD, xr[2 * i], ta, xr[2 * i + 1], tb);
-                ok &= ta == tag_in && tb == tag_in;
-              }
-              if (__all_sync(FULL, ok)) break;
-              spin_check();
-              if (__any_sync(FULL, bad)) bad = true;
-            }
-            if (PROF && prof_on) PROF_F(4);
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { s1 += h1[i]; s2 += h2[i]; }
-            float q1 = 0.f, q2 = 0.f;
-            {
-              const float l1 = s1 * 0.125f, l2 = s2 * 0.125f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float d1 = h1[i] - l1, d2 = h2[i] - l2;
-                q1 = fmaf(d1, d1, q1);
-                q2 = fmaf(d2, d2, q2);
-              }
-            }
-            warp_stats2<8>(s1, q1, s2, q2);
-            const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
-            const float r1 = rstd_fast(q1 / (float)HD);
-            const float r2 = rstd_fast(q2 / (float)HD);
-            float uu[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int ch = 2 * lane + 64 * (i >> 1) + (i & 1);
-              const float a = (h1[i] - m1) * r1 * g1[ch] + b1[ch];
-              const float bb = (h2[i] - m2) * r2 * g2[ch] + b2[ch];
-              const float gt = sigmoid_fast(a);
-              uu[i] = gt * bb + (1.0f - gt) * xr[i];
-            }
-            if (pro == PRO_HWY) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) xcur[(size_t)(2 * lane + 64 * (i >> 1) + (i & 1)) * RT] = uu[i];
-              if (st.hwy && (lane >> 4) == (part & 1)) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (i == (part >> 1))
-                    st_word2(raw_out + (size_t)b * WS_WORDS + 2 * HD + 2 * lane + 64 * i, uu[2 * i], uu[2 * i + 1], tag);
-              }
-            } else {
-              // windowed attention, models/TTSModel.py:281-295: logits over [pma, min(pma+2, N-1)];
-              // every other character is masked to -2^32 and gets softmax weight exactly 0.
-              const int p0 = pma_s[b];
-              const int cnt = min(p0 + 2, p.N - 1) - p0 + 1;
-              const float* kp = p.Kt + ((size_t)b * p.N + p0) * HD;
-              const float* vp = p.Vt + ((size_t)b * p.N + p0) * HD;
-              if (kv_pref) {                                  // window rows already in shared memory
-                asm volatile("cp.async.wait_all;\n" ::: "memory");
-                __syncwarp();
-                kp = kvs;
-                vp = kvs + 3 * HD;
-              }
-              float l0 = 0.f, l1 = 0.f, l2 = 0.f;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int ch = 2 * lane + 64 * i;
-                const float2 k0 = *reinterpret_cast<const float2*>(kp + ch);
-                l0 = fmaf(k0.x, uu[2 * i], l0); l0 = fmaf(k0.y, uu[2 * i + 1], l0);
-                if (cnt > 1) {
-                  const float2 k1 = *reinterpret_cast<const float2*>(kp + HD + ch);
-                  l1 = fmaf(k1.x, uu[2 * i], l1); l1 = fmaf(k1.y, uu[2 * i + 1], l1);
-                }
-                if (cnt > 2) {
-                  const float2 k2 = *reinterpret_cast<const float2*>(kp + 2 * HD + ch);
-                  l2 = fmaf(k2.x, uu[2 * i], l2); l2 = fmaf(k2.y, uu[2 * i + 1], l2);
-                }
-              }
-              warp_sum2(l0, l1);
-              l2 = warp_sum(l2);
-              l0 *= 0.0625f; l1 *= 0.0625f; l2 *= 0.0625f;    // 1/sqrt(256)
-              float mx = l0;
-              if (cnt > 1) mx = fmaxf(mx, l1);
-              if (cnt > 2) mx = fmaxf(mx, l2);
-              const float e0 = expf(l0 - mx);
-              const float e1 = cnt > 1 ? expf(l1 - mx) : 0.f;
-              const float e2 = cnt > 2 ? expf(l2 - mx) : 0.f;
-              const float den = e0 + e1 + e2;
-              const float a0 = e0 / den, a1 = e1 / den, a2 = e2 / den;
-              int best = 0;
-              float bv = a0;
-              if (cnt > 1 && a1 > bv) { best = 1; bv = a1; }
-              if (cnt > 2 && a2 > bv) { best = 2; bv = a2; }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int ch = 2 * lane + 64 * i;
-                const float2 v0 = *reinterpret_cast<const float2*>(vp + ch);
-                float rx = a0 * v0.x, ry = a0 * v0.y;
-                if (cnt > 1) {
-                  const float2 v1 = *reinterpret_cast<const float2*>(vp + HD + ch);
-                  rx = fmaf(a1, v1.x, rx); ry = fmaf(a1, v1.y, ry);
-                }
-                if (cnt > 2) {
-                  const float2 v2 = *reinterpret_cast<const float2*>(vp + 2 * HD + ch);
-                  rx = fmaf(a2, v2.x, rx); ry = fmaf(a2, v2.y, ry);
-                }
-                xcur[(size_t)ch * RT] = rx;                    // R
-                xcur[(size_t)(ch + 1) * RT] = ry;
-                xcur[(size_t)(HD + ch) * RT] = uu[2 * i];      // Q
-                xcur[(size_t)(HD + ch + 1) * RT] = uu[2 * i + 1];
-              }
-              if (lane == 0 && !bad) {
-                pma_s[b] = p0 + best;
-                if (designated) {
-                  float* Ab = p.A + ((size_t)b * p.N + p0) * p.t_cap + t;
-                  Ab[0] = a0;
-                  if (cnt > 1) Ab[p.t_cap] = a1;
-                  if (cnt > 2) Ab[2 * (size_t)p.t_cap] = a2;
-                  p.pma_traj[(size_t)t * B + b] = p0 + best;
-                  p.pma_state[b] = p0 + best;
-                }
-              }
-            }
-          }
-        }
-      }
-      if (final_visit) continue;                 // stage 0 after the last frame: prologue only
-      PROF_F(6);
-      __syncwarp();                              // my row of the micro-batch is in X
-      // ---- 4. my stage input of frame t joins the recent-row ring and my private ring (taps of later frames)
-      if (st.ntaps == 3) {
-        const int slot = t % st.hist_depth;
-        float* dst = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * (HD * RT) + r;
-        float* rdst = rec + ((size_t)(v % NREC) * RT + r) * HD;
-        const float* xcur = X + (size_t)koff * RT + r;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ch = lane + 32 * i;
-          const float xv = xcur[(size_t)ch * RT];
-          rdst[ch] = xv;
-          __stcg(dst + (size_t)ch * RT, xv);
-        }
-        __syncwarp();
-      }
-      if (lane == 0) {
-        mbar_arrive(&c.curfull[q]);              // release: X row, recent row and ring stores precede it
-        if (PROF && p.prof != nullptr && r == 0) c.t_seen[8 + q] = clock64();
-        __threadfence_block();
-        fe_done[warp] = my_visits + 1;
-      }
-      if (__any_sync(FULL, bad)) return;         // aborted launch: the mat-vec warps leave through their own bounded waits
-      // ---- 5. global-ring taps of my next visit: issue the loads now, they land while I wait for its producer.
-      //         (Rows at least NBUF + NV visits old: written before the "empty" wait this visit has passed.)
-      have_pref = false;
-      if (st.ntaps == 3 && v + NV < total_visits) {
-        int step2 = step, g2 = g + NV;
-        while (g2 >= G) { g2 -= G; ++step2; }
-        const int t2 = p.t_start + step2;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int back = (2 - j) * st.dil;
-          const int tt = t2 - back;
-          const int dist = back * G;
-          if (tt >= 0 && !(tt >= p.t_start && dist < NBUF + NV)) {
-            const int slot = tt % st.hist_depth;
-            const float* src = p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g2) * (HD * RT) + r;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tp[j][i] = __ldcg(src + (size_t)(lane + 32 * i) * RT);
-          }
-        }
-        have_pref = true;
-      }
-      if ((my_visits & 15) == 15) {               // a launch aborted elsewhere: leave
-        int ab = 0;
-        if (lane == 0) ab = *reinterpret_cast<volatile int*>(p.abort_flag);
-        if (__shfl_sync(FULL, ab, 0) != 0) return;
-      }
-      PROF_F(5);
-    }
-  }
-  if (prof_on) {
-#pragma unroll
-    for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 16 + i] = prof_acc[i];
-    p.prof[(size_t)blockIdx.x * 16 + 15] = my_visits > 0 ? my_visits : 1;
-  }
-#undef PROF_F
-}
-
-
-// ------------------------------------------------------------------------------------------------------
 // Cooperative front end (warps 0-3): the 4 / RT warps of a row split its 256 channels, so the dependent chain of
 // one stage -- tagged-word loads, two LayerNorm reductions, gate, X stores -- is 2 * RT channels per lane instead
 // of 8.  One micro-batch is in the front end at a time; a warp reads only taps that it wrote itself (its channel
 // slice), so the taps need no cross-warp synchronisation at all.
 template <int WPR>
-__device__ __forceinline__ void row_reduce(float& a, float& b, float& c3, bool& bad, float* red, int round, int warp, int r, int lane) {
+__device__ __forceinline__ void row_reduce(float& a, float& b, float& c3, bool& bad, float* red, int round, int warp, int wbase, int barid, int lane) {
   warp_sum2(a, b);
   c3 = warp_sum(c3);
   if (WPR > 1) {
     float4* slot = reinterpret_cast<float4*>(red) + round * 8;
     if (lane == 0) slot[2 * warp] = make_float4(a, b, c3, bad ? 1.f : 0.f);
-    named_bar(2 + r, WPR * 32);
+    named_bar(barid, WPR * 32);
     float sa = 0.f, sb = 0.f, sc = 0.f, sf = 0.f;
 #pragma unroll
     for (int w = 0; w < WPR; ++w) {          // fixed order: every warp of the row gets bit-identical sums
-      const float4 x = slot[2 * (r * WPR + w)];
+      const float4 x = slot[2 * (wbase + w)];
       sa += x.x; sb += x.y; sc += x.z; sf += x.w;
     }
     a = sa; b = sb; c3 = sc;
@@ -830,7 +387,7 @@ __device__ __forceinline__ void row_reduce(float& a, float& b, float& c3, bool& 
 // (sum, M2) of two channels over the whole row: per-warp butterfly, then the WPR warp totals (CW values each) are
 // merged pairwise in a fixed order by every warp.
 template <int WPR, int N0>
-__device__ __forceinline__ void row_stats2(float& s1, float& m1, float& s2, float& m2, bool& bad, float* red, int round, int warp, int r, int lane) {
+__device__ __forceinline__ void row_stats2(float& s1, float& m1, float& s2, float& m2, bool& bad, float* red, int round, int warp, int wbase, int barid, int lane) {
   warp_stats2<N0>(s1, m1, s2, m2);
   if (WPR > 1) {
     constexpr int CW = HD / WPR;
@@ -839,13 +396,13 @@ __device__ __forceinline__ void row_stats2(float& s1, float& m1, float& s2, floa
       slot[2 * warp] = make_float4(s1, m1, s2, m2);
       slot[2 * warp + 1] = make_float4(bad ? 1.f : 0.f, 0.f, 0.f, 0.f);
     }
-    named_bar(2 + r, WPR * 32);
+    named_bar(barid, WPR * 32);
     float4 e[WPR];
     float sf = 0.f;
 #pragma unroll
     for (int w = 0; w < WPR; ++w) {
-      e[w] = slot[2 * (r * WPR + w)];
-      sf += slot[2 * (r * WPR + w) + 1].x;
+      e[w] = slot[2 * (wbase + w)];
+      sf += slot[2 * (wbase + w) + 1].x;
     }
 #pragma unroll
     for (int n = CW, cnt = WPR; cnt > 1; cnt >>= 1, n <<= 1) {
@@ -862,15 +419,16 @@ __device__ __forceinline__ void row_stats2(float& s1, float& m1, float& s2, floa
   }
 }
 
-template <int RT, bool PROF>
-__device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStage& st, const Ctx& c, int tid) {
-  constexpr int WPR = 4 / RT;               // warps per row
-  constexpr int NP = RT;                    // channel pairs per lane
+template <int RT, int WPR, bool PROF>
+__device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st, const Ctx& c, int tid) {
+  constexpr int NV = 4 / (RT * WPR);        // micro-batches in flight in the front end (visit slots)
+  constexpr int NP = 4 / WPR;               // channel pairs per lane
   constexpr int CW = HD / WPR;              // channels per warp
   constexpr int NBUF = MAXBUF / RT;
-  constexpr int NREC = 24 / RT;
+  constexpr int NREC = 24 / RT;             // a multiple of NV: a warp only ever meets its own entries
   const int warp = tid >> 5, lane = tid & 31;
-  const int r = warp / WPR, sub = warp % WPR;
+  const int vs = warp / (RT * WPR), r = (warp / WPR) % RT, sub = warp % WPR;
+  const int barid = 2 + vs * RT + r, wbase = warp - sub;
   const int cb = sub * CW + 2 * lane;       // pair i: channels cb + 64 i, cb + 64 i + 1
   const int s = c.s, part = c.part, G = c.G, B = c.B;
   const bool designated = part == 0;
@@ -882,7 +440,7 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
   int* pma_w = reinterpret_cast<int*>(c.smem + SM_PMA) + sub * B;     // my warp's own copy of the alignment state
   float* red = c.smem + SM_RED;
   float* rec = c.smem + SM_REC;
-  float* kvs = c.smem + SM_KV + r * (6 * HD);
+  float* kvs = c.smem + SM_KV + (vs * RT + r) * (6 * HD);
   const Word* raw_in = reinterpret_cast<const Word*>(p.ws_raw) + (size_t)c.prev * B * WS_WORDS;
   Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)s * B * WS_WORDS;
   const int koff = st.hwy ? 2 * TAPP : 0;
@@ -900,11 +458,21 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
     prof_last = now_;                              \
   }
 
+  // LayerNorm parameters of my channels (fixed for the whole launch)
+  float2 G1[NP], B1[NP], G2[NP], B2[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    G1[i] = *reinterpret_cast<const float2*>(g1 + cb + 64 * i);
+    B1[i] = *reinterpret_cast<const float2*>(b1 + cb + 64 * i);
+    G2[i] = *reinterpret_cast<const float2*>(g2 + cb + 64 * i);
+    B2[i] = *reinterpret_cast<const float2*>(b2 + cb + 64 * i);
+  }
+
   float2 tp[2][NP];
   bool have_pref = false, bad = false;
-  int step = 0, g = 0;
-  for (int v = 0; v < total_visits; ++v, ++g) {
-    if (g == G) { g = 0; ++step; }
+  int step = 0, g = vs, vi = 0;              // G is a multiple of NV: slot vs always meets the same micro-batches
+  for (int v = vs; v < total_visits; v += NV, g += NV, ++vi) {
+    while (g >= G) { g -= G; ++step; }
     const int t = p.t_start + step;
     const bool final_visit = s == 0 && step == p.n_steps;
     const int tag = p.seq_base + t + 1;
@@ -917,7 +485,7 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
     const bool live = row0 + r < B;
     const int b = row0 + r;
     PROF_F(0);
-    if ((v & 15) == 15) {                    // a launch aborted elsewhere: becomes row-uniform in the next reduction
+    if ((vi & 15) == 15) {                   // a launch aborted elsewhere: becomes row-uniform in the next reduction
       int ab = 0;
       if (lane == 0) ab = *reinterpret_cast<volatile int*>(p.abort_flag);
       if (__shfl_sync(FULL, ab, 0) != 0) bad = true;
@@ -1096,14 +664,14 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
             qq = fmaf(d1, d1, qq);
           }
         }
-        row_stats2<WPR, 2 * NP>(sum, qq, z0, z1, bad, red, 2 * (v & 1), warp, r, lane);
+        row_stats2<WPR, 2 * NP>(sum, qq, z0, z1, bad, red, 2 * (vi & 1), warp, wbase, barid, lane);
         const float mean = sum / (float)HD;
         const float rstd = rstd_fast(qq / (float)HD);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           const int ch = cb + 64 * i;
-          float o0 = (vv[i].x - mean) * rstd * g1[ch] + b1[ch];
-          float o1 = (vv[i].y - mean) * rstd * g1[ch + 1] + b1[ch + 1];
+          float o0 = (vv[i].x - mean) * rstd * G1[i].x + B1[i].x;
+          float o1 = (vv[i].y - mean) * rstd * G1[i].y + B1[i].y;
           if (pro == PRO_LN_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
           o[i] = make_float2(o0, o1);
           xstore(ch, o[i]);
@@ -1145,17 +713,16 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
             d = h2[i].y - l2; q2 = fmaf(d, d, q2);
           }
         }
-        row_stats2<WPR, 2 * NP>(s1, q1, s2, q2, bad, red, 2 * (v & 1), warp, r, lane);
+        row_stats2<WPR, 2 * NP>(s1, q1, s2, q2, bad, red, 2 * (vi & 1), warp, wbase, barid, lane);
         const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
         const float r1 = rstd_fast(q1 / (float)HD);
         const float r2 = rstd_fast(q2 / (float)HD);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          const int ch = cb + 64 * i;
-          const float a0 = (h1[i].x - m1) * r1 * g1[ch] + b1[ch];
-          const float a1 = (h1[i].y - m1) * r1 * g1[ch + 1] + b1[ch + 1];
-          const float c0 = (h2[i].x - m2) * r2 * g2[ch] + b2[ch];
-          const float c1 = (h2[i].y - m2) * r2 * g2[ch + 1] + b2[ch + 1];
+          const float a0 = (h1[i].x - m1) * r1 * G1[i].x + B1[i].x;
+          const float a1 = (h1[i].y - m1) * r1 * G1[i].y + B1[i].y;
+          const float c0 = (h2[i].x - m2) * r2 * G2[i].x + B2[i].x;
+          const float c1 = (h2[i].y - m2) * r2 * G2[i].y + B2[i].y;
           const float gt0 = sigmoid_fast(a0), gt1 = sigmoid_fast(a1);
           o[i] = make_float2(gt0 * c0 + (1.0f - gt0) * xr[i].x, gt1 * c1 + (1.0f - gt1) * xr[i].y);
         }
@@ -1188,7 +755,7 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
               l2 = fmaf(k2.x, o[i].x, l2); l2 = fmaf(k2.y, o[i].y, l2);
             }
           }
-          row_reduce<WPR>(l0, l1, l2, bad, red, 2 * (v & 1) + 1, warp, r, lane);
+          row_reduce<WPR>(l0, l1, l2, bad, red, 2 * (vi & 1) + 1, warp, wbase, barid, lane);
           l0 *= 0.0625f; l1 *= 0.0625f; l2 *= 0.0625f;    // 1/sqrt(256)
           float mx = l0;
           if (cnt > 1) mx = fmaxf(mx, l1);
@@ -1255,9 +822,9 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
     if (bad && (WPR == 1 || pro == PRO_X || live)) return;
     // ---- 5. global-ring taps of the next visit: issue the loads now, they land while I wait for its producer
     have_pref = false;
-    if (st.ntaps == 3 && v + 1 < total_visits) {
-      int step2 = step, g2 = g + 1;
-      if (g2 == G) { g2 = 0; ++step2; }
+    if (st.ntaps == 3 && v + NV < total_visits) {
+      int step2 = step, g2 = g + NV;
+      if (g2 >= G) { g2 -= G; ++step2; }
       const int t2 = p.t_start + step2;
       if (g2 * RT + r < B) {
 #pragma unroll
@@ -1280,17 +847,16 @@ __device__ __forceinline__ void front_role_coop(const DecParams& p, const WsStag
   if (prof_on) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 16 + i] = prof_acc[i];
-    p.prof[(size_t)blockIdx.x * 16 + 15] = total_visits > 0 ? total_visits : 1;
+    p.prof[(size_t)blockIdx.x * 16 + 15] = vi > 0 ? vi : 1;
   }
 #undef PROF_F
 }
 
-template <int RT, bool PROF, bool COOP>
+template <int RT, int WPR, bool PROF>
 __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t bars[3 * MAXBUF + 6];
   __shared__ int s_bad;
-  __shared__ int s_fe_done[4];
   __shared__ long long s_t_seen[2 * MAXBUF];
   const int tid = threadIdx.x;
 
@@ -1318,7 +884,6 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   c.pfree = bars + 3 * MAXBUF + 2;
   c.rdone = bars + 3 * MAXBUF + 4;
   c.s_bad = &s_bad;
-  c.fe_done = s_fe_done;
   c.t_seen = s_t_seen;
 
   // ---- one-time loads: tap-0 weights of a highway CTA, LayerNorm parameters, bias, alignment state
@@ -1343,18 +908,17 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
     }
     if (st.pro == PRO_ATT) {
       int* pma_s = reinterpret_cast<int*>(smem + SM_PMA);
-      const int copies = COOP ? 4 / RT : 1;               // cooperative front end: one copy per warp of a row
       for (int i = tid; i < p.B; i += NT) {
         const int pv = p.pma_in ? (int)p.pma_in[i] : p.pma_state[i];
-        for (int w = 0; w < copies; ++w) pma_s[w * p.B + i] = max(0, min(pv, p.N - 1));
+        for (int w = 0; w < WPR; ++w) pma_s[w * p.B + i]      // one copy per warp of a row
+          = max(0, min(pv, p.N - 1));
       }
     }
     if (tid == 0) {
       s_bad = 0;
-      s_fe_done[0] = s_fe_done[1] = s_fe_done[2] = s_fe_done[3] = 0;
       for (int i = 0; i < MAXBUF; ++i) {
-        mbar_init(&bars[i], COOP ? 4 : RT);              // tapsfull: one arrival per front-end warp of the visit
-        mbar_init(&bars[MAXBUF + i], COOP ? 4 : RT);     // curfull: likewise
+        mbar_init(&bars[i], RT * WPR);                   // tapsfull: one arrival per front-end warp of the visit
+        mbar_init(&bars[MAXBUF + i], RT * WPR);          // curfull: likewise
         mbar_init(&bars[2 * MAXBUF + i], 1);       // empty
       }
       for (int i = 0; i < 2; ++i) {
@@ -1369,8 +933,7 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   }
 
   if (tid < FE_T) {
-    if (COOP) front_role_coop<RT, PROF>(p, st, c, tid);
-    else front_role<RT, PROF>(p, st, c, tid);
+    front_role<RT, WPR, PROF>(p, st, c, tid);
   } else {
     const int gtid = tid - FE_T;
     if (st.hwy) gemv_role<RT, 16, true, PROF>(p, st, c, gtid);
@@ -1406,25 +969,24 @@ __global__ void ws_pack_image_kernel(const float* __restrict__ W, WsStage w, flo
   }
 }
 
-template <int RT, bool PROF, bool COOP>
-int launch_rt(const DecParams& p, cudaStream_t s) {
+template <int RT, int WPR, bool PROF>
+int launch_cfg(const DecParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)SM_TOTAL * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT, PROF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT, WPR, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   DecParams pl = p;
   void* args[] = {&pl};
-  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT, PROF, COOP>, dim3(WS_GRID), dim3(NT), args, smem, s));
+  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT, WPR, PROF>, dim3(WS_GRID), dim3(NT), args, smem, s));
   ++g_launches;
   return kOk;
 }
 
-template <bool COOP>
-int launch_fe(const DecParams& p, cudaStream_t s) {
-  if (p.prof) return p.R == 1 ? launch_rt<1, true, COOP>(p, s) : p.R == 2 ? launch_rt<2, true, COOP>(p, s) : launch_rt<4, true, COOP>(p, s);
-  return p.R == 1 ? launch_rt<1, false, COOP>(p, s) : p.R == 2 ? launch_rt<2, false, COOP>(p, s) : launch_rt<4, false, COOP>(p, s);
+template <int RT, int WPR>
+int launch_prof(const DecParams& p, cudaStream_t s) {
+  return p.prof ? launch_cfg<RT, WPR, true>(p, s) : launch_cfg<RT, WPR, false>(p, s);
 }
 
 }  // namespace
@@ -1459,6 +1021,31 @@ int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStr
   return kOk;
 }
 
+// Shape of the front end for a batch: rows per micro-batch R, warps per row W (4 / (R W) micro-batches in flight in
+// the front end), micro-batch count G (padded to a multiple of the in-flight count; padding rows are dead).
+// Measured on B200 (us/frame).
+void ws_plan(int B, int* R, int* W, int* G) {
+  int r, w;
+  if (B <= 8) { r = 1; w = 4; }            // 30 us/frame
+  else if (B <= 24) { r = 1; w = 2; }      // B=16 32, B=24 34 (4 warps per row: 34.5 at B=16)
+  else if (B <= 32) { r = 2; w = 2; }      // 40
+  else if (B <= 128) { r = 2; w = 1; }     // B=40 46 (R=1 47), B=64 54 (R=4 59), B=128 109 (R=4 110)
+  else { r = 4; w = 1; }                   // B=256 228
+  if (const char* e = getenv("SSV_DECODE_R")) {          // development knobs
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) { r = v; if (r * w > 4) w = 4 / r; }
+  }
+  if (const char* e = getenv("SSV_DECODE_W")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && r * v <= 4) w = v;
+  }
+  if (w * B > WS_MAX_BATCH) w = 1;
+  const int nv = 4 / (r * w);
+  int g = (B + r - 1) / r;
+  g = (g + nv - 1) / nv * nv;
+  *R = r; *W = w; *G = g;
+}
+
 bool decode_ws_supported(int sm_count) {
   static int ok = -1;
   if (ok < 0) {
@@ -1480,20 +1067,27 @@ int launch_decode_ws(const DecParams& p, cudaStream_t s) {
   SSV_CHECK(p.B <= WS_MAX_BATCH, "decode: batch %d exceeds %d", p.B, WS_MAX_BATCH);
   SSV_CHECK(p.ws_stages && p.ws_raw && p.ws_sent && p.ws_hist, "decode: weight-stationary buffers missing");
   SSV_CHECK(p.R == 1 || p.R == 2 || p.R == 4, "decode: micro-batch rows must be 1, 2 or 4");
-  // Front end: "coop" = the 4 / R warps of a row split its channels (one micro-batch in the front end at a time);
-  // "warp" = one warp per row, 4 / R micro-batches in flight.  (SSV_WS_FE picks one for A/B runs.)
-  static int fe = -1, rowpoll = 1;
-  if (fe < 0) {
-    const char* e = getenv("SSV_WS_FE");
-    fe = !e ? 2 : !strcmp(e, "warp") ? 0 : !strcmp(e, "coop") ? 1 : 2;
+  SSV_CHECK(p.W == 1 || p.W == 2 || p.W == 4, "decode: warps per row must be 1, 2 or 4");
+  SSV_CHECK(p.R * p.W <= 4 && p.G % (4 / (p.R * p.W)) == 0, "decode: micro-batch count %d does not fit %d x %d front-end warps", p.G, p.R, p.W);
+  SSV_CHECK(p.W * p.B <= WS_MAX_BATCH, "decode: per-warp alignment state does not fit");
+  static int rowpoll = -1;
+  if (rowpoll < 0) {
     const char* q = getenv("SSV_WS_POLL");
     rowpoll = !(q && !strcmp(q, "sentinel"));
   }
-  bool coop = fe == 1 || (fe == 2 && p.G <= 16);      // the cooperative front end serves one micro-batch at a time
-  coop = coop && (4 / p.R) * p.B <= WS_MAX_BATCH;     // per-warp copies of the alignment state must fit
   DecParams pl = p;
   pl.ws_flags = rowpoll ? WS_FLAG_ROWPOLL : 0;
-  return coop ? launch_fe<true>(pl, s) : launch_fe<false>(pl, s);
+  switch (p.R * 8 + p.W) {
+    case 1 * 8 + 1: return launch_prof<1, 1>(pl, s);
+    case 1 * 8 + 2: return launch_prof<1, 2>(pl, s);
+    case 1 * 8 + 4: return launch_prof<1, 4>(pl, s);
+    case 2 * 8 + 1: return launch_prof<2, 1>(pl, s);
+    case 2 * 8 + 2: return launch_prof<2, 2>(pl, s);
+    case 4 * 8 + 1: return launch_prof<4, 1>(pl, s);
+    default: break;
+  }
+  set_error("decode: unsupported front-end shape R=%d W=%d", p.R, p.W);
+  return kInval;
 }
 
 }  // namespace ssv
