@@ -286,7 +286,6 @@ struct ssv_decoder {
   long long* prof = nullptr;
   int impl = DEC_IMPL_GRID;
   unsigned long long* ws_raw = nullptr;
-  int* ws_sent = nullptr;
   float* ws_hist = nullptr;
   int seq_base = 0, R = 1, G = 1, W = 4;
   // per-batch state
@@ -677,12 +676,9 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
   if (d->impl == DEC_IMPL_WS) {
     const size_t bp = (size_t)round_up(max_batch, 4);
     const size_t raw_words = (size_t)DEC_STAGES * max_batch * WS_WORDS;
-    const size_t sent_ints = (size_t)DEC_STAGES * bp * WS_MAX_PARTS;      // micro-batch count may be padded by up to 3
     if (st == kOk) st = d->arena.alloc<unsigned long long>(raw_words, &d->ws_raw);
-    if (st == kOk) st = d->arena.alloc<int>(sent_ints, &d->ws_sent);
     if (st == kOk) st = d->arena.alloc<float>((size_t)m->ws_hist_blocks * bp * H, &d->ws_hist);
     if (st == kOk && cudaMemset(d->ws_raw, 0, raw_words * sizeof(unsigned long long)) != cudaSuccess) st = kCuda;
-    if (st == kOk && cudaMemset(d->ws_sent, 0, sent_ints * sizeof(int)) != cudaSuccess) st = kCuda;
   } else {
     if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_STAGES * max_batch * DEC_RAW_LD, &d->raw);
     if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_HIST * max_batch * max_frames * H, &d->hist);
@@ -729,7 +725,6 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
     d->seq_base += d->t_cap + 2;
     if (d->seq_base > (1 << 30)) {
       SSV_CUDA(cudaMemsetAsync(d->ws_raw, 0, (size_t)DEC_STAGES * d->maxB * WS_WORDS * sizeof(unsigned long long), s));
-      SSV_CUDA(cudaMemsetAsync(d->ws_sent, 0, (size_t)DEC_STAGES * round_up(d->maxB, 4) * WS_MAX_PARTS * sizeof(int), s));
       d->seq_base = 0;
     }
     ws_plan(B, &d->R, &d->W, &d->G);
@@ -764,7 +759,7 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.abort_flag = d->abort_flag;
   p.prof = d->prof;
   p.ws_stages = m->ws_stages_dev;
-  p.ws_raw = d->ws_raw; p.ws_sent = d->ws_sent; p.ws_hist = d->ws_hist;
+  p.ws_raw = d->ws_raw; p.ws_hist = d->ws_hist;
   p.seq_base = d->seq_base; p.R = d->R; p.G = d->G; p.W = d->W;
   const int sms = device_sm_count();
   SSV_CHECK(sms > 0, "decoder: no CUDA device");

@@ -53,11 +53,9 @@ struct WsStage {
   int hist_blk0;       // first ring block of the stage (block = [G][256][RT] floats)
 };
 constexpr int WS_WORDS = 768;        // tagged 8-byte words per (stage, utterance): 512 outputs + 256 residual
-constexpr int WS_MAX_PARTS = 8;
 constexpr int WS_GRID = 145;         // 16 highway layers x 8 + 17 CTAs for the eight 1x1 stages
 constexpr int WS_GEMV_THREADS = 384; // warps 4-15 of a CTA
 constexpr int WS_TAP_ROWS = 264;     // 256 input channels of a tap, padded to a multiple of 24 k-slices
-constexpr int WS_FLAG_ROWPOLL = 1;   // front end polls the tagged words of its row directly (no sentinel look first)
 constexpr int WS_MAX_BATCH = 1024;
 enum DecodeImpl { DEC_IMPL_WS = 0, DEC_IMPL_CLUSTER = 1, DEC_IMPL_GRID = 2 };
 
@@ -83,11 +81,9 @@ struct DecParams {
   // weight-stationary pipeline only
   const WsStage* ws_stages;     // device [DEC_STAGES]
   unsigned long long* ws_raw;   // [DEC_STAGES][B][WS_WORDS] tagged words {float, tag}
-  int* ws_sent;                 // [DEC_STAGES][G][WS_MAX_PARTS] sentinel tags
   float* ws_hist;               // private input-history rings, [blocks][G][256][R]
   int seq_base;                 // tag of frame t is seq_base + t + 1 (advanced by every begin())
   int R, G, W;                  // rows per micro-batch (1, 2, 4), micro-batches, front-end warps per row (1, 2, 4)
-  int ws_flags;                 // WS_FLAG_* (set by launch_decode_ws)
 };
 
 int launch_decode(const DecParams& p, int sm_count, int impl, cudaStream_t s);

@@ -34,8 +34,8 @@
 // row slice directly -- it loads them, checks every tag and re-loads until all match -- so there is exactly one
 // L2 round trip between "the producer's store landed" and "the consumer has the data", no fences and no
 // release/acquire chain on the critical path, and a word that has not landed yet can never be mistaken for data.
-// (Polling a per-CTA sentinel first and loading the row afterwards costs a second dependent round trip per stage:
-// 43 vs 31 us/frame at B = 1; SSV_WS_POLL=sentinel keeps that mode for A/B runs.)  Everything else a CTA touches
+// (Polling a per-CTA sentinel first and loading the row afterwards, as the first version did, costs a second
+// dependent round trip per stage: 43 vs 31 us/frame at B = 1.)  Everything else a CTA touches
 // is private to it (weights, LayerNorm parameters, its own ring of past stage inputs), so the tagged words are
 // the only cross-CTA traffic.
 #include "decode.cuh"
@@ -224,7 +224,7 @@ __device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, c
 }
 
 struct Ctx {                 // per-CTA constants shared by both roles
-  int s, prev, part, prev_parts, G, B;
+  int s, prev, part, G, B;
   float* smem;
   uint64_t* tapsfull;        // [8] old taps of the X buffer have landed (cp.async)
   uint64_t* curfull;         // [8] current tap (prologue output) is in the X buffer
@@ -282,6 +282,19 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
       const int q = v % NBUF;
       const unsigned par = (unsigned)(v / NBUF) & 1u;
       const float* X = c.smem + SM_X + q * (XROWS * RT) + ks * RT;
+      // publisher threads: the hoisted speaker projection of my output is fetched now, not after the mat-vec
+      const int row0 = g * RT;
+      float sb[(RT * NCOL + GV_T - 1) / GV_T];
+#pragma unroll
+      for (int i = 0; i < (RT * NCOL + GV_T - 1) / GV_T; ++i) {
+        const int o = gtid + i * GV_T;
+        sb[i] = 0.f;
+        if (st.bias_b != 0 && o < RT * NCOL) {
+          const int r = o / NCOL, lc = o - r * NCOL;
+          const int gc = gcol(st, c.part, lc), b = row0 + r;
+          if (b < c.B && gc < st.n) sb[i] = __ldg((st.bias_b == 1 ? p.s1 : p.s2) + (size_t)b * HD + gc);
+        }
+      }
       float acc[RT][4];
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
@@ -325,27 +338,27 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
       if (gtid == 0) mbar_arrive(&c.empty[q]);     // X buffer q may be refilled
       PROF_G(3);
       // reduce the 12 k-slices, add bias (+ hoisted speaker projection), publish tagged words
-      const int row0 = g * RT;
-      for (int o = gtid; o < RT * NCOL; o += GV_T) {
-        const int r = o / NCOL, lc = o - r * NCOL;
-        float sum = 0.f;
 #pragma unroll
-        for (int sl = 0; sl < 12; ++sl) sum += parts[((size_t)sl * RT + r) * NCOL + lc];
-        const int gc = gcol(st, c.part, lc);
-        const int b = row0 + r;
-        if (b < c.B && gc < st.n) {
-          sum += bias_s[lc];
-          if (st.bias_b == 1) sum += __ldg(p.s1 + (size_t)b * HD + gc);
-          else if (st.bias_b == 2) sum += __ldg(p.s2 + (size_t)b * HD + gc);
-          st_word(raw_out + (size_t)b * WS_WORDS + gc, sum, tag);
+      for (int i = 0; i < (RT * NCOL + GV_T - 1) / GV_T; ++i) {
+        const int o = gtid + i * GV_T;
+        if (o < RT * NCOL) {
+          const int r = o / NCOL, lc = o - r * NCOL;
+          float sum = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < 12; ++sl) sum += parts[((size_t)sl * RT + r) * NCOL + lc];
+          const int gc = gcol(st, c.part, lc);
+          const int b = row0 + r;
+          if (b < c.B && gc < st.n) st_word(raw_out + (size_t)b * WS_WORDS + gc, sum + bias_s[lc] + sb[i], tag);
         }
       }
+      // Second CTA-wide barrier: the k-slice buffer may be rewritten, and -- measured -- it keeps the warps without
+      // an output from running ahead into the next micro-batch and taking issue slots from the publishing warps
+      // (without it: B = 64 54 -> 60 us/frame, B = 128 108 -> 122).
       named_bar(1, GV_T);
-      if (*reinterpret_cast<volatile int*>(c.s_bad) == 2) return;     // uniform: written before the barrier
-      if (gtid == 0) {
-        st_relaxed_s32(p.ws_sent + ((size_t)c.s * c.G + g) * WS_MAX_PARTS + c.part, tag);
-        if ((v & 15) == 15 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) *c.s_bad = 2;   // seen at the next barrier
-      }
+      // abort flag: thread 0 looks at it at the end of visits 16k + 15, everybody reads the verdict after this barrier
+      // of visit 16k + 16 (written a whole visit earlier, next written 15 visits later: the read is uniform)
+      if ((v & 15) == 0 && *reinterpret_cast<volatile int*>(c.s_bad) == 2) return;
+      if (gtid == 0 && (v & 15) == 15 && *reinterpret_cast<volatile int*>(p.abort_flag) != 0) *c.s_bad = 2;
       PROF_G(4);
       if (PROF && prof_on) lat_acc += prof_last - c.t_seen[q];
     }
@@ -573,15 +586,6 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
           if (*reinterpret_cast<volatile int*>(p.abort_flag) != 0) bad = true;
         }
       };
-      if (need_wait && !(p.ws_flags & WS_FLAG_ROWPOLL)) {
-        const int* sp = p.ws_sent + ((size_t)c.prev * G + g) * WS_MAX_PARTS;
-        for (;;) {
-          const int sv = lane < c.prev_parts ? ld_relaxed_s32(sp + lane) : tag_in;
-          if (__all_sync(FULL, sv - tag_in >= 0)) break;
-          spin_check();
-          if (__any_sync(FULL, bad)) { bad = true; break; }
-        }
-      }
       PROF_F(3);
       if (PROF && p.prof != nullptr && tid == 0) c.t_seen[q] = clock64();
       const Word* R = raw_in + (size_t)b * WS_WORDS;
@@ -873,7 +877,6 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   c.s = s;
   c.prev = (s + DEC_STAGES - 1) % DEC_STAGES;
   c.part = (int)blockIdx.x - st.cta0;
-  c.prev_parts = p.ws_stages[c.prev].parts;
   c.G = p.G;
   c.B = p.B;
   c.smem = smem;
@@ -1065,25 +1068,18 @@ int launch_decode_ws(const DecParams& p, cudaStream_t s) {
   SSV_CHECK(p.F <= 96 && p.F % 4 == 0, "decode: freq_bins must be <= 96 and a multiple of 4");
   SSV_CHECK(p.B >= 1 && p.n_steps >= 1, "decode: empty launch");
   SSV_CHECK(p.B <= WS_MAX_BATCH, "decode: batch %d exceeds %d", p.B, WS_MAX_BATCH);
-  SSV_CHECK(p.ws_stages && p.ws_raw && p.ws_sent && p.ws_hist, "decode: weight-stationary buffers missing");
+  SSV_CHECK(p.ws_stages && p.ws_raw && p.ws_hist, "decode: weight-stationary buffers missing");
   SSV_CHECK(p.R == 1 || p.R == 2 || p.R == 4, "decode: micro-batch rows must be 1, 2 or 4");
   SSV_CHECK(p.W == 1 || p.W == 2 || p.W == 4, "decode: warps per row must be 1, 2 or 4");
   SSV_CHECK(p.R * p.W <= 4 && p.G % (4 / (p.R * p.W)) == 0, "decode: micro-batch count %d does not fit %d x %d front-end warps", p.G, p.R, p.W);
   SSV_CHECK(p.W * p.B <= WS_MAX_BATCH, "decode: per-warp alignment state does not fit");
-  static int rowpoll = -1;
-  if (rowpoll < 0) {
-    const char* q = getenv("SSV_WS_POLL");
-    rowpoll = !(q && !strcmp(q, "sentinel"));
-  }
-  DecParams pl = p;
-  pl.ws_flags = rowpoll ? WS_FLAG_ROWPOLL : 0;
   switch (p.R * 8 + p.W) {
-    case 1 * 8 + 1: return launch_prof<1, 1>(pl, s);
-    case 1 * 8 + 2: return launch_prof<1, 2>(pl, s);
-    case 1 * 8 + 4: return launch_prof<1, 4>(pl, s);
-    case 2 * 8 + 1: return launch_prof<2, 1>(pl, s);
-    case 2 * 8 + 2: return launch_prof<2, 2>(pl, s);
-    case 4 * 8 + 1: return launch_prof<4, 1>(pl, s);
+    case 1 * 8 + 1: return launch_prof<1, 1>(p, s);
+    case 1 * 8 + 2: return launch_prof<1, 2>(p, s);
+    case 1 * 8 + 4: return launch_prof<1, 4>(p, s);
+    case 2 * 8 + 1: return launch_prof<2, 1>(p, s);
+    case 2 * 8 + 2: return launch_prof<2, 2>(p, s);
+    case 4 * 8 + 1: return launch_prof<4, 1>(p, s);
     default: break;
   }
   set_error("decode: unsupported front-end shape R=%d W=%d", p.R, p.W);
