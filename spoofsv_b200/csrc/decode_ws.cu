@@ -302,10 +302,14 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
         // old taps: independent of the producer stage, overlaps the front end's wait
         mbar_wait(&c.tapsfull[q], par, p.abort_flag);     // on abort: fall through, the uniform exit is below
         PROF_G(0);
+        // shared-memory-weight tiles (tap t-2d) alternate with register-weight tiles (tap t-d): twice the FMAs
+        // between two LDS.128 weight fetches, so their latency hides with the two fragment buffers the register
+        // budget allows (back to back, every other tile stalled on its fetch: 18 % of all samples short-scoreboard)
 #pragma unroll
-        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, wsm[j * GV_T], X + (size_t)(KS * j) * RT);
-#pragma unroll
-        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[j], X + (size_t)(TAPP + KS * j) * RT);
+        for (int j = 0; j < 11; ++j) {
+          fma_tile<RT>(acc, wsm[j * GV_T], X + (size_t)(KS * j) * RT);
+          fma_tile<RT>(acc, w[j], X + (size_t)(TAPP + KS * j) * RT);
+        }
         PROF_G(1);
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);

@@ -178,17 +178,22 @@ def test_decode_batch_sizes_vs_oracle(B, cuda_models):
     assert _maxabs(Y, oY) <= FP32_TOL and _maxabs(A, oA) <= FP32_TOL
 
 
-@pytest.mark.parametrize("B,R", [(3, 2), (5, 4), (7, 1), (41, None), (67, 4), (130, None)])
-def test_decode_micro_batch_shapes_vs_oracle(B, R, cuda_models, monkeypatch):
-    """Weight-stationary pipeline: rows per micro-batch 1 / 2 / 4 (forced through the development knob and by
-    the batch-size policy), ragged last micro-batch, more micro-batches than pipeline stages."""
+@pytest.mark.parametrize("B,R,Wp", [(3, 2, None), (5, 4, None), (7, 1, None), (41, None, None), (67, 4, None),
+                                    (130, None, None), (9, 1, 1), (6, 1, 2), (26, None, None), (13, 2, 1), (21, 1, 4)])
+def test_decode_micro_batch_shapes_vs_oracle(B, R, Wp, cuda_models, monkeypatch):
+    """Weight-stationary pipeline, every front-end shape: rows per micro-batch R = 1 / 2 / 4 and warps per row
+    W = 1 / 2 / 4 (forced through the development knobs and chosen by ws_plan), 4 / (R W) micro-batches in flight,
+    ragged last micro-batch, micro-batch count padded to the in-flight count (dead micro-batches), more
+    micro-batches than pipeline stages."""
     m1, _, sd1, _ = cuda_models
     names, emb, _ = W.load_fixtures()
     if R is not None:
         monkeypatch.setenv("SSV_DECODE_R", str(R))
+    if Wp is not None:
+        monkeypatch.setenv("SSV_DECODE_W", str(Wp))
     ids = W.synthetic_text(B, 40, seed=100 + B)
     spk = torch.from_numpy(emb[[i % len(emb) for i in range(B)]].copy())[:, :, None]
-    T = 64 if B <= 8 else 12           # small batches: long enough for the dilation-27 taps to leave the zero region
+    T = 64 if B <= 9 else 12           # small batches: long enough for the dilation-27 taps to leave the zero region
     Y, A, traj, _, _ = m1.synthesize(ids.cuda(), spk.cuda(), T)
     with torch.no_grad():
         oY, oA, otraj = O.ar_loop_incremental(sd1, ids, spk, T)
