@@ -133,6 +133,17 @@ int ssv_synthesize_host_wait(ssv_decoder* d, int ticket);
  * synthesize.py:144).  x, y: dev (B, n) contiguous; in place (y == x) is allowed. */
 int ssv_deemphasis(const float* x, float* y, int B, long n, float coeff, void* stream);
 
+/* ---- feature front-end (next row of the scope table) -------------------------------------------
+ * Spectrogram features of one utterance: replaces data/dataset.py:97-118 (np.abs of the STFT, np.dot with
+ * librosa.filters.mel, the LOG_FEATURE / NORM_POWER.ANALYSIS normalisation, every `reduction`-th mel frame,
+ * the linear spectrogram cut to reduction * (T / reduction) frames).
+ * stft_ri: dev (F, T) complex64 as interleaved (re, im) floats -- the layout of the STFT of the trimmed,
+ * pre-emphasised signal; melfb: dev (n_mels, F) filter bank; lin_norm: dev (F, reduction * (T / reduction));
+ * mel_red: dev (n_mels, T / reduction); workspace: dev, at least F * T + n_mels * T + 2 floats. */
+int ssv_spec_features(const float* stft_ri, int F, int T, const float* melfb, int n_mels, int log_feature,
+                      float norm_power, float ref_db, float max_db, int reduction, float* lin_norm, float* mel_red,
+                      float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1128,6 +1128,19 @@ int ssv_synthesize_host_submit(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, co
 int ssv_synthesize_host_wait(ssv_decoder* d, int ticket) { return synth_wait(d, ticket); }
 
 // ------------------------------------------------------------------------------------------------
+int ssv_spec_features(const float* stft_ri, int F, int T, const float* melfb, int n_mels, int log_feature,
+                      float norm_power, float ref_db, float max_db, int reduction, float* lin_norm, float* mel_red,
+                      float* workspace, void* stream) {
+  SSV_CHECK(stft_ri && melfb && lin_norm && mel_red && workspace, "spec_features: null pointer");
+  SSV_CHECK(F >= 1 && F <= 1025 && T >= 1, "spec_features: bad spectrogram shape (%d, %d)", F, T);
+  SSV_CHECK(n_mels >= 1 && n_mels <= 128, "spec_features: n_mels must be in [1, 128]");
+  SSV_CHECK(reduction >= 1, "spec_features: reduction must be >= 1");
+  SSV_CHECK(log_feature || norm_power > 0.f, "spec_features: norm_power must be positive");
+  SSV_CHECK(!log_feature || max_db > 0.f, "spec_features: MAX_DB must be positive");
+  return launch_spec_features(stft_ri, F, T, melfb, n_mels, log_feature, norm_power, ref_db, max_db, reduction, lin_norm,
+                              mel_red, workspace, as_stream(stream));
+}
+
 int ssv_deemphasis(const float* x, float* y, int B, long n, float coeff, void* stream) {
   SSV_CHECK(x && y, "deemphasis: null pointer");
   SSV_CHECK(B >= 0 && n >= 0, "deemphasis: negative size");

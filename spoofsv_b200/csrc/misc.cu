@@ -113,6 +113,94 @@ __global__ void linear_small_kernel(const float* __restrict__ x, long x_ld, cons
   if (lane == 0) y[(long)b * y_ld + o] = acc + bias[o];
 }
 
+// ---- feature front-end (data/dataset.py:97-118): |STFT| -> mel projection -> normalise -> frame reduction ----------
+// Pass 1, one block per 32 spectrogram frames: magnitudes of the block's (F x 32) tile go to shared memory and to the
+// workspace, the mel projection (n_mels x F filter bank, L2-resident) is taken from the shared tile, and the maxima
+// of both spectrograms are folded into two device words (the values are >= 0, so their bit patterns order like
+// unsigned integers).  Pass 2 normalises element-wise and keeps every `reduction`-th mel frame.
+constexpr int FEAT_T = 256;
+constexpr int FEAT_COLS = 32;
+constexpr int FEAT_MAX_MELS = 128;
+__global__ void __launch_bounds__(FEAT_T) spec_mag_mel_kernel(const float2* __restrict__ stft, int F, int T,
+                                                              const float* __restrict__ melfb, int n_mels,
+                                                              float* __restrict__ lin_raw, float* __restrict__ mel_raw,
+                                                              unsigned* __restrict__ maxima) {
+  extern __shared__ float tile[];                       // [F][32]
+  __shared__ float red[2][FEAT_T / 32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int t = blockIdx.x * FEAT_COLS + tx;
+  float mx_lin = 0.f, mx_mel = 0.f;
+  for (int f = ty; f < F; f += FEAT_T / 32) {
+    float m = 0.f;
+    if (t < T) {
+      const float2 v = stft[(long)f * T + t];
+      m = hypotf(v.x, v.y);
+      lin_raw[(long)f * T + t] = m;
+    }
+    tile[f * FEAT_COLS + tx] = m;
+    mx_lin = fmaxf(mx_lin, m);
+  }
+  __syncthreads();
+  float acc[FEAT_MAX_MELS / 8];
+#pragma unroll
+  for (int i = 0; i < FEAT_MAX_MELS / 8; ++i) acc[i] = 0.f;
+  for (int f = 0; f < F; ++f) {
+    const float sv = tile[f * FEAT_COLS + tx];
+#pragma unroll
+    for (int i = 0; i < FEAT_MAX_MELS / 8; ++i) {
+      const int m = ty + 8 * i;
+      if (m < n_mels) acc[i] = fmaf(__ldg(melfb + (long)m * F + f), sv, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < FEAT_MAX_MELS / 8; ++i) {
+    const int m = ty + 8 * i;
+    if (m < n_mels && t < T) {
+      mel_raw[(long)m * T + t] = acc[i];
+      mx_mel = fmaxf(mx_mel, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx_lin = fmaxf(mx_lin, __shfl_xor_sync(0xffffffffu, mx_lin, o));
+    mx_mel = fmaxf(mx_mel, __shfl_xor_sync(0xffffffffu, mx_mel, o));
+  }
+  if (tx == 0) { red[0][ty] = mx_lin; red[1][ty] = mx_mel; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float m = 0.f;
+    for (int i = 0; i < FEAT_T / 32; ++i) m = fmaxf(m, red[threadIdx.x][i]);
+    atomicMax(maxima + threadIdx.x, __float_as_uint(m));
+  }
+}
+
+__device__ __forceinline__ float feat_norm(float x, float mx, int log_feature, float p, float ref_db, float max_db) {
+  if (log_feature) {
+    const float db = 20.0f * log10f(fmaxf(1e-5f, x));
+    return fminf(fmaxf((db - ref_db + max_db) / max_db, 1e-8f), 1.0f);
+  }
+  return powf(x / mx, p);
+}
+
+__global__ void spec_norm_kernel(const float* __restrict__ lin_raw, const float* __restrict__ mel_raw,
+                                 const unsigned* __restrict__ maxima, int F, int T, int n_mels, int reduction, int T4,
+                                 int log_feature, float p, float ref_db, float max_db, float* __restrict__ lin_norm,
+                                 float* __restrict__ mel_red) {
+  const float mx_lin = __uint_as_float(maxima[0]), mx_mel = __uint_as_float(maxima[1]);
+  const int Tc = reduction * T4;
+  const long n_lin = (long)F * Tc, n_mel = (long)n_mels * T4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n_lin + n_mel; i += (long)gridDim.x * blockDim.x) {
+    if (i < n_lin) {
+      const int f = (int)(i / Tc), t = (int)(i % Tc);
+      lin_norm[i] = feat_norm(lin_raw[(long)f * T + t], mx_lin, log_feature, p, ref_db, max_db);
+    } else {
+      const long j = i - n_lin;
+      const int m = (int)(j / T4), k = (int)(j % T4);
+      mel_red[j] = feat_norm(mel_raw[(long)m * T + (long)reduction * k], mx_mel, log_feature, p, ref_db, max_db);
+    }
+  }
+}
+
 // De-emphasis y[n] = x[n] + c y[n-1] (scipy.signal.lfilter([1], [1, -c]) at generate_test_utterances.py:136) of one
 // waveform per block: 1024 threads filter contiguous chunks from zero state, one warp-free serial pass chains the
 // 1024 chunk ends (carry_t = end_{t-1} + c^L carry_{t-1}), and a second pass adds c^(i+1) * carry to every sample.
@@ -292,6 +380,35 @@ int launch_linear_small(const float* x, long x_ld, const float* w, const float* 
   linear_small_kernel<<<(int)((threads + 255) / 256), 256, 0, s>>>(x, x_ld, w, b, B, in_f, out_f, y, y_ld);
   ++g_launches;
   SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_spec_features(const float* stft_ri, int F, int T, const float* melfb, int n_mels, int log_feature,
+                         float norm_power, float ref_db, float max_db, int reduction, float* lin_norm,
+                         float* mel_red, float* workspace, cudaStream_t s) {
+  float* lin_raw = workspace;
+  float* mel_raw = workspace + (size_t)F * T;
+  unsigned* maxima = reinterpret_cast<unsigned*>(mel_raw + (size_t)n_mels * T);
+  SSV_CUDA(cudaMemsetAsync(maxima, 0, 2 * sizeof(unsigned), s));
+  const size_t smem = (size_t)F * FEAT_COLS * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    SSV_CUDA(cudaFuncSetAttribute(spec_mag_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  spec_mag_mel_kernel<<<(T + FEAT_COLS - 1) / FEAT_COLS, FEAT_T, smem, s>>>(reinterpret_cast<const float2*>(stft_ri), F, T,
+                                                                            melfb, n_mels, lin_raw, mel_raw, maxima);
+  SSV_CUDA(cudaGetLastError());
+  const int T4 = T / reduction;
+  const long total = (long)F * reduction * T4 + (long)n_mels * T4;
+  if (total > 0) {
+    long g = (total + 255) / 256;
+    if (g > 4096) g = 4096;
+    spec_norm_kernel<<<(int)g, 256, 0, s>>>(lin_raw, mel_raw, maxima, F, T, n_mels, reduction, T4, log_feature, norm_power,
+                                            ref_db, max_db, lin_norm, mel_red);
+    SSV_CUDA(cudaGetLastError());
+  }
+  g_launches += 2;
   return kOk;
 }
 

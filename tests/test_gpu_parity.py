@@ -290,6 +290,26 @@ def test_full_size_decode_properties(cuda_models):
     assert _maxabs(Ys, Y[sub]) <= 1e-5
 
 
+def test_reference_driver_maximum_sizes_vs_oracle(cuda_models):
+    """The stock generate_test_utterances.py loop at its configured maxima: 20 sentences per speaker padded to
+    MAX_TEXT_LEN = 186, MAX_FRAME_NUM + 1 = 326 frames (config.json:13-14, generate_test_utterances.py:105-116);
+    two of the rows are checked against the oracle's incremental loop, all of them for the window constraint."""
+    m1, _, sd1, _ = cuda_models
+    names, emb, _ = W.load_fixtures()
+    B, N, T = 20, 186, 326
+    ids = W.synthetic_text(B, N, seed=77)
+    spk = torch.from_numpy(emb[40:40 + B].copy())[:, :, None]
+    Y, A, traj, _, _ = m1.synthesize(ids.cuda(), spk.cuda(), T)
+    assert tuple(Y.shape) == (B, 80, T) and tuple(A.shape) == (B, N, T)
+    step = traj[1:] - traj[:-1]
+    assert int(step.min()) >= 0 and int(step.max()) <= 2 and int(traj.max()) <= N - 1
+    sub = [0, B - 1]
+    with torch.no_grad():
+        oY, oA, otraj = O.ar_loop_incremental(sd1, ids[sub], spk[sub], T)
+    assert np.array_equal(traj[:, sub].cpu().numpy(), otraj.numpy())
+    assert _maxabs(Y[sub], oY) <= FP32_TOL and _maxabs(A[sub], oA) <= FP32_TOL
+
+
 # --------------------------------------------------------------------------- host-buffer entry point
 def test_synthesize_host_matches_module_path(cuda_models):
     from spoofsv_b200.synth import Synthesizer
