@@ -133,6 +133,15 @@ int ssv_synthesize_host_wait(ssv_decoder* d, int ticket);
  * synthesize.py:144).  x, y: dev (B, n) contiguous; in place (y == x) is allowed. */
 int ssv_deemphasis(const float* x, float* y, int B, long n, float coeff, void* stream);
 
+/* Fast Griffin-Lim: replaces librosa.core.griffinlim(S=spec, n_iter=64, hop_length=256, win_length=1024)
+ * (generate_test_utterances.py:133, synthesize.py:141; librosa 0.7: momentum 0.99, periodic Hann window, centred
+ * reflect-padded frames) for a whole batch.  S: dev (B, 513, T) magnitudes; angles0_ri: dev (B, 513, T) complex64
+ * initial phases as interleaved (re, im) -- librosa draws them as exp(2j pi rand); y: dev (B, 256 (T - 1)) samples;
+ * workspace: dev, ssv_griffin_lim_workspace(B, T) floats.  Only the reference's STFT shape is built. */
+long long ssv_griffin_lim_workspace(int B, int T);
+int ssv_griffin_lim(const float* S, const float* angles0_ri, int B, int F, int T, int n_iter, int hop, int win_length,
+                    float momentum, float* y, float* workspace, long long workspace_floats, void* stream);
+
 /* ---- feature front-end (next row of the scope table) -------------------------------------------
  * Spectrogram features of one utterance: replaces data/dataset.py:97-118 (np.abs of the STFT, np.dot with
  * librosa.filters.mel, the LOG_FEATURE / NORM_POWER.ANALYSIS normalisation, every `reduction`-th mel frame,

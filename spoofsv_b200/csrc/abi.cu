@@ -1128,6 +1128,21 @@ int ssv_synthesize_host_submit(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, co
 int ssv_synthesize_host_wait(ssv_decoder* d, int ticket) { return synth_wait(d, ticket); }
 
 // ------------------------------------------------------------------------------------------------
+long long ssv_griffin_lim_workspace(int B, int T) {
+  if (B < 1 || T < 2) return 0;
+  return (long long)griffin_lim_workspace_floats(B, T);
+}
+
+int ssv_griffin_lim(const float* S, const float* angles0_ri, int B, int F, int T, int n_iter, int hop, int win_length,
+                    float momentum, float* y, float* workspace, long long workspace_floats, void* stream) {
+  SSV_CHECK(S && angles0_ri && y && workspace, "griffin_lim: null pointer");
+  SSV_CHECK(F == 513 && hop == 256 && win_length == 1024, "griffin_lim: only n_fft = win_length = 1024, hop = 256 (the reference's STFT) is built, got F=%d hop=%d win=%d", F, hop, win_length);
+  SSV_CHECK(B >= 1 && T >= 3, "griffin_lim: need B >= 1 and at least 3 frames (reflect padding)");
+  SSV_CHECK(n_iter >= 0 && momentum >= 0.f && momentum < 1.f, "griffin_lim: bad n_iter / momentum");
+  SSV_CHECK(workspace_floats >= (long long)griffin_lim_workspace_floats(B, T), "griffin_lim: workspace too small");
+  return launch_griffin_lim(S, angles0_ri, B, T, n_iter, momentum, y, workspace, as_stream(stream));
+}
+
 int ssv_spec_features(const float* stft_ri, int F, int T, const float* melfb, int n_mels, int log_feature,
                       float norm_power, float ref_db, float max_db, int reduction, float* lin_norm, float* mel_red,
                       float* workspace, void* stream) {

@@ -97,6 +97,9 @@ int launch_linear_small(const float* x, long x_ld, const float* w, const float* 
 int launch_train_attention(const float* Kx /*(B,N,512)*/, const float* Q /*(B,T,256)*/, int B, int N, int T,
                            float* A /*(B,N,T)*/, float* RQ /*(B,T,512)*/, cudaStream_t s);
 int launch_deemphasis(const float* x, float* y, int B, long n, float coeff, cudaStream_t s);   // y[n] = x[n] + c y[n-1] per row
+size_t griffin_lim_workspace_floats(int B, int T);                 // griffinlim.cu
+int launch_griffin_lim(const float* S /*(B,513,T)*/, const float* angles0_ri /*(B,513,T,2)*/, int B, int T, int n_iter,
+                       float momentum, float* y /*(B, 256 (T-1))*/, float* workspace, cudaStream_t s);
 int launch_spec_features(const float* stft_ri, int F, int T, const float* melfb, int n_mels, int log_feature,
                          float norm_power, float ref_db, float max_db, int reduction, float* lin_norm,
                          float* mel_red, float* workspace, cudaStream_t s);     // |STFT| -> mel -> normalise -> reduce

@@ -1,0 +1,263 @@
+// Fused fast Griffin-Lim for the waveform stage (generate_test_utterances.py:133, synthesize.py:141:
+// librosa.core.griffinlim(S, n_iter=64, hop_length=256, win_length=1024) of librosa 0.7, momentum 0.99).
+//
+//   for it in range(n_iter):  tprev = rebuilt;  rebuilt = stft(istft(S * angles));
+//                             angles = rebuilt - momentum / (1 + momentum) * tprev;  angles /= |angles| + 1e-16
+//   return istft(S * angles)
+//
+// As a chain of library calls every iteration walks the (B, 513, T) complex spectrogram about a dozen times
+// (complex multiply, irfft, window, overlap-add, envelope division, padding, framing, rfft, momentum update,
+// abs, divide): 3.3 ms per iteration for 64 utterances x 1304 frames.  Here an iteration is three kernels and
+// roughly two passes over the data:
+//
+//   gl_istft_kernel   one frame PAIR per trip: Z = A + iB (two Hermitian spectra packed into one complex signal, so
+//                     one 1024-point complex FFT inverts both), shared-memory Stockham radix-4 FFT, window, store
+//                     the two windowed frames;
+//   gl_ola_kernel     overlap-add of the 4 frames covering a sample, division by the window sum-square;
+//   gl_stft_kernel    frame pair a + ib gathered from the signal with reflect padding, window, FFT, unpack the two
+//                     spectra, momentum update and phase normalisation fused into the epilogue.
+//
+// Spectra live in a time-major layout (B, T, 513) inside the loop (a frame's bins are contiguous), S and the initial
+// phases are transposed once.  FFT size and hop are the reference's (n_fft = win_length = 1024, hop = 256).
+#include "common.cuh"
+
+namespace ssv {
+
+namespace {
+
+constexpr int GL_N = 1024;          // n_fft = win_length
+constexpr int GL_HOP = 256;
+constexpr int GL_F = GL_N / 2 + 1;  // 513 bins
+constexpr int GL_T = 256;           // threads: one radix-4 butterfly each per pass
+
+struct GlSmem {
+  float2 a[GL_N];
+  float2 b[GL_N];
+  float2 tw[GL_N];                  // e^{-2 pi i k / 1024}
+  float win[GL_N];                  // periodic Hann
+};
+
+__device__ __forceinline__ float2 cmul(float2 x, float2 y) { return make_float2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x); }
+
+__device__ __forceinline__ void gl_tables(GlSmem& sm, int tid) {
+  for (int k = tid; k < GL_N; k += GL_T) {
+    float s, c;
+    sincospif(-2.0f * (float)k / (float)GL_N, &s, &c);
+    sm.tw[k] = make_float2(c, s);
+    sm.win[k] = 0.5f - 0.5f * cospif(2.0f * (float)k / (float)GL_N);
+  }
+}
+
+// 1024-point complex FFT, Stockham autosort radix 4, five passes; input in sm.a, result in sm.b.
+// INV: conjugate twiddles and butterfly (no 1/N scaling here).
+template <bool INV>
+__device__ __forceinline__ void fft1024(GlSmem& sm, int tid) {
+  float2* in = sm.a;
+  float2* out = sm.b;
+#pragma unroll
+  for (int pass = 0; pass < 5; ++pass) {
+    const int Ns = 1 << (2 * pass);
+    const int k = tid & (Ns - 1);
+    const int tstep = (GL_N / 4) >> (2 * pass);           // 1024 / (4 Ns)
+    float2 v0 = in[tid], v1 = in[tid + 256], v2 = in[tid + 512], v3 = in[tid + 768];
+    if (pass > 0) {
+      float2 w1 = sm.tw[k * tstep], w2 = sm.tw[2 * k * tstep], w3 = sm.tw[3 * k * tstep];
+      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
+    }
+    const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+    const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+    const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
+    const float2 t3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);      // +-i (v1 - v3)
+    const int j0 = ((tid - k) << 2) + k;
+    out[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
+    out[j0 + Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
+    out[j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
+    out[j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
+    __syncthreads();
+    float2* tmp = in; in = out; out = tmp;
+  }
+  // five passes: the result sits in the buffer that was `out` in the last pass = sm.b
+}
+
+// (B, F, T) -> (B, T, F): magnitudes and initial phases, once.
+__global__ void gl_setup_kernel(const float* __restrict__ S, const float2* __restrict__ ang0, int B, int T,
+                                float* __restrict__ St, float2* __restrict__ ang) {
+  __shared__ float ts[32][33];
+  __shared__ float2 ta[32][33];
+  const int b = blockIdx.z, f0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int f = f0 + i, t = t0 + threadIdx.x;
+    if (f < GL_F && t < T) {
+      ts[i][threadIdx.x] = S[((long)b * GL_F + f) * T + t];
+      ta[i][threadIdx.x] = ang0[((long)b * GL_F + f) * T + t];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, f = f0 + threadIdx.x;
+    if (f < GL_F && t < T) {
+      St[((long)b * T + t) * GL_F + f] = ts[threadIdx.x][i];
+      ang[((long)b * T + t) * GL_F + f] = ta[threadIdx.x][i];
+    }
+  }
+}
+
+// Inverse STFT of frame pairs: frames[b][t][n] = w[n] * irfft(S[b][t] * ang[b][t])[n].
+__global__ void __launch_bounds__(GL_T) gl_istft_kernel(const float* __restrict__ St, const float2* __restrict__ ang,
+                                                        int T, long n_pairs, int pairs_per_utt,
+                                                        float* __restrict__ frames) {
+  __shared__ GlSmem sm;
+  const int tid = threadIdx.x;
+  gl_tables(sm, tid);
+  __syncthreads();
+  for (long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+    const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
+    const bool second = t + 1 < T;
+    const float* Sa = St + ((long)b * T + t) * GL_F;
+    const float2* Aa = ang + ((long)b * T + t) * GL_F;
+    // Z[k] = A[k] + i B[k] (k <= 512), Z[1024 - k] = conj(A[k]) + i conj(B[k]); irfft ignores Im of bins 0 and 512
+    for (int k = tid; k < GL_F; k += GL_T) {
+      float2 A = Aa[k];
+      const float sa = Sa[k];
+      A = make_float2(A.x * sa, A.y * sa);
+      float2 Bv = make_float2(0.f, 0.f);
+      if (second) {
+        Bv = Aa[GL_F + k];
+        const float sb = Sa[GL_F + k];
+        Bv = make_float2(Bv.x * sb, Bv.y * sb);
+      }
+      if (k == 0 || k == GL_N / 2) { A.y = 0.f; Bv.y = 0.f; }
+      sm.a[k] = make_float2(A.x - Bv.y, A.y + Bv.x);
+      if (k > 0 && k < GL_N / 2) sm.a[GL_N - k] = make_float2(A.x + Bv.y, Bv.x - A.y);
+    }
+    __syncthreads();
+    fft1024<true>(sm, tid);
+    float* fa = frames + ((long)b * T + t) * GL_N;
+    const float sc = 1.0f / (float)GL_N;
+    for (int n = tid; n < GL_N; n += GL_T) {
+      const float2 z = sm.b[n];
+      const float w = sm.win[n] * sc;
+      fa[n] = z.x * w;
+      if (second) fa[GL_N + n] = z.y * w;
+    }
+    __syncthreads();
+  }
+}
+
+// y[b][m] = sum_t frames[b][t][m + 512 - 256 t] / sum_t w^2[m + 512 - 256 t]   (centre trimmed: m in [0, 256 (T - 1)))
+__global__ void gl_ola_kernel(const float* __restrict__ frames, int B, int T, long L, float* __restrict__ y) {
+  const long total = (long)B * L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / L);
+    const long m = i % L;
+    const long p = m + GL_N / 2;
+    const int tq = (int)(p / GL_HOP);
+    float acc = 0.f, wss = 0.f;
+#pragma unroll
+    for (int d = 3; d >= 0; --d) {
+      const int t = tq - d;
+      if (t >= 0 && t < T) {
+        const int n = (int)(p - (long)t * GL_HOP);
+        const float w = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)GL_N);
+        acc += frames[((long)b * T + t) * GL_N + n];
+        wss = fmaf(w, w, wss);
+      }
+    }
+    y[i] = wss > 1.17549435e-38f ? acc / wss : acc;
+  }
+}
+
+// STFT of frame pairs + momentum phase update.  rebuilt -> tprev, angles updated in place.
+__global__ void __launch_bounds__(GL_T) gl_stft_kernel(const float* __restrict__ y, int T, long L, long n_pairs,
+                                                       int pairs_per_utt, float c, int first,
+                                                       float2* __restrict__ ang, float2* __restrict__ tprev) {
+  __shared__ GlSmem sm;
+  const int tid = threadIdx.x;
+  gl_tables(sm, tid);
+  __syncthreads();
+  for (long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+    const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
+    const bool second = t + 1 < T;
+    const float* yb = y + (long)b * L;
+    for (int n = tid; n < GL_N; n += GL_T) {
+      long ma = (long)t * GL_HOP + n - GL_N / 2;           // centre = True, reflect padding
+      long mb = ma + GL_HOP;
+      ma = ma < 0 ? -ma : (ma >= L ? 2 * (L - 1) - ma : ma);
+      mb = mb < 0 ? -mb : (mb >= L ? 2 * (L - 1) - mb : mb);
+      const float w = sm.win[n];
+      sm.a[n] = make_float2(w * yb[ma], second ? w * yb[mb] : 0.f);
+    }
+    __syncthreads();
+    fft1024<false>(sm, tid);
+    float2* Aa = ang + ((long)b * T + t) * GL_F;
+    float2* Pa = tprev + ((long)b * T + t) * GL_F;
+    for (int k = tid; k < GL_F; k += GL_T) {
+      const float2 z = sm.b[k];
+      const float2 zc = sm.b[(GL_N - k) & (GL_N - 1)];       // Z[N - k], conjugated below
+      // A = (Z[k] + conj(Z[N-k])) / 2,  B = (Z[k] - conj(Z[N-k])) / (2i)
+      const float2 A = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+      const float2 Bv = make_float2(0.5f * (z.y + zc.y), 0.5f * (zc.x - z.x));
+      {
+        float2 n_ = A;
+        if (!first) { const float2 pv = Pa[k]; n_ = make_float2(A.x - c * pv.x, A.y - c * pv.y); }
+        const float inv = 1.0f / (sqrtf(n_.x * n_.x + n_.y * n_.y) + 1e-16f);
+        Aa[k] = make_float2(n_.x * inv, n_.y * inv);
+        Pa[k] = A;
+      }
+      if (second) {
+        float2 n_ = Bv;
+        if (!first) { const float2 pv = Pa[GL_F + k]; n_ = make_float2(Bv.x - c * pv.x, Bv.y - c * pv.y); }
+        const float inv = 1.0f / (sqrtf(n_.x * n_.x + n_.y * n_.y) + 1e-16f);
+        Aa[GL_F + k] = make_float2(n_.x * inv, n_.y * inv);
+        Pa[GL_F + k] = Bv;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// St is padded to a multiple of 4 floats so that the complex arrays behind it stay 16-byte aligned
+static size_t st_floats(size_t bt) { return (bt * GL_F + 3) / 4 * 4; }
+
+size_t griffin_lim_workspace_floats(int B, int T) {
+  const size_t bt = (size_t)B * T;
+  return st_floats(bt) /*St*/ + 2 * bt * GL_F /*ang*/ + 2 * bt * GL_F /*tprev*/ + bt * GL_N /*frames*/;
+}
+
+int launch_griffin_lim(const float* S, const float* angles0_ri, int B, int T, int n_iter, float momentum, float* y,
+                       float* workspace, cudaStream_t s) {
+  const size_t bt = (size_t)B * T;
+  float* St = workspace;
+  float2* ang = reinterpret_cast<float2*>(St + st_floats(bt));
+  float2* tprev = ang + bt * GL_F;
+  float* frames = reinterpret_cast<float*>(tprev + bt * GL_F);
+  const long L = (long)GL_HOP * (T - 1);
+  const int pairs_per_utt = (T + 1) / 2;
+  const long n_pairs = (long)B * pairs_per_utt;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int fft_grid = (int)(n_pairs < (long)sms * 6 ? n_pairs : (long)sms * 6);
+  long ola_blocks = ((long)B * L + 255) / 256;
+  if (ola_blocks > (long)sms * 32) ola_blocks = (long)sms * 32;
+  const float c = momentum / (1.0f + momentum);
+
+  gl_setup_kernel<<<dim3((T + 31) / 32, (GL_F + 31) / 32, B), dim3(32, 8), 0, s>>>(
+      S, reinterpret_cast<const float2*>(angles0_ri), B, T, St, ang);
+  SSV_CUDA(cudaGetLastError());
+  ++g_launches;
+  for (int it = 0; it <= n_iter; ++it) {
+    gl_istft_kernel<<<fft_grid, GL_T, 0, s>>>(St, ang, T, n_pairs, pairs_per_utt, frames);
+    gl_ola_kernel<<<(int)ola_blocks, 256, 0, s>>>(frames, B, T, L, y);
+    g_launches += 2;
+    if (it == n_iter) break;
+    gl_stft_kernel<<<fft_grid, GL_T, 0, s>>>(y, T, L, n_pairs, pairs_per_utt, c, it == 0 ? 1 : 0, ang, tprev);
+    ++g_launches;
+  }
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace ssv

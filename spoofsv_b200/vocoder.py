@@ -2,9 +2,10 @@
 
 generate_test_utterances.py:130-139 / synthesize.py:134-147 run, per utterance and on one CPU thread:
 max-normalise, `** (RECONSTRUCTION / ANALYSIS)`, 64 iterations of librosa's fast Griffin-Lim (n_fft 1024, hop 256),
-de-emphasis, trim (30 dB), 9 s cap, peak 0.75, wav.  Here the whole batch is processed at once: batched
-STFT / ISTFT (cuFFT through torch.stft / torch.istft -- library FFTs, as librosa's are), the phase update in torch
-element-wise ops, de-emphasis in the library's own scan kernel (`ssv_deemphasis`), trim bounds from framed RMS.
+de-emphasis, trim (30 dB), 9 s cap, peak 0.75, wav.  Here the whole batch is processed at once: Griffin-Lim in
+the library's fused kernels (`ssv_griffin_lim`: shared-memory FFTs, overlap-add, momentum phase update; a chain of
+torch.stft / torch.istft calls remains as the path for other STFT shapes and as a cross-check), de-emphasis in the
+library's own scan kernel (`ssv_deemphasis`), trim bounds from framed RMS.
 librosa seeds the phases from numpy's global RNG, so a reference run is not reproducible sample by sample;
 `angles0` makes this implementation comparable with the CPU restatement in oracle/vocoder_oracle.py.
 """
@@ -19,20 +20,39 @@ from . import _lib
 
 
 def griffin_lim(S: torch.Tensor, n_iter: int = 64, hop: int = 256, win_length: int = 1024, momentum: float = 0.99,
-                angles0: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+                angles0: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None,
+                fused: Optional[bool] = None) -> torch.Tensor:
     """(B, 1 + n_fft/2, frames) magnitudes on the GPU -> (B, hop * (frames - 1)) samples.
-    librosa.core.griffinlim (0.7): momentum 0.99, hann window, centred reflect-padded frames."""
+    librosa.core.griffinlim (0.7): momentum 0.99, hann window, centred reflect-padded frames.
+
+    The reference's STFT shape (n_fft = win_length = 1024, hop = 256) runs in the library's fused kernels
+    (`ssv_griffin_lim`, csrc/griffinlim.cu: shared-memory FFTs on frame pairs, momentum update in the STFT epilogue);
+    other shapes, or fused=False, take the chain of torch.stft / torch.istft calls (cuFFT)."""
     _lib.require_cuda(S, "griffin_lim")
     B, F, T = S.shape
     n_fft = 2 * (F - 1)
-    window = torch.hann_window(win_length, periodic=True, device=S.device, dtype=torch.float32)
     if angles0 is None:
         ph = torch.rand((B, F, T), device=S.device, generator=generator) * (2.0 * np.pi)
         angles = torch.polar(torch.ones_like(ph), ph)
     else:
         angles = angles0.to(device=S.device, dtype=torch.complex64)
-    S = S.to(torch.float32)
+    S = S.to(torch.float32).contiguous()
     length = hop * (T - 1)
+    can_fuse = n_fft == 1024 and hop == 256 and win_length == 1024 and T >= 3
+    if fused is None:
+        fused = can_fuse
+    if fused:
+        if not can_fuse:
+            raise ValueError("griffin_lim: the fused kernels are built for n_fft = win_length = 1024, hop = 256 only")
+        lib = _lib.load()
+        n_ws = int(lib.ssv_griffin_lim_workspace(B, T))
+        ws = torch.empty(n_ws, device=S.device, dtype=torch.float32)
+        y = torch.empty((B, length), device=S.device, dtype=torch.float32)
+        a_ri = torch.view_as_real(angles.contiguous())
+        _lib.check(lib.ssv_griffin_lim(S.data_ptr(), a_ri.data_ptr(), B, F, T, int(n_iter), hop, win_length,
+                                       float(momentum), y.data_ptr(), ws.data_ptr(), n_ws, _lib.current_stream_ptr()))
+        return y
+    window = torch.hann_window(win_length, periodic=True, device=S.device, dtype=torch.float32)
     istft = lambda D: torch.istft(D, n_fft, hop_length=hop, win_length=win_length, window=window, center=True, length=length)
     rebuilt = None
     c = momentum / (1.0 + momentum)

@@ -52,12 +52,24 @@ def test_gpu_waveform_stage_matches_oracle():
     rng = np.random.default_rng(2)
     specs = np.stack([_spec(rng, 36), _spec(rng, 36)])
     a0 = np.exp(2j * np.pi * rng.random(specs.shape))
-    # Griffin-Lim alone, same initial phases: sample-level agreement (fp32 cuFFT vs float64 numpy, 16 iterations)
-    y = G.griffin_lim(torch.from_numpy(specs).float().cuda(), n_iter=16, angles0=torch.from_numpy(a0)).cpu().numpy()
-    for k in range(2):
-        want = V.griffinlim(specs[k], a0[k], n_iter=16)
-        assert y[k].shape == want.shape
-        assert np.abs(y[k] - want).max() <= 2e-3 * np.abs(want).max()
+    # Griffin-Lim alone, same initial phases: sample-level agreement (fp32 FFTs vs float64 numpy, 16 iterations),
+    # for the fused kernels and for the chain of library FFT calls
+    for fused in (True, False):
+        y = G.griffin_lim(torch.from_numpy(specs).float().cuda(), n_iter=16, angles0=torch.from_numpy(a0), fused=fused).cpu().numpy()
+        for k in range(2):
+            want = V.griffinlim(specs[k], a0[k], n_iter=16)
+            assert y[k].shape == want.shape
+            assert np.abs(y[k] - want).max() <= 2e-3 * np.abs(want).max()
+    # zero iterations = one inverse STFT; an odd frame count leaves the last frame without a partner
+    for T in (35, 36, 3):
+        sp = np.stack([_spec(rng, 36)[:, :T]])
+        ph = np.exp(2j * np.pi * rng.random(sp.shape))
+        y0 = G.griffin_lim(torch.from_numpy(sp).float().cuda(), n_iter=0, angles0=torch.from_numpy(ph)).cpu().numpy()[0]
+        want0 = V.istft(sp[0] * ph[0], 256, 1024)
+        assert y0.shape == want0.shape and np.abs(y0 - want0).max() <= 1e-5 * max(np.abs(want0).max(), 1e-3)
+        y3 = G.griffin_lim(torch.from_numpy(sp).float().cuda(), n_iter=3, angles0=torch.from_numpy(ph)).cpu().numpy()[0]
+        want3 = V.griffinlim(sp[0], ph[0], n_iter=3)
+        assert np.abs(y3 - want3).max() <= 1e-3 * np.abs(want3).max()
     # de-emphasis scan kernel: long rows, several blocks, in agreement with lfilter
     x = rng.standard_normal((3, 333568)).astype(np.float32)
     got = G.deemphasis(torch.from_numpy(x).cuda(), 0.97).cpu().numpy()

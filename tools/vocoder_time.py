@@ -11,3 +11,9 @@ for rep in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     w = G.postprocess(lin, cfg)
     torch.cuda.synchronize(); print(f"postprocess 64 x 1304 frames: {1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
+S = (lin / lin.amax(dim=(1, 2), keepdim=True)).pow(1.3 / 0.6)
+for fused in (True, False):
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        y = G.griffin_lim(S, 64, fused=fused)
+        torch.cuda.synchronize(); print(f"griffin_lim fused={fused}: {1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
