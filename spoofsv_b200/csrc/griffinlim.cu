@@ -30,25 +30,32 @@ constexpr int GL_HOP = 256;
 constexpr int GL_F = GL_N / 2 + 1;  // 513 bins
 constexpr int GL_T = 256;           // threads: one radix-4 butterfly each per pass
 
+// Shared-memory FFT buffers are padded by one element per 16 (index i lives at i + i / 16): the radix-4 stores of the
+// first two passes (stride 4 and 16 elements between neighbouring lanes) would otherwise be 4-way bank conflicts.
+constexpr int GL_PAD = GL_N + GL_N / 16;
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+
 struct GlSmem {
-  float2 a[GL_N];
-  float2 b[GL_N];
-  float2 tw[GL_N];                  // e^{-2 pi i k / 1024}
+  float2 a[GL_PAD];
+  float2 b[GL_PAD];
+  float2 tw[4 + 16 + 64 + 256];     // per pass p = 1..4 (Ns = 4^p): e^{-2 pi i k / (4 Ns)}, k < Ns, stored contiguously
   float win[GL_N];                  // periodic Hann
 };
 
 __device__ __forceinline__ float2 cmul(float2 x, float2 y) { return make_float2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x); }
 
 __device__ __forceinline__ void gl_tables(GlSmem& sm, int tid) {
-  for (int k = tid; k < GL_N; k += GL_T) {
+  for (int k = tid; k < GL_N; k += GL_T) sm.win[k] = 0.5f - 0.5f * cospif(2.0f * (float)k / (float)GL_N);
+  for (int i = tid; i < 4 + 16 + 64 + 256; i += GL_T) {
+    const int Ns = i < 4 ? 4 : i < 20 ? 16 : i < 84 ? 64 : 256;
+    const int k = i - (Ns == 4 ? 0 : Ns == 16 ? 4 : Ns == 64 ? 20 : 84);
     float s, c;
-    sincospif(-2.0f * (float)k / (float)GL_N, &s, &c);
-    sm.tw[k] = make_float2(c, s);
-    sm.win[k] = 0.5f - 0.5f * cospif(2.0f * (float)k / (float)GL_N);
+    sincospif(-2.0f * (float)k / (float)(4 * Ns), &s, &c);
+    sm.tw[i] = make_float2(c, s);
   }
 }
 
-// 1024-point complex FFT, Stockham autosort radix 4, five passes; input in sm.a, result in sm.b.
+// 1024-point complex FFT, Stockham autosort radix 4, five passes; input in sm.a, result in sm.b (padded indexing).
 // INV: conjugate twiddles and butterfly (no 1/N scaling here).
 template <bool INV>
 __device__ __forceinline__ void fft1024(GlSmem& sm, int tid) {
@@ -58,11 +65,12 @@ __device__ __forceinline__ void fft1024(GlSmem& sm, int tid) {
   for (int pass = 0; pass < 5; ++pass) {
     const int Ns = 1 << (2 * pass);
     const int k = tid & (Ns - 1);
-    const int tstep = (GL_N / 4) >> (2 * pass);           // 1024 / (4 Ns)
-    float2 v0 = in[tid], v1 = in[tid + 256], v2 = in[tid + 512], v3 = in[tid + 768];
+    float2 v0 = in[pidx(tid)], v1 = in[pidx(tid + 256)], v2 = in[pidx(tid + 512)], v3 = in[pidx(tid + 768)];
     if (pass > 0) {
-      float2 w1 = sm.tw[k * tstep], w2 = sm.tw[2 * k * tstep], w3 = sm.tw[3 * k * tstep];
-      if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      const int base = pass == 1 ? 0 : pass == 2 ? 4 : pass == 3 ? 20 : 84;
+      float2 w1 = sm.tw[base + k];
+      if (INV) w1.y = -w1.y;
+      const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
       v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3);
     }
     const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
@@ -70,10 +78,10 @@ __device__ __forceinline__ void fft1024(GlSmem& sm, int tid) {
     const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
     const float2 t3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);      // +-i (v1 - v3)
     const int j0 = ((tid - k) << 2) + k;
-    out[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-    out[j0 + Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
-    out[j0 + 2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
-    out[j0 + 3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
+    out[pidx(j0)] = make_float2(t0.x + t2.x, t0.y + t2.y);
+    out[pidx(j0 + Ns)] = make_float2(t1.x + t3.x, t1.y + t3.y);
+    out[pidx(j0 + 2 * Ns)] = make_float2(t0.x - t2.x, t0.y - t2.y);
+    out[pidx(j0 + 3 * Ns)] = make_float2(t1.x - t3.x, t1.y - t3.y);
     __syncthreads();
     float2* tmp = in; in = out; out = tmp;
   }
@@ -104,39 +112,64 @@ __global__ void gl_setup_kernel(const float* __restrict__ S, const float2* __res
 }
 
 // Inverse STFT of frame pairs: frames[b][t][n] = w[n] * irfft(S[b][t] * ang[b][t])[n].
+// The spectra of the next pair are fetched into registers before the FFT passes of the current one.
+struct IstftRegs {
+  float2 A[3], Bv[3];      // bins tid, tid + 256, (tid == 0: 512) of the two frames, already scaled by S
+};
+
+__device__ __forceinline__ void istft_fetch(IstftRegs& r, const float* __restrict__ St, const float2* __restrict__ ang,
+                                            int T, long pr, int pairs_per_utt, int tid) {
+  const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
+  const bool second = t + 1 < T;
+  const float* Sa = St + ((long)b * T + t) * GL_F;
+  const float2* Aa = ang + ((long)b * T + t) * GL_F;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int k = tid + GL_T * i;
+    r.A[i] = r.Bv[i] = make_float2(0.f, 0.f);
+    if (k < GL_F && (i < 2 || tid == 0)) {
+      const float2 a = Aa[k];
+      const float sa = Sa[k];
+      r.A[i] = make_float2(a.x * sa, a.y * sa);
+      if (second) {
+        const float2 bb = Aa[GL_F + k];
+        const float sb = Sa[GL_F + k];
+        r.Bv[i] = make_float2(bb.x * sb, bb.y * sb);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(GL_T) gl_istft_kernel(const float* __restrict__ St, const float2* __restrict__ ang,
                                                         int T, long n_pairs, int pairs_per_utt,
                                                         float* __restrict__ frames) {
   __shared__ GlSmem sm;
   const int tid = threadIdx.x;
   gl_tables(sm, tid);
+  IstftRegs cur;
+  if ((long)blockIdx.x < n_pairs) istft_fetch(cur, St, ang, T, blockIdx.x, pairs_per_utt, tid);
   __syncthreads();
   for (long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
     const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
     const bool second = t + 1 < T;
-    const float* Sa = St + ((long)b * T + t) * GL_F;
-    const float2* Aa = ang + ((long)b * T + t) * GL_F;
     // Z[k] = A[k] + i B[k] (k <= 512), Z[1024 - k] = conj(A[k]) + i conj(B[k]); irfft ignores Im of bins 0 and 512
-    for (int k = tid; k < GL_F; k += GL_T) {
-      float2 A = Aa[k];
-      const float sa = Sa[k];
-      A = make_float2(A.x * sa, A.y * sa);
-      float2 Bv = make_float2(0.f, 0.f);
-      if (second) {
-        Bv = Aa[GL_F + k];
-        const float sb = Sa[GL_F + k];
-        Bv = make_float2(Bv.x * sb, Bv.y * sb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = tid + GL_T * i;
+      if (i < 2 || tid == 0) {
+        float2 A = cur.A[i], Bv = cur.Bv[i];
+        if (k == 0 || k == GL_N / 2) { A.y = 0.f; Bv.y = 0.f; }
+        sm.a[pidx(k)] = make_float2(A.x - Bv.y, A.y + Bv.x);
+        if (k > 0 && k < GL_N / 2) sm.a[pidx(GL_N - k)] = make_float2(A.x + Bv.y, Bv.x - A.y);
       }
-      if (k == 0 || k == GL_N / 2) { A.y = 0.f; Bv.y = 0.f; }
-      sm.a[k] = make_float2(A.x - Bv.y, A.y + Bv.x);
-      if (k > 0 && k < GL_N / 2) sm.a[GL_N - k] = make_float2(A.x + Bv.y, Bv.x - A.y);
     }
     __syncthreads();
+    if (pr + gridDim.x < n_pairs) istft_fetch(cur, St, ang, T, pr + gridDim.x, pairs_per_utt, tid);   // lands under the FFT
     fft1024<true>(sm, tid);
     float* fa = frames + ((long)b * T + t) * GL_N;
     const float sc = 1.0f / (float)GL_N;
     for (int n = tid; n < GL_N; n += GL_T) {
-      const float2 z = sm.b[n];
+      const float2 z = sm.b[pidx(n)];
       const float w = sm.win[n] * sc;
       fa[n] = z.x * w;
       if (second) fa[GL_N + n] = z.y * w;
@@ -146,25 +179,37 @@ __global__ void __launch_bounds__(GL_T) gl_istft_kernel(const float* __restrict_
 }
 
 // y[b][m] = sum_t frames[b][t][m + 512 - 256 t] / sum_t w^2[m + 512 - 256 t]   (centre trimmed: m in [0, 256 (T - 1)))
+// Four consecutive samples per thread (L is a multiple of 256, so a float4 never straddles a hop or an utterance).
 __global__ void gl_ola_kernel(const float* __restrict__ frames, int B, int T, long L, float* __restrict__ y) {
-  const long total = (long)B * L;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  const long total4 = (long)B * L / 4;
+  for (long i4 = blockIdx.x * (long)blockDim.x + threadIdx.x; i4 < total4; i4 += (long)gridDim.x * blockDim.x) {
+    const long i = i4 * 4;
     const int b = (int)(i / L);
     const long m = i % L;
     const long p = m + GL_N / 2;
     const int tq = (int)(p / GL_HOP);
-    float acc = 0.f, wss = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), wss = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool interior = tq >= 3 && tq < T;            // all four frames exist: Hann^2 at 75 % overlap sums to 1.5
 #pragma unroll
     for (int d = 3; d >= 0; --d) {
       const int t = tq - d;
       if (t >= 0 && t < T) {
         const int n = (int)(p - (long)t * GL_HOP);
-        const float w = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)GL_N);
-        acc += frames[((long)b * T + t) * GL_N + n];
-        wss = fmaf(w, w, wss);
+        const float4 f = *reinterpret_cast<const float4*>(frames + ((long)b * T + t) * GL_N + n);
+        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+        if (!interior) {
+          const float w0 = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)GL_N);
+          const float w1 = 0.5f - 0.5f * cospif(2.0f * (float)(n + 1) / (float)GL_N);
+          const float w2 = 0.5f - 0.5f * cospif(2.0f * (float)(n + 2) / (float)GL_N);
+          const float w3 = 0.5f - 0.5f * cospif(2.0f * (float)(n + 3) / (float)GL_N);
+          wss.x = fmaf(w0, w0, wss.x); wss.y = fmaf(w1, w1, wss.y); wss.z = fmaf(w2, w2, wss.z); wss.w = fmaf(w3, w3, wss.w);
+        }
       }
     }
-    y[i] = wss > 1.17549435e-38f ? acc / wss : acc;
+    if (interior) wss = make_float4(1.5f, 1.5f, 1.5f, 1.5f);
+    const float tiny = 1.17549435e-38f;
+    *reinterpret_cast<float4*>(y + i) = make_float4(wss.x > tiny ? acc.x / wss.x : acc.x, wss.y > tiny ? acc.y / wss.y : acc.y,
+                                                    wss.z > tiny ? acc.z / wss.z : acc.z, wss.w > tiny ? acc.w / wss.w : acc.w);
   }
 }
 
@@ -176,41 +221,68 @@ __global__ void __launch_bounds__(GL_T) gl_stft_kernel(const float* __restrict__
   const int tid = threadIdx.x;
   gl_tables(sm, tid);
   __syncthreads();
-  for (long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+  auto fetch = [&](long pr, float (&ya)[4], float (&yb2)[4]) {
     const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
     const bool second = t + 1 < T;
     const float* yb = y + (long)b * L;
-    for (int n = tid; n < GL_N; n += GL_T) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = tid + GL_T * i;
       long ma = (long)t * GL_HOP + n - GL_N / 2;           // centre = True, reflect padding
       long mb = ma + GL_HOP;
       ma = ma < 0 ? -ma : (ma >= L ? 2 * (L - 1) - ma : ma);
       mb = mb < 0 ? -mb : (mb >= L ? 2 * (L - 1) - mb : mb);
+      ya[i] = yb[ma];
+      yb2[i] = second ? yb[mb] : 0.f;
+    }
+  };
+  float ca[4], cb[4];
+  if ((long)blockIdx.x < n_pairs) fetch(blockIdx.x, ca, cb);
+  for (long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+    const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
+    const bool second = t + 1 < T;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = tid + GL_T * i;
       const float w = sm.win[n];
-      sm.a[n] = make_float2(w * yb[ma], second ? w * yb[mb] : 0.f);
+      sm.a[pidx(n)] = make_float2(w * ca[i], w * cb[i]);
     }
     __syncthreads();
-    fft1024<false>(sm, tid);
+    if (pr + gridDim.x < n_pairs) fetch(pr + gridDim.x, ca, cb);      // lands under the FFT
     float2* Aa = ang + ((long)b * T + t) * GL_F;
     float2* Pa = tprev + ((long)b * T + t) * GL_F;
-    for (int k = tid; k < GL_F; k += GL_T) {
-      const float2 z = sm.b[k];
-      const float2 zc = sm.b[(GL_N - k) & (GL_N - 1)];       // Z[N - k], conjugated below
-      // A = (Z[k] + conj(Z[N-k])) / 2,  B = (Z[k] - conj(Z[N-k])) / (2i)
-      const float2 A = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
-      const float2 Bv = make_float2(0.5f * (z.y + zc.y), 0.5f * (zc.x - z.x));
-      {
-        float2 n_ = A;
-        if (!first) { const float2 pv = Pa[k]; n_ = make_float2(A.x - c * pv.x, A.y - c * pv.y); }
-        const float inv = 1.0f / (sqrtf(n_.x * n_.x + n_.y * n_.y) + 1e-16f);
-        Aa[k] = make_float2(n_.x * inv, n_.y * inv);
-        Pa[k] = A;
+    float2 pva[3], pvb[3];                                           // previous spectra of my bins: fetched under the FFT too
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = tid + GL_T * i;
+      pva[i] = pvb[i] = make_float2(0.f, 0.f);
+      if (!first && (i < 2 || tid == 0)) {
+        pva[i] = Pa[k];
+        if (second) pvb[i] = Pa[GL_F + k];
       }
-      if (second) {
-        float2 n_ = Bv;
-        if (!first) { const float2 pv = Pa[GL_F + k]; n_ = make_float2(Bv.x - c * pv.x, Bv.y - c * pv.y); }
-        const float inv = 1.0f / (sqrtf(n_.x * n_.x + n_.y * n_.y) + 1e-16f);
-        Aa[GL_F + k] = make_float2(n_.x * inv, n_.y * inv);
-        Pa[GL_F + k] = Bv;
+    }
+    fft1024<false>(sm, tid);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = tid + GL_T * i;
+      if (i < 2 || tid == 0) {
+        const float2 z = sm.b[pidx(k)];
+        const float2 zc = sm.b[pidx((GL_N - k) & (GL_N - 1))];       // Z[N - k], conjugated below
+        // A = (Z[k] + conj(Z[N-k])) / 2,  B = (Z[k] - conj(Z[N-k])) / (2i)
+        const float2 A = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+        const float2 Bv = make_float2(0.5f * (z.y + zc.y), 0.5f * (zc.x - z.x));
+        {
+          const float2 n_ = make_float2(A.x - c * pva[i].x, A.y - c * pva[i].y);
+          const float inv = 1.0f / (sqrtf(n_.x * n_.x + n_.y * n_.y) + 1e-16f);
+          Aa[k] = make_float2(n_.x * inv, n_.y * inv);
+          Pa[k] = A;
+        }
+        if (second) {
+          const float2 n_ = make_float2(Bv.x - c * pvb[i].x, Bv.y - c * pvb[i].y);
+          const float inv = 1.0f / (sqrtf(n_.x * n_.x + n_.y * n_.y) + 1e-16f);
+          Aa[GL_F + k] = make_float2(n_.x * inv, n_.y * inv);
+          Pa[GL_F + k] = Bv;
+        }
       }
     }
     __syncthreads();
@@ -240,7 +312,7 @@ int launch_griffin_lim(const float* S, const float* angles0_ri, int B, int T, in
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int fft_grid = (int)(n_pairs < (long)sms * 6 ? n_pairs : (long)sms * 6);
-  long ola_blocks = ((long)B * L + 255) / 256;
+  long ola_blocks = ((long)B * L / 4 + 255) / 256;
   if (ola_blocks > (long)sms * 32) ola_blocks = (long)sms * 32;
   const float c = momentum / (1.0f + momentum);
 
