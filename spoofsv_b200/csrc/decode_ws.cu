@@ -56,11 +56,11 @@ constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks
 constexpr unsigned FULL = 0xffffffffu;
 
 // shared-memory carve-up (floats)
-constexpr int XROWS = 3 * TAPP;                    // rows of one X buffer ([rows][RT] floats)
-constexpr int XREGION = 8 * XROWS;                 // 8 / RT buffers: 8 (RT = 1), 4 (RT = 2), 2 (RT = 4)
+constexpr int XROWS = 3 * TAPP;                    // rows of one X buffer ([rows][RT] activations; RT = 1 stores each as (x, x))
+constexpr int XREGION = 2 * 8 * XROWS;             // floats; 8 / RT buffers: 8 (RT = 1, two floats each), 4 (RT = 2), 2 (RT = 4)
 constexpr int MAXBUF = 8;
 constexpr int SM_WSM = 0;                          // [11][384] float4: tap-0 weights of a highway CTA
-constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [8 / RT][XROWS][RT]
+constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [8 / RT][XROWS][RT * XLayout<RT>::D]
 constexpr int SM_PART = SM_X + XREGION;            // [12][RT][ncol <= 128] k-slice partial sums
 constexpr int SM_REC = SM_PART + 12 * 4 * 128;     // [24 / RT][RT][256] stage inputs of the most recent visits (short-distance taps)
 constexpr int SM_LN = SM_REC + 24 * HD;            // [4][256] LayerNorm parameters of my prologue
@@ -193,33 +193,39 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float rstd_fast(float var) { return rsqrtf(var + 1e-5f); }
 
-template <int RT> struct XVec;
-template <> struct XVec<1> {
-  static __device__ __forceinline__ void ld(const float* p, float (&x)[1]) { x[0] = *p; }
-};
-template <> struct XVec<2> {
-  static __device__ __forceinline__ void ld(const float* p, float (&x)[2]) {
-    const float2 v = *reinterpret_cast<const float2*>(p);
-    x[0] = v.x; x[1] = v.y;
-  }
-};
-template <> struct XVec<4> {
-  static __device__ __forceinline__ void ld(const float* p, float (&x)[4]) {
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-  }
-};
+// One k row of the mat-vec tile: acc[r][0..3] += x[r] * w[0..3] for the RT rows of the micro-batch.
+// RT = 1 (latency mode) uses packed FMAs (fma.rn.f32x2: two independent IEEE fp32 FMAs per instruction,
+// bit-identical to fmaf): the accumulators are column pairs, the weights are the halves of the thread's float4 and X
+// holds every activation twice, (x, x), so the multiplicand needs no shuffling -- 2 FMA instructions + one LDS.64
+// per row instead of 4 + 1.  Measured: B = 1 30.0 -> 28.9 us/frame.  With 2 or 4 rows per micro-batch the mat-vec
+// phases are bound by the FMA pipe, where the packed form is ~9 % slower than scalar FFMA (B = 64: 53.7 -> 58
+// us/frame), so those shapes keep scalar FMAs and the plain X layout.
+template <int RT> struct XLayout { static constexpr int D = RT == 1 ? 2 : 1; };   // floats per stored activation
 
 template <int RT>
 __device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, const float* xp) {
-  float x[RT];
-  XVec<RT>::ld(xp, x);
+  if constexpr (RT == 1) {
+    const float2 x = *reinterpret_cast<const float2*>(xp);                         // (x, x)
+    float2 a01 = make_float2(acc[0][0], acc[0][1]), a23 = make_float2(acc[0][2], acc[0][3]);
+    a01 = __ffma2_rn(x, make_float2(w.x, w.y), a01);
+    a23 = __ffma2_rn(x, make_float2(w.z, w.w), a23);
+    acc[0][0] = a01.x; acc[0][1] = a01.y; acc[0][2] = a23.x; acc[0][3] = a23.y;
+  } else {
+    float x[RT];
+    if constexpr (RT == 2) {
+      const float2 v = *reinterpret_cast<const float2*>(xp);
+      x[0] = v.x; x[1] = v.y;
+    } else {
+      const float4 v = *reinterpret_cast<const float4*>(xp);
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    acc[r][0] = fmaf(x[r], w.x, acc[r][0]);
-    acc[r][1] = fmaf(x[r], w.y, acc[r][1]);
-    acc[r][2] = fmaf(x[r], w.z, acc[r][2]);
-    acc[r][3] = fmaf(x[r], w.w, acc[r][3]);
+    for (int r = 0; r < RT; ++r) {
+      acc[r][0] = fmaf(x[r], w.x, acc[r][0]);
+      acc[r][1] = fmaf(x[r], w.y, acc[r][1]);
+      acc[r][2] = fmaf(x[r], w.z, acc[r][2]);
+      acc[r][3] = fmaf(x[r], w.w, acc[r][3]);
+    }
   }
 }
 
@@ -281,7 +287,8 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
     for (int g = 0; g < c.G; ++g, ++v) {
       const int q = v % NBUF;
       const unsigned par = (unsigned)(v / NBUF) & 1u;
-      const float* X = c.smem + SM_X + q * (XROWS * RT) + ks * RT;
+      constexpr int XS = RT * XLayout<RT>::D;          // floats per X row
+      const float* X = c.smem + SM_X + q * (XROWS * XS) + ks * XS;
       // publisher threads: the hoisted speaker projection of my output is fetched now, not after the mat-vec
       const int row0 = g * RT;
       float sb[(RT * NCOL + GV_T - 1) / GV_T];
@@ -307,21 +314,21 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
         // budget allows (back to back, every other tile stalled on its fetch: 18 % of all samples short-scoreboard)
 #pragma unroll
         for (int j = 0; j < 11; ++j) {
-          fma_tile<RT>(acc, wsm[j * GV_T], X + (size_t)(KS * j) * RT);
-          fma_tile<RT>(acc, w[j], X + (size_t)(TAPP + KS * j) * RT);
+          fma_tile<RT>(acc, wsm[j * GV_T], X + (size_t)(KS * j) * XS);
+          fma_tile<RT>(acc, w[j], X + (size_t)(TAPP + KS * j) * XS);
         }
         PROF_G(1);
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);
         if (PROF && prof_on) wake_acc += prof_last - c.t_seen[8 + q];
 #pragma unroll
-        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[11 + j], X + (size_t)(2 * TAPP + KS * j) * RT);
+        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[11 + j], X + (size_t)(2 * TAPP + KS * j) * XS);
       } else {
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);
 #pragma unroll
         for (int j = 0; j < 22; ++j)
-          if (j < st.nj) fma_tile<RT>(acc, w[j], X + (size_t)(KS * j) * RT);
+          if (j < st.nj) fma_tile<RT>(acc, w[j], X + (size_t)(KS * j) * XS);
       }
       // k-slices -> shared memory
       bool writer = true;
@@ -475,15 +482,27 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     prof_last = now_;                              \
   }
 
-  // LayerNorm parameters of my channels (fixed for the whole launch)
+  // LayerNorm parameters of my channels (fixed for the whole launch): in registers when a lane owns 2 or 4
+  // channels; with 8 channels per lane (W = 1) 32 more live registers spill, so they stay in shared memory
+  constexpr bool LNREG = NP <= 2;
   float2 G1[NP], B1[NP], G2[NP], B2[NP];
+  if (LNREG) {
 #pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    G1[i] = *reinterpret_cast<const float2*>(g1 + cb + 64 * i);
-    B1[i] = *reinterpret_cast<const float2*>(b1 + cb + 64 * i);
-    G2[i] = *reinterpret_cast<const float2*>(g2 + cb + 64 * i);
-    B2[i] = *reinterpret_cast<const float2*>(b2 + cb + 64 * i);
+    for (int i = 0; i < NP; ++i) {
+      G1[i] = *reinterpret_cast<const float2*>(g1 + cb + 64 * i);
+      B1[i] = *reinterpret_cast<const float2*>(b1 + cb + 64 * i);
+      G2[i] = *reinterpret_cast<const float2*>(g2 + cb + 64 * i);
+      B2[i] = *reinterpret_cast<const float2*>(b2 + cb + 64 * i);
+    }
   }
+  auto lnp1 = [&](int i, float2& gg, float2& bb) {
+    if (LNREG) { gg = G1[i]; bb = B1[i]; }
+    else { gg = *reinterpret_cast<const float2*>(g1 + cb + 64 * i); bb = *reinterpret_cast<const float2*>(b1 + cb + 64 * i); }
+  };
+  auto lnp2 = [&](int i, float2& gg, float2& bb) {
+    if (LNREG) { gg = G2[i]; bb = B2[i]; }
+    else { gg = *reinterpret_cast<const float2*>(g2 + cb + 64 * i); bb = *reinterpret_cast<const float2*>(b2 + cb + 64 * i); }
+  };
 
   float2 tp[2][NP];
   bool have_pref = false, bad = false;
@@ -497,7 +516,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     const bool need_wait = !(s == 0 && step == 0);
     const int q = v % NBUF;
     const int u = v / NBUF;
-    float* X = c.smem + SM_X + q * (XROWS * RT);
+    float* X = c.smem + SM_X + q * (XROWS * RT * XLayout<RT>::D);
     const int row0 = g * RT;
     const bool live = row0 + r < B;
     const int b = row0 + r;
@@ -538,9 +557,12 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          float* xp = X + ((size_t)j * TAPP + cb + 64 * i) * RT + r;
-          if (RT == 1) *reinterpret_cast<float2*>(xp) = tp[j][i];
-          else { xp[0] = tp[j][i].x; xp[RT] = tp[j][i].y; }
+          if (RT == 1) {
+            *reinterpret_cast<float4*>(X + ((size_t)j * TAPP + cb + 64 * i) * 2) = make_float4(tp[j][i].x, tp[j][i].x, tp[j][i].y, tp[j][i].y);
+          } else {
+            float* xp = X + ((size_t)j * TAPP + cb + 64 * i) * RT + r;
+            xp[0] = tp[j][i].x; xp[RT] = tp[j][i].y;
+          }
         }
       __syncwarp();
       if (lane == 0) mbar_arrive(&c.tapsfull[q]);
@@ -569,15 +591,21 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     float2 o[NP];                                          // my slice of the stage input (joins the rings below)
 #pragma unroll
     for (int i = 0; i < NP; ++i) o[i] = make_float2(0.f, 0.f);
-    float* xcur = X + (size_t)koff * RT + r;               // channel ch at xcur[ch * RT]
+    constexpr int XS = RT * XLayout<RT>::D;               // floats per X row
+    float* xcur = X + (size_t)koff * XS + r;               // channel ch at xcur[ch * XS] (RT = 1: as the pair (x, x))
     auto xstore = [&](int ch, float2 val) {
-      float* xp = xcur + (size_t)ch * RT;
-      if (RT == 1) *reinterpret_cast<float2*>(xp) = val;
+      float* xp = xcur + (size_t)ch * XS;
+      if (RT == 1) *reinterpret_cast<float4*>(xp) = make_float4(val.x, val.x, val.y, val.y);
       else { xp[0] = val.x; xp[RT] = val.y; }
+    };
+    auto xstore1 = [&](int ch, float val) {
+      float* xp = xcur + (size_t)ch * XS;
+      if (RT == 1) *reinterpret_cast<float2*>(xp) = make_float2(val, val);
+      else xp[0] = val;
     };
     if (!live) {
       if (!final_visit)
-        for (int ch = lane + 32 * sub; ch < st.k_seg; ch += 32 * WPR) xcur[(size_t)ch * RT] = 0.f;
+        for (int ch = lane + 32 * sub; ch < st.k_seg; ch += 32 * WPR) xstore1(ch, 0.f);
     } else if (pro == PRO_X && sub != 0) {
       // 80 mel channels: the first warp of the row does them alone
     } else {
@@ -642,7 +670,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int f = lane + 32 * i;
-            if (f < p.F) xcur[(size_t)f * RT] = y[i];
+            if (f < p.F) xstore1(f, y[i]);
           }
         }
       } else if (pro == PRO_LN || pro == PRO_LN_RELU) {
@@ -678,8 +706,10 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           const int ch = cb + 64 * i;
-          float o0 = (vv[i].x - mean) * rstd * G1[i].x + B1[i].x;
-          float o1 = (vv[i].y - mean) * rstd * G1[i].y + B1[i].y;
+          float2 ga, ba;
+          lnp1(i, ga, ba);
+          float o0 = (vv[i].x - mean) * rstd * ga.x + ba.x;
+          float o1 = (vv[i].y - mean) * rstd * ga.y + ba.y;
           if (pro == PRO_LN_RELU) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
           o[i] = make_float2(o0, o1);
           xstore(ch, o[i]);
@@ -727,10 +757,13 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
         const float r2 = rstd_fast(q2 / (float)HD);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          const float a0 = (h1[i].x - m1) * r1 * G1[i].x + B1[i].x;
-          const float a1 = (h1[i].y - m1) * r1 * G1[i].y + B1[i].y;
-          const float c0 = (h2[i].x - m2) * r2 * G2[i].x + B2[i].x;
-          const float c1 = (h2[i].y - m2) * r2 * G2[i].y + B2[i].y;
+          float2 ga, ba, gb, bb;
+          lnp1(i, ga, ba);
+          lnp2(i, gb, bb);
+          const float a0 = (h1[i].x - m1) * r1 * ga.x + ba.x;
+          const float a1 = (h1[i].y - m1) * r1 * ga.y + ba.y;
+          const float c0 = (h2[i].x - m2) * r2 * gb.x + bb.x;
+          const float c1 = (h2[i].y - m2) * r2 * gb.y + bb.y;
           const float gt0 = sigmoid_fast(a0), gt1 = sigmoid_fast(a1);
           o[i] = make_float2(gt0 * c0 + (1.0f - gt0) * xr[i].x, gt1 * c1 + (1.0f - gt1) * xr[i].y);
         }
