@@ -1066,11 +1066,10 @@ int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStr
 // Measured on B200 (us/frame).
 void ws_plan(int B, int* R, int* W, int* G) {
   int r, w;
-  if (B <= 8) { r = 1; w = 4; }            // 30 us/frame
-  else if (B <= 24) { r = 1; w = 2; }      // B=16 32, B=24 34 (4 warps per row: 34.5 at B=16)
-  else if (B <= 32) { r = 2; w = 2; }      // 40
-  else if (B <= 128) { r = 2; w = 1; }     // B=40 46 (R=1 47), B=64 54 (R=4 59), B=128 109 (R=4 110)
-  else { r = 4; w = 1; }                   // B=256 228
+  if (B <= 12) { r = 1; w = 4; }           // B=1 28.3 us/frame, B=12 28.9 (W=2: 30.1)
+  else if (B <= 32) { r = 1; w = 2; }      // B=16 30.5 (W=4: 32.7), B=24 31.8, B=32 37.1 (R=2 W=2: 39.3, W=1: 38.8)
+  else if (B <= 128) { r = 2; w = 1; }     // B=40 45.1 (R=1: 46.6), B=48 47.4 (R=1: 56.5), B=64 51.7 (R=1 75.7, R=4 59), B=128 104
+  else { r = 4; w = 1; }                   // B=256 220
   if (const char* e = getenv("SSV_DECODE_R")) {          // development knobs
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) { r = v; if (r * w > 4) w = 4 / r; }
