@@ -15,8 +15,8 @@ SPK_EMB_DIR for MAX_FRAME_NUM + 1 frames (:105-116), then SSRN (:120).  What is 
 
 With --save_spectrogram DIR it writes the linear spectrograms as `s<spk>/s<spk>_<nnn>.npy`; with --save_wav DIR it
 also runs the waveform stage of the reference (:126-139: Griffin-Lim, de-emphasis, trim, wav files) batched on
-the GPU (spoofsv_b200/vocoder.py) and writes `s<spk>/s<spk>_<nnn>.wav`.  The Kaldi / GE2E directory shuffling
-(:141-259) is a later row of the scope table.
+the GPU (spoofsv_b200/vocoder.py) and writes `s<spk>/s<spk>_<nnn>.wav`; --write_layouts then lays them out for the
+Kaldi / GE2E / anti-spoofing consumers as :141-259 does (spoofsv_b200/protocols.py).
 """
 from __future__ import annotations
 
@@ -37,8 +37,8 @@ from .synth import Unit, plan_batches, shard_range
 def build_parser() -> argparse.ArgumentParser:
     ps = argparse.ArgumentParser(description="Adversarial Conditional Text-to-speech")
     ps.add_argument("-C", "--configuration", type=str, default=None)
-    ps.add_argument("--train_spk_num", type=int, default=88)      # accepted for CLI compatibility (used by the
-    ps.add_argument("--enroll_utt_num", type=int, default=3)      # Kaldi / GE2E file shuffling only)
+    ps.add_argument("--train_spk_num", type=int, default=88)      # used by --write_layouts (the Kaldi / GE2E file
+    ps.add_argument("--enroll_utt_num", type=int, default=3)      # shuffling of the reference) only
     ps.add_argument("--eval_utt_num", type=int, default=20)
     ps.add_argument("-T", "--current_time", type=str, required=True)
     # extensions
@@ -52,6 +52,10 @@ def build_parser() -> argparse.ArgumentParser:
                          "trim, 9 s cap, peak 0.75, as generate_test_utterances.py:130-139 (default there: "
                          "SRC_ROOT_DIR/test/<current_time>/spoof_data/)")
     ps.add_argument("--gl_iters", type=int, default=64)
+    ps.add_argument("--write_layouts", action="store_true",
+                    help="after synthesis (rank 0, needs --save_wav and the VCTK corpus under DATA_ROOT_DIR): the Kaldi "
+                         "i-vector tree, GE2E links and, when ANTISPOOF_DIR exists, the anti-spoofing set of "
+                         "generate_test_utterances.py:141-259 under SRC_ROOT_DIR/test/<current_time>/")
     ps.add_argument("--random_init", type=int, default=None, metavar="SEED",
                     help="random-init weights instead of the INFERENCE_* checkpoints (no checkpoints are vendored)")
     return ps
@@ -157,8 +161,32 @@ def run(args, on_batch=None) -> Dict[str, float]:
     sec = time.perf_counter() - t0
     stats = {"rank": rank, "world": world, "utterances": n_utt, "frames": frames, "seconds": sec,
              "frames_per_s": n_utt * frames / sec if sec > 0 else 0.0}
+    if getattr(args, "write_layouts", False):
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier()                       # every rank's wavs are on disk
+        if rank == 0:
+            stats["layouts"] = write_layouts(args, cfg)
     print(json.dumps(stats), flush=True)
     return stats
+
+
+def write_layouts(args, cfg: dict) -> dict:
+    """generate_test_utterances.py:141-259 for the wavs under --save_wav."""
+    from . import protocols as P
+    if not args.save_wav:
+        raise ValueError("--write_layouts needs --save_wav (the synthesised wavs are its input)")
+    with open(cfg["TTS_TEXTS"], "r") as f:
+        sentences = [s.strip() for s in f.readlines()]
+    out_root = os.path.join(cfg["SRC_ROOT_DIR"], "test", args.current_time)
+    done = {"ivector": P.write_ivector_layout(cfg["DATA_ROOT_DIR"], args.save_wav, out_root, sentences, args.train_spk_num,
+                                              args.enroll_utt_num, args.eval_utt_num),
+            "ge2e_links": P.link_ge2e(out_root)}
+    anti = cfg.get("ANTISPOOF_DIR")
+    if anti and os.path.isdir(os.path.join(anti, "ASVspoof2019_LA_cm_protocols")):
+        done["antispoof"] = P.write_antispoof_set(anti, args.save_wav, args.current_time)
+    return done
 
 
 def main(argv: Optional[List[str]] = None) -> int:
