@@ -127,6 +127,16 @@ int ssv_synthesize_host_submit(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* s, con
                                int t2m_precision, int ssrn_precision, void* stream, int* ticket);
 int ssv_synthesize_host_wait(ssv_decoder* d, int ticket);
 
+/* ---- training step, first building block (next row of the scope table) ---------------------
+ * Backward of one highwayConv, FP32: what autograd computes for highwayConv.forward
+ * (models/TTSModel.py:63-84) inside loss.backward() of the training step
+ * (train/adversarial_wasserstein_gp.py:298-300).  x, dy, dx: dev (B, d, T); dconv_w (2d, d, k), dconv_b (2d),
+ * dln*_w/b (d): dev, overwritten (not accumulated). */
+int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, const float* conv_b, const float* ln1_w,
+                         const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
+                         int dilation, int causal, float* dx, float* dconv_w, float* dconv_b, float* dln1_w,
+                         float* dln1_b, float* dln2_w, float* dln2_b, void* stream);
+
 /* ---- waveform stage (next row of the scope table) -------------------------------------------
  * De-emphasis of B waveforms of n samples each, y[n] = x[n] + coeff * y[n-1]: replaces
  * scipy.signal.lfilter([1], [1, -PREEMPH], time_signal) (generate_test_utterances.py:136,

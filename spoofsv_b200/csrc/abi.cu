@@ -398,6 +398,68 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
   return kOk;
 }
 
+// Backward of one highwayConv, FP32 (see backward.cu).  Standalone like ssv_highway_conv_fwd: weights are packed per call.
+int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, const float* conv_b, const float* ln1_w,
+                         const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
+                         int dilation, int causal, float* dx, float* dconv_w, float* dconv_b, float* dln1_w,
+                         float* dln1_b, float* dln2_w, float* dln2_b, void* stream) {
+  SSV_CHECK(x && dy && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b, "highway_conv_bwd: null input pointer");
+  SSV_CHECK(dx && dconv_w && dconv_b && dln1_w && dln1_b && dln2_w && dln2_b, "highway_conv_bwd: null output pointer");
+  SSV_CHECK(B > 0 && T > 0, "highway_conv_bwd: empty input");
+  SSV_CHECK(d == 256 || d == 512, "highway_conv_bwd: dimension %d unsupported (256 or 512)", d);
+  SSV_CHECK(k == 1 || k == 3, "highway_conv_bwd: kernel_size %d unsupported (1 or 3)", k);
+  SSV_CHECK(dilation >= 1, "highway_conv_bwd: dilation must be >= 1");
+  cudaStream_t s = as_stream(stream);
+  Arena ar;
+  ParamMap pm;
+  pm.m["conv.weight"] = {conv_w, (int64_t)2 * d * d * k};
+  pm.m["conv.bias"] = {conv_b, 2 * d};
+  pm.m["ln1.weight"] = {ln1_w, d};
+  pm.m["ln1.bias"] = {ln1_b, d};
+  pm.m["ln2.weight"] = {ln2_w, d};
+  pm.m["ln2.bias"] = {ln2_b, d};
+  ConvPack c;
+  SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
+  const int M = B * T;
+  float *xin, *dyr, *H, *dH, *dxr, *dxc, *partial, *sums, *Wd, *zero_bias, *P;
+  SSV_TRY(ar.alloc<float>((size_t)M * d, &xin));
+  SSV_TRY(ar.alloc<float>((size_t)M * d, &dyr));
+  SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &H));
+  SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &dH));
+  SSV_TRY(ar.alloc<float>((size_t)M * d, &dxr));
+  SSV_TRY(ar.alloc<float>((size_t)M * d, &dxc));
+  SSV_TRY(ar.alloc<float>((size_t)hwy_bwd_row_blocks(M) * 6 * d, &partial));
+  SSV_TRY(ar.alloc<float>((size_t)6 * d, &sums));
+  SSV_TRY(ar.alloc<float>((size_t)k * 2 * d * d, &Wd));
+  SSV_TRY(ar.alloc<float>((size_t)d, &zero_bias));
+  SSV_TRY(ar.alloc<float>((size_t)wgrad_chunks(M) * k * 2 * d * d, &P));
+  SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
+  SSV_TRY(launch_transpose_in(dy, (long)d * T, T, 1, B, d, T, dyr, d, s));
+  // 1. H = conv(X) + b, raw
+  SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, H, 2 * d, s));
+  // 2. gate + LayerNorm backward per row, parameter partial sums
+  int nblk = 0;
+  SSV_TRY(launch_hwy_bwd_rows(H, xin, dyr, M, d, ln1_w, ln1_b, ln2_w, ln2_b, dH, dxr, partial, &nblk, s));
+  SSV_TRY(launch_colsum_partials(partial, nblk, 6 * d, sums, s));
+  SSV_CUDA(cudaMemcpyAsync(dln1_w, sums, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+  SSV_CUDA(cudaMemcpyAsync(dln1_b, sums + d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+  SSV_CUDA(cudaMemcpyAsync(dln2_w, sums + 2 * d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+  SSV_CUDA(cudaMemcpyAsync(dln2_b, sums + 3 * d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
+  SSV_CUDA(cudaMemcpyAsync(dconv_b, sums + 4 * d, sizeof(float) * 2 * d, cudaMemcpyDeviceToDevice, s));
+  // 3. dgrad: the forward's conv kernel on dH with time-flipped, transposed weights and mirrored taps
+  SSV_TRY(launch_pack_dgrad_w(conv_w, d, k, Wd, s));
+  SSV_CUDA(cudaMemsetAsync(zero_bias, 0, sizeof(float) * d, s));
+  ConvPack g;
+  g.W = Wd; g.bias = zero_bias; g.cin = 2 * d; g.cin_p = 2 * d; g.k = k; g.n = d; g.n_pad = d;
+  SSV_TRY(run_conv(g, EPI_NONE, dilation, causal ? 2 : 0, dH, 2 * d, T, B, dxc, d, s));
+  SSV_TRY(launch_add_inplace(dxc, dxr, (long)M * d, s));
+  SSV_TRY(launch_transpose_out(dxc, d, B, d, T, dx, s));
+  // 4. wgrad
+  SSV_TRY(launch_wgrad(dH, xin, M, T, d, k, dilation, causal ? 1 : 0, P, dconv_w, s));
+  SSV_CUDA(cudaStreamSynchronize(s));   // arena is freed on return
+  return kOk;
+}
+
 // ------------------------------------------------------------------------------------------------
 static int fill_stage(ssv_text2mel* m, const ParamMap& pm, int idx, const std::string& conv, int n, int cin, int k,
                       int dil, int pro, const float* g1, const float* b1, const float* g2, const float* b2,

@@ -62,7 +62,7 @@ struct ConvArgs {
   const float* g1; const float* b1;   // LN affine (LN1 of highway / the only LN)
   const float* g2; const float* b2;   // LN2 of highway
   int cin_p;           // input channels rounded up to 16
-  int ktaps, dil, causal;
+  int ktaps, dil, causal;   // causal: 0 = centred taps, 1 = taps t-(k-1)d .. t, 2 = taps t .. t+(k-1)d (fp32 kernel only)
   int n;               // real output columns (<= n_pad)
   int epi;
   float* Y;            // output, channels-last
@@ -97,6 +97,18 @@ int launch_linear_small(const float* x, long x_ld, const float* w, const float* 
 int launch_train_attention(const float* Kx /*(B,N,512)*/, const float* Q /*(B,T,256)*/, int B, int N, int T,
                            float* A /*(B,N,T)*/, float* RQ /*(B,T,512)*/, cudaStream_t s);
 int launch_deemphasis(const float* x, float* y, int B, long n, float coeff, cudaStream_t s);   // y[n] = x[n] + c y[n-1] per row
+// ---- backward building blocks (backward.cu) ----
+int hwy_bwd_row_blocks(int M);
+int launch_hwy_bwd_rows(const float* H, const float* X, const float* dY, int M, int d, const float* g1, const float* b1,
+                        const float* g2, const float* b2, float* dH, float* dXres, float* partial /*[blocks][6d]*/,
+                        int* nblk_out, cudaStream_t s);
+int launch_colsum_partials(const float* partial, int nblk, int ncol, float* out, cudaStream_t s);
+int launch_pack_dgrad_w(const float* conv_w /*(2d,d,k)*/, int d, int k, float* dst /*[k*2d][d]*/, cudaStream_t s);
+int launch_add_inplace(float* a, const float* b, long n, cudaStream_t s);
+int wgrad_chunks(int M);
+int launch_wgrad(const float* dH, const float* X, int M, int T, int d, int k, int dil, int causal,
+                 float* P /*[chunks][k][2d][d]*/, float* dW /*(2d,d,k)*/, cudaStream_t s);
+
 size_t griffin_lim_workspace_floats(int B, int T);                 // griffinlim.cu
 int launch_griffin_lim(const float* S /*(B,513,T)*/, const float* angles0_ri /*(B,513,T,2)*/, int B, int T, int n_iter,
                        float momentum, float* y /*(B, 256 (T-1))*/, float* workspace, cudaStream_t s);

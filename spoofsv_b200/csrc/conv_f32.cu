@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(NT) conv_f32_kernel(const ConvArgs a) {
 
   const int chunks_per_tap = a.cin_p / KC;
   const int nchunks = a.ktaps * chunks_per_tap;
-  const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
+  const int tap_base = a.causal == 1 ? -(a.ktaps - 1) : a.causal == 2 ? 0 : -((a.ktaps - 1) / 2);   // 2: anti-causal (dgrad of a causal conv)
 
   // One mbarrier per ring stage collects both halves of a chunk: the weight block (KC x NP floats, contiguous) comes
   // as one bulk copy issued by thread 0 (complete_tx), the activation rows as per-thread zero-fill cp.async whose
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(SPL_T) conv_f32_split_kernel(const ConvArgs a,
   const int col0 = blockIdx.x * 64, ks = blockIdx.y;
   const int K = a.ktaps * a.cin_p;
   const int k0 = ks * klen, k1 = min(K, k0 + klen);
-  const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
+  const int tap_base = a.causal == 1 ? -(a.ktaps - 1) : a.causal == 2 ? 0 : -((a.ktaps - 1) / 2);   // 2: anti-causal (dgrad of a causal conv)
   // stage my K range of every row: thread (r, q) copies the float4s q, q + T/Mp, ... of row r (channels are contiguous
   // in X; k0 and cin_p are multiples of 16, so a float4 never straddles a tap), transposed into xs[k][r]
   {

@@ -116,19 +116,55 @@ class highwayConv(nn.Module):
         _lib.require_cuda(inputs, "highwayConv.forward")
         if inputs.dim() != 3 or inputs.shape[1] != self.dimension:
             raise ValueError(f"highwayConv expects (B, {self.dimension}, T), got {tuple(inputs.shape)}")
-        x = inputs.detach().to(torch.float32).contiguous()
-        B, d, T = x.shape
-        y = torch.empty_like(x)
-        if x.numel() == 0:
-            return y
         ps = [self.conv.weight, self.conv.bias, self.ln1.weight, self.ln1.bias, self.ln2.weight, self.ln2.bias]
-        ps = [p.detach().contiguous() for p in ps]
         for p in ps:
             _lib.require_cuda(p, "highwayConv parameter")
-        _lib.check(_lib.load().ssv_highway_conv_fwd(
-            x.data_ptr(), *[p.data_ptr() for p in ps], B, d, T, self.kernel_size, self.dilation, int(self.causal),
-            y.data_ptr(), _prec(self.precision), _lib.current_stream_ptr()))
+        # the backward pass exists for the FP32 arm; the bf16 tensor-core arm is inference-only (no autograd graph)
+        if self.precision == "fp32" and torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in ps)):
+            return _HighwayConvFn.apply(inputs, *ps, self.kernel_size, self.dilation, bool(self.causal))
+        return _highway_fwd(inputs, ps, self.kernel_size, self.dilation, self.causal, self.precision)
+
+
+def _highway_fwd(inputs, ps, k, dilation, causal, precision):
+    x = inputs.detach().to(torch.float32).contiguous()
+    B, d, T = x.shape
+    y = torch.empty_like(x)
+    if x.numel() == 0:
         return y
+    ps = [p.detach().contiguous() for p in ps]
+    _lib.check(_lib.load().ssv_highway_conv_fwd(
+        x.data_ptr(), *[p.data_ptr() for p in ps], B, d, T, k, dilation, int(causal),
+        y.data_ptr(), _prec(precision), _lib.current_stream_ptr()))
+    return y
+
+
+class _HighwayConvFn(torch.autograd.Function):
+    """highwayConv with a hand-written backward (ssv_highway_conv_bwd): what autograd derives for
+    models/TTSModel.py:63-84 -- gate, both LayerNorms, dgrad and wgrad of the dilated conv -- in FP32."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, g1, b1, g2, b2, k, dilation, causal):
+        ps = [w, b, g1, b1, g2, b2]
+        y = _highway_fwd(x, ps, k, dilation, causal, "fp32")
+        ctx.save_for_backward(x.detach().to(torch.float32).contiguous(), *[p.detach().contiguous() for p in ps])
+        ctx.cfg = (k, dilation, causal)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, g1, b1, g2, b2 = ctx.saved_tensors
+        k, dilation, causal = ctx.cfg
+        B, d, T = x.shape
+        dy = dy.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        grads = [torch.empty_like(p) for p in (w, b, g1, b1, g2, b2)]
+        if x.numel() == 0:
+            return (dx, *[torch.zeros_like(p) for p in (w, b, g1, b1, g2, b2)], None, None, None)
+        _lib.check(_lib.load().ssv_highway_conv_bwd(
+            x.data_ptr(), dy.data_ptr(), w.data_ptr(), b.data_ptr(), g1.data_ptr(), b1.data_ptr(), g2.data_ptr(),
+            b2.data_ptr(), B, d, T, k, dilation, int(causal), dx.data_ptr(), *[g.data_ptr() for g in grads],
+            _lib.current_stream_ptr()))
+        return (dx, *grads, None, None, None)
 
 
 class melSyn(_Native):

@@ -490,3 +490,36 @@ def test_train_mode_forward_config5_shape_vs_oracle(cuda_models):
     with torch.no_grad():
         oY, oA = O.melsyn_train_forward(sd1, mel, ids, spk)
     assert _maxabs(Y, oY) <= FP32_TOL and _maxabs(A, oA) <= FP32_TOL
+
+
+# --------------------------------------------------------------------------- training step, first building block
+@pytest.mark.parametrize("d,k,dil,causal,B,T", [(256, 3, 1, True, 2, 37), (256, 3, 27, True, 3, 70), (256, 3, 3, False, 2, 45),
+                                                  (512, 3, 9, False, 2, 58), (512, 1, 1, False, 3, 33), (256, 3, 1, False, 5, 130)])
+def test_highway_conv_backward_vs_autograd(d, k, dil, causal, B, T):
+    """ssv_highway_conv_bwd against torch.autograd through the oracle's restatement of highwayConv.forward
+    (models/TTSModel.py:63-84): input, conv, bias and LayerNorm gradients, few rows and many, every tap layout."""
+    from spoofsv_b200.models.TTSModel import highwayConv
+    torch.manual_seed(d + k + dil)
+    hc = highwayConv(d, k, dil, causal=causal).cuda()
+    with torch.no_grad():
+        for p in (hc.ln1.weight, hc.ln2.weight):
+            p.add_(0.2 * torch.randn_like(p))
+        for p in (hc.ln1.bias, hc.ln2.bias):
+            p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(B, d, T, device="cuda", requires_grad=True)
+    gy = torch.randn(B, d, T, device="cuda")
+    y = hc(x)
+    assert y.requires_grad
+    y.backward(gy)
+    got = [x.grad] + [p.grad for p in (hc.conv.weight, hc.conv.bias, hc.ln1.weight, hc.ln1.bias, hc.ln2.weight, hc.ln2.bias)]
+    # oracle: the same computation in torch ops on the CPU, float64, differentiated by autograd
+    sd = {"h." + n: p.detach().cpu().double().requires_grad_(True) for n, p in hc.state_dict().items()}
+    xo = x.detach().cpu().double().requires_grad_(True)
+    yo = O.highway_conv(xo, sd, "h", dil, causal)
+    assert _maxabs(y, yo.float()) <= FP32_TOL
+    yo.backward(gy.cpu().double())
+    want = [xo.grad] + [sd["h." + n].grad for n in ("conv.weight", "conv.bias", "ln1.weight", "ln1.bias", "ln2.weight", "ln2.bias")]
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        scale = float(w.abs().max())
+        assert float((g.detach().cpu().double() - w).abs().max()) <= 2e-5 * max(scale, 1.0), (g.shape, scale)
