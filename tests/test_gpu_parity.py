@@ -523,3 +523,39 @@ def test_highway_conv_backward_vs_autograd(d, k, dil, causal, B, T):
         assert g.shape == w.shape
         scale = float(w.abs().max())
         assert float((g.detach().cpu().double() - w).abs().max()) <= 2e-5 * max(scale, 1.0), (g.shape, scale)
+
+
+def test_text2mel_training_backward_vs_autograd(cuda_models_k):
+    """loss.backward() through the train branch (train/adversarial_wasserstein_gp.py:277-300): every parameter
+    gradient of Text2Mel against float64 autograd through the oracle's restatement, on the same weights."""
+    m1, _, sd1, _ = cuda_models_k
+    names, emb, _ = W.load_fixtures()
+    B, N, T = 2, 11, 14
+    ids = W.synthetic_text(B, N, seed=5)
+    spk = torch.from_numpy(emb[:B].copy())[:, :, None]
+    mel = torch.rand((B, 80, T), generator=torch.Generator().manual_seed(4))
+    tgt = torch.rand((B, 80, T), generator=torch.Generator().manual_seed(6))
+    m1.train()
+    try:
+        m1.zero_grad(set_to_none=True)
+        Y, A = m1(mel.cuda(), ids.cuda(), spk.cuda())
+        assert Y.requires_grad
+        loss = (Y - tgt.cuda()).abs().mean() + 0.1 * (A * A).mean()
+        loss.backward()
+        got = {n: p.grad.detach().cpu().double() for n, p in m1.named_parameters()}
+    finally:
+        m1.eval()
+        m1.zero_grad(set_to_none=True)
+    sd = {k: v.double().requires_grad_(True) for k, v in sd1.items()}
+    oY, oA = O.melsyn_train_forward(sd, mel.double(), ids, spk.double())
+    assert _maxabs(Y, oY.float()) <= FP32_TOL and _maxabs(A, oA.float()) <= FP32_TOL
+    ((oY - tgt.double()).abs().mean() + 0.1 * (oA * oA).mean()).backward()
+    assert set(got) == set(sd)
+    worst = 0.0
+    for n, g in got.items():
+        w = sd[n].grad
+        assert w is not None and g.shape == w.shape, n
+        err = float((g - w).abs().max()) / max(float(w.abs().max()), 1e-6)
+        worst = max(worst, err)
+        assert err <= 2e-3, (n, err)
+    print(f"training backward: worst relative gradient error {worst:.2e}")
