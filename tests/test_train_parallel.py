@@ -1,0 +1,82 @@
+"""Gradient bucketing / allreduce of the data-parallel training step on CPU (gloo, world_size 2)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spoofsv_b200.train import allreduce_gradients, plan_buckets, shard_batch
+
+
+def test_plan_buckets_preserves_order_and_limits():
+    sizes = [5, 3, 9, 1, 1, 20, 2]
+    b = plan_buckets(sizes, 10)
+    assert [i for g in b for i in g] == list(range(len(sizes)))
+    assert b == [[0, 1], [2, 3], [4], [5], [6]]
+    assert all(sum(sizes[i] for i in g) <= 10 or len(g) == 1 for g in b)
+    assert plan_buckets([], 4) == []
+    with pytest.raises(ValueError):
+        plan_buckets([1], 0)
+
+
+def test_shard_batch_covers_everything():
+    for n, w in [(32, 8), (33, 4), (5, 8), (0, 2)]:
+        parts = [shard_batch(n, w, r) for r in range(w)]
+        assert parts[0].start == 0 and parts[-1].stop == n
+        assert all(a.stop == b.start for a, b in zip(parts, parts[1:]))
+        assert max(p.stop - p.start for p in parts) - min(p.stop - p.start for p in parts) <= 1
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                                   # same model on both ranks
+        model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        frozen = torch.nn.Parameter(torch.ones(4), requires_grad=False)
+        unused = torch.nn.Parameter(torch.ones(6))             # never receives a gradient
+        params = list(model.parameters()) + [frozen, unused]
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(8, 7, generator=g), torch.randn(8, 3, generator=g)
+        sl = shard_batch(8, world, rank)
+        loss = ((model(x[sl]) - y[sl]) ** 2).sum() / 8         # mean over the GLOBAL batch, split by rank
+        loss.backward()
+        n = allreduce_gradients(params, bucket_mb=1e-4, average=False)     # tiny buckets: several in flight
+        ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        ref.load_state_dict(model.state_dict())
+        (((ref(x) - y) ** 2).sum() / 8).backward()
+        err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(model.parameters(), ref.parameters()))
+        q.put((rank, n, err, float(unused.grad.abs().max()), frozen.grad is None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_gradients_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n, err, unused_max, frozen_none in out:
+        assert n == 7 * 5 + 5 + 5 * 3 + 3 + 6           # every trainable element, the frozen one excluded
+        assert err <= 1e-6                              # summed shard gradients == gradient of the global batch
+        assert unused_max == 0.0 and frozen_none
+
+
+def test_allreduce_is_a_noop_without_a_process_group():
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.full((3,), 2.0)
+    assert allreduce_gradients([p]) == 0 and float(p.grad[0]) == 2.0
