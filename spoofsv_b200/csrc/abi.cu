@@ -31,13 +31,35 @@ namespace {
 
 struct Arena {
   std::vector<void*> ptrs;
+  cudaStream_t async_stream = nullptr;
+  bool async = false;
+  Arena() = default;
+  // Stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on `s`, pool memory kept between calls): for the per-call
+  // workspaces of the standalone ops, which would otherwise pay a cudaMalloc / cudaFree (= device sync) per buffer.
+  explicit Arena(cudaStream_t s) : async_stream(s), async(true) {
+    static bool pool_configured = false;
+    if (!pool_configured) {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      pool_configured = true;
+    }
+  }
   ~Arena() {
-    for (void* p : ptrs) cudaFree(p);
+    for (void* p : ptrs) {
+      if (async) cudaFreeAsync(p, async_stream);
+      else cudaFree(p);
+    }
   }
   template <typename T>
   int alloc(size_t count, T** out) {
     void* p = nullptr;
-    if (cudaMalloc(&p, count * sizeof(T) + 256) != cudaSuccess) {
+    const cudaError_t e = async ? cudaMallocAsync(&p, count * sizeof(T) + 256, async_stream) : cudaMalloc(&p, count * sizeof(T) + 256);
+    if (e != cudaSuccess) {
       cudaGetLastError();
       set_error("cudaMalloc of %zu bytes failed", count * sizeof(T));
       return kNoMem;
@@ -364,7 +386,10 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
   SSV_CHECK(k == 1 || k == 3, "highway_conv: kernel_size %d unsupported (1 or 3)", k);
   SSV_CHECK(dilation >= 1, "highway_conv: dilation must be >= 1");
   cudaStream_t s = as_stream(stream);
-  Arena ar;
+  Arena ar_sync, ar_async(s);
+  // FP32 arm: stream-ordered scratch, no host synchronisation (it sits inside training steps); the tensor-core arm
+  // reports asynchronous MMA-pipeline errors, so it keeps the synchronous form
+  Arena& ar = precision == SSV_PREC_BF16 ? ar_sync : ar_async;
   ParamMap pm;
   pm.m["conv.weight"] = {conv_w, (int64_t)2 * d * d * k};
   pm.m["conv.bias"] = {conv_b, 2 * d};
@@ -393,8 +418,10 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
     SSV_TRY(run_conv(c, EPI_HIGHWAY, dilation, causal, xin, d, T, B, yout, d, s));
   }
   SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
-  SSV_CUDA(cudaStreamSynchronize(s));   // arena is freed on return
-  if (precision == SSV_PREC_BF16) SSV_TRY(tc_check_error());
+  if (precision == SSV_PREC_BF16) {
+    SSV_CUDA(cudaStreamSynchronize(s));   // arena is freed on return
+    SSV_TRY(tc_check_error());
+  }
   return kOk;
 }
 
@@ -410,7 +437,7 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_CHECK(k == 1 || k == 3, "highway_conv_bwd: kernel_size %d unsupported (1 or 3)", k);
   SSV_CHECK(dilation >= 1, "highway_conv_bwd: dilation must be >= 1");
   cudaStream_t s = as_stream(stream);
-  Arena ar;
+  Arena ar(s);                          // stream-ordered scratch: no host synchronisation inside a training step
   ParamMap pm;
   pm.m["conv.weight"] = {conv_w, (int64_t)2 * d * d * k};
   pm.m["conv.bias"] = {conv_b, 2 * d};
@@ -456,7 +483,6 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_TRY(launch_transpose_out(dxc, d, B, d, T, dx, s));
   // 4. wgrad
   SSV_TRY(launch_wgrad(dH, xin, M, T, d, k, dilation, causal ? 1 : 0, P, dconv_w, s));
-  SSV_CUDA(cudaStreamSynchronize(s));   // arena is freed on return
   return kOk;
 }
 
