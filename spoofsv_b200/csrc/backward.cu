@@ -141,8 +141,8 @@ constexpr int WG_ROWS = 32;
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dH, const float* __restrict__ X, int M, int T,
                                                      int d, int k, int dil, int tap_base, int chunks, int rows_per_chunk,
                                                      float* __restrict__ P) {
-  __shared__ float As[WG_ROWS][64 + 4];       // dH tile  [row][co]
-  __shared__ float Bs[WG_ROWS][64 + 4];       // X tile   [row][ci]
+  __shared__ __align__(16) float As[WG_ROWS][64 + 4];       // dH tile  [row][co]
+  __shared__ __align__(16) float Bs[WG_ROWS][64 + 4];       // X tile   [row][ci]
   const int co0 = blockIdx.x * 64, ci0 = blockIdx.y * 64;
   const int j = blockIdx.z % k, chunk = blockIdx.z / k;
   const int off = (tap_base + j) * dil;
@@ -163,15 +163,15 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dH
         const int b = row / T, t = row % T + off;
         if (t >= 0 && t < T) vb = *reinterpret_cast<const float4*>(X + ((size_t)b * T + t) * d + ci0 + c4);
       }
-      As[rr][c4] = va.x; As[rr][c4 + 1] = va.y; As[rr][c4 + 2] = va.z; As[rr][c4 + 3] = va.w;
-      Bs[rr][c4] = vb.x; Bs[rr][c4 + 1] = vb.y; Bs[rr][c4 + 2] = vb.z; Bs[rr][c4 + 3] = vb.w;
+      *reinterpret_cast<float4*>(&As[rr][c4]) = va;
+      *reinterpret_cast<float4*>(&Bs[rr][c4]) = vb;
     }
     __syncthreads();
 #pragma unroll 8
     for (int rr = 0; rr < WG_ROWS; ++rr) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[rr][ty * 4 + i]; b[i] = Bs[rr][tx * 4 + i]; }
+      const float4 av = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int ia = 0; ia < 4; ++ia)
 #pragma unroll
