@@ -134,8 +134,13 @@ int ssv_synthesize_host_wait(ssv_decoder* d, int ticket);
  * dln*_w/b (d): dev, overwritten (not accumulated). */
 int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, const float* conv_b, const float* ln1_w,
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
-                         int dilation, int causal, float* dx, float* dconv_w, float* dconv_b, float* dln1_w,
-                         float* dln1_b, float* dln2_w, float* dln2_b, void* stream);
+                         int dilation, int causal, const float* h_saved, float* dx, float* dconv_w, float* dconv_b,
+                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, void* stream);
+/* Training-time forward: like ssv_highway_conv_fwd (FP32) and also writes H = conv(x) + b, dev ((B T), 2d) in the
+ * library's row layout, for h_saved of ssv_highway_conv_bwd (NULL there: the conv is recomputed). */
+int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
+                              const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
+                              int dilation, int causal, float* y, float* h_save, void* stream);
 
 /* ---- waveform stage (next row of the scope table) -------------------------------------------
  * De-emphasis of B waveforms of n samples each, y[n] = x[n] + coeff * y[n-1]: replaces

@@ -425,11 +425,39 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
   return kOk;
 }
 
+// Training-time forward of one highwayConv, FP32: also hands back H = conv(x) + b in the library's row layout
+// ((B T) x 2d), which ssv_highway_conv_bwd takes instead of recomputing the conv.
+int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
+                              const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
+                              int dilation, int causal, float* y, float* h_save, void* stream) {
+  SSV_CHECK(x && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b && y && h_save, "highway_conv_fwd_save: null pointer");
+  SSV_CHECK(B > 0 && T > 0, "highway_conv_fwd_save: empty input");
+  SSV_CHECK(d == 256 || d == 512, "highway_conv_fwd_save: dimension %d unsupported (256 or 512)", d);
+  SSV_CHECK(k == 1 || k == 3, "highway_conv_fwd_save: kernel_size %d unsupported (1 or 3)", k);
+  SSV_CHECK(dilation >= 1, "highway_conv_fwd_save: dilation must be >= 1");
+  cudaStream_t s = as_stream(stream);
+  Arena ar(s);
+  ParamMap pm;
+  pm.m["conv.weight"] = {conv_w, (int64_t)2 * d * d * k};
+  pm.m["conv.bias"] = {conv_b, 2 * d};
+  ConvPack c;
+  SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
+  const int M = B * T;
+  float *xin, *yout;
+  SSV_TRY(ar.alloc<float>((size_t)M * d, &xin));
+  SSV_TRY(ar.alloc<float>((size_t)M * d, &yout));
+  SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
+  SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, h_save, 2 * d, s));
+  SSV_TRY(launch_hwy_fwd_rows(h_save, xin, M, d, ln1_w, ln1_b, ln2_w, ln2_b, yout, s));
+  SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
+  return kOk;
+}
+
 // Backward of one highwayConv, FP32 (see backward.cu).  Standalone like ssv_highway_conv_fwd: weights are packed per call.
 int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, const float* conv_b, const float* ln1_w,
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
-                         int dilation, int causal, float* dx, float* dconv_w, float* dconv_b, float* dln1_w,
-                         float* dln1_b, float* dln2_w, float* dln2_b, void* stream) {
+                         int dilation, int causal, const float* h_saved, float* dx, float* dconv_w, float* dconv_b,
+                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, void* stream) {
   SSV_CHECK(x && dy && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b, "highway_conv_bwd: null input pointer");
   SSV_CHECK(dx && dconv_w && dconv_b && dln1_w && dln1_b && dln2_w && dln2_b, "highway_conv_bwd: null output pointer");
   SSV_CHECK(B > 0 && T > 0, "highway_conv_bwd: empty input");
@@ -445,13 +473,11 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   pm.m["ln1.bias"] = {ln1_b, d};
   pm.m["ln2.weight"] = {ln2_w, d};
   pm.m["ln2.bias"] = {ln2_b, d};
-  ConvPack c;
-  SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
   const int M = B * T;
-  float *xin, *dyr, *H, *dH, *dxr, *dxc, *partial, *sums, *Wd, *zero_bias, *P;
+  float *xin, *dyr, *Hbuf = nullptr, *dH, *dxr, *dxc, *partial, *sums, *Wd, *zero_bias, *P;
   SSV_TRY(ar.alloc<float>((size_t)M * d, &xin));
   SSV_TRY(ar.alloc<float>((size_t)M * d, &dyr));
-  SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &H));
+  if (!h_saved) SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &Hbuf));
   SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &dH));
   SSV_TRY(ar.alloc<float>((size_t)M * d, &dxr));
   SSV_TRY(ar.alloc<float>((size_t)M * d, &dxc));
@@ -462,8 +488,14 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_TRY(ar.alloc<float>((size_t)wgrad_chunks(M) * k * 2 * d * d, &P));
   SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
   SSV_TRY(launch_transpose_in(dy, (long)d * T, T, 1, B, d, T, dyr, d, s));
-  // 1. H = conv(X) + b, raw
-  SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, H, 2 * d, s));
+  // 1. H = conv(X) + b, raw: saved by the training-time forward, or recomputed here
+  const float* H = h_saved;
+  if (!h_saved) {
+    ConvPack c;
+    SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
+    SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, Hbuf, 2 * d, s));
+    H = Hbuf;
+  }
   // 2. gate + LayerNorm backward per row, parameter partial sums
   int nblk = 0;
   SSV_TRY(launch_hwy_bwd_rows(H, xin, dyr, M, d, ln1_w, ln1_b, ln2_w, ln2_b, dH, dxr, partial, &nblk, s));

@@ -111,6 +111,43 @@ __global__ void __launch_bounds__(32 * BWD_WARPS) hwy_bwd_rows_kernel(
   }
 }
 
+// Forward epilogue as a separate pass over a saved H (training keeps H for the backward pass instead of
+// recomputing the conv): Y = sigmoid(LN1(H1)) * LN2(H2) + (1 - sigmoid(LN1(H1))) * X, one warp per row.
+template <int CH>
+__global__ void __launch_bounds__(256) hwy_fwd_rows_kernel(const float* __restrict__ H, const float* __restrict__ X, int M,
+                                                           const float* __restrict__ g1, const float* __restrict__ b1,
+                                                           const float* __restrict__ g2, const float* __restrict__ b2,
+                                                           float* __restrict__ Y) {
+  constexpr int d = 32 * CH;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* h = H + (size_t)row * 2 * d;
+  float h1[CH], h2[CH];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    h1[i] = h[lane + 32 * i]; h2[i] = h[d + lane + 32 * i];
+    s1 += h1[i]; s2 += h2[i];
+  }
+  const float inv_d = 1.0f / (float)d;
+  const float m1 = wsum(s1) * inv_d, m2 = wsum(s2) * inv_d;
+  float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const float e1 = h1[i] - m1, e2 = h2[i] - m2;
+    q1 = fmaf(e1, e1, q1); q2 = fmaf(e2, e2, q2);
+  }
+  const float r1 = 1.0f / sqrtf(wsum(q1) * inv_d + 1e-5f), r2 = 1.0f / sqrtf(wsum(q2) * inv_d + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int c = lane + 32 * i;
+    const float a = (h1[i] - m1) * r1 * g1[c] + b1[c], cc = (h2[i] - m2) * r2 * g2[c] + b2[c];
+    const float g = 1.0f / (1.0f + expf(-a));
+    Y[(size_t)row * d + c] = g * cc + (1.0f - g) * X[(size_t)row * d + c];
+  }
+}
+
 // out[c] = sum_blk partial[blk][c], blocks in order
 __global__ void colsum_partials_kernel(const float* __restrict__ partial, int nblk, int ncol, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,6 +256,17 @@ int launch_hwy_bwd_rows(const float* H, const float* X, const float* dY, int M, 
   SSV_CUDA(cudaGetLastError());
   ++g_launches;
   *nblk_out = nblk;
+  return kOk;
+}
+
+int launch_hwy_fwd_rows(const float* H, const float* X, int M, int d, const float* g1, const float* b1, const float* g2,
+                        const float* b2, float* Y, cudaStream_t s) {
+  const int grid = (M + 7) / 8;
+  if (d == 256) hwy_fwd_rows_kernel<8><<<grid, 256, 0, s>>>(H, X, M, g1, b1, g2, b2, Y);
+  else if (d == 512) hwy_fwd_rows_kernel<16><<<grid, 256, 0, s>>>(H, X, M, g1, b1, g2, b2, Y);
+  else { set_error("highway_conv: dimension %d unsupported (256 or 512)", d); return kInval; }
+  SSV_CUDA(cudaGetLastError());
+  ++g_launches;
   return kOk;
 }
 

@@ -99,6 +99,8 @@ int launch_train_attention(const float* Kx /*(B,N,512)*/, const float* Q /*(B,T,
 int launch_deemphasis(const float* x, float* y, int B, long n, float coeff, cudaStream_t s);   // y[n] = x[n] + c y[n-1] per row
 // ---- backward building blocks (backward.cu) ----
 int hwy_bwd_row_blocks(int M);
+int launch_hwy_fwd_rows(const float* H, const float* X, int M, int d, const float* g1, const float* b1, const float* g2,
+                        const float* b2, float* Y, cudaStream_t s);
 int launch_hwy_bwd_rows(const float* H, const float* X, const float* dY, int M, int d, const float* g1, const float* b1,
                         const float* g2, const float* b2, float* dH, float* dXres, float* partial /*[blocks][6d]*/,
                         int* nblk_out, cudaStream_t s);

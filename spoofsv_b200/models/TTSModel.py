@@ -142,18 +142,34 @@ class _HighwayConvFn(torch.autograd.Function):
     """highwayConv with a hand-written backward (ssv_highway_conv_bwd): what autograd derives for
     models/TTSModel.py:63-84 -- gate, both LayerNorms, dgrad and wgrad of the dilated conv -- in FP32."""
 
+    save_h = True        # keep H = conv(x) + b for the backward pass (2d floats per row) instead of recomputing it
+
     @staticmethod
     def forward(ctx, x, w, b, g1, b1, g2, b2, k, dilation, causal):
-        ps = [w, b, g1, b1, g2, b2]
-        y = _highway_fwd(x, ps, k, dilation, causal, "fp32")
-        ctx.save_for_backward(x.detach().to(torch.float32).contiguous(), *[p.detach().contiguous() for p in ps])
-        ctx.cfg = (k, dilation, causal)
+        ps = [p.detach().contiguous() for p in (w, b, g1, b1, g2, b2)]
+        xs = x.detach().to(torch.float32).contiguous()
+        B, d, T = xs.shape
+        h = None
+        if xs.numel() == 0:
+            y = torch.empty_like(xs)
+        elif _HighwayConvFn.save_h:
+            y = torch.empty_like(xs)
+            h = torch.empty((B * T, 2 * d), device=xs.device, dtype=torch.float32)
+            _lib.check(_lib.load().ssv_highway_conv_fwd_save(
+                xs.data_ptr(), *[p.data_ptr() for p in ps], B, d, T, k, dilation, int(causal), y.data_ptr(), h.data_ptr(),
+                _lib.current_stream_ptr()))
+        else:
+            y = _highway_fwd(xs, ps, k, dilation, causal, "fp32")
+        ctx.save_for_backward(xs, *ps, *([h] if h is not None else []))
+        ctx.cfg = (k, dilation, causal, h is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, b, g1, b1, g2, b2 = ctx.saved_tensors
-        k, dilation, causal = ctx.cfg
+        k, dilation, causal, has_h = ctx.cfg
+        saved = ctx.saved_tensors
+        x, w, b, g1, b1, g2, b2 = saved[:7]
+        h = saved[7] if has_h else None
         B, d, T = x.shape
         dy = dy.detach().to(torch.float32).contiguous()
         dx = torch.empty_like(x)
@@ -162,8 +178,8 @@ class _HighwayConvFn(torch.autograd.Function):
             return (dx, *[torch.zeros_like(p) for p in (w, b, g1, b1, g2, b2)], None, None, None)
         _lib.check(_lib.load().ssv_highway_conv_bwd(
             x.data_ptr(), dy.data_ptr(), w.data_ptr(), b.data_ptr(), g1.data_ptr(), b1.data_ptr(), g2.data_ptr(),
-            b2.data_ptr(), B, d, T, k, dilation, int(causal), dx.data_ptr(), *[g.data_ptr() for g in grads],
-            _lib.current_stream_ptr()))
+            b2.data_ptr(), B, d, T, k, dilation, int(causal), h.data_ptr() if h is not None else None, dx.data_ptr(),
+            *[g.data_ptr() for g in grads], _lib.current_stream_ptr()))
         return (dx, *grads, None, None, None)
 
 

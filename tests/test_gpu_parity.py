@@ -495,10 +495,14 @@ def test_train_mode_forward_config5_shape_vs_oracle(cuda_models):
 # --------------------------------------------------------------------------- training step, first building block
 @pytest.mark.parametrize("d,k,dil,causal,B,T", [(256, 3, 1, True, 2, 37), (256, 3, 27, True, 3, 70), (256, 3, 3, False, 2, 45),
                                                   (512, 3, 9, False, 2, 58), (512, 1, 1, False, 3, 33), (256, 3, 1, False, 5, 130)])
-def test_highway_conv_backward_vs_autograd(d, k, dil, causal, B, T):
+@pytest.mark.parametrize("save_h", [True, False])
+def test_highway_conv_backward_vs_autograd(d, k, dil, causal, B, T, save_h, monkeypatch):
     """ssv_highway_conv_bwd against torch.autograd through the oracle's restatement of highwayConv.forward
-    (models/TTSModel.py:63-84): input, conv, bias and LayerNorm gradients, few rows and many, every tap layout."""
+    (models/TTSModel.py:63-84): input, conv, bias and LayerNorm gradients, few rows and many, every tap layout;
+    with H saved by the training-time forward and with H recomputed in the backward pass."""
+    from spoofsv_b200.models import TTSModel as TM
     from spoofsv_b200.models.TTSModel import highwayConv
+    monkeypatch.setattr(TM._HighwayConvFn, "save_h", save_h)
     torch.manual_seed(d + k + dil)
     hc = highwayConv(d, k, dil, causal=causal).cuda()
     with torch.no_grad():
