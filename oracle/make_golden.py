@@ -92,8 +92,93 @@ def golden_train(R, ref_ids, emb):
                         Y=Y.numpy(), A=A.numpy())
 
 
+def golden_train_step(R, ref_ids, emb):
+    """Known answers for one generator and one discriminator iteration of train/adversarial_wasserstein_gp.py:
+    the unmodified reference melSyn (train mode) and melDisc (eval mode: its two dropouts off, everything else as
+    in training), kaiming init + jittered LayerNorm affine, B = 3, T = 24.  The statements between the marks are
+    the reference's own (:269-300 for G, :302-316 for D) with `device` / logging removed; the interpolation
+    weights of the gradient penalty (reference: torch.rand(B)) are stored in the fixture."""
+    import importlib
+    D = importlib.import_module("models.discriminator")
+    assert str(REF) in D.__file__
+    k1, k2 = W.state_dicts(7, init="kaiming", ln_jitter=True)
+    model, _ = ref_models(R, k1, k2)
+    model.train()
+    torch.manual_seed(11)
+    disc = D.melDisc(freq_bins=W.CFG["freq_bins"], disc_dim=128)
+    for m in disc.modules():                                   # train/ordinary.py:16-19 init_weights
+        if isinstance(m, torch.nn.Conv1d):
+            torch.nn.init.kaiming_normal_(m.weight)
+    disc.eval()
+    ids = O.pad_text_ids([ref_ids[1], ref_ids[7], ref_ids[3]])
+    spk_emb = torch.from_numpy(emb[[3, 40, 77]])[:, :, None]
+    g = torch.Generator().manual_seed(21)
+    mel_gt = torch.rand((3, W.CFG["freq_bins"], 24), generator=g) * 0.9 + 0.05
+    coeff_b = torch.rand(3, generator=g)
+    MAX_TEXT_LEN, MAX_FRAME_NUM, LAMBDA = 186, 325, 10
+    import math
+    gaw = torch.zeros((MAX_TEXT_LEN, MAX_FRAME_NUM))
+    for a in range(MAX_TEXT_LEN):
+        for b in range(MAX_FRAME_NUM):
+            gaw[a, b] = 1 - math.exp(-(b / MAX_FRAME_NUM - a / MAX_TEXT_LEN) ** 2 / (2 * 0.2 * 0.2))
+    F = torch.nn.functional
+    text_id = ids
+    B, C, T = mel_gt.shape
+    # ---- G iteration (reference :269-300)
+    spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
+    pred_mel_prob, att_mat = model(spec_inputs, text_id, spk_emb)
+    disc_syn = disc(pred_mel_prob)
+    loss_l1 = torch.mean(torch.abs(mel_gt - pred_mel_prob))
+    loss_bin_div = torch.mean(-mel_gt * torch.log(pred_mel_prob + 1e-8) - (1 - mel_gt) * torch.log(1 - pred_mel_prob + 1e-8))
+    att_aug = F.pad(att_mat, (0, MAX_FRAME_NUM - att_mat.size()[-1], 0, MAX_TEXT_LEN - att_mat.size()[-2]), value=-1)
+    loss_att = torch.sum(torch.ne(att_aug, -1).float() * att_aug * gaw) / torch.sum(torch.ne(att_aug, -1).float())
+    loss_disc = torch.mean(-disc_syn)
+    loss = loss_l1 + loss_bin_div + loss_att + (loss_l1.item() + loss_bin_div.item() + loss_att.item()) / (abs(loss_disc.item())) * loss_disc
+    loss.backward()
+    g_grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    g_terms = np.array([loss_l1.item(), loss_bin_div.item(), loss_att.item(), loss_disc.item(), loss.item()])
+    disc.zero_grad()
+    # ---- D iteration (reference :302-316)
+    coeff = torch.stack(T * [torch.stack(C * [coeff_b], dim=1)], dim=2)
+    input_mid = coeff * mel_gt.detach() + (1 - coeff) * pred_mel_prob.detach()
+    input_mid.requires_grad = True
+    output_mid = disc(input_mid)
+    gradients = torch.autograd.grad(outputs=output_mid, inputs=input_mid, grad_outputs=torch.ones(output_mid.size()),
+                                    retain_graph=True, create_graph=True)[0]
+    loss_gp = torch.mean(LAMBDA * (torch.norm(gradients, p=2, dim=(1, 2)) - 1) ** 2)
+    loss_gp.backward()
+    disc_gt = disc(mel_gt.detach())
+    disc_syn = disc(pred_mel_prob.detach())
+    loss_D = torch.mean(disc_syn - disc_gt)
+    loss_D.backward()
+    d_terms = np.array([loss_gp.item(), -loss_D.item()])
+    d_grads = {n: p.grad.detach().clone() for n, p in disc.named_parameters()}
+    pick = ["text_encoder.hci1.hc2.conv.weight", "audio_encoder.hc2.ln1.weight", "audio_decoder.conv5.weight",
+            "audio_encoder.fc1.weight", "text_encoder.textemb_layer.W.weight", "audio_decoder.hci.hc4.conv.bias"]
+    out = {"mel_gt": mel_gt.numpy(), "textid": ids.numpy(), "spk": spk_emb.numpy(), "coeff": coeff_b.numpy(),
+           "g_terms": g_terms, "d_terms": d_terms}
+    for n in pick:                                             # big tensors: every 37th element keeps the fixture small
+        gn = g_grads[n].numpy()
+        out["ggrad/" + n] = gn.reshape(-1)[::37] if gn.size > 20000 else gn
+    for n, v in disc.state_dict().items():
+        out["disc/" + n] = v.numpy()
+    for n in ("conv1.weight", "hc.conv.weight", "ln3.weight", "conv5.bias"):
+        dn = d_grads[n].numpy()
+        out["dgrad/" + n] = dn.reshape(-1)[::37] if dn.size > 20000 else dn
+    np.savez_compressed(GOLDEN / "train_step_seed7.npz", **out)
+    print("train step: G terms", g_terms, " D terms", d_terms)
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    if "--train-step-only" in sys.argv:
+        R = import_reference()
+        torch.set_num_threads(8)
+        lines = [ln.strip() for ln in (REF / "havard.txt").read_text().splitlines()]
+        names = sorted(p.stem for p in (REF / "spk_emb").glob("*.npy"))
+        emb = np.stack([np.load(REF / "spk_emb" / f"{n}.npy").astype(np.float32) for n in names])
+        golden_train_step(R, [O.text2id(s) for s in lines], emb)
+        return
     if "--train-only" in sys.argv:                             # add the train-branch vector without rewriting the rest
         R = import_reference()
         torch.set_num_threads(8)

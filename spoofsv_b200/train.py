@@ -84,3 +84,139 @@ def shard_batch(n: int, world: int, rank: int) -> slice:
     base, extra = divmod(n, world)
     lo = rank * base + min(rank, extra)
     return slice(lo, lo + base + (1 if rank < extra else 0))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The adversarial training step of Text2Mel (train/adversarial_wasserstein_gp.py:261-322).
+# Generator: spoofsv_b200.models.TTSModel.melSyn in train() mode (highway convs forward / backward in the library's
+# kernels).  Discriminator: the reference's melDisc restated in torch ops -- it is 0.3 % of the step's FLOPs and the
+# gradient penalty differentiates through its backward pass, so it stays in autograd.
+import math
+
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class _DiscHighway(nn.Module):
+    """models/TTSModel_dropout.py:37-86 (centred taps, dropout 0.05 on the output)."""
+
+    def __init__(self, dimension: int, kernel_size: int, dilation: int):
+        super().__init__()
+        self.dimension = dimension
+        self.conv = nn.Conv1d(dimension, 2 * dimension, kernel_size, padding=dilation * (kernel_size - 1) // 2, dilation=dilation)
+        self.ln1 = nn.LayerNorm(dimension)
+        self.ln2 = nn.LayerNorm(dimension)
+        self.dp = nn.Dropout(p=0.05)
+
+    def forward(self, x):
+        h = self.conv(x)
+        h1 = self.ln1(h[:, :self.dimension].transpose(1, 2)).transpose(1, 2)
+        h2 = self.ln2(h[:, self.dimension:].transpose(1, 2)).transpose(1, 2)
+        g = torch.sigmoid(h1)
+        return self.dp(g * h2 + (1 - g) * x)
+
+
+class melDisc(nn.Module):
+    """models/discriminator.py:6-42: same constructor, same state_dict keys, same forward."""
+
+    def __init__(self, freq_bins: int, disc_dim: int):
+        super().__init__()
+        self.conv1 = nn.Conv1d(freq_bins, disc_dim, 1)
+        self.ln1 = nn.LayerNorm(disc_dim)
+        self.dp1 = nn.Dropout(p=0.05)
+        self.hc = _DiscHighway(disc_dim, 3, 1)
+        self.conv2 = nn.Conv1d(disc_dim, 64, 1)
+        self.pl1 = nn.AvgPool1d(4)
+        self.ln2 = nn.LayerNorm(64)
+        self.dp2 = nn.Dropout(p=0.05)
+        self.conv3 = nn.Conv1d(64, 16, 1)
+        self.pl2 = nn.AvgPool1d(2)
+        self.ln3 = nn.LayerNorm(16)
+        self.conv4 = nn.Conv1d(16, 4, 1)
+        self.ln4 = nn.LayerNorm(4)
+        self.conv5 = nn.Conv1d(4, 1, 1)
+        self.pl3 = nn.AdaptiveAvgPool1d(1)
+
+    @staticmethod
+    def _ln(m, x):
+        return m(x.transpose(1, 2)).transpose(1, 2)
+
+    def forward(self, inputs):
+        x = self.dp1(self._ln(self.ln1, self.conv1(inputs)))
+        x = self.hc(x)
+        x = self.dp2(F.leaky_relu(self._ln(self.ln2, self.pl1(self.conv2(x))), 0.05))
+        x = self._ln(self.ln3, self.pl2(self.conv3(x)))
+        x = self._ln(self.ln4, self.conv4(F.leaky_relu(x, 0.05)))
+        return self.pl3(self.conv5(F.leaky_relu(x, 0.05)))
+
+
+def guided_attention_mat(max_text_len: int, max_frame_num: int, g: float = 0.2, device=None) -> torch.Tensor:
+    """train/adversarial_wasserstein_gp.py guided_attention_mat: W[n, t] = 1 - exp(-(t/T - n/N)^2 / (2 g^2))."""
+    n = torch.arange(max_text_len, dtype=torch.float32)[:, None] / max_text_len
+    t = torch.arange(max_frame_num, dtype=torch.float32)[None, :] / max_frame_num
+    w = 1.0 - torch.exp(-(t - n) ** 2 / (2.0 * g * g))
+    return w.to(device) if device is not None else w
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def fp32_math():
+    """The step is FP32 end to end: torch's convolutions and matmuls would otherwise run the discriminator in TF32
+    on this GPU (2e-4 relative noise in every generator gradient through the adversarial term)."""
+    conv, mm = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv, mm
+
+
+def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group=None):
+    """One 'G' iteration (:277-300): teacher-forced forward, L1 + binary divergence + guided attention + adversarial
+    term scaled to the size of the other three, backward, gradient allreduce, Adam step.  Returns the loss terms."""
+    opt_syn.zero_grad(set_to_none=True)
+    spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
+    with fp32_math():
+        pred, att = model(spec_inputs, text_id, spk_emb)
+        disc_syn = disc(pred)
+        loss_l1 = torch.mean(torch.abs(mel_gt - pred))
+        loss_bd = torch.mean(-mel_gt * torch.log(pred + 1e-8) - (1 - mel_gt) * torch.log(1 - pred + 1e-8))
+        N, T = att.shape[-2], att.shape[-1]
+        # the reference pads A with -1 to (MAX_TEXT_LEN, MAX_FRAME_NUM) and masks the padding out again: same value
+        loss_att = torch.sum(att * gaw[:N, :T]) / float(att.numel())
+        loss_disc = torch.mean(-disc_syn)
+        scale = (loss_l1.item() + loss_bd.item() + loss_att.item()) / abs(loss_disc.item())
+        loss = loss_l1 + loss_bd + loss_att + scale * loss_disc
+        loss.backward()
+    allreduce_gradients(model.parameters(), group=group)
+    opt_syn.step()
+    return {"l1": loss_l1.item(), "bin_div": loss_bd.item(), "att": loss_att.item(), "disc": loss_disc.item(),
+            "loss": loss.item()}
+
+
+def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff=None, group=None):
+    """One 'D' iteration (:302-322): WGAN-GP.  The generator runs without a graph (its output is detached in the
+    reference), the gradient penalty differentiates through the discriminator's backward pass (autograd).
+    `coeff` (B,) are the interpolation weights (reference: torch.rand(B), one per utterance)."""
+    opt_disc.zero_grad(set_to_none=True)
+    spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
+    with torch.no_grad():
+        pred, _ = model(spec_inputs, text_id, spk_emb)
+    B = mel_gt.shape[0]
+    if coeff is None:
+        coeff = torch.rand(B, device=mel_gt.device)
+    c = coeff.to(mel_gt.device, mel_gt.dtype)[:, None, None]
+    mid = (c * mel_gt + (1 - c) * pred).requires_grad_(True)
+    with fp32_math():
+        out_mid = disc(mid)
+        grads = torch.autograd.grad(out_mid, mid, torch.ones_like(out_mid), retain_graph=True, create_graph=True)[0]
+        loss_gp = torch.mean(cfg["LAMBDA"] * (torch.norm(grads, p=2, dim=(1, 2)) - 1) ** 2)
+        loss_gp.backward()
+        loss_d = torch.mean(disc(pred) - disc(mel_gt))
+        loss_d.backward()
+    allreduce_gradients(disc.parameters(), group=group)
+    opt_disc.step()
+    return {"gp": loss_gp.item(), "wd": -loss_d.item(), "loss": loss_d.item() + loss_gp.item()}

@@ -563,3 +563,54 @@ def test_text2mel_training_backward_vs_autograd(cuda_models_k):
         worst = max(worst, err)
         assert err <= 2e-3, (n, err)
     print(f"training backward: worst relative gradient error {worst:.2e}")
+
+
+def test_adversarial_training_step_golden(golden_dir, cuda_models_k):
+    """One generator and one discriminator iteration of train/adversarial_wasserstein_gp.py:269-316 against the
+    unmodified reference (tests/golden/train_step_seed7.npz, oracle/make_golden.py --train-step-only): loss terms,
+    generator gradients (highway convs in the library's kernels), gradient penalty, discriminator gradients."""
+    from spoofsv_b200 import train as TR
+    g = np.load(golden_dir / "train_step_seed7.npz")
+    m1 = cuda_models_k[0]
+    disc = TR.melDisc(80, 128).cuda()
+    disc.load_state_dict({k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("disc/")})
+    disc.eval()                                        # dropout off, as in the fixture
+    mel_gt, ids, spk = (torch.from_numpy(g[k]).cuda() for k in ("mel_gt", "textid", "spk"))
+    cfg = {"LAMBDA": 10}
+    gaw = TR.guided_attention_mat(186, 325, device="cuda")
+    opt_g = torch.optim.SGD(m1.parameters(), lr=0.0)   # the step itself leaves the shared fixture model untouched
+    opt_d = torch.optim.SGD(disc.parameters(), lr=0.0)
+    m1.train()
+    try:
+        terms = TR.generator_step(m1, disc, opt_g, mel_gt, ids, spk, gaw, cfg)
+        want = g["g_terms"]
+        for k, w in zip(("l1", "bin_div", "att", "disc"), want[:4]):
+            assert abs(terms[k] - w) <= 1e-5 * max(1.0, abs(w)), (k, terms[k], w)
+        grads = dict(m1.named_parameters())
+        for k in g.files:
+            if not k.startswith("ggrad/"):
+                continue
+            got = grads[k[6:]].grad.detach().cpu().numpy()
+            ref = g[k]
+            if got.size != ref.size:
+                got = got.reshape(-1)[::37]
+            err = np.abs(got.reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-6)
+            print(f"G grad {k[6:]}: rel err {err:.2e}")
+            assert err <= 1e-4, k                   # the fixture is the reference's own fp32 CPU run
+        dterms = TR.discriminator_step(m1, disc, opt_d, mel_gt, ids, spk, cfg, coeff=torch.from_numpy(g["coeff"]))
+        assert abs(dterms["gp"] - g["d_terms"][0]) <= 1e-4 * abs(g["d_terms"][0])
+        assert abs(dterms["wd"] - g["d_terms"][1]) <= 1e-5
+        dgr = dict(disc.named_parameters())
+        for k in g.files:
+            if not k.startswith("dgrad/"):
+                continue
+            got = dgr[k[6:]].grad.detach().cpu().numpy()
+            ref = g[k]
+            if got.size != ref.size:
+                got = got.reshape(-1)[::37]
+            err = np.abs(got.reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-6)
+            print(f"D grad {k[6:]}: rel err {err:.2e}")
+            assert err <= 1e-4, k
+    finally:
+        m1.eval()
+        m1.zero_grad(set_to_none=True)
