@@ -97,6 +97,22 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _conv1d_mm(x, conv: nn.Conv1d):
+    """nn.Conv1d (stride 1, zero padding, dilation) as shifted FP32 matmuls.  cuDNN picks its algorithm (Winograd,
+    FFT, ...) by problem size; in the discriminator that made a sharded step differ from the full-batch one by 1e-4
+    of the gradient, scaled up by the adversarial weight.  Matmuls are exact FP32 and differentiate twice."""
+    w, k = conv.weight, conv.kernel_size[0]
+    pad, dil = conv.padding[0], conv.dilation[0]
+    if pad:
+        x = F.pad(x, (pad, pad))
+    T = x.shape[-1] - dil * (k - 1)
+    y = None
+    for j in range(k):
+        term = torch.matmul(w[:, :, j], x[:, :, j * dil: j * dil + T])
+        y = term if y is None else y + term
+    return y + conv.bias[None, :, None]
+
+
 class _DiscHighway(nn.Module):
     """models/TTSModel_dropout.py:37-86 (centred taps, dropout 0.05 on the output)."""
 
@@ -109,7 +125,7 @@ class _DiscHighway(nn.Module):
         self.dp = nn.Dropout(p=0.05)
 
     def forward(self, x):
-        h = self.conv(x)
+        h = _conv1d_mm(x, self.conv)
         h1 = self.ln1(h[:, :self.dimension].transpose(1, 2)).transpose(1, 2)
         h2 = self.ln2(h[:, self.dimension:].transpose(1, 2)).transpose(1, 2)
         g = torch.sigmoid(h1)
@@ -142,12 +158,12 @@ class melDisc(nn.Module):
         return m(x.transpose(1, 2)).transpose(1, 2)
 
     def forward(self, inputs):
-        x = self.dp1(self._ln(self.ln1, self.conv1(inputs)))
+        x = self.dp1(self._ln(self.ln1, _conv1d_mm(inputs, self.conv1)))
         x = self.hc(x)
-        x = self.dp2(F.leaky_relu(self._ln(self.ln2, self.pl1(self.conv2(x))), 0.05))
-        x = self._ln(self.ln3, self.pl2(self.conv3(x)))
-        x = self._ln(self.ln4, self.conv4(F.leaky_relu(x, 0.05)))
-        return self.pl3(self.conv5(F.leaky_relu(x, 0.05)))
+        x = self.dp2(F.leaky_relu(self._ln(self.ln2, self.pl1(_conv1d_mm(x, self.conv2))), 0.05))
+        x = self._ln(self.ln3, self.pl2(_conv1d_mm(x, self.conv3)))
+        x = self._ln(self.ln4, _conv1d_mm(F.leaky_relu(x, 0.05), self.conv4))
+        return self.pl3(_conv1d_mm(F.leaky_relu(x, 0.05), self.conv5))
 
 
 def guided_attention_mat(max_text_len: int, max_frame_num: int, g: float = 0.2, device=None) -> torch.Tensor:
@@ -188,13 +204,19 @@ def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, gro
         # the reference pads A with -1 to (MAX_TEXT_LEN, MAX_FRAME_NUM) and masks the padding out again: same value
         loss_att = torch.sum(att * gaw[:N, :T]) / float(att.numel())
         loss_disc = torch.mean(-disc_syn)
-        scale = (loss_l1.item() + loss_bd.item() + loss_att.item()) / abs(loss_disc.item())
+        # the adversarial weight is a ratio of GLOBAL-batch loss values (the reference computes it on the gathered
+        # DataParallel output): average the four scalars over the ranks first
+        terms = torch.stack([loss_l1.detach(), loss_bd.detach(), loss_att.detach(), loss_disc.detach()])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group)
+            terms /= dist.get_world_size(group)
+        t_l1, t_bd, t_att, t_disc = (float(v) for v in terms.tolist())
+        scale = (t_l1 + t_bd + t_att) / abs(t_disc)
         loss = loss_l1 + loss_bd + loss_att + scale * loss_disc
         loss.backward()
     allreduce_gradients(model.parameters(), group=group)
     opt_syn.step()
-    return {"l1": loss_l1.item(), "bin_div": loss_bd.item(), "att": loss_att.item(), "disc": loss_disc.item(),
-            "loss": loss.item()}
+    return {"l1": t_l1, "bin_div": t_bd, "att": t_att, "disc": t_disc, "loss": t_l1 + t_bd + t_att + scale * t_disc}
 
 
 def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff=None, group=None):

@@ -529,12 +529,13 @@ def test_highway_conv_backward_vs_autograd(d, k, dil, causal, B, T, save_h, monk
         assert float((g.detach().cpu().double() - w).abs().max()) <= 2e-5 * max(scale, 1.0), (g.shape, scale)
 
 
-def test_text2mel_training_backward_vs_autograd(cuda_models_k):
+@pytest.mark.parametrize("B,N,T", [(2, 11, 14), (5, 23, 131)])
+def test_text2mel_training_backward_vs_autograd(B, N, T, cuda_models_k):
     """loss.backward() through the train branch (train/adversarial_wasserstein_gp.py:277-300): every parameter
-    gradient of Text2Mel against float64 autograd through the oracle's restatement, on the same weights."""
+    gradient of Text2Mel against float64 autograd through the oracle's restatement, on the same weights; a tiny
+    shape and one longer than every receptive field, with several row tiles and wgrad chunks."""
     m1, _, sd1, _ = cuda_models_k
     names, emb, _ = W.load_fixtures()
-    B, N, T = 2, 11, 14
     ids = W.synthetic_text(B, N, seed=5)
     spk = torch.from_numpy(emb[:B].copy())[:, :, None]
     mel = torch.rand((B, 80, T), generator=torch.Generator().manual_seed(4))

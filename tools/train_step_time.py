@@ -39,3 +39,15 @@ torch.backends.cudnn.allow_tf32 = True; torch.backends.cuda.matmul.allow_tf32 = 
 print("torch tf32      gpu %.2f ms, wall %.2f ms" % timeit(step_torch), flush=True)
 with torch.no_grad():
     print("ours  fwd only (fused train fwd) gpu %.2f ms, wall %.2f ms" % timeit(lambda: m1(mel, ids, spk)), flush=True)
+
+# ---- whole iterations (losses, backward, Adam), as train/adversarial_wasserstein_gp.py runs them
+from spoofsv_b200 import train as TR
+disc = TR.melDisc(80, 128).cuda().train()
+gaw = TR.guided_attention_mat(186, 325, device="cuda")
+cfg = {"LAMBDA": 10}
+opt_g = torch.optim.Adam(m1.parameters(), 2e-4, (0.5, 0.9), 1e-6)
+opt_d = torch.optim.Adam(disc.parameters(), 2e-4, (0.5, 0.9), 1e-6)
+mel_gt = torch.rand((B, 80, T), device="cuda") * 0.9 + 0.05
+m1.train()
+print("G iteration  gpu %.2f ms, wall %.2f ms" % timeit(lambda: TR.generator_step(m1, disc, opt_g, mel_gt, ids, spk, gaw, cfg)), flush=True)
+print("D iteration  gpu %.2f ms, wall %.2f ms" % timeit(lambda: TR.discriminator_step(m1, disc, opt_d, mel_gt, ids, spk, cfg)), flush=True)
