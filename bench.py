@@ -417,14 +417,37 @@ def main():
                 Yt, _ = m1(mel_t, ids_t, spk_t)
                 (Yt - tgt_t).abs().mean().backward()
 
-            for _ in range(2):
-                train_step()
-            ea, eb = ev(), ev()
-            ea.record()
-            for _ in range(3):
-                train_step()
-            eb.record(); torch.cuda.synchronize()
-            extra["config5_generator_fwd_bwd_ms"] = ea.elapsed_time(eb) / 3
+            def timed(fn, n=3):
+                for _ in range(2):
+                    fn()
+                ea, eb = ev(), ev()
+                ea.record()
+                for _ in range(n):
+                    fn()
+                eb.record(); torch.cuda.synchronize()
+                return ea.elapsed_time(eb) / n
+
+            extra["config5_generator_fwd_bwd_ms"] = timed(train_step)
+            # whole iterations of train/adversarial_wasserstein_gp.py:269-316 (losses, discriminator, backward; the
+            # optimizer step is left out so that the benchmark model keeps its weights)
+            if world > 1:
+                raise StopIteration                    # the iteration helpers all-reduce: only timed in a 1-process run
+            from spoofsv_b200 import train as TR
+
+            class _NoStep:
+                def __init__(self, params): self.params = list(params)
+                def zero_grad(self, set_to_none=True):
+                    for p in self.params: p.grad = None
+                def step(self): pass
+
+            disc = TR.melDisc(80, 128).cuda().train()
+            gaw = TR.guided_attention_mat(186, 325, device="cuda")
+            mel_g = torch.rand((Bt, 80, T), device="cuda") * 0.9 + 0.05
+            og, od = _NoStep(m1.parameters()), _NoStep(disc.parameters())
+            extra["config5_g_iteration_ms"] = timed(lambda: TR.generator_step(m1, disc, og, mel_g, ids_t, spk_t, gaw, {"LAMBDA": 10}))
+            extra["config5_d_iteration_ms"] = timed(lambda: TR.discriminator_step(m1, disc, od, mel_g, ids_t, spk_t, {"LAMBDA": 10}))
+        except StopIteration:
+            pass
         finally:
             m1.eval()
             m1.zero_grad(set_to_none=True)
