@@ -481,10 +481,52 @@ class SSRN(_Native):
     def _dims(self):
         return (self.freq_bins, self.output_bins, self.ssrn_dim)
 
+    def _forward_autograd(self, inputs):
+        """SSRN.forward (:342-362) with an autograd graph, for the `train_ssrn` step
+        (train/adversarial_wasserstein_gp.py:324-360): the eight highway convs (94 % of the FLOPs) forward and
+        backward in the library's kernels, the 1x1 convs, the two transposed convs and the LayerNorms as FP32 torch
+        matmuls / ops."""
+        import torch.nn.functional as F
+
+        def ln(x, m):
+            return F.layer_norm(x.transpose(1, 2), (m.weight.numel(),), m.weight, m.bias, 1e-5).transpose(1, 2)
+
+        def pw(x, m):
+            return torch.matmul(m.weight[:, :, 0], x) + m.bias[None, :, None]
+
+        def hc(x, bag, dil):
+            return _HighwayConvFn.apply(x, bag.conv.weight, bag.conv.bias, bag.ln1.weight, bag.ln1.bias, bag.ln2.weight,
+                                        bag.ln2.bias, 3, dil, False)
+
+        def ups(x, bag):
+            w = bag.deconv.weight                                   # (in, out, 2), stride 2: out[2t + j] = W[:, :, j]^T x[t]
+            y = torch.stack((torch.matmul(w[:, :, 0].t(), x), torch.matmul(w[:, :, 1].t(), x)), dim=-1)
+            y = y.reshape(x.shape[0], w.shape[1], 2 * x.shape[2]) + bag.deconv.bias[None, :, None]
+            return hc(hc(y, bag.hc1, 1), bag.hc2, 3)
+
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            x = ln(pw(inputs.to(torch.float32), self.conv1), self.ln1)
+            x = hc(hc(x, self.hc1, 1), self.hc2, 3)
+            x = ups(ups(x, self.ups1), self.ups2)
+            x = ln(pw(x, self.conv2), self.ln2)
+            x = hc(hc(x, self.hc3, 1), self.hc4, 1)
+            x = ln(pw(x, self.conv3), self.ln3)
+            x = ln(pw(x, self.conv4), self.ln4)
+            x = ln(pw(F.relu(x), self.conv5), self.ln5)
+            x = ln(pw(F.relu(x), self.conv6), self.ln6)
+            return torch.sigmoid(x)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
     def forward(self, inputs):
         _lib.require_cuda(inputs, "SSRN.forward")
         if inputs.dim() != 3 or inputs.shape[1] != self.freq_bins:
             raise ValueError(f"SSRN expects (B, {self.freq_bins}, T), got {tuple(inputs.shape)}")
+        if (self.training and self.precision == "fp32" and torch.is_grad_enabled()
+                and any(p.requires_grad for p in self.parameters()) and inputs.numel() > 0):
+            return self._forward_autograd(inputs)
         x = inputs.detach()
         if x.dtype != torch.float32:
             x = x.to(torch.float32)

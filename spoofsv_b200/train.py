@@ -133,24 +133,25 @@ class _DiscHighway(nn.Module):
 
 
 class melDisc(nn.Module):
-    """models/discriminator.py:6-42: same constructor, same state_dict keys, same forward."""
+    """models/discriminator.py:6-42 (and linDisc, :44-80, through the pooling / width arguments): same constructor,
+    same state_dict keys, same forward."""
 
-    def __init__(self, freq_bins: int, disc_dim: int):
+    def __init__(self, freq_bins: int, disc_dim: int, pool1: int = 4, pool2: int = 2, narrow: int = 4):
         super().__init__()
         self.conv1 = nn.Conv1d(freq_bins, disc_dim, 1)
         self.ln1 = nn.LayerNorm(disc_dim)
         self.dp1 = nn.Dropout(p=0.05)
         self.hc = _DiscHighway(disc_dim, 3, 1)
         self.conv2 = nn.Conv1d(disc_dim, 64, 1)
-        self.pl1 = nn.AvgPool1d(4)
+        self.pl1 = nn.AvgPool1d(pool1)
         self.ln2 = nn.LayerNorm(64)
         self.dp2 = nn.Dropout(p=0.05)
         self.conv3 = nn.Conv1d(64, 16, 1)
-        self.pl2 = nn.AvgPool1d(2)
+        self.pl2 = nn.AvgPool1d(pool2)
         self.ln3 = nn.LayerNorm(16)
-        self.conv4 = nn.Conv1d(16, 4, 1)
-        self.ln4 = nn.LayerNorm(4)
-        self.conv5 = nn.Conv1d(4, 1, 1)
+        self.conv4 = nn.Conv1d(16, narrow, 1)
+        self.ln4 = nn.LayerNorm(narrow)
+        self.conv5 = nn.Conv1d(narrow, 1, 1)
         self.pl3 = nn.AdaptiveAvgPool1d(1)
 
     @staticmethod
@@ -164,6 +165,13 @@ class melDisc(nn.Module):
         x = self._ln(self.ln3, self.pl2(_conv1d_mm(x, self.conv3)))
         x = self._ln(self.ln4, _conv1d_mm(F.leaky_relu(x, 0.05), self.conv4))
         return self.pl3(_conv1d_mm(F.leaky_relu(x, 0.05), self.conv5))
+
+
+class linDisc(melDisc):
+    """models/discriminator.py:44-80: the SSRN-side discriminator (pooling 8 / 4, 8 channels before the last conv)."""
+
+    def __init__(self, freq_bins: int, disc_dim: int):
+        super().__init__(freq_bins, disc_dim, pool1=8, pool2=4, narrow=8)
 
 
 def guided_attention_mat(max_text_len: int, max_frame_num: int, g: float = 0.2, device=None) -> torch.Tensor:
@@ -227,18 +235,52 @@ def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coe
     spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
     with torch.no_grad():
         pred, _ = model(spec_inputs, text_id, spk_emb)
-    B = mel_gt.shape[0]
+    return _wgan_gp_step(disc, opt_disc, mel_gt, pred, cfg, coeff, group)
+
+
+def _wgan_gp_step(disc, opt_disc, real, fake, cfg, coeff, group):
+    B = real.shape[0]
     if coeff is None:
-        coeff = torch.rand(B, device=mel_gt.device)
-    c = coeff.to(mel_gt.device, mel_gt.dtype)[:, None, None]
-    mid = (c * mel_gt + (1 - c) * pred).requires_grad_(True)
+        coeff = torch.rand(B, device=real.device)
+    c = coeff.to(real.device, real.dtype)[:, None, None]
+    mid = (c * real + (1 - c) * fake).requires_grad_(True)
     with fp32_math():
         out_mid = disc(mid)
         grads = torch.autograd.grad(out_mid, mid, torch.ones_like(out_mid), retain_graph=True, create_graph=True)[0]
         loss_gp = torch.mean(cfg["LAMBDA"] * (torch.norm(grads, p=2, dim=(1, 2)) - 1) ** 2)
         loss_gp.backward()
-        loss_d = torch.mean(disc(pred) - disc(mel_gt))
+        loss_d = torch.mean(disc(fake) - disc(real))
         loss_d.backward()
     allreduce_gradients(disc.parameters(), group=group)
     opt_disc.step()
     return {"gp": loss_gp.item(), "wd": -loss_d.item(), "loss": loss_d.item() + loss_gp.item()}
+
+
+def ssrn_generator_step(model, disc, opt_syn, mel_gt, lin_gt, cfg=None, group=None):
+    """One 'G' iteration of `train_ssrn` (train/adversarial_wasserstein_gp.py:324-338): SSRN forward, L1 + binary
+    divergence + the adversarial term scaled to their size, backward, gradient allreduce, optimizer step."""
+    opt_syn.zero_grad(set_to_none=True)
+    with fp32_math():
+        pred = model(mel_gt)
+        disc_syn = disc(pred)
+        loss_l1 = torch.mean(torch.abs(lin_gt - pred))
+        loss_bd = torch.mean(-lin_gt * torch.log(pred + 1e-8) - (1 - lin_gt) * torch.log(1 - pred + 1e-8))
+        loss_disc = torch.mean(-disc_syn)
+        terms = torch.stack([loss_l1.detach(), loss_bd.detach(), loss_disc.detach()])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group)
+            terms /= dist.get_world_size(group)
+        t_l1, t_bd, t_disc = (float(v) for v in terms.tolist())
+        scale = (t_l1 + t_bd) / abs(t_disc)
+        (loss_l1 + loss_bd + scale * loss_disc).backward()
+    allreduce_gradients(model.parameters(), group=group)
+    opt_syn.step()
+    return {"l1": t_l1, "bin_div": t_bd, "disc": t_disc, "loss": t_l1 + t_bd + scale * t_disc}
+
+
+def ssrn_discriminator_step(model, disc, opt_disc, mel_gt, lin_gt, cfg, coeff=None, group=None):
+    """One 'D' iteration of `train_ssrn` (:340-360): WGAN-GP on linear spectrograms."""
+    opt_disc.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        pred = model(mel_gt)
+    return _wgan_gp_step(disc, opt_disc, lin_gt, pred, cfg, coeff, group)

@@ -615,3 +615,87 @@ def test_adversarial_training_step_golden(golden_dir, cuda_models_k):
     finally:
         m1.eval()
         m1.zero_grad(set_to_none=True)
+
+
+def test_ssrn_training_backward_vs_autograd(cuda_models_k):
+    """SSRN in train() mode (the `train_ssrn` step, train/adversarial_wasserstein_gp.py:324-338): forward and
+    every parameter gradient against float64 autograd through the oracle's restatement of SSRN.forward."""
+    _, m2, _, sd2 = cuda_models_k
+    B, T = 2, 19
+    mel = torch.rand((B, 80, T), generator=torch.Generator().manual_seed(8))
+    tgt = torch.rand((B, 513, 4 * T), generator=torch.Generator().manual_seed(9))
+    prec = m2.precision
+    m2.precision = "fp32"
+    m2.train()
+    try:
+        m2.zero_grad(set_to_none=True)
+        Y = m2(mel.cuda())
+        assert Y.requires_grad and tuple(Y.shape) == (B, 513, 4 * T)
+        t = tgt.cuda()
+        ((Y - t).abs().mean() + torch.mean(-t * torch.log(Y + 1e-8) - (1 - t) * torch.log(1 - Y + 1e-8))).backward()
+        got = {n: p.grad.detach().cpu().double() for n, p in m2.named_parameters()}
+    finally:
+        m2.eval()
+        m2.precision = prec
+        m2.zero_grad(set_to_none=True)
+    sd = {k: v.double().requires_grad_(True) for k, v in sd2.items()}
+    oY = O.ssrn(mel.double(), sd)
+    assert _maxabs(Y, oY.float()) <= FP32_TOL
+    td = tgt.double()
+    ((oY - td).abs().mean() + torch.mean(-td * torch.log(oY + 1e-8) - (1 - td) * torch.log(1 - oY + 1e-8))).backward()
+    assert set(got) == set(sd)
+    worst = 0.0
+    for n, g in got.items():
+        w = sd[n].grad
+        err = float((g - w).abs().max()) / max(float(w.abs().max()), 1e-9)
+        worst = max(worst, err)
+        assert err <= 1e-3, (n, err)
+    print(f"SSRN training backward: worst relative gradient error {worst:.2e}")
+
+
+def test_ssrn_adversarial_step_vs_oracle(cuda_models_k):
+    """`train_ssrn` iterations (train/adversarial_wasserstein_gp.py:324-360): loss terms of the generator step and
+    gradient penalty / Wasserstein distance of the discriminator step against the same statements evaluated on the
+    oracle's SSRN in float64 on the CPU."""
+    from spoofsv_b200 import train as TR
+    _, m2, _, sd2 = cuda_models_k
+    B, T = 2, 19
+    g = torch.Generator().manual_seed(12)
+    mel = torch.rand((B, 80, T), generator=g)
+    lin = torch.rand((B, 513, 4 * T), generator=g) * 0.9 + 0.05
+    coeff = torch.rand(B, generator=g)
+    torch.manual_seed(3)
+    disc = TR.linDisc(513, 128).eval()
+    ref_disc = TR.linDisc(513, 128).double().eval()
+    ref_disc.load_state_dict({k: v.double() for k, v in disc.state_dict().items()})
+    disc = disc.cuda()
+
+    class _NoStep:
+        def __init__(self, ps): self.ps = list(ps)
+        def zero_grad(self, set_to_none=True):
+            for p in self.ps: p.grad = None
+        def step(self): pass
+
+    prec = m2.precision
+    m2.precision = "fp32"
+    m2.train()
+    try:
+        gt = TR.ssrn_generator_step(m2, disc, _NoStep(m2.parameters()), mel.cuda(), lin.cuda())
+        dt = TR.ssrn_discriminator_step(m2, disc, _NoStep(disc.parameters()), mel.cuda(), lin.cuda(), {"LAMBDA": 10}, coeff=coeff)
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in disc.parameters())
+    finally:
+        m2.eval()
+        m2.precision = prec
+        m2.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        pred = O.ssrn(mel.double(), {k: v.double() for k, v in sd2.items()})
+    l1 = float(torch.mean(torch.abs(lin.double() - pred)))
+    bd = float(torch.mean(-lin.double() * torch.log(pred + 1e-8) - (1 - lin.double()) * torch.log(1 - pred + 1e-8)))
+    ld = float(torch.mean(-ref_disc(pred)))
+    assert abs(gt["l1"] - l1) <= 1e-5 and abs(gt["bin_div"] - bd) <= 1e-5 and abs(gt["disc"] - ld) <= 1e-4 * max(1.0, abs(ld))
+    c = coeff.double()[:, None, None]
+    mid = (c * lin.double() + (1 - c) * pred).requires_grad_(True)
+    gr = torch.autograd.grad(ref_disc(mid).sum(), mid)[0]
+    gp = float(torch.mean(10 * (torch.norm(gr, p=2, dim=(1, 2)) - 1) ** 2))
+    wd = -float(torch.mean(ref_disc(pred) - ref_disc(lin.double())))
+    assert abs(dt["gp"] - gp) <= 1e-4 * max(1.0, abs(gp)) and abs(dt["wd"] - wd) <= 1e-4 * max(1.0, abs(wd))
