@@ -242,6 +242,78 @@ def adversarial_train(train_step: str, train_pattern: str, cfg: dict, spec_dir: 
     return out
 
 
+def ordinary_train(train_step: str, train_pattern: str, cfg: dict, spec_dir: Optional[str], resume_checkpoints: Optional[str],
+                   current_time: str, max_iterations: Optional[int] = None) -> dict:
+    """train/ordinary.py:130-292: the trainer without a discriminator (checkpoints under .../not_adversarial/<T>/ with
+    the keys epoch, iteration, model_state_dict, optimizer_state_dict, loss_val_log)."""
+    import torch.distributed as dist
+    from torch.utils.data import DataLoader
+    from . import train as TR
+    from .data import collate_pad_2, collate_pad_3, dataset
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl")
+    save_dir = cfg["SRC_ROOT_DIR"] + "checkpoints/" + train_pattern + "/not_adversarial/" + current_time
+    if rank == 0:
+        os.makedirs(save_dir, exist_ok=True)
+    text2mel = train_step == "train_text2mel"
+    m1, m2 = _models(cfg, train_pattern)
+    model = m1 if text2mel else m2
+    adam = cfg["ADAM"]
+    mk_opt = lambda m: torch.optim.Adam(m.parameters(), adam["ALPHA"], (adam["BETA_1"], adam["BETA_2"]), adam["EPSILON"])
+    epoch = iteration = 0
+    loss_val_log = []
+    if resume_checkpoints is None:
+        torch.manual_seed(0)
+        model.apply(_init_weights)
+        model = model.cuda()
+        opt = mk_opt(model)
+    else:
+        ck = torch.load(resume_checkpoints, map_location="cpu")
+        epoch, iteration, loss_val_log = ck["epoch"], ck["iteration"], ck.get("loss_val_log", [])
+        model.load_state_dict(ck["model_state_dict"])
+        model = model.cuda()
+        opt = mk_opt(model)
+        opt.load_state_dict(ck["optimizer_state_dict"])
+    model.train()
+    collate = collate_pad_3 if text2mel else collate_pad_2
+    mk_loader = lambda mode, bs, shuffle: DataLoader(
+        dataset(cfg=cfg, mode=mode, pattern=train_pattern, step=train_step, spec_dir=spec_dir),
+        batch_size=bs, shuffle=shuffle, num_workers=0, collate_fn=collate, generator=torch.Generator().manual_seed(1234 + epoch))
+    train_loader, val_loader = mk_loader("train", cfg["BATCH_SIZE"], True), mk_loader("validate", 8, False)
+    gaw = TR.guided_attention_mat(cfg["MAX_TEXT_LEN"], cfg["MAX_FRAME_NUM"], device="cuda")
+    done, last = False, None
+    while epoch < cfg["MAX_EPOCHS"] and not done:
+        for sp in train_loader:
+            sl = TR.shard_batch(sp["data_0"].shape[0], world, rank)
+            if sl.stop == sl.start:
+                continue
+            keys = ("data_0", "data_1", "data_2") if text2mel else ("data_0", "data_1")
+            last = TR.ordinary_step(model, opt, tuple(sp[k][sl].cuda() for k in keys), gaw, text2mel)
+            if rank == 0:
+                print("global iteration {}: {}".format(iteration + 1, json.dumps(last)), flush=True)
+            if iteration % cfg["VAL_EVERY_ITER"] == 0 and iteration > 0:
+                model.eval()
+                loss_val_log.append(_validate(val_loader, gaw, cfg, model, train_step))
+                model.train()
+                if rank == 0:
+                    ck = {"epoch": epoch + 1, "iteration": iteration + 1, "model_state_dict": model.state_dict(),
+                          "optimizer_state_dict": opt.state_dict(), "loss_val_log": loss_val_log}
+                    if loss_val_log.index(min(loss_val_log)) == len(loss_val_log) - 1:
+                        torch.save(ck, save_dir + "/{}_best_model.tar.pth".format(train_step[6:]))
+                    torch.save(ck, save_dir + "/{}_iteration_{}.tar.pth".format(train_step[6:], iteration + 1))
+            iteration += 1
+            if max_iterations is not None and iteration >= max_iterations:
+                done = True
+                break
+        epoch += 1
+    out = {"iterations": iteration, "epochs": epoch, "save_dir": save_dir, "last": last}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    return out
+
+
 def main(argv=None) -> int:
     args = build_parser().parse_args(argv)
     if args.configuration is None:
@@ -256,9 +328,8 @@ def main(argv=None) -> int:
         spec_dir = cfg["SRC_ROOT_DIR"] + "spec/"
         os.makedirs(spec_dir, exist_ok=True)
     if args.step in ("train_text2mel", "train_ssrn"):
-        if not args.adversarial:
-            raise NotImplementedError("only the adversarial trainer (--adversarial, train/adversarial_wasserstein_gp.py) is built")
-        adversarial_train(args.step, args.pattern, cfg, spec_dir, args.resume, args.current_time, args.max_iterations)
+        trainer = adversarial_train if args.adversarial else ordinary_train
+        trainer(args.step, args.pattern, cfg, spec_dir, args.resume, args.current_time, args.max_iterations)
     else:
         synthesize(args.pattern, cfg, spec_dir, args.current_time, args.random_init, args.gl_iters)
     return 0

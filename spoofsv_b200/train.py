@@ -284,3 +284,31 @@ def ssrn_discriminator_step(model, disc, opt_disc, mel_gt, lin_gt, cfg, coeff=No
     with torch.no_grad():
         pred = model(mel_gt)
     return _wgan_gp_step(disc, opt_disc, lin_gt, pred, cfg, coeff, group)
+
+
+def ordinary_step(model, opt, batch, gaw, text2mel: bool, group=None):
+    """One iteration of the non-adversarial trainer (train/ordinary.py:219-256): L1 + binary divergence
+    (+ guided attention for Text2Mel), backward, gradient allreduce, optimizer step."""
+    opt.zero_grad(set_to_none=True)
+    with fp32_math():
+        if text2mel:
+            mel_gt, text_id, spk_emb = batch
+            spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
+            pred, att = model(spec_inputs, text_id, spk_emb)
+            target = mel_gt
+        else:
+            mel_gt, target = batch
+            pred, att = model(mel_gt), None
+        loss_l1 = torch.mean(torch.abs(target - pred))
+        loss_bd = torch.mean(-target * torch.log(pred + 1e-8) - (1 - target) * torch.log(1 - pred + 1e-8))
+        loss = loss_l1 + loss_bd
+        out = {"l1": loss_l1.item(), "bin_div": loss_bd.item()}
+        if att is not None:
+            loss_att = torch.sum(att * gaw[:att.shape[-2], :att.shape[-1]]) / float(att.numel())
+            loss = loss + loss_att
+            out["att"] = loss_att.item()
+        loss.backward()
+    allreduce_gradients(model.parameters(), group=group)
+    opt.step()
+    out["loss"] = loss.item()
+    return out

@@ -73,3 +73,8 @@ def test_main_synthesize_and_adversarial_training(tmp_path):
     out3 = M.adversarial_train("train_ssrn", "conditional", cfg, str(tmp_path / "spec") + "/", None, "t3", max_iterations=4)
     assert out3["iterations"] == 4 and np.isfinite(out3["last_G"]) and np.isfinite(out3["last_D"])
     assert (tmp_path / "checkpoints" / "conditional" / "adversarial" / "t3" / "ssrn_iteration_4.tar.pth").exists()
+    # the trainer without a discriminator (train/ordinary.py), through the CLI
+    assert M.main(["train_text2mel", "-C", str(cfg_path), "-T", "t4", "--save_spectrogram", "--max_iterations", "5"]) == 0
+    ck = torch.load(tmp_path / "checkpoints" / "conditional" / "not_adversarial" / "t4" / "text2mel_iteration_4.tar.pth", map_location="cpu")
+    assert set(ck) == {"epoch", "iteration", "model_state_dict", "optimizer_state_dict", "loss_val_log"}
+    assert M.main(["train_ssrn", "-C", str(cfg_path), "-T", "t5", "--save_spectrogram", "--max_iterations", "2"]) == 0
