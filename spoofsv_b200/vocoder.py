@@ -107,12 +107,36 @@ def postprocess(pred_lin: torch.Tensor, cfg: dict, n_iter: int = 64, angles0: Op
     sig = deemphasis(sig, cfg["PREEMPH"])
     starts, ends = trim_bounds(sig, 30.0)
     cap = 9 * cfg["SAMPLING_RATE"]
-    host = sig.cpu().numpy()
-    out = []
-    for k in range(host.shape[0]):
-        w = host[k, starts[k]:ends[k]][:cap]
-        out.append((w / np.max(w) * 0.75).astype(np.float32) if w.size else w.astype(np.float32))
-    return out
+    ends = [min(e, s + cap) for s, e in zip(starts, ends)]
+    # peak normalisation (time_signal / np.max(time_signal) * 0.75 over the trimmed, capped signal) on the device, one
+    # copy of the batch through a pinned buffer, then per-utterance slices
+    B, L = sig.shape
+    idx = torch.arange(L, device=sig.device)[None, :]
+    lo = torch.tensor(starts, device=sig.device)[:, None]
+    hi = torch.tensor(ends, device=sig.device)[:, None]
+    inside = (idx >= lo) & (idx < hi)
+    peak = torch.where(inside, sig, torch.full_like(sig, -float("inf"))).amax(dim=1, keepdim=True)
+    scaled = sig * (0.75 / peak)
+    host = _pinned_like(scaled)
+    host.copy_(scaled, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    arr = host.numpy()
+    return [arr[k, starts[k]:ends[k]].copy() if ends[k] > starts[k] else np.zeros(0, np.float32) for k in range(B)]
+
+
+_PINNED = {}
+
+
+def _pinned_like(t: torch.Tensor) -> torch.Tensor:
+    """A reusable pinned host buffer of t's shape (one per shape: the corpus driver calls with a fixed batch shape)."""
+    key = (tuple(t.shape), t.dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) > 4:
+            _PINNED.clear()
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        _PINNED[key] = buf
+    return buf
 
 
 def write_wav(path, samples: np.ndarray, sampling_rate: int) -> None:
