@@ -148,7 +148,8 @@ def run(args, on_batch=None) -> Dict[str, float]:
                     path = Path(args.save_wav) / (output_name(speakers[u.speaker], u.sentence) + ".wav")
                     path.parent.mkdir(parents=True, exist_ok=True)
                     vocoder.write_wav(path, w, cfg["SAMPLING_RATE"])
-            lin = lin_d.cpu().numpy()
+            # the 114 MB spectrogram batch crosses PCIe only when somebody wants it on the host
+            lin = lin_d.cpu().numpy() if (on_batch is not None or args.save_spectrogram) else None
             m1.check()
             n_utt += len(group)
             if on_batch is not None:
