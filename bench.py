@@ -51,7 +51,8 @@ DECODE_FLOP_PER_FRAME = 13_630_000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default: 30 for the native arm, 8 for the CPU reference arm: 3.4 s per step there)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -61,7 +62,10 @@ def parse():
                          "Text2Mel always runs the fp32 arm (identical alignments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 8 if args.impl == "reference" else 30
+    return args
 
 
 def measured_peaks():
