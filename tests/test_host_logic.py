@@ -116,3 +116,37 @@ def test_driver_texts_speakers_plan(tmp_path, write_driver_cfg):
     seen = [u for r in range(2) for b in G.plan(3, 4, 2, r, 5) for u in b]
     assert seen == [Unit(s, k) for s in range(3) for k in range(4)]
     assert [len(b) for b in G.plan(3, 4, 1, 0, 5)] == [5, 5, 2]
+
+
+def test_collate_functions_pad_like_the_reference():
+    """data/dataset.py:184-263: text ids are padded with id 0 ('P'), spectrograms with zero frames, to the batch maxima."""
+    import torch
+    from spoofsv_b200.data import collate_pad_2, collate_pad_3, collate_pad_4
+    mk = lambda t_mel, n_txt: {"data_0": torch.ones(80, t_mel), "data_1": torch.full((1, n_txt), 5, dtype=torch.int64),
+                              "data_2": torch.ones(200, 1), "data_3": torch.ones(513, 4 * t_mel)}
+    b3 = collate_pad_3([mk(7, 4), mk(5, 9)])
+    assert tuple(b3["data_0"].shape) == (2, 80, 7) and tuple(b3["data_1"].shape) == (2, 1, 9) and tuple(b3["data_2"].shape) == (2, 200, 1)
+    assert b3["data_1"].dtype == torch.int64 and int(b3["data_1"][0, 0, 4:].sum()) == 0 and float(b3["data_0"][1, :, 5:].abs().sum()) == 0
+    b4 = collate_pad_4([mk(3, 2), mk(6, 2)])
+    assert tuple(b4["data_3"].shape) == (2, 513, 24) and float(b4["data_3"][0, :, 12:].abs().sum()) == 0
+    b2 = collate_pad_2([{"data_0": torch.ones(80, 3), "data_1": torch.ones(513, 12)}, {"data_0": torch.ones(80, 4), "data_1": torch.ones(513, 16)}])
+    assert tuple(b2["data_0"].shape) == (2, 80, 4) and tuple(b2["data_1"].shape) == (2, 513, 16)
+
+
+def test_dataset_reads_the_reference_path_lists(tmp_path):
+    from spoofsv_b200.data import dataset
+    from spoofsv_b200 import text as T
+    root = tmp_path / "d"
+    (root / "data_path" / "ordinary").mkdir(parents=True)
+    (root / "data_path" / "ubm-finetune").mkdir(parents=True)
+    (root / "data_path" / "ordinary" / "wav.path.train").write_text("/x/wav22/p225/p225_001.wav\n/x/wav22/p226/p226_004.wav\n")
+    (root / "data_path" / "ordinary" / "txt.path.train").write_text("/x/txt/p225/p225_001.txt\n/x/txt/p226/p226_004.txt\n")
+    (root / "data_path" / "ubm-finetune" / "wav.path.ubm.validate").write_text("/x/wav22/p227/p227_002.wav\n")
+    (root / "data_path" / "ubm-finetune" / "txt.path.ubm.validate").write_text("/x/txt/p227/p227_002.txt\n")
+    cfg = {"DATA_ROOT_DIR": str(root) + "/", "SPK_EMB_DIR": "/x/spk/", "VOCABULARY": T.DEFAULT_VOCABULARY}
+    ds = dataset(cfg, mode="train")
+    assert len(ds) == 2 and ds.wavlist[1].endswith("p226_004.wav") and ds.wavlist[1][-12:-8] == "p226"
+    assert len(dataset(cfg, mode="validate", pattern="ubm-finetune", stage="ubm")) == 1
+    import pytest
+    with pytest.raises(ValueError):
+        dataset(cfg, mode="train", pattern="ubm-finetune", stage=None)
