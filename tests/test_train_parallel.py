@@ -80,3 +80,20 @@ def test_allreduce_is_a_noop_without_a_process_group():
     p = torch.nn.Parameter(torch.ones(3))
     p.grad = torch.full((3,), 2.0)
     assert allreduce_gradients([p]) == 0 and float(p.grad[0]) == 2.0
+
+
+def test_discriminators_keep_the_reference_state_dict_layout():
+    """models/discriminator.py:6-80: parameter names and shapes (checkpoints carry `disc_state_dict`)."""
+    from spoofsv_b200.train import guided_attention_mat, linDisc, melDisc
+    m, l = melDisc(80, 128), linDisc(513, 128)
+    keys = list(m.state_dict().keys())
+    assert keys[:4] == ["conv1.weight", "conv1.bias", "ln1.weight", "ln1.bias"]
+    assert keys[4:10] == ["hc.conv.weight", "hc.conv.bias", "hc.ln1.weight", "hc.ln1.bias", "hc.ln2.weight", "hc.ln2.bias"]
+    assert list(l.state_dict().keys()) == keys
+    assert tuple(m.state_dict()["hc.conv.weight"].shape) == (256, 128, 3) and tuple(m.state_dict()["conv4.weight"].shape) == (4, 16, 1)
+    assert tuple(l.state_dict()["conv4.weight"].shape) == (8, 16, 1) and tuple(l.state_dict()["conv1.weight"].shape) == (128, 513, 1)
+    assert sum(p.numel() for p in m.parameters()) == 119233          # SURVEY 8e: elements all-reduced on a D step
+    x = torch.rand(2, 80, 40)
+    assert tuple(m.eval()(x).shape) == (2, 1, 1)
+    w = guided_attention_mat(186, 325)
+    assert tuple(w.shape) == (186, 325) and float(w[0, 0]) == 0.0 and 0.99 < float(w[0, 324]) <= 1.0
