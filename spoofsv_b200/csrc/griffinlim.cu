@@ -7,15 +7,15 @@
 //
 // As a chain of library calls every iteration walks the (B, 513, T) complex spectrogram about a dozen times
 // (complex multiply, irfft, window, overlap-add, envelope division, padding, framing, rfft, momentum update,
-// abs, divide): 3.3 ms per iteration for 64 utterances x 1304 frames.  Here an iteration is three kernels and
-// roughly two passes over the data:
+// abs, divide): 2.4 ms per iteration for 64 utterances x 1304 frames.  Here an iteration is two kernels:
 //
-//   gl_istft_kernel   one frame PAIR per trip: Z = A + iB (two Hermitian spectra packed into one complex signal, so
-//                     one 1024-point complex FFT inverts both), shared-memory Stockham radix-4 FFT, window, store
-//                     the two windowed frames;
-//   gl_ola_kernel     overlap-add of the 4 frames covering a sample, division by the window sum-square;
-//   gl_stft_kernel    frame pair a + ib gathered from the signal with reflect padding, window, FFT, unpack the two
-//                     spectra, momentum update and phase normalisation fused into the epilogue.
+//   gl_istft_ola_kernel  a CTA owns 24 consecutive output hops of one utterance; the frames touching them go through
+//                        the FFT as PAIRS (Z = A + iB: two Hermitian spectra packed into one complex signal, so one
+//                        1024-point complex FFT inverts both; shared-memory Stockham radix 4), and their windowed
+//                        segments are overlap-added in shared memory in frame order; the window sum-square division
+//                        is applied on the way out.  Three halo frames per chunk are recomputed instead of exchanged.
+//   gl_stft_kernel       frame pair a + ib gathered from the signal with reflect padding, window, FFT, unpack the two
+//                        spectra, momentum update and phase normalisation fused into the epilogue.
 //
 // Spectra live in a time-major layout (B, T, 513) inside the loop (a frame's bins are contiguous), S and the initial
 // phases are transposed once.  FFT size and hop are the reference's (n_fft = win_length = 1024, hop = 256).
@@ -111,15 +111,14 @@ __global__ void gl_setup_kernel(const float* __restrict__ S, const float2* __res
   }
 }
 
-// Inverse STFT of frame pairs: frames[b][t][n] = w[n] * irfft(S[b][t] * ang[b][t])[n].
+// Operands of one frame pair for the inverse STFT (S * angles of frames t and t + 1).
 // The spectra of the next pair are fetched into registers before the FFT passes of the current one.
 struct IstftRegs {
   float2 A[3], Bv[3];      // bins tid, tid + 256, (tid == 0: 512) of the two frames, already scaled by S
 };
 
-__device__ __forceinline__ void istft_fetch(IstftRegs& r, const float* __restrict__ St, const float2* __restrict__ ang,
-                                            int T, long pr, int pairs_per_utt, int tid) {
-  const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
+__device__ __forceinline__ void istft_fetch_bt(IstftRegs& r, const float* __restrict__ St, const float2* __restrict__ ang,
+                                               int T, int b, int t, int tid) {
   const bool second = t + 1 < T;
   const float* Sa = St + ((long)b * T + t) * GL_F;
   const float2* Aa = ang + ((long)b * T + t) * GL_F;
@@ -140,76 +139,69 @@ __device__ __forceinline__ void istft_fetch(IstftRegs& r, const float* __restric
   }
 }
 
-__global__ void __launch_bounds__(GL_T) gl_istft_kernel(const float* __restrict__ St, const float2* __restrict__ ang,
-                                                        int T, long n_pairs, int pairs_per_utt,
-                                                        float* __restrict__ frames) {
+// Inverse STFT with the overlap-add fused in: a CTA owns GL_CH consecutive output hops of one utterance, runs the
+// (up to GL_CH + 3) frames that touch them -- three frames of halo are recomputed instead of exchanged -- through the
+// paired FFT, and accumulates their windowed segments in shared memory in frame order (deterministic, no atomics).
+// The windowed frames never go to global memory (35 % of the loop's DRAM traffic), and there is no separate
+// overlap-add pass.
+constexpr int GL_CH = 24;
+__global__ void __launch_bounds__(GL_T) gl_istft_ola_kernel(const float* __restrict__ St, const float2* __restrict__ ang,
+                                                            int T, int chunks_per_utt, float* __restrict__ y) {
   __shared__ GlSmem sm;
+  extern __shared__ float accs[];                       // [GL_CH][256]
   const int tid = threadIdx.x;
+  const int b = blockIdx.x / chunks_per_utt, c = blockIdx.x % chunks_per_utt;
+  const int o0 = c * GL_CH;                              // first output hop of this chunk
+  const int nh = min(GL_CH, (T - 1) - o0);               // output hops here (the signal has T - 1 hops)
+  const int t_lo = max(0, o0 - 1), t_hi = min(T - 1, o0 + nh + 1);      // frames touching padded hops o0 + 2 .. o0 + nh + 1
   gl_tables(sm, tid);
+  for (int i = tid; i < GL_CH * GL_HOP; i += GL_T) accs[i] = 0.f;
   IstftRegs cur;
-  if ((long)blockIdx.x < n_pairs) istft_fetch(cur, St, ang, T, blockIdx.x, pairs_per_utt, tid);
+  istft_fetch_bt(cur, St, ang, T, b, t_lo, tid);
   __syncthreads();
-  for (long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-    const int b = (int)(pr / pairs_per_utt), t = 2 * (int)(pr % pairs_per_utt);
-    const bool second = t + 1 < T;
-    // Z[k] = A[k] + i B[k] (k <= 512), Z[1024 - k] = conj(A[k]) + i conj(B[k]); irfft ignores Im of bins 0 and 512
+  const float sc = 1.0f / (float)GL_N;
+  for (int t = t_lo; t <= t_hi; t += 2) {
+    const bool second = t + 1 <= t_hi;                  // a frame past t_hi contributes nothing here: drop it
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int k = tid + GL_T * i;
       if (i < 2 || tid == 0) {
-        float2 A = cur.A[i], Bv = cur.Bv[i];
+        float2 A = cur.A[i], Bv = second ? cur.Bv[i] : make_float2(0.f, 0.f);
         if (k == 0 || k == GL_N / 2) { A.y = 0.f; Bv.y = 0.f; }
         sm.a[pidx(k)] = make_float2(A.x - Bv.y, A.y + Bv.x);
         if (k > 0 && k < GL_N / 2) sm.a[pidx(GL_N - k)] = make_float2(A.x + Bv.y, Bv.x - A.y);
       }
     }
     __syncthreads();
-    if (pr + gridDim.x < n_pairs) istft_fetch(cur, St, ang, T, pr + gridDim.x, pairs_per_utt, tid);   // lands under the FFT
+    if (t + 2 <= t_hi) istft_fetch_bt(cur, St, ang, T, b, t + 2, tid);      // lands under the FFT
     fft1024<true>(sm, tid);
-    float* fa = frames + ((long)b * T + t) * GL_N;
-    const float sc = 1.0f / (float)GL_N;
-    for (int n = tid; n < GL_N; n += GL_T) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                        // segment q of frame t lands in padded hop t + q = output hop t + q - 2
+      const int n = tid + GL_HOP * q;
       const float2 z = sm.b[pidx(n)];
       const float w = sm.win[n] * sc;
-      fa[n] = z.x * w;
-      if (second) fa[GL_N + n] = z.y * w;
+      const int ia = t + q - 2 - o0, ib = ia + 1;
+      if (ia >= 0 && ia < nh) accs[ia * GL_HOP + tid] += z.x * w;
+      if (second && ib >= 0 && ib < nh) accs[ib * GL_HOP + tid] += z.y * w;
     }
     __syncthreads();
   }
-}
-
-// y[b][m] = sum_t frames[b][t][m + 512 - 256 t] / sum_t w^2[m + 512 - 256 t]   (centre trimmed: m in [0, 256 (T - 1)))
-// Four consecutive samples per thread (L is a multiple of 256, so a float4 never straddles a hop or an utterance).
-__global__ void gl_ola_kernel(const float* __restrict__ frames, int B, int T, long L, float* __restrict__ y) {
-  const long total4 = (long)B * L / 4;
-  for (long i4 = blockIdx.x * (long)blockDim.x + threadIdx.x; i4 < total4; i4 += (long)gridDim.x * blockDim.x) {
-    const long i = i4 * 4;
-    const int b = (int)(i / L);
-    const long m = i % L;
-    const long p = m + GL_N / 2;
-    const int tq = (int)(p / GL_HOP);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), wss = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool interior = tq >= 3 && tq < T;            // all four frames exist: Hann^2 at 75 % overlap sums to 1.5
+  float* yb = y + (long)b * GL_HOP * (T - 1) + (long)o0 * GL_HOP;
+  for (int i = tid; i < nh * GL_HOP; i += GL_T) {
+    const int h = o0 + i / GL_HOP + 2, r = i % GL_HOP;   // padded hop, offset in it
+    float wss = 1.5f;                                    // Hann^2 at 75 % overlap, all four frames present
+    if (h < 3 || h > T - 1) {
+      wss = 0.f;
 #pragma unroll
-    for (int d = 3; d >= 0; --d) {
-      const int t = tq - d;
-      if (t >= 0 && t < T) {
-        const int n = (int)(p - (long)t * GL_HOP);
-        const float4 f = *reinterpret_cast<const float4*>(frames + ((long)b * T + t) * GL_N + n);
-        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
-        if (!interior) {
-          const float w0 = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)GL_N);
-          const float w1 = 0.5f - 0.5f * cospif(2.0f * (float)(n + 1) / (float)GL_N);
-          const float w2 = 0.5f - 0.5f * cospif(2.0f * (float)(n + 2) / (float)GL_N);
-          const float w3 = 0.5f - 0.5f * cospif(2.0f * (float)(n + 3) / (float)GL_N);
-          wss.x = fmaf(w0, w0, wss.x); wss.y = fmaf(w1, w1, wss.y); wss.z = fmaf(w2, w2, wss.z); wss.w = fmaf(w3, w3, wss.w);
+      for (int d = 0; d < 4; ++d) {
+        const int t = h - d;
+        if (t >= 0 && t < T) {
+          const float w = sm.win[r + GL_HOP * d];
+          wss = fmaf(w, w, wss);
         }
       }
     }
-    if (interior) wss = make_float4(1.5f, 1.5f, 1.5f, 1.5f);
-    const float tiny = 1.17549435e-38f;
-    *reinterpret_cast<float4*>(y + i) = make_float4(wss.x > tiny ? acc.x / wss.x : acc.x, wss.y > tiny ? acc.y / wss.y : acc.y,
-                                                    wss.z > tiny ? acc.z / wss.z : acc.z, wss.w > tiny ? acc.w / wss.w : acc.w);
+    yb[i] = wss > 1.17549435e-38f ? accs[i] / wss : accs[i];
   }
 }
 
@@ -296,7 +288,7 @@ static size_t st_floats(size_t bt) { return (bt * GL_F + 3) / 4 * 4; }
 
 size_t griffin_lim_workspace_floats(int B, int T) {
   const size_t bt = (size_t)B * T;
-  return st_floats(bt) /*St*/ + 2 * bt * GL_F /*ang*/ + 2 * bt * GL_F /*tprev*/ + bt * GL_N /*frames*/;
+  return st_floats(bt) /*St*/ + 2 * bt * GL_F /*ang*/ + 2 * bt * GL_F /*tprev*/;
 }
 
 int launch_griffin_lim(const float* S, const float* angles0_ri, int B, int T, int n_iter, float momentum, float* y,
@@ -305,25 +297,28 @@ int launch_griffin_lim(const float* S, const float* angles0_ri, int B, int T, in
   float* St = workspace;
   float2* ang = reinterpret_cast<float2*>(St + st_floats(bt));
   float2* tprev = ang + bt * GL_F;
-  float* frames = reinterpret_cast<float*>(tprev + bt * GL_F);
   const long L = (long)GL_HOP * (T - 1);
   const int pairs_per_utt = (T + 1) / 2;
   const long n_pairs = (long)B * pairs_per_utt;
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int fft_grid = (int)(n_pairs < (long)sms * 6 ? n_pairs : (long)sms * 6);
-  long ola_blocks = ((long)B * L / 4 + 255) / 256;
-  if (ola_blocks > (long)sms * 32) ola_blocks = (long)sms * 32;
   const float c = momentum / (1.0f + momentum);
 
   gl_setup_kernel<<<dim3((T + 31) / 32, (GL_F + 31) / 32, B), dim3(32, 8), 0, s>>>(
       S, reinterpret_cast<const float2*>(angles0_ri), B, T, St, ang);
   SSV_CUDA(cudaGetLastError());
   ++g_launches;
+  const int chunks_per_utt = (T - 1 + GL_CH - 1) / GL_CH;
+  const size_t acc_bytes = (size_t)GL_CH * GL_HOP * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    SSV_CUDA(cudaFuncSetAttribute(gl_istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+    configured = true;
+  }
   for (int it = 0; it <= n_iter; ++it) {
-    gl_istft_kernel<<<fft_grid, GL_T, 0, s>>>(St, ang, T, n_pairs, pairs_per_utt, frames);
-    gl_ola_kernel<<<(int)ola_blocks, 256, 0, s>>>(frames, B, T, L, y);
-    g_launches += 2;
+    gl_istft_ola_kernel<<<B * chunks_per_utt, GL_T, acc_bytes, s>>>(St, ang, T, chunks_per_utt, y);
+    ++g_launches;
     if (it == n_iter) break;
     gl_stft_kernel<<<fft_grid, GL_T, 0, s>>>(y, T, L, n_pairs, pairs_per_utt, c, it == 0 ? 1 : 0, ang, tprev);
     ++g_launches;
