@@ -46,6 +46,7 @@ DECODE_STATE_BYTES_PER_UTT = 16 * 3 * 256 * 4 + 6 * 1024 + 640       # taps r/w,
 SSRN_FLOP_PER_FRAME = 46_469_144
 TEXTENC_FLOP_PER_CHAR = 34_218_496
 DECODE_FLOP_PER_FRAME = 13_630_000
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12         # 74.45
 
 
 def parse():
@@ -62,6 +63,8 @@ def parse():
                          "Text2Mel always runs the fp32 arm (identical alignments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
+    ap.add_argument("--dump-lin", default=None, help="(reference arm) write the sample's linear spectrogram to this .npy")
+    ap.add_argument("--no-eager", action="store_true", help="skip extra.torch_eager_gpu")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 8 if args.impl == "reference" else 30
@@ -194,12 +197,39 @@ def cpu_reference_step(sd1, sd2, ids, spk, frames):
         return time.perf_counter() - t0, lin
 
 
+def reference_module_step(R, r1, r2, ids, spk, frames):
+    """One step through the UNMODIFIED reference module (oracle/_ref/models/TTSModel.py) on its own `device`:
+    the AR loop of generate_test_utterances.py:105-116 + SSRN (:120)."""
+    import torch
+    from oracle import build_ref
+    with torch.no_grad():
+        tid = torch.from_numpy(ids)[:, None, :].to(R.device)
+        e = torch.from_numpy(spk)[:, :, None].to(R.device)
+        if R.device.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Y, A, pma = build_ref.ar_loop(R, r1, tid, e, frames)
+        lin = r2(Y)
+        if R.device.type == "cuda":
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0, lin
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path, rank 0 only.
+
+    With oracle/_ref staged (oracle/build_ref.py) this is the unmodified models/TTSModel.py (`kind: "reference"`),
+    otherwise the oracle port (`kind: "port"`).  Every step is a bounded sample of the native arm's workload
+    (`--cpu-sample` of its `batch_per_gpu` utterances, all frames); `config` is the native arm's."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""            # the reference binds `device` at import: this arm is the CPU path
+    import warnings
+    warnings.filterwarnings("ignore")
+    import numpy as np
     import torch
+    from oracle import build_ref
     from oracle import weights as W
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -207,23 +237,78 @@ def run_reference(args):
     nb = max(1, min(args.cpu_sample, args.batch))
     ids, spk = workload(args.batch, 0)
     ids, spk = ids[:nb], spk[:nb]
+    if build_ref.available():
+        R = build_ref.load()
+        r1, r2 = build_ref.models(R, sd1, sd2, W.CFG)
+        step = lambda frames: reference_module_step(R, r1, r2, ids, spk, frames)
+        kind, what = "reference", "unmodified reference models/TTSModel.py (oracle/_ref) driven by the loop of generate_test_utterances.py:105-116"
+    else:
+        step = lambda frames: cpu_reference_step(sd1, sd2, ids, spk, frames)
+        kind, what = "port", "oracle port of models/TTSModel.py"
     for _ in range(args.warmup):
-        cpu_reference_step(sd1, sd2, ids, spk, min(args.frames, 8))       # short warm-up: thread pools, oneDNN primitives
-    times = [cpu_reference_step(sd1, sd2, ids, spk, args.frames)[0] for _ in range(args.steps)]
+        step(min(args.frames, 8))       # short warm-up: thread pools, oneDNN primitives
+    times, lin = [], None
+    for _ in range(args.steps):
+        sec, lin = step(args.frames)
+        times.append(sec)
+    if args.dump_lin:
+        np.save(args.dump_lin, lin.cpu().numpy())
     total = sum(times)
     value = nb * args.frames * args.steps / total
-    sample = (f"{nb} of the {args.batch} utterances per step, all {args.frames} frames, reference re-encoding AR loop + SSRN "
-              f"(oracle port of models/TTSModel.py, torch {torch.__version__} CPU fp32)")
+    sample = (f"{nb} of the {args.batch} utterances per step, all {args.frames} frames, re-encoding AR loop + SSRN: "
+              f"{what}, torch {torch.__version__} CPU fp32, {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": config_dict(args, args.batch),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "bounded_sample": {"utterances_per_step": nb, "of_batch_per_gpu": args.batch,
+                           "note": "ms_per_step is the time of the sample; value = sample frames / sample time"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def torch_eager_gpu(sd1, sd2, ids, spk, frames):
+    """Same-GPU comparison, outside the timed region, clearly NOT the product path: stock eager PyTorch on this B200.
+    (a) the unmodified reference module (oracle/_ref) driven by the reference's re-encoding AR loop + SSRN, whole
+    batch; (b) the oracle's O(T) incremental loop + SSRN as eager torch ops on the GPU.  PyTorch defaults (cuDNN convs
+    may use TF32).  One warm-up of a few frames, then one timed run each (wall clock around synchronize)."""
+    import torch
+    from oracle import build_ref
+    from oracle import ttsmodel_oracle as O
+    from oracle import weights as W
+    out = {"note": "stock eager PyTorch on the same GPU, cudnn.allow_tf32 default; reported for context, not the product path"}
+    B = ids.shape[0]
+    try:
+        with torch.no_grad():
+            if build_ref.available():
+                R = build_ref.load()
+                if R.device.type == "cuda":
+                    r1, r2 = build_ref.models(R, sd1, sd2, W.CFG)
+                    reference_module_step(R, r1, r2, ids, spk, 6)
+                    sec, _ = reference_module_step(R, r1, r2, ids, spk, frames)
+                    out["reference_loop"] = {"ms": 1e3 * sec, "frames_per_s": B * frames / sec, "batch": B,
+                                             "what": "unmodified models/TTSModel.py, generate_test_utterances.py:105-116 loop + SSRN"}
+                    del r1, r2
+            g1 = {k: v.cuda() for k, v in sd1.items()}
+            g2 = {k: v.cuda() for k, v in sd2.items()}
+            tid = torch.from_numpy(ids)[:, None, :].cuda()
+            e = torch.from_numpy(spk)[:, :, None].cuda()
+            with torch.device("cuda"):
+                O.synthesize(g1, g2, tid, e, 6, incremental=True)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                O.synthesize(g1, g2, tid, e, frames, incremental=True)
+                torch.cuda.synchronize()
+                sec = time.perf_counter() - t0
+            out["incremental_loop"] = {"ms": 1e3 * sec, "frames_per_s": B * frames / sec, "batch": B,
+                                       "what": "oracle incremental (O(T)) loop + SSRN as eager torch ops on the GPU"}
+    except Exception as exc:      # context only: never fail the bench line over it
+        out["error"] = f"{type(exc).__name__}: {exc}"
+    return out
 
 
 def config_dict(args, batch):
@@ -284,7 +369,7 @@ def main():
     def device_step(parts=None):
         e = [ev() for _ in range(4)]
         e[0].record()
-        K, V = m1.encode_text(ids_d)
+        K, V = m1.encode_text(ids_d, check=False)      # ids are verified on the device; m1.check() after the loop reports
         dec = m1._begin(K, V, spk_d, T)
         e[1].record()
         _lib.check(lib.ssv_decoder_run(dec, T, _lib.current_stream_ptr()))
@@ -483,22 +568,47 @@ def main():
                      "achieved": dec_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm"],
                      "traffic": traffic, "peak_source": peaks["source"],
                      "algorithmic_bytes_per_launch": dec_bytes, "us_per_frame": 1e3 * dec_ms / T},
+        "roofline_fma": {"kernel": "decode_ws_kernel", "bound": "fp32 FMA", "achieved": B * T * DECODE_FLOP_PER_FRAME / (dec_ms * 1e-3) / 1e12,
+                         "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": B * T * DECODE_FLOP_PER_FRAME / (dec_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                         "peak_source": "148 SMs x 128 lanes x 2 x 1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)"},
         "roofline_ssrn": {"bound": "tensor", "achieved": ssrn_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                           "frac": ssrn_tflops / peaks["bf16_sustained"], "precision": args.ssrn_precision},
         "extra": extra,
     }
+    if rank == 0 and world == 1 and not args.no_eager:
+        line["extra"]["torch_eager_gpu"] = torch_eager_gpu(sd1, sd2, ids_np, spk_np, T)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import build_ref
         cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
         nb = max(1, min(args.cpu_sample, B))
-        cpu_reference_step(sd1, sd2, ids_np[:nb], spk_np[:nb], 8)
-        sec, olin = cpu_reference_step(sd1, sd2, ids_np[:nb], spk_np[:nb], T)
         got = syn.synthesize_host(ids_np, spk_np, T)["lin"][:nb]
-        line["cpu_baseline"] = {
-            "value": nb * T / sec, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{nb} of the {B} utterances, all {T} frames, reference re-encoding AR loop + SSRN (oracle port, torch CPU fp32)",
-            "max_abs_err_vs_gpu_lin": float(np.abs(got - olin.numpy()).max()),
-            "rel_l2_err_vs_gpu_lin": float(np.linalg.norm((got - olin.numpy()).ravel()) / np.linalg.norm(olin.numpy().ravel()))}
+        olin, cb = None, None
+        if build_ref.available():
+            # the unmodified reference module on the host cores, in a child process with the GPUs hidden (the module
+            # binds `device` at import): one timed step of the bounded sample, its spectrogram kept for the check below
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                dump = os.path.join(td, "lin.npy")
+                cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                       "--batch", str(B), "--frames", str(T), "--cpu-sample", str(nb), "--dump-lin", dump]
+                env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, timeout=900)
+                for ln in r.stdout.splitlines():
+                    if ln.startswith("{"):
+                        cb = json.loads(ln)["cpu_baseline"]
+                if cb is not None and os.path.exists(dump):
+                    olin = np.load(dump)
+        if cb is None:
+            torch.set_num_threads(cores)
+            cpu_reference_step(sd1, sd2, ids_np[:nb], spk_np[:nb], 8)
+            sec, o = cpu_reference_step(sd1, sd2, ids_np[:nb], spk_np[:nb], T)
+            olin = o.numpy()
+            cb = {"value": nb * T / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                  "sample": f"{nb} of the {B} utterances, all {T} frames, reference re-encoding AR loop + SSRN (oracle port, torch CPU fp32)"}
+        cb["max_abs_err_vs_gpu_lin"] = float(np.abs(got - olin).max())
+        cb["rel_l2_err_vs_gpu_lin"] = float(np.linalg.norm((got - olin).ravel()) / np.linalg.norm(olin.ravel()))
+        line["cpu_baseline"] = cb
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -67,6 +67,11 @@ int ssv_text2mel_destroy(ssv_text2mel* m);
 int ssv_text_encoder_fwd(ssv_text2mel* m, const int64_t* textid, int B, int N, float* K, float* V,
                          int precision, void* stream);
 
+/* Synchronise `stream` and report text ids outside [0, vocab_len) seen by the embedding gather since the last
+ * check (textEmbedding.forward, models/TTSModel.py:25-35, would raise from scatter_): SSV_EINVAL.  The id range is
+ * verified on the device inside the gather, so the hot path needs no host round trip before launching. */
+int ssv_text2mel_check(ssv_text2mel* m, void* stream);
+
 /* replaces the train branch of melSyn.forward (models/TTSModel.py:263-273; teacher-forced, as the training loops
  * call it: train/adversarial_wasserstein_gp.py:277-278): full-sequence forward, unmasked attention.  melspec: dev
  * (B, F, T); textid: dev int64 (B, 1, N); spkemb: dev (B, E, 1); Y: dev (B, F, T); A: dev (B, N, T).  Forward only:
@@ -91,6 +96,10 @@ int ssv_decoder_step(ssv_decoder* d, const float* x, long x_stride_b, long x_str
 /* n_steps frames free-running in one launch: x_0 = 0 (or Y[:, :, t-1] when continuing),
  * x_t = y_{t-1}. */
 int ssv_decoder_run(ssv_decoder* d, int n_steps, void* stream);
+/* Front-end shape of the decode kernel for the batches begun after this call: rows per micro-batch (1, 2, 4) and
+ * front-end warps per row (1, 2, 4); 0 = the measured choice for the batch size.  Tuning and test hook: every
+ * shape computes the same values (tests/test_gpu_parity.py runs them all against the oracle). */
+int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_row);
 /* Frames decoded since begin. */
 int ssv_decoder_frames(const ssv_decoder* d);
 /* Synchronise `stream` and report a decode-kernel abort (barrier timeout) if one happened. */

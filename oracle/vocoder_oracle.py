@@ -93,10 +93,16 @@ def trim_bounds(y: np.ndarray, top_db: float = 30.0, frame_length: int = 2048, h
 
 
 def postprocess(pred_lin: np.ndarray, angles0: np.ndarray, cfg: dict, n_iter: int = 64) -> np.ndarray:
-    """One utterance of generate_test_utterances.py:130-139 (LOG_FEATURE false): (513, 4T) in (0, 1) -> samples."""
-    spec = (pred_lin / pred_lin.max()) ** (cfg["NORM_POWER"]["RECONSTRUCTION"] / cfg["NORM_POWER"]["ANALYSIS"])
+    """One utterance of generate_test_utterances.py:126-139: (513, 4T) in (0, 1) -> samples.  LOG_FEATURE (:126-128):
+    dB mapping instead of the max-normalisation, and the signal is written without peak scaling (:139)."""
+    log_feature = bool(cfg.get("LOG_FEATURE", False))
+    if log_feature:
+        pred_lin = np.power(10, 0.05 * (pred_lin * cfg["MAX_DB"] - cfg["MAX_DB"] + cfg["REF_DB"]))
+    else:
+        pred_lin = pred_lin / pred_lin.max()
+    spec = pred_lin ** (cfg["NORM_POWER"]["RECONSTRUCTION"] / cfg["NORM_POWER"]["ANALYSIS"])
     sig = griffinlim(spec, angles0, n_iter, cfg["STFT"]["HOP_LENGTH"], cfg["STFT"]["FFT_LENGTH"])
     sig = deemphasis(sig, cfg["PREEMPH"])
     a, b = trim_bounds(sig, 30.0)
     sig = sig[a:b][: 9 * cfg["SAMPLING_RATE"]]
-    return sig / np.max(sig) * 0.75
+    return sig if log_feature else sig / np.max(sig) * 0.75

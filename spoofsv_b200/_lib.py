@@ -39,6 +39,8 @@ SIGNATURES = {
     "ssv_decoder_step": (C.c_int, [C.c_void_p, _c_f32p, C.c_long, C.c_long, _c_i64p, C.c_void_p]),
     "ssv_decoder_run": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ssv_decoder_frames": (C.c_int, [C.c_void_p]),
+    "ssv_decoder_set_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ssv_text2mel_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssv_decoder_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssv_ssrn_create": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
                         + [C.c_int] * 4 + [C.POINTER(C.c_void_p)]),
@@ -73,6 +75,16 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    import os
+    override = os.environ.get("SSV_B200_LIB")          # development aid: an A/B build from `build.py --variant=...`
+    if override:
+        lib = C.CDLL(override)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
     if build_if_missing:
         from . import build as _build
         try:

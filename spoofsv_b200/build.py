@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libspoofsv_b200.so"
-SOURCES = ["abi.cu", "backward.cu", "conv_f32.cu", "conv_tc.cu", "decode.cu", "decode_cluster.cu", "decode_ws.cu", "griffinlim.cu", "misc.cu"]
+SOURCES = ["abi.cu", "backward.cu", "conv_f32.cu", "conv_tc.cu", "decode_ws.cu", "griffinlim.cu", "misc.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -32,13 +32,21 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), variant: str | None = None) -> Path:
+    """Compile the library.  `variant` (development aid for A/B kernel experiments): build with the extra `-D` flags in
+    `defines` into build/variants/<variant>/libspoofsv_b200.so instead of the product library; load it by pointing
+    SSV_B200_LIB at it (spoofsv_b200/_lib.py)."""
+    lib = LIB
+    out_dir = PKG / "build"
+    if variant:
+        out_dir = PKG / "build" / "variants" / variant
+        lib = out_dir / "libspoofsv_b200.so"
+        force = True
+    elif not force and not _stale():
         return LIB
     objs = []
-    out_dir = PKG / "build"
-    out_dir.mkdir(exist_ok=True)
-    common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
+    out_dir.mkdir(parents=True, exist_ok=True)
+    common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH, *[f"-D{d}" for d in defines]]
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []
@@ -55,14 +63,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [_nvcc(), "-shared", *ARCH, "-o", str(LIB), *objs]
+    cmd = [_nvcc(), "-shared", *ARCH, "-o", str(lib), *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("nvcc link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    var = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--variant=")), None)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, variant=var)
     print(path)

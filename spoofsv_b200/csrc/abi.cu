@@ -301,15 +301,14 @@ struct ssv_decoder {
   ssv_text2mel* m;
   Arena arena;
   int maxB, maxN, maxT;
-  float *raw, *hist, *Kt, *Vt, *s1, *s2;
+  float *Kt, *Vt, *s1, *s2;
   int* pma_state;
-  unsigned* bar;
   int* abort_flag;
   long long* prof = nullptr;
-  int impl = DEC_IMPL_GRID;
   unsigned long long* ws_raw = nullptr;
   float* ws_hist = nullptr;
   int seq_base = 0, R = 1, G = 1, W = 4;
+  int force_r = 0, force_w = 0;           // ssv_decoder_set_plan
   // per-batch state
   bool begun = false;
   int B = 0, N = 0, t_cap = 0, t = 0;
@@ -791,24 +790,28 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
   d->maxB = max_batch; d->maxN = max_text; d->maxT = max_frames;
   const int H = m->H;
   int st = kOk;
-  d->impl = decode_select_impl(device_sm_count());
-  if (d->impl == DEC_IMPL_WS && max_batch > WS_MAX_BATCH) d->impl = DEC_IMPL_GRID;
-  if (d->impl == DEC_IMPL_WS) {
+  if (max_batch > WS_MAX_BATCH) {
+    delete d;
+    set_error("decoder_create: max_batch %d exceeds %d", max_batch, WS_MAX_BATCH);
+    return kInval;
+  }
+  if (!decode_ws_supported(device_sm_count())) {
+    delete d;
+    set_error("decoder_create: the decode kernel needs a cooperative launch of %d co-resident CTAs (B200: 148 SMs)", WS_GRID);
+    return kState;
+  }
+  {
     const size_t bp = (size_t)round_up(max_batch, 4);
     const size_t raw_words = (size_t)DEC_STAGES * max_batch * WS_WORDS;
     if (st == kOk) st = d->arena.alloc<unsigned long long>(raw_words, &d->ws_raw);
     if (st == kOk) st = d->arena.alloc<float>((size_t)m->ws_hist_blocks * bp * H, &d->ws_hist);
     if (st == kOk && cudaMemset(d->ws_raw, 0, raw_words * sizeof(unsigned long long)) != cudaSuccess) st = kCuda;
-  } else {
-    if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_STAGES * max_batch * DEC_RAW_LD, &d->raw);
-    if (st == kOk) st = d->arena.alloc<float>((size_t)DEC_HIST * max_batch * max_frames * H, &d->hist);
   }
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * max_text * H, &d->Kt);
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * max_text * H, &d->Vt);
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * H, &d->s1);
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * H, &d->s2);
   if (st == kOk) st = d->arena.alloc<int>(max_batch, &d->pma_state);
-  if (st == kOk) st = d->arena.alloc<unsigned>(DEC_MAX_GRID, &d->bar);
   if (st == kOk) st = d->arena.alloc<int>(1, &d->abort_flag);
   if (st == kOk && getenv("SSV_DECODE_PROF")) st = d->arena.alloc<long long>((size_t)DEC_MAX_GRID * 16, &d->prof);
   if (st != kOk) { delete d; return st; }
@@ -840,15 +843,13 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
   SSV_TRY(launch_linear_small(spkemb, m->E, m->fc2_w, m->fc2_b, B, m->E, H, d->s2, H, s));
   SSV_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * (size_t)B * N * t_cap, s));
   SSV_CUDA(cudaMemsetAsync(d->pma_state, 0, sizeof(int) * B, s));
-  if (d->impl == DEC_IMPL_WS) {
-    // tags of this batch: seq_base + t + 1, strictly above every tag of earlier batches
-    d->seq_base += d->t_cap + 2;
-    if (d->seq_base > (1 << 30)) {
-      SSV_CUDA(cudaMemsetAsync(d->ws_raw, 0, (size_t)DEC_STAGES * d->maxB * WS_WORDS * sizeof(unsigned long long), s));
-      d->seq_base = 0;
-    }
-    ws_plan(B, &d->R, &d->W, &d->G);
+  // tags of this batch: seq_base + t + 1, strictly above every tag of earlier batches
+  d->seq_base += d->t_cap + 2;
+  if (d->seq_base > (1 << 30)) {
+    SSV_CUDA(cudaMemsetAsync(d->ws_raw, 0, (size_t)DEC_STAGES * d->maxB * WS_WORDS * sizeof(unsigned long long), s));
+    d->seq_base = 0;
   }
+  ws_plan(B, d->force_r, d->force_w, &d->R, &d->W, &d->G);
   d->B = B; d->N = N; d->t_cap = t_cap; d->t = 0;
   d->Y = Y; d->A = A; d->traj = reinterpret_cast<long long*>(pma_traj);
   d->begun = true;
@@ -866,7 +867,6 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   DecParams p{};
   p.stages = m->stages_dev;
   p.fin_g = m->fin_g; p.fin_b = m->fin_b;
-  p.raw = d->raw; p.hist = d->hist;
   p.Kt = d->Kt; p.Vt = d->Vt; p.s1 = d->s1; p.s2 = d->s2;
   p.Y = d->Y; p.A = d->A; p.pma_traj = d->traj;
   p.pma_in = reinterpret_cast<const long long*>(pma_in);
@@ -874,29 +874,24 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.x_ext = x_ext; p.x_sb = x_sb; p.x_sf = x_sf;
   p.B = d->B; p.N = d->N; p.t_cap = d->t_cap; p.F = m->F; p.H = m->H;
   p.t_start = d->t; p.n_steps = n_steps;
-  p.RG = 1;
-  p.bar_counter = d->bar;
   p.abort_flag = d->abort_flag;
   p.prof = d->prof;
   p.ws_stages = m->ws_stages_dev;
   p.ws_raw = d->ws_raw; p.ws_hist = d->ws_hist;
   p.seq_base = d->seq_base; p.R = d->R; p.G = d->G; p.W = d->W;
-  const int sms = device_sm_count();
-  SSV_CHECK(sms > 0, "decoder: no CUDA device");
   if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 16, s));
-  SSV_TRY(launch_decode(p, sms, d->impl, s));
+  SSV_TRY(launch_decode_ws(p, s));
   if (d->prof) {   // development aid: per-phase SM cycles, mean / max over CTAs, per stage visit
     SSV_CUDA(cudaStreamSynchronize(s));
-    const bool ws = d->impl == DEC_IMPL_WS;
-    const int stride = ws ? 16 : 8, cnt_slot = ws ? 15 : 7, n_ph = ws ? 15 : 7;
+    const bool ws = true;
+    const int stride = 16, cnt_slot = 15, n_ph = 15;
     std::vector<long long> h((size_t)DEC_MAX_GRID * 16);
     SSV_CUDA(cudaMemcpy(h.data(), d->prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
-    const char* nm_old[7] = {"loop-top", "arm/arrive+prefetch-issue", "wait", "prologue", "cp.async-wait+sync", "gemv", "tail (sync / bulk-copy issue)"};
     const char* nm_ws[15] = {"FE loop-top", "FE wait X buffer empty", "FE tap prefetch issue", "FE wait for producer sentinel", "FE row poll / load (tags verified)", "FE ring write + tap prefetch", "FE prologue math + X stores", "-",
                              "MV wait taps", "MV old taps (2/3)", "MV wait current tap", "MV current tap + k-slice store", "MV reducer: reduce + publish",
                              "sentinel seen -> my sentinel out", "curfull arrive -> MV awake (highway)"};
-    const char* const* nm = ws ? nm_ws : nm_old;
-    fprintf(stderr, "[decode prof] impl=%d B=%d R=%d W=%d G=%d steps=%d (cycles per stage visit: mean / max over CTAs)\n", d->impl, d->B, d->R, d->W, d->G, n_steps);
+    const char* const* nm = nm_ws;
+    fprintf(stderr, "[decode prof] B=%d R=%d W=%d G=%d steps=%d (cycles per stage visit: mean / max over CTAs)\n", d->B, d->R, d->W, d->G, n_steps);
     for (int i = 0; i < n_ph; ++i) {
       if (nm[i][0] == '-') continue;
       double sum = 0, mx = 0; int cnt = 0;
@@ -925,6 +920,30 @@ int ssv_decoder_run(ssv_decoder* d, int n_steps, void* stream) {
 }
 
 int ssv_decoder_frames(const ssv_decoder* d) { return d ? d->t : 0; }
+
+int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_row) {
+  SSV_CHECK(d, "decoder_set_plan: null decoder");
+  SSV_CHECK(rows_per_microbatch == 0 || rows_per_microbatch == 1 || rows_per_microbatch == 2 || rows_per_microbatch == 4,
+            "decoder_set_plan: rows per micro-batch must be 0 (automatic), 1, 2 or 4");
+  SSV_CHECK(warps_per_row == 0 || warps_per_row == 1 || warps_per_row == 2 || warps_per_row == 4,
+            "decoder_set_plan: warps per row must be 0 (automatic), 1, 2 or 4");
+  d->force_r = rows_per_microbatch;
+  d->force_w = warps_per_row;
+  return kOk;
+}
+
+int ssv_text2mel_check(ssv_text2mel* m, void* stream) {
+  SSV_CHECK(m, "text2mel_check: null model");
+  SSV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  int eflag = 0;
+  SSV_CUDA(cudaMemcpy(&eflag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (eflag != 0) {
+    set_error("text id outside [0, vocab_len)");
+    cudaMemset(m->err_flag, 0, sizeof(int));
+    return kInval;
+  }
+  return kOk;
+}
 
 int ssv_decoder_check(ssv_decoder* d, void* stream) {
   SSV_CHECK(d, "decoder_check: null decoder");
@@ -1257,7 +1276,8 @@ int ssv_griffin_lim(const float* S, const float* angles0_ri, int B, int F, int T
                     float momentum, float* y, float* workspace, long long workspace_floats, void* stream) {
   SSV_CHECK(S && angles0_ri && y && workspace, "griffin_lim: null pointer");
   SSV_CHECK(F == 513 && hop == 256 && win_length == 1024, "griffin_lim: only n_fft = win_length = 1024, hop = 256 (the reference's STFT) is built, got F=%d hop=%d win=%d", F, hop, win_length);
-  SSV_CHECK(B >= 1 && T >= 3, "griffin_lim: need B >= 1 and at least 3 frames (reflect padding)");
+  // the STFT kernel reflects an index once: the signal (256 (T - 1) samples) must be longer than the 512-sample pad
+  SSV_CHECK(B >= 1 && T >= 4, "griffin_lim: need B >= 1 and at least 4 frames (single reflection of the 512-sample padding)");
   SSV_CHECK(n_iter >= 0 && momentum >= 0.f && momentum < 1.f, "griffin_lim: bad n_iter / momentum");
   SSV_CHECK(workspace_floats >= (long long)griffin_lim_workspace_floats(B, T), "griffin_lim: workspace too small");
   return launch_griffin_lim(S, angles0_ri, B, T, n_iter, momentum, y, workspace, as_stream(stream));

@@ -30,10 +30,7 @@ struct DecStage {
 };
 
 constexpr int DEC_STAGES = 24;
-constexpr int DEC_HIST = 16;
-constexpr int DEC_RAW_LD = 512;
-constexpr int DEC_XS_LD = 768;
-constexpr int DEC_MAX_GRID = 1024;   // barrier flag words
+constexpr int DEC_MAX_GRID = 1024;   // rows of the profiling buffer
 
 // ---- weight-stationary pipeline (decode_ws.cu): one CTA group per stage, weights resident in registers / shared memory
 struct WsStage {
@@ -57,13 +54,10 @@ constexpr int WS_GRID = 145;         // 16 highway layers x 8 + 17 CTAs for the 
 constexpr int WS_GEMV_THREADS = 384; // warps 4-15 of a CTA
 constexpr int WS_TAP_ROWS = 264;     // 256 input channels of a tap, padded to a multiple of 24 k-slices
 constexpr int WS_MAX_BATCH = 1024;
-enum DecodeImpl { DEC_IMPL_WS = 0, DEC_IMPL_CLUSTER = 1, DEC_IMPL_GRID = 2 };
 
 struct DecParams {
   const DecStage* stages;       // [DEC_STAGES]
   const float* fin_g; const float* fin_b;   // LN5 of the decoder (80)
-  float* raw;                   // [DEC_STAGES][B][DEC_RAW_LD]
-  float* hist;                  // [DEC_HIST][B][t_cap][H]
   const float* Kt; const float* Vt;   // [B][N][H] channels-last
   const float* s1; const float* s2;   // [B][H] hoisted speaker projections
   float* Y;                     // (B, F, t_cap) caller-owned
@@ -74,11 +68,8 @@ struct DecParams {
   const float* x_ext; long x_sb, x_sf;   // optional external frame for the first step of the launch
   int B, N, t_cap, F, H;
   int t_start, n_steps;
-  int RG;                       // row groups
-  unsigned* bar_counter;      // [DEC_MAX_GRID] per-CTA barrier flags
   int* abort_flag;
-  long long* prof;              // optional [grid][8] ([grid][16]: decode_ws) phase cycle counters (SSV_DECODE_PROF=1)
-  // weight-stationary pipeline only
+  long long* prof;              // optional [grid][16] phase cycle counters (SSV_DECODE_PROF=1)
   const WsStage* ws_stages;     // device [DEC_STAGES]
   unsigned long long* ws_raw;   // [DEC_STAGES][B][WS_WORDS] tagged words {float, tag}
   float* ws_hist;               // private input-history rings, [blocks][G][256][R]
@@ -86,16 +77,12 @@ struct DecParams {
   int R, G, W;                  // rows per micro-batch (1, 2, 4), micro-batches, front-end warps per row (1, 2, 4)
 };
 
-int launch_decode(const DecParams& p, int sm_count, int impl, cudaStream_t s);
-int launch_decode_cluster(const DecParams& p, cudaStream_t s);     // decode_cluster.cu
-int decode_cluster_capacity();
 int launch_decode_ws(const DecParams& p, cudaStream_t s);          // decode_ws.cu
 bool decode_ws_supported(int sm_count);
-void ws_plan(int B, int* R, int* W, int* G);                      // front-end shape for a batch
+// front-end shape for a batch; force_r / force_w != 0 override the measured choice (ssv_decoder_set_plan)
+void ws_plan(int B, int force_r, int force_w, int* R, int* W, int* G);
 void ws_stage_layout(const DecStage& d, WsStage* w);
 size_t ws_image_floats(const WsStage& w);
 int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStream_t s);
-int decode_select_impl(int sm_count);                              // SSV_DECODE_IMPL=ws|cluster|grid overrides
-int decode_max_grid(int* out);
 
 }  // namespace ssv

@@ -1,8 +1,8 @@
 // Weight-stationary, layer-pipelined incremental Text2Mel decode (the default decode kernel).
 //
 // Replaces the reference AR loop (generate_test_utterances.py:105-116, synthesize.py:103-109 driving the
-// eval branch of melSyn.forward, models/TTSModel.py:275-300).  Algorithm as in decode.cu: every causal
-// highwayConv keeps the history of its own input, so frame t costs O(1) instead of O(t).
+// eval branch of melSyn.forward, models/TTSModel.py:275-300): every causal highwayConv keeps the history of
+// its own input, so frame t costs O(1) instead of O(t).
 //
 // What is different here is WHERE the work lives.  The 24 mat-vec stages of a frame (AudioEnc 13,
 // attention + AudioDec 11) own 6.8 M fp32 weights = 27.3 MB; a B200 has 37 MB of registers and 33 MB of
@@ -18,7 +18,7 @@
 //
 // Inside a CTA the work is warp-specialised.  Warps 0-3 are the front end: they fetch the taps t-2d, t-d from the
 // CTA's private history ring, wait for the producer stage, redo the cheap LayerNorm / highway gate / windowed
-// attention of the input row (redundantly per consumer CTA, as decode.cu does), and fill an X buffer.  How the
+// attention of the input row (redundantly per consumer CTA), and fill an X buffer.  How the
 // four warps are dealt is a launch-time shape (ws_plan): W warps share one row (each owns 256 / W channels, the
 // LayerNorm sums cross warps through shared memory and a named barrier), R rows make a micro-batch, and
 // 4 / (R W) micro-batches are in the front end at a time.  Few utterances: W = 4 or 2, the dependent chain of a
@@ -1064,20 +1064,14 @@ int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStr
 // Shape of the front end for a batch: rows per micro-batch R, warps per row W (4 / (R W) micro-batches in flight in
 // the front end), micro-batch count G (padded to a multiple of the in-flight count; padding rows are dead).
 // Measured on B200 (us/frame).
-void ws_plan(int B, int* R, int* W, int* G) {
+void ws_plan(int B, int force_r, int force_w, int* R, int* W, int* G) {
   int r, w;
   if (B <= 12) { r = 1; w = 4; }           // B=1 28.3 us/frame, B=12 28.9 (W=2: 30.1)
   else if (B <= 32) { r = 1; w = 2; }      // B=16 30.5 (W=4: 32.7), B=24 31.8, B=32 37.1 (R=2 W=2: 39.3, W=1: 38.8)
   else if (B <= 128) { r = 2; w = 1; }     // B=40 45.1 (R=1: 46.6), B=48 47.4 (R=1: 56.5), B=64 51.7 (R=1 75.7, R=4 59), B=128 104
   else { r = 4; w = 1; }                   // B=256 220
-  if (const char* e = getenv("SSV_DECODE_R")) {          // development knobs
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) { r = v; if (r * w > 4) w = 4 / r; }
-  }
-  if (const char* e = getenv("SSV_DECODE_W")) {
-    const int v = atoi(e);
-    if ((v == 1 || v == 2 || v == 4) && r * v <= 4) w = v;
-  }
+  if (force_r == 1 || force_r == 2 || force_r == 4) { r = force_r; if (r * w > 4) w = 4 / r; }      // ssv_decoder_set_plan
+  if ((force_w == 1 || force_w == 2 || force_w == 4) && r * force_w <= 4) w = force_w;
   if (w * B > WS_MAX_BATCH) w = 1;
   const int nv = 4 / (r * w);
   int g = (B + r - 1) / r;

@@ -116,6 +116,10 @@ def cache_features(wav_path: str, spec_dir: str, cfg: dict):
     mel, lin = wav_features(y, sr, cfg)
     mel, lin = mel.cpu().numpy(), lin.cpu().numpy()
     os.makedirs(os.path.dirname(mel_f), exist_ok=True)
-    np.save(mel_f, mel)
-    np.save(lin_f, lin)
+    # several ranks (torchrun) may compute the same utterance at once: write to a private temporary file and
+    # rename it into place, so that a reader never sees a half-written array
+    for dst, arr in ((mel_f, mel), (lin_f, lin)):
+        tmp = "{}.{}.{}.tmp.npy".format(dst, os.getpid(), os.environ.get("RANK", "0"))
+        np.save(tmp, arr)
+        os.replace(tmp, dst)
     return mel, lin

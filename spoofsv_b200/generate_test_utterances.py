@@ -45,7 +45,9 @@ def build_parser() -> argparse.ArgumentParser:
     ps.add_argument("--batch", type=int, default=64, help="utterances per decode launch")
     ps.add_argument("--frames", type=int, default=None, help="frames per utterance (default MAX_FRAME_NUM + 1)")
     ps.add_argument("--speakers", type=int, default=None, help="only the first N speakers (dry runs)")
-    ps.add_argument("--ssrn_precision", default="bf16", choices=["fp32", "bf16"])
+    ps.add_argument("--ssrn_precision", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32 (default, the reference's numerics: 1e-4 max-abs) or bf16 (tcgen05 tensor cores, 2e-2 "
+                         "relative L2 on the linear spectrogram; opt-in)")
     ps.add_argument("--save_spectrogram", type=str, default=None, help="directory for s<spk>/s<spk>_<nnn>.npy")
     ps.add_argument("--save_wav", type=str, default=None,
                     help="directory for s<spk>/s<spk>_<nnn>.wav: batched GPU Griffin-Lim (64 iterations), de-emphasis, "
@@ -164,13 +166,32 @@ def run(args, on_batch=None) -> Dict[str, float]:
              "frames_per_s": n_utt * frames / sec if sec > 0 else 0.0}
     if getattr(args, "write_layouts", False):
         if world > 1:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                dist.barrier()                       # every rank's wavs are on disk
+            _wait_for_all_ranks(args, rank, world)   # every rank's wavs are on disk before rank 0 reads them
         if rank == 0:
             stats["layouts"] = write_layouts(args, cfg)
     print(json.dumps(stats), flush=True)
     return stats
+
+
+def _wait_for_all_ranks(args, rank: int, world: int, timeout_s: float = 24 * 3600.0, poll_s: float = 0.5) -> None:
+    """Synthesis uses no collective (and no process group), so the ranks meet through the file system: every rank
+    drops `<save_wav>/.done.<current_time>.<rank>` when its shard is on disk and rank 0 waits for all of them."""
+    if not args.save_wav:
+        raise ValueError("--write_layouts needs --save_wav (the synthesised wavs are its input)")
+    root = Path(args.save_wav)
+    root.mkdir(parents=True, exist_ok=True)
+    mark = lambda r: root / ".done.{}.{}".format(args.current_time, r)
+    mark(rank).write_text("ok\n")
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    while not all(mark(r).exists() for r in range(world)):
+        if time.perf_counter() - t0 > timeout_s:
+            missing = [r for r in range(world) if not mark(r).exists()]
+            raise RuntimeError("write_layouts: ranks {} did not finish their shard".format(missing))
+        time.sleep(poll_s)
+    for r in range(world):
+        mark(r).unlink()
 
 
 def write_layouts(args, cfg: dict) -> dict:

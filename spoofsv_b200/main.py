@@ -95,14 +95,18 @@ def synthesize(pattern: str, cfg: dict, spec_dir: Optional[str], current_time: s
                                         torch.nn.functional.pad(lin_gt, (0, lin.shape[-1] - lin_gt.shape[-1])))
             print("syn set ssrn loss: {} {} {}".format(l1s.item(), bds.item(), (l1s + bds).item()))
             tot_ssrn += (l1s + bds).item()
-            if cfg.get("LOG_FEATURE", False):
-                raise NotImplementedError("LOG_FEATURE waveform reconstruction is not built")
-            # synthesize.py:134-147 keeps the whole signal (no trim, no 9 s cap): Griffin-Lim, de-emphasis, peak 0.75
+            # synthesize.py:134-147 keeps the whole signal (no trim, no 9 s cap): Griffin-Lim, de-emphasis, peak 0.75;
+            # LOG_FEATURE (:134-136): dB mapping instead of the max-normalisation, signal written as is
             x = lin.to(torch.float32)
-            spec = (x / x.amax(dim=(1, 2), keepdim=True)).pow(cfg["NORM_POWER"]["RECONSTRUCTION"] / cfg["NORM_POWER"]["ANALYSIS"])
+            log_feature = bool(cfg.get("LOG_FEATURE", False))
+            power = cfg["NORM_POWER"]["RECONSTRUCTION"] / cfg["NORM_POWER"]["ANALYSIS"]
+            if log_feature:
+                spec = torch.pow(10.0, 0.05 * (x * cfg["MAX_DB"] - cfg["MAX_DB"] + cfg["REF_DB"])).pow(power)
+            else:
+                spec = (x / x.amax(dim=(1, 2), keepdim=True)).pow(power)
             sig = vocoder.deemphasis(vocoder.griffin_lim(spec, gl_iters, cfg["STFT"]["HOP_LENGTH"], cfg["STFT"]["FFT_LENGTH"]),
                                      cfg["PREEMPH"])
-            sig = (sig / sig.amax(dim=1, keepdim=True) * 0.75).cpu().numpy()
+            sig = (sig if log_feature else sig / sig.amax(dim=1, keepdim=True) * 0.75).cpu().numpy()
             for k in range(B):
                 vocoder.write_wav(sample_dir + "S{}_B{}.wav".format(k + 1, i + 1), sig[k], cfg["SAMPLING_RATE"])
                 n_wavs += 1
@@ -191,23 +195,26 @@ def adversarial_train(train_step: str, train_pattern: str, cfg: dict, spec_dir: 
     t_start = time.perf_counter()
     while epoch < cfg["MAX_EPOCHS"] and not done:
         for sp in train_loader:                              # every rank draws the same batch and keeps its slice
-            sl = TR.shard_batch(sp["data_0"].shape[0], world, rank)
-            if sl.stop == sl.start:
-                continue
+            n_items = sp["data_0"].shape[0]
+            if n_items < world:
+                continue                                     # decided from the GLOBAL batch: every rank skips together, so no
+                                                             # rank misses a collective or falls out of the G / D schedule
+            sl = TR.shard_batch(n_items, world, rank)
+            sw = TR.shard_weight(n_items, world, rank)       # uneven shards: weight by local / global items
             target = "D" if iteration % (cfg["RATIO"] + 1) else "G"
             a = sp["data_0"][sl].cuda()
             if text2mel:
                 ids, spk = sp["data_1"][sl].cuda(), sp["data_2"][sl].cuda()
                 if target == "G":
-                    t = TR.generator_step(model, disc, opt_syn, a, ids, spk, gaw, cfg)
+                    t = TR.generator_step(model, disc, opt_syn, a, ids, spk, gaw, cfg, shard_weight=sw)
                 else:
-                    t = TR.discriminator_step(model, disc, opt_disc, a, ids, spk, cfg)
+                    t = TR.discriminator_step(model, disc, opt_disc, a, ids, spk, cfg, shard_weight=sw)
             else:
                 lin_gt = sp["data_1"][sl].cuda()
                 if target == "G":
-                    t = TR.ssrn_generator_step(model, disc, opt_syn, a, lin_gt, cfg)
+                    t = TR.ssrn_generator_step(model, disc, opt_syn, a, lin_gt, cfg, shard_weight=sw)
                 else:
-                    t = TR.ssrn_discriminator_step(model, disc, opt_disc, a, lin_gt, cfg)
+                    t = TR.ssrn_discriminator_step(model, disc, opt_disc, a, lin_gt, cfg, shard_weight=sw)
             if target == "G":
                 logs["loss_train_log_syn"].append(t["loss"])
                 logs["loss_train_log_syn_onlyfromD"].append(t["disc"])
@@ -286,11 +293,13 @@ def ordinary_train(train_step: str, train_pattern: str, cfg: dict, spec_dir: Opt
     done, last = False, None
     while epoch < cfg["MAX_EPOCHS"] and not done:
         for sp in train_loader:
-            sl = TR.shard_batch(sp["data_0"].shape[0], world, rank)
-            if sl.stop == sl.start:
-                continue
+            n_items = sp["data_0"].shape[0]
+            if n_items < world:
+                continue                                     # every rank skips together (see adversarial_train)
+            sl = TR.shard_batch(n_items, world, rank)
             keys = ("data_0", "data_1", "data_2") if text2mel else ("data_0", "data_1")
-            last = TR.ordinary_step(model, opt, tuple(sp[k][sl].cuda() for k in keys), gaw, text2mel)
+            last = TR.ordinary_step(model, opt, tuple(sp[k][sl].cuda() for k in keys), gaw, text2mel,
+                                    shard_weight=TR.shard_weight(n_items, world, rank))
             if rank == 0:
                 print("global iteration {}: {}".format(iteration + 1, json.dumps(last)), flush=True)
             if iteration % cfg["VAL_EVERY_ITER"] == 0 and iteration > 0:

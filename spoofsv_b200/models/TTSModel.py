@@ -213,6 +213,8 @@ class melSyn(_Native):
             conv4=pw(h, h), ln4=nn.LayerNorm(h), conv5=pw(h, freq_bins), ln5=nn.LayerNorm(freq_bins))
         self.precision = "fp32"
         self.max_frames = 1024      # decoder capacity (reference MAX_FRAME_NUM is 325)
+        self.decode_plan = None     # (rows per micro-batch, warps per row) override of the decode kernel's front-end
+                                    # shape, None / 0 = measured choice (ssv_decoder_set_plan; tuning and tests)
         self._dec: Optional[int] = None
         self._dec_cap = (0, 0, 0)
         self._state = None
@@ -247,11 +249,18 @@ class melSyn(_Native):
             out = C.c_void_p()
             _lib.check(_lib.load().ssv_decoder_create(h, *cap, C.byref(out)))
             self._dec, self._dec_cap = out.value, cap
+        r, w = self.decode_plan or (0, 0)
+        _lib.check(_lib.load().ssv_decoder_set_plan(C.c_void_p(self._dec), int(r or 0), int(w or 0)))
         return C.c_void_p(self._dec)
 
     # ---- pieces --------------------------------------------------------------------------
-    def encode_text(self, textid: torch.Tensor):
-        """textEncoder.forward (reference :126-140): (B, 1, N) int -> K, V (B, hidden, N)."""
+    def encode_text(self, textid: torch.Tensor, check: bool = True):
+        """textEncoder.forward (reference :126-140): (B, 1, N) int -> K, V (B, hidden, N).
+
+        The id range is verified on the device by the embedding gather (no host round trip before the launch);
+        ``check=True`` synchronises afterwards and raises ValueError for an id outside [0, vocab_len), as the
+        reference's one-hot scatter would.  The decode paths pass ``check=False``: ``ssv_decoder_check`` at the end of
+        the utterance batch reports the same flag."""
         _lib.require_cuda(textid, "melSyn text ids")
         ids = textid.detach().to(torch.int64).contiguous()
         if ids.dim() != 3 or ids.shape[1] != 1:
@@ -259,12 +268,13 @@ class melSyn(_Native):
         B, _, N = ids.shape
         if B == 0 or N == 0:
             raise ValueError("textid is empty")
-        if int(ids.min()) < 0 or int(ids.max()) >= self.vocab_len:
-            raise ValueError(f"text ids must lie in [0, {self.vocab_len})")
         K = torch.empty((B, self.hidden_dim, N), device=ids.device, dtype=torch.float32)
         V = torch.empty_like(K)
-        _lib.check(_lib.load().ssv_text_encoder_fwd(self._native(), ids.data_ptr(), B, N, K.data_ptr(), V.data_ptr(),
+        h = self._native()
+        _lib.check(_lib.load().ssv_text_encoder_fwd(h, ids.data_ptr(), B, N, K.data_ptr(), V.data_ptr(),
                                                     _prec(self.precision), _lib.current_stream_ptr()))
+        if check:
+            _lib.check(_lib.load().ssv_text2mel_check(h, _lib.current_stream_ptr()))
         return K, V
 
     def _begin(self, K, V, spkemb, t_cap: int):
@@ -290,7 +300,7 @@ class melSyn(_Native):
         Returns (Y (B,F,T), A (B,N,T), pma trajectory (T,B), K, V)."""
         if n_frames < 1:
             raise ValueError("n_frames must be >= 1")
-        K, V = self.encode_text(textid)
+        K, V = self.encode_text(textid, check=False)        # bad ids surface in ssv_decoder_check below
         dec = self._begin(K, V, spkemb, n_frames)
         lib = _lib.load()
         _lib.check(lib.ssv_decoder_run(dec, n_frames, _lib.current_stream_ptr()))
@@ -373,17 +383,17 @@ class melSyn(_Native):
         N = ids.shape[-1]
         if B == 0 or T == 0 or N == 0:
             raise ValueError("empty input")
-        if int(ids.min()) < 0 or int(ids.max()) >= self.vocab_len:
-            raise ValueError(f"text ids must lie in [0, {self.vocab_len})")
         x = melspec.detach().to(torch.float32).contiguous()
         spk = spkemb.detach().to(torch.float32).contiguous()
         if spk.shape != (B, self.spkemb_dim, 1):
             raise ValueError(f"spkemb must be ({B}, {self.spkemb_dim}, 1), got {tuple(spk.shape)}")
         Y = torch.empty((B, self.freq_bins, T), device=x.device, dtype=torch.float32)
         A = torch.empty((B, N, T), device=x.device, dtype=torch.float32)
-        _lib.check(_lib.load().ssv_text2mel_train_fwd(self._native(), x.data_ptr(), ids.data_ptr(), spk.data_ptr(), B, N, T,
+        h = self._native()
+        _lib.check(_lib.load().ssv_text2mel_train_fwd(h, x.data_ptr(), ids.data_ptr(), spk.data_ptr(), B, N, T,
                                                       Y.data_ptr(), A.data_ptr(), _prec(self.precision),
                                                       _lib.current_stream_ptr()))
+        _lib.check(_lib.load().ssv_text2mel_check(h, _lib.current_stream_ptr()))      # ids verified on the device
         return Y, A
 
     def _train_forward_autograd(self, melspec, textid, spkemb):

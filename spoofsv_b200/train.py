@@ -79,6 +79,13 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_mb: float =
     return total
 
 
+def shard_weight(n: int, world: int, rank: int) -> float:
+    """Weight of this rank's mean loss in the global-batch mean, times `world` (allreduce_gradients divides by it):
+    local_items * world / n.  1.0 whenever the batch divides evenly."""
+    sl = shard_batch(n, world, rank)
+    return (sl.stop - sl.start) * world / float(n)
+
+
 def shard_batch(n: int, world: int, rank: int) -> slice:
     """Contiguous slice of a global batch of n items for this rank (sizes differ by at most one)."""
     base, extra = divmod(n, world)
@@ -198,9 +205,12 @@ def fp32_math():
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv, mm
 
 
-def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group=None):
+def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group=None, shard_weight: float = 1.0):
     """One 'G' iteration (:277-300): teacher-forced forward, L1 + binary divergence + guided attention + adversarial
-    term scaled to the size of the other three, backward, gradient allreduce, Adam step.  Returns the loss terms."""
+    term scaled to the size of the other three, backward, gradient allreduce, Adam step.  Returns the loss terms.
+    `shard_weight` = local_items * world / global_items (1.0 for equal shards): the rank's mean losses and their
+    gradients are weighted by it, so that the average over ranks is the mean over the GLOBAL batch even when the
+    shard sizes differ by one (`shard_weights`)."""
     opt_syn.zero_grad(set_to_none=True)
     spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
     with fp32_math():
@@ -214,20 +224,20 @@ def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, gro
         loss_disc = torch.mean(-disc_syn)
         # the adversarial weight is a ratio of GLOBAL-batch loss values (the reference computes it on the gathered
         # DataParallel output): average the four scalars over the ranks first
-        terms = torch.stack([loss_l1.detach(), loss_bd.detach(), loss_att.detach(), loss_disc.detach()])
+        terms = torch.stack([loss_l1.detach(), loss_bd.detach(), loss_att.detach(), loss_disc.detach()]) * shard_weight
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group)
             terms /= dist.get_world_size(group)
         t_l1, t_bd, t_att, t_disc = (float(v) for v in terms.tolist())
         scale = (t_l1 + t_bd + t_att) / abs(t_disc)
         loss = loss_l1 + loss_bd + loss_att + scale * loss_disc
-        loss.backward()
+        (loss * shard_weight if shard_weight != 1.0 else loss).backward()
     allreduce_gradients(model.parameters(), group=group)
     opt_syn.step()
     return {"l1": t_l1, "bin_div": t_bd, "att": t_att, "disc": t_disc, "loss": t_l1 + t_bd + t_att + scale * t_disc}
 
 
-def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff=None, group=None):
+def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff=None, group=None, shard_weight: float = 1.0):
     """One 'D' iteration (:302-322): WGAN-GP.  The generator runs without a graph (its output is detached in the
     reference), the gradient penalty differentiates through the discriminator's backward pass (autograd).
     `coeff` (B,) are the interpolation weights (reference: torch.rand(B), one per utterance)."""
@@ -235,10 +245,10 @@ def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coe
     spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
     with torch.no_grad():
         pred, _ = model(spec_inputs, text_id, spk_emb)
-    return _wgan_gp_step(disc, opt_disc, mel_gt, pred, cfg, coeff, group)
+    return _wgan_gp_step(disc, opt_disc, mel_gt, pred, cfg, coeff, group, shard_weight)
 
 
-def _wgan_gp_step(disc, opt_disc, real, fake, cfg, coeff, group):
+def _wgan_gp_step(disc, opt_disc, real, fake, cfg, coeff, group, shard_weight: float = 1.0):
     B = real.shape[0]
     if coeff is None:
         coeff = torch.rand(B, device=real.device)
@@ -248,15 +258,15 @@ def _wgan_gp_step(disc, opt_disc, real, fake, cfg, coeff, group):
         out_mid = disc(mid)
         grads = torch.autograd.grad(out_mid, mid, torch.ones_like(out_mid), retain_graph=True, create_graph=True)[0]
         loss_gp = torch.mean(cfg["LAMBDA"] * (torch.norm(grads, p=2, dim=(1, 2)) - 1) ** 2)
-        loss_gp.backward()
+        (loss_gp * shard_weight if shard_weight != 1.0 else loss_gp).backward()
         loss_d = torch.mean(disc(fake) - disc(real))
-        loss_d.backward()
+        (loss_d * shard_weight if shard_weight != 1.0 else loss_d).backward()
     allreduce_gradients(disc.parameters(), group=group)
     opt_disc.step()
     return {"gp": loss_gp.item(), "wd": -loss_d.item(), "loss": loss_d.item() + loss_gp.item()}
 
 
-def ssrn_generator_step(model, disc, opt_syn, mel_gt, lin_gt, cfg=None, group=None):
+def ssrn_generator_step(model, disc, opt_syn, mel_gt, lin_gt, cfg=None, group=None, shard_weight: float = 1.0):
     """One 'G' iteration of `train_ssrn` (train/adversarial_wasserstein_gp.py:324-338): SSRN forward, L1 + binary
     divergence + the adversarial term scaled to their size, backward, gradient allreduce, optimizer step."""
     opt_syn.zero_grad(set_to_none=True)
@@ -266,27 +276,27 @@ def ssrn_generator_step(model, disc, opt_syn, mel_gt, lin_gt, cfg=None, group=No
         loss_l1 = torch.mean(torch.abs(lin_gt - pred))
         loss_bd = torch.mean(-lin_gt * torch.log(pred + 1e-8) - (1 - lin_gt) * torch.log(1 - pred + 1e-8))
         loss_disc = torch.mean(-disc_syn)
-        terms = torch.stack([loss_l1.detach(), loss_bd.detach(), loss_disc.detach()])
+        terms = torch.stack([loss_l1.detach(), loss_bd.detach(), loss_disc.detach()]) * shard_weight
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group)
             terms /= dist.get_world_size(group)
         t_l1, t_bd, t_disc = (float(v) for v in terms.tolist())
         scale = (t_l1 + t_bd) / abs(t_disc)
-        (loss_l1 + loss_bd + scale * loss_disc).backward()
+        ((loss_l1 + loss_bd + scale * loss_disc) * shard_weight).backward()
     allreduce_gradients(model.parameters(), group=group)
     opt_syn.step()
     return {"l1": t_l1, "bin_div": t_bd, "disc": t_disc, "loss": t_l1 + t_bd + scale * t_disc}
 
 
-def ssrn_discriminator_step(model, disc, opt_disc, mel_gt, lin_gt, cfg, coeff=None, group=None):
+def ssrn_discriminator_step(model, disc, opt_disc, mel_gt, lin_gt, cfg, coeff=None, group=None, shard_weight: float = 1.0):
     """One 'D' iteration of `train_ssrn` (:340-360): WGAN-GP on linear spectrograms."""
     opt_disc.zero_grad(set_to_none=True)
     with torch.no_grad():
         pred = model(mel_gt)
-    return _wgan_gp_step(disc, opt_disc, lin_gt, pred, cfg, coeff, group)
+    return _wgan_gp_step(disc, opt_disc, lin_gt, pred, cfg, coeff, group, shard_weight)
 
 
-def ordinary_step(model, opt, batch, gaw, text2mel: bool, group=None):
+def ordinary_step(model, opt, batch, gaw, text2mel: bool, group=None, shard_weight: float = 1.0):
     """One iteration of the non-adversarial trainer (train/ordinary.py:219-256): L1 + binary divergence
     (+ guided attention for Text2Mel), backward, gradient allreduce, optimizer step."""
     opt.zero_grad(set_to_none=True)
@@ -307,7 +317,7 @@ def ordinary_step(model, opt, batch, gaw, text2mel: bool, group=None):
             loss_att = torch.sum(att * gaw[:att.shape[-2], :att.shape[-1]]) / float(att.numel())
             loss = loss + loss_att
             out["att"] = loss_att.item()
-        loss.backward()
+        (loss * shard_weight if shard_weight != 1.0 else loss).backward()
     allreduce_gradients(model.parameters(), group=group)
     opt.step()
     out["loss"] = loss.item()

@@ -38,7 +38,7 @@ def griffin_lim(S: torch.Tensor, n_iter: int = 64, hop: int = 256, win_length: i
         angles = angles0.to(device=S.device, dtype=torch.complex64)
     S = S.to(torch.float32).contiguous()
     length = hop * (T - 1)
-    can_fuse = n_fft == 1024 and hop == 256 and win_length == 1024 and T >= 3
+    can_fuse = n_fft == 1024 and hop == 256 and win_length == 1024 and T >= 4      # single reflection: 256 (T - 1) > 512
     if fused is None:
         fused = can_fuse
     if fused:
@@ -96,13 +96,18 @@ def trim_bounds(y: torch.Tensor, top_db: float = 30.0, frame_length: int = 2048,
 
 def postprocess(pred_lin: torch.Tensor, cfg: dict, n_iter: int = 64, angles0: Optional[torch.Tensor] = None,
                 generator: Optional[torch.Generator] = None) -> List[np.ndarray]:
-    """generate_test_utterances.py:130-139 (LOG_FEATURE false) for a whole batch: (B, 513, 4T) in (0, 1) on the GPU
-    -> one float32 waveform per utterance (peak 0.75, trimmed, at most 9 s)."""
-    if cfg.get("LOG_FEATURE", False):
-        raise NotImplementedError("LOG_FEATURE spectrograms are not used by the vendored config.json")
+    """generate_test_utterances.py:126-139 / synthesize.py:134-147 for a whole batch: (B, 513, 4T) in (0, 1) on the GPU
+    -> one float32 waveform per utterance (trimmed, at most 9 s).  LOG_FEATURE false: per-utterance max-normalised
+    magnitudes, output peak 0.75.  LOG_FEATURE true (:126-128): the prediction is a normalised dB value,
+    magnitude = 10 ** (0.05 * (p * MAX_DB - MAX_DB + REF_DB)), no max-normalisation and no output scaling."""
     _lib.require_cuda(pred_lin, "postprocess")
     x = pred_lin.to(torch.float32)
-    spec = (x / x.amax(dim=(1, 2), keepdim=True)).pow(cfg["NORM_POWER"]["RECONSTRUCTION"] / cfg["NORM_POWER"]["ANALYSIS"])
+    log_feature = bool(cfg.get("LOG_FEATURE", False))
+    power = cfg["NORM_POWER"]["RECONSTRUCTION"] / cfg["NORM_POWER"]["ANALYSIS"]
+    if log_feature:
+        spec = torch.pow(10.0, 0.05 * (x * cfg["MAX_DB"] - cfg["MAX_DB"] + cfg["REF_DB"])).pow(power)
+    else:
+        spec = (x / x.amax(dim=(1, 2), keepdim=True)).pow(power)
     sig = griffin_lim(spec, n_iter, cfg["STFT"]["HOP_LENGTH"], cfg["STFT"]["FFT_LENGTH"], angles0=angles0, generator=generator)
     sig = deemphasis(sig, cfg["PREEMPH"])
     starts, ends = trim_bounds(sig, 30.0)
@@ -115,8 +120,11 @@ def postprocess(pred_lin: torch.Tensor, cfg: dict, n_iter: int = 64, angles0: Op
     lo = torch.tensor(starts, device=sig.device)[:, None]
     hi = torch.tensor(ends, device=sig.device)[:, None]
     inside = (idx >= lo) & (idx < hi)
-    peak = torch.where(inside, sig, torch.full_like(sig, -float("inf"))).amax(dim=1, keepdim=True)
-    scaled = sig * (0.75 / peak)
+    if log_feature:
+        scaled = sig                                   # written as is (generate_test_utterances.py:139)
+    else:
+        peak = torch.where(inside, sig, torch.full_like(sig, -float("inf"))).amax(dim=1, keepdim=True)
+        scaled = sig * (0.75 / peak)
     host = _pinned_like(scaled)
     host.copy_(scaled, non_blocking=True)
     torch.cuda.current_stream().synchronize()

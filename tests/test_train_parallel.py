@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from spoofsv_b200.train import allreduce_gradients, plan_buckets, shard_batch
+from spoofsv_b200.train import allreduce_gradients, plan_buckets, shard_batch, shard_weight
 
 
 def test_plan_buckets_preserves_order_and_limits():
@@ -74,6 +74,45 @@ def test_allreduce_gradients_two_ranks_gloo():
         assert n == 7 * 5 + 5 + 5 * 3 + 3 + 6           # every trainable element, the frozen one excluded
         assert err <= 1e-6                              # summed shard gradients == gradient of the global batch
         assert unused_max == 0.0 and frozen_none
+
+
+def _worker_uneven(rank: int, world: int, port: int, q):
+    """A global batch of 5 over 2 ranks (shards of 3 and 2): per-rank MEAN losses weighted by shard_weight, averaged by
+    allreduce_gradients, must equal the gradient of the mean over the global batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.randn(5, 7, generator=g), torch.randn(5, 3, generator=g)
+        sl = shard_batch(5, world, rank)
+        w = shard_weight(5, world, rank)
+        (((model(x[sl]) - y[sl]) ** 2).mean() * w).backward()
+        allreduce_gradients(model.parameters(), average=True)
+        ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        ref.load_state_dict(model.state_dict())
+        ((ref(x) - y) ** 2).mean().backward()
+        err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(model.parameters(), ref.parameters()))
+        q.put((rank, w, err))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_uneven_shards_are_weighted_to_the_global_mean_gloo():
+    assert shard_weight(32, 8, 3) == 1.0 and abs(sum(shard_weight(5, 2, r) for r in range(2)) - 2.0) < 1e-12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_uneven, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [round(w, 6) for _, w, _ in out] == [1.2, 0.8]
+    assert all(err <= 1e-6 for _, _, err in out)
 
 
 def test_allreduce_is_a_noop_without_a_process_group():

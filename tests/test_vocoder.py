@@ -87,3 +87,12 @@ def test_gpu_waveform_stage_matches_oracle():
         assert abs(float(np.max(waves[k])) - 0.75) < 1e-6
         if len(waves[k]) == len(want):
             assert np.abs(waves[k][:n] - want[:n]).max() <= 5e-3
+    # LOG_FEATURE branch (generate_test_utterances.py:126-128): dB mapping, no max-normalisation, no peak scaling
+    log_cfg = dict(CFG, LOG_FEATURE=True, MAX_DB=100, REF_DB=20)
+    lin_db = np.clip((20 * np.log10(np.maximum(specs, 1e-5)) - 20 + 100) / 100, 1e-8, 1.0)
+    waves = G.postprocess(torch.from_numpy(lin_db).float().cuda(), log_cfg, n_iter=16, angles0=torch.from_numpy(a0))
+    for k in range(2):
+        want = V.postprocess(lin_db[k], a0[k], log_cfg, n_iter=16)
+        assert abs(len(waves[k]) - len(want)) <= 512
+        if len(waves[k]) == len(want):
+            assert np.abs(waves[k] - want).max() <= 5e-3 * np.abs(want).max()
