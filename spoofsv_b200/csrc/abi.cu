@@ -307,6 +307,7 @@ struct ssv_decoder {
   long long* prof = nullptr;
   unsigned long long* ws_raw = nullptr;
   float* ws_hist = nullptr;
+  float* ws_zero = nullptr;
   int seq_base = 0, R = 1, G = 1, W = 4;
   int force_r = 0, force_w = 0;           // ssv_decoder_set_plan
   // per-batch state
@@ -804,7 +805,10 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
     const size_t bp = (size_t)round_up(max_batch, 4);
     const size_t raw_words = (size_t)DEC_STAGES * max_batch * WS_WORDS;
     if (st == kOk) st = d->arena.alloc<unsigned long long>(raw_words, &d->ws_raw);
-    if (st == kOk) st = d->arena.alloc<float>((size_t)m->ws_hist_blocks * bp * H, &d->ws_hist);
+    // ring entries are [256][XS] floats per micro-batch, XS = 2 (R = 1: every activation as the pair (x, x); R = 2) or 4
+    if (st == kOk) st = d->arena.alloc<float>((size_t)m->ws_hist_blocks * bp * H * 2, &d->ws_hist);
+    if (st == kOk) st = d->arena.alloc<float>((size_t)H * 4, &d->ws_zero);
+    if (st == kOk && cudaMemset(d->ws_zero, 0, sizeof(float) * H * 4) != cudaSuccess) st = kCuda;
     if (st == kOk && cudaMemset(d->ws_raw, 0, raw_words * sizeof(unsigned long long)) != cudaSuccess) st = kCuda;
   }
   if (st == kOk) st = d->arena.alloc<float>((size_t)max_batch * max_text * H, &d->Kt);
@@ -877,7 +881,7 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.abort_flag = d->abort_flag;
   p.prof = d->prof;
   p.ws_stages = m->ws_stages_dev;
-  p.ws_raw = d->ws_raw; p.ws_hist = d->ws_hist;
+  p.ws_raw = d->ws_raw; p.ws_hist = d->ws_hist; p.ws_zero = d->ws_zero;
   p.seq_base = d->seq_base; p.R = d->R; p.G = d->G; p.W = d->W;
   if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 16, s));
   SSV_TRY(launch_decode_ws(p, s));
@@ -903,6 +907,20 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
         sum += v; mx = v > mx ? v : mx; ++cnt;
       }
       fprintf(stderr, "  %-32s %9.0f / %9.0f\n", nm[i], cnt ? sum / cnt : 0.0, mx);
+    }
+    // per stage (mean over the stage's CTAs): which stage sets the pace of the pipeline
+    fprintf(stderr, "  stage  ctas | FE: top  taps  wait  poll  ring  math | MV: wtaps  old  wcur  cur  publish\n");
+    for (int sidx = 0; sidx < DEC_STAGES; ++sidx) {
+      const WsStage& w = m->ws_stages[sidx];
+      double acc[15] = {0};
+      for (int c = w.cta0; c < w.cta0 + w.parts; ++c)
+        for (int i = 0; i < 15; ++i) {
+          const int cs = i >= 8 ? 7 : cnt_slot;
+          const double den = (double)h[(size_t)c * stride + cs];
+          if (den > 0) acc[i] += (double)h[(size_t)c * stride + i] / den / w.parts;
+        }
+      fprintf(stderr, "  %5d %5d | %7.0f %5.0f %5.0f %5.0f %5.0f %5.0f | %8.0f %5.0f %5.0f %5.0f %5.0f\n", sidx, w.parts, acc[0], acc[2],
+              acc[3], acc[4], acc[5], acc[6], acc[8], acc[9], acc[10], acc[11], acc[12]);
     }
   }
   d->t += n_steps;

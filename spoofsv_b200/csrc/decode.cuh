@@ -72,7 +72,8 @@ struct DecParams {
   long long* prof;              // optional [grid][16] phase cycle counters (SSV_DECODE_PROF=1)
   const WsStage* ws_stages;     // device [DEC_STAGES]
   unsigned long long* ws_raw;   // [DEC_STAGES][B][WS_WORDS] tagged words {float, tag}
-  float* ws_hist;               // private input-history rings, [blocks][G][256][R]
+  float* ws_hist;               // private input-history rings: entries [256][XS] (X's own layout), [blocks][G] of them
+  const float* ws_zero;         // one entry of zeros (taps before frame 0)
   int seq_base;                 // tag of frame t is seq_base + t + 1 (advanced by every begin())
   int R, G, W;                  // rows per micro-batch (1, 2, 4), micro-batches, front-end warps per row (1, 2, 4)
 };

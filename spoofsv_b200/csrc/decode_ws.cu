@@ -57,13 +57,18 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // shared-memory carve-up (floats)
 constexpr int XROWS = 3 * TAPP;                    // rows of one X buffer ([rows][RT] activations; RT = 1 stores each as (x, x))
-constexpr int XREGION = 2 * 8 * XROWS;             // floats; 8 / RT buffers: 8 (RT = 1, two floats each), 4 (RT = 2), 2 (RT = 4)
+constexpr int XREGION = 2 * 8 * XROWS;             // floats; ws_nbuf(RT) buffers of XROWS rows x (2 or 4) floats
 constexpr int MAXBUF = 8;
+// X buffers per shape: 8 (one- and two-row micro-batches, 2 floats per X row) or 4 (four rows)
+#ifdef SSV_NBUF2
+__host__ __device__ constexpr int ws_nbuf(int rt) { return rt == 4 ? 4 : rt == 2 ? SSV_NBUF2 : 8; }
+#else
+__host__ __device__ constexpr int ws_nbuf(int rt) { return rt == 4 ? 4 : 8; }
+#endif
 constexpr int SM_WSM = 0;                          // [11][384] float4: tap-0 weights of a highway CTA
 constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [8 / RT][XROWS][RT * XLayout<RT>::D]
 constexpr int SM_PART = SM_X + XREGION;            // [12][RT][ncol <= 128] k-slice partial sums
-constexpr int SM_REC = SM_PART + 12 * 4 * 128;     // [24 / RT][RT][256] stage inputs of the most recent visits (short-distance taps)
-constexpr int SM_LN = SM_REC + 24 * HD;            // [4][256] LayerNorm parameters of my prologue
+constexpr int SM_LN = SM_PART + 12 * 4 * 128;      // [4][256] LayerNorm parameters of my prologue
 constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
 constexpr int SM_PMA = SM_BIAS + 128;              // [WS_MAX_BATCH] ints (attention stage only)
 constexpr int SM_KV = SM_PMA + WS_MAX_BATCH;        // [4 warps][K window 3 | V window 3][256]: attention rows prefetched by cp.async
@@ -103,6 +108,26 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz));
+}
+// ---- bulk copies (TMA, 1-D): the history ring entries move between global memory and the X buffers without
+// passing through registers.  Entry = the stage input of one (frame, micro-batch) in X's own layout [256][XS].
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread's bulk stores: all but the newest are complete (written), and the newest has read its source
+__device__ __forceinline__ void bulk_wait_prev_written_last_read() {
+  asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // ---- mbarriers (CTA-local producer / consumer hand-off of the X buffers)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -254,7 +279,7 @@ template <int RT, int CG, bool HWY, bool PROF>
 __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st, const Ctx& c, int gtid) {
   constexpr int KS = GV_T / CG;            // k-slices: 24 (64 columns) or 12 (128 columns)
   constexpr int NCOL = 4 * CG;
-  constexpr int NBUF = MAXBUF / RT;
+  constexpr int NBUF = ws_nbuf(RT);
   const int cg = gtid % CG, ks = gtid / CG;
   const int lane = gtid & 31, gwarp = gtid >> 5;
   float* parts = c.smem + SM_PART;
@@ -281,6 +306,12 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
   }
 
   Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)c.s * c.B * WS_WORDS;
+  auto ring_store = [&](int step, int g, int q) {
+    constexpr int XS = RT * XLayout<RT>::D;
+    const int slot = (p.t_start + step) % st.hist_depth;
+    float* dst = p.ws_hist + (((size_t)(st.hist_blk0 + c.part * st.hist_depth + slot)) * c.G + g) * (HD * XS);
+    bulk_s2g(dst, c.smem + SM_X + q * (XROWS * XS) + (size_t)(2 * TAPP) * XS, HD * XS * (unsigned)sizeof(float));
+  };
   int v = 0;                                // visit counter (same sequence as the front end; < 2^31: checked at launch)
   for (int step = 0; step < p.n_steps; ++step) {
     const int tag = p.seq_base + p.t_start + step + 1;
@@ -321,14 +352,26 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);
         if (PROF && prof_on) wake_acc += prof_last - c.t_seen[8 + q];
+        // The finished current-tap rows of this (frame, micro-batch) join the history ring: one bulk copy (TMA)
+        // from the X buffer, in X's own layout, read back the same way when they become the taps t-d, t-2d.  The
+        // front-end lanes fenced their stores towards the async proxy before they arrived on curfull.  Multi-row
+        // micro-batches: issued ahead of this thread's FMAs, the other warps fill the issue slots meanwhile (issued by
+        // the last warp after its FMAs instead, the barrier below waited for it: B = 128 88.8 -> 94.4 us/frame).
+        // Latency mode (one row): after the publish, off the frame's critical path.
+        if (RT > 1 && gtid == 0) ring_store(step, g, q);
 #pragma unroll
         for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[11 + j], X + (size_t)(2 * TAPP + KS * j) * XS);
       } else {
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);
+#ifndef SSV_EXP_SKIP_PW
 #pragma unroll
         for (int j = 0; j < 22; ++j)
           if (j < st.nj) fma_tile<RT>(acc, w[j], X + (size_t)(KS * j) * XS);
+#else
+        if (p.n_steps < 0) acc[0][0] = w[3].x + w[21].y + X[0];     // timing experiment only: wrong values
+#endif
+        PROF_G(1);                  // 1x1 stages: "old taps" column = the tile loop, "current tap" = k-slice store + barrier
       }
       // k-slices -> shared memory
       bool writer = true;
@@ -346,7 +389,7 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
               make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
       }
       named_bar(1, GV_T);
-      if (gtid == 0) mbar_arrive(&c.empty[q]);     // X buffer q may be refilled
+      if (!HWY && gtid == 0) mbar_arrive(&c.empty[q]);     // X buffer q may be refilled (highway: after the publish, below)
       PROF_G(3);
       // reduce the 12 k-slices, add bias (+ hoisted speaker projection), publish tagged words
 #pragma unroll
@@ -361,6 +404,11 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
           const int b = row0 + r;
           if (b < c.B && gc < st.n) st_word(raw_out + (size_t)b * WS_WORDS + gc, sum + bias_s[lc] + sb[i], tag);
         }
+      }
+      if (HWY && gtid == 0) {
+        if (RT == 1) ring_store(step, g, q);
+        bulk_wait_prev_written_last_read();        // older ring entries are in memory, this one has left the X buffer
+        mbar_arrive(&c.empty[q]);
       }
       // Second CTA-wide barrier: the k-slice buffer may be rewritten, and -- measured -- it keeps the warps without
       // an output from running ahead into the next micro-batch and taking issue slots from the publishing warps
@@ -448,8 +496,9 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
   constexpr int NV = 4 / (RT * WPR);        // micro-batches in flight in the front end (visit slots)
   constexpr int NP = 4 / WPR;               // channel pairs per lane
   constexpr int CW = HD / WPR;              // channels per warp
-  constexpr int NBUF = MAXBUF / RT;
-  constexpr int NREC = 24 / RT;             // a multiple of NV: a warp only ever meets its own entries
+  constexpr int NBUF = ws_nbuf(RT);
+  constexpr int XSF = RT * XLayout<RT>::D;  // floats per X row (one channel of the micro-batch)
+  constexpr unsigned ENTRY_BYTES = HD * XSF * sizeof(float);     // one history ring entry = one tap region of X
   const int warp = tid >> 5, lane = tid & 31;
   const int vs = warp / (RT * WPR), r = (warp / WPR) % RT, sub = warp % WPR;
   const int barid = 2 + vs * RT + r, wbase = warp - sub;
@@ -463,7 +512,6 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
   const float* b2 = lnp + 3 * HD;
   int* pma_w = reinterpret_cast<int*>(c.smem + SM_PMA) + sub * B;     // my warp's own copy of the alignment state
   float* red = c.smem + SM_RED;
-  float* rec = c.smem + SM_REC;
   float* kvs = c.smem + SM_KV + (vs * RT + r) * (6 * HD);
   const Word* raw_in = reinterpret_cast<const Word*>(p.ws_raw) + (size_t)c.prev * B * WS_WORDS;
   Word* raw_out = reinterpret_cast<Word*>(p.ws_raw) + (size_t)s * B * WS_WORDS;
@@ -504,8 +552,8 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     else { gg = *reinterpret_cast<const float2*>(g2 + cb + 64 * i); bb = *reinterpret_cast<const float2*>(b2 + cb + 64 * i); }
   };
 
-  float2 tp[2][NP];
-  bool have_pref = false, bad = false;
+  const bool issuer = (warp % (RT * WPR)) == 0;      // the visit's first warp issues its bulk copies
+  bool bad = false;
   int step = 0, g = vs, vi = 0;              // G is a multiple of NV: slot vs always meets the same micro-batches
   for (int v = vs; v < total_visits; v += NV, g += NV, ++vi) {
     while (g >= G) { g -= G; ++step; }
@@ -527,45 +575,55 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
       if (__shfl_sync(FULL, ab, 0) != 0) bad = true;
     }
 
-    // ---- 1. my slice of the old taps t-2d, t-d -> X rows [0, 256) and [264, 520): from the recent-row ring in
-    //         shared memory when one of the last NREC visits produced it, else from my private ring in global
-    //         memory (prefetched at the end of the previous visit).  Both were written by this very warp.
+    // ---- 1. the old taps t-2d, t-d -> X rows [0, 256) and [264, 520).  The stage input of (frame, micro-batch) is
+    //         kept as a ring ENTRY in X's own layout [256][XS]: the mat-vec side stores the finished current-tap rows
+    //         with one bulk copy (TMA) and the taps come back the same way, straight into the X buffer -- no
+    //         registers, no per-lane stores.  Only when the tap was produced by one of the last NBUF visits (tiny
+    //         batches) it is still in that visit's X buffer, and my warp copies its own channel slice from there
+    //         (written by this very warp: the micro-batch count is a multiple of the visit slots).  A ring entry is
+    //         therefore read back more than NBUF visits after it was stored: the storing thread has seen that store
+    //         complete before it released the X buffer this visit waited for (cp.async.bulk.wait_group 1 there).
     if (st.ntaps == 3) {
+      if (u >= 1) {
+        if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
+      }
+      unsigned tx = 0;
+      const float* bsrc[2] = {nullptr, nullptr};
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int back = (2 - j) * st.dil;
         const int tt = t - back;
         const int dist = back * G;
-        if (tt < 0 || !live) {
+        if (tt >= p.t_start && tt >= 0 && dist <= NBUF) {      // dist == NBUF: this very buffer, not yet overwritten
+          const float* srcX = c.smem + SM_X + ((v - dist) % NBUF) * (XROWS * XSF) + (size_t)koff * XSF;
+          float* dstX = X + (size_t)j * TAPP * XSF;
 #pragma unroll
-          for (int i = 0; i < NP; ++i) tp[j][i] = make_float2(0.f, 0.f);
-        } else if (tt >= p.t_start && dist < NREC) {
-          const float* src = rec + ((size_t)((v - dist) % NREC) * RT + r) * HD + cb;
-#pragma unroll
-          for (int i = 0; i < NP; ++i) tp[j][i] = *reinterpret_cast<const float2*>(src + 64 * i);
-        } else if (!have_pref) {
-          const int slot = tt % st.hist_depth;
-          const float* src = p.ws_hist + ((((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * RT + r) * HD + cb;
-#pragma unroll
-          for (int i = 0; i < NP; ++i) tp[j][i] = __ldcg(reinterpret_cast<const float2*>(src + 64 * i));
-        }
-      }
-      if (u >= 1) {
-        if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          if (RT == 1) {
-            *reinterpret_cast<float4*>(X + ((size_t)j * TAPP + cb + 64 * i) * 2) = make_float4(tp[j][i].x, tp[j][i].x, tp[j][i].y, tp[j][i].y);
-          } else {
-            float* xp = X + ((size_t)j * TAPP + cb + 64 * i) * RT + r;
-            xp[0] = tp[j][i].x; xp[RT] = tp[j][i].y;
+          for (int i = 0; i < NP; ++i) {
+            const int ch = cb + 64 * i;
+            if (RT == 1) {
+              *reinterpret_cast<float4*>(dstX + (size_t)ch * 2) = *reinterpret_cast<const float4*>(srcX + (size_t)ch * 2);
+            } else {
+              dstX[(size_t)ch * XSF + r] = srcX[(size_t)ch * XSF + r];
+              dstX[(size_t)(ch + 1) * XSF + r] = srcX[(size_t)(ch + 1) * XSF + r];
+            }
           }
+        } else {
+          bsrc[j] = tt < 0 ? p.ws_zero
+                           : p.ws_hist + (((size_t)(st.hist_blk0 + part * st.hist_depth + tt % st.hist_depth)) * G + g) * (HD * XSF);
+          tx += ENTRY_BYTES;
         }
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&c.tapsfull[q]);
+      if (lane == 0) {
+        if (issuer && tx != 0) {
+          mbar_arrive_expect_tx(&c.tapsfull[q], tx);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (bsrc[j] != nullptr) bulk_g2s(X + (size_t)j * TAPP * XSF, bsrc[j], ENTRY_BYTES, &c.tapsfull[q]);
+        } else {
+          mbar_arrive(&c.tapsfull[q]);
+        }
+      }
     } else if (!final_visit && u >= 1) {
       if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
     }
@@ -612,6 +670,9 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
       long long t0 = 0;
       unsigned spins = 0;
       auto spin_check = [&]() {
+#ifdef SSV_POLL_SLEEP
+        __nanosleep(SSV_POLL_SLEEP);               // a failed poll backs off: its 12 loads per attempt share the LSU with the mat-vec
+#endif
         if ((++spins & 255u) == 0) {
           if (t0 == 0) t0 = clock64();
           else if (clock64() - t0 > SPIN_LIMIT) atomicExch(p.abort_flag, 8);
@@ -843,46 +904,18 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     }
     if (final_visit) continue;                 // stage 0 after the last frame: prologue only
     PROF_F(6);
+    // the mat-vec side hands the finished current-tap rows to the history ring with a bulk copy (async proxy):
+    // order my generic-proxy stores before it
+#ifndef SSV_NO_FE_FENCE
+    if (st.ntaps == 3) fence_proxy_async_smem();
+#endif
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&c.curfull[q]);              // release: my slice of the micro-batch is in X
       if (PROF && p.prof != nullptr && tid == 0) c.t_seen[8 + q] = clock64();
     }
-    // ---- 4. my slice of the stage input joins the recent-row ring and my private global ring (later frames' taps)
-    if (st.ntaps == 3 && live) {
-      const int slot = t % st.hist_depth;
-      float* dst = p.ws_hist + ((((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g) * RT + r) * HD + cb;
-      float* rdst = rec + ((size_t)(v % NREC) * RT + r) * HD + cb;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        *reinterpret_cast<float2*>(rdst + 64 * i) = o[i];
-        __stcg(reinterpret_cast<float2*>(dst + 64 * i), o[i]);
-      }
-    }
     // leave an aborted launch only where every warp of my row agrees (after a reduction, or where there is none)
     if (bad && (WPR == 1 || pro == PRO_X || live)) return;
-    // ---- 5. global-ring taps of the next visit: issue the loads now, they land while I wait for its producer
-    have_pref = false;
-    if (st.ntaps == 3 && v + NV < total_visits) {
-      int step2 = step, g2 = g + NV;
-      if (g2 >= G) { g2 -= G; ++step2; }
-      const int t2 = p.t_start + step2;
-      if (g2 * RT + r < B) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int back = (2 - j) * st.dil;
-          const int tt = t2 - back;
-          const int dist = back * G;
-          if (tt >= 0 && !(tt >= p.t_start && dist < NREC)) {
-            const int slot = tt % st.hist_depth;
-            const float* src = p.ws_hist + ((((size_t)(st.hist_blk0 + part * st.hist_depth + slot)) * G + g2) * RT + r) * HD + cb;
-#pragma unroll
-            for (int i = 0; i < NP; ++i) tp[j][i] = __ldcg(reinterpret_cast<const float2*>(src + 64 * i));
-          }
-        }
-        have_pref = true;
-      }
-    }
     PROF_F(5);
   }
   if (prof_on) {
@@ -972,10 +1005,20 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
     __syncthreads();
   }
 
-  if (tid < FE_T) {
-    front_role<RT, WPR, PROF>(p, st, c, tid);
+  // Warps 0-3 are the front end, warps 4-15 the mat-vec.  (Tried: the front end as the four HIGHEST warps, which the
+  // issue arbiter is said to prefer -- 3-4 % slower at every batch size: B = 1 31.3 -> 32.4, B = 64 50.1 -> 51.9,
+  // B = 128 93.3 -> 97.8 us/frame.)
+#ifdef SSV_FE_HIGH
+  const bool is_fe = tid >= GV_T;
+  const int rtid = is_fe ? tid - GV_T : tid;
+#else
+  const bool is_fe = tid < FE_T;
+  const int rtid = is_fe ? tid : tid - FE_T;
+#endif
+  if (is_fe) {
+    front_role<RT, WPR, PROF>(p, st, c, rtid);
   } else {
-    const int gtid = tid - FE_T;
+    const int gtid = rtid;
     if (st.hwy) gemv_role<RT, 16, true, PROF>(p, st, c, gtid);
     else if (st.cg == 16) gemv_role<RT, 16, false, PROF>(p, st, c, gtid);
     else gemv_role<RT, 32, false, PROF>(p, st, c, gtid);
