@@ -33,8 +33,10 @@ extern "C" {
 #define SSV_ENOMEM 3
 #define SSV_ESTATE 4   /* call sequence error, decode kernel aborted */
 
-#define SSV_PREC_FP32 0   /* CUDA-core FP32 FMA, <= 1e-4 max-abs vs the reference */
-#define SSV_PREC_BF16 1   /* tcgen05 BF16 tensor cores, FP32 accumulate, <= 2e-2 rel-L2 */
+#define SSV_PREC_FP32 0        /* FP32-accurate, <= 1e-4 max-abs vs the reference: tcgen05 tensor cores with 3xTF32 split
+                                * operands where that arm is built (TextEnc, highwayConv), CUDA-core FP32 FMA elsewhere */
+#define SSV_PREC_BF16 1        /* tcgen05 BF16 tensor cores, FP32 accumulate, <= 2e-2 rel-L2 */
+#define SSV_PREC_FP32_FFMA 2   /* FP32-accurate on the CUDA cores only (cross-check of the split tensor-core arm) */
 
 typedef struct ssv_text2mel ssv_text2mel;   /* packed Text2Mel weights (melSyn) */
 typedef struct ssv_decoder ssv_decoder;     /* incremental AR decode state */

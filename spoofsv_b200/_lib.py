@@ -12,8 +12,9 @@ from typing import Optional
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libspoofsv_b200.so"
 
-PREC_FP32 = 0
+PREC_FP32 = 0          # FP32-accurate: tensor cores (3xTF32 split) where built, CUDA cores elsewhere
 PREC_BF16 = 1
+PREC_FP32_FFMA = 2     # FP32-accurate on the CUDA cores only
 
 _c_f32p = C.c_void_p
 _c_i64p = C.c_void_p

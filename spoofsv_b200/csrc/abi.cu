@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc32.cuh"
 #include "decode.cuh"
 
 namespace ssv {
@@ -224,6 +225,23 @@ void tc_shape_plain(TcLayer* L, int n) {            // LN-only / no-epilogue lay
   }
 }
 
+// ---- tensor-core FP32-accurate (3xTF32) packing: reuses the fp32 pack's bias / LayerNorm copies ----
+int tf32_pack_layer(Arena& ar, const ParamMap& pm, const std::string& wname, const ConvPack& c, int rows, int cin, int k,
+                    Tf32Layer* L, cudaStream_t s) {
+  const float* w;
+  SSV_TRY(pm.get(wname, (int64_t)rows * cin * k, &w));
+  L->rows = rows;
+  L->cin = cin;
+  L->cin_p = round_up(cin, T32_BK);
+  L->k = k;
+  L->bias = c.bias;
+  L->g1 = c.g1; L->b1 = c.b1; L->g2 = c.g2; L->b2 = c.b2;
+  const size_t n = (size_t)rows * k * L->cin_p;
+  SSV_TRY(ar.alloc<float>(n, &L->Wh));
+  SSV_TRY(ar.alloc<float>(n, &L->Wl));
+  return tf32_pack_weights(w, rows, cin, k, L->cin_p, L->Wh, L->Wl, s);
+}
+
 cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 int device_sm_count() {
@@ -277,6 +295,13 @@ struct ssv_text2mel {
   ConvPack te_conv1, te_conv2;
   ConvPack te_hc[12];
   int te_dil[12];
+  Tf32Layer te32_conv1, te32_conv2, te32_hc[12];     // the same layers for the tensor-core (3xTF32) arm
+  float* te32_ws[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t te32_floats = 0;
+  ~ssv_text2mel() {
+    for (float* p : te32_ws)
+      if (p) cudaFree(p);
+  }
   // speaker projections
   float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
   // AudioEnc / AudioDec packed for the tiled kernels (train-mode full-sequence forward)
@@ -387,9 +412,9 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
   SSV_CHECK(dilation >= 1, "highway_conv: dilation must be >= 1");
   cudaStream_t s = as_stream(stream);
   Arena ar_sync, ar_async(s);
-  // FP32 arm: stream-ordered scratch, no host synchronisation (it sits inside training steps); the tensor-core arm
-  // reports asynchronous MMA-pipeline errors, so it keeps the synchronous form
-  Arena& ar = precision == SSV_PREC_BF16 ? ar_sync : ar_async;
+  // CUDA-core arm: stream-ordered scratch, no host synchronisation (it sits inside training steps); the tensor-core
+  // arms report asynchronous MMA-pipeline errors, so they keep the synchronous form
+  Arena& ar = precision == SSV_PREC_FP32_FFMA ? ar_async : ar_sync;
   ParamMap pm;
   pm.m["conv.weight"] = {conv_w, (int64_t)2 * d * d * k};
   pm.m["conv.bias"] = {conv_b, 2 * d};
@@ -413,14 +438,24 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
     SSV_TRY(ar.alloc<__nv_bfloat16>((size_t)B * T * d, &xb));
     SSV_TRY(launch_cast_f32_to_bf16(xin, xb, (size_t)B * T * d, s));
     SSV_TRY(tc_launch(L, EPI_HIGHWAY, dilation, causal, xb, d, T, B, yout, d, true, s));
+  } else if (precision == SSV_PREC_FP32) {
+    // FP32-accurate tensor-core arm: tcgen05 kind::tf32 with split operands (conv_tc32.cu)
+    Tf32Layer L;
+    tf32_shape_highway(&L, d);
+    SSV_TRY(tf32_pack_layer(ar, pm, "conv.weight", c, 2 * d, d, k, &L, s));
+    float *xh, *xl;
+    SSV_TRY(ar.alloc<float>((size_t)B * T * d, &xh));
+    SSV_TRY(ar.alloc<float>((size_t)B * T * d, &xl));
+    SSV_TRY(launch_split_tf32(xin, xh, xl, (size_t)B * T * d, s));
+    SSV_TRY(tf32_launch(L, EPI_HIGHWAY, dilation, causal, xh, xl, d, T, B, yout, nullptr, d, s));
   } else {
-    SSV_CHECK(precision == SSV_PREC_FP32, "highway_conv: unknown precision %d", precision);
+    SSV_CHECK(precision == SSV_PREC_FP32_FFMA, "highway_conv: unknown precision %d", precision);
     SSV_TRY(run_conv(c, EPI_HIGHWAY, dilation, causal, xin, d, T, B, yout, d, s));
   }
   SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
-  if (precision == SSV_PREC_BF16) {
+  if (precision == SSV_PREC_BF16 || precision == SSV_PREC_FP32) {
     SSV_CUDA(cudaStreamSynchronize(s));   // arena is freed on return
-    SSV_TRY(tc_check_error());
+    SSV_TRY(precision == SSV_PREC_BF16 ? tc_check_error() : tf32_check_error());
   }
   return kOk;
 }
@@ -579,7 +614,14 @@ int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, 
     for (int i = 0; i < 12; ++i) {
       T2M_TRY(pack_highway(m->arena, pm, std::string("text_encoder.") + nm[i], D2, ks[i], &m->te_hc[i], s));
       m->te_dil[i] = dil[i];
+      tf32_shape_highway(&m->te32_hc[i], D2);
+      T2M_TRY(tf32_pack_layer(m->arena, pm, std::string("text_encoder.") + nm[i] + ".conv.weight", m->te_hc[i], 2 * D2, D2, ks[i],
+                              &m->te32_hc[i], s));
     }
+    tf32_shape_plain(&m->te32_conv1, D2);
+    T2M_TRY(tf32_pack_layer(m->arena, pm, "text_encoder.conv1.weight", m->te_conv1, D2, textemb_dim, 1, &m->te32_conv1, s));
+    tf32_shape_plain(&m->te32_conv2, D2);
+    T2M_TRY(tf32_pack_layer(m->arena, pm, "text_encoder.conv2.weight", m->te_conv2, D2, D2, 1, &m->te32_conv2, s));
   }
   // ---- speaker projections
   T2M_TRY(copy_vec(m->arena, pm, "audio_encoder.fc1.weight", H * spkemb_dim, &m->fc1_w, s));
@@ -718,14 +760,55 @@ static int text_encoder_cl(ssv_text2mel* m, const int64_t* textid, int B, int N,
   return kOk;
 }
 
+// The same on the tensor cores (conv_tc32.cu: tcgen05 kind::tf32 with split operands, FP32-accurate): activations
+// travel between layers as the (hi, lo) pair the next layer's TMA reads; the last layer writes plain fp32.
+static int text_encoder_cl_tc(ssv_text2mel* m, const int64_t* textid, int B, int N, float** out_cl, cudaStream_t s) {
+  const int D2 = 2 * m->H;
+  const size_t need = (size_t)B * N * D2;
+  if (need > m->te32_floats) {
+    for (float*& p : m->te32_ws) {
+      if (p) cudaFree(p);
+      p = nullptr;
+    }
+    m->te32_floats = 0;
+    for (float*& p : m->te32_ws)
+      if (cudaMalloc((void**)&p, need * sizeof(float) + 256) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("text_encoder: workspace cudaMalloc of %zu bytes failed", need * sizeof(float));
+        return kNoMem;
+      }
+    m->te32_floats = need;
+  }
+  float *Ph = m->te32_ws[0], *Pl = m->te32_ws[1], *Qh = m->te32_ws[2], *Ql = m->te32_ws[3];
+  const int e_ld = m->te32_conv1.cin_p;
+  SSV_TRY(launch_embed(textid, B, N, m->emb_wt, m->emb_b, m->vocab, m->temb, Qh, e_ld, m->err_flag, s));
+  SSV_TRY(launch_split_tf32(Qh, Ph, Pl, (size_t)B * N * e_ld, s));
+  SSV_TRY(tf32_launch(m->te32_conv1, EPI_LN_RELU, 1, 0, Ph, Pl, e_ld, N, B, Qh, Ql, D2, s));
+  SSV_TRY(tf32_launch(m->te32_conv2, EPI_LN, 1, 0, Qh, Ql, D2, N, B, Ph, Pl, D2, s));
+  float *ch = Ph, *cl = Pl, *nh = Qh, *nl = Ql;
+  for (int i = 0; i < 12; ++i) {
+    const bool last = i == 11;
+    SSV_TRY(tf32_launch(m->te32_hc[i], EPI_HIGHWAY, m->te_dil[i], 0, ch, cl, D2, N, B, nh, last ? nullptr : nl, D2, s));
+    float* t = ch; ch = nh; nh = t;
+    t = cl; cl = nl; nl = t;
+  }
+  *out_cl = ch;
+  return kOk;
+}
+
 int ssv_text_encoder_fwd(ssv_text2mel* m, const int64_t* textid, int B, int N, float* K, float* V, int precision,
                          void* stream) {
   SSV_CHECK(m && textid && K && V, "text_encoder: null pointer");
   SSV_CHECK(B > 0 && N > 0, "text_encoder: empty input");
-  SSV_CHECK(precision == SSV_PREC_FP32, "text_encoder: only SSV_PREC_FP32 is implemented");
+  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA,
+            "text_encoder: SSV_PREC_FP32 (tensor cores, 3xTF32 split) or SSV_PREC_FP32_FFMA (CUDA cores); a BF16 TextEnc moves "
+            "the alignment trajectory and is not built");
   cudaStream_t s = as_stream(stream);
   float* x;
-  SSV_TRY(text_encoder_cl(m, textid, B, N, &x, s));
+  if (precision == SSV_PREC_FP32 && m->temb % T32_BK == 0)
+    SSV_TRY(text_encoder_cl_tc(m, textid, B, N, &x, s));
+  else
+    SSV_TRY(text_encoder_cl(m, textid, B, N, &x, s));
   SSV_TRY(launch_transpose_out2(x, 2 * m->H, 0, B, m->H, N, K, s));
   SSV_TRY(launch_transpose_out2(x, 2 * m->H, m->H, B, m->H, N, V, s));
   return kOk;
@@ -953,6 +1036,7 @@ int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_
 int ssv_text2mel_check(ssv_text2mel* m, void* stream) {
   SSV_CHECK(m, "text2mel_check: null model");
   SSV_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  SSV_TRY(tf32_check_error());
   int eflag = 0;
   SSV_CUDA(cudaMemcpy(&eflag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
   if (eflag != 0) {
@@ -973,6 +1057,7 @@ int ssv_decoder_check(ssv_decoder* d, void* stream) {
     cudaMemset(d->abort_flag, 0, sizeof(int));
     return kState;
   }
+  SSV_TRY(tf32_check_error());            // TextEnc runs on the split tensor-core arm: its pipeline-timeout flag
   int eflag = 0;
   SSV_CUDA(cudaMemcpy(&eflag, d->m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
   if (eflag != 0) {

@@ -1,0 +1,611 @@
+// FP32-accurate tensor-core arm of the batched conv stacks: tcgen05 (kind::tf32) implicit-GEMM conv1d with split
+// operands ("3xTF32") + the fused LayerNorm / highway-gate epilogue.
+//
+// TextEnc (models/TTSModel.py:126-140) has to stay inside the FP32 bar (1e-4 max-abs on the spectrograms, identical
+// alignments): its K / V feed 217 argmax decisions per utterance.  Plain TF32 / BF16 operands are 1e-3 off.
+// Here every fp32 operand x is carried as two TF32 numbers, hi = tf32(x) and lo = tf32(x - hi) (22 mantissa bits
+// together), and a product is three MMAs,
+//      D0 += A_hi B_hi            D1 += A_hi B_lo + A_lo B_hi            (A_lo B_lo ~ 2^-22: dropped)
+// with the large term and the two corrections in SEPARATE fp32 TMEM accumulators, so the corrections are not
+// truncated against the 2^11 times larger running sum; the epilogue adds D0 + D1 in fp32.
+//
+// GEMM view as in conv_tc.cu: M = 128 rows of time steps (T <= 64: two utterances of 64 rows, so the 58-character
+// TextEnc batch fills 91 % of a tile instead of 45 %), K = taps * Cin (tap-major), N = output channels.  TMA stages
+// both halves of both operands in 64-byte-swizzled shared memory (k-blocks of 16 fp32; a conv tap is the same box at
+// a shifted T coordinate, zero padding is TMA out-of-bounds fill).  A CTA owns 256 accumulator columns (D0 and D1
+// fill the 512 TMEM columns); wider layers split N over a cluster of 2 or 4 CTAs, each with matching H1 / H2 column
+// slices, and the per-row LayerNorm partial sums cross the cluster through distributed shared memory.
+// The output is written as the (hi, lo) pair the next layer's TMA reads, or as plain fp32 for the last layer.
+#include "conv_tc32.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace ssv {
+
+namespace {
+
+constexpr int NT = 384;                   // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-11: epilogue
+constexpr int TMEM_COLS = 512;
+constexpr long long WAIT_LIMIT = 2000000000LL;
+constexpr uint32_t A_HALF_BYTES = T32_BM * T32_BK * 4;          // 8 KB: one of (hi, lo) of the activation tile
+constexpr uint32_t B_HALF_BYTES = T32_NL * T32_BK * 4;          // 16 KB: one of (hi, lo) of the weight tile
+constexpr uint32_t STAGE_BYTES = 2 * A_HALF_BYTES + 2 * B_HALF_BYTES;   // 48 KB
+constexpr int RES_LD = 132;               // floats per row of the staged residual / highway output tile (odd number of 16-byte units)
+constexpr int OUT_LD = 260;               // floats per row of the staged 256-column output tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must not hang the GPU.  Returns false after ~1 s and flags the error.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WAIT_LIMIT) {
+      atomicExch(err, 5);
+      return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major fp32 read as TF32 (K = 8 per instruction).
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// K-major SWIZZLE_64B operand tile: rows of 64 bytes, 8-row groups 512 bytes apart
+// (cute::UMMA::SmemDescriptor: start >> 4 | LBO = 1 | SBO = 32 | version = 1 | layout_type = 4).
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+// cute::UMMA::InstrDescriptor, kind::tf32: D = F32 (bit 4), A = B = TF32 (2 at bits 7 and 10), both K-major, N = 256, M = 128.
+__device__ __forceinline__ uint32_t umma_idesc_tf32() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T32_NL >> 3) << 17) | ((uint32_t)(T32_BM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_peer_f32x4(float4* local_ptr, uint32_t peer, float4 v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(peer));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// round to nearest TF32 (10 explicit mantissa bits), kept in an fp32 container
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z), to_tf32(v.w - hi.w));
+}
+
+__global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constant__ ConvTf32Args a, int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)a.nstages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + a.nstages;
+  uint64_t* accum_bar = empty_bar + a.nstages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  float4* prm_s = reinterpret_cast<float4*>(smem + (((size_t)a.nstages * STAGE_BYTES + (2 * a.nstages + 1) * 8 + 8 + 15) & ~size_t(15)));
+  float4* part_s = prm_s + T32_NL;                                // [2][128] per-row partial sums of the two column halves
+  float4* stat_s = part_s + 2 * T32_BM;                           // [4 ranks][128] the cluster's sums
+  float* res_s = reinterpret_cast<float*>(tiles);                 // [128][RES_LD] residual tile (aliases the drained stages)
+  // output staging tile: behind the residual tile (highway, 128 columns) or at the start (plain LayerNorm, 256 columns)
+  float* out_s = reinterpret_cast<float*>(tiles) + (a.epi == EPI_HIGHWAY ? T32_BM * RES_LD : 0);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = a.cluster_n > 1 ? cluster_rank() : 0u;
+  const int tile = blockIdx.x / a.cluster_n;
+  int b0, t0;
+  if (a.utt_per_tile > 1) { b0 = tile * a.utt_per_tile; t0 = 0; }
+  else { b0 = tile / a.tiles_per_b; t0 = (tile - b0 * a.tiles_per_b) * T32_BM; }
+  const int w0 = a.w0_base + (int)rank * a.w0_rank;
+  const int w1 = a.w1_base + (int)rank * a.w1_rank;
+  const int nk = a.ktaps * a.kb_per_tap;
+  const bool hwy = a.epi == EPI_HIGHWAY;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&a.tmAh); prefetch_tmap(&a.tmAl); prefetch_tmap(&a.tmBh); prefetch_tmap(&a.tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a.nstages; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  // per-column parameters of my 256 local columns -> smem: {bias, LN weight, LN bias, 0}
+  for (int j = threadIdx.x; j < T32_NL; j += NT) {
+    const int gc = j < 128 ? w0 + j : w1 + (j - 128);
+    float g, be;
+    if (hwy) {
+      const int c = j < 128 ? gc : gc - a.n_real;          // channel inside LN1 / LN2
+      g = j < 128 ? a.g1[c] : a.g2[c];
+      be = j < 128 ? a.b1[c] : a.b2[c];
+    } else {
+      g = a.g1[gc];
+      be = a.b1[gc];
+    }
+    prm_s[j] = make_float4(a.bias[gc], g, be, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (a.cluster_n > 1) cluster_sync_all();     // every CTA of the cluster is running before a DSMEM store targets it
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % a.nstages;
+        const uint32_t ph = (uint32_t)(kb / a.nstages) & 1u;
+        if (!mbar_wait(empty_bar + st, ph ^ 1u, err)) break;
+        uint8_t* S = tiles + (size_t)st * STAGE_BYTES;
+        mbar_expect_tx(full_bar + st, STAGE_BYTES);
+        const int j = kb / a.kb_per_tap;
+        const int c0 = (kb - j * a.kb_per_tap) * T32_BK;
+        const int tc = t0 + (tap_base + j) * a.dil;
+        tma_load_3d(S, &a.tmAh, full_bar + st, c0, tc, b0);
+        tma_load_3d(S + A_HALF_BYTES, &a.tmAl, full_bar + st, c0, tc, b0);
+        uint8_t* Bh = S + 2 * A_HALF_BYTES;
+        uint8_t* Bl = Bh + B_HALF_BYTES;
+        tma_load_2d(Bh, &a.tmBh, full_bar + st, kb * T32_BK, w0);
+        tma_load_2d(Bh + B_HALF_BYTES / 2, &a.tmBh, full_bar + st, kb * T32_BK, w1);
+        tma_load_2d(Bl, &a.tmBl, full_bar + st, kb * T32_BK, w0);
+        tma_load_2d(Bl + B_HALF_BYTES / 2, &a.tmBl, full_bar + st, kb * T32_BK, w1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32();
+      const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)T32_NL;
+      bool ok = true;
+      for (int kb = 0; kb < nk && ok; ++kb) {
+        const int st = kb % a.nstages;
+        const uint32_t ph = (uint32_t)(kb / a.nstages) & 1u;
+        ok = mbar_wait(full_bar + st, ph, err);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t Ah = smem_u32(tiles + (size_t)st * STAGE_BYTES);
+        const uint32_t Al = Ah + A_HALF_BYTES;
+        const uint32_t Bh = Al + A_HALF_BYTES;
+        const uint32_t Bl = Bh + B_HALF_BYTES;
+#pragma unroll
+        for (int k = 0; k < T32_BK / 8; ++k) {
+          const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+          const uint64_t ah = umma_desc64(Ah + k * 32), al = umma_desc64(Al + k * 32);
+          const uint64_t bh = umma_desc64(Bh + k * 32), bl = umma_desc64(Bl + k * 32);
+          umma_tf32(d_main, ah, bh, idesc, acc);
+          umma_tf32(d_corr, ah, bl, idesc, acc);
+          umma_tf32(d_corr, al, bh, idesc, 1u);
+        }
+        umma_commit(empty_bar + st);          // frees the smem slot once these MMAs retire
+      }
+      umma_commit(accum_bar);                 // accumulators complete
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> LN / gate -> smem -> global =====================
+    // 8 warps: warp (q, hsel) reads TMEM lane quadrant q (rows q*32 ..) and column half hsel of each 128-column block.
+    const int q = warp & 3, hsel = (warp - 4) >> 2, ew = warp - 4;
+    const int row = q * 32 + lane;
+    const bool got = mbar_wait(accum_bar, 0u, err);
+    tc_fence_after();
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    auto row_coords = [&](int r, int& bb, int& tt) {
+      const int u = r / a.rows_per_utt;
+      bb = b0 + u;
+      tt = t0 + (r - u * a.rows_per_utt);
+      return got && bb < a.B && tt < a.T;
+    };
+
+    if (hwy) {
+      // the residual rows (my 128-channel slice, hi + lo) -> smem, coalesced; the pipeline stages are drained
+      for (int i = 0; i < T32_BM / 8; ++i) {
+        const int r = ew * (T32_BM / 8) + i;
+        int bb, tt;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_coords(r, bb, tt)) {
+          const long off = (long)bb * a.x_sb + (long)tt * a.x_st + w0 + lane * 4;
+          const float4 h = *reinterpret_cast<const float4*>(a.Xh + off);
+          const float4 l = *reinterpret_cast<const float4*>(a.Xl + off);
+          v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+        }
+        *reinterpret_cast<float4*>(res_s + (size_t)r * RES_LD + lane * 4) = v;
+      }
+    }
+
+    uint32_t r0[16], r1[16], r2[16], r3[16];
+    float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
+    // pass 1: per-row sums over my columns.  Highway: my 64 channels of H1 (block 0) and of H2 (block 1);
+    // plain LayerNorm: my 128 columns (block hsel).
+    const int c_lo = hwy ? hsel * 64 : hsel * 128;
+    const int c_n = hwy ? 64 : 128;
+    for (int c = c_lo; c < c_lo + c_n; c += 16) {
+      tmem_ld16_issue(tq + c, r0);
+      tmem_ld16_issue(tq + T32_NL + c, r1);
+      if (hwy) {
+        tmem_ld16_issue(tq + 128 + c, r2);
+        tmem_ld16_issue(tq + T32_NL + 128 + c, r3);
+      }
+      tmem_wait16(r0);
+      tmem_wait16(r1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + prm_s[c + i].x;
+        s1 += x; q1 = fmaf(x, x, q1);
+      }
+      if (hwy) {
+        tmem_wait16(r2);
+        tmem_wait16(r3);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + prm_s[128 + c + i].x;
+          s2 += x; q2 = fmaf(x, x, q2);
+        }
+      }
+    }
+    part_s[hsel * T32_BM + row] = make_float4(s1, q1, s2, q2);
+    epi_bar_sync();                             // also: the residual tile is complete
+    {
+      const float4 lo4 = part_s[row], hi4 = part_s[T32_BM + row];        // fixed order: both halves get identical sums
+      s1 = lo4.x + hi4.x; q1 = lo4.y + hi4.y; s2 = lo4.z + hi4.z; q2 = lo4.w + hi4.w;
+    }
+    if (a.cluster_n > 1) {
+      if (hsel == 0) {
+        const float4 mine = make_float4(s1, q1, s2, q2);
+        stat_s[rank * T32_BM + row] = mine;
+        for (uint32_t p = 0; p < (uint32_t)a.cluster_n; ++p)
+          if (p != rank) st_peer_f32x4(stat_s + rank * T32_BM + row, p, mine);
+      }
+      cluster_sync_all();
+      s1 = q1 = s2 = q2 = 0.f;
+      for (int p = 0; p < a.cluster_n; ++p) {                              // fixed order: every CTA gets identical sums
+        const float4 v = stat_s[p * T32_BM + row];
+        s1 += v.x; q1 += v.y; s2 += v.z; q2 += v.w;
+      }
+    }
+    const float inv_n = 1.0f / (float)a.n_real;
+    const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+    const float rs1 = 1.0f / sqrtf(fmaxf(q1 * inv_n - m1 * m1, 0.f) + 1e-5f);
+    const float rs2 = 1.0f / sqrtf(fmaxf(q2 * inv_n - m2 * m2, 0.f) + 1e-5f);
+
+    // pass 2: normalise (+ gate with the residual), into the staging tile
+    const int o_ld = hwy ? RES_LD : OUT_LD;
+    const bool relu = a.epi == EPI_LN_RELU;
+    for (int c = c_lo; c < c_lo + c_n; c += 16) {
+      tmem_ld16_issue(tq + c, r0);
+      tmem_ld16_issue(tq + T32_NL + c, r1);
+      if (hwy) {
+        tmem_ld16_issue(tq + 128 + c, r2);
+        tmem_ld16_issue(tq + T32_NL + 128 + c, r3);
+      }
+      tmem_wait16(r0);
+      tmem_wait16(r1);
+      float o[16];
+      if (hwy) {
+        tmem_wait16(r2);
+        tmem_wait16(r3);
+        const float* xr = res_s + (size_t)row * RES_LD + c;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 p1 = prm_s[c + i], p2 = prm_s[128 + c + i];
+          const float x1 = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + p1.x;
+          const float x2 = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + p2.x;
+          const float h1 = (x1 - m1) * rs1 * p1.y + p1.z;
+          const float h2 = (x2 - m2) * rs2 * p2.y + p2.z;
+          const float g = sigmoid_acc(h1);
+          o[i] = g * h2 + (1.0f - g) * xr[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 p1 = prm_s[c + i];
+          const float x1 = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + p1.x;
+          const float h1 = (x1 - m1) * rs1 * p1.y + p1.z;
+          o[i] = relu ? fmaxf(h1, 0.f) : h1;
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(out_s + (size_t)row * o_ld + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+    epi_bar_sync();
+    // coalesced copy-out of my CTA's columns: highway [w0, w0 + 128); plain [w0, w0 + 128) and [w1, w1 + 128)
+    const int f4_per_row = hwy ? 32 : 64;
+    for (int i = 0; i < T32_BM / 8; ++i) {
+      const int r = ew * (T32_BM / 8) + i;
+      int bb, tt;
+      if (!row_coords(r, bb, tt)) continue;
+      const long yoff = (long)bb * a.y_sb + (long)tt * a.y_st;
+      for (int f = lane; f < f4_per_row; f += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(out_s + (size_t)r * o_ld + f * 4);
+        const int gc = f < 32 ? w0 + f * 4 : w1 + (f - 32) * 4;
+        if (a.Yl != nullptr) {
+          float4 hi, lo;
+          split4(v, hi, lo);
+          *reinterpret_cast<float4*>(a.Yh + yoff + gc) = hi;
+          *reinterpret_cast<float4*>(a.Yl + yoff + gc) = lo;
+        } else {
+          *reinterpret_cast<float4*>(a.Yh + yoff + gc) = v;
+        }
+      }
+    }
+  }
+
+  // non-epilogue warps of a cluster-split layer still have to take part in the cluster barrier
+  if (a.cluster_n > 1 && warp < 4) cluster_sync_all();
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn32() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int make_map_f32(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                 const cuuint32_t* box) {
+  auto fn = encode_fn32();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return kCuda;
+  }
+  cuuint32_t ones[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+    return kCuda;
+  }
+  return kOk;
+}
+
+// [n][cin][k] fp32 -> [n][k * cin_p] (K contiguous, tap-major), split into hi / lo
+__global__ void pack_w_tf32_kernel(const float* __restrict__ w, int n, int cin, int k, int cin_p, float* __restrict__ hi,
+                                   float* __restrict__ lo) {
+  const long kp = (long)k * cin_p;
+  const long total = (long)n * kp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % kp);
+    const int row = (int)(i / kp);
+    const int j = kk / cin_p, ci = kk % cin_p;
+    const float v = ci < cin ? w[((long)row * cin + ci) * k + j] : 0.f;
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(v - h);
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(v - h);
+  }
+}
+
+int* tf32_err_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc((void**)&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+}  // namespace
+
+void tf32_shape_highway(Tf32Layer* L, int d) {
+  L->n_real = d;
+  L->cluster_n = d / 128;
+  L->w0_base = 0; L->w0_rank = 128;
+  L->w1_base = d; L->w1_rank = 128;
+}
+
+void tf32_shape_plain(Tf32Layer* L, int n) {
+  L->n_real = n;
+  L->cluster_n = n / 256;
+  L->w0_base = 0; L->w0_rank = 256;
+  L->w1_base = 128; L->w1_rank = 256;
+}
+
+int tf32_pack_weights(const float* w, int n, int cin, int k, int cin_p, float* hi, float* lo, cudaStream_t s) {
+  pack_w_tf32_kernel<<<1024, 256, 0, s>>>(w, n, cin, k, cin_p, hi, lo);
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t s) {
+  split_tf32_kernel<<<1024, 256, 0, s>>>(x, hi, lo, n);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int tf32_check_error() {
+  int* flag = tf32_err_flag();
+  if (!flag) return kOk;
+  int h = 0;
+  SSV_CUDA(cudaMemcpy(&h, flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h != 0) {
+    cudaMemset(flag, 0, sizeof(int));
+    set_error("tcgen05 (3xTF32) conv kernel: pipeline wait timed out (code %d)", h);
+    return kState;
+  }
+  return kOk;
+}
+
+int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
+                float* Yh, float* Yl, int y_ld, cudaStream_t s) {
+  SSV_CHECK(L.cin_p % T32_BK == 0 && x_ld >= L.cin_p && x_ld % 4 == 0, "conv_tf32: bad K padding (cin_p %d, ld %d)", L.cin_p, x_ld);
+  SSV_CHECK(epi == EPI_HIGHWAY || epi == EPI_LN || epi == EPI_LN_RELU, "conv_tf32: epilogue %d not built", epi);
+  SSV_CHECK(L.cluster_n == 1 || L.cluster_n == 2 || L.cluster_n == 4, "conv_tf32: cluster_n must be 1, 2 or 4");
+  SSV_CHECK(y_ld % 4 == 0, "conv_tf32: output row stride must be a multiple of 4");
+  int* err = tf32_err_flag();
+  SSV_CHECK(err != nullptr, "conv_tf32: cannot allocate the error flag");
+
+  ConvTf32Args a;
+  memset(&a, 0, sizeof(a));
+  a.T = T; a.B = B;
+  a.rows_per_utt = T <= 64 ? 64 : T32_BM;
+  a.utt_per_tile = T32_BM / a.rows_per_utt;
+  a.tiles_per_b = (T + T32_BM - 1) / T32_BM;
+  const int n_tiles = a.utt_per_tile > 1 ? (B + a.utt_per_tile - 1) / a.utt_per_tile : B * a.tiles_per_b;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)x_ld, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)x_ld * 4, (cuuint64_t)T * x_ld * 4};
+    cuuint32_t box[3] = {(cuuint32_t)T32_BK, (cuuint32_t)a.rows_per_utt, (cuuint32_t)a.utt_per_tile};
+    SSV_TRY(make_map_f32(&a.tmAh, Xh, 3, dims, strides, box));
+    SSV_TRY(make_map_f32(&a.tmAl, Xl, 3, dims, strides, box));
+  }
+  const int kp = L.k * L.cin_p;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)L.rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * 4};
+    cuuint32_t box[2] = {(cuuint32_t)T32_BK, 128};
+    SSV_TRY(make_map_f32(&a.tmBh, L.Wh, 2, dims, strides, box));
+    SSV_TRY(make_map_f32(&a.tmBl, L.Wl, 2, dims, strides, box));
+  }
+  a.kb_per_tap = L.cin_p / T32_BK;
+  a.ktaps = L.k; a.dil = dil; a.causal = causal;
+  a.cluster_n = L.cluster_n;
+  a.w0_base = L.w0_base; a.w0_rank = L.w0_rank; a.w1_base = L.w1_base; a.w1_rank = L.w1_rank;
+  a.n_real = L.n_real;
+  a.epi = epi;
+  a.bias = L.bias;
+  a.g1 = L.g1; a.b1 = L.b1; a.g2 = L.g2; a.b2 = L.b2;
+  a.Xh = Xh; a.Xl = Xl; a.x_sb = (long)T * x_ld; a.x_st = x_ld;
+  a.Yh = Yh; a.Yl = Yl; a.y_sb = (long)T * y_ld; a.y_st = y_ld;
+  a.nstages = 4;
+  const size_t fixed = 1024 /*align*/ + 256 /*barriers, tmem slot*/ + (size_t)T32_NL * 16 + 2 * T32_BM * 16 + 4 * T32_BM * 16;
+  const size_t smem = fixed + (size_t)a.nstages * STAGE_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    SSV_CUDA(cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(n_tiles * L.cluster_n));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)L.cluster_n;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SSV_CUDA(cudaLaunchKernelEx(&cfg, conv_tf32x3_kernel, a, err));
+  ++g_launches;
+  return kOk;
+}
+
+}  // namespace ssv

@@ -1,0 +1,56 @@
+// tcgen05 / TMEM / TMA implicit-GEMM conv + LayerNorm / highway-gate kernel, FP32-accurate: 3xTF32 split operands.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ssv {
+
+constexpr int T32_BM = 128;   // rows per CTA tile == UMMA M
+constexpr int T32_BK = 16;    // fp32 elements per k-block: 64-byte rows, SWIZZLE_64B; two K = 8 MMA steps
+constexpr int T32_NL = 256;   // accumulator columns per CTA = two 128-row weight blocks
+
+// Kernel argument block (__grid_constant__; holds the TMA descriptors).
+struct alignas(64) ConvTf32Args {
+  CUtensorMap tmAh, tmAl;   // activations hi / lo, 3-D (C, T, B) fp32, box (16, rows_per_utt, utt_per_tile)
+  CUtensorMap tmBh, tmBl;   // weights hi / lo, 2-D (K, rows) fp32, box (16, 128)
+  int T, B;
+  int rows_per_utt;         // 64 (two utterances per tile: T <= 64) or 128
+  int utt_per_tile;         // 128 / rows_per_utt
+  int tiles_per_b;          // ceil(T / 128) when utt_per_tile == 1
+  int kb_per_tap;           // cin_p / 16
+  int ktaps, dil, causal;
+  int cluster_n;            // CTAs splitting N: 1, 2 or 4
+  int w0_base, w0_rank;     // weight-row / output-column origin of block 0 = w0_base + rank * w0_rank
+  int w1_base, w1_rank;     // same for block 1
+  int n_real;               // LayerNorm width
+  int epi;                  // Epilogue (EPI_LN, EPI_LN_RELU, EPI_HIGHWAY)
+  int nstages;
+  const float* bias;        // [N] fp32, indexed by global column
+  const float* g1; const float* b1; const float* g2; const float* b2;
+  const float* Xh; const float* Xl; long x_sb, x_st;   // residual input of a highway layer = Xh + Xl (channels-last)
+  float* Yh; float* Yl;     // output, channels-last: the TF32 split (hi, lo) for the next layer's operands, or,
+                            // with Yl == nullptr, the plain fp32 value in Yh
+  long y_sb, y_st;
+};
+
+// One layer packed for this path: weights [rows][taps * cin_p] fp32 (K contiguous, tap-major) split into hi / lo.
+struct Tf32Layer {
+  float* Wh = nullptr;
+  float* Wl = nullptr;
+  const float* bias = nullptr;
+  const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+  int rows = 0, cin = 0, cin_p = 0, k = 1;
+  int cluster_n = 1, w0_base = 0, w0_rank = 0, w1_base = 0, w1_rank = 0, n_real = 0;
+};
+
+void tf32_shape_highway(Tf32Layer* L, int d);     // rows = 2 d, d in {256, 512}
+void tf32_shape_plain(Tf32Layer* L, int n);       // n in {256, 512}
+int tf32_pack_weights(const float* w /*[n][cin][k]*/, int n, int cin, int k, int cin_p, float* hi, float* lo, cudaStream_t s);
+// x (fp32, any layout, n elements) -> hi = tf32(x), lo = tf32(x - hi)
+int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t s);
+int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
+                float* Yh, float* Yl, int y_ld, cudaStream_t s);
+int tf32_check_error();
+
+}  // namespace ssv

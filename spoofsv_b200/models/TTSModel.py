@@ -45,9 +45,9 @@ def _hci(d: int) -> _Bag:
 
 def _prec(name: str) -> int:
     try:
-        return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[name]
+        return {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp32-ffma": _lib.PREC_FP32_FFMA}[name]
     except KeyError:
-        raise ValueError(f"precision must be 'fp32' or 'bf16', got {name!r}") from None
+        raise ValueError(f"precision must be 'fp32', 'fp32-ffma' or 'bf16', got {name!r}") from None
 
 
 class _Native(nn.Module):
@@ -159,7 +159,7 @@ class _HighwayConvFn(torch.autograd.Function):
                 xs.data_ptr(), *[p.data_ptr() for p in ps], B, d, T, k, dilation, int(causal), y.data_ptr(), h.data_ptr(),
                 _lib.current_stream_ptr()))
         else:
-            y = _highway_fwd(xs, ps, k, dilation, causal, "fp32")
+            y = _highway_fwd(xs, ps, k, dilation, causal, "fp32-ffma")
         ctx.save_for_backward(xs, *ps, *([h] if h is not None else []))
         ctx.cfg = (k, dilation, causal, h is not None)
         return y

@@ -106,6 +106,52 @@ def test_text_encoder_golden(golden_dir, cuda_models_k):
     assert _maxabs(K, _t(z["K"])) <= FP32_TOL and _maxabs(V, _t(z["V"])) <= FP32_TOL
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp32-ffma"])
+def test_text_encoder_both_fp32_arms(prec, golden_dir, cuda_models_k, cuda_models):
+    """TextEnc on the tensor cores (tcgen05 kind::tf32, split operands: the default FP32 arm) and on the CUDA cores
+    (FFMA, the cross-check) against the reference's K / V: the kaiming-init ragged batch, BASELINE config 1, and the
+    bench batch (64 x 58, against the oracle)."""
+    m1k, m1 = cuda_models_k[0], cuda_models[0]
+    for m in (m1k, m1):
+        m.precision = prec
+    try:
+        z = np.load(golden_dir / "small_seed7.npz")
+        K, V = m1k.encode_text(_t(z["textid"]).cuda())
+        assert _maxabs(K, _t(z["K"])) <= FP32_TOL and _maxabs(V, _t(z["V"])) <= FP32_TOL
+        z = np.load(golden_dir / "cfg1_seed0.npz")
+        K, V = m1.encode_text(_t(z["textid"]).cuda())
+        assert _maxabs(K, _t(z["K"])) <= FP32_TOL
+        ids = W.synthetic_text(64, 58, seed=11)
+        with torch.no_grad():
+            oK, oV = O.text_encoder(ids, cuda_models[2])
+        K, V = m1.encode_text(ids.cuda())
+        assert _maxabs(K, oK) <= FP32_TOL and _maxabs(V, oV) <= FP32_TOL
+        # odd batch (the second utterance of the last 2 x 64-row tile is out of bounds), one character, 65 characters
+        # (one utterance per 128-row tile), 130 (two tiles per utterance)
+        for B, N in ((3, 58), (1, 1), (2, 65), (2, 130)):
+            ids = W.synthetic_text(B, N, seed=B + N)
+            with torch.no_grad():
+                oK, oV = O.text_encoder(ids, cuda_models[2])
+            K, V = m1.encode_text(ids.cuda())
+            assert _maxabs(K, oK) <= FP32_TOL and _maxabs(V, oV) <= FP32_TOL, (B, N)
+    finally:
+        for m in (m1k, m1):
+            m.precision = "fp32"
+
+
+def test_highway_conv_ffma_arm_all_classes(golden_dir):
+    """The CUDA-core FP32 arm (precision 'fp32-ffma'; the training backward's forward) stays pinned to the goldens."""
+    from spoofsv_b200.models import highwayConv
+    z = np.load(golden_dir / "highway_cases.npz")
+    for i, (d, k, dil, causal) in enumerate(z["cases"].tolist()):
+        hc = highwayConv(dimension=d, kernel_size=k, dilation=dil, causal=bool(causal))
+        hc.load_state_dict(W.highway_params(d, k, 100 + i), strict=True)
+        hc = hc.cuda().eval()
+        hc.precision = "fp32-ffma"
+        x = torch.randn((2, d, 45), generator=torch.Generator().manual_seed(200 + i))
+        assert _maxabs(hc(x.cuda()), _t(z[f"y{i}"])) <= FP32_TOL, (d, k, dil, causal)
+
+
 def test_text_encoder_rejects_bad_ids(cuda_models):
     m1, _, _, _ = cuda_models
     with pytest.raises(ValueError):
