@@ -552,7 +552,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp32" if args.ssrn_precision == "fp32" else "fp32 Text2Mel (FFMA) + bf16 SSRN (tcgen05, fp32 accumulate)",
+        "dtype": ("fp32 (TextEnc: tcgen05 kind::tf32 with 3xTF32 split operands, FP32-accurate; decode: FFMA)"
+                  + (" + fp32 SSRN (FFMA)" if args.ssrn_precision == "fp32" else " + bf16 SSRN (tcgen05, fp32 accumulate)")),
         "data": "synthetic",
         "config": config_dict(args, B),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(syn.h2d_bytes),
@@ -572,6 +573,15 @@ def main():
                          "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": B * T * DECODE_FLOP_PER_FRAME / (dec_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
                          "peak_source": "148 SMs x 128 lanes x 2 x 1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)"},
+        "roofline_textenc": {"kernel": "conv_tf32x3_kernel x 14 (+ embedding gather, split, K/V transposes, decoder begin)",
+                             "bound": "tensor", "unit": "TFLOP/s",
+                             "achieved": 3 * B * N_TEXT * TEXTENC_FLOP_PER_CHAR / (te_ms * 1e-3) / 1e12,
+                             "peak": peaks["bf16_sustained"] / 2,
+                             "frac": 3 * B * N_TEXT * TEXTENC_FLOP_PER_CHAR / (te_ms * 1e-3) / 1e12 / (peaks["bf16_sustained"] / 2),
+                             "useful_fp32_tflops": B * N_TEXT * TEXTENC_FLOP_PER_CHAR / (te_ms * 1e-3) / 1e12,
+                             "note": "achieved counts the three TF32 MMAs per product (hi*hi, hi*lo, lo*hi); peak = half the measured "
+                                     "sustained bf16 rate (kind::tf32 issues at half the kind::f16 rate); useful_fp32_tflops is the "
+                                     "algorithmic FP32 rate (CUDA-core FP32 peak: 74.4)"},
         "roofline_ssrn": {"bound": "tensor", "achieved": ssrn_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                           "frac": ssrn_tflops / peaks["bf16_sustained"], "precision": args.ssrn_precision},
         "extra": extra,

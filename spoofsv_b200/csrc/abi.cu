@@ -298,6 +298,8 @@ struct ssv_text2mel {
   Tf32Layer te32_conv1, te32_conv2, te32_hc[12];     // the same layers for the tensor-core (3xTF32) arm
   float* te32_ws[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t te32_floats = 0;
+  Tf32Launch te32_plan[14];                           // encoded launches of the 14 layers for (te32_B, te32_N)
+  int te32_B = 0, te32_N = 0;
   ~ssv_text2mel() {
     for (float* p : te32_ws)
       if (p) cudaFree(p);
@@ -778,20 +780,27 @@ static int text_encoder_cl_tc(ssv_text2mel* m, const int64_t* textid, int B, int
         return kNoMem;
       }
     m->te32_floats = need;
+    m->te32_B = m->te32_N = 0;                     // the launches hold the old buffer addresses
   }
   float *Ph = m->te32_ws[0], *Pl = m->te32_ws[1], *Qh = m->te32_ws[2], *Ql = m->te32_ws[3];
   const int e_ld = m->te32_conv1.cin_p;
+  if (m->te32_B != B || m->te32_N != N) {          // (re)build the 14 launches: TMA descriptors of this shape
+    m->te32_B = m->te32_N = 0;
+    SSV_TRY(tf32_prepare(m->te32_conv1, EPI_LN_RELU, 1, 0, Ph, Pl, e_ld, N, B, Qh, Ql, D2, &m->te32_plan[0]));
+    SSV_TRY(tf32_prepare(m->te32_conv2, EPI_LN, 1, 0, Qh, Ql, D2, N, B, Ph, Pl, D2, &m->te32_plan[1]));
+    float *ch = Ph, *cl = Pl, *nh = Qh, *nl = Ql;
+    for (int i = 0; i < 12; ++i) {
+      const bool last = i == 11;
+      SSV_TRY(tf32_prepare(m->te32_hc[i], EPI_HIGHWAY, m->te_dil[i], 0, ch, cl, D2, N, B, nh, last ? nullptr : nl, D2, &m->te32_plan[2 + i]));
+      float* t = ch; ch = nh; nh = t;
+      t = cl; cl = nl; nl = t;
+    }
+    m->te32_B = B; m->te32_N = N;
+  }
   SSV_TRY(launch_embed(textid, B, N, m->emb_wt, m->emb_b, m->vocab, m->temb, Qh, e_ld, m->err_flag, s));
   SSV_TRY(launch_split_tf32(Qh, Ph, Pl, (size_t)B * N * e_ld, s));
-  SSV_TRY(tf32_launch(m->te32_conv1, EPI_LN_RELU, 1, 0, Ph, Pl, e_ld, N, B, Qh, Ql, D2, s));
-  SSV_TRY(tf32_launch(m->te32_conv2, EPI_LN, 1, 0, Qh, Ql, D2, N, B, Ph, Pl, D2, s));
-  float *ch = Ph, *cl = Pl, *nh = Qh, *nl = Ql;
-  for (int i = 0; i < 12; ++i) {
-    const bool last = i == 11;
-    SSV_TRY(tf32_launch(m->te32_hc[i], EPI_HIGHWAY, m->te_dil[i], 0, ch, cl, D2, N, B, nh, last ? nullptr : nl, D2, s));
-    float* t = ch; ch = nh; nh = t;
-    t = cl; cl = nl; nl = t;
-  }
+  for (int i = 0; i < 14; ++i) SSV_TRY(tf32_run(m->te32_plan[i], s));
+  float* ch = Ph;                                  // 12 highway layers: the result is back in the first buffer
   *out_cl = ch;
   return kOk;
 }

@@ -150,7 +150,8 @@ __device__ __forceinline__ void st_peer_f32x4(float4* local_ptr, uint32_t peer, 
                : "memory");
 }
 
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU-based (2 ulp), as the decode kernel's gate: the epilogue is instruction-bound on the IEEE slow paths otherwise
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // round to nearest TF32 (10 explicit mantissa bits), kept in an fp32 container
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
   float4* prm_s = reinterpret_cast<float4*>(smem + (((size_t)a.nstages * STAGE_BYTES + (2 * a.nstages + 1) * 8 + 8 + 15) & ~size_t(15)));
   float4* part_s = prm_s + T32_NL;                                // [2][128] per-row partial sums of the two column halves
   float4* stat_s = part_s + 2 * T32_BM;                           // [4 ranks][128] the cluster's sums
-  float* res_s = reinterpret_cast<float*>(tiles);                 // [128][RES_LD] residual tile (aliases the drained stages)
-  // output staging tile: behind the residual tile (highway, 128 columns) or at the start (plain LayerNorm, 256 columns)
-  float* out_s = reinterpret_cast<float*>(tiles) + (a.epi == EPI_HIGHWAY ? T32_BM * RES_LD : 0);
+  float* out_s = reinterpret_cast<float*>(tiles);                 // output staging tile (aliases the drained pipeline stages)
 
+  const long long t_begin = clock64();
+  long long* prof = a.prof ? a.prof + (size_t)blockIdx.x * 8 : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = a.cluster_n > 1 ? cluster_rank() : 0u;
   const int tile = blockIdx.x / a.cluster_n;
@@ -220,6 +221,8 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (a.cluster_n > 1) cluster_sync_all();     // every CTA of the cluster is running before a DSMEM store targets it
+  const long long t_setup = clock64();
+  if (prof && threadIdx.x == 0) prof[0] = t_setup - t_begin;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -250,10 +253,13 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
       const uint32_t idesc = umma_idesc_tf32();
       const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)T32_NL;
       bool ok = true;
+      long long wait_cycles = 0;
       for (int kb = 0; kb < nk && ok; ++kb) {
         const int st = kb % a.nstages;
         const uint32_t ph = (uint32_t)(kb / a.nstages) & 1u;
+        const long long tw = prof ? clock64() : 0;
         ok = mbar_wait(full_bar + st, ph, err);
+        if (prof) wait_cycles += clock64() - tw;
         if (!ok) break;
         tc_fence_after();
         const uint32_t Ah = smem_u32(tiles + (size_t)st * STAGE_BYTES);
@@ -272,38 +278,40 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
         umma_commit(empty_bar + st);          // frees the smem slot once these MMAs retire
       }
       umma_commit(accum_bar);                 // accumulators complete
+      if (prof) { prof[1] = wait_cycles; prof[2] = clock64() - t_setup; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> LN / gate -> smem -> global =====================
     // 8 warps: warp (q, hsel) reads TMEM lane quadrant q (rows q*32 ..) and column half hsel of each 128-column block.
     const int q = warp & 3, hsel = (warp - 4) >> 2, ew = warp - 4;
     const int row = q * 32 + lane;
-    const bool got = mbar_wait(accum_bar, 0u, err);
-    tc_fence_after();
-    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-
     auto row_coords = [&](int r, int& bb, int& tt) {
       const int u = r / a.rows_per_utt;
       bb = b0 + u;
       tt = t0 + (r - u * a.rows_per_utt);
-      return got && bb < a.B && tt < a.T;
+      return bb < a.B && tt < a.T;
     };
-
+    // highway: my row's residual (my 64 channels, hi + lo) -> registers while the mainloop runs
+    float xres[64];
     if (hwy) {
-      // the residual rows (my 128-channel slice, hi + lo) -> smem, coalesced; the pipeline stages are drained
-      for (int i = 0; i < T32_BM / 8; ++i) {
-        const int r = ew * (T32_BM / 8) + i;
-        int bb, tt;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_coords(r, bb, tt)) {
-          const long off = (long)bb * a.x_sb + (long)tt * a.x_st + w0 + lane * 4;
-          const float4 h = *reinterpret_cast<const float4*>(a.Xh + off);
-          const float4 l = *reinterpret_cast<const float4*>(a.Xl + off);
-          v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
-        }
-        *reinterpret_cast<float4*>(res_s + (size_t)r * RES_LD + lane * 4) = v;
+      int bb, tt;
+      const bool ok = row_coords(row, bb, tt);
+      const long off = ok ? (long)bb * a.x_sb + (long)tt * a.x_st + w0 + hsel * 64 : 0;
+      float4 h4[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h4[i] = ok ? __ldg(reinterpret_cast<const float4*>(a.Xh + off) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 l4 = ok ? __ldg(reinterpret_cast<const float4*>(a.Xl + off) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xres[4 * i] = h4[i].x + l4.x; xres[4 * i + 1] = h4[i].y + l4.y; xres[4 * i + 2] = h4[i].z + l4.z; xres[4 * i + 3] = h4[i].w + l4.w;
       }
     }
+    const bool got = mbar_wait(accum_bar, 0u, err);
+    tc_fence_after();
+    const bool ptime = prof != nullptr && warp == 4 && lane == 0;
+    long long t_acc = clock64(), t_p1 = t_acc, t_ex = t_acc, t_p2 = t_acc;
+    if (ptime) prof[3] = t_acc - t_setup;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
 
     uint32_t r0[16], r1[16], r2[16], r3[16];
     float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
@@ -335,8 +343,9 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
         }
       }
     }
+    t_p1 = clock64();
     part_s[hsel * T32_BM + row] = make_float4(s1, q1, s2, q2);
-    epi_bar_sync();                             // also: the residual tile is complete
+    epi_bar_sync();
     {
       const float4 lo4 = part_s[row], hi4 = part_s[T32_BM + row];        // fixed order: both halves get identical sums
       s1 = lo4.x + hi4.x; q1 = lo4.y + hi4.y; s2 = lo4.z + hi4.z; q2 = lo4.w + hi4.w;
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
         s1 += v.x; q1 += v.y; s2 += v.z; q2 += v.w;
       }
     }
+    t_ex = clock64();
     const float inv_n = 1.0f / (float)a.n_real;
     const float m1 = s1 * inv_n, m2 = s2 * inv_n;
     const float rs1 = 1.0f / sqrtf(fmaxf(q1 * inv_n - m1 * m1, 0.f) + 1e-5f);
@@ -363,7 +373,10 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
     // pass 2: normalise (+ gate with the residual), into the staging tile
     const int o_ld = hwy ? RES_LD : OUT_LD;
     const bool relu = a.epi == EPI_LN_RELU;
-    for (int c = c_lo; c < c_lo + c_n; c += 16) {
+#pragma unroll
+    for (int cc = 0; cc < 128; cc += 16) {
+      if (cc >= c_n) break;
+      const int c = c_lo + cc;
       tmem_ld16_issue(tq + c, r0);
       tmem_ld16_issue(tq + T32_NL + c, r1);
       if (hwy) {
@@ -376,7 +389,6 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
       if (hwy) {
         tmem_wait16(r2);
         tmem_wait16(r3);
-        const float* xr = res_s + (size_t)row * RES_LD + c;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float4 p1 = prm_s[c + i], p2 = prm_s[128 + c + i];
@@ -384,8 +396,9 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
           const float x2 = (__uint_as_float(r2[i]) + __uint_as_float(r3[i])) + p2.x;
           const float h1 = (x1 - m1) * rs1 * p1.y + p1.z;
           const float h2 = (x2 - m2) * rs2 * p2.y + p2.z;
-          const float g = sigmoid_acc(h1);
-          o[i] = g * h2 + (1.0f - g) * xr[i];
+          const float g = sigmoid_fast(h1);
+          const float xr = xres[(cc & 63) + i];
+          o[i] = g * h2 + (1.0f - g) * xr;
         }
       } else {
 #pragma unroll
@@ -400,26 +413,44 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
+    t_p2 = clock64();
     epi_bar_sync();
     // coalesced copy-out of my CTA's columns: highway [w0, w0 + 128); plain [w0, w0 + 128) and [w1, w1 + 128)
     const int f4_per_row = hwy ? 32 : 64;
-    for (int i = 0; i < T32_BM / 8; ++i) {
-      const int r = ew * (T32_BM / 8) + i;
-      int bb, tt;
-      if (!row_coords(r, bb, tt)) continue;
-      const long yoff = (long)bb * a.y_sb + (long)tt * a.y_st;
-      for (int f = lane; f < f4_per_row; f += 32) {
-        const float4 v = *reinterpret_cast<const float4*>(out_s + (size_t)r * o_ld + f * 4);
-        const int gc = f < 32 ? w0 + f * 4 : w1 + (f - 32) * 4;
-        if (a.Yl != nullptr) {
-          float4 hi, lo;
-          split4(v, hi, lo);
-          *reinterpret_cast<float4*>(a.Yh + yoff + gc) = hi;
-          *reinterpret_cast<float4*>(a.Yl + yoff + gc) = lo;
-        } else {
-          *reinterpret_cast<float4*>(a.Yh + yoff + gc) = v;
+    for (int i = 0; i < T32_BM / 8; i += 4) {
+      float4 v[4][2];
+      long yoff[4];
+      bool okr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = ew * (T32_BM / 8) + i + u;
+        int bb, tt;
+        okr[u] = row_coords(r, bb, tt) && got;
+        yoff[u] = (long)bb * a.y_sb + (long)tt * a.y_st;
+        v[u][0] = *reinterpret_cast<const float4*>(out_s + (size_t)r * o_ld + lane * 4);
+        if (!hwy) v[u][1] = *reinterpret_cast<const float4*>(out_s + (size_t)r * o_ld + (lane + 32) * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!okr[u]) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h * 32 >= f4_per_row) break;
+          const int gc = h == 0 ? w0 + lane * 4 : w1 + lane * 4;
+          if (a.Yl != nullptr) {
+            float4 hi, lo;
+            split4(v[u][h], hi, lo);
+            *reinterpret_cast<float4*>(a.Yh + yoff[u] + gc) = hi;
+            *reinterpret_cast<float4*>(a.Yl + yoff[u] + gc) = lo;
+          } else {
+            *reinterpret_cast<float4*>(a.Yh + yoff[u] + gc) = v[u][h];
+          }
         }
       }
+    }
+    if (ptime) {
+      const long long t_end = clock64();
+      prof[4] = t_p1 - t_acc; prof[5] = t_ex - t_p1; prof[6] = t_p2 - t_ex; prof[7] = t_end - t_begin;
     }
   }
 
@@ -491,6 +522,16 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+long long* tf32_prof_buf() {       // SSV_TC_PROF=1: [4096 CTAs][8] cycle counters of the last launch
+  static long long* buf = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (getenv("SSV_TC_PROF") && cudaMalloc((void**)&buf, sizeof(long long) * 4096 * 8) != cudaSuccess) buf = nullptr;
+  }
+  return buf;
+}
+
 int* tf32_err_flag() {
   static int* flag = nullptr;
   if (!flag) {
@@ -542,16 +583,13 @@ int tf32_check_error() {
   return kOk;
 }
 
-int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
-                float* Yh, float* Yl, int y_ld, cudaStream_t s) {
+int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
+                 float* Yh, float* Yl, int y_ld, Tf32Launch* out) {
   SSV_CHECK(L.cin_p % T32_BK == 0 && x_ld >= L.cin_p && x_ld % 4 == 0, "conv_tf32: bad K padding (cin_p %d, ld %d)", L.cin_p, x_ld);
   SSV_CHECK(epi == EPI_HIGHWAY || epi == EPI_LN || epi == EPI_LN_RELU, "conv_tf32: epilogue %d not built", epi);
   SSV_CHECK(L.cluster_n == 1 || L.cluster_n == 2 || L.cluster_n == 4, "conv_tf32: cluster_n must be 1, 2 or 4");
   SSV_CHECK(y_ld % 4 == 0, "conv_tf32: output row stride must be a multiple of 4");
-  int* err = tf32_err_flag();
-  SSV_CHECK(err != nullptr, "conv_tf32: cannot allocate the error flag");
-
-  ConvTf32Args a;
+  ConvTf32Args& a = out->args;
   memset(&a, 0, sizeof(a));
   a.T = T; a.B = B;
   a.rows_per_utt = T <= 64 ? 64 : T32_BM;
@@ -584,15 +622,23 @@ int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* X
   a.Xh = Xh; a.Xl = Xl; a.x_sb = (long)T * x_ld; a.x_st = x_ld;
   a.Yh = Yh; a.Yl = Yl; a.y_sb = (long)T * y_ld; a.y_st = y_ld;
   a.nstages = 4;
+  out->n_ctas = n_tiles * L.cluster_n;
+  out->cluster_n = L.cluster_n;
+  return kOk;
+}
+
+int tf32_run(const Tf32Launch& L, cudaStream_t s) {
+  int* err = tf32_err_flag();
+  SSV_CHECK(err != nullptr, "conv_tf32: cannot allocate the error flag");
   const size_t fixed = 1024 /*align*/ + 256 /*barriers, tmem slot*/ + (size_t)T32_NL * 16 + 2 * T32_BM * 16 + 4 * T32_BM * 16;
-  const size_t smem = fixed + (size_t)a.nstages * STAGE_BYTES;
+  const size_t smem = fixed + (size_t)L.args.nstages * STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
     SSV_CUDA(cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(n_tiles * L.cluster_n));
+  cfg.gridDim = dim3((unsigned)L.n_ctas);
   cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -603,9 +649,40 @@ int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* X
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SSV_CUDA(cudaLaunchKernelEx(&cfg, conv_tf32x3_kernel, a, err));
+  long long* prof = tf32_prof_buf();
+  const int ncta = L.n_ctas;
+  if (prof && ncta <= 4096) {
+    Tf32Launch P = L;
+    P.args.prof = prof;
+    SSV_CUDA(cudaMemsetAsync(prof, 0, sizeof(long long) * 4096 * 8, s));
+    SSV_CUDA(cudaLaunchKernelEx(&cfg, conv_tf32x3_kernel, P.args, err));
+    ++g_launches;
+    SSV_CUDA(cudaStreamSynchronize(s));
+    std::vector<long long> h((size_t)ncta * 8);
+    SSV_CUDA(cudaMemcpy(h.data(), prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    const char* nm[8] = {"setup", "mma-wait-full", "mma-loop", "epi-wait-accum", "pass1", "exchange", "pass2", "total"};
+    fprintf(stderr, "[tf32 prof] grid=%d cluster=%d K=%d epi=%d T=%d B=%d :", ncta, L.cluster_n, L.args.ktaps * L.args.kb_per_tap * T32_BK,
+            L.args.epi, L.args.T, L.args.B);
+    for (int i = 0; i < 8; ++i) {
+      double sum = 0;
+      int cnt = 0;
+      for (int c = 0; c < ncta; ++c)
+        if (h[(size_t)c * 8 + i] != 0) { sum += (double)h[(size_t)c * 8 + i]; ++cnt; }
+      fprintf(stderr, " %s=%.0f", nm[i], cnt ? sum / cnt : 0.0);
+    }
+    fprintf(stderr, "\n");
+    return kOk;
+  }
+  SSV_CUDA(cudaLaunchKernelEx(&cfg, conv_tf32x3_kernel, L.args, err));
   ++g_launches;
   return kOk;
+}
+
+int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
+                float* Yh, float* Yl, int y_ld, cudaStream_t s) {
+  Tf32Launch P;
+  SSV_TRY(tf32_prepare(L, epi, dil, causal, Xh, Xl, x_ld, T, B, Yh, Yl, y_ld, &P));
+  return tf32_run(P, s);
 }
 
 }  // namespace ssv

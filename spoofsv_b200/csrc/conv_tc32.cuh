@@ -32,6 +32,7 @@ struct alignas(64) ConvTf32Args {
   float* Yh; float* Yl;     // output, channels-last: the TF32 split (hi, lo) for the next layer's operands, or,
                             // with Yl == nullptr, the plain fp32 value in Yh
   long y_sb, y_st;
+  long long* prof;          // optional per-CTA cycle counters (SSV_TC_PROF=1)
 };
 
 // One layer packed for this path: weights [rows][taps * cin_p] fp32 (K contiguous, tap-major) split into hi / lo.
@@ -49,8 +50,17 @@ void tf32_shape_plain(Tf32Layer* L, int n);       // n in {256, 512}
 int tf32_pack_weights(const float* w /*[n][cin][k]*/, int n, int cin, int k, int cin_p, float* hi, float* lo, cudaStream_t s);
 // x (fp32, any layout, n elements) -> hi = tf32(x), lo = tf32(x - hi)
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t s);
+// A launch with its TMA descriptors encoded: built once per (layer, buffers, shape) and replayed (encoding four tensor
+// maps per launch on the host cost more than the kernel's own prologue: 23 us per layer against 60 us of GPU time).
+struct Tf32Launch {
+  ConvTf32Args args;
+  int n_ctas = 0, cluster_n = 1;
+};
+int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
+                 float* Yh, float* Yl, int y_ld, Tf32Launch* out);
+int tf32_run(const Tf32Launch& L, cudaStream_t s);
 int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
-                float* Yh, float* Yl, int y_ld, cudaStream_t s);
+                float* Yh, float* Yl, int y_ld, cudaStream_t s);    // prepare + run
 int tf32_check_error();
 
 }  // namespace ssv
