@@ -363,7 +363,10 @@ def main():
     ids_d = torch.from_numpy(ids_np)[:, None, :].cuda()
     spk_d = torch.from_numpy(spk_np)[:, :, None].cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    syn = Synthesizer(m1, m2, ssrn_precision=args.ssrn_precision)
+    # end-to-end arm: the spectrogram leaves the device in the SSRN arm's own operand precision (bf16 arm: bf16 host
+    # buffer, half the D2H bytes; fp32 arm: fp32); the fp32-output variant of the bf16 arm is reported beside it
+    lin_dtype = "bf16" if args.ssrn_precision == "bf16" else "fp32"
+    syn = Synthesizer(m1, m2, ssrn_precision=args.ssrn_precision, lin_dtype=lin_dtype)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def device_step(parts=None):
@@ -446,6 +449,26 @@ def main():
         e2e_pipe = time.perf_counter() - t0
         barrier()
         e2e_total = max_over_ranks(e2e_pipe)
+        d2h_bytes, h2d_bytes = int(syn.d2h_bytes), int(syn.h2d_bytes)
+        e2e_fp32_total = None
+        if lin_dtype != "fp32":                              # the same loop with the reference's fp32 host result
+            syn32 = Synthesizer(m1, m2, ssrn_precision=args.ssrn_precision, lin_dtype="fp32")
+            for _ in range(2):
+                syn32.synthesize_host(ids_np, spk_np, T)
+            barrier()
+            t0 = time.perf_counter()
+            pend = None
+            for _ in range(args.steps):
+                cur = syn32.submit(ids_np, spk_np, T)
+                if pend is not None:
+                    syn32.collect(pend)
+                pend = cur
+            syn32.collect(pend)
+            e2e_fp32_total = max_over_ranks(time.perf_counter() - t0)
+            d2h_fp32 = int(syn32.d2h_bytes)
+            for _ in range(2):
+                syn.synthesize_host(ids_np, spk_np, T)       # back to the headline's host buffers
+            barrier()
     finally:
         sampler.__exit__(None, None, None)
     clocks = clk.summary()
@@ -491,55 +514,72 @@ def main():
         syn.synthesize_host(ids_np, spk_np, T)          # back to the headline shape (re-creates the staging buffers)
     extra["decode_batch1"] = {"ms": best1, "us_per_frame": 1e3 * best1 / T, "frames_per_s": T / (best1 * 1e-3),
                               "hbm_roofline_frac": T * (DECODE_WEIGHT_BYTES + DECODE_STATE_BYTES_PER_UTT) / (best1 * 1e-3) / 1e9 / measured_peaks()["hbm"]}
-    # BASELINE config 5 shape (B = 32, N = 64, T = 217), generator only: forward + backward of the Text2Mel train branch
-    # (FP32; highway convs in the library's kernels both ways, the small layers in torch ops), rank 0 only
-    if rank == 0:
-        try:
-            m1.train()
-            Bt, Nt = 32, 64
-            ids_t = torch.randint(2, 34, (Bt, 1, Nt), device="cuda")
-            spk_t = spk_d[:Bt] if spk_d.shape[0] >= Bt else spk_d[:1].expand(Bt, -1, -1).contiguous()
-            mel_t, tgt_t = torch.rand((Bt, 80, T), device="cuda"), torch.rand((Bt, 80, T), device="cuda")
+    # BASELINE config 5 (B = 32 global, N = 64, T = 217): the adversarial training step of Text2Mel, outside the headline's
+    # timed region.  FP32 (highway convs forward / backward in the library's kernels, the small layers in torch ops).
+    # Under torchrun the global batch of 32 is sharded over the ranks (strong scaling) and the generator's gradients
+    # (24,073,584 fp32 elements) are all-reduced over NCCL from gradient hooks, overlapped with the backward pass; the
+    # discriminator's 119,233 after its two backward passes.  Times are the max over ranks.
+    try:
+        from spoofsv_b200 import train as TR
+        m1.train()
+        Bg, Nt = 32, 64
+        sl = TR.shard_batch(Bg, world, rank)
+        gen = torch.Generator(device="cuda").manual_seed(1234)           # the same global batch on every rank
+        ids_t = torch.randint(2, 34, (Bg, 1, Nt), device="cuda", generator=gen)[sl]
+        spk_g = spk_d[:Bg] if spk_d.shape[0] >= Bg else spk_d[:1].expand(Bg, -1, -1).contiguous()
+        spk_t = spk_g[sl].contiguous()
+        mel_t = torch.rand((Bg, 80, T), device="cuda", generator=gen)[sl].contiguous()
+        tgt_t = torch.rand((Bg, 80, T), device="cuda", generator=gen)[sl].contiguous()
+        mel_g = (torch.rand((Bg, 80, T), device="cuda", generator=gen) * 0.9 + 0.05)[sl].contiguous()
 
+        def timed(fn, n=3):
+            for _ in range(2):
+                fn()
+            barrier()
+            ea, eb = ev(), ev()
+            ea.record()
+            for _ in range(n):
+                fn()
+            eb.record(); torch.cuda.synchronize()
+            return max_over_ranks(ea.elapsed_time(eb) / n)
+
+        if sl.stop > sl.start:
             def train_step():
                 m1.zero_grad(set_to_none=True)
                 Yt, _ = m1(mel_t, ids_t, spk_t)
                 (Yt - tgt_t).abs().mean().backward()
 
-            def timed(fn, n=3):
-                for _ in range(2):
-                    fn()
-                ea, eb = ev(), ev()
-                ea.record()
-                for _ in range(n):
-                    fn()
-                eb.record(); torch.cuda.synchronize()
-                return ea.elapsed_time(eb) / n
+            if world == 1:
+                extra["config5_generator_fwd_bwd_ms"] = timed(train_step)
 
-            extra["config5_generator_fwd_bwd_ms"] = timed(train_step)
-            # whole iterations of train/adversarial_wasserstein_gp.py:269-316 (losses, discriminator, backward; the
-            # optimizer step is left out so that the benchmark model keeps its weights)
-            if world > 1:
-                raise StopIteration                    # the iteration helpers all-reduce: only timed in a 1-process run
-            from spoofsv_b200 import train as TR
-
-            class _NoStep:
+            class _NoStep:        # the optimizer step is left out so that the benchmark model keeps its weights
                 def __init__(self, params): self.params = list(params)
                 def zero_grad(self, set_to_none=True):
                     for p in self.params: p.grad = None
                 def step(self): pass
 
+            torch.manual_seed(4321)                                     # identical discriminator on every rank
             disc = TR.melDisc(80, 128).cuda().train()
             gaw = TR.guided_attention_mat(186, 325, device="cuda")
-            mel_g = torch.rand((Bt, 80, T), device="cuda") * 0.9 + 0.05
             og, od = _NoStep(m1.parameters()), _NoStep(disc.parameters())
-            extra["config5_g_iteration_ms"] = timed(lambda: TR.generator_step(m1, disc, og, mel_g, ids_t, spk_t, gaw, {"LAMBDA": 10}))
-            extra["config5_d_iteration_ms"] = timed(lambda: TR.discriminator_step(m1, disc, od, mel_g, ids_t, spk_t, {"LAMBDA": 10}))
-        except StopIteration:
-            pass
-        finally:
-            m1.eval()
-            m1.zero_grad(set_to_none=True)
+            sw = TR.shard_weight(Bg, world, rank)
+            red = TR.OverlappedGradReducer(m1.parameters()) if world > 1 else None
+            g_ms = timed(lambda: TR.generator_step(m1, disc, og, mel_g, ids_t, spk_t, gaw, {"LAMBDA": 10}, shard_weight=sw, reducer=red))
+            d_ms = timed(lambda: TR.discriminator_step(m1, disc, od, mel_g, ids_t, spk_t, {"LAMBDA": 10}, shard_weight=sw))
+            if red is not None:
+                g_post_ms = timed(lambda: TR.generator_step(m1, disc, og, mel_g, ids_t, spk_t, gaw, {"LAMBDA": 10}, shard_weight=sw))
+                red.close()
+                extra["config5_g_iteration_allreduce_after_backward_ms"] = g_post_ms
+            extra["config5_g_iteration_ms"] = g_ms
+            extra["config5_d_iteration_ms"] = d_ms
+            extra["config5"] = {"global_batch": Bg, "per_rank_batch": sl.stop - sl.start, "text_len": Nt, "frames": T, "dtype": "fp32",
+                                "allreduce": "NCCL, 8 MB buckets launched from gradient hooks during backward" if world > 1 else "none (1 rank)",
+                                "g_allreduce_elements": 24_073_584 if world > 1 else 0, "d_allreduce_elements": 119_233 if world > 1 else 0}
+    except Exception as exc:           # context only: never lose the headline line over it
+        extra["config5_error"] = f"{type(exc).__name__}: {exc}"
+    finally:
+        m1.eval()
+        m1.zero_grad(set_to_none=True)
 
     peaks = measured_peaks()
     dec_bytes = T * (DECODE_WEIGHT_BYTES + B * DECODE_STATE_BYTES_PER_UTT)
@@ -556,8 +596,11 @@ def main():
                   + (" + fp32 SSRN (FFMA)" if args.ssrn_precision == "fp32" else " + bf16 SSRN (tcgen05, fp32 accumulate)")),
         "data": "synthetic",
         "config": config_dict(args, B),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(syn.h2d_bytes),
-                "d2h_bytes_per_step": int(syn.d2h_bytes), "ms_per_step": 1e3 * e2e_total / args.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e2e_total / args.steps,
+                "d2h_dtype": lin_dtype + " linear spectrogram (B, 513, 4T) + int64 alignment trajectory",
+                **({"fp32_out_value": frames_total / e2e_fp32_total, "fp32_out_ms_per_step": 1e3 * e2e_fp32_total / args.steps,
+                    "fp32_out_d2h_bytes_per_step": d2h_fp32} if e2e_fp32_total else {}),
                 "api": "ssv_synthesize_host_submit / _wait (C ABI, pinned host buffers, two batches in flight)",
                 "sync_value": frames_total / e2e_sync_total, "sync_ms_per_step": 1e3 * e2e_sync_total / args.steps,
                 "sync_api": "ssv_synthesize_host (one batch at a time)"},
@@ -593,6 +636,8 @@ def main():
         cores = os.cpu_count() or 1
         nb = max(1, min(args.cpu_sample, B))
         got = syn.synthesize_host(ids_np, spk_np, T)["lin"][:nb]
+        if not isinstance(got, np.ndarray):
+            got = got.float().numpy()
         olin, cb = None, None
         if build_ref.available():
             # the unmodified reference module on the host cores, in a child process with the GPUs hidden (the module

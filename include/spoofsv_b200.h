@@ -137,6 +137,11 @@ int ssv_synthesize_host_submit(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* s, con
                                float* mel_host, float* A_host, int64_t* pma_traj_host,
                                int t2m_precision, int ssrn_precision, void* stream, int* ticket);
 int ssv_synthesize_host_wait(ssv_decoder* d, int ticket);
+/* Element type of `lin_host` for the calls above: 0 = fp32 (default, what the reference's .cpu() returns), 1 = bf16
+ * (the same (B, O, 4*n_frames) elements as 2-byte bfloat16: half the device->host bytes -- the copy is what limits
+ * the end-to-end rate when eight GPUs write into one host; meant for the BF16 SSRN arm, whose values carry bf16
+ * operand rounding already). */
+int ssv_decoder_set_lin_output(ssv_decoder* d, int bf16);
 
 /* ---- training step, first building block (next row of the scope table) ---------------------
  * Backward of one highwayConv, FP32: what autograd computes for highwayConv.forward

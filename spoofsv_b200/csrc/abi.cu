@@ -348,6 +348,8 @@ struct ssv_decoder {
   int64_t* h_textid = nullptr;
   float *h_spk = nullptr, *h_K = nullptr, *h_V = nullptr, *h_Y = nullptr, *h_A = nullptr;
   float* h_lin[2] = {nullptr, nullptr};   // one per in-flight batch (the D2H of batch i overlaps batch i + 1)
+  __nv_bfloat16* h_lin16[2] = {nullptr, nullptr};   // bf16 copy for the half-size D2H (ssv_decoder_set_lin_output)
+  int lin_out_bf16 = 0;
   long long* h_traj = nullptr;
   cudaStream_t copy_stream = nullptr;     // D2H of finished SSRN chunks
   cudaEvent_t copy_ev[2] = {nullptr, nullptr}, done_ev[2] = {nullptr, nullptr}, lin_ev[2] = {nullptr, nullptr};
@@ -1042,6 +1044,14 @@ int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_
   return kOk;
 }
 
+int ssv_decoder_set_lin_output(ssv_decoder* d, int bf16) {
+  SSV_CHECK(d, "decoder_set_lin_output: null decoder");
+  if (d->lin_out_bf16 == (bf16 ? 1 : 0)) return kOk;
+  SSV_CHECK(!d->inflight[0] && !d->inflight[1], "decoder_set_lin_output: a batch is in flight");
+  d->lin_out_bf16 = bf16 ? 1 : 0;
+  return kOk;
+}
+
 int ssv_text2mel_check(ssv_text2mel* m, void* stream) {
   SSV_CHECK(m, "text2mel_check: null model");
   SSV_CUDA(cudaStreamSynchronize(as_stream(stream)));
@@ -1281,6 +1291,7 @@ static int synth_enqueue(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const in
     SSV_TRY(d->host_arena.alloc<float>((size_t)B * N * T, &d->h_A));
     SSV_TRY(d->host_arena.alloc<long long>((size_t)T * B, &d->h_traj));
     for (int i = 0; i < 2; ++i) SSV_TRY(d->host_arena.alloc<float>((size_t)B * O * 4 * T, &d->h_lin[i]));
+    for (int i = 0; i < 2; ++i) SSV_TRY(d->host_arena.alloc<__nv_bfloat16>((size_t)B * O * 4 * T, &d->h_lin16[i]));
     d->hs_key = key;
   }
   if (d->copy_stream == nullptr) {
@@ -1312,10 +1323,16 @@ static int synth_enqueue(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const in
       const int nb = B - b0 < chunk ? B - b0 : chunk;
       SSV_TRY(ssv_ssrn_fwd(sr, d->h_Y + (size_t)b0 * F * T, (long)F * T, T, 1, nb, T, lin_dev + b0 * lin_per_utt,
                            ssrn_precision, s));
+      if (d->lin_out_bf16)      // half-size result: the spectrogram leaves the device as bf16 (ssv_decoder_set_lin_output)
+        SSV_TRY(launch_cast_f32_to_bf16(lin_dev + b0 * lin_per_utt, d->h_lin16[slot] + b0 * lin_per_utt, nb * lin_per_utt, s));
       SSV_CUDA(cudaEventRecord(d->copy_ev[ci & 1], s));
       SSV_CUDA(cudaStreamWaitEvent(d->copy_stream, d->copy_ev[ci & 1], 0));
-      SSV_CUDA(cudaMemcpyAsync(lin_host + b0 * lin_per_utt, lin_dev + b0 * lin_per_utt, sizeof(float) * nb * lin_per_utt,
-                               cudaMemcpyDeviceToHost, d->copy_stream));
+      if (d->lin_out_bf16)
+        SSV_CUDA(cudaMemcpyAsync(reinterpret_cast<__nv_bfloat16*>(lin_host) + b0 * lin_per_utt, d->h_lin16[slot] + b0 * lin_per_utt,
+                                 sizeof(__nv_bfloat16) * nb * lin_per_utt, cudaMemcpyDeviceToHost, d->copy_stream));
+      else
+        SSV_CUDA(cudaMemcpyAsync(lin_host + b0 * lin_per_utt, lin_dev + b0 * lin_per_utt, sizeof(float) * nb * lin_per_utt,
+                                 cudaMemcpyDeviceToHost, d->copy_stream));
     }
     SSV_CUDA(cudaEventRecord(d->lin_ev[slot], d->copy_stream));
   }

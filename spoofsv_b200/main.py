@@ -191,6 +191,8 @@ def adversarial_train(train_step: str, train_pattern: str, cfg: dict, spec_dir: 
         batch_size=bs, shuffle=shuffle, num_workers=0, collate_fn=collate, generator=torch.Generator().manual_seed(1234 + epoch))
     train_loader, val_loader = mk_loader("train", cfg["BATCH_SIZE"], True), mk_loader("validate", 8, False)
     gaw = TR.guided_attention_mat(cfg["MAX_TEXT_LEN"], cfg["MAX_FRAME_NUM"], device="cuda")
+    # generator iterations of Text2Mel: bucket allreduces launched from gradient hooks, overlapped with backward
+    reducer = TR.OverlappedGradReducer(model.parameters()) if (world > 1 and text2mel) else None
     done = False
     t_start = time.perf_counter()
     while epoch < cfg["MAX_EPOCHS"] and not done:
@@ -206,7 +208,7 @@ def adversarial_train(train_step: str, train_pattern: str, cfg: dict, spec_dir: 
             if text2mel:
                 ids, spk = sp["data_1"][sl].cuda(), sp["data_2"][sl].cuda()
                 if target == "G":
-                    t = TR.generator_step(model, disc, opt_syn, a, ids, spk, gaw, cfg, shard_weight=sw)
+                    t = TR.generator_step(model, disc, opt_syn, a, ids, spk, gaw, cfg, shard_weight=sw, reducer=reducer)
                 else:
                     t = TR.discriminator_step(model, disc, opt_disc, a, ids, spk, cfg, shard_weight=sw)
             else:

@@ -46,9 +46,14 @@ def plan_batches(units: Sequence[Unit], batch: int) -> List[List[Unit]]:
 class Synthesizer:
     """Text2Mel + SSRN on one GPU through the C ABI's host-buffer entry point."""
 
-    def __init__(self, text2mel: melSyn, ssrn: SSRN, ssrn_precision: str = "fp32"):
+    def __init__(self, text2mel: melSyn, ssrn: SSRN, ssrn_precision: str = "fp32", lin_dtype: str = "fp32"):
+        """lin_dtype: element type of the returned linear spectrogram, "fp32" (the reference's) or "bf16" (half the
+        device->host bytes; `out["lin"]` is then a torch.bfloat16 CPU tensor instead of a numpy array)."""
+        if lin_dtype not in ("fp32", "bf16"):
+            raise ValueError("lin_dtype must be 'fp32' or 'bf16'")
         self.m1, self.m2 = text2mel, ssrn
         self.ssrn_precision = ssrn_precision
+        self.lin_dtype = lin_dtype
         self._pinned: Dict[str, torch.Tensor] = {}
         self._next_buf = 0
 
@@ -89,11 +94,13 @@ class Synthesizer:
         h_spk = self._pin(f"spk{k}", (B, spk.shape[1]), torch.float32)
         h_ids.numpy()[...] = ids
         h_spk.numpy()[...] = spk
-        h_lin = self._pin(f"lin{k}", (B, O, 4 * T), torch.float32)
+        lin16 = self.lin_dtype == "bf16"
+        h_lin = self._pin(f"lin{k}", (B, O, 4 * T), torch.bfloat16 if lin16 else torch.float32)
         h_traj = self._pin(f"traj{k}", (T, B), torch.int64)
         h_mel = self._pin(f"mel{k}", (B, F, T), torch.float32) if want_mel else None
         h_att = self._pin(f"att{k}", (B, N, T), torch.float32) if want_att else None
         dec = self.m1._decoder(B, N, T)
+        _lib.check(_lib.load().ssv_decoder_set_lin_output(dec, int(lin16)))      # no-op unless it changes
         ptr = lambda t: None if t is None else t.data_ptr()
         ticket = C.c_int(-1)
         args = (self.m1._native(), dec, self.m2._native(), h_ids.data_ptr(), h_spk.data_ptr(), B, N, T,
@@ -104,13 +111,13 @@ class Synthesizer:
         else:
             _lib.check(_lib.load().ssv_synthesize_host_submit(*args, C.byref(ticket)))
         self.m1._state = None       # the decoder's buffers now belong to the C side
-        out = {"lin": h_lin.numpy(), "traj": h_traj.numpy()}
+        out = {"lin": h_lin if lin16 else h_lin.numpy(), "traj": h_traj.numpy()}
         if want_mel:
             out["mel"] = h_mel.numpy()
         if want_att:
             out["att"] = h_att.numpy()
         self.h2d_bytes = ids.nbytes + spk.nbytes
-        self.d2h_bytes = h_lin.numel() * 4 + h_traj.numel() * 8 + (h_mel.numel() * 4 if want_mel else 0) + (
+        self.d2h_bytes = h_lin.numel() * h_lin.element_size() + h_traj.numel() * 8 + (h_mel.numel() * 4 if want_mel else 0) + (
             h_att.numel() * 4 if want_att else 0)
         return (dec, ticket.value, out)
 

@@ -79,6 +79,87 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_mb: float =
     return total
 
 
+class OverlappedGradReducer:
+    """Gradient allreduce overlapped with the backward pass (replaces the reduce-add onto GPU 0 that `nn.DataParallel`
+    performs after backward, train/adversarial_wasserstein_gp.py:183-196).
+
+    The parameters are packed, in REVERSE registration order (the order their gradients become final during backward:
+    AudioDec, AudioEnc, then TextEnc, whose 68 MB finish last), into buckets of about `bucket_mb`; a
+    post-accumulate-grad hook counts the finished gradients of a bucket and launches its NCCL allreduce the moment the
+    last one lands, so the collective of layer k runs under the backward kernels of the layers before it.  `finish()`
+    after `backward()` launches whatever never became ready (parameters without a gradient contribute zeros), waits,
+    averages and scatters the sums back into `.grad`.  One backward pass per step (the generator iteration); the
+    discriminator iteration calls backward twice and keeps `allreduce_gradients`."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 8.0, group=None):
+        self.group = group
+        self.params = [p for p in params if p.requires_grad]
+        order = list(reversed(self.params))
+        limit = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.buckets = [[order[i] for i in idxs] for idxs in plan_buckets([p.numel() for p in order], limit)]
+        self.bucket_of = {id(p): bi for bi, ps in enumerate(self.buckets) for p in ps}
+        self.ready = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
+        self.inflight = []
+        self.enabled = False
+        self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+
+    def _active(self) -> bool:
+        return self.enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _hook(self, p):
+        if not self._active():
+            return
+        b = self.bucket_of[id(p)]
+        self.ready[b] += 1
+        if self.ready[b] == len(self.buckets[b]) and not self.launched[b]:
+            self._launch(b)
+
+    def _launch(self, b: int):
+        ps = self.buckets[b]
+        for p in ps:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.inflight.append((work, flat, ps))
+        self.launched[b] = True
+
+    def begin(self):
+        """Arm the hooks for the backward pass that follows."""
+        self.ready = [0] * len(self.buckets)
+        self.launched = [False] * len(self.buckets)
+        self.inflight = []
+        self.enabled = True
+
+    def finish(self, average: bool = True) -> int:
+        """After backward(): every rank ends with the (averaged) sum of the gradients.  Returns the elements reduced."""
+        total = 0
+        if self._active():
+            world = dist.get_world_size(self.group)
+            for b in range(len(self.buckets)):
+                if not self.launched[b]:
+                    self._launch(b)
+            for work, flat, ps in self.inflight:
+                work.wait()
+                if average:
+                    flat.div_(world)
+                off = 0
+                for p in ps:
+                    n = p.numel()
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                    off += n
+                total += flat.numel()
+        self.inflight = []
+        self.enabled = False
+        return total
+
+    def close(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+
 def shard_weight(n: int, world: int, rank: int) -> float:
     """Weight of this rank's mean loss in the global-batch mean, times `world` (allreduce_gradients divides by it):
     local_items * world / n.  1.0 whenever the batch divides evenly."""
@@ -205,10 +286,12 @@ def fp32_math():
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv, mm
 
 
-def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group=None, shard_weight: float = 1.0):
+def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group=None, shard_weight: float = 1.0,
+                   reducer: "OverlappedGradReducer | None" = None):
     """One 'G' iteration (:277-300): teacher-forced forward, L1 + binary divergence + guided attention + adversarial
     term scaled to the size of the other three, backward, gradient allreduce, Adam step.  Returns the loss terms.
-    `shard_weight` = local_items * world / global_items (1.0 for equal shards): the rank's mean losses and their
+    `reducer` (an OverlappedGradReducer over model.parameters()) overlaps the bucket allreduces with the backward pass;
+    without it the buckets are reduced after backward.  `shard_weight` = local_items * world / global_items (1.0 for equal shards): the rank's mean losses and their
     gradients are weighted by it, so that the average over ranks is the mean over the GLOBAL batch even when the
     shard sizes differ by one (`shard_weights`)."""
     opt_syn.zero_grad(set_to_none=True)
@@ -231,8 +314,13 @@ def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, gro
         t_l1, t_bd, t_att, t_disc = (float(v) for v in terms.tolist())
         scale = (t_l1 + t_bd + t_att) / abs(t_disc)
         loss = loss_l1 + loss_bd + loss_att + scale * loss_disc
+        if reducer is not None:
+            reducer.begin()                      # bucket allreduces start from the gradient hooks, under the backward pass
         (loss * shard_weight if shard_weight != 1.0 else loss).backward()
-    allreduce_gradients(model.parameters(), group=group)
+    if reducer is not None:
+        reducer.finish()
+    else:
+        allreduce_gradients(model.parameters(), group=group)
     opt_syn.step()
     return {"l1": t_l1, "bin_div": t_bd, "att": t_att, "disc": t_disc, "loss": t_l1 + t_bd + t_att + scale * t_disc}
 

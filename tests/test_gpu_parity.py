@@ -498,6 +498,21 @@ def test_pipelined_submit_wait_matches_sync(cuda_models):
         syn.collect(a)
 
 
+def test_host_result_as_bf16(cuda_models):
+    """ssv_decoder_set_lin_output: the half-size device->host result equals the fp32 one rounded to bfloat16."""
+    from spoofsv_b200.synth import Synthesizer
+    m1, m2, _, _ = cuda_models
+    names, emb, _ = W.load_fixtures()
+    ids = W.synthetic_text(3, 25, seed=8).numpy()[:, 0, :]
+    spk = emb[:3].copy()
+    want = Synthesizer(m1, m2).synthesize_host(ids, spk, 12)["lin"].copy()
+    got = Synthesizer(m1, m2, lin_dtype="bf16").synthesize_host(ids, spk, 12)["lin"]
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == want.shape
+    assert torch.equal(got, torch.from_numpy(want).to(torch.bfloat16))
+    back = Synthesizer(m1, m2).synthesize_host(ids, spk, 12)["lin"]          # and back to fp32 on the same decoder
+    assert np.array_equal(back, want)
+
+
 def test_corpus_driver_writes_wavs(tmp_path, write_driver_cfg):
     """--save_wav: the reference's file naming and sample format (float32 wav at SAMPLING_RATE, peak 0.75, <= 9 s)."""
     import json

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from spoofsv_b200.train import allreduce_gradients, plan_buckets, shard_batch, shard_weight
+from spoofsv_b200.train import OverlappedGradReducer, allreduce_gradients, plan_buckets, shard_batch, shard_weight
 
 
 def test_plan_buckets_preserves_order_and_limits():
@@ -113,6 +113,55 @@ def test_uneven_shards_are_weighted_to_the_global_mean_gloo():
         assert p.exitcode == 0
     assert [round(w, 6) for _, w, _ in out] == [1.2, 0.8]
     assert all(err <= 1e-6 for _, _, err in out)
+
+
+def _worker_overlap(rank: int, world: int, port: int, q):
+    """The hook-driven reducer (bucket allreduces launched during backward) gives the same gradients as the global
+    batch; a parameter that gets no gradient contributes zeros; a second step re-arms cleanly."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(7, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+        unused = torch.nn.Parameter(torch.ones(6))
+        params = list(model.parameters()) + [unused]
+        red = OverlappedGradReducer(params, bucket_mb=1e-4)            # tiny buckets: several launches from the hooks
+        assert len(red.buckets) >= 3
+        g = torch.Generator().manual_seed(1)
+        errs = []
+        for step in range(2):
+            x, y = torch.randn(8, 7, generator=g), torch.randn(8, 3, generator=g)
+            for p in params:
+                p.grad = None
+            sl = shard_batch(8, world, rank)
+            red.begin()
+            ((model(x[sl]) - y[sl]) ** 2).mean().backward()
+            launched_in_backward = sum(red.launched)
+            n = red.finish(average=True)
+            ref = torch.nn.Sequential(torch.nn.Linear(7, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+            ref.load_state_dict(model.state_dict())
+            ((ref(x) - y) ** 2).mean().backward()
+            errs.append(max(float((a.grad - b.grad).abs().max()) for a, b in zip(model.parameters(), ref.parameters())))
+            assert launched_in_backward >= 2 and n == sum(p.numel() for p in params)
+            assert float(unused.grad.abs().max()) == 0.0
+        red.close()
+        q.put((rank, max(errs)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_reducer_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlap, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(err <= 1e-6 for _, err in out)
 
 
 def test_allreduce_is_a_noop_without_a_process_group():
