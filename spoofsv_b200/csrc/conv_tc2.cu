@@ -1,0 +1,473 @@
+// tcgen05 implicit-GEMM conv1d + LayerNorm / highway-gate kernel, BF16 operands, second generation.
+//
+// The BF16 arm of the SSRN conv stack (models/TTSModel.py:342-362: highwayConv :63-84, 1x1 conv + LayerNorm,
+// ConvTranspose1d as a 1x1 GEMM).  Same GEMM view as conv_tc.cu (M = 128 time steps of one utterance, K = taps * Cin
+// tap-major, N = output channels, TMA tap loads with out-of-bounds zero fill), different occupancy plan:
+//   * a CTA owns 256 accumulator columns (one 128 x 256 fp32 tile = HALF of TMEM) and 90 KB of shared memory, so TWO
+//     CTAs are resident per SM: while one runs its epilogue (TMEM -> LayerNorm -> gate -> global), the other one's
+//     MMAs keep the tensor pipe busy -- the overlap a persistent kernel gets from TMEM double buffering, without
+//     a tile scheduler (conv_tc.cu: 512 columns, one CTA per SM, epilogue serial with the mainloop: 36 % tensor-pipe
+//     activity on the d = 512 layers);
+//   * wider layers split N over a cluster of 2 (d = 256 highway, 512-column plain layers) or 4 CTAs (d = 512
+//     highway), each CTA with matching H1 / H2 column slices; the per-row LayerNorm sums cross the cluster through
+//     distributed shared memory;
+//   * 4 epilogue warps, one thread per row; the residual is read from global memory one 16-channel chunk ahead.
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace ssv {
+
+namespace {
+
+using namespace tcx;
+
+constexpr int NT = 256;                   // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
+constexpr int BM = 128, NL = 256;
+constexpr int BKE = 32;                   // bf16 elements per k-block: 64-byte rows, SWIZZLE_64B, two K = 16 MMA steps
+constexpr int NSTAGES = 3;
+constexpr uint32_t A_BYTES = BM * BKE * 2;            // 8 KB
+constexpr uint32_t B_BYTES = NL * BKE * 2;            // 16 KB
+constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;   // 24 KB
+constexpr int HW_LD = 136;                // bf16 per row of the staged 128-column output tile (272 B: odd number of 16-byte units)
+constexpr int PL_LD = 264;                // same for 256 columns (528 B)
+
+struct alignas(64) Args {
+  CUtensorMap tmA;        // activations, 3-D (C, T, B) bf16, box (32, 128 / nn, 1), SWIZZLE_64B
+  CUtensorMap tmB;        // weights, 2-D (K, rows) bf16, box (32, 256 / nm)
+  int T, B, tiles_per_b, n_tiles;
+  int kb_per_tap, ktaps, dil, causal;
+  int cluster_n;          // = nn: CTAs splitting N (they share the activation tile)
+  int nm;                 // M tiles per cluster (they share the weight tile); cluster size = nn * nm
+  int w0_base, w0_rank, w1_base, w1_rank;
+  int n_real, epi;
+  const float* bias; const float* g1; const float* b1; const float* g2; const float* b2;
+  const __nv_bfloat16* Xres; long x_sb, x_st;
+  __nv_bfloat16* Y; long y_sb, y_st;
+};
+
+__device__ __forceinline__ uint32_t idesc_bf16() {   // kind::f16: D = F32, A = B = BF16, K-major, N = 256, M = 128
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NL >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+
+__global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_constant__ Args a, int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)NSTAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NSTAGES;
+  uint64_t* accum_bar = empty_bar + NSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  float4* prm_s = reinterpret_cast<float4*>(smem + (((size_t)NSTAGES * STAGE_BYTES + (2 * NSTAGES + 1) * 8 + 8 + 15) & ~size_t(15)));
+  float4* stat_s = prm_s + NL;                                    // [4 ranks][128] the cluster's sums
+  __nv_bfloat16* out_s = reinterpret_cast<__nv_bfloat16*>(tiles); // output staging tile (aliases the drained stages)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // cluster = nm M-tiles x nn N-slices.  The nn CTAs of an M-tile share its activation tile, the nm CTAs of an N-slice
+  // share its weight tile: every CTA fetches 1 / nn of the one and 1 / nm of the other and MULTICASTS them (L2 -> SM
+  // traffic per CTA drops from 128 + 256 rows per k-step to 128 / nn + 256 / nm: without it the d = 512 layers needed
+  // 96 B/clk/SM against the ~42 B/clk/SM the L2 delivers to 148 SMs, and sat at 36 % tensor-pipe activity).
+  const int csize = a.cluster_n * a.nm;
+  const uint32_t crank = csize > 1 ? cluster_rank() : 0u;
+  const uint32_t rank = crank % (uint32_t)a.cluster_n;           // N slice
+  const uint32_t rank_m = crank / (uint32_t)a.cluster_n;         // M tile inside the cluster
+  const int tile = (blockIdx.x / csize) * a.nm + (int)rank_m;
+  const bool tile_in = tile < a.n_tiles;                         // padding CTAs take part in the loads, write nothing
+  const int b = tile / a.tiles_per_b;
+  const int t0 = (tile - b * a.tiles_per_b) * BM;
+  const int w0 = a.w0_base + (int)rank * a.w0_rank;
+  const int w1 = a.w1_base + (int)rank * a.w1_rank;
+  const int nk = a.ktaps * a.kb_per_tap;
+  const bool hwy = a.epi == EPI_HIGHWAY;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&a.tmA); prefetch_tmap(&a.tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGES; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, (uint32_t)csize);     // every CTA of the cluster releases the stage in every CTA
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, NL);
+  for (int j = threadIdx.x; j < NL; j += NT) {
+    const int gc = j < 128 ? w0 + j : w1 + (j - 128);
+    float g = 1.f, be = 0.f;
+    if (hwy) {
+      const int c = j < 128 ? gc : gc - a.n_real;
+      g = j < 128 ? a.g1[c] : a.g2[c];
+      be = j < 128 ? a.b1[c] : a.b2[c];
+    } else if (a.epi != EPI_NONE) {
+      g = a.g1[gc];
+      be = a.b1[gc];
+    }
+    prm_s[j] = make_float4(a.bias[gc], g, be, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (csize > 1) cluster_sync_all();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % NSTAGES;
+        const uint32_t ph = (uint32_t)(kb / NSTAGES) & 1u;
+        if (!mbar_wait(empty_bar + st, ph ^ 1u, err)) break;
+        uint8_t* S = tiles + (size_t)st * STAGE_BYTES;
+        mbar_expect_tx(full_bar + st, STAGE_BYTES);
+        const int j = kb / a.kb_per_tap;
+        const int c0 = (kb - j * a.kb_per_tap) * BKE;
+        if (csize == 1) {
+          tma_load_3d(S, &a.tmA, full_bar + st, c0, t0 + (tap_base + j) * a.dil, b);
+          tma_load_2d(S + A_BYTES, &a.tmB, full_bar + st, kb * BKE, w0);
+          tma_load_2d(S + A_BYTES + B_BYTES / 2, &a.tmB, full_bar + st, kb * BKE, w1);
+        } else {
+          // my 128 / nn rows of the activation tile -> the nn CTAs of my M-tile
+          const int a_rows = BM / a.cluster_n;
+          const uint16_t mask_a = (uint16_t)(((1u << a.cluster_n) - 1u) << (rank_m * a.cluster_n));
+          tma_load_3d_mc(S + (size_t)rank * a_rows * (BKE * 2), &a.tmA, full_bar + st, c0,
+                         t0 + (tap_base + j) * a.dil + (int)rank * a_rows, b, mask_a);
+          // my 256 / nm rows of the weight tile -> the nm CTAs of my N-slice
+          const int b_rows = NL / a.nm;
+          const int r0 = (int)rank_m * b_rows;
+          uint16_t mask_b = 0;
+          for (int i = 0; i < a.nm; ++i) mask_b |= (uint16_t)(1u << (i * a.cluster_n + (int)rank));
+          const int box_rows = b_rows > 128 ? 128 : b_rows;            // a box never straddles the two weight blocks
+          for (int r = r0; r < r0 + b_rows; r += box_rows)
+            tma_load_2d_mc(S + A_BYTES + (size_t)r * (BKE * 2), &a.tmB, full_bar + st, kb * BKE,
+                           (r < 128 ? w0 + r : w1 + (r - 128)), mask_b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16();
+      bool ok = true;
+      for (int kb = 0; kb < nk && ok; ++kb) {
+        const int st = kb % NSTAGES;
+        const uint32_t ph = (uint32_t)(kb / NSTAGES) & 1u;
+        ok = mbar_wait(full_bar + st, ph, err);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t As = smem_u32(tiles + (size_t)st * STAGE_BYTES);
+        const uint32_t Bs = As + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKE / 16; ++k)
+          umma_bf16(tmem_base, umma_desc64(As + k * 32), umma_desc64(Bs + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+        if (csize == 1) umma_commit(empty_bar + st);
+        else umma_commit_mc(empty_bar + st, (uint16_t)((1u << csize) - 1u));
+      }
+      umma_commit(accum_bar);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: one thread per row =====================
+    const int q = warp & 3, ew = warp - 4;
+    const int row = q * 32 + lane;
+    const int t = t0 + row;
+    const bool row_in = t < a.T && tile_in;
+    const __nv_bfloat16* xres = a.Xres + (long)b * a.x_sb + (long)t * a.x_st + w0;
+    // the first residual chunk travels while the mainloop runs
+    bf16x8 xr0, xr1;
+    xr0.v[0] = xr0.v[1] = xr0.v[2] = xr0.v[3] = xr1.v[0] = xr1.v[1] = xr1.v[2] = xr1.v[3] = __floats2bfloat162_rn(0.f, 0.f);
+    if (hwy && row_in) {
+      xr0 = *reinterpret_cast<const bf16x8*>(xres);
+      xr1 = *reinterpret_cast<const bf16x8*>(xres + 8);
+    }
+    const bool got = mbar_wait(accum_bar, 0u, err);
+    tc_fence_after();
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t r0[16], r1[16];
+    const int ncol = hwy ? 128 : NL;          // columns per LayerNorm pass of this thread (highway: H1 and H2 side by side)
+
+    float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
+    if (a.epi != EPI_NONE) {
+      for (int c = 0; c < ncol; c += 16) {
+        tmem_ld16_issue(tq + c, r0);
+        if (hwy) tmem_ld16_issue(tq + 128 + c, r1);
+        tmem_wait16(r0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x = __uint_as_float(r0[i]) + prm_s[c + i].x;
+          s1 += x; q1 = fmaf(x, x, q1);
+        }
+        if (hwy) {
+          tmem_wait16(r1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = __uint_as_float(r1[i]) + prm_s[128 + c + i].x;
+            s2 += x; q2 = fmaf(x, x, q2);
+          }
+        }
+      }
+      if (a.cluster_n > 1) {
+        const float4 mine = make_float4(s1, q1, s2, q2);
+        stat_s[rank * BM + row] = mine;
+        for (uint32_t p = 0; p < (uint32_t)a.cluster_n; ++p)
+          if (p != rank) st_peer_f32x4(stat_s + rank * BM + row, rank_m * (uint32_t)a.cluster_n + p, mine);
+        cluster_sync_all();
+        s1 = q1 = s2 = q2 = 0.f;
+        for (int p = 0; p < a.cluster_n; ++p) {
+          const float4 v = stat_s[p * BM + row];
+          s1 += v.x; q1 += v.y; s2 += v.z; q2 += v.w;
+        }
+      }
+    }
+    const float inv_n = 1.0f / (float)a.n_real;
+    const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+    const float rs1 = rsqrtf(fmaxf(q1 * inv_n - m1 * m1, 0.f) + 1e-5f);
+    const float rs2 = rsqrtf(fmaxf(q2 * inv_n - m2 * m2, 0.f) + 1e-5f);
+
+    const int o_ld = hwy ? HW_LD : PL_LD;
+    const bool relu = a.epi == EPI_LN_RELU, none = a.epi == EPI_NONE;
+    for (int c = 0; c < ncol; c += 16) {
+      tmem_ld16_issue(tq + c, r0);
+      if (hwy) tmem_ld16_issue(tq + 128 + c, r1);
+      bf16x8 nx0 = xr0, nx1 = xr1;
+      if (hwy && row_in && c + 16 < ncol) {                      // next chunk's residual
+        nx0 = *reinterpret_cast<const bf16x8*>(xres + c + 16);
+        nx1 = *reinterpret_cast<const bf16x8*>(xres + c + 24);
+      }
+      tmem_wait16(r0);
+      float o[16];
+      if (hwy) {
+        tmem_wait16(r1);
+        float xr[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 fa = __bfloat1622float2(xr0.v[i]), fb = __bfloat1622float2(xr1.v[i]);
+          xr[2 * i] = fa.x; xr[2 * i + 1] = fa.y; xr[8 + 2 * i] = fb.x; xr[8 + 2 * i + 1] = fb.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 p1 = prm_s[c + i], p2 = prm_s[128 + c + i];
+          const float A1 = rs1 * p1.y, A2 = rs2 * p2.y;
+          const float h1 = fmaf(__uint_as_float(r0[i]), A1, fmaf(p1.x - m1, A1, p1.z));
+          const float h2 = fmaf(__uint_as_float(r1[i]), A2, fmaf(p2.x - m2, A2, p2.z));
+          const float g = sigmoid_fast(h1);
+          o[i] = fmaf(g, h2 - xr[i], xr[i]);
+        }
+      } else if (none) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r0[i]) + prm_s[c + i].x;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 p1 = prm_s[c + i];
+          const float A1 = rs1 * p1.y;
+          const float h1 = fmaf(__uint_as_float(r0[i]), A1, fmaf(p1.x - m1, A1, p1.z));
+          o[i] = relu ? fmaxf(h1, 0.f) : h1;
+        }
+      }
+      bf16x8 oa, ob;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        oa.v[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        ob.v[i] = __floats2bfloat162_rn(o[8 + 2 * i], o[8 + 2 * i + 1]);
+      }
+      bf16x8* dst = reinterpret_cast<bf16x8*>(out_s + (size_t)row * o_ld + c);
+      dst[0] = oa;
+      dst[1] = ob;
+      xr0 = nx0; xr1 = nx1;
+    }
+    epi_sync();
+    // coalesced copy-out: highway: columns [w0, w0 + 128) (16 lanes x 16 B per row, two rows per warp pass);
+    // plain: [w0, w0 + 128) | [w1, w1 + 128) (32 lanes per row)
+    if (hwy) {
+      const int half = lane >> 4, l16 = lane & 15;
+      for (int i = 0; i < BM / 4; i += 2) {
+        const int r = ew * (BM / 4) + i + half;
+        const int tr = t0 + r;
+        if (tr < a.T && got && tile_in) {
+          const uint4 v = *reinterpret_cast<const uint4*>(out_s + (size_t)r * o_ld + l16 * 8);
+          *reinterpret_cast<uint4*>(a.Y + (long)b * a.y_sb + (long)tr * a.y_st + w0 + l16 * 8) = v;
+        }
+      }
+    } else {
+      for (int i = 0; i < BM / 4; ++i) {
+        const int r = ew * (BM / 4) + i;
+        const int tr = t0 + r;
+        if (tr < a.T && got && tile_in) {
+          const uint4 v = *reinterpret_cast<const uint4*>(out_s + (size_t)r * o_ld + lane * 8);
+          const int gc = lane < 16 ? w0 + lane * 8 : w1 + (lane - 16) * 8;
+          *reinterpret_cast<uint4*>(a.Y + (long)b * a.y_sb + (long)tr * a.y_st + gc) = v;
+        }
+      }
+    }
+  }
+
+  if (a.cluster_n > 1 && a.epi != EPI_NONE && warp < 4) cluster_sync_all();
+  // multicast: no CTA leaves while a peer's stage release (a remote mbarrier arrive) may still be on its way to it
+  if (csize > 1) cluster_sync_all();
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, NL);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn2() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int make_map_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+  auto fn = encode_fn2();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return kCuda;
+  }
+  cuuint32_t ones[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+    return kCuda;
+  }
+  return kOk;
+}
+
+int* v2_err_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc((void**)&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+}  // namespace
+
+struct Tc2LaunchImpl {
+  Args args;
+};
+static_assert(sizeof(Tc2LaunchImpl) <= sizeof(((Tc2Launch*)nullptr)->storage), "Tc2Launch::storage too small");
+
+bool tc2_supported(const TcLayer& L, int epi) {
+  if (epi == EPI_HIGHWAY) return L.n_real == 256 || L.n_real == 512;
+  if (epi == EPI_LN || epi == EPI_LN_RELU || epi == EPI_NONE) return L.rows == 256 || L.rows == 512;
+  return false;
+}
+
+int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloat16* X, int x_ld, int T, int B,
+                __nv_bfloat16* Y, int y_ld, Tc2Launch* out) {
+  SSV_CHECK(tc2_supported(L, epi), "conv_tc2: layer shape (rows %d, epilogue %d) not built", L.rows, epi);
+  SSV_CHECK(L.cin_p % BKE == 0 && x_ld >= L.cin_p && x_ld % 8 == 0 && y_ld % 8 == 0, "conv_tc2: bad padding (cin_p %d, ld %d)", L.cin_p, x_ld);
+  Args& a = reinterpret_cast<Tc2LaunchImpl*>(out->storage)->args;
+  memset(&a, 0, sizeof(a));
+  const int nn = epi == EPI_HIGHWAY ? L.n_real / 128 : L.rows / 256;
+  a.T = T; a.B = B;
+  a.tiles_per_b = (T + BM - 1) / BM;
+  a.n_tiles = B * a.tiles_per_b;
+  // M tiles per cluster: 8 CTAs per cluster when there are enough tiles to share a weight tile
+  int nm = 8 / nn;
+  while (nm > 1 && a.n_tiles < 4 * nm) nm >>= 1;
+  if (const char* e = getenv("SSV_TC2_NM")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nm = v; }
+  if (nn * nm > 8) nm = 8 / nn;
+  a.nm = nm;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)x_ld, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)x_ld * 2, (cuuint64_t)T * x_ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BKE, (cuuint32_t)(nn * nm > 1 ? BM / nn : BM), 1};
+    SSV_TRY(make_map_bf16(&a.tmA, X, 3, dims, strides, box));
+  }
+  const int kp = L.k * L.cin_p;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)L.rows_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(NL / nm > 128 ? 128 : NL / nm)};
+    SSV_TRY(make_map_bf16(&a.tmB, L.W, 2, dims, strides, box));
+  }
+  a.kb_per_tap = L.cin_p / BKE;
+  a.ktaps = L.k; a.dil = dil; a.causal = causal;
+  if (epi == EPI_HIGHWAY) {
+    a.cluster_n = L.n_real / 128;
+    a.w0_base = 0; a.w0_rank = 128; a.w1_base = L.n_real; a.w1_rank = 128;
+    a.n_real = L.n_real;
+  } else {
+    a.cluster_n = L.rows / 256;
+    a.w0_base = 0; a.w0_rank = 256; a.w1_base = 128; a.w1_rank = 256;
+    a.n_real = L.rows;
+  }
+  a.epi = epi;
+  a.bias = L.bias;
+  a.g1 = L.g1; a.b1 = L.b1; a.g2 = L.g2; a.b2 = L.b2;
+  a.Xres = X; a.x_sb = (long)T * x_ld; a.x_st = x_ld;
+  a.Y = Y; a.y_sb = (long)T * y_ld; a.y_st = y_ld;
+  out->n_ctas = ((a.n_tiles + nm - 1) / nm) * nm * a.cluster_n;
+  out->cluster_n = a.cluster_n * nm;
+  return kOk;
+}
+
+int tc2_run(const Tc2Launch& L, cudaStream_t s) {
+  int* err = v2_err_flag();
+  SSV_CHECK(err != nullptr, "conv_tc2: cannot allocate the error flag");
+  const size_t smem = 1024 + (size_t)NSTAGES * STAGE_BYTES + 256 + (size_t)NL * 16 + 4 * BM * 16;
+  static bool configured = false;
+  if (!configured) {
+    SSV_CUDA(cudaFuncSetAttribute(conv_bf16_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)L.n_ctas);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)L.cluster_n;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SSV_CUDA(cudaLaunchKernelEx(&cfg, conv_bf16_v2_kernel, reinterpret_cast<const Tc2LaunchImpl*>(L.storage)->args, err));
+  ++g_launches;
+  return kOk;
+}
+
+int tc2_check_error() {
+  int* flag = v2_err_flag();
+  if (!flag) return kOk;
+  int h = 0;
+  SSV_CUDA(cudaMemcpy(&h, flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h != 0) {
+    cudaMemset(flag, 0, sizeof(int));
+    set_error("tcgen05 conv kernel (v2): pipeline wait timed out (code %d)", h);
+    return kState;
+  }
+  return kOk;
+}
+
+}  // namespace ssv
