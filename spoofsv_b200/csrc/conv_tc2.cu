@@ -12,6 +12,12 @@
 //     highway), each CTA with matching H1 / H2 column slices; the per-row LayerNorm sums cross the cluster through
 //     distributed shared memory;
 //   * 4 epilogue warps, one thread per row; the residual is read from global memory one 16-channel chunk ahead.
+// What bounds it (ncu, profiles/): the d = 512 layers stream 2.1 GB of operand tiles from L2 per layer (a 128 x 256 tile
+// has 43 MAC per operand byte), 7.6 TB/s -- the L2 ceiling -- at 36 % tensor-pipe activity, in this kernel as in
+// conv_tc.cu.  Tried: TMA multicast of the activation tile over the N slices and of the weight tile over the M tiles
+// of a 2 x 4 / 4 x 2 cluster (every CTA fetches 1/nn + 1/nm of the stage): SSRN 64 x 217 1.65 -> 1.87 / 1.94 ms, the
+// cluster-wide stage hand-shake and the 2 KB boxes cost more than the L2 traffic saved (git history).  The lever that
+// is left is cta_group::2 (a CTA pair shares the weight tile: 64 MAC per byte).
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -38,12 +44,11 @@ constexpr int HW_LD = 136;                // bf16 per row of the staged 128-colu
 constexpr int PL_LD = 264;                // same for 256 columns (528 B)
 
 struct alignas(64) Args {
-  CUtensorMap tmA;        // activations, 3-D (C, T, B) bf16, box (32, 128 / nn, 1), SWIZZLE_64B
-  CUtensorMap tmB;        // weights, 2-D (K, rows) bf16, box (32, 256 / nm)
-  int T, B, tiles_per_b, n_tiles;
+  CUtensorMap tmA;        // activations, 3-D (C, T, B) bf16, box (32, 128, 1), SWIZZLE_64B
+  CUtensorMap tmB;        // weights, 2-D (K, rows) bf16, box (32, 128)
+  int T, B, tiles_per_b;
   int kb_per_tap, ktaps, dil, causal;
-  int cluster_n;          // = nn: CTAs splitting N (they share the activation tile)
-  int nm;                 // M tiles per cluster (they share the weight tile); cluster size = nn * nm
+  int cluster_n;          // CTAs splitting N
   int w0_base, w0_rank, w1_base, w1_rank;
   int n_real, epi;
   const float* bias; const float* g1; const float* b1; const float* g2; const float* b2;
@@ -81,16 +86,8 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
   __nv_bfloat16* out_s = reinterpret_cast<__nv_bfloat16*>(tiles); // output staging tile (aliases the drained stages)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // cluster = nm M-tiles x nn N-slices.  The nn CTAs of an M-tile share its activation tile, the nm CTAs of an N-slice
-  // share its weight tile: every CTA fetches 1 / nn of the one and 1 / nm of the other and MULTICASTS them (L2 -> SM
-  // traffic per CTA drops from 128 + 256 rows per k-step to 128 / nn + 256 / nm: without it the d = 512 layers needed
-  // 96 B/clk/SM against the ~42 B/clk/SM the L2 delivers to 148 SMs, and sat at 36 % tensor-pipe activity).
-  const int csize = a.cluster_n * a.nm;
-  const uint32_t crank = csize > 1 ? cluster_rank() : 0u;
-  const uint32_t rank = crank % (uint32_t)a.cluster_n;           // N slice
-  const uint32_t rank_m = crank / (uint32_t)a.cluster_n;         // M tile inside the cluster
-  const int tile = (blockIdx.x / csize) * a.nm + (int)rank_m;
-  const bool tile_in = tile < a.n_tiles;                         // padding CTAs take part in the loads, write nothing
+  const uint32_t rank = a.cluster_n > 1 ? cluster_rank() : 0u;
+  const int tile = blockIdx.x / a.cluster_n;
   const int b = tile / a.tiles_per_b;
   const int t0 = (tile - b * a.tiles_per_b) * BM;
   const int w0 = a.w0_base + (int)rank * a.w0_rank;
@@ -102,7 +99,7 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NSTAGES; ++i) {
       mbar_init(full_bar + i, 1);
-      mbar_init(empty_bar + i, (uint32_t)csize);     // every CTA of the cluster releases the stage in every CTA
+      mbar_init(empty_bar + i, 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -126,7 +123,7 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (csize > 1) cluster_sync_all();
+  if (a.cluster_n > 1) cluster_sync_all();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -139,26 +136,9 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
         mbar_expect_tx(full_bar + st, STAGE_BYTES);
         const int j = kb / a.kb_per_tap;
         const int c0 = (kb - j * a.kb_per_tap) * BKE;
-        if (csize == 1) {
-          tma_load_3d(S, &a.tmA, full_bar + st, c0, t0 + (tap_base + j) * a.dil, b);
-          tma_load_2d(S + A_BYTES, &a.tmB, full_bar + st, kb * BKE, w0);
-          tma_load_2d(S + A_BYTES + B_BYTES / 2, &a.tmB, full_bar + st, kb * BKE, w1);
-        } else {
-          // my 128 / nn rows of the activation tile -> the nn CTAs of my M-tile
-          const int a_rows = BM / a.cluster_n;
-          const uint16_t mask_a = (uint16_t)(((1u << a.cluster_n) - 1u) << (rank_m * a.cluster_n));
-          tma_load_3d_mc(S + (size_t)rank * a_rows * (BKE * 2), &a.tmA, full_bar + st, c0,
-                         t0 + (tap_base + j) * a.dil + (int)rank * a_rows, b, mask_a);
-          // my 256 / nm rows of the weight tile -> the nm CTAs of my N-slice
-          const int b_rows = NL / a.nm;
-          const int r0 = (int)rank_m * b_rows;
-          uint16_t mask_b = 0;
-          for (int i = 0; i < a.nm; ++i) mask_b |= (uint16_t)(1u << (i * a.cluster_n + (int)rank));
-          const int box_rows = b_rows > 128 ? 128 : b_rows;            // a box never straddles the two weight blocks
-          for (int r = r0; r < r0 + b_rows; r += box_rows)
-            tma_load_2d_mc(S + A_BYTES + (size_t)r * (BKE * 2), &a.tmB, full_bar + st, kb * BKE,
-                           (r < 128 ? w0 + r : w1 + (r - 128)), mask_b);
-        }
+        tma_load_3d(S, &a.tmA, full_bar + st, c0, t0 + (tap_base + j) * a.dil, b);
+        tma_load_2d(S + A_BYTES, &a.tmB, full_bar + st, kb * BKE, w0);
+        tma_load_2d(S + A_BYTES + B_BYTES / 2, &a.tmB, full_bar + st, kb * BKE, w1);
       }
     }
   } else if (warp == 1) {
@@ -176,8 +156,7 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < BKE / 16; ++k)
           umma_bf16(tmem_base, umma_desc64(As + k * 32), umma_desc64(Bs + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-        if (csize == 1) umma_commit(empty_bar + st);
-        else umma_commit_mc(empty_bar + st, (uint16_t)((1u << csize) - 1u));
+        umma_commit(empty_bar + st);
       }
       umma_commit(accum_bar);
     }
@@ -186,7 +165,7 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
     const int q = warp & 3, ew = warp - 4;
     const int row = q * 32 + lane;
     const int t = t0 + row;
-    const bool row_in = t < a.T && tile_in;
+    const bool row_in = t < a.T;
     const __nv_bfloat16* xres = a.Xres + (long)b * a.x_sb + (long)t * a.x_st + w0;
     // the first residual chunk travels while the mainloop runs
     bf16x8 xr0, xr1;
@@ -225,7 +204,7 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
         const float4 mine = make_float4(s1, q1, s2, q2);
         stat_s[rank * BM + row] = mine;
         for (uint32_t p = 0; p < (uint32_t)a.cluster_n; ++p)
-          if (p != rank) st_peer_f32x4(stat_s + rank * BM + row, rank_m * (uint32_t)a.cluster_n + p, mine);
+          if (p != rank) st_peer_f32x4(stat_s + rank * BM + row, p, mine);
         cluster_sync_all();
         s1 = q1 = s2 = q2 = 0.f;
         for (int p = 0; p < a.cluster_n; ++p) {
@@ -299,7 +278,7 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
       for (int i = 0; i < BM / 4; i += 2) {
         const int r = ew * (BM / 4) + i + half;
         const int tr = t0 + r;
-        if (tr < a.T && got && tile_in) {
+        if (tr < a.T && got) {
           const uint4 v = *reinterpret_cast<const uint4*>(out_s + (size_t)r * o_ld + l16 * 8);
           *reinterpret_cast<uint4*>(a.Y + (long)b * a.y_sb + (long)tr * a.y_st + w0 + l16 * 8) = v;
         }
@@ -308,7 +287,7 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
       for (int i = 0; i < BM / 4; ++i) {
         const int r = ew * (BM / 4) + i;
         const int tr = t0 + r;
-        if (tr < a.T && got && tile_in) {
+        if (tr < a.T && got) {
           const uint4 v = *reinterpret_cast<const uint4*>(out_s + (size_t)r * o_ld + lane * 8);
           const int gc = lane < 16 ? w0 + lane * 8 : w1 + (lane - 16) * 8;
           *reinterpret_cast<uint4*>(a.Y + (long)b * a.y_sb + (long)tr * a.y_st + gc) = v;
@@ -318,8 +297,6 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
   }
 
   if (a.cluster_n > 1 && a.epi != EPI_NONE && warp < 4) cluster_sync_all();
-  // multicast: no CTA leaves while a peer's stage release (a remote mbarrier arrive) may still be on its way to it
-  if (csize > 1) cluster_sync_all();
 
   tc_fence_before();
   __syncthreads();
@@ -387,27 +364,19 @@ int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloa
   SSV_CHECK(L.cin_p % BKE == 0 && x_ld >= L.cin_p && x_ld % 8 == 0 && y_ld % 8 == 0, "conv_tc2: bad padding (cin_p %d, ld %d)", L.cin_p, x_ld);
   Args& a = reinterpret_cast<Tc2LaunchImpl*>(out->storage)->args;
   memset(&a, 0, sizeof(a));
-  const int nn = epi == EPI_HIGHWAY ? L.n_real / 128 : L.rows / 256;
   a.T = T; a.B = B;
   a.tiles_per_b = (T + BM - 1) / BM;
-  a.n_tiles = B * a.tiles_per_b;
-  // M tiles per cluster: 8 CTAs per cluster when there are enough tiles to share a weight tile
-  int nm = 8 / nn;
-  while (nm > 1 && a.n_tiles < 4 * nm) nm >>= 1;
-  if (const char* e = getenv("SSV_TC2_NM")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nm = v; }
-  if (nn * nm > 8) nm = 8 / nn;
-  a.nm = nm;
   {
     cuuint64_t dims[3] = {(cuuint64_t)x_ld, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)x_ld * 2, (cuuint64_t)T * x_ld * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BKE, (cuuint32_t)(nn * nm > 1 ? BM / nn : BM), 1};
+    cuuint32_t box[3] = {(cuuint32_t)BKE, BM, 1};
     SSV_TRY(make_map_bf16(&a.tmA, X, 3, dims, strides, box));
   }
   const int kp = L.k * L.cin_p;
   {
     cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)L.rows_pad};
     cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(NL / nm > 128 ? 128 : NL / nm)};
+    cuuint32_t box[2] = {(cuuint32_t)BKE, 128};
     SSV_TRY(make_map_bf16(&a.tmB, L.W, 2, dims, strides, box));
   }
   a.kb_per_tap = L.cin_p / BKE;
@@ -426,8 +395,8 @@ int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloa
   a.g1 = L.g1; a.b1 = L.b1; a.g2 = L.g2; a.b2 = L.b2;
   a.Xres = X; a.x_sb = (long)T * x_ld; a.x_st = x_ld;
   a.Y = Y; a.y_sb = (long)T * y_ld; a.y_st = y_ld;
-  out->n_ctas = ((a.n_tiles + nm - 1) / nm) * nm * a.cluster_n;
-  out->cluster_n = a.cluster_n * nm;
+  out->n_ctas = B * a.tiles_per_b * a.cluster_n;
+  out->cluster_n = a.cluster_n;
   return kOk;
 }
 

@@ -60,11 +60,7 @@ constexpr int XROWS = 3 * TAPP;                    // rows of one X buffer ([row
 constexpr int XREGION = 2 * 8 * XROWS;             // floats; ws_nbuf(RT) buffers of XROWS rows x (2 or 4) floats
 constexpr int MAXBUF = 8;
 // X buffers per shape: 8 (one- and two-row micro-batches, 2 floats per X row) or 4 (four rows)
-#ifdef SSV_NBUF2
-__host__ __device__ constexpr int ws_nbuf(int rt) { return rt == 4 ? 4 : rt == 2 ? SSV_NBUF2 : 8; }
-#else
 __host__ __device__ constexpr int ws_nbuf(int rt) { return rt == 4 ? 4 : 8; }
-#endif
 constexpr int SM_WSM = 0;                          // [11][384] float4: tap-0 weights of a highway CTA
 constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [8 / RT][XROWS][RT * XLayout<RT>::D]
 constexpr int SM_PART = SM_X + XREGION;            // [12][RT][ncol <= 128] k-slice partial sums
@@ -364,13 +360,9 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
       } else {
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);
-#ifndef SSV_EXP_SKIP_PW
 #pragma unroll
         for (int j = 0; j < 22; ++j)
           if (j < st.nj) fma_tile<RT>(acc, w[j], X + (size_t)(KS * j) * XS);
-#else
-        if (p.n_steps < 0) acc[0][0] = w[3].x + w[21].y + X[0];     // timing experiment only: wrong values
-#endif
         PROF_G(1);                  // 1x1 stages: "old taps" column = the tile loop, "current tap" = k-slice store + barrier
       }
       // k-slices -> shared memory
@@ -670,9 +662,6 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
       long long t0 = 0;
       unsigned spins = 0;
       auto spin_check = [&]() {
-#ifdef SSV_POLL_SLEEP
-        __nanosleep(SSV_POLL_SLEEP);               // a failed poll backs off: its 12 loads per attempt share the LSU with the mat-vec
-#endif
         if ((++spins & 255u) == 0) {
           if (t0 == 0) t0 = clock64();
           else if (clock64() - t0 > SPIN_LIMIT) atomicExch(p.abort_flag, 8);
@@ -906,9 +895,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     PROF_F(6);
     // the mat-vec side hands the finished current-tap rows to the history ring with a bulk copy (async proxy):
     // order my generic-proxy stores before it
-#ifndef SSV_NO_FE_FENCE
     if (st.ntaps == 3) fence_proxy_async_smem();
-#endif
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&c.curfull[q]);              // release: my slice of the micro-batch is in X
@@ -1008,13 +995,8 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
   // Warps 0-3 are the front end, warps 4-15 the mat-vec.  (Tried: the front end as the four HIGHEST warps, which the
   // issue arbiter is said to prefer -- 3-4 % slower at every batch size: B = 1 31.3 -> 32.4, B = 64 50.1 -> 51.9,
   // B = 128 93.3 -> 97.8 us/frame.)
-#ifdef SSV_FE_HIGH
-  const bool is_fe = tid >= GV_T;
-  const int rtid = is_fe ? tid - GV_T : tid;
-#else
   const bool is_fe = tid < FE_T;
   const int rtid = is_fe ? tid : tid - FE_T;
-#endif
   if (is_fe) {
     front_role<RT, WPR, PROF>(p, st, c, rtid);
   } else {
