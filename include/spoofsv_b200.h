@@ -98,10 +98,11 @@ int ssv_decoder_step(ssv_decoder* d, const float* x, long x_stride_b, long x_str
 /* n_steps frames free-running in one launch: x_0 = 0 (or Y[:, :, t-1] when continuing),
  * x_t = y_{t-1}. */
 int ssv_decoder_run(ssv_decoder* d, int n_steps, void* stream);
-/* Front-end shape of the decode kernel for the batches begun after this call: rows per micro-batch (1, 2, 4) and
- * front-end warps per row (1, 2, 4); 0 = the measured choice for the batch size.  Tuning and test hook: every
- * shape computes the same values (tests/test_gpu_parity.py runs them all against the oracle). */
-int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_row);
+/* Front-end shape of the decode kernel for the batches begun after this call: rows per micro-batch (1, 2, 4),
+ * front-end warps per row (1, 2, 4) and front-end warps per CTA (4 or 8); 0 = the measured choice for the batch
+ * size.  Tuning and test hook: every shape computes the same values (tests/test_gpu_parity.py runs them all
+ * against the oracle). */
+int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_row, int front_end_warps);
 /* Frames decoded since begin. */
 int ssv_decoder_frames(const ssv_decoder* d);
 /* Synchronise `stream` and report a decode-kernel abort (barrier timeout) if one happened. */

@@ -40,7 +40,7 @@ SIGNATURES = {
     "ssv_decoder_step": (C.c_int, [C.c_void_p, _c_f32p, C.c_long, C.c_long, _c_i64p, C.c_void_p]),
     "ssv_decoder_run": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ssv_decoder_frames": (C.c_int, [C.c_void_p]),
-    "ssv_decoder_set_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ssv_decoder_set_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ssv_text2mel_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssv_decoder_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssv_ssrn_create": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]

@@ -335,8 +335,8 @@ struct ssv_decoder {
   unsigned long long* ws_raw = nullptr;
   float* ws_hist = nullptr;
   float* ws_zero = nullptr;
-  int seq_base = 0, R = 1, G = 1, W = 4;
-  int force_r = 0, force_w = 0;           // ssv_decoder_set_plan
+  int seq_base = 0, R = 1, G = 1, W = 4, F = 4;
+  int force_r = 0, force_w = 0, force_f = 0;     // ssv_decoder_set_plan
   // per-batch state
   bool begun = false;
   int B = 0, N = 0, t_cap = 0, t = 0;
@@ -898,7 +898,7 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
     return kState;
   }
   {
-    const size_t bp = (size_t)round_up(max_batch, 4);
+    const size_t bp = (size_t)round_up(max_batch, 8) + 8;      // micro-batch count is padded to the visit slots
     const size_t raw_words = (size_t)DEC_STAGES * max_batch * WS_WORDS;
     if (st == kOk) st = d->arena.alloc<unsigned long long>(raw_words, &d->ws_raw);
     // ring entries are [256][XS] floats per micro-batch, XS = 2 (R = 1: every activation as the pair (x, x); R = 2) or 4
@@ -949,7 +949,7 @@ int ssv_decoder_begin(ssv_decoder* d, const float* K, const float* V, const floa
     SSV_CUDA(cudaMemsetAsync(d->ws_raw, 0, (size_t)DEC_STAGES * d->maxB * WS_WORDS * sizeof(unsigned long long), s));
     d->seq_base = 0;
   }
-  ws_plan(B, d->force_r, d->force_w, &d->R, &d->W, &d->G);
+  ws_plan(B, d->force_r, d->force_w, d->force_f, &d->R, &d->W, &d->F, &d->G);
   d->B = B; d->N = N; d->t_cap = t_cap; d->t = 0;
   d->Y = Y; d->A = A; d->traj = reinterpret_cast<long long*>(pma_traj);
   d->begun = true;
@@ -978,7 +978,7 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.prof = d->prof;
   p.ws_stages = m->ws_stages_dev;
   p.ws_raw = d->ws_raw; p.ws_hist = d->ws_hist; p.ws_zero = d->ws_zero;
-  p.seq_base = d->seq_base; p.R = d->R; p.G = d->G; p.W = d->W;
+  p.seq_base = d->seq_base; p.R = d->R; p.G = d->G; p.W = d->W; p.FEW = d->F;
   if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 16, s));
   SSV_TRY(launch_decode_ws(p, s));
   if (d->prof) {   // development aid: per-phase SM cycles, mean / max over CTAs, per stage visit
@@ -1035,14 +1035,17 @@ int ssv_decoder_run(ssv_decoder* d, int n_steps, void* stream) {
 
 int ssv_decoder_frames(const ssv_decoder* d) { return d ? d->t : 0; }
 
-int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_row) {
+int ssv_decoder_set_plan(ssv_decoder* d, int rows_per_microbatch, int warps_per_row, int front_end_warps) {
   SSV_CHECK(d, "decoder_set_plan: null decoder");
   SSV_CHECK(rows_per_microbatch == 0 || rows_per_microbatch == 1 || rows_per_microbatch == 2 || rows_per_microbatch == 4,
             "decoder_set_plan: rows per micro-batch must be 0 (automatic), 1, 2 or 4");
   SSV_CHECK(warps_per_row == 0 || warps_per_row == 1 || warps_per_row == 2 || warps_per_row == 4,
             "decoder_set_plan: warps per row must be 0 (automatic), 1, 2 or 4");
+  SSV_CHECK(front_end_warps == 0 || front_end_warps == 4 || front_end_warps == 8,
+            "decoder_set_plan: front-end warps must be 0 (automatic), 4 or 8");
   d->force_r = rows_per_microbatch;
   d->force_w = warps_per_row;
+  d->force_f = front_end_warps;
   return kOk;
 }
 

@@ -76,12 +76,13 @@ struct DecParams {
   const float* ws_zero;         // one entry of zeros (taps before frame 0)
   int seq_base;                 // tag of frame t is seq_base + t + 1 (advanced by every begin())
   int R, G, W;                  // rows per micro-batch (1, 2, 4), micro-batches, front-end warps per row (1, 2, 4)
+  int FEW;                      // front-end warps of a CTA (4 or 8)
 };
 
 int launch_decode_ws(const DecParams& p, cudaStream_t s);          // decode_ws.cu
 bool decode_ws_supported(int sm_count);
 // front-end shape for a batch; force_r / force_w != 0 override the measured choice (ssv_decoder_set_plan)
-void ws_plan(int B, int force_r, int force_w, int* R, int* W, int* G);
+void ws_plan(int B, int force_r, int force_w, int force_f, int* R, int* W, int* F, int* G);
 void ws_stage_layout(const DecStage& d, WsStage* w);
 size_t ws_image_floats(const WsStage& w);
 int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStream_t s);

@@ -47,9 +47,8 @@ namespace ssv {
 
 namespace {
 
-constexpr int NT = 512;
-constexpr int FE_T = 128;                // front-end threads (warps 0-3)
-constexpr int GV_T = WS_GEMV_THREADS;    // mat-vec threads (warps 4-15)
+constexpr int GV_T = WS_GEMV_THREADS;    // mat-vec threads (the 12 warps after the front end)
+constexpr int MAX_FEW = 8;               // front-end warps: 4 (512-thread CTA) or 8 (640 threads, setmaxnreg)
 constexpr int HD = 256;
 constexpr int TAPP = WS_TAP_ROWS;        // rows of one tap in X (256 padded to a multiple of 24)
 constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks
@@ -67,9 +66,9 @@ constexpr int SM_PART = SM_X + XREGION;            // [12][RT][ncol <= 128] k-sl
 constexpr int SM_LN = SM_PART + 12 * 4 * 128;      // [4][256] LayerNorm parameters of my prologue
 constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
 constexpr int SM_PMA = SM_BIAS + 128;              // [WS_MAX_BATCH] ints (attention stage only)
-constexpr int SM_KV = SM_PMA + WS_MAX_BATCH;        // [4 warps][K window 3 | V window 3][256]: attention rows prefetched by cp.async
-constexpr int SM_RED = SM_KV + 4 * 6 * HD;          // [4 rounds][4 warps][8]: cross-warp LayerNorm statistics / logit sums (cooperative front end)
-constexpr int SM_TOTAL = SM_RED + 4 * 4 * 8;
+constexpr int SM_KV = SM_PMA + WS_MAX_BATCH;        // [rows in the front end <= 8][K window 3 | V window 3][256]: attention rows prefetched by cp.async
+constexpr int SM_RED = SM_KV + MAX_FEW * 6 * HD;    // [4 rounds][8 warps][8]: cross-warp LayerNorm statistics / logit sums (cooperative front end)
+constexpr int SM_TOTAL = SM_RED + 4 * MAX_FEW * 8;
 
 struct __align__(8) Word { float v; int tag; };
 
@@ -223,23 +222,20 @@ __device__ __forceinline__ float rstd_fast(float var) { return rsqrtf(var + 1e-5
 // us/frame), so those shapes keep scalar FMAs and the plain X layout.
 template <int RT> struct XLayout { static constexpr int D = RT == 1 ? 2 : 1; };   // floats per stored activation
 
+template <int RT> struct XVec { using T = float2; };          // one X row: (x, x) | (x0, x1) | (x0, x1, x2, x3)
+template <> struct XVec<4> { using T = float4; };
+
 template <int RT>
-__device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, const float* xp) {
+__device__ __forceinline__ void fma_row(float (&acc)[RT][4], const float4& w, const typename XVec<RT>::T& v) {
   if constexpr (RT == 1) {
-    const float2 x = *reinterpret_cast<const float2*>(xp);                         // (x, x)
     float2 a01 = make_float2(acc[0][0], acc[0][1]), a23 = make_float2(acc[0][2], acc[0][3]);
-    a01 = __ffma2_rn(x, make_float2(w.x, w.y), a01);
-    a23 = __ffma2_rn(x, make_float2(w.z, w.w), a23);
+    a01 = __ffma2_rn(v, make_float2(w.x, w.y), a01);
+    a23 = __ffma2_rn(v, make_float2(w.z, w.w), a23);
     acc[0][0] = a01.x; acc[0][1] = a01.y; acc[0][2] = a23.x; acc[0][3] = a23.y;
   } else {
     float x[RT];
-    if constexpr (RT == 2) {
-      const float2 v = *reinterpret_cast<const float2*>(xp);
-      x[0] = v.x; x[1] = v.y;
-    } else {
-      const float4 v = *reinterpret_cast<const float4*>(xp);
-      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-    }
+    if constexpr (RT == 2) { x[0] = v.x; x[1] = v.y; }
+    else { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       acc[r][0] = fmaf(x[r], w.x, acc[r][0]);
@@ -249,7 +245,10 @@ __device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, c
     }
   }
 }
-
+template <int RT>
+__device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, const float* xp) {
+  fma_row<RT>(acc, w, *reinterpret_cast<const typename XVec<RT>::T*>(xp));
+}
 struct Ctx {                 // per-CTA constants shared by both roles
   int s, prev, part, G, B;
   float* smem;
@@ -360,6 +359,8 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
       } else {
         mbar_wait(&c.curfull[q], par, p.abort_flag);
         PROF_G(2);
+        // (Tried: the X rows of the 1x1 stages fetched as batches ahead of straight-line FMAs instead of row by row
+        // under the row-count predicate: B = 64 49.4 -> 48.3 us/frame, but B = 1 29.4 -> 30.2 and B = 128 89.5 -> 95.3.)
 #pragma unroll
         for (int j = 0; j < 22; ++j)
           if (j < st.nj) fma_tile<RT>(acc, w[j], X + (size_t)(KS * j) * XS);
@@ -434,7 +435,7 @@ __device__ __forceinline__ void row_reduce(float& a, float& b, float& c3, bool& 
   warp_sum2(a, b);
   c3 = warp_sum(c3);
   if (WPR > 1) {
-    float4* slot = reinterpret_cast<float4*>(red) + round * 8;
+    float4* slot = reinterpret_cast<float4*>(red) + round * (2 * MAX_FEW);
     if (lane == 0) slot[2 * warp] = make_float4(a, b, c3, bad ? 1.f : 0.f);
     named_bar(barid, WPR * 32);
     float sa = 0.f, sb = 0.f, sc = 0.f, sf = 0.f;
@@ -455,7 +456,7 @@ __device__ __forceinline__ void row_stats2(float& s1, float& m1, float& s2, floa
   warp_stats2<N0>(s1, m1, s2, m2);
   if (WPR > 1) {
     constexpr int CW = HD / WPR;
-    float4* slot = reinterpret_cast<float4*>(red) + round * 8;
+    float4* slot = reinterpret_cast<float4*>(red) + round * (2 * MAX_FEW);
     if (lane == 0) {
       slot[2 * warp] = make_float4(s1, m1, s2, m2);
       slot[2 * warp + 1] = make_float4(bad ? 1.f : 0.f, 0.f, 0.f, 0.f);
@@ -483,9 +484,9 @@ __device__ __forceinline__ void row_stats2(float& s1, float& m1, float& s2, floa
   }
 }
 
-template <int RT, int WPR, bool PROF>
+template <int RT, int WPR, int FEW, bool PROF>
 __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st, const Ctx& c, int tid) {
-  constexpr int NV = 4 / (RT * WPR);        // micro-batches in flight in the front end (visit slots)
+  constexpr int NV = FEW / (RT * WPR);      // micro-batches in flight in the front end (visit slots)
   constexpr int NP = 4 / WPR;               // channel pairs per lane
   constexpr int CW = HD / WPR;              // channels per warp
   constexpr int NBUF = ws_nbuf(RT);
@@ -524,7 +525,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 
   // LayerNorm parameters of my channels (fixed for the whole launch): in registers when a lane owns 2 or 4
   // channels; with 8 channels per lane (W = 1) 32 more live registers spill, so they stay in shared memory
-  constexpr bool LNREG = NP <= 2;
+  constexpr bool LNREG = NP <= 2 && FEW == 4;      // eight front-end warps run on 56-72 registers (setmaxnreg)
   float2 G1[NP], B1[NP], G2[NP], B2[NP];
   if (LNREG) {
 #pragma unroll
@@ -913,8 +914,20 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 #undef PROF_F
 }
 
-template <int RT, int WPR, bool PROF>
-__global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
+// Register budget with eight front-end warps: 640 threads x 96 registers at launch is the CTA's pool for good
+// (setmaxnreg moves registers between the warpgroups of a CTA, it cannot take more from the SM).  The two front-end
+// warpgroups give registers back and the three mat-vec warpgroups, whose threads keep 88 weights each, take them:
+// 256 x 72 + 384 x 112 = 61440 for one- and two-row micro-batches (no spills in either role with two or four warps
+// per row); four-row micro-batches need 16 accumulators per mat-vec thread: 256 x 56 + 384 x 120 = 60416.
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int RT> struct Regs8 { static constexpr int FE = RT == 4 ? 56 : 72, MV = RT == 4 ? 120 : 112; };
+static_assert(256 * Regs8<1>::FE + 384 * Regs8<1>::MV <= 640 * 96 && 256 * Regs8<4>::FE + 384 * Regs8<4>::MV <= 640 * 96, "register pool");
+
+template <int RT, int WPR, int FEW, bool PROF>
+__global__ void __launch_bounds__(GV_T + 32 * FEW, 1) decode_ws_kernel(const DecParams p) {
+  constexpr int NT = GV_T + 32 * FEW;
+  constexpr int FE_T = 32 * FEW;
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t bars[3 * MAXBUF + 6];
   __shared__ int s_bad;
@@ -992,14 +1005,16 @@ __global__ void __launch_bounds__(NT, 1) decode_ws_kernel(const DecParams p) {
     __syncthreads();
   }
 
-  // Warps 0-3 are the front end, warps 4-15 the mat-vec.  (Tried: the front end as the four HIGHEST warps, which the
-  // issue arbiter is said to prefer -- 3-4 % slower at every batch size: B = 1 31.3 -> 32.4, B = 64 50.1 -> 51.9,
-  // B = 128 93.3 -> 97.8 us/frame.)
+  // The first FEW warps are the front end, the 12 after them the mat-vec.  (Tried: the front end as the HIGHEST
+  // warps, which the issue arbiter is said to prefer -- 3-4 % slower at every batch size: B = 1 31.3 -> 32.4,
+  // B = 64 50.1 -> 51.9, B = 128 93.3 -> 97.8 us/frame.)
   const bool is_fe = tid < FE_T;
   const int rtid = is_fe ? tid : tid - FE_T;
   if (is_fe) {
-    front_role<RT, WPR, PROF>(p, st, c, rtid);
+    if constexpr (FEW == 8) reg_dec<Regs8<RT>::FE>();
+    front_role<RT, WPR, FEW, PROF>(p, st, c, rtid);
   } else {
+    if constexpr (FEW == 8) reg_inc<Regs8<RT>::MV>();
     const int gtid = rtid;
     if (st.hwy) gemv_role<RT, 16, true, PROF>(p, st, c, gtid);
     else if (st.cg == 16) gemv_role<RT, 16, false, PROF>(p, st, c, gtid);
@@ -1034,24 +1049,24 @@ __global__ void ws_pack_image_kernel(const float* __restrict__ W, WsStage w, flo
   }
 }
 
-template <int RT, int WPR, bool PROF>
+template <int RT, int WPR, int FEW, bool PROF>
 int launch_cfg(const DecParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)SM_TOTAL * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT, WPR, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSV_CUDA(cudaFuncSetAttribute(decode_ws_kernel<RT, WPR, FEW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   DecParams pl = p;
   void* args[] = {&pl};
-  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT, WPR, PROF>, dim3(WS_GRID), dim3(NT), args, smem, s));
+  SSV_CUDA(cudaLaunchCooperativeKernel((void*)decode_ws_kernel<RT, WPR, FEW, PROF>, dim3(WS_GRID), dim3(GV_T + 32 * FEW), args, smem, s));
   ++g_launches;
   return kOk;
 }
 
-template <int RT, int WPR>
+template <int RT, int WPR, int FEW>
 int launch_prof(const DecParams& p, cudaStream_t s) {
-  return p.prof ? launch_cfg<RT, WPR, true>(p, s) : launch_cfg<RT, WPR, false>(p, s);
+  return p.prof ? launch_cfg<RT, WPR, FEW, true>(p, s) : launch_cfg<RT, WPR, FEW, false>(p, s);
 }
 
 }  // namespace
@@ -1089,19 +1104,25 @@ int ws_pack_image(const float* W_rowmajor, const WsStage& w, float* dst, cudaStr
 // Shape of the front end for a batch: rows per micro-batch R, warps per row W (4 / (R W) micro-batches in flight in
 // the front end), micro-batch count G (padded to a multiple of the in-flight count; padding rows are dead).
 // Measured on B200 (us/frame).
-void ws_plan(int B, int force_r, int force_w, int* R, int* W, int* G) {
-  int r, w;
+void ws_plan(int B, int force_r, int force_w, int force_f, int* R, int* W, int* F, int* G) {
+  int r, w, f = 4;
   if (B <= 12) { r = 1; w = 4; }           // B=1 28.3 us/frame, B=12 28.9 (W=2: 30.1)
   else if (B <= 32) { r = 1; w = 2; }      // B=16 30.5 (W=4: 32.7), B=24 31.8, B=32 37.1 (R=2 W=2: 39.3, W=1: 38.8)
   else if (B <= 128) { r = 2; w = 1; }     // B=40 45.1 (R=1: 46.6), B=48 47.4 (R=1: 56.5), B=64 51.7 (R=1 75.7, R=4 59), B=128 104
-  else { r = 4; w = 1; }                   // B=256 220
-  if (force_r == 1 || force_r == 2 || force_r == 4) { r = force_r; if (r * w > 4) w = 4 / r; }      // ssv_decoder_set_plan
-  if ((force_w == 1 || force_w == 2 || force_w == 4) && r * force_w <= 4) w = force_w;
+  else { r = 4; w = 1; f = 8; }            // B=256: 178-183 with eight front-end warps (two visit slots), 192 with four
+  // Eight front-end warps (round 2): only the four-row shape gains.  B=64: R=2 W=2 F=8 51.2, R=2 W=1 F=8 (four slots)
+  // 72.7, R=4 W=1 F=8 88.1, R=4 W=2 F=8 68.9 against 49.4; B=128: 99.9 / 130.8 / 100.4 / 100.2 against 89.5; B=1: 33.1
+  // against 29.4; B=16: 34.8 against 31.1 -- the mat-vec warps lose 16 registers each and four more warps compete for
+  // the issue slots, and the front end was not the limiter (profiles/r2_decode_ws_fe8.md).
+  if (force_f == 4 || force_f == 8) f = force_f;                                                     // ssv_decoder_set_plan
+  if (force_r == 1 || force_r == 2 || force_r == 4) { r = force_r; if (r * w > f) w = f / r; }
+  if ((force_w == 1 || force_w == 2 || force_w == 4) && r * force_w <= f) w = force_w;
   if (w * B > WS_MAX_BATCH) w = 1;
-  const int nv = 4 / (r * w);
+  if (f == 8 && r * w == 1) w = 2;         // eight one-warp visit slots would need more X buffers than there are
+  const int nv = f / (r * w);
   int g = (B + r - 1) / r;
   g = (g + nv - 1) / nv * nv;
-  *R = r; *W = w; *G = g;
+  *R = r; *W = w; *F = f; *G = g;
 }
 
 bool decode_ws_supported(int sm_count) {
@@ -1126,18 +1147,26 @@ int launch_decode_ws(const DecParams& p, cudaStream_t s) {
   SSV_CHECK(p.ws_stages && p.ws_raw && p.ws_hist, "decode: weight-stationary buffers missing");
   SSV_CHECK(p.R == 1 || p.R == 2 || p.R == 4, "decode: micro-batch rows must be 1, 2 or 4");
   SSV_CHECK(p.W == 1 || p.W == 2 || p.W == 4, "decode: warps per row must be 1, 2 or 4");
-  SSV_CHECK(p.R * p.W <= 4 && p.G % (4 / (p.R * p.W)) == 0, "decode: micro-batch count %d does not fit %d x %d front-end warps", p.G, p.R, p.W);
+  SSV_CHECK(p.FEW == 4 || p.FEW == 8, "decode: front-end warps must be 4 or 8");
+  SSV_CHECK(p.R * p.W <= p.FEW && p.G % (p.FEW / (p.R * p.W)) == 0, "decode: micro-batch count %d does not fit %d x %d of %d front-end warps", p.G, p.R, p.W, p.FEW);
   SSV_CHECK(p.W * p.B <= WS_MAX_BATCH, "decode: per-warp alignment state does not fit");
-  switch (p.R * 8 + p.W) {
-    case 1 * 8 + 1: return launch_prof<1, 1>(p, s);
-    case 1 * 8 + 2: return launch_prof<1, 2>(p, s);
-    case 1 * 8 + 4: return launch_prof<1, 4>(p, s);
-    case 2 * 8 + 1: return launch_prof<2, 1>(p, s);
-    case 2 * 8 + 2: return launch_prof<2, 2>(p, s);
-    case 4 * 8 + 1: return launch_prof<4, 1>(p, s);
+  switch (p.FEW * 64 + p.R * 8 + p.W) {
+    case 4 * 64 + 1 * 8 + 1: return launch_prof<1, 1, 4>(p, s);
+    case 4 * 64 + 1 * 8 + 2: return launch_prof<1, 2, 4>(p, s);
+    case 4 * 64 + 1 * 8 + 4: return launch_prof<1, 4, 4>(p, s);
+    case 4 * 64 + 2 * 8 + 1: return launch_prof<2, 1, 4>(p, s);
+    case 4 * 64 + 2 * 8 + 2: return launch_prof<2, 2, 4>(p, s);
+    case 4 * 64 + 4 * 8 + 1: return launch_prof<4, 1, 4>(p, s);
+    case 8 * 64 + 1 * 8 + 2: return launch_prof<1, 2, 8>(p, s);
+    case 8 * 64 + 1 * 8 + 4: return launch_prof<1, 4, 8>(p, s);
+    case 8 * 64 + 2 * 8 + 1: return launch_prof<2, 1, 8>(p, s);
+    case 8 * 64 + 2 * 8 + 2: return launch_prof<2, 2, 8>(p, s);
+    case 8 * 64 + 2 * 8 + 4: return launch_prof<2, 4, 8>(p, s);
+    case 8 * 64 + 4 * 8 + 1: return launch_prof<4, 1, 8>(p, s);
+    case 8 * 64 + 4 * 8 + 2: return launch_prof<4, 2, 8>(p, s);
     default: break;
   }
-  set_error("decode: unsupported front-end shape R=%d W=%d", p.R, p.W);
+  set_error("decode: unsupported front-end shape R=%d W=%d F=%d", p.R, p.W, p.FEW);
   return kInval;
 }
 

@@ -213,8 +213,9 @@ class melSyn(_Native):
             conv4=pw(h, h), ln4=nn.LayerNorm(h), conv5=pw(h, freq_bins), ln5=nn.LayerNorm(freq_bins))
         self.precision = "fp32"
         self.max_frames = 1024      # decoder capacity (reference MAX_FRAME_NUM is 325)
-        self.decode_plan = None     # (rows per micro-batch, warps per row) override of the decode kernel's front-end
-                                    # shape, None / 0 = measured choice (ssv_decoder_set_plan; tuning and tests)
+        self.decode_plan = None     # (rows per micro-batch, warps per row[, front-end warps per CTA]) override of the
+                                    # decode kernel's front-end shape, None / 0 = measured choice
+                                    # (ssv_decoder_set_plan; tuning and tests)
         self._dec: Optional[int] = None
         self._dec_cap = (0, 0, 0)
         self._state = None
@@ -249,8 +250,8 @@ class melSyn(_Native):
             out = C.c_void_p()
             _lib.check(_lib.load().ssv_decoder_create(h, *cap, C.byref(out)))
             self._dec, self._dec_cap = out.value, cap
-        r, w = self.decode_plan or (0, 0)
-        _lib.check(_lib.load().ssv_decoder_set_plan(C.c_void_p(self._dec), int(r or 0), int(w or 0)))
+        r, w, f = (tuple(self.decode_plan or ()) + (0, 0, 0))[:3]
+        _lib.check(_lib.load().ssv_decoder_set_plan(C.c_void_p(self._dec), int(r or 0), int(w or 0), int(f or 0)))
         return C.c_void_p(self._dec)
 
     # ---- pieces --------------------------------------------------------------------------

@@ -232,19 +232,22 @@ def test_decode_batch_sizes_vs_oracle(B, cuda_models):
     assert _maxabs(Y, oY) <= FP32_TOL and _maxabs(A, oA) <= FP32_TOL
 
 
-@pytest.mark.parametrize("B,R,Wp", [(3, 2, None), (5, 4, None), (7, 1, None), (41, None, None), (67, 4, None),
-                                    (130, None, None), (9, 1, 1), (6, 1, 2), (26, None, None), (13, 2, 1), (21, 1, 4)])
-def test_decode_micro_batch_shapes_vs_oracle(B, R, Wp, cuda_models):
-    """Weight-stationary pipeline, every front-end shape: rows per micro-batch R = 1 / 2 / 4 and warps per row
-    W = 1 / 2 / 4 (forced through ssv_decoder_set_plan and chosen by ws_plan), 4 / (R W) micro-batches in flight,
-    ragged last micro-batch, micro-batch count padded to the in-flight count (dead micro-batches), more
-    micro-batches than pipeline stages."""
+@pytest.mark.parametrize("B,R,Wp,F", [(3, 2, None, None), (5, 4, None, None), (7, 1, None, None), (41, None, None, None),
+                                      (67, 4, None, None), (130, None, None, None), (9, 1, 1, None), (6, 1, 2, None),
+                                      (26, None, None, None), (13, 2, 1, None), (21, 1, 4, None),
+                                      (1, 1, 4, 8), (7, 1, 2, 8), (9, 2, 1, 8), (5, 2, 2, 8), (3, 2, 4, 8), (6, 4, 1, 8),
+                                      (9, 4, 2, 8), (67, 2, 2, 8), (131, 4, 2, 8), (70, 2, 1, 8)])
+def test_decode_micro_batch_shapes_vs_oracle(B, R, Wp, F, cuda_models):
+    """Weight-stationary pipeline, every front-end shape: rows per micro-batch R = 1 / 2 / 4, warps per row
+    W = 1 / 2 / 4 and F = 4 / 8 front-end warps per CTA (forced through ssv_decoder_set_plan and chosen by ws_plan),
+    F / (R W) micro-batches in flight, ragged last micro-batch, micro-batch count padded to the in-flight count
+    (dead micro-batches), more micro-batches than pipeline stages."""
     m1, _, sd1, _ = cuda_models
     names, emb, _ = W.load_fixtures()
     ids = W.synthetic_text(B, 40, seed=100 + B)
     spk = torch.from_numpy(emb[[i % len(emb) for i in range(B)]].copy())[:, :, None]
     T = 64 if B <= 9 else 12           # small batches: long enough for the dilation-27 taps to leave the zero region
-    m1.decode_plan = (R or 0, Wp or 0)
+    m1.decode_plan = (R or 0, Wp or 0, F or 0)
     try:
         Y, A, traj, _, _ = m1.synthesize(ids.cuda(), spk.cuda(), T)
     finally:

@@ -9,10 +9,10 @@ m1, _ = W.build_models(0); m1 = m1.cuda()
 names, emb, _ = W.load_fixtures()
 lib = _lib.load()
 T = 217
-# arguments: batch sizes; "B:R:W" forces the front-end shape (ssv_decoder_set_plan)
+# arguments: batch sizes; "B:R:W[:F]" forces the front-end shape (ssv_decoder_set_plan)
 for arg in sys.argv[1:] or ["1", "64"]:
-    B, R, Wp = ([int(x) for x in arg.split(":")] + [0, 0])[:3]
-    m1.decode_plan = (R, Wp) if (R or Wp) else None
+    B, R, Wp, F = ([int(x) for x in arg.split(":")] + [0, 0, 0])[:4]
+    m1.decode_plan = (R, Wp, F) if (R or Wp or F) else None
     ids = W.synthetic_text(B, 58, seed=11).cuda()
     spk = torch.from_numpy(emb[[i % len(emb) for i in range(B)]].copy())[:, :, None].cuda()
     K, V = m1.encode_text(ids)
@@ -23,4 +23,4 @@ for arg in sys.argv[1:] or ["1", "64"]:
         e0.record(); _lib.check(lib.ssv_decoder_run(dec, T, _lib.current_stream_ptr())); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     m1.check()
-    print(f"B={B:4d} plan R={R} W={Wp} decode {best:8.3f} ms  {1e3 * best / T:7.1f} us/frame  {B * T / best * 1e3:12.0f} frames/s", flush=True)
+    print(f"B={B:4d} plan R={R} W={Wp} F={F} decode {best:8.3f} ms  {1e3 * best / T:7.1f} us/frame  {B * T / best * 1e3:12.0f} frames/s", flush=True)
