@@ -353,7 +353,7 @@ struct ssv_decoder {
   long long* h_traj = nullptr;
   cudaStream_t copy_stream = nullptr;     // D2H of finished SSRN chunks
   cudaEvent_t copy_ev[2] = {nullptr, nullptr}, done_ev[2] = {nullptr, nullptr}, lin_ev[2] = {nullptr, nullptr};
-  int* h_flags = nullptr;                 // pinned: {decode abort, bad text id} per slot
+  int* h_flags = nullptr;                 // pinned: {decode abort, bad text id, three tensor-core pipeline timeouts} per slot
   bool inflight[2] = {false, false}, slot_bf16[2] = {false, false};
   cudaStream_t slot_stream[2] = {nullptr, nullptr};
   ~ssv_decoder() {
@@ -1313,7 +1313,8 @@ static int synth_enqueue(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const in
       SSV_CUDA(cudaEventCreateWithFlags(&d->done_ev[i], cudaEventDisableTiming));
       SSV_CUDA(cudaEventCreateWithFlags(&d->lin_ev[i], cudaEventDisableTiming));
     }
-    SSV_CUDA(cudaHostAlloc((void**)&d->h_flags, sizeof(int) * 4, cudaHostAllocDefault));
+    SSV_CUDA(cudaHostAlloc((void**)&d->h_flags, sizeof(int) * 16, cudaHostAllocDefault));
+    memset(d->h_flags, 0, sizeof(int) * 16);
   }
   float* lin_dev = d->h_lin[slot];
   SSV_CUDA(cudaMemcpyAsync(d->h_textid, textid_host, sizeof(int64_t) * B * N, cudaMemcpyHostToDevice, s));
@@ -1353,8 +1354,18 @@ static int synth_enqueue(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const in
   if (pma_traj_host)
     SSV_CUDA(cudaMemcpyAsync(pma_traj_host, d->h_traj, sizeof(long long) * (size_t)T * B, cudaMemcpyDeviceToHost, s));
   // error flags of this batch (decode abort, bad text id) -> pinned host words, read by the wait
-  SSV_CUDA(cudaMemcpyAsync(d->h_flags + 2 * slot, d->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  SSV_CUDA(cudaMemcpyAsync(d->h_flags + 2 * slot + 1, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot, d->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot + 1, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  {
+    // pipeline-timeout flags of the tensor-core kernels: fetched in stream order like the others.  (They used to be read
+    // in the wait with a synchronous cudaMemcpy, which -- on the legacy default stream -- also waited for the NEXT batch
+    // already in flight: the submit / wait pair then never had two batches overlapping, 0.7 ms per step at B = 64.)
+    int* tcf[3] = {tc_err_flag_dev(), tc2_err_flag_dev(), tf32_err_flag_dev()};
+    for (int i = 0; i < 3; ++i) {
+      d->h_flags[8 * slot + 2 + i] = 0;
+      if (tcf[i]) SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot + 2 + i, tcf[i], sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+  }
   SSV_CUDA(cudaEventRecord(d->done_ev[slot], s));
   d->inflight[slot] = true;
   d->slot_bf16[slot] = ssrn_precision == SSV_PREC_BF16;
@@ -1367,7 +1378,7 @@ static int synth_wait(ssv_decoder* d, int slot) {
   d->inflight[slot] = false;
   SSV_CUDA(cudaEventSynchronize(d->done_ev[slot]));
   SSV_CUDA(cudaEventSynchronize(d->lin_ev[slot]));
-  const int abort_code = d->h_flags[2 * slot], bad_id = d->h_flags[2 * slot + 1];
+  const int abort_code = d->h_flags[8 * slot], bad_id = d->h_flags[8 * slot + 1];
   if (abort_code != 0) {
     set_error("decode kernel aborted (hand-off timeout, code %d)", abort_code);
     cudaMemsetAsync(d->abort_flag, 0, sizeof(int), d->slot_stream[slot]);
@@ -1378,10 +1389,10 @@ static int synth_wait(ssv_decoder* d, int slot) {
     cudaMemsetAsync(d->m->err_flag, 0, sizeof(int), d->slot_stream[slot]);
     return kInval;
   }
-  if (d->slot_bf16[slot]) {
-    SSV_TRY(tc_check_error());
-    SSV_TRY(tc2_check_error());
-  }
+  // a tensor-core pipeline timed out: the synchronous check reads the flag again, reports and clears it
+  if (d->h_flags[8 * slot + 2] != 0) SSV_TRY(tc_check_error());
+  if (d->h_flags[8 * slot + 3] != 0) SSV_TRY(tc2_check_error());
+  if (d->h_flags[8 * slot + 4] != 0) SSV_TRY(tf32_check_error());
   return kOk;
 }
 

@@ -717,6 +717,8 @@ int launch_cast_bf16_to_f32(const __nv_bfloat16* src, float* dst, size_t n, cuda
   return kOk;
 }
 
+int* tc_err_flag_dev() { return tc_err_flag(); }
+
 int tc_check_error() {
   int* flag = tc_err_flag();
   if (!flag) return kOk;

@@ -55,6 +55,7 @@ int tc_pack_deconv(const float* w /*[cin][cout][2]*/, int cin, int cout, __nv_bf
 int tc_launch(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloat16* X, int x_ld, int T, int B,
               void* Y, int y_ld, bool out_fp32, cudaStream_t s);
 int tc_check_error();   // synchronous: reads and clears the device-side timeout flag
+int* tc_err_flag_dev();  // the flag itself (device word), for callers that fetch it with their own asynchronous copy
 
 // ---- second-generation BF16 kernel (conv_tc2.cu): 256 accumulator columns per CTA, two CTAs per SM, N split over a
 // cluster of 1 / 2 / 4 CTAs; highway (d = 256, 512), LayerNorm (+ReLU) and plain (ConvTranspose1d) layers with 256 or 512
@@ -69,6 +70,7 @@ int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloa
                 __nv_bfloat16* Y, int y_ld, Tc2Launch* out);
 int tc2_run(const Tc2Launch& L, cudaStream_t s);
 int tc2_check_error();
+int* tc2_err_flag_dev();
 int launch_transpose_in_bf16(const float* src, long sb, long sc, long st, int B, int C, int T,
                              __nv_bfloat16* dst, int ld, cudaStream_t s);
 int launch_cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s);

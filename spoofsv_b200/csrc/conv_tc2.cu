@@ -426,6 +426,8 @@ int tc2_run(const Tc2Launch& L, cudaStream_t s) {
   return kOk;
 }
 
+int* tc2_err_flag_dev() { return v2_err_flag(); }
+
 int tc2_check_error() {
   int* flag = v2_err_flag();
   if (!flag) return kOk;

@@ -464,6 +464,8 @@ int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream
   return kOk;
 }
 
+int* tf32_err_flag_dev() { return tf32_err_flag(); }
+
 int tf32_check_error() {
   int* flag = tf32_err_flag();
   if (!flag) return kOk;

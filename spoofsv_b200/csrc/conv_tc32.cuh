@@ -62,5 +62,6 @@ int tf32_run(const Tf32Launch& L, cudaStream_t s);
 int tf32_launch(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
                 float* Yh, float* Yl, int y_ld, cudaStream_t s);    // prepare + run
 int tf32_check_error();
+int* tf32_err_flag_dev();
 
 }  // namespace ssv

@@ -1008,6 +1008,8 @@ __global__ void __launch_bounds__(GV_T + 32 * FEW, 1) decode_ws_kernel(const Dec
   // The first FEW warps are the front end, the 12 after them the mat-vec.  (Tried: the front end as the HIGHEST
   // warps, which the issue arbiter is said to prefer -- 3-4 % slower at every batch size: B = 1 31.3 -> 32.4,
   // B = 64 50.1 -> 51.9, B = 128 93.3 -> 97.8 us/frame.)
+  // (Tried: the four front-end warps on one scheduler (warps 0, 4, 8, 12), the mat-vec warps on the other three:
+  // B = 16 31.1 -> 34.8, B = 64 49.4 -> 51.0, B = 128 89.5 -> 98.1 us/frame.)
   const bool is_fe = tid < FE_T;
   const int rtid = is_fe ? tid : tid - FE_T;
   if (is_fe) {
