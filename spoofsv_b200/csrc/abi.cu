@@ -332,6 +332,7 @@ struct ssv_decoder {
   int* pma_state;
   int* abort_flag;
   long long* prof = nullptr;
+  long long* totals = nullptr;
   unsigned long long* ws_raw = nullptr;
   float* ws_hist = nullptr;
   float* ws_zero = nullptr;
@@ -914,6 +915,7 @@ int ssv_decoder_create(ssv_text2mel* m, int max_batch, int max_text, int max_fra
   if (st == kOk) st = d->arena.alloc<int>(max_batch, &d->pma_state);
   if (st == kOk) st = d->arena.alloc<int>(1, &d->abort_flag);
   if (st == kOk && getenv("SSV_DECODE_PROF")) st = d->arena.alloc<long long>((size_t)DEC_MAX_GRID * 16, &d->prof);
+  if (st == kOk && !d->prof && getenv("SSV_DECODE_TOTALS")) st = d->arena.alloc<long long>((size_t)DEC_MAX_GRID * 4, &d->totals);
   if (st != kOk) { delete d; return st; }
   cudaMemset(d->abort_flag, 0, sizeof(int));
   *out = d;
@@ -976,11 +978,26 @@ static int decoder_launch(ssv_decoder* d, int n_steps, const float* x_ext, long 
   p.t_start = d->t; p.n_steps = n_steps;
   p.abort_flag = d->abort_flag;
   p.prof = d->prof;
+  p.totals = d->totals;
   p.ws_stages = m->ws_stages_dev;
   p.ws_raw = d->ws_raw; p.ws_hist = d->ws_hist; p.ws_zero = d->ws_zero;
   p.seq_base = d->seq_base; p.R = d->R; p.G = d->G; p.W = d->W; p.FEW = d->F;
   if (d->prof) SSV_CUDA(cudaMemsetAsync(d->prof, 0, sizeof(long long) * DEC_MAX_GRID * 16, s));
   SSV_TRY(launch_decode_ws(p, s));
+  if (d->totals) {   // development aid: cycles per stage visit of each role, from the un-instrumented kernel
+    SSV_CUDA(cudaStreamSynchronize(s));
+    std::vector<long long> h((size_t)DEC_MAX_GRID * 4);
+    SSV_CUDA(cudaMemcpy(h.data(), d->totals, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    const double visits = (double)n_steps * d->G;
+    fprintf(stderr, "[decode totals] B=%d R=%d W=%d F=%d G=%d steps=%d: cycles per visit, mean over the stage's CTAs\n  stage ctas |  front end  (waiting) |  mat-vec  (waiting)\n", d->B, d->R, d->W, d->F, d->G, n_steps);
+    for (int sidx = 0; sidx < DEC_STAGES; ++sidx) {
+      const WsStage& w = m->ws_stages[sidx];
+      double a[4] = {0, 0, 0, 0};
+      for (int c = w.cta0; c < w.cta0 + w.parts; ++c)
+        for (int i = 0; i < 4; ++i) a[i] += (double)h[(size_t)c * 4 + i] / visits / w.parts;
+      fprintf(stderr, "  %5d %4d | %10.0f %10.0f | %8.0f %10.0f\n", sidx, w.parts, a[0], a[1], a[2], a[3]);
+    }
+  }
   if (d->prof) {   // development aid: per-phase SM cycles, mean / max over CTAs, per stage visit
     SSV_CUDA(cudaStreamSynchronize(s));
     const bool ws = true;

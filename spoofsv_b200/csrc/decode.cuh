@@ -70,6 +70,8 @@ struct DecParams {
   int t_start, n_steps;
   int* abort_flag;
   long long* prof;              // optional [grid][16] phase cycle counters (SSV_DECODE_PROF=1)
+  long long* totals;            // optional [grid][4]: SM cycles each role of a CTA spent in the launch, and the cycles of
+                                // those it spent waiting for other CTAs / the other role (SSV_DECODE_TOTALS=1; un-instrumented kernel)
   const WsStage* ws_stages;     // device [DEC_STAGES]
   unsigned long long* ws_raw;   // [DEC_STAGES][B][WS_WORDS] tagged words {float, tag}
   float* ws_hist;               // private input-history rings: entries [256][XS] (X's own layout), [blocks][G] of them

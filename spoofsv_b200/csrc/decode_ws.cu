@@ -53,15 +53,37 @@ constexpr int HD = 256;
 constexpr int TAPP = WS_TAP_ROWS;        // rows of one tap in X (256 padded to a multiple of 24)
 constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks
 constexpr unsigned FULL = 0xffffffffu;
+// timing-only knock-outs (wrong values): free-running stages, gutted roles
+#ifdef SSV_KO_NOPOLL
+constexpr bool KO_NOPOLL = true;
+#else
+constexpr bool KO_NOPOLL = false;
+#endif
+#ifdef SSV_KO_NOFE
+constexpr bool KO_NOFE = true;
+#else
+constexpr bool KO_NOFE = false;
+#endif
+#ifdef SSV_KO_NOMV
+constexpr bool KO_NOMV = true;
+#else
+constexpr bool KO_NOMV = false;
+#endif
+
+// floats per stored activation in an X buffer: 2 = the pair (x, x), the multiplicand of a packed FMA (fma.rn.f32x2)
+// (two-row micro-batches in the packed form, X rows (x0, x0, x1, x1): the mat-vec role alone runs 10 % slower, 45.8 vs
+// 41.4 us per frame at B = 64 -- the packed FMA issues at less than half the rate of the scalar one)
+template <int RT> struct XLayout { static constexpr int D = RT == 1 ? 2 : 1; };
 
 // shared-memory carve-up (floats)
 constexpr int XROWS = 3 * TAPP;                    // rows of one X buffer ([rows][RT] activations; RT = 1 stores each as (x, x))
 constexpr int XREGION = 2 * 8 * XROWS;             // floats; ws_nbuf(RT) buffers of XROWS rows x (2 or 4) floats
 constexpr int MAXBUF = 8;
 // X buffers per shape: 8 (one- and two-row micro-batches, 2 floats per X row) or 4 (four rows)
-__host__ __device__ constexpr int ws_nbuf(int rt) { return rt == 4 ? 4 : 8; }
-constexpr int SM_WSM = 0;                          // [11][384] float4: tap-0 weights of a highway CTA
-constexpr int SM_X = SM_WSM + 11 * GV_T * 4;       // [8 / RT][XROWS][RT * XLayout<RT>::D]
+__host__ __device__ constexpr int ws_nbuf(int rt) { return rt * (rt == 1 ? XLayout<1>::D : rt == 2 ? XLayout<2>::D : XLayout<4>::D) >= 4 ? 4 : 8; }
+constexpr int WSM_TILES = 15;                      // k rows of weights a mat-vec thread may keep in shared memory
+constexpr int SM_WSM = 0;                          // [<= 15][384] float4: the weight rows that do not fit the registers
+constexpr int SM_X = SM_WSM + WSM_TILES * GV_T * 4;       // [8 / RT][XROWS][RT * XLayout<RT>::D]
 constexpr int SM_PART = SM_X + XREGION;            // [12][RT][ncol <= 128] k-slice partial sums
 constexpr int SM_LN = SM_PART + 12 * 4 * 128;      // [4][256] LayerNorm parameters of my prologue
 constexpr int SM_BIAS = SM_LN + 4 * HD;            // [128] bias of my columns
@@ -81,12 +103,18 @@ __device__ __forceinline__ void st_word2(Word* p, float v0, float v1, int tag) {
                : "memory");
 }
 __device__ __forceinline__ void ld_word(const Word* p, float& v, int& tag) {
+#ifdef SSV_KO_NOLOAD
+  v = 0.25f; tag = 0; return;
+#endif
   int a, b;
   asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
   v = __int_as_float(a);
   tag = b;
 }
 __device__ __forceinline__ void ld_word2(const Word* p, float& v0, int& t0, float& v1, int& t1) {   // 16-byte aligned
+#ifdef SSV_KO_NOLOAD
+  v0 = 0.25f; v1 = 0.5f; t0 = t1 = 0; return;
+#endif
   int a, b, c, d;
   asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
   v0 = __int_as_float(a); t0 = b; v1 = __int_as_float(c); t1 = d;
@@ -120,7 +148,11 @@ __device__ __forceinline__ void bulk_wait_prev_written_last_read() {
   asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+#ifdef SSV_KO_NOFENCE
+__device__ __forceinline__ void fence_proxy_async_smem() {}
+#else
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -210,8 +242,13 @@ __device__ __forceinline__ void warp_stats1(float& s1, float& m1) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 // Highway gate / LayerNorm scale on the frame's critical path: MUFU-based, branch-free (2 ulp), so the eight
 // per-lane chains interleave instead of serialising on the slow-path calls of IEEE division / sqrt.
+#ifdef SSV_KO_NOGATE
+__device__ __forceinline__ float sigmoid_fast(float x) { return 0.5f * x; }
+__device__ __forceinline__ float rstd_fast(float var) { return var + 1e-5f; }
+#else
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float rstd_fast(float var) { return rsqrtf(var + 1e-5f); }
+#endif
 
 // One k row of the mat-vec tile: acc[r][0..3] += x[r] * w[0..3] for the RT rows of the micro-batch.
 // RT = 1 (latency mode) uses packed FMAs (fma.rn.f32x2: two independent IEEE fp32 FMAs per instruction,
@@ -220,10 +257,10 @@ __device__ __forceinline__ float rstd_fast(float var) { return rsqrtf(var + 1e-5
 // per row instead of 4 + 1.  Measured: B = 1 30.0 -> 28.9 us/frame.  With 2 or 4 rows per micro-batch the mat-vec
 // phases are bound by the FMA pipe, where the packed form is ~9 % slower than scalar FFMA (B = 64: 53.7 -> 58
 // us/frame), so those shapes keep scalar FMAs and the plain X layout.
-template <int RT> struct XLayout { static constexpr int D = RT == 1 ? 2 : 1; };   // floats per stored activation
 
-template <int RT> struct XVec { using T = float2; };          // one X row: (x, x) | (x0, x1) | (x0, x1, x2, x3)
-template <> struct XVec<4> { using T = float4; };
+template <int XS> struct XVecN { using T = float2; };         // one X row: (x, x) | (x0, x1) | (x0, x0, x1, x1) | (x0, x1, x2, x3)
+template <> struct XVecN<4> { using T = float4; };
+template <int RT> struct XVec { using T = typename XVecN<RT * XLayout<RT>::D>::T; };
 
 template <int RT>
 __device__ __forceinline__ void fma_row(float (&acc)[RT][4], const float4& w, const typename XVec<RT>::T& v) {
@@ -232,6 +269,15 @@ __device__ __forceinline__ void fma_row(float (&acc)[RT][4], const float4& w, co
     a01 = __ffma2_rn(v, make_float2(w.x, w.y), a01);
     a23 = __ffma2_rn(v, make_float2(w.z, w.w), a23);
     acc[0][0] = a01.x; acc[0][1] = a01.y; acc[0][2] = a23.x; acc[0][3] = a23.y;
+  } else if constexpr (RT == 2 && XLayout<RT>::D == 2) {
+    const float2 x0 = make_float2(v.x, v.y), x1 = make_float2(v.z, v.w);
+    const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+    float2 a = make_float2(acc[0][0], acc[0][1]), b = make_float2(acc[0][2], acc[0][3]);
+    float2 c = make_float2(acc[1][0], acc[1][1]), d = make_float2(acc[1][2], acc[1][3]);
+    a = __ffma2_rn(x0, w01, a); b = __ffma2_rn(x0, w23, b);
+    c = __ffma2_rn(x1, w01, c); d = __ffma2_rn(x1, w23, d);
+    acc[0][0] = a.x; acc[0][1] = a.y; acc[0][2] = b.x; acc[0][3] = b.y;
+    acc[1][0] = c.x; acc[1][1] = c.y; acc[1][2] = d.x; acc[1][3] = d.y;
   } else {
     float x[RT];
     if constexpr (RT == 2) { x[0] = v.x; x[1] = v.y; }
@@ -249,6 +295,25 @@ template <int RT>
 __device__ __forceinline__ void fma_tile(float (&acc)[RT][4], const float4& w, const float* xp) {
   fma_row<RT>(acc, w, *reinterpret_cast<const typename XVec<RT>::T*>(xp));
 }
+
+// Development build (-DSSV_WS_TOTALS): every role of a CTA records the SM cycles it spent in the launch and those it spent
+// waiting (mbarriers of the other role, tagged words of the producer stage); two clock reads per wait, nothing else.
+#ifdef SSV_WS_TOTALS
+#define TOT_DECL long long tot_wait_ = 0, tot_w0_ = 0
+#define TOT_W0 tot_w0_ = clock64()
+#define TOT_W1 tot_wait_ += clock64() - tot_w0_
+#define TOT_END(role_, cond_)                                                  \
+  if (p.totals != nullptr && (cond_)) {                                        \
+    p.totals[(size_t)blockIdx.x * 4 + 2 * (role_)] = clock64() - c.t0;         \
+    p.totals[(size_t)blockIdx.x * 4 + 2 * (role_) + 1] = tot_wait_;            \
+  }
+#else
+#define TOT_DECL
+#define TOT_W0
+#define TOT_W1
+#define TOT_END(role_, cond_)
+#endif
+
 struct Ctx {                 // per-CTA constants shared by both roles
   int s, prev, part, G, B;
   float* smem;
@@ -260,6 +325,7 @@ struct Ctx {                 // per-CTA constants shared by both roles
   uint64_t* rdone;           // [2] second reducer warp has published its half (wide tiles)
   int* s_bad;
   volatile long long* t_seen;   // profiling, [2][8]: SM clock at which the front end saw the producer's sentinel / handed X over
+  long long t0;                 // SM clock at the start of the roles (DecParams::totals)
 };
 
 // global column (= tagged word index) of local column lc; highway CTAs own matching H1 / H2 slices
@@ -269,7 +335,11 @@ __device__ __forceinline__ int gcol(const WsStage& st, int part, int lc) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Mat-vec role (warps 4-15).  Thread (cg, ks) owns 4 columns and the k rows ks + KS*j of every tap.
+// Mat-vec role (the 12 warps after the front end).  Thread (cg, ks) owns 4 columns and the k rows ks + KS*j of every
+// tap: 33 rows ("tiles") of a highway layer, <= 22 of a 1x1 conv.  The last ws_nreg(RT) of them live in registers, the
+// first ones in shared memory: 22 + 11 for one- and two-row micro-batches; four rows need 16 accumulators and 8 fetch
+// registers, so 18 + 15 (with 22 the tile loops spilled: 2.95 k cycles of FMA loop per visit against 2 x 1.25 k).
+__host__ __device__ constexpr int ws_nreg(int rt) { return rt == 4 ? 18 : 22; }
 template <int RT, int CG, bool HWY, bool PROF>
 __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st, const Ctx& c, int gtid) {
   constexpr int KS = GV_T / CG;            // k-slices: 24 (64 columns) or 12 (128 columns)
@@ -281,16 +351,19 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
   const float* bias_s = c.smem + SM_BIAS;
   const float4* wsm = reinterpret_cast<const float4*>(c.smem + SM_WSM) + gtid;
 
-  // my weights -> registers (image is thread-major: [j][384] float4); highway CTAs: tap 1 and tap 2
-  float4 w[22];
+  // my weights -> registers (image is thread-major: [tile][384] float4): the last NREG tiles
+  constexpr int NREG = ws_nreg(RT);
+  constexpr int NSM = (HWY ? 33 : 22) - NREG;       // tiles [0, NSM) are read from shared memory
+  float4 w[NREG];
   {
     const float4* img = reinterpret_cast<const float4*>(st.img) + (size_t)c.part * st.njt * GV_T + gtid;
-    const int j0 = HWY ? 11 : 0;
 #pragma unroll
-    for (int j = 0; j < 22; ++j) w[j] = j < st.nj ? __ldg(img + (size_t)(j0 + j) * GV_T) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NREG; ++j) w[j] = NSM + j < st.njt ? __ldg(img + (size_t)(NSM + j) * GV_T) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  auto wt = [&](int t) -> float4 { return t < NSM ? wsm[t * GV_T] : w[t - NSM]; };     // t is a compile-time constant
 
   long long prof_last = 0, prof_acc[5] = {0, 0, 0, 0, 0}, lat_acc = 0, wake_acc = 0;
+  TOT_DECL;
   const bool prof_on = PROF && p.prof != nullptr && gtid == 0;
   if (prof_on) prof_last = clock64();
 #define PROF_G(i)                                  \
@@ -328,23 +401,39 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
           if (b < c.B && gc < st.n) sb[i] = __ldg((st.bias_b == 1 ? p.s1 : p.s2) + (size_t)b * HD + gc);
         }
       }
+      if (KO_NOMV) {                // timing-only: the mat-vec role just hands the X buffers back
+        if (HWY) mbar_wait(&c.tapsfull[q], par, p.abort_flag);
+        mbar_wait(&c.curfull[q], par, p.abort_flag);
+#ifndef SSV_KO_NORING
+        if (HWY && gtid == 0) { ring_store(step, g, q); bulk_wait_prev_written_last_read(); }
+#endif
+        named_bar(1, GV_T);
+        if (gtid == 0) mbar_arrive(&c.empty[q]);
+        continue;
+      }
       float acc[RT][4];
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
       if (HWY) {
         // old taps: independent of the producer stage, overlaps the front end's wait
+        TOT_W0;
         mbar_wait(&c.tapsfull[q], par, p.abort_flag);     // on abort: fall through, the uniform exit is below
+        TOT_W1;
         PROF_G(0);
         // shared-memory-weight tiles (tap t-2d) alternate with register-weight tiles (tap t-d): twice the FMAs
         // between two LDS.128 weight fetches, so their latency hides with the two fragment buffers the register
         // budget allows (back to back, every other tile stalled on its fetch: 18 % of all samples short-scoreboard)
+#ifndef SSV_KO_NOFMA
 #pragma unroll
         for (int j = 0; j < 11; ++j) {
-          fma_tile<RT>(acc, wsm[j * GV_T], X + (size_t)(KS * j) * XS);
-          fma_tile<RT>(acc, w[j], X + (size_t)(TAPP + KS * j) * XS);
+          fma_tile<RT>(acc, wt(j), X + (size_t)(KS * j) * XS);
+          fma_tile<RT>(acc, wt(11 + j), X + (size_t)(TAPP + KS * j) * XS);
         }
+#endif
         PROF_G(1);
+        TOT_W0;
         mbar_wait(&c.curfull[q], par, p.abort_flag);
+        TOT_W1;
         PROF_G(2);
         if (PROF && prof_on) wake_acc += prof_last - c.t_seen[8 + q];
         // The finished current-tap rows of this (frame, micro-batch) join the history ring: one bulk copy (TMA)
@@ -353,17 +442,29 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
         // micro-batches: issued ahead of this thread's FMAs, the other warps fill the issue slots meanwhile (issued by
         // the last warp after its FMAs instead, the barrier below waited for it: B = 128 88.8 -> 94.4 us/frame).
         // Latency mode (one row): after the publish, off the frame's critical path.
+#ifndef SSV_KO_NORING
         if (RT > 1 && gtid == 0) ring_store(step, g, q);
+#endif
+#ifdef SSV_KO_NOFMA
+        acc[0][0] += w[0].x * X[0];
+#else
 #pragma unroll
-        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, w[11 + j], X + (size_t)(2 * TAPP + KS * j) * XS);
+        for (int j = 0; j < 11; ++j) fma_tile<RT>(acc, wt(22 + j), X + (size_t)(2 * TAPP + KS * j) * XS);
+#endif
       } else {
+        TOT_W0;
         mbar_wait(&c.curfull[q], par, p.abort_flag);
+        TOT_W1;
         PROF_G(2);
         // (Tried: the X rows of the 1x1 stages fetched as batches ahead of straight-line FMAs instead of row by row
         // under the row-count predicate: B = 64 49.4 -> 48.3 us/frame, but B = 1 29.4 -> 30.2 and B = 128 89.5 -> 95.3.)
+#ifdef SSV_KO_NOFMA
+        acc[0][0] += w[0].x * X[0];
+#else
 #pragma unroll
         for (int j = 0; j < 22; ++j)
-          if (j < st.nj) fma_tile<RT>(acc, w[j], X + (size_t)(KS * j) * XS);
+          if (j < st.nj) fma_tile<RT>(acc, wt(j), X + (size_t)(KS * j) * XS);
+#endif
         PROF_G(1);                  // 1x1 stages: "old taps" column = the tile loop, "current tap" = k-slice store + barrier
       }
       // k-slices -> shared memory
@@ -385,6 +486,9 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
       if (!HWY && gtid == 0) mbar_arrive(&c.empty[q]);     // X buffer q may be refilled (highway: after the publish, below)
       PROF_G(3);
       // reduce the 12 k-slices, add bias (+ hoisted speaker projection), publish tagged words
+#ifdef SSV_KO_NOPUB
+      if (false)
+#endif
 #pragma unroll
       for (int i = 0; i < (RT * NCOL + GV_T - 1) / GV_T; ++i) {
         const int o = gtid + i * GV_T;
@@ -399,8 +503,10 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
         }
       }
       if (HWY && gtid == 0) {
+#ifndef SSV_KO_NORING
         if (RT == 1) ring_store(step, g, q);
-        bulk_wait_prev_written_last_read();        // older ring entries are in memory, this one has left the X buffer
+        bulk_wait_prev_written_last_read();
+#endif        // older ring entries are in memory, this one has left the X buffer
         mbar_arrive(&c.empty[q]);
       }
       // Second CTA-wide barrier: the k-slice buffer may be rewritten, and -- measured -- it keeps the warps without
@@ -415,6 +521,7 @@ __device__ __forceinline__ void gemv_role(const DecParams& p, const WsStage& st,
       if (PROF && prof_on) lat_acc += prof_last - c.t_seen[q];
     }
   }
+  TOT_END(1, gtid == 0);
   if (prof_on) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) p.prof[(size_t)blockIdx.x * 16 + 8 + i] = prof_acc[i];
@@ -514,6 +621,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
   const int pro = st.pro;
 
   long long prof_last = 0, prof_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  TOT_DECL;
   const bool prof_on = PROF && p.prof != nullptr && tid == 0;
   if (prof_on) prof_last = clock64();
 #define PROF_F(i)                                  \
@@ -578,7 +686,9 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     //         complete before it released the X buffer this visit waited for (cp.async.bulk.wait_group 1 there).
     if (st.ntaps == 3) {
       if (u >= 1) {
+        TOT_W0;
         if (!mbar_wait(&c.empty[q], (unsigned)(u - 1) & 1u, p.abort_flag)) bad = true;
+        TOT_W1;
       }
       unsigned tx = 0;
       const float* bsrc[2] = {nullptr, nullptr};
@@ -595,6 +705,9 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
             const int ch = cb + 64 * i;
             if (RT == 1) {
               *reinterpret_cast<float4*>(dstX + (size_t)ch * 2) = *reinterpret_cast<const float4*>(srcX + (size_t)ch * 2);
+            } else if (XLayout<RT>::D == 2) {
+              *reinterpret_cast<float2*>(dstX + (size_t)ch * XSF + 2 * r) = *reinterpret_cast<const float2*>(srcX + (size_t)ch * XSF + 2 * r);
+              *reinterpret_cast<float2*>(dstX + (size_t)(ch + 1) * XSF + 2 * r) = *reinterpret_cast<const float2*>(srcX + (size_t)(ch + 1) * XSF + 2 * r);
             } else {
               dstX[(size_t)ch * XSF + r] = srcX[(size_t)ch * XSF + r];
               dstX[(size_t)(ch + 1) * XSF + r] = srcX[(size_t)(ch + 1) * XSF + r];
@@ -606,6 +719,9 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
           tx += ENTRY_BYTES;
         }
       }
+#ifdef SSV_KO_NOTAPS
+      tx = 0;
+#endif
       __syncwarp();
       if (lane == 0) {
         if (issuer && tx != 0) {
@@ -643,18 +759,22 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 #pragma unroll
     for (int i = 0; i < NP; ++i) o[i] = make_float2(0.f, 0.f);
     constexpr int XS = RT * XLayout<RT>::D;               // floats per X row
-    float* xcur = X + (size_t)koff * XS + r;               // channel ch at xcur[ch * XS] (RT = 1: as the pair (x, x))
+    float* xcur = X + (size_t)koff * XS + r * XLayout<RT>::D;   // channel ch at xcur[ch * XS] (D = 2: as the pair (x, x))
     auto xstore = [&](int ch, float2 val) {
       float* xp = xcur + (size_t)ch * XS;
       if (RT == 1) *reinterpret_cast<float4*>(xp) = make_float4(val.x, val.x, val.y, val.y);
-      else { xp[0] = val.x; xp[RT] = val.y; }
+      else if (XLayout<RT>::D == 2) {
+        *reinterpret_cast<float2*>(xp) = make_float2(val.x, val.x);
+        *reinterpret_cast<float2*>(xp + XS) = make_float2(val.y, val.y);
+      } else { xp[0] = val.x; xp[XS] = val.y; }
     };
     auto xstore1 = [&](int ch, float val) {
       float* xp = xcur + (size_t)ch * XS;
-      if (RT == 1) *reinterpret_cast<float2*>(xp) = make_float2(val, val);
+      if (XLayout<RT>::D == 2) *reinterpret_cast<float2*>(xp) = make_float2(val, val);
       else xp[0] = val;
     };
-    if (!live) {
+    if (KO_NOFE) {
+    } else if (!live) {
       if (!final_visit)
         for (int ch = lane + 32 * sub; ch < st.k_seg; ch += 32 * WPR) xstore1(ch, 0.f);
     } else if (pro == PRO_X && sub != 0) {
@@ -672,6 +792,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
       PROF_F(3);
       if (PROF && p.prof != nullptr && tid == 0) c.t_seen[q] = clock64();
       const Word* R = raw_in + (size_t)b * WS_WORDS;
+      TOT_W0;                                                // poll time (includes the one L2 round trip of the loads)
       if (pro == PRO_X) {
         float y[3];
         if (!need_wait) {
@@ -695,10 +816,11 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
               vv[i] = 0.f;
               if (f < p.F) { int tg; ld_word(R + f, vv[i], tg); ok &= tg == tag_in; }
             }
-            if (__all_sync(FULL, ok)) break;
+            if (KO_NOPOLL || __all_sync(FULL, ok)) break;
             spin_check();
             if (__any_sync(FULL, bad)) bad = true;
           }
+          TOT_W1;
           float sm = vv[0] + vv[1] + vv[2];
           sm = warp_sum(sm);
           const float mean = sm / (float)p.F;
@@ -734,10 +856,11 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
             ld_word2(R + cb + 64 * i, vv[i].x, ta, vv[i].y, tb);
             ok &= ta == tag_in && tb == tag_in;
           }
-          if (__all_sync(FULL, ok)) break;
+          if (KO_NOPOLL || __all_sync(FULL, ok)) break;
           spin_check();
           if (__any_sync(FULL, bad)) bad = true;
         }
+        TOT_W1;
         if (PROF && prof_on) PROF_F(4);
         float sum = 0.f, qq = 0.f, z0 = 0.f, z1 = 0.f;
 #pragma unroll
@@ -751,7 +874,9 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
             qq = fmaf(d1, d1, qq);
           }
         }
+#ifndef SSV_KO_NOSTATS
         row_stats2<WPR, 2 * NP>(sum, qq, z0, z1, bad, red, 2 * (vi & 1), warp, wbase, barid, lane);
+#endif
         const float mean = sum / (float)HD;
         const float rstd = rstd_fast(qq / (float)HD);
 #pragma unroll
@@ -784,10 +909,11 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
             ld_word2(wp + 2 * HD, xr[i].x, ta, xr[i].y, tb);
             ok &= ta == tag_in && tb == tag_in;
           }
-          if (__all_sync(FULL, ok)) break;
+          if (KO_NOPOLL || __all_sync(FULL, ok)) break;
           spin_check();
           if (__any_sync(FULL, bad)) bad = true;
         }
+        TOT_W1;
         if (PROF && prof_on) PROF_F(4);
         float s1 = 0.f, s2 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
@@ -802,7 +928,9 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
             d = h2[i].y - l2; q2 = fmaf(d, d, q2);
           }
         }
+#ifndef SSV_KO_NOSTATS
         row_stats2<WPR, 2 * NP>(s1, q1, s2, q2, bad, red, 2 * (vi & 1), warp, wbase, barid, lane);
+#endif
         const float m1 = s1 / (float)HD, m2 = s2 / (float)HD;
         const float r1 = rstd_fast(q1 / (float)HD);
         const float r2 = rstd_fast(q2 / (float)HD);
@@ -906,6 +1034,7 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
     if (bad && (WPR == 1 || pro == PRO_X || live)) return;
     PROF_F(5);
   }
+  TOT_END(0, tid == 0);
   if (prof_on) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) p.prof[(size_t)blockIdx.x * 16 + i] = prof_acc[i];
@@ -917,11 +1046,11 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 // Register budget with eight front-end warps: 640 threads x 96 registers at launch is the CTA's pool for good
 // (setmaxnreg moves registers between the warpgroups of a CTA, it cannot take more from the SM).  The two front-end
 // warpgroups give registers back and the three mat-vec warpgroups, whose threads keep 88 weights each, take them:
-// 256 x 72 + 384 x 112 = 61440 for one- and two-row micro-batches (no spills in either role with two or four warps
-// per row); four-row micro-batches need 16 accumulators per mat-vec thread: 256 x 56 + 384 x 120 = 60416.
+// 256 x 72 + 384 x 112 = 61440 (no spills in either role with two or four warps per row; four-row micro-batches keep
+// 18 instead of 22 weight rows per thread in registers, ws_nreg).
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int RT> struct Regs8 { static constexpr int FE = RT == 4 ? 56 : 72, MV = RT == 4 ? 120 : 112; };
+template <int RT> struct Regs8 { static constexpr int FE = 72, MV = 112; };
 static_assert(256 * Regs8<1>::FE + 384 * Regs8<1>::MV <= 640 * 96 && 256 * Regs8<4>::FE + 384 * Regs8<4>::MV <= 640 * 96, "register pool");
 
 template <int RT, int WPR, int FEW, bool PROF>
@@ -962,10 +1091,11 @@ __global__ void __launch_bounds__(GV_T + 32 * FEW, 1) decode_ws_kernel(const Dec
   // ---- one-time loads: tap-0 weights of a highway CTA, LayerNorm parameters, bias, alignment state
   {
     float* lnp = smem + SM_LN;
-    if (st.hwy) {
+    {
+      const int nsm = min((st.hwy ? 33 : 22) - ws_nreg(RT), st.njt);      // leading tiles of my weight image -> shared memory
       const float4* img = reinterpret_cast<const float4*>(st.img) + (size_t)c.part * st.njt * GV_T;
       float4* dst = reinterpret_cast<float4*>(smem + SM_WSM);
-      for (int i = tid; i < 11 * GV_T; i += NT) dst[i] = __ldg(img + i);
+      for (int i = tid; i < nsm * GV_T; i += NT) dst[i] = __ldg(img + i);
     }
     for (int i = tid; i < XREGION; i += NT) smem[SM_X + i] = 0.f;       // padding rows of X stay zero for good
     for (int i = tid; i < 4 * HD; i += NT) {
@@ -1012,6 +1142,9 @@ __global__ void __launch_bounds__(GV_T + 32 * FEW, 1) decode_ws_kernel(const Dec
   // B = 16 31.1 -> 34.8, B = 64 49.4 -> 51.0, B = 128 89.5 -> 98.1 us/frame.)
   const bool is_fe = tid < FE_T;
   const int rtid = is_fe ? tid : tid - FE_T;
+#ifdef SSV_WS_TOTALS
+  c.t0 = clock64();
+#endif
   if (is_fe) {
     if constexpr (FEW == 8) reg_dec<Regs8<RT>::FE>();
     front_role<RT, WPR, FEW, PROF>(p, st, c, rtid);
@@ -1110,8 +1243,8 @@ void ws_plan(int B, int force_r, int force_w, int force_f, int* R, int* W, int* 
   int r, w, f = 4;
   if (B <= 12) { r = 1; w = 4; }           // B=1 28.3 us/frame, B=12 28.9 (W=2: 30.1)
   else if (B <= 32) { r = 1; w = 2; }      // B=16 30.5 (W=4: 32.7), B=24 31.8, B=32 37.1 (R=2 W=2: 39.3, W=1: 38.8)
-  else if (B <= 128) { r = 2; w = 1; }     // B=40 45.1 (R=1: 46.6), B=48 47.4 (R=1: 56.5), B=64 51.7 (R=1 75.7, R=4 59), B=128 104
-  else { r = 4; w = 1; f = 8; }            // B=256: 178-183 with eight front-end warps (two visit slots), 192 with four
+  else if (B <= 160) { r = 2; w = 1; }     // B=40 45.1 (R=1: 46.6), B=48 47.4 (R=1: 56.5), B=64 51.7 (R=1 75.7, R=4 59), B=128 104
+  else { r = 4; w = 1; f = 8; }            // B=192: 129, B=256: 178-183 with eight front-end warps (two visit slots), 192 with four
   // Eight front-end warps (round 2): only the four-row shape gains.  B=64: R=2 W=2 F=8 51.2, R=2 W=1 F=8 (four slots)
   // 72.7, R=4 W=1 F=8 88.1, R=4 W=2 F=8 68.9 against 49.4; B=128: 99.9 / 130.8 / 100.4 / 100.2 against 89.5; B=1: 33.1
   // against 29.4; B=16: 34.8 against 31.1 -- the mat-vec warps lose 16 registers each and four more warps compete for
