@@ -39,7 +39,7 @@ METRIC = "Text2Mel+SSRN synthesized frames/s"
 UNIT = "reduced mel frames/s"
 N_TEXT = 58
 T_FRAMES = 217
-BATCH = 64
+BATCH = 256            # utterances per step and GPU (decode throughput: 1.29 M frames/s at 64, 1.43 M at 128, 1.55 M at 256)
 # SURVEY.md 8(d) cfg 3: algorithmic bytes per decode step = AudioEnc+AudioDec weights (fc1/fc2 hoisted)
 DECODE_WEIGHT_BYTES = 6_821_360 * 4
 DECODE_STATE_BYTES_PER_UTT = 16 * 3 * 256 * 4 + 6 * 1024 + 640       # taps r/w, K/V window, x/y  (~56 KB)
@@ -369,11 +369,13 @@ def main():
     syn = Synthesizer(m1, m2, ssrn_precision=args.ssrn_precision, lin_dtype=lin_dtype)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    def device_step(parts=None):
+    def device_step(parts=None, ids_x=None, spk_x=None):
+        ids_x = ids_d if ids_x is None else ids_x
+        spk_x = spk_d if spk_x is None else spk_x
         e = [ev() for _ in range(4)]
         e[0].record()
-        K, V = m1.encode_text(ids_d, check=False)      # ids are verified on the device; m1.check() after the loop reports
-        dec = m1._begin(K, V, spk_d, T)
+        K, V = m1.encode_text(ids_x, check=False)      # ids are verified on the device; m1.check() after the loop reports
+        dec = m1._begin(K, V, spk_x, T)
         e[1].record()
         _lib.check(lib.ssv_decoder_run(dec, T, _lib.current_stream_ptr()))
         e[2].record()
@@ -481,6 +483,35 @@ def main():
 
     # ---- secondary measurements (outside the headline's timed region)
     extra = {}
+    if B != 64 and B > 64:
+        # the round-1 / BASELINE config 3 batch (64 utterances per step), device-resident, for continuity
+        i64, s64 = ids_d[:64].contiguous(), spk_d[:64].contiguous()
+        for _ in range(3):
+            flush.fill_(1)
+            device_step(ids_x=i64, spk_x=s64)
+        torch.cuda.synchronize()
+        ms64, parts64 = [], []
+        for _ in range(10):
+            flush.fill_(1)
+            e, lin64 = device_step(ids_x=i64, spk_x=s64)
+            torch.cuda.synchronize()
+            ms64.append(e[0].elapsed_time(e[3]))
+            parts64.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])))
+        del lin64
+        d64 = statistics.mean(p[1] for p in parts64)
+        b64_bytes = T * (DECODE_WEIGHT_BYTES + 64 * DECODE_STATE_BYTES_PER_UTT)
+        extra["batch64"] = {
+            "what": "the same step with 64 utterances (round-1 bench shape; BASELINE config 3 decode batch), one rank, device-resident",
+            "value": 64 * T / (statistics.mean(ms64) * 1e-3), "ms_per_step": statistics.mean(ms64),
+            "phases_ms": {"text_encoder+begin": statistics.mean(p[0] for p in parts64), "decode": d64,
+                          "ssrn": statistics.mean(p[2] for p in parts64)},
+            "decode_us_per_frame": 1e3 * d64 / T,
+            "decode_hbm_roofline_frac": b64_bytes / (d64 * 1e-3) / 1e9 / measured_peaks()["hbm"],
+            "decode_fma_roofline_frac": 64 * T * DECODE_FLOP_PER_FRAME / (d64 * 1e-3) / 1e12 / FP32_PEAK_TFLOPS}
+        for _ in range(2):
+            flush.fill_(1)
+            device_step()                       # back to the headline shape
+        torch.cuda.synchronize()
     other = "fp32" if args.ssrn_precision == "bf16" else "bf16"
     m2.precision = other
     device_step()
@@ -587,7 +618,10 @@ def main():
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
-        traffic = json.loads(tp.read_text()).get("decode_kernel_dram_bytes_per_launch")
+        tj = json.loads(tp.read_text())          # ncu --set full captures of one decode launch, keyed by batch size
+        traffic = tj.get("by_batch", {}).get(str(B), {}).get("decode_kernel_dram_bytes_per_launch")
+        if traffic is None and B == 64:
+            traffic = tj.get("decode_kernel_dram_bytes_per_launch")
     ssrn_tflops = B * T * SSRN_FLOP_PER_FRAME / (ssrn_ms * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -1140,8 +1140,10 @@ __global__ void __launch_bounds__(GV_T + 32 * FEW, 1) decode_ws_kernel(const Dec
   // B = 64 50.1 -> 51.9, B = 128 93.3 -> 97.8 us/frame.)
   // (Tried: the four front-end warps on one scheduler (warps 0, 4, 8, 12), the mat-vec warps on the other three:
   // B = 16 31.1 -> 34.8, B = 64 49.4 -> 51.0, B = 128 89.5 -> 98.1 us/frame.)
-  const bool is_fe = tid < FE_T;
-  const int rtid = is_fe ? tid : tid - FE_T;
+  // Eight front-end warps sit ABOVE the mat-vec warps (the arbiter serves the higher warp ids first): B = 256 R=4 W=1
+  // 180 -> 165 us/frame.  With four front-end warps the same order is slower (B = 64 49.4 -> 50.8, B = 128 89.5 -> 93.5).
+  const bool is_fe = FEW == 8 ? tid >= GV_T : tid < FE_T;
+  const int rtid = FEW == 8 ? (is_fe ? tid - GV_T : tid) : (is_fe ? tid : tid - FE_T);
 #ifdef SSV_WS_TOTALS
   c.t0 = clock64();
 #endif
