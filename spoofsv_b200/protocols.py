@@ -19,6 +19,8 @@ The reference shuffles each speaker's utterance list with the unseeded global `r
 argument.  The anti-spoofing audio is resampled to 16 kHz (polyphase, scipy) and written by a caller-supplied
 writer: the reference writes FLAC through `soundfile`, which this image does not have -- the default writer
 stores 16-bit PCM wav under the same stem and the protocol lines are unchanged.
+Parity: tests/test_protocols.py compares every path, link, copied file and text with a tree written by the reference's
+own lines (tests/golden/protocols_ref.json, made by oracle/protocols_fixture.py).
 """
 from __future__ import annotations
 

@@ -96,3 +96,35 @@ def test_resample_keeps_a_tone():
     assert len(z) == 16000
     ref = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0)
     assert np.abs(z[200:-200] - ref[200:-200]).max() < 1e-3
+
+
+def test_layouts_match_the_reference_code(tmp_path, monkeypatch):
+    """The writers against a tree produced by the REFERENCE'S OWN lines (generate_test_utterances.py:142-259, executed
+    unmodified by oracle/protocols_fixture.py in the build container): every path, symlink target, copied wav (SHA-1),
+    both transcripts and the anti-spoofing protocol."""
+    import hashlib
+    import json
+    from pathlib import Path
+    from oracle import protocols_fixture as PF
+
+    gold = json.loads((Path(__file__).parent / "golden" / "protocols_ref.json").read_text())
+    cfg = PF.build_corpus(tmp_path)
+    # the fixture run listed directories in sorted order (the reference shuffles the raw file-system order)
+    real_listdir = os.listdir
+    monkeypatch.setattr(P.os, "listdir", lambda p=".": sorted(real_listdir(p)))
+    out = Path(cfg["SRC_ROOT_DIR"]) / "test" / PF.TAG
+    syn = out / "spoof_data"
+    P.write_ivector_layout(cfg["DATA_ROOT_DIR"], str(syn), str(out), PF.SENTENCES, PF.TRAIN_SPK, PF.ENROLL, PF.EVAL,
+                           rng=random.Random(PF.SEED))
+    P.link_ge2e(str(out))
+    P.write_antispoof_set(cfg["ANTISPOOF_DIR"], str(syn), PF.TAG, bonafide_num=PF.BONAFIDE,
+                          writer=lambda path, samples, sr: Path(path).write_bytes(b"resampled"), ext=".flac")
+    monkeypatch.undo()
+    snap = PF.snapshot(tmp_path, cfg)
+    bona = {k: v for k, v in snap["files"].items() if "/flac/" in k and v != "resampled"}
+    rest = {k: v for k, v in snap["files"].items() if k not in bona}
+    assert len(bona) == gold["bonafide_count"]
+    assert hashlib.sha1(json.dumps(sorted(bona.items())).encode()).hexdigest() == gold["bonafide_digest"]
+    assert rest == gold["files"]
+    assert snap["links"] == gold["links"]
+    assert snap["texts"] == gold["texts"]
