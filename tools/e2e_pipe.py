@@ -7,10 +7,10 @@ from oracle import weights as W
 from spoofsv_b200.synth import Synthesizer
 m1, m2 = W.build_models(0); m1, m2 = m1.cuda(), m2.cuda(); m2.precision = "bf16"
 names, emb, _ = W.load_fixtures()
-B, T = 64, 217
+B, T = (int(sys.argv[1]) if len(sys.argv) > 1 else 256), 217
 ids = W.synthetic_text(B, 58, seed=11).numpy()[:, 0, :]
 spk = emb[[i % len(emb) for i in range(B)]].copy()
-syn = Synthesizer(m1, m2, ssrn_precision="bf16")
+syn = Synthesizer(m1, m2, ssrn_precision="bf16", lin_dtype=(sys.argv[2] if len(sys.argv) > 2 else "bf16"))
 for _ in range(4):
     syn.synthesize_host(ids, spk, T)
 torch.cuda.synchronize()
