@@ -58,8 +58,8 @@ int tc_check_error();   // synchronous: reads and clears the device-side timeout
 int* tc_err_flag_dev();  // the flag itself (device word), for callers that fetch it with their own asynchronous copy
 
 // ---- second-generation BF16 kernel (conv_tc2.cu): 256 accumulator columns per CTA, two CTAs per SM, N split over a
-// cluster of 1 / 2 / 4 CTAs; highway (d = 256, 512), LayerNorm (+ReLU) and plain (ConvTranspose1d) layers with 256 or 512
-// output columns, bf16 in and out.  A launch is prepared once per (layer, buffers, shape) -- the TMA descriptors are
+// cluster of 1 / 2 / 4 CTAs; highway (d = 256, 512), LayerNorm (+ReLU / sigmoid) and plain (ConvTranspose1d) layers with 256
+// or 512 output columns, and the 513-column heads (512 + one column on the CUDA cores); bf16 in, bf16 or fp32 out.  A launch is prepared once per (layer, buffers, shape) -- the TMA descriptors are
 // encoded there -- and replayed.
 struct Tc2Launch {
   alignas(64) unsigned char storage[640];
@@ -67,7 +67,7 @@ struct Tc2Launch {
 };
 bool tc2_supported(const TcLayer& L, int epi);
 int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloat16* X, int x_ld, int T, int B,
-                __nv_bfloat16* Y, int y_ld, Tc2Launch* out);
+                void* Y, int y_ld, bool out_fp32, Tc2Launch* out);
 int tc2_run(const Tc2Launch& L, cudaStream_t s);
 int tc2_check_error();
 int* tc2_err_flag_dev();
