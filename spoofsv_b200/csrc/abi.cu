@@ -377,7 +377,6 @@ struct ssv_ssrn {
   Workspace ws;
   __nv_bfloat16* tws[2] = {nullptr, nullptr};
   size_t tws_elems = 0;
-  const float* plan_f32 = nullptr;  // fp32 output buffer the last prepared launch writes
   Tc2Launch plan2[16];              // prepared launches of the layers the second-generation kernel runs, for (plan_B, plan_T)
   int plan_B = 0, plan_T = 0;
   ~ssv_ssrn() {
@@ -1255,32 +1254,31 @@ static int ssrn_fwd_bf16(ssv_ssrn* m, const float* mel, long sb, long sf, long s
   }
   __nv_bfloat16* P = m->tws[0];
   __nv_bfloat16* Q = m->tws[1];
-  if (m->plan_B != B || m->plan_T != T || m->plan_f32 != m->ws.buf[0]) {          // encode the TMA descriptors of this shape once
+  if (m->plan_B != B || m->plan_T != T) {          // encode the TMA descriptors of this shape once
     m->plan_B = m->plan_T = 0;
     Tc2Launch* L = m->plan2;
-    SSV_TRY(tc2_prepare(m->t_conv1, EPI_LN, 1, 0, P, f_ld, T, B, Q, D, false, &L[0]));
-    SSV_TRY(tc2_prepare(m->t_hc1, EPI_HIGHWAY, 1, 0, Q, D, T, B, P, D, false, &L[1]));
-    SSV_TRY(tc2_prepare(m->t_hc2, EPI_HIGHWAY, 3, 0, P, D, T, B, Q, D, false, &L[2]));
-    SSV_TRY(tc2_prepare(m->t_dc1, EPI_NONE, 1, 0, Q, D, T, B, P, 2 * D, false, &L[3]));           // (B,T,2D) == (B,2T,D)
-    SSV_TRY(tc2_prepare(m->t_u1h1, EPI_HIGHWAY, 1, 0, P, D, 2 * T, B, Q, D, false, &L[4]));
-    SSV_TRY(tc2_prepare(m->t_u1h2, EPI_HIGHWAY, 3, 0, Q, D, 2 * T, B, P, D, false, &L[5]));
-    SSV_TRY(tc2_prepare(m->t_dc2, EPI_NONE, 1, 0, P, D, 2 * T, B, Q, 2 * D, false, &L[6]));
-    SSV_TRY(tc2_prepare(m->t_u2h1, EPI_HIGHWAY, 1, 0, Q, D, 4 * T, B, P, D, false, &L[7]));
-    SSV_TRY(tc2_prepare(m->t_u2h2, EPI_HIGHWAY, 3, 0, P, D, 4 * T, B, Q, D, false, &L[8]));
-    SSV_TRY(tc2_prepare(m->t_conv2, EPI_LN, 1, 0, Q, D, 4 * T, B, P, 2 * D, false, &L[9]));
-    SSV_TRY(tc2_prepare(m->t_hc3, EPI_HIGHWAY, 1, 0, P, 2 * D, 4 * T, B, Q, 2 * D, false, &L[10]));
-    SSV_TRY(tc2_prepare(m->t_hc4, EPI_HIGHWAY, 1, 0, Q, 2 * D, 4 * T, B, P, 2 * D, false, &L[11]));
+    SSV_TRY(tc2_prepare(m->t_conv1, EPI_LN, 1, 0, P, f_ld, T, B, Q, D, 0, &L[0]));
+    SSV_TRY(tc2_prepare(m->t_hc1, EPI_HIGHWAY, 1, 0, Q, D, T, B, P, D, 0, &L[1]));
+    SSV_TRY(tc2_prepare(m->t_hc2, EPI_HIGHWAY, 3, 0, P, D, T, B, Q, D, 0, &L[2]));
+    SSV_TRY(tc2_prepare(m->t_dc1, EPI_NONE, 1, 0, Q, D, T, B, P, 2 * D, 0, &L[3]));           // (B,T,2D) == (B,2T,D)
+    SSV_TRY(tc2_prepare(m->t_u1h1, EPI_HIGHWAY, 1, 0, P, D, 2 * T, B, Q, D, 0, &L[4]));
+    SSV_TRY(tc2_prepare(m->t_u1h2, EPI_HIGHWAY, 3, 0, Q, D, 2 * T, B, P, D, 0, &L[5]));
+    SSV_TRY(tc2_prepare(m->t_dc2, EPI_NONE, 1, 0, P, D, 2 * T, B, Q, 2 * D, 0, &L[6]));
+    SSV_TRY(tc2_prepare(m->t_u2h1, EPI_HIGHWAY, 1, 0, Q, D, 4 * T, B, P, D, 0, &L[7]));
+    SSV_TRY(tc2_prepare(m->t_u2h2, EPI_HIGHWAY, 3, 0, P, D, 4 * T, B, Q, D, 0, &L[8]));
+    SSV_TRY(tc2_prepare(m->t_conv2, EPI_LN, 1, 0, Q, D, 4 * T, B, P, 2 * D, 0, &L[9]));
+    SSV_TRY(tc2_prepare(m->t_hc3, EPI_HIGHWAY, 1, 0, P, 2 * D, 4 * T, B, Q, 2 * D, 0, &L[10]));
+    SSV_TRY(tc2_prepare(m->t_hc4, EPI_HIGHWAY, 1, 0, Q, 2 * D, 4 * T, B, P, 2 * D, 0, &L[11]));
     // the four 513-bin heads: 512 columns on the tensor cores + the 513th as a dot product in the epilogue warps
-    SSV_TRY(tc2_prepare(m->t_conv3, EPI_LN, 1, 0, P, 2 * D, 4 * T, B, Q, o_ld, false, &L[12]));
-    SSV_TRY(tc2_prepare(m->t_conv4, EPI_LN_RELU, 1, 0, Q, o_ld, 4 * T, B, P, o_ld, false, &L[13]));
-    SSV_TRY(tc2_prepare(m->t_conv5, EPI_LN_RELU, 1, 0, P, o_ld, 4 * T, B, Q, o_ld, false, &L[14]));
-    SSV_TRY(tc2_prepare(m->t_conv6, EPI_LN_SIGMOID, 1, 0, Q, o_ld, 4 * T, B, m->ws.buf[0], o_ld, true, &L[15]));
-    m->plan_B = B; m->plan_T = T; m->plan_f32 = m->ws.buf[0];
+    SSV_TRY(tc2_prepare(m->t_conv3, EPI_LN, 1, 0, P, 2 * D, 4 * T, B, Q, o_ld, 0, &L[12]));
+    SSV_TRY(tc2_prepare(m->t_conv4, EPI_LN_RELU, 1, 0, Q, o_ld, 4 * T, B, P, o_ld, 0, &L[13]));
+    SSV_TRY(tc2_prepare(m->t_conv5, EPI_LN_RELU, 1, 0, P, o_ld, 4 * T, B, Q, o_ld, 0, &L[14]));
+    SSV_TRY(tc2_prepare(m->t_conv6, EPI_LN_SIGMOID, 1, 0, Q, o_ld, 4 * T, B, out, o_ld, 2, &L[15]));   // (B, 513, 4T) directly
+    m->plan_B = B; m->plan_T = T;
   }
   SSV_TRY(launch_transpose_in_bf16(mel, sb, sf, st_, B, m->F, T, P, f_ld, s));
+  tc2_set_output(&m->plan2[15], out);              // the caller's buffer of this call
   for (int i = 0; i < 16; ++i) SSV_TRY(tc2_run(m->plan2[i], s));
-  float* F32 = m->ws.buf[0];
-  SSV_TRY(launch_transpose_out(F32, o_ld, B, O, 4 * T, out, s));
   return kOk;
 }
 

@@ -67,7 +67,8 @@ struct Tc2Launch {
 };
 bool tc2_supported(const TcLayer& L, int epi);
 int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloat16* X, int x_ld, int T, int B,
-                void* Y, int y_ld, bool out_fp32, Tc2Launch* out);
+                void* Y, int y_ld, int out_fp32 /* 0: bf16 rows, 1: fp32 rows, 2: fp32 channels-first (B, n, T) */, Tc2Launch* out);
+void tc2_set_output(Tc2Launch* L, void* Y);      // replace the output pointer of a prepared launch
 int tc2_run(const Tc2Launch& L, cudaStream_t s);
 int tc2_check_error();
 int* tc2_err_flag_dev();

@@ -55,7 +55,9 @@ struct alignas(64) Args {
   int w0_base, w0_rank, w1_base, w1_rank;
   int n_real, epi;
   int xcol;               // 1: the layer has n_real = 512 + 1 columns; column 512 is a dot product on the CUDA cores (rank 0)
-  int out_fp32;           // plain layers: write fp32 rows straight from the registers (the last SSRN layer)
+  int out_fp32;           // plain layers: fp32 output straight from the registers (the last SSRN layer): 1 = channels-last rows,
+                          // 2 = channels-first (B, n_real, T) -- the module's output layout: for every channel the 32 lanes
+                          // of a warp (32 consecutive time steps) store one 128-byte segment, no transpose kernel afterwards
   const float* bias; const float* g1; const float* b1; const float* g2; const float* b2;
   const __nv_bfloat16* Wx;                        // weight row of the extra column, [K]
   const __nv_bfloat16* Xres; long x_sb, x_st;
@@ -339,7 +341,14 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
           o[i] = relu ? fmaxf(h1, 0.f) : (sigm ? sigmoid_fast(h1) : h1);
         }
       }
-      if (a.out_fp32) {          // 64 contiguous bytes per thread and chunk: whole sectors
+      if (a.out_fp32 == 2) {
+        if (row_in && got) {
+          const int j = cbase + c;
+          float* dst = reinterpret_cast<float*>(a.Y) + ((long)b * a.n_real + (j < 128 ? w0 + j : w1 + (j - 128))) * a.T + t;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dst[(long)i * a.T] = o[i];
+        }
+      } else if (a.out_fp32) {          // 64 contiguous bytes per thread and chunk: whole sectors
         if (row_in && got) {
           const int j = cbase + c;
           float4* dst = reinterpret_cast<float4*>(yf + (j < 128 ? w0 + j : w1 + (j - 128)));
@@ -365,7 +374,9 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
       const float4 pp = prm_s[NL];
       const float h = (x512 - m1) * rs1 * pp.y + pp.z;
       const float y = relu ? fmaxf(h, 0.f) : (sigm ? sigmoid_fast(h) : h);
-      if (a.out_fp32) {
+      if (a.out_fp32 == 2) {
+        reinterpret_cast<float*>(a.Y)[((long)b * a.n_real + 512) * a.T + t] = y;
+      } else if (a.out_fp32) {
         yf[512] = y;
       } else {
         __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(a.Y) + (long)b * a.y_sb + (long)t * a.y_st + 512;
@@ -475,7 +486,7 @@ bool tc2_supported(const TcLayer& L, int epi) {
 }
 
 int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloat16* X, int x_ld, int T, int B,
-                void* Y, int y_ld, bool out_fp32, Tc2Launch* out) {
+                void* Y, int y_ld, int out_fp32, Tc2Launch* out) {
   SSV_CHECK(tc2_supported(L, epi), "conv_tc2: layer shape (rows %d, epilogue %d) not built", L.rows, epi);
   SSV_CHECK(L.cin_p % BKE == 0 && x_ld >= L.cin_p && x_ld % 8 == 0 && y_ld % 8 == 0, "conv_tc2: bad padding (cin_p %d, ld %d)", L.cin_p, x_ld);
   const bool xcol = L.rows == 513;                 // 512 tensor-core columns + one on the CUDA cores
@@ -511,7 +522,7 @@ int tc2_prepare(const TcLayer& L, int epi, int dil, int causal, const __nv_bfloa
   }
   a.xcol = xcol ? 1 : 0;
   a.Wx = xcol ? L.W + (size_t)512 * kp : nullptr;
-  a.out_fp32 = out_fp32 ? 1 : 0;
+  a.out_fp32 = out_fp32;
   a.epi = epi;
   a.bias = L.bias;
   a.g1 = L.g1; a.b1 = L.b1; a.g2 = L.g2; a.b2 = L.b2;
@@ -531,6 +542,8 @@ static long long* v2_prof_buf() {       // SSV_TC_PROF=1: [4096 CTAs][8] cycle c
   }
   return buf;
 }
+
+void tc2_set_output(Tc2Launch* L, void* Y) { reinterpret_cast<Tc2LaunchImpl*>(L->storage)->args.Y = Y; }
 
 int tc2_run(const Tc2Launch& L, cudaStream_t s) {
   int* err = v2_err_flag();
