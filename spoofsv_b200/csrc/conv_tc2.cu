@@ -207,12 +207,14 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
     const int cw = hwy ? 64 : 128;            // columns of one LayerNorm pass of this thread
     const int cbase = half * cw;              // first TMEM column (highway: of H1; H2 is 128 further)
     const __nv_bfloat16* xres = a.Xres + (long)b * a.x_sb + (long)t * a.x_st + w0 + cbase;
-    // the first residual chunk travels while the mainloop runs
-    bf16x8 xr0, xr1;
-    xr0.v[0] = xr0.v[1] = xr0.v[2] = xr0.v[3] = xr1.v[0] = xr1.v[1] = xr1.v[2] = xr1.v[3] = __floats2bfloat162_rn(0.f, 0.f);
+    // the thread's 64 residual channels travel while the mainloop runs.  (One chunk ahead inside the gate pass, as the
+    // first version did, stalls every chunk: tcgen05.wait::ld also waits for the thread's outstanding global loads.)
+    bf16x8 xrs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xrs[i].v[0] = xrs[i].v[1] = xrs[i].v[2] = xrs[i].v[3] = __floats2bfloat162_rn(0.f, 0.f);
     if (hwy && row_in) {
-      xr0 = *reinterpret_cast<const bf16x8*>(xres);
-      xr1 = *reinterpret_cast<const bf16x8*>(xres + 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xrs[i] = *reinterpret_cast<const bf16x8*>(xres + 8 * i);
     }
     // extra column (the 513th bin of the SSRN heads): x[row] . w over the operand tiles as they pass through the pipeline
     // -- the epilogue warps are idle during the mainloop, the activations are in shared memory anyway, and the
@@ -302,19 +304,18 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
     const int o_ld = hwy ? HW_LD : PL_LD;
     const bool relu = a.epi == EPI_LN_RELU, none = a.epi == EPI_NONE, sigm = a.epi == EPI_LN_SIGMOID;
     float* yf = reinterpret_cast<float*>(a.Y) + (long)b * a.y_sb + (long)t * a.y_st;
-    for (int c = 0; c < cw; c += 16) {
+#pragma unroll
+    for (int c = 0; c < 128; c += 16) {
+      if (c >= cw) break;
       tmem_ld16_issue(tq + c, r0);
       if (hwy) tmem_ld16_issue(tq + 128 + c, r1);
-      bf16x8 nx0 = xr0, nx1 = xr1;
-      if (hwy && row_in && c + 16 < cw) {                      // next chunk's residual
-        nx0 = *reinterpret_cast<const bf16x8*>(xres + c + 16);
-        nx1 = *reinterpret_cast<const bf16x8*>(xres + c + 24);
-      }
       tmem_wait16(r0);
       float o[16];
       if (hwy) {
         tmem_wait16(r1);
         float xr[16];
+#pragma unroll
+        const bf16x8 xr0 = xrs[(c >> 3) & 7], xr1 = xrs[((c >> 3) + 1) & 7];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 fa = __bfloat1622float2(xr0.v[i]), fb = __bfloat1622float2(xr1.v[i]);
@@ -366,7 +367,6 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
         dst[0] = oa;
         dst[1] = ob;
       }
-      xr0 = nx0; xr1 = nx1;
     }
     // the extra column: normalised like the others; bf16 rows also get their zero tail (columns 513..575 are the next
     // layer's K padding)
