@@ -153,6 +153,29 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
                          int dilation, int causal, const float* h_saved, float* dx, float* dconv_w, float* dconv_b,
                          float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, void* stream);
+
+/* ---- the small layers of the Text2Mel training graph, FP32 (reference: the autograd of the nn.Conv1d(kernel 1) +
+ * nn.LayerNorm pairs, models/TTSModel.py:128-131, 173-180, 218-230; the unmasked attention of the train branch,
+ * :268-272; textEmbedding, :25-35; the speaker projections, :172-173).  All tensors channels-first fp32 on the device. */
+/* y (B, n, T) = LN(W relu?(x) + b (+ sb per utterance)); h_save: (B T) x round_up(n, 64) floats for the backward. */
+int ssv_conv_ln_fwd_save(const float* x, const float* w, const float* b, const float* sb /* (B, n) or NULL */,
+                         const float* ln_w, const float* ln_b, int B, int cin, int n, int T, int relu_in, float* y,
+                         float* h_save, void* stream);
+int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float* ln_w, const float* h_saved, int B, int cin,
+                    int n, int T, int relu_in, float* dx /* or NULL */, float* dw, float* db, float* dsb /* (B, n) or NULL */,
+                    float* dln_w, float* dln_b, void* stream);
+/* kv (B, 512, N) = [K ; V], q (B, 256, T) -> A (B, N, T) = softmax_n(K^T q / 16), rq (B, 512, T) = [V A ; q] */
+int ssv_attention_train_fwd(const float* kv, const float* q, int B, int N, int T, float* A, float* rq, void* stream);
+int ssv_attention_train_bwd(const float* kv, const float* q, const float* A, const float* dA /* or NULL */, const float* drq,
+                            int B, int N, int T, float* dkv, float* dq, void* stream);
+/* ids (B, N) int64, weight (E, vocab), bias (E) -> y (B, E, N) */
+int ssv_text_embedding_fwd(const int64_t* ids, const float* weight, const float* bias, int B, int N, int vocab, int E, float* y,
+                           void* stream);
+int ssv_text_embedding_bwd(const int64_t* ids, const float* dy, int B, int N, int vocab, int E, float* dweight, float* dbias,
+                           void* stream);
+/* y (B, out) = x (B, in) W^T + b */
+int ssv_linear_small_fwd(const float* x, const float* w, const float* b, int B, int in_f, int out_f, float* y, void* stream);
+int ssv_linear_small_bwd(const float* x, const float* dy, int B, int in_f, int out_f, float* dw, float* db, void* stream);
 /* Training-time forward: like ssv_highway_conv_fwd (FP32) and also writes H = conv(x) + b, dev ((B T), 2d) in the
  * library's row layout, for h_saved of ssv_highway_conv_bwd (NULL there: the conv is recomputed). */
 int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libspoofsv_b200.so"
-SOURCES = ["abi.cu", "backward.cu", "conv_f32.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc32.cu", "decode_ws.cu", "griffinlim.cu", "misc.cu"]
+SOURCES = ["abi.cu", "backward.cu", "conv_f32.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc32.cu", "decode_ws.cu", "griffinlim.cu", "misc.cu", "train_small.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -561,6 +561,165 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// The small layers of the Text2Mel training graph, FP32 (train_small.cu): standalone like the highway-conv pair above.
+
+// y = LN(W relu?(x) + b (+ sb per utterance)): models/TTSModel.py:128-131, 173-180, 218-230.  h_save receives the raw
+// conv output ((B T) x round_up(n, 64)), which ssv_conv_ln_bwd takes.
+int ssv_conv_ln_fwd_save(const float* x, const float* w, const float* b, const float* sb, const float* ln_w, const float* ln_b,
+                         int B, int cin, int n, int T, int relu_in, float* y, float* h_save, void* stream) {
+  SSV_CHECK(x && w && b && ln_w && ln_b && y && h_save, "conv_ln_fwd_save: null pointer");
+  SSV_CHECK(B > 0 && T > 0 && cin > 0 && n > 0 && n <= 512 && cin <= 512, "conv_ln_fwd_save: bad shape (B=%d, cin=%d, n=%d, T=%d)", B, cin, n, T);
+  cudaStream_t s = as_stream(stream);
+  Arena ar(s);
+  ParamMap pm;
+  pm.m["conv.weight"] = {w, (int64_t)n * cin};
+  pm.m["conv.bias"] = {b, n};
+  ConvPack c;
+  SSV_TRY(pack_conv(ar, pm, "conv", n, cin, 1, &c, s));
+  const int M = B * T, x_ld = round_up(cin, 64), n_pad = round_up(n, 64);
+  float *xin, *yr;
+  SSV_TRY(ar.alloc<float>((size_t)M * x_ld, &xin));
+  SSV_TRY(ar.alloc<float>((size_t)M * n_pad, &yr));
+  SSV_TRY(launch_transpose_in(x, (long)cin * T, T, 1, B, cin, T, xin, x_ld, s));
+  if (relu_in) SSV_TRY(launch_relu_rows(xin, (long)M * x_ld, s));
+  SSV_TRY(run_conv(c, EPI_NONE, 1, 0, xin, x_ld, T, B, h_save, n_pad, s, sb, n));
+  SSV_TRY(launch_ln_rows_fwd(h_save, n_pad, M, n, ln_w, ln_b, yr, n_pad, s));
+  SSV_TRY(launch_transpose_out(yr, n_pad, B, n, T, y, s));
+  return kOk;
+}
+
+int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float* ln_w, const float* h_saved, int B, int cin, int n,
+                    int T, int relu_in, float* dx, float* dw, float* db, float* dsb, float* dln_w, float* dln_b, void* stream) {
+  SSV_CHECK(x && dy && w && ln_w && h_saved && dw && db && dln_w && dln_b, "conv_ln_bwd: null pointer");
+  SSV_CHECK(B > 0 && T > 0 && cin > 0 && n > 0 && n <= 512 && cin <= 512, "conv_ln_bwd: bad shape (B=%d, cin=%d, n=%d, T=%d)", B, cin, n, T);
+  cudaStream_t s = as_stream(stream);
+  Arena ar(s);
+  const int M = B * T, x_ld = round_up(cin, 64), n_pad = round_up(n, 64), pc = ln_bwd_partial_cols(n), nblk = ln_bwd_row_blocks(M);
+  float *xin, *dyr, *dH, *partial, *sums, *U, *P;
+  SSV_TRY(ar.alloc<float>((size_t)M * x_ld, &xin));
+  SSV_TRY(ar.alloc<float>((size_t)M * n_pad, &dyr));
+  SSV_TRY(ar.alloc<float>((size_t)M * n_pad, &dH));
+  SSV_TRY(ar.alloc<float>((size_t)nblk * pc, &partial));
+  SSV_TRY(ar.alloc<float>((size_t)pc, &sums));
+  SSV_TRY(ar.alloc<float>((size_t)B * n, &U));
+  SSV_TRY(ar.alloc<float>((size_t)wgrad_plain_chunks(M) * n * cin, &P));
+  SSV_TRY(launch_transpose_in(x, (long)cin * T, T, 1, B, cin, T, xin, x_ld, s));
+  if (relu_in) SSV_TRY(launch_relu_rows(xin, (long)M * x_ld, s));
+  SSV_TRY(launch_transpose_in(dy, (long)n * T, T, 1, B, n, T, dyr, n_pad, s));
+  // LayerNorm backward per row, parameter sums
+  SSV_TRY(launch_ln_rows_bwd(h_saved, n_pad, dyr, n_pad, M, n, ln_w, dH, partial, s));
+  SSV_TRY(launch_colsum_partials(partial, nblk, pc, sums, s));
+  SSV_CUDA(cudaMemcpyAsync(dln_w, sums, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  SSV_CUDA(cudaMemcpyAsync(dln_b, sums + pc / 2, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  // bias gradients: per utterance (the speaker projection's), summed over the utterances for the conv bias
+  SSV_TRY(launch_utt_colsum(dH, n_pad, B, T, n, U, s));
+  SSV_TRY(launch_colsum_partials(U, B, n, db, s));
+  if (dsb) SSV_CUDA(cudaMemcpyAsync(dsb, U, sizeof(float) * B * n, cudaMemcpyDeviceToDevice, s));
+  // dgrad: dX = dH W through the forward's conv kernel (W as the [K = n][N = cin] operand)
+  if (dx) {
+    const int k_p = round_up(n, 16);
+    float *Wd, *zero_bias, *dxr;
+    SSV_TRY(ar.alloc<float>((size_t)k_p * x_ld, &Wd));
+    SSV_TRY(ar.alloc<float>((size_t)x_ld, &zero_bias));
+    SSV_TRY(ar.alloc<float>((size_t)M * x_ld, &dxr));
+    SSV_TRY(launch_pad_matrix(w, n, cin, k_p, x_ld, Wd, s));
+    SSV_CUDA(cudaMemsetAsync(zero_bias, 0, sizeof(float) * x_ld, s));
+    ConvPack g;
+    g.W = Wd; g.bias = zero_bias; g.cin = n; g.cin_p = k_p; g.k = 1; g.n = cin; g.n_pad = x_ld;
+    SSV_TRY(run_conv(g, EPI_NONE, 1, 0, dH, n_pad, T, B, dxr, x_ld, s));
+    if (relu_in) SSV_TRY(launch_relu_mask(dxr, xin, (long)M * x_ld, s));
+    SSV_TRY(launch_transpose_out(dxr, x_ld, B, cin, T, dx, s));
+  }
+  SSV_TRY(launch_wgrad_plain(dH, n_pad, xin, x_ld, M, n, cin, P, dw, s));
+  return kOk;
+}
+
+// Unmasked softmax attention of the train branch (models/TTSModel.py:268-272): kv (B, 512, N) = [K ; V] as TextEnc emits
+// them, q (B, 256, T) -> A (B, N, T), rq (B, 512, T) = [V A ; q].
+int ssv_attention_train_fwd(const float* kv, const float* q, int B, int N, int T, float* A, float* rq, void* stream) {
+  SSV_CHECK(kv && q && A && rq, "attention_train_fwd: null pointer");
+  SSV_CHECK(B > 0 && N > 0 && T > 0, "attention_train_fwd: empty input");
+  cudaStream_t s = as_stream(stream);
+  Arena ar(s);
+  float *Kx, *Qt, *RQ;
+  SSV_TRY(ar.alloc<float>((size_t)B * N * 512, &Kx));
+  SSV_TRY(ar.alloc<float>((size_t)B * T * 256, &Qt));
+  SSV_TRY(ar.alloc<float>((size_t)B * T * 512, &RQ));
+  SSV_TRY(launch_transpose_in(kv, (long)512 * N, N, 1, B, 512, N, Kx, 512, s));
+  SSV_TRY(launch_transpose_in(q, (long)256 * T, T, 1, B, 256, T, Qt, 256, s));
+  SSV_TRY(launch_train_attention(Kx, Qt, B, N, T, A, RQ, s));
+  SSV_TRY(launch_transpose_out(RQ, 512, B, 512, T, rq, s));
+  return kOk;
+}
+
+// dA may be null (no loss term on the alignment).  drq is the gradient of [R ; q]; dq collects both of q's paths.
+int ssv_attention_train_bwd(const float* kv, const float* q, const float* A, const float* dA, const float* drq, int B, int N, int T,
+                            float* dkv, float* dq, void* stream) {
+  SSV_CHECK(kv && q && A && drq && dkv && dq, "attention_train_bwd: null pointer");
+  SSV_CHECK(B > 0 && N > 0 && T > 0, "attention_train_bwd: empty input");
+  cudaStream_t s = as_stream(stream);
+  Arena ar(s);
+  float *Kx, *Qt, *dRQ, *dS, *dqr, *dKx;
+  SSV_TRY(ar.alloc<float>((size_t)B * N * 512, &Kx));
+  SSV_TRY(ar.alloc<float>((size_t)B * T * 256, &Qt));
+  SSV_TRY(ar.alloc<float>((size_t)B * T * 512, &dRQ));
+  SSV_TRY(ar.alloc<float>((size_t)B * N * T, &dS));
+  SSV_TRY(ar.alloc<float>((size_t)B * T * 256, &dqr));
+  SSV_TRY(ar.alloc<float>((size_t)B * N * 512, &dKx));
+  SSV_TRY(launch_transpose_in(kv, (long)512 * N, N, 1, B, 512, N, Kx, 512, s));
+  SSV_TRY(launch_transpose_in(q, (long)256 * T, T, 1, B, 256, T, Qt, 256, s));
+  SSV_TRY(launch_transpose_in(drq, (long)512 * T, T, 1, B, 512, T, dRQ, 512, s));
+  SSV_TRY(launch_att_bwd(Kx, Qt, dRQ, 512, dRQ + 256, A, dA, B, N, T, dS, dqr, dKx, s));
+  SSV_TRY(launch_transpose_out(dKx, 512, B, 512, N, dkv, s));
+  SSV_TRY(launch_transpose_out(dqr, 256, B, 256, T, dq, s));
+  return kOk;
+}
+
+// textEmbedding (models/TTSModel.py:25-35) as a column gather: ids (B, N), weight (E, vocab), bias (E) -> y (B, E, N)
+int ssv_text_embedding_fwd(const int64_t* ids, const float* weight, const float* bias, int B, int N, int vocab, int E, float* y,
+                           void* stream) {
+  SSV_CHECK(ids && weight && bias && y, "text_embedding_fwd: null pointer");
+  SSV_CHECK(B > 0 && N > 0 && vocab > 0 && E > 0, "text_embedding_fwd: empty input");
+  cudaStream_t s = as_stream(stream);
+  Arena ar(s);
+  float *Wt, *rows;
+  int* flag;
+  SSV_TRY(ar.alloc<float>((size_t)vocab * E, &Wt));
+  SSV_TRY(ar.alloc<float>((size_t)B * N * E, &rows));
+  SSV_TRY(ar.alloc<int>(1, &flag));
+  SSV_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  SSV_TRY(launch_transpose_in(weight, 0, vocab, 1, 1, E, vocab, Wt, E, s));        // (E, vocab) -> (vocab, E)
+  SSV_TRY(launch_embed(ids, B, N, Wt, bias, vocab, E, rows, E, flag, s));
+  SSV_TRY(launch_transpose_out(rows, E, B, E, N, y, s));
+  return kOk;
+}
+
+int ssv_text_embedding_bwd(const int64_t* ids, const float* dy, int B, int N, int vocab, int E, float* dweight, float* dbias,
+                           void* stream) {
+  SSV_CHECK(ids && dy && dweight && dbias, "text_embedding_bwd: null pointer");
+  SSV_CHECK(B > 0 && N > 0 && vocab > 0 && E > 0, "text_embedding_bwd: empty input");
+  cudaStream_t s = as_stream(stream);
+  Arena ar(s);
+  float *rows, *dWt;
+  SSV_TRY(ar.alloc<float>((size_t)B * N * E, &rows));
+  SSV_TRY(ar.alloc<float>((size_t)vocab * E, &dWt));
+  SSV_TRY(launch_transpose_in(dy, (long)E * N, N, 1, B, E, N, rows, E, s));
+  SSV_TRY(launch_embed_bwd(ids, B * N, rows, E, vocab, E, dWt, dbias, s));
+  SSV_TRY(launch_transpose_out(dWt, E, 1, E, vocab, dweight, s));                   // (vocab, E) -> (E, vocab)
+  return kOk;
+}
+
+// Speaker projections fc1 / fc2 (models/TTSModel.py:172-173): y (B, out) = x (B, in) W^T + b, and the parameter gradients
+int ssv_linear_small_fwd(const float* x, const float* w, const float* b, int B, int in_f, int out_f, float* y, void* stream) {
+  SSV_CHECK(x && w && b && y && B > 0 && in_f > 0 && out_f > 0, "linear_small_fwd: bad arguments");
+  return launch_linear_small(x, in_f, w, b, B, in_f, out_f, y, out_f, as_stream(stream));
+}
+int ssv_linear_small_bwd(const float* x, const float* dy, int B, int in_f, int out_f, float* dw, float* db, void* stream) {
+  SSV_CHECK(x && dy && dw && db && B > 0 && in_f > 0 && out_f > 0, "linear_small_bwd: bad arguments");
+  return launch_linear_small_bwd(dy, out_f, x, in_f, B, in_f, out_f, dw, db, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
 static int fill_stage(ssv_text2mel* m, const ParamMap& pm, int idx, const std::string& conv, int n, int cin, int k,
                       int dil, int pro, const float* g1, const float* b1, const float* g2, const float* b2,
                       int hist_in, int res_hist, int bias_b, cudaStream_t s) {

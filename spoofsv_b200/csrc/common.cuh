@@ -111,6 +111,27 @@ int wgrad_chunks(int M);
 int launch_wgrad(const float* dH, const float* X, int M, int T, int d, int k, int dil, int causal,
                  float* P /*[chunks][k][2d][d]*/, float* dW /*(2d,d,k)*/, cudaStream_t s);
 
+// ---- the small layers of the training graph (train_small.cu) ----
+int launch_ln_rows_fwd(const float* H, int ldh, int M, int n, const float* g, const float* b, float* Y, int ldy, cudaStream_t s);
+int ln_bwd_row_blocks(int M);
+int ln_bwd_partial_cols(int n);                                     // columns of one block's partial: (d gamma | d beta), padded
+int launch_ln_rows_bwd(const float* H, int ldh, const float* dY, int ldy, int M, int n, const float* g, float* dH,
+                       float* partial /*[blocks][ln_bwd_partial_cols(n)]*/, cudaStream_t s);
+int launch_utt_colsum(const float* X, int ld, int B, int T, int n, float* U /*[B][n]*/, cudaStream_t s);
+int launch_relu_rows(float* x, long n, cudaStream_t s);
+int launch_relu_mask(float* dx, const float* x, long n, cudaStream_t s);
+int launch_pad_matrix(const float* src, int n_rows, int n_cols, int rows, int ld, float* dst, cudaStream_t s);
+int wgrad_plain_chunks(int M);
+int launch_wgrad_plain(const float* dH, int ldh, const float* X, int ldx, int M, int n, int cin, float* P /*[chunks][n][cin]*/,
+                       float* dW /*(n, cin)*/, cudaStream_t s);
+int launch_att_bwd(const float* Kx /*(B,N,512)*/, const float* Q /*(B,T,256)*/, const float* dR, int ldr, const float* dq_add,
+                   const float* A, const float* dA, int B, int N, int T, float* dS /*(B,N,T)*/, float* dq /*(B,T,256)*/,
+                   float* dKx /*(B,N,512)*/, cudaStream_t s);
+int launch_embed_bwd(const int64_t* ids, int rows, const float* dX, int ld, int vocab, int E, float* dWt /*[vocab][E]*/, float* dbias,
+                     cudaStream_t s);
+int launch_linear_small_bwd(const float* dS, int ds_ld, const float* x, long x_ld, int B, int in_f, int out_f, float* dW, float* db,
+                            cudaStream_t s);
+
 size_t griffin_lim_workspace_floats(int B, int T);                 // griffinlim.cu
 int launch_griffin_lim(const float* S /*(B,513,T)*/, const float* angles0_ri /*(B,513,T,2)*/, int B, int T, int n_iter,
                        float momentum, float* y /*(B, 256 (T-1))*/, float* workspace, cudaStream_t s);

@@ -98,6 +98,38 @@ def output_name(spk: str, sentence: int) -> str:
     return f"s{spk[1:]}/s{spk[1:]}_{str(sentence + 1).zfill(3)}"
 
 
+class _HostPipe:
+    """Device -> host copies of the spectrogram batches on a side stream into two alternating pinned buffers."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.stream = torch.cuda.Stream()
+        self.bufs = [None, None]
+        self.k = 0
+
+    def submit(self, t):
+        torch = self.torch
+        k = self.k
+        self.k ^= 1
+        if self.bufs[k] is None or self.bufs[k].shape != t.shape:
+            self.bufs[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        ready = torch.cuda.Event()
+        ready.record()                                   # the producing kernels on the current stream
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.bufs[k].copy_(t, non_blocking=True)
+            done.record()
+        t.record_stream(self.stream)                     # the allocator must not hand the device buffer out before the copy ran
+        return k, done
+
+    def collect(self, ticket):
+        k, done = ticket
+        done.synchronize()
+        return self.bufs[k].numpy()                      # valid until the second-next submit
+
+
 def run(args, on_batch=None) -> Dict[str, float]:
     import torch
     from .models.TTSModel import SSRN, melSyn
@@ -135,7 +167,23 @@ def run(args, on_batch=None) -> Dict[str, float]:
     K, V = m1.encode_text(torch.from_numpy(text_id)[:, None, :].cuda())    # once: K/V do not depend on the speaker
     lib = _lib.load()
     batches = plan(len(speakers), text_id.shape[0], world, rank, args.batch)
+    want_host = on_batch is not None or bool(args.save_spectrogram)
+    pipe = _HostPipe() if want_host else None
     n_utt, t0 = 0, time.perf_counter()
+
+    def finish(job):
+        """Second half of a batch, one batch behind the launches: host copy done -> callbacks and files."""
+        group, ticket, state = job
+        lin = pipe.collect(ticket)
+        if on_batch is not None:
+            on_batch(group, lin, state)
+        if args.save_spectrogram:
+            for u, spec in zip(group, lin):
+                path = Path(args.save_spectrogram) / (output_name(speakers[u.speaker], u.sentence) + ".npy")
+                path.parent.mkdir(parents=True, exist_ok=True)
+                np.save(path, spec)
+
+    pending = None
     with torch.no_grad():
         for group in batches:
             sent = torch.tensor([u.sentence for u in group], device="cuda")
@@ -143,6 +191,13 @@ def run(args, on_batch=None) -> Dict[str, float]:
             dec = m1._begin(K[sent].contiguous(), V[sent].contiguous(), spk, frames)
             _lib.check(lib.ssv_decoder_run(dec, frames, _lib.current_stream_ptr()))
             lin_d = m2(m1._state["Y"])                                      # (B, 513, 4T), the reference's pred_lin
+            # the spectrogram batch (114 MB at 64 utterances) crosses PCIe only when somebody wants it on the host, and
+            # then on a copy stream into one of two pinned buffers, under the next batch's decode (the same overlap
+            # as ssv_synthesize_host_submit / _wait, with the text encoder hoisted out of the loop)
+            job = None
+            if want_host:
+                st = m1._state
+                job = (group, pipe.submit(lin_d), {"Y": st["Y"].clone(), "A": st["A"].clone(), "traj": st["traj"].clone()})
             if args.save_wav:
                 from . import vocoder
                 waves = vocoder.postprocess(lin_d, cfg, n_iter=args.gl_iters)
@@ -150,17 +205,13 @@ def run(args, on_batch=None) -> Dict[str, float]:
                     path = Path(args.save_wav) / (output_name(speakers[u.speaker], u.sentence) + ".wav")
                     path.parent.mkdir(parents=True, exist_ok=True)
                     vocoder.write_wav(path, w, cfg["SAMPLING_RATE"])
-            # the 114 MB spectrogram batch crosses PCIe only when somebody wants it on the host
-            lin = lin_d.cpu().numpy() if (on_batch is not None or args.save_spectrogram) else None
-            m1.check()
+            if pending is not None:
+                finish(pending)
+            pending = job
             n_utt += len(group)
-            if on_batch is not None:
-                on_batch(group, lin, m1._state)
-            if args.save_spectrogram:
-                for u, spec in zip(group, lin):
-                    path = Path(args.save_spectrogram) / (output_name(speakers[u.speaker], u.sentence) + ".npy")
-                    path.parent.mkdir(parents=True, exist_ok=True)
-                    np.save(path, spec)
+        if pending is not None:
+            finish(pending)
+        m1.check()
     sec = time.perf_counter() - t0
     stats = {"rank": rank, "world": world, "utterances": n_utt, "frames": frames, "seconds": sec,
              "frames_per_s": n_utt * frames / sec if sec > 0 else 0.0}

@@ -183,6 +183,132 @@ class _HighwayConvFn(torch.autograd.Function):
         return (dx, *grads, None, None, None)
 
 
+class _ConvLnFn(torch.autograd.Function):
+    """1x1 conv (+ per-utterance bias) + LayerNorm with a hand-written backward (ssv_conv_ln_fwd_save / ssv_conv_ln_bwd):
+    the eleven plain layers of Text2Mel (models/TTSModel.py:128-131, 173-180, 218-230), FP32.  relu_in folds the ReLU the
+    reference applies to the layer's input."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, sb, g, beta, relu_in):
+        xs = x.detach().to(torch.float32).contiguous()
+        ws, bs, gs, betas = (p.detach().contiguous() for p in (w, b, g, beta))
+        sbs = None if sb is None else sb.detach().to(torch.float32).contiguous()
+        B, cin, T = xs.shape
+        n = ws.shape[0]
+        y = torch.empty((B, n, T), device=xs.device, dtype=torch.float32)
+        h = torch.empty((B * T, (n + 63) // 64 * 64), device=xs.device, dtype=torch.float32)
+        _lib.check(_lib.load().ssv_conv_ln_fwd_save(
+            xs.data_ptr(), ws.data_ptr(), bs.data_ptr(), None if sbs is None else sbs.data_ptr(), gs.data_ptr(), betas.data_ptr(),
+            B, cin, n, T, int(relu_in), y.data_ptr(), h.data_ptr(), _lib.current_stream_ptr()))
+        ctx.save_for_backward(xs, ws, gs, h)
+        ctx.cfg = (bool(relu_in), sbs is not None, ctx.needs_input_grad[0])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        relu_in, has_sb, need_dx = ctx.cfg
+        x, w, g, h = ctx.saved_tensors
+        B, cin, T = x.shape
+        n = w.shape[0]
+        dy = dy.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.empty_like(w)
+        db = torch.empty((n,), device=x.device, dtype=torch.float32)
+        dsb = torch.empty((B, n), device=x.device, dtype=torch.float32) if has_sb else None
+        dg, dbeta = torch.empty_like(db), torch.empty_like(db)
+        _lib.check(_lib.load().ssv_conv_ln_bwd(
+            x.data_ptr(), dy.data_ptr(), w.data_ptr(), g.data_ptr(), h.data_ptr(), B, cin, n, T, int(relu_in),
+            None if dx is None else dx.data_ptr(), dw.data_ptr(), db.data_ptr(), None if dsb is None else dsb.data_ptr(),
+            dg.data_ptr(), dbeta.data_ptr(), _lib.current_stream_ptr()))
+        return dx, dw, db, dsb, dg, dbeta, None
+
+
+class _AttentionTrainFn(torch.autograd.Function):
+    """Unmasked softmax attention of the train branch (models/TTSModel.py:268-272): kv = [K ; V] (B, 512, N),
+    q (B, 256, T) -> A (B, N, T), [V A ; q] (B, 512, T); backward in ssv_attention_train_bwd."""
+
+    @staticmethod
+    def forward(ctx, kv, q):
+        kvs, qs = kv.detach().to(torch.float32).contiguous(), q.detach().to(torch.float32).contiguous()
+        B, _, N = kvs.shape
+        T = qs.shape[-1]
+        A = torch.empty((B, N, T), device=qs.device, dtype=torch.float32)
+        rq = torch.empty((B, 512, T), device=qs.device, dtype=torch.float32)
+        _lib.check(_lib.load().ssv_attention_train_fwd(kvs.data_ptr(), qs.data_ptr(), B, N, T, A.data_ptr(), rq.data_ptr(),
+                                                       _lib.current_stream_ptr()))
+        ctx.save_for_backward(kvs, qs, A)
+        return A, rq
+
+    @staticmethod
+    def backward(ctx, dA, drq):
+        kv, q, A = ctx.saved_tensors
+        B, _, N = kv.shape
+        T = q.shape[-1]
+        drq = (torch.zeros((B, 512, T), device=q.device) if drq is None else drq.detach().to(torch.float32)).contiguous()
+        dA = None if dA is None else dA.detach().to(torch.float32).contiguous()
+        dkv, dq = torch.empty_like(kv), torch.empty_like(q)
+        _lib.check(_lib.load().ssv_attention_train_bwd(kv.data_ptr(), q.data_ptr(), A.data_ptr(), None if dA is None else dA.data_ptr(),
+                                                       drq.data_ptr(), B, N, T, dkv.data_ptr(), dq.data_ptr(),
+                                                       _lib.current_stream_ptr()))
+        return dkv, dq
+
+
+class _TextEmbeddingFn(torch.autograd.Function):
+    """textEmbedding (models/TTSModel.py:25-35) as a column gather of W.weight + bias; backward sums per vocabulary id."""
+
+    @staticmethod
+    def forward(ctx, ids, weight, bias):
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        idc = ids.detach().to(torch.int64).contiguous()
+        B, N = idc.shape
+        E, vocab = w.shape
+        y = torch.empty((B, E, N), device=w.device, dtype=torch.float32)
+        _lib.check(_lib.load().ssv_text_embedding_fwd(idc.data_ptr(), w.data_ptr(), b.data_ptr(), B, N, vocab, E, y.data_ptr(),
+                                                      _lib.current_stream_ptr()))
+        ctx.save_for_backward(idc)
+        ctx.shape = (E, vocab)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        E, vocab = ctx.shape
+        B, N = ids.shape
+        dy = dy.detach().to(torch.float32).contiguous()
+        dw = torch.empty((E, vocab), device=dy.device, dtype=torch.float32)
+        db = torch.empty((E,), device=dy.device, dtype=torch.float32)
+        _lib.check(_lib.load().ssv_text_embedding_bwd(ids.data_ptr(), dy.data_ptr(), B, N, vocab, E, dw.data_ptr(), db.data_ptr(),
+                                                      _lib.current_stream_ptr()))
+        return None, dw, db
+
+
+class _LinearSmallFn(torch.autograd.Function):
+    """Speaker projection fc1 / fc2 (models/TTSModel.py:172-173): (B, in) -> (B, out); the input needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xs, w, b = x.detach().to(torch.float32).contiguous(), weight.detach().contiguous(), bias.detach().contiguous()
+        B, in_f = xs.shape
+        out_f = w.shape[0]
+        y = torch.empty((B, out_f), device=xs.device, dtype=torch.float32)
+        _lib.check(_lib.load().ssv_linear_small_fwd(xs.data_ptr(), w.data_ptr(), b.data_ptr(), B, in_f, out_f, y.data_ptr(),
+                                                    _lib.current_stream_ptr()))
+        ctx.save_for_backward(xs)
+        ctx.shape = (in_f, out_f)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        in_f, out_f = ctx.shape
+        dy = dy.detach().to(torch.float32).contiguous()
+        dw = torch.empty((out_f, in_f), device=x.device, dtype=torch.float32)
+        db = torch.empty((out_f,), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().ssv_linear_small_bwd(x.data_ptr(), dy.data_ptr(), x.shape[0], in_f, out_f, dw.data_ptr(), db.data_ptr(),
+                                                    _lib.current_stream_ptr()))
+        return None, dw, db
+
+
 class melSyn(_Native):
     """Text2Mel.  reference models/TTSModel.py:234-300."""
 
@@ -401,20 +527,17 @@ class melSyn(_Native):
         """Train branch (:263-273) WITH an autograd graph, for `loss.backward()` of the training step
         (train/adversarial_wasserstein_gp.py:277-300).  The 38 highway convs -- 98 % of the TextEnc, 96 % of the
         AudioEnc and 87 % of the AudioDec FLOPs -- run forward and backward in the library's kernels
-        (`_HighwayConvFn`); the eleven 1x1 conv + LayerNorm layers, the embedding gather, the two speaker
-        projections and the unmasked attention are FP32 torch ops for now (TF32 off, so the result stays within
-        the 1e-4 bar)."""
+        (`_HighwayConvFn`), and so do the eleven 1x1 conv + LayerNorm layers (`_ConvLnFn`), the embedding gather, the
+        two speaker projections and the unmasked attention (csrc/train_small.cu); what is left to torch is the final
+        sigmoid and the graph bookkeeping."""
         import torch.nn.functional as F
         _lib.require_cuda(melspec, "melSyn.forward melspec")
         if textid is None:
             raise ValueError("melSyn.forward in train() mode needs textid")
         te, ae, ad = self.text_encoder, self.audio_encoder, self.audio_decoder
 
-        def ln(x, m):
-            return F.layer_norm(x.transpose(1, 2), (m.weight.numel(),), m.weight, m.bias, 1e-5).transpose(1, 2)
-
-        def pw(x, m):                                   # 1x1 conv as an FP32 matmul (cuDNN would pick TF32)
-            return torch.matmul(m.weight[:, :, 0], x) + m.bias[None, :, None]
+        def cl(x, conv, lnm, relu_in=False, sb=None):       # 1x1 conv (+ speaker term) + LayerNorm, fwd / bwd in the library
+            return _ConvLnFn.apply(x, conv.weight, conv.bias, sb, lnm.weight, lnm.bias, relu_in)
 
         def hc(x, bag, k, dil, causal):
             return _HighwayConvFn.apply(x, bag.conv.weight, bag.conv.bias, bag.ln1.weight, bag.ln1.bias, bag.ln2.weight,
@@ -429,35 +552,33 @@ class melSyn(_Native):
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
             ids = textid.long()[:, 0, :]
-            x = (te.textemb_layer.W.weight.t()[ids] + te.textemb_layer.W.bias).transpose(1, 2)
-            x = ln(pw(x, te.conv1), te.ln1)
-            x = ln(pw(F.relu(x), te.conv2), te.ln2)
+            x = _TextEmbeddingFn.apply(ids, te.textemb_layer.W.weight, te.textemb_layer.W.bias)
+            x = cl(x, te.conv1, te.ln1)
+            x = cl(x, te.conv2, te.ln2, relu_in=True)
             x = hci(hci(x, te.hci1, False), te.hci2, False)
             for bag, k in ((te.hc1, 3), (te.hc2, 3), (te.hc3, 1), (te.hc4, 1)):
                 x = hc(x, bag, k, 1, False)
-            h = x.shape[1] // 2
-            K, V = x[:, :h], x[:, h:]
+            kv = x                                          # [K ; V] (B, 2 hidden, N)
 
             mel = melspec.to(torch.float32)
-            spk = spkemb.to(torch.float32).transpose(1, 2)
-            s1 = F.linear(spk, ae.fc1.weight, ae.fc1.bias).transpose(1, 2)
-            s2 = F.linear(spk, ae.fc2.weight, ae.fc2.bias).transpose(1, 2)
-            q = ln(pw(mel, ae.conv1) + s1, ae.ln1)
-            q = ln(pw(F.relu(q), ae.conv2), ae.ln2)
-            q = ln(pw(F.relu(q), ae.conv3) + s2, ae.ln3)
+            spk = spkemb.to(torch.float32)[:, :, 0]
+            s1 = _LinearSmallFn.apply(spk, ae.fc1.weight, ae.fc1.bias)
+            s2 = _LinearSmallFn.apply(spk, ae.fc2.weight, ae.fc2.bias)
+            q = cl(mel, ae.conv1, ae.ln1, sb=s1)
+            q = cl(q, ae.conv2, ae.ln2, relu_in=True)
+            q = cl(q, ae.conv3, ae.ln3, relu_in=True, sb=s2)
             q = hci(hci(q, ae.hci1, True), ae.hci2, True)
             q = hc(hc(q, ae.hc1, 3, 3, True), ae.hc2, 3, 3, True)
 
-            A = torch.softmax(torch.matmul(K.transpose(1, 2), q) / (h ** 0.5), dim=1)
-            r = torch.cat((torch.matmul(V, A), q), dim=1)
+            A, r = _AttentionTrainFn.apply(kv, q)           # r = [V A ; q]
 
-            y = ln(pw(r, ad.conv1), ad.ln1)
+            y = cl(r, ad.conv1, ad.ln1)
             y = hci(y, ad.hci, True)
             y = hc(hc(y, ad.hc1, 3, 1, True), ad.hc2, 3, 1, True)
-            y = ln(pw(y, ad.conv2), ad.ln2)
-            y = ln(pw(F.relu(y), ad.conv3), ad.ln3)
-            y = ln(pw(F.relu(y), ad.conv4), ad.ln4)
-            y = ln(pw(F.relu(y), ad.conv5), ad.ln5)
+            y = cl(y, ad.conv2, ad.ln2)
+            y = cl(y, ad.conv3, ad.ln3, relu_in=True)
+            y = cl(y, ad.conv4, ad.ln4, relu_in=True)
+            y = cl(y, ad.conv5, ad.ln5, relu_in=True)
             return torch.sigmoid(y), A
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
