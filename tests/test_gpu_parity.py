@@ -605,6 +605,101 @@ def test_highway_conv_backward_vs_autograd(d, k, dil, causal, B, T, save_h, monk
         assert float((g.detach().cpu().double() - w).abs().max()) <= 2e-5 * max(scale, 1.0), (g.shape, scale)
 
 
+def _grad_close(got, want, tol=2e-5):
+    assert got.shape == want.shape
+    scale = max(float(want.abs().max()), 1.0)
+    assert float((got.detach().cpu().double() - want).abs().max()) <= tol * scale, (tuple(got.shape), scale)
+
+
+@pytest.mark.parametrize("cin,n,relu_in,with_sb,B,T", [(80, 256, False, True, 3, 37), (256, 256, True, False, 2, 70),
+                                                        (512, 256, False, False, 1, 5), (256, 80, True, False, 3, 129),
+                                                        (128, 512, False, False, 2, 33), (256, 256, True, True, 4, 9)])
+def test_conv_ln_forward_backward_vs_autograd(cin, n, relu_in, with_sb, B, T):
+    """ssv_conv_ln_fwd_save / ssv_conv_ln_bwd (the eleven 1x1 conv + LayerNorm layers of Text2Mel,
+    models/TTSModel.py:128-131, 173-180, 218-230) against float64 autograd of the same torch statements: output and the
+    gradients of the input, the conv, the per-utterance speaker term and the LayerNorm; ragged row counts, the 80-bin
+    layers, a batch of one."""
+    import torch.nn.functional as F
+    from spoofsv_b200.models.TTSModel import _ConvLnFn
+    g = torch.Generator().manual_seed(cin + n + T)
+    x = torch.randn((B, cin, T), generator=g)
+    w = torch.randn((n, cin, 1), generator=g) / cin ** 0.5
+    b, gam, bet = (torch.randn((n,), generator=g) * s + o for s, o in ((0.1, 0.0), (0.2, 1.0), (0.1, 0.0)))
+    sb = torch.randn((B, n), generator=g) * 0.3 if with_sb else None
+    gy = torch.randn((B, n, T), generator=g)
+    dev = [t.cuda().requires_grad_(True) for t in (x, w, b, gam, bet)]
+    sbd = sb.cuda().requires_grad_(True) if with_sb else None
+    y = _ConvLnFn.apply(dev[0], dev[1], dev[2], sbd, dev[3], dev[4], relu_in)
+    y.backward(gy.cuda())
+    ref = [t.double().requires_grad_(True) for t in (x, w, b, gam, bet)]
+    sbr = sb.double().requires_grad_(True) if with_sb else None
+    h = F.conv1d(F.relu(ref[0]) if relu_in else ref[0], ref[1], ref[2])
+    if with_sb:
+        h = h + sbr[:, :, None]
+    yo = F.layer_norm(h.transpose(1, 2), (n,), ref[3], ref[4], 1e-5).transpose(1, 2)
+    yo.backward(gy.double())
+    assert _maxabs(y, yo.float()) <= FP32_TOL
+    for got, want in zip(dev, ref):
+        _grad_close(got.grad, want.grad)
+    if with_sb:
+        _grad_close(sbd.grad, sbr.grad)
+
+
+@pytest.mark.parametrize("B,N,T", [(2, 13, 21), (1, 64, 217), (3, 1, 4)])
+def test_train_attention_forward_backward_vs_autograd(B, N, T):
+    """ssv_attention_train_fwd / _bwd (models/TTSModel.py:268-272: A = softmax(K^T q / sqrt(d)) over the characters,
+    R = V A, [R ; q]) against float64 autograd, with a loss on the alignment as well (the guided-attention term)."""
+    from spoofsv_b200.models.TTSModel import _AttentionTrainFn
+    g = torch.Generator().manual_seed(B * 100 + N)
+    kv = torch.randn((B, 512, N), generator=g)
+    q = torch.randn((B, 256, T), generator=g)
+    gA, gr = torch.randn((B, N, T), generator=g), torch.randn((B, 512, T), generator=g)
+    kvd, qd = kv.cuda().requires_grad_(True), q.cuda().requires_grad_(True)
+    A, rq = _AttentionTrainFn.apply(kvd, qd)
+    ((A * gA.cuda()).sum() + (rq * gr.cuda()).sum()).backward()
+    kvr, qr = kv.double().requires_grad_(True), q.double().requires_grad_(True)
+    Ao = torch.softmax(torch.matmul(kvr[:, :256].transpose(1, 2), qr) / 16.0, dim=1)
+    ro = torch.cat((torch.matmul(kvr[:, 256:], Ao), qr), dim=1)
+    ((Ao * gA.double()).sum() + (ro * gr.double()).sum()).backward()
+    assert _maxabs(A, Ao.float()) <= 1e-5 and _maxabs(rq, ro.float()) <= FP32_TOL
+    _grad_close(kvd.grad, kvr.grad)
+    _grad_close(qd.grad, qr.grad)
+
+
+def test_text_embedding_and_speaker_projection_vs_autograd():
+    """textEmbedding as a gather (models/TTSModel.py:25-35) and the speaker projections (:172-173), forward and
+    parameter gradients against float64 autograd of the reference's statements."""
+    import torch.nn.functional as F
+    from spoofsv_b200.models.TTSModel import _LinearSmallFn, _TextEmbeddingFn
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 34, (3, 17), generator=g)
+    W_, b_ = torch.randn((128, 34), generator=g), torch.randn((128,), generator=g)
+    gy = torch.randn((3, 128, 17), generator=g)
+    wd, bd = W_.cuda().requires_grad_(True), b_.cuda().requires_grad_(True)
+    y = _TextEmbeddingFn.apply(ids.cuda(), wd, bd)
+    y.backward(gy.cuda())
+    wr, br = W_.double().requires_grad_(True), b_.double().requires_grad_(True)
+    onehot = F.one_hot(ids, 34).double()                                   # the reference's scatter + Linear
+    yo = F.linear(onehot, wr, br).transpose(1, 2)
+    yo.backward(gy.double())
+    assert _maxabs(y, yo.float()) <= 1e-6
+    _grad_close(wd.grad, wr.grad)
+    _grad_close(bd.grad, br.grad)
+
+    x = torch.randn((5, 200), generator=g)
+    W2, b2 = torch.randn((256, 200), generator=g) / 14, torch.randn((256,), generator=g)
+    g2 = torch.randn((5, 256), generator=g)
+    w2d, b2d = W2.cuda().requires_grad_(True), b2.cuda().requires_grad_(True)
+    s = _LinearSmallFn.apply(x.cuda(), w2d, b2d)
+    s.backward(g2.cuda())
+    w2r, b2r = W2.double().requires_grad_(True), b2.double().requires_grad_(True)
+    so = F.linear(x.double(), w2r, b2r)
+    so.backward(g2.double())
+    assert _maxabs(s, so.float()) <= 1e-5
+    _grad_close(w2d.grad, w2r.grad)
+    _grad_close(b2d.grad, b2r.grad)
+
+
 @pytest.mark.parametrize("B,N,T", [(2, 11, 14), (5, 23, 131)])
 def test_text2mel_training_backward_vs_autograd(B, N, T, cuda_models_k):
     """loss.backward() through the train branch (train/adversarial_wasserstein_gp.py:277-300): every parameter
