@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(NT, 2) conv_bf16_v2_kernel(const __grid_consta
       if (hwy) {
         tmem_wait16(r1);
         float xr[16];
-#pragma unroll
         const bf16x8 xr0 = xrs[(c >> 3) & 7], xr1 = xrs[((c >> 3) + 1) & 7];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
