@@ -1516,6 +1516,28 @@ static int synth_enqueue(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const in
         SSV_TRY(launch_cast_f32_to_bf16(lin_dev + b0 * lin_per_utt, d->h_lin16[slot] + b0 * lin_per_utt, nb * lin_per_utt, s));
       SSV_CUDA(cudaEventRecord(d->copy_ev[ci & 1], s));
       SSV_CUDA(cudaStreamWaitEvent(d->copy_stream, d->copy_ev[ci & 1], 0));
+      if (b0 + chunk >= B) {
+        // Every device->host copy of the batch rides the copy stream, the small ones AHEAD of the last spectrogram
+        // chunk.  (They used to follow on the compute stream: behind the 228 MB spectrogram copy in the DMA engine's
+        // queue, and the next batch's kernels behind them in stream order -- every other batch completed 4 ms late
+        // at 256 utterances.)  The compute stream only waits for the small ones, whose sources the next batch's
+        // decoder overwrites.
+        cudaStream_t cs = d->copy_stream;
+        if (mel_host) SSV_CUDA(cudaMemcpyAsync(mel_host, d->h_Y, sizeof(float) * (size_t)B * F * T, cudaMemcpyDeviceToHost, cs));
+        if (A_host) SSV_CUDA(cudaMemcpyAsync(A_host, d->h_A, sizeof(float) * (size_t)B * N * T, cudaMemcpyDeviceToHost, cs));
+        if (pma_traj_host)
+          SSV_CUDA(cudaMemcpyAsync(pma_traj_host, d->h_traj, sizeof(long long) * (size_t)T * B, cudaMemcpyDeviceToHost, cs));
+        // error flags of this batch (decode abort, bad text id, tensor-core pipeline timeouts) -> pinned host words
+        SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot, d->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot + 1, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        int* tcf[3] = {tc_err_flag_dev(), tc2_err_flag_dev(), tf32_err_flag_dev()};
+        for (int i = 0; i < 3; ++i) {
+          d->h_flags[8 * slot + 2 + i] = 0;
+          if (tcf[i]) SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot + 2 + i, tcf[i], sizeof(int), cudaMemcpyDeviceToHost, cs));
+        }
+        SSV_CUDA(cudaEventRecord(d->done_ev[slot], cs));
+        SSV_CUDA(cudaStreamWaitEvent(s, d->done_ev[slot], 0));
+      }
       if (d->lin_out_bf16)
         SSV_CUDA(cudaMemcpyAsync(reinterpret_cast<__nv_bfloat16*>(lin_host) + b0 * lin_per_utt, d->h_lin16[slot] + b0 * lin_per_utt,
                                  sizeof(__nv_bfloat16) * nb * lin_per_utt, cudaMemcpyDeviceToHost, d->copy_stream));
@@ -1525,24 +1547,6 @@ static int synth_enqueue(ssv_text2mel* m, ssv_decoder* d, ssv_ssrn* sr, const in
     }
     SSV_CUDA(cudaEventRecord(d->lin_ev[slot], d->copy_stream));
   }
-  if (mel_host) SSV_CUDA(cudaMemcpyAsync(mel_host, d->h_Y, sizeof(float) * (size_t)B * F * T, cudaMemcpyDeviceToHost, s));
-  if (A_host) SSV_CUDA(cudaMemcpyAsync(A_host, d->h_A, sizeof(float) * (size_t)B * N * T, cudaMemcpyDeviceToHost, s));
-  if (pma_traj_host)
-    SSV_CUDA(cudaMemcpyAsync(pma_traj_host, d->h_traj, sizeof(long long) * (size_t)T * B, cudaMemcpyDeviceToHost, s));
-  // error flags of this batch (decode abort, bad text id) -> pinned host words, read by the wait
-  SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot, d->abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot + 1, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  {
-    // pipeline-timeout flags of the tensor-core kernels: fetched in stream order like the others.  (They used to be read
-    // in the wait with a synchronous cudaMemcpy, which -- on the legacy default stream -- also waited for the NEXT batch
-    // already in flight: the submit / wait pair then never had two batches overlapping, 0.7 ms per step at B = 64.)
-    int* tcf[3] = {tc_err_flag_dev(), tc2_err_flag_dev(), tf32_err_flag_dev()};
-    for (int i = 0; i < 3; ++i) {
-      d->h_flags[8 * slot + 2 + i] = 0;
-      if (tcf[i]) SSV_CUDA(cudaMemcpyAsync(d->h_flags + 8 * slot + 2 + i, tcf[i], sizeof(int), cudaMemcpyDeviceToHost, s));
-    }
-  }
-  SSV_CUDA(cudaEventRecord(d->done_ev[slot], s));
   d->inflight[slot] = true;
   d->slot_bf16[slot] = ssrn_precision == SSV_PREC_BF16;
   d->slot_stream[slot] = s;
