@@ -1052,6 +1052,8 @@ __device__ __forceinline__ void front_role(const DecParams& p, const WsStage& st
 // 18 instead of 22 weight rows per thread in registers, ws_nreg).
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// (four-row shape, B = 256 / 192: 80 + 104 registers 165.3 / 126.1 us per frame, 64 + 112: 189 / 135, 88 + 96: 176 / 139,
+// against 164.8 / 129 with 72 + 112)
 template <int RT> struct Regs8 { static constexpr int FE = 72, MV = 112; };
 static_assert(256 * Regs8<1>::FE + 384 * Regs8<1>::MV <= 640 * 96 && 256 * Regs8<4>::FE + 384 * Regs8<4>::MV <= 640 * 96, "register pool");
 
