@@ -1249,8 +1249,9 @@ void ws_plan(int B, int force_r, int force_w, int force_f, int* R, int* W, int* 
   int r, w, f = 4;
   if (B <= 12) { r = 1; w = 4; }           // B=1 28.3 us/frame, B=12 28.9 (W=2: 30.1)
   else if (B <= 32) { r = 1; w = 2; }      // B=16 30.5 (W=4: 32.7), B=24 31.8, B=32 37.1 (R=2 W=2: 39.3, W=1: 38.8)
-  else if (B <= 160) { r = 2; w = 1; }     // B=40 45.1 (R=1: 46.6), B=48 47.4 (R=1: 56.5), B=64 51.7 (R=1 75.7, R=4 59), B=128 104
-  else { r = 4; w = 1; f = 8; }            // B=192: 129, B=256: 178-183 with eight front-end warps (two visit slots), 192 with four
+  else if (B <= 120) { r = 2; w = 1; }     // B=40 45.1 (R=1: 46.6), B=48 47.4 (R=1: 56.5), B=64 51.7 (R=1 75.7, R=4 59), B=128 104
+  else { r = 4; w = 1; f = 8; }            // eight front-end warps above the mat-vec warps: B=128 89.3 (R=2 F=4: 90.7), B=144 94.2 (101.7),
+                                           // B=160 101.4 (115.7), B=176 113.2 (130.8), B=256 164.8 (192)
   // Eight front-end warps (round 2): only the four-row shape gains.  B=64: R=2 W=2 F=8 51.2, R=2 W=1 F=8 (four slots)
   // 72.7, R=4 W=1 F=8 88.1, R=4 W=2 F=8 68.9 against 49.4; B=128: 99.9 / 130.8 / 100.4 / 100.2 against 89.5; B=1: 33.1
   // against 29.4; B=16: 34.8 against 31.1 -- the mat-vec warps lose 16 registers each and four more warps compete for

@@ -236,7 +236,7 @@ def test_decode_batch_sizes_vs_oracle(B, cuda_models):
                                       (67, 4, None, None), (130, None, None, None), (9, 1, 1, None), (6, 1, 2, None),
                                       (26, None, None, None), (13, 2, 1, None), (21, 1, 4, None),
                                       (1, 1, 4, 8), (7, 1, 2, 8), (9, 2, 1, 8), (5, 2, 2, 8), (3, 2, 4, 8), (6, 4, 1, 8),
-                                      (9, 4, 2, 8), (67, 2, 2, 8), (131, 4, 2, 8), (70, 2, 1, 8)])
+                                      (9, 4, 2, 8), (67, 2, 2, 8), (131, 4, 2, 8), (70, 2, 1, 8), (200, None, None, None)])
 def test_decode_micro_batch_shapes_vs_oracle(B, R, Wp, F, cuda_models):
     """Weight-stationary pipeline, every front-end shape: rows per micro-batch R = 1 / 2 / 4, warps per row
     W = 1 / 2 / 4 and F = 4 / 8 front-end warps per CTA (forced through ssv_decoder_set_plan and chosen by ws_plan),
