@@ -645,7 +645,12 @@ def main():
         "roofline": {"kernel": "decode_ws_kernel (weight-stationary pipelined incremental Text2Mel decode)", "bound": "hbm",
                      "achieved": dec_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": dec_gbs / peaks["hbm"],
                      "traffic": traffic, "peak_source": peaks["source"],
-                     "algorithmic_bytes_per_launch": dec_bytes, "us_per_frame": 1e3 * dec_ms / T},
+                     "algorithmic_bytes_per_launch": dec_bytes, "us_per_frame": 1e3 * dec_ms / T,
+                     "frac_at_batch64": extra.get("batch64", {}).get("decode_hbm_roofline_frac"),
+                     "note": "SURVEY 8d's decode model (27.29 MB of weights once per frame + 56 KB of state per utterance) "
+                             "against the measured HBM copy bandwidth; the weights never leave the SMs, so this fraction "
+                             "falls with the batch by construction (frac_at_batch64: BASELINE config 3's batch, same run); "
+                             "from ~32 utterances on the binding roof is the FP32 pipe: roofline_fma"},
         "roofline_fma": {"kernel": "decode_ws_kernel", "bound": "fp32 FMA", "achieved": B * T * DECODE_FLOP_PER_FRAME / (dec_ms * 1e-3) / 1e12,
                          "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": B * T * DECODE_FLOP_PER_FRAME / (dec_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
