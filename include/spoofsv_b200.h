@@ -152,7 +152,8 @@ int ssv_decoder_set_lin_output(ssv_decoder* d, int bf16);
 int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, const float* conv_b, const float* ln1_w,
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
                          int dilation, int causal, const float* h_saved, float* dx, float* dconv_w, float* dconv_b,
-                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, void* stream);
+                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b,
+                         int precision /* as the forward: recomputed H and dgrad on the tensor cores or the CUDA cores */, void* stream);
 
 /* ---- the small layers of the Text2Mel training graph, FP32 (reference: the autograd of the nn.Conv1d(kernel 1) +
  * nn.LayerNorm pairs, models/TTSModel.py:128-131, 173-180, 218-230; the unmasked attention of the train branch,
@@ -180,7 +181,8 @@ int ssv_linear_small_bwd(const float* x, const float* dy, int B, int in_f, int o
  * library's row layout, for h_saved of ssv_highway_conv_bwd (NULL there: the conv is recomputed). */
 int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
                               const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
-                              int dilation, int causal, float* y, float* h_save, void* stream);
+                              int dilation, int causal, float* y, float* h_save,
+                              int precision /* SSV_PREC_FP32: conv on the tensor cores (3xTF32); SSV_PREC_FP32_FFMA */, void* stream);
 
 /* ---- waveform stage (next row of the scope table) -------------------------------------------
  * De-emphasis of B waveforms of n samples each, y[n] = x[n] + coeff * y[n-1]: replaces

@@ -467,12 +467,31 @@ int ssv_highway_conv_fwd(const float* x, const float* conv_w, const float* conv_
   return kOk;
 }
 
+// Raw conv (no epilogue) of the training graph on the tensor cores at FP32 accuracy (conv_tc32.cu: tcgen05 kind::tf32
+// with split operands): X (B T x x_ld) channels-last -> Y (B T x y_ld).  Wh / Wl: the [rows][k * cin] operand split by
+// tf32_pack_weights / tf32_pack_dgrad_weights.
+static int tf32_raw_conv(Arena& ar, float* Wh, float* Wl, const float* bias, int rows, int cin, int k, int dil, int causal,
+                         const float* X, int x_ld, int T, int B, float* Y, int y_ld, cudaStream_t s) {
+  const size_t n = (size_t)B * T * x_ld;
+  float *xh, *xl;
+  SSV_TRY(ar.alloc<float>(n, &xh));
+  SSV_TRY(ar.alloc<float>(n, &xl));
+  SSV_TRY(launch_split_tf32(X, xh, xl, n, s));
+  Tf32Layer L;
+  L.Wh = Wh; L.Wl = Wl; L.bias = bias;
+  L.rows = rows; L.cin = cin; L.cin_p = cin; L.k = k;
+  tf32_shape_plain(&L, rows);
+  return tf32_launch(L, EPI_NONE, dil, causal, xh, xl, x_ld, T, B, Y, nullptr, y_ld, s);
+}
+
 // Training-time forward of one highwayConv, FP32: also hands back H = conv(x) + b in the library's row layout
 // ((B T) x 2d), which ssv_highway_conv_bwd takes instead of recomputing the conv.
 int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
                               const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
-                              int dilation, int causal, float* y, float* h_save, void* stream) {
+                              int dilation, int causal, float* y, float* h_save, int precision, void* stream) {
   SSV_CHECK(x && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b && y && h_save, "highway_conv_fwd_save: null pointer");
+  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "highway_conv_fwd_save: precision must be SSV_PREC_FP32 (tensor cores, 3xTF32) or SSV_PREC_FP32_FFMA");
+  const bool tc = precision == SSV_PREC_FP32;
   SSV_CHECK(B > 0 && T > 0, "highway_conv_fwd_save: empty input");
   SSV_CHECK(d == 256 || d == 512, "highway_conv_fwd_save: dimension %d unsupported (256 or 512)", d);
   SSV_CHECK(k == 1 || k == 3, "highway_conv_fwd_save: kernel_size %d unsupported (1 or 3)", k);
@@ -483,13 +502,21 @@ int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* 
   pm.m["conv.weight"] = {conv_w, (int64_t)2 * d * d * k};
   pm.m["conv.bias"] = {conv_b, 2 * d};
   ConvPack c;
-  SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
+  if (!tc) SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
   const int M = B * T;
   float *xin, *yout;
   SSV_TRY(ar.alloc<float>((size_t)M * d, &xin));
   SSV_TRY(ar.alloc<float>((size_t)M * d, &yout));
   SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
-  SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, h_save, 2 * d, s));
+  if (tc) {
+    float *wh, *wl;
+    SSV_TRY(ar.alloc<float>((size_t)2 * d * k * d, &wh));
+    SSV_TRY(ar.alloc<float>((size_t)2 * d * k * d, &wl));
+    SSV_TRY(tf32_pack_weights(conv_w, 2 * d, d, k, d, wh, wl, s));
+    SSV_TRY(tf32_raw_conv(ar, wh, wl, conv_b, 2 * d, d, k, dilation, causal ? 1 : 0, xin, d, T, B, h_save, 2 * d, s));
+  } else {
+    SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, h_save, 2 * d, s));
+  }
   SSV_TRY(launch_hwy_fwd_rows(h_save, xin, M, d, ln1_w, ln1_b, ln2_w, ln2_b, yout, s));
   SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
   return kOk;
@@ -499,8 +526,10 @@ int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* 
 int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, const float* conv_b, const float* ln1_w,
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
                          int dilation, int causal, const float* h_saved, float* dx, float* dconv_w, float* dconv_b,
-                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, void* stream) {
+                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, int precision, void* stream) {
   SSV_CHECK(x && dy && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b, "highway_conv_bwd: null input pointer");
+  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "highway_conv_bwd: precision must be SSV_PREC_FP32 (tensor cores, 3xTF32) or SSV_PREC_FP32_FFMA");
+  const bool tc = precision == SSV_PREC_FP32;
   SSV_CHECK(dx && dconv_w && dconv_b && dln1_w && dln1_b && dln2_w && dln2_b, "highway_conv_bwd: null output pointer");
   SSV_CHECK(B > 0 && T > 0, "highway_conv_bwd: empty input");
   SSV_CHECK(d == 256 || d == 512, "highway_conv_bwd: dimension %d unsupported (256 or 512)", d);
@@ -533,9 +562,17 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   // 1. H = conv(X) + b, raw: saved by the training-time forward, or recomputed here
   const float* H = h_saved;
   if (!h_saved) {
-    ConvPack c;
-    SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
-    SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, Hbuf, 2 * d, s));
+    if (tc) {
+      float *wh, *wl;
+      SSV_TRY(ar.alloc<float>((size_t)2 * d * k * d, &wh));
+      SSV_TRY(ar.alloc<float>((size_t)2 * d * k * d, &wl));
+      SSV_TRY(tf32_pack_weights(conv_w, 2 * d, d, k, d, wh, wl, s));
+      SSV_TRY(tf32_raw_conv(ar, wh, wl, conv_b, 2 * d, d, k, dilation, causal ? 1 : 0, xin, d, T, B, Hbuf, 2 * d, s));
+    } else {
+      ConvPack c;
+      SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
+      SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, Hbuf, 2 * d, s));
+    }
     H = Hbuf;
   }
   // 2. gate + LayerNorm backward per row, parameter partial sums
@@ -548,11 +585,18 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_CUDA(cudaMemcpyAsync(dln2_b, sums + 3 * d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
   SSV_CUDA(cudaMemcpyAsync(dconv_b, sums + 4 * d, sizeof(float) * 2 * d, cudaMemcpyDeviceToDevice, s));
   // 3. dgrad: the forward's conv kernel on dH with time-flipped, transposed weights and mirrored taps
-  SSV_TRY(launch_pack_dgrad_w(conv_w, d, k, Wd, s));
   SSV_CUDA(cudaMemsetAsync(zero_bias, 0, sizeof(float) * d, s));
-  ConvPack g;
-  g.W = Wd; g.bias = zero_bias; g.cin = 2 * d; g.cin_p = 2 * d; g.k = k; g.n = d; g.n_pad = d;
-  SSV_TRY(run_conv(g, EPI_NONE, dilation, causal ? 2 : 0, dH, 2 * d, T, B, dxc, d, s));
+  if (tc) {
+    float* Wdl;
+    SSV_TRY(ar.alloc<float>((size_t)k * 2 * d * d, &Wdl));
+    SSV_TRY(tf32_pack_dgrad_weights(conv_w, d, k, Wd, Wdl, s));
+    SSV_TRY(tf32_raw_conv(ar, Wd, Wdl, zero_bias, d, 2 * d, k, dilation, causal ? 2 : 0, dH, 2 * d, T, B, dxc, d, s));
+  } else {
+    SSV_TRY(launch_pack_dgrad_w(conv_w, d, k, Wd, s));
+    ConvPack g;
+    g.W = Wd; g.bias = zero_bias; g.cin = 2 * d; g.cin_p = 2 * d; g.k = k; g.n = d; g.n_pad = d;
+    SSV_TRY(run_conv(g, EPI_NONE, dilation, causal ? 2 : 0, dH, 2 * d, T, B, dxc, d, s));
+  }
   SSV_TRY(launch_add_inplace(dxc, dxr, (long)M * d, s));
   SSV_TRY(launch_transpose_out(dxc, d, B, d, T, dx, s));
   // 4. wgrad
@@ -994,7 +1038,7 @@ int ssv_text2mel_train_fwd(ssv_text2mel* m, const float* melspec, const int64_t*
                            int N, int T, float* Y, float* A, int precision, void* stream) {
   SSV_CHECK(m && melspec && textid && spkemb && Y && A, "text2mel_train_fwd: null pointer");
   SSV_CHECK(B > 0 && N > 0 && T > 0, "text2mel_train_fwd: empty input");
-  SSV_CHECK(precision == SSV_PREC_FP32, "text2mel_train_fwd: only SSV_PREC_FP32 is implemented");
+  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "text2mel_train_fwd: only the FP32 arms are implemented (this forward runs on the CUDA cores in both)");
   cudaStream_t s = as_stream(stream);
   const int H = m->H, D2 = 2 * H, F = m->F;
   float* kx;                                                   // (B, N, 512): K | V, channels-last, in m->ws

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
   const int w0 = a.w0_base + (int)rank * a.w0_rank;
   const int w1 = a.w1_base + (int)rank * a.w1_rank;
   const int nk = a.ktaps * a.kb_per_tap;
-  const bool hwy = a.epi == EPI_HIGHWAY;
+  const bool hwy = a.epi == EPI_HIGHWAY, none = a.epi == EPI_NONE;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&a.tmAh); prefetch_tmap(&a.tmAl); prefetch_tmap(&a.tmBh); prefetch_tmap(&a.tmBl);
@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
       const int c = j < 128 ? gc : gc - a.n_real;          // channel inside LN1 / LN2
       g = j < 128 ? a.g1[c] : a.g2[c];
       be = j < 128 ? a.b1[c] : a.b2[c];
+    } else if (none) {
+      g = 1.f;
+      be = 0.f;
     } else {
       g = a.g1[gc];
       be = a.b1[gc];
@@ -121,7 +124,8 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int tap_base = a.causal ? -(a.ktaps - 1) : -((a.ktaps - 1) / 2);
+      // causal: 0 = centred taps, 1 = taps t-(k-1)d .. t, 2 = taps t .. t+(k-1)d (the dgrad of a causal conv)
+      const int tap_base = a.causal == 1 ? -(a.ktaps - 1) : (a.causal == 2 ? 0 : -((a.ktaps - 1) / 2));
       for (int kb = 0; kb < nk; ++kb) {
         const int st = kb % a.nstages;
         const uint32_t ph = (uint32_t)(kb / a.nstages) & 1u;
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
     // plain LayerNorm: my 128 columns (block hsel).
     const int c_lo = hwy ? hsel * 64 : hsel * 128;
     const int c_n = hwy ? 64 : 128;
-    for (int c = c_lo; c < c_lo + c_n; c += 16) {
+    for (int c = c_lo; c < c_lo + c_n && !none; c += 16) {
       tmem_ld16_issue(tq + c, r0);
       tmem_ld16_issue(tq + T32_NL + c, r1);
       if (hwy) {
@@ -238,13 +242,13 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
       }
     }
     t_p1 = clock64();
-    part_s[hsel * T32_BM + row] = make_float4(s1, q1, s2, q2);
-    epi_bar_sync();
-    {
+    if (!none) {
+      part_s[hsel * T32_BM + row] = make_float4(s1, q1, s2, q2);
+      epi_bar_sync();
       const float4 lo4 = part_s[row], hi4 = part_s[T32_BM + row];        // fixed order: both halves get identical sums
       s1 = lo4.x + hi4.x; q1 = lo4.y + hi4.y; s2 = lo4.z + hi4.z; q2 = lo4.w + hi4.w;
     }
-    if (a.cluster_n > 1) {
+    if (a.cluster_n > 1 && !none) {
       if (hsel == 0) {
         const float4 mine = make_float4(s1, q1, s2, q2);
         stat_s[rank * T32_BM + row] = mine;
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
           const float4 p1 = prm_s[c + i];
           const float x1 = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + p1.x;
           const float h1 = (x1 - m1) * rs1 * p1.y + p1.z;
-          o[i] = relu ? fmaxf(h1, 0.f) : h1;
+          o[i] = none ? x1 : (relu ? fmaxf(h1, 0.f) : h1);          // EPI_NONE: the raw conv output (training keeps it)
         }
       }
       float4* dst = reinterpret_cast<float4*>(out_s + (size_t)row * o_ld + c);
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
   }
 
   // non-epilogue warps of a cluster-split layer still have to take part in the cluster barrier
-  if (a.cluster_n > 1 && warp < 4) cluster_sync_all();
+  if (a.cluster_n > 1 && warp < 4 && !none) cluster_sync_all();
 
   tc_fence_before();
   __syncthreads();
@@ -451,6 +455,28 @@ void tf32_shape_plain(Tf32Layer* L, int n) {
   L->w1_base = 128; L->w1_rank = 256;
 }
 
+// dgrad operand of a highwayConv (weight (2d, d, k)): rows = d input channels, K = k taps x 2d conv outputs, taps mirrored:
+// dst[ci][j' * 2d + co] = w[co][ci][k - 1 - j'], split into hi / lo
+__global__ void pack_dgrad_w_tf32_kernel(const float* __restrict__ w, int d, int k, float* __restrict__ hi, float* __restrict__ lo) {
+  const long kp = (long)k * 2 * d;
+  const long total = (long)d * kp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % kp);
+    const int ci = (int)(i / kp);
+    const int jp = kk / (2 * d), co = kk - jp * 2 * d;
+    const float v = w[((long)co * d + ci) * k + (k - 1 - jp)];
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(v - h);
+  }
+}
+
+int tf32_pack_dgrad_weights(const float* w, int d, int k, float* hi, float* lo, cudaStream_t s) {
+  pack_dgrad_w_tf32_kernel<<<1024, 256, 0, s>>>(w, d, k, hi, lo);
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int tf32_pack_weights(const float* w, int n, int cin, int k, int cin_p, float* hi, float* lo, cudaStream_t s) {
   pack_w_tf32_kernel<<<1024, 256, 0, s>>>(w, n, cin, k, cin_p, hi, lo);
   SSV_CUDA(cudaGetLastError());
@@ -482,7 +508,7 @@ int tf32_check_error() {
 int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
                  float* Yh, float* Yl, int y_ld, Tf32Launch* out) {
   SSV_CHECK(L.cin_p % T32_BK == 0 && x_ld >= L.cin_p && x_ld % 4 == 0, "conv_tf32: bad K padding (cin_p %d, ld %d)", L.cin_p, x_ld);
-  SSV_CHECK(epi == EPI_HIGHWAY || epi == EPI_LN || epi == EPI_LN_RELU, "conv_tf32: epilogue %d not built", epi);
+  SSV_CHECK(epi == EPI_HIGHWAY || epi == EPI_LN || epi == EPI_LN_RELU || epi == EPI_NONE, "conv_tf32: epilogue %d not built", epi);
   SSV_CHECK(L.cluster_n == 1 || L.cluster_n == 2 || L.cluster_n == 4, "conv_tf32: cluster_n must be 1, 2 or 4");
   SSV_CHECK(y_ld % 4 == 0, "conv_tf32: output row stride must be a multiple of 4");
   ConvTf32Args& a = out->args;

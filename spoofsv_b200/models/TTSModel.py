@@ -120,8 +120,8 @@ class highwayConv(nn.Module):
         for p in ps:
             _lib.require_cuda(p, "highwayConv parameter")
         # the backward pass exists for the FP32 arm; the bf16 tensor-core arm is inference-only (no autograd graph)
-        if self.precision == "fp32" and torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in ps)):
-            return _HighwayConvFn.apply(inputs, *ps, self.kernel_size, self.dilation, bool(self.causal))
+        if self.precision in ("fp32", "fp32-ffma") and torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in ps)):
+            return _HighwayConvFn.apply(inputs, *ps, self.kernel_size, self.dilation, bool(self.causal), _prec(self.precision))
         return _highway_fwd(inputs, ps, self.kernel_size, self.dilation, self.causal, self.precision)
 
 
@@ -140,12 +140,13 @@ def _highway_fwd(inputs, ps, k, dilation, causal, precision):
 
 class _HighwayConvFn(torch.autograd.Function):
     """highwayConv with a hand-written backward (ssv_highway_conv_bwd): what autograd derives for
-    models/TTSModel.py:63-84 -- gate, both LayerNorms, dgrad and wgrad of the dilated conv -- in FP32."""
+    models/TTSModel.py:63-84 -- gate, both LayerNorms, dgrad and wgrad of the dilated conv -- in FP32.  prec: the conv and
+    its dgrad on the tensor cores with split operands (PREC_FP32, FP32-accurate) or on the CUDA cores (PREC_FP32_FFMA)."""
 
     save_h = True        # keep H = conv(x) + b for the backward pass (2d floats per row) instead of recomputing it
 
     @staticmethod
-    def forward(ctx, x, w, b, g1, b1, g2, b2, k, dilation, causal):
+    def forward(ctx, x, w, b, g1, b1, g2, b2, k, dilation, causal, prec=0):
         ps = [p.detach().contiguous() for p in (w, b, g1, b1, g2, b2)]
         xs = x.detach().to(torch.float32).contiguous()
         B, d, T = xs.shape
@@ -157,16 +158,16 @@ class _HighwayConvFn(torch.autograd.Function):
             h = torch.empty((B * T, 2 * d), device=xs.device, dtype=torch.float32)
             _lib.check(_lib.load().ssv_highway_conv_fwd_save(
                 xs.data_ptr(), *[p.data_ptr() for p in ps], B, d, T, k, dilation, int(causal), y.data_ptr(), h.data_ptr(),
-                _lib.current_stream_ptr()))
+                int(prec), _lib.current_stream_ptr()))
         else:
-            y = _highway_fwd(xs, ps, k, dilation, causal, "fp32-ffma")
+            y = _highway_fwd(xs, ps, k, dilation, causal, "fp32-ffma" if prec == _lib.PREC_FP32_FFMA else "fp32")
         ctx.save_for_backward(xs, *ps, *([h] if h is not None else []))
-        ctx.cfg = (k, dilation, causal, h is not None)
+        ctx.cfg = (k, dilation, causal, h is not None, int(prec))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        k, dilation, causal, has_h = ctx.cfg
+        k, dilation, causal, has_h, prec = ctx.cfg
         saved = ctx.saved_tensors
         x, w, b, g1, b1, g2, b2 = saved[:7]
         h = saved[7] if has_h else None
@@ -175,12 +176,12 @@ class _HighwayConvFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         grads = [torch.empty_like(p) for p in (w, b, g1, b1, g2, b2)]
         if x.numel() == 0:
-            return (dx, *[torch.zeros_like(p) for p in (w, b, g1, b1, g2, b2)], None, None, None)
+            return (dx, *[torch.zeros_like(p) for p in (w, b, g1, b1, g2, b2)], None, None, None, None)
         _lib.check(_lib.load().ssv_highway_conv_bwd(
             x.data_ptr(), dy.data_ptr(), w.data_ptr(), b.data_ptr(), g1.data_ptr(), b1.data_ptr(), g2.data_ptr(),
             b2.data_ptr(), B, d, T, k, dilation, int(causal), h.data_ptr() if h is not None else None, dx.data_ptr(),
-            *[g.data_ptr() for g in grads], _lib.current_stream_ptr()))
-        return (dx, *grads, None, None, None)
+            *[g.data_ptr() for g in grads], prec, _lib.current_stream_ptr()))
+        return (dx, *grads, None, None, None, None)
 
 
 class _ConvLnFn(torch.autograd.Function):
@@ -444,7 +445,7 @@ class melSyn(_Native):
         column is the next input frame -> (Y (B,F,t), A (B,N,t), max_att).  Y and A are views of
         decoder-owned buffers.  ``A_last`` is not read (its columns are already held here)."""
         if self.training:
-            if self.precision == "fp32" and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self.precision in ("fp32", "fp32-ffma") and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
                 return self._train_forward_autograd(melspec, textid, spkemb)
             return self._train_forward(melspec, textid, spkemb)
         _lib.require_cuda(melspec, "melSyn.forward melspec")
@@ -539,9 +540,11 @@ class melSyn(_Native):
         def cl(x, conv, lnm, relu_in=False, sb=None):       # 1x1 conv (+ speaker term) + LayerNorm, fwd / bwd in the library
             return _ConvLnFn.apply(x, conv.weight, conv.bias, sb, lnm.weight, lnm.bias, relu_in)
 
+        prec = _prec(self.precision)        # "fp32": the highway convs' forward and dgrad on the tensor cores (3xTF32)
+
         def hc(x, bag, k, dil, causal):
             return _HighwayConvFn.apply(x, bag.conv.weight, bag.conv.bias, bag.ln1.weight, bag.ln1.bias, bag.ln2.weight,
-                                        bag.ln2.bias, k, dil, causal)
+                                        bag.ln2.bias, k, dil, causal, prec)
 
         def hci(x, bag, causal):
             for i, dil in enumerate((1, 3, 9, 27), start=1):
@@ -626,9 +629,11 @@ class SSRN(_Native):
         def pw(x, m):
             return torch.matmul(m.weight[:, :, 0], x) + m.bias[None, :, None]
 
+        prec = _prec(self.precision)
+
         def hc(x, bag, dil):
             return _HighwayConvFn.apply(x, bag.conv.weight, bag.conv.bias, bag.ln1.weight, bag.ln1.bias, bag.ln2.weight,
-                                        bag.ln2.bias, 3, dil, False)
+                                        bag.ln2.bias, 3, dil, False, prec)
 
         def ups(x, bag):
             w = bag.deconv.weight                                   # (in, out, 2), stride 2: out[2t + j] = W[:, :, j]^T x[t]
@@ -656,7 +661,7 @@ class SSRN(_Native):
         _lib.require_cuda(inputs, "SSRN.forward")
         if inputs.dim() != 3 or inputs.shape[1] != self.freq_bins:
             raise ValueError(f"SSRN expects (B, {self.freq_bins}, T), got {tuple(inputs.shape)}")
-        if (self.training and self.precision == "fp32" and torch.is_grad_enabled()
+        if (self.training and self.precision in ("fp32", "fp32-ffma") and torch.is_grad_enabled()
                 and any(p.requires_grad for p in self.parameters()) and inputs.numel() > 0):
             return self._forward_autograd(inputs)
         x = inputs.detach()

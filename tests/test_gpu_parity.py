@@ -753,6 +753,7 @@ def test_adversarial_training_step_golden(golden_dir, cuda_models_k):
     opt_g = torch.optim.SGD(m1.parameters(), lr=0.0)   # the step itself leaves the shared fixture model untouched
     opt_d = torch.optim.SGD(disc.parameters(), lr=0.0)
     m1.train()
+    m1.precision = "fp32-ffma"          # the CUDA-core arm: 1e-4 of the reference's own fp32 run on every gradient
     try:
         terms = TR.generator_step(m1, disc, opt_g, mel_gt, ids, spk, gaw, cfg)
         want = g["g_terms"]
@@ -783,7 +784,28 @@ def test_adversarial_training_step_golden(golden_dir, cuda_models_k):
             err = np.abs(got.reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-6)
             print(f"D grad {k[6:]}: rel err {err:.2e}")
             assert err <= 1e-4, k
+        # the tensor-core arm (highway convs' forward and dgrad as 3xTF32 tcgen05 MMAs): the same loss terms; gradients to
+        # 2e-3 of their largest element (a ReLU gate at |x| ~ 1e-6 flips here or there: the same effect separates torch's
+        # own fp32 GPU run from its CPU run on this model)
+        m1.precision = "fp32"
+        m1.zero_grad(set_to_none=True)
+        terms = TR.generator_step(m1, disc, opt_g, mel_gt, ids, spk, gaw, cfg)
+        for k, w in zip(("l1", "bin_div", "att", "disc"), g["g_terms"][:4]):
+            assert abs(terms[k] - w) <= 2e-5 * max(1.0, abs(w)), (k, terms[k], w)
+        worst = 0.0
+        for k in g.files:
+            if not k.startswith("ggrad/"):
+                continue
+            got = grads[k[6:]].grad.detach().cpu().numpy()
+            ref = g[k]
+            if got.size != ref.size:
+                got = got.reshape(-1)[::37]
+            err = np.abs(got.reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-6)
+            worst = max(worst, err)
+            assert err <= 2e-3, (k, err)
+        print(f"tensor-core arm: worst relative gradient error {worst:.2e}")
     finally:
+        m1.precision = "fp32"
         m1.eval()
         m1.zero_grad(set_to_none=True)
 
