@@ -303,12 +303,19 @@ struct ssv_text2mel {
   ~ssv_text2mel() {
     for (float* p : te32_ws)
       if (p) cudaFree(p);
+    for (float* p : tr32_ws)
+      if (p) cudaFree(p);
   }
   // speaker projections
   float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
   // AudioEnc / AudioDec packed for the tiled kernels (train-mode full-sequence forward)
   ConvPack ae_conv1, ae_conv2, ae_conv3, ae_hc[10], ad_conv1, ad_hc[6], ad_conv2, ad_conv3, ad_conv4, ad_conv5;
   int ae_dil[10], ad_dil[6];
+  Tf32Layer ae32_hc[10], ad32_hc[6];                 // the 16 causal highway layers for the tensor-core (3xTF32) arm
+  float* tr32_ws[4] = {nullptr, nullptr, nullptr, nullptr};   // (hi, lo) ping-pong activations of the train-mode forward
+  size_t tr32_floats = 0;
+  Tf32Launch tr32_plan[16];                          // encoded launches for (tr32_B, tr32_T)
+  int tr32_B = 0, tr32_T = 0;
   Workspace tws;      // train-mode activations
   float *ts1 = nullptr, *ts2 = nullptr;
   int ts_cap = 0;
@@ -849,6 +856,8 @@ int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, 
     for (int i = 0; i < 10; ++i) {
       T2M_TRY(pack_highway(m->arena, pm, ae + eh[i], H, 3, &m->ae_hc[i], s));
       m->ae_dil[i] = ed[i];
+      tf32_shape_highway(&m->ae32_hc[i], H);
+      T2M_TRY(tf32_pack_layer(m->arena, pm, ae + eh[i] + ".conv.weight", m->ae_hc[i], 2 * H, H, 3, &m->ae32_hc[i], s));
     }
     T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv1", ad + "ln1", H, D2, &m->ad_conv1, s));
     const char* dh[6] = {"hci.hc1", "hci.hc2", "hci.hc3", "hci.hc4", "hc1", "hc2"};
@@ -856,6 +865,8 @@ int ssv_text2mel_create(const char* const* names, const float* const* dev_ptrs, 
     for (int i = 0; i < 6; ++i) {
       T2M_TRY(pack_highway(m->arena, pm, ad + dh[i], H, 3, &m->ad_hc[i], s));
       m->ad_dil[i] = dd[i];
+      tf32_shape_highway(&m->ad32_hc[i], H);
+      T2M_TRY(tf32_pack_layer(m->arena, pm, ad + dh[i] + ".conv.weight", m->ad_hc[i], 2 * H, H, 3, &m->ad32_hc[i], s));
     }
     T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv2", ad + "ln2", H, H, &m->ad_conv2, s));
     T2M_TRY(pack_conv_ln(m->arena, pm, ad + "conv3", ad + "ln3", H, H, &m->ad_conv3, s));
@@ -1038,11 +1049,47 @@ int ssv_text2mel_train_fwd(ssv_text2mel* m, const float* melspec, const int64_t*
                            int N, int T, float* Y, float* A, int precision, void* stream) {
   SSV_CHECK(m && melspec && textid && spkemb && Y && A, "text2mel_train_fwd: null pointer");
   SSV_CHECK(B > 0 && N > 0 && T > 0, "text2mel_train_fwd: empty input");
-  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "text2mel_train_fwd: only the FP32 arms are implemented (this forward runs on the CUDA cores in both)");
+  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA,
+            "text2mel_train_fwd: SSV_PREC_FP32 (highway stacks on the tensor cores, 3xTF32 split) or SSV_PREC_FP32_FFMA (CUDA cores)");
   cudaStream_t s = as_stream(stream);
   const int H = m->H, D2 = 2 * H, F = m->F;
-  float* kx;                                                   // (B, N, 512): K | V, channels-last, in m->ws
-  SSV_TRY(text_encoder_cl(m, textid, B, N, &kx, s));
+  const bool tc = precision == SSV_PREC_FP32 && m->temb % T32_BK == 0;
+  float* kx;                                                   // (B, N, 512): K | V, channels-last
+  if (tc) SSV_TRY(text_encoder_cl_tc(m, textid, B, N, &kx, s));
+  else SSV_TRY(text_encoder_cl(m, textid, B, N, &kx, s));
+  if (tc) {       // the 16 causal highway layers: (hi, lo) ping-pong buffers and encoded launches for this shape
+    const size_t need = (size_t)B * T * H;
+    if (need > m->tr32_floats) {
+      for (float*& p : m->tr32_ws) {
+        if (p) cudaFree(p);
+        p = nullptr;
+      }
+      m->tr32_floats = 0;
+      for (float*& p : m->tr32_ws)
+        if (cudaMalloc((void**)&p, need * sizeof(float) + 256) != cudaSuccess) {
+          cudaGetLastError();
+          set_error("text2mel_train_fwd: workspace cudaMalloc of %zu bytes failed", need * sizeof(float));
+          return kNoMem;
+        }
+      m->tr32_floats = need;
+      m->tr32_B = m->tr32_T = 0;
+    }
+    if (m->tr32_B != B || m->tr32_T != T) {
+      m->tr32_B = m->tr32_T = 0;
+      float** w = m->tr32_ws;                                  // set 0 = (w[0], w[1]), set 1 = (w[2], w[3])
+      for (int i = 0; i < 10; ++i) {
+        const int a_ = (i & 1) * 2, b_ = ((i + 1) & 1) * 2;
+        SSV_TRY(tf32_prepare(m->ae32_hc[i], EPI_HIGHWAY, m->ae_dil[i], 1, w[a_], w[a_ + 1], H, T, B, w[b_], i == 9 ? nullptr : w[b_ + 1], H,
+                             &m->tr32_plan[i]));
+      }
+      for (int i = 0; i < 6; ++i) {
+        const int a_ = (i & 1) * 2, b_ = ((i + 1) & 1) * 2;
+        SSV_TRY(tf32_prepare(m->ad32_hc[i], EPI_HIGHWAY, m->ad_dil[i], 1, w[a_], w[a_ + 1], H, T, B, w[b_], i == 5 ? nullptr : w[b_ + 1], H,
+                             &m->tr32_plan[10 + i]));
+      }
+      m->tr32_B = B; m->tr32_T = T;
+    }
+  }
   SSV_TRY(m->tws.ensure((size_t)B * T * D2));
   if (m->ts_cap < B) {
     SSV_TRY(m->arena.alloc<float>((size_t)B * H, &m->ts1));
@@ -1061,17 +1108,32 @@ int ssv_text2mel_train_fwd(ssv_text2mel* m, const float* melspec, const int64_t*
   SSV_TRY(run_conv(m->ae_conv3, EPI_LN, 1, 0, P, H, T, B, Q, H, s, m->ts2, H));
   float* cur = Q;
   float* nxt = P;
-  for (int i = 0; i < 10; ++i) {
-    SSV_TRY(run_conv(m->ae_hc[i], EPI_HIGHWAY, m->ae_dil[i], 1, cur, H, T, B, nxt, H, s));
-    float* t_ = cur; cur = nxt; nxt = t_;
+  if (tc) {       // split, ten layers on the tensor cores, the last one writes plain fp32 (even count: back in set 0)
+    SSV_TRY(launch_split_tf32(cur, m->tr32_ws[0], m->tr32_ws[1], (size_t)B * T * H, s));
+    for (int i = 0; i < 10; ++i) SSV_TRY(tf32_run(m->tr32_plan[i], s));
+    cur = m->tr32_ws[0];
+    nxt = P;
+  } else {
+    for (int i = 0; i < 10; ++i) {
+      SSV_TRY(run_conv(m->ae_hc[i], EPI_HIGHWAY, m->ae_dil[i], 1, cur, H, T, B, nxt, H, s));
+      float* t_ = cur; cur = nxt; nxt = t_;
+    }
   }
   // attention (:266-270) -> A (B, N, T), [R ; Q] (B, T, 512)
   SSV_TRY(launch_train_attention(kx, cur, B, N, T, A, nxt, s));
   // AudioDec (:217-232)
-  SSV_TRY(run_conv(m->ad_conv1, EPI_LN, 1, 0, nxt, D2, T, B, cur, H, s));
-  for (int i = 0; i < 6; ++i) {
-    SSV_TRY(run_conv(m->ad_hc[i], EPI_HIGHWAY, m->ad_dil[i], 1, cur, H, T, B, nxt, H, s));
-    float* t_ = cur; cur = nxt; nxt = t_;
+  if (tc) {
+    SSV_TRY(run_conv(m->ad_conv1, EPI_LN, 1, 0, nxt, D2, T, B, Q, H, s));
+    SSV_TRY(launch_split_tf32(Q, m->tr32_ws[0], m->tr32_ws[1], (size_t)B * T * H, s));
+    for (int i = 0; i < 6; ++i) SSV_TRY(tf32_run(m->tr32_plan[10 + i], s));
+    cur = m->tr32_ws[0];
+    nxt = P;
+  } else {
+    SSV_TRY(run_conv(m->ad_conv1, EPI_LN, 1, 0, nxt, D2, T, B, cur, H, s));
+    for (int i = 0; i < 6; ++i) {
+      SSV_TRY(run_conv(m->ad_hc[i], EPI_HIGHWAY, m->ad_dil[i], 1, cur, H, T, B, nxt, H, s));
+      float* t_ = cur; cur = nxt; nxt = t_;
+    }
   }
   SSV_TRY(run_conv(m->ad_conv2, EPI_LN_RELU, 1, 0, cur, H, T, B, nxt, H, s));
   SSV_TRY(run_conv(m->ad_conv3, EPI_LN_RELU, 1, 0, nxt, H, T, B, cur, H, s));
