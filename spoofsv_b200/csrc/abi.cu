@@ -386,9 +386,18 @@ struct ssv_ssrn {
   size_t tws_elems = 0;
   Tc2Launch plan2[16];              // prepared launches of the layers the second-generation kernel runs, for (plan_B, plan_T)
   int plan_B = 0, plan_T = 0;
+  // FP32-accurate tensor-core arm (3xTF32), all 16 layers (the 513-bin heads on three-CTA clusters, 255 padding columns)
+  Tf32Layer f_conv1, f_hc1, f_hc2, f_dc1, f_u1h1, f_u1h2, f_dc2, f_u2h1, f_u2h2, f_conv2, f_hc3, f_hc4, f_conv3, f_conv4, f_conv5, f_conv6;
+  float* fws[4] = {nullptr, nullptr, nullptr, nullptr};      // (hi, lo) ping-pong activations
+  size_t fws_floats = 0;
+  Tf32Launch fplan[16];
+  int fplan_B = 0, fplan_T = 0;
+  const float* fplan_out = nullptr;                           // ws.buf[0] the last plan stores into (ws may be re-grown)
   ~ssv_ssrn() {
     for (int i = 0; i < 2; ++i)
       if (tws[i]) cudaFree(tws[i]);
+    for (float* p : fws)
+      if (p) cudaFree(p);
   }
 };
 
@@ -1448,6 +1457,42 @@ int ssv_ssrn_create(const char* const* names, const float* const* dev_ptrs, cons
     S_TRY(pl("conv5", m->conv5, O, O, &m->t_conv5));
     S_TRY(pl("conv6", m->conv6, O, O, &m->t_conv6));
   }
+  {   // FP32-accurate tensor-core arm (conv_tc32.cu)
+    auto fh = [&](const char* name, const ConvPack& c, int d, Tf32Layer* L) -> int {
+      tf32_shape_highway(L, d);
+      return tf32_pack_layer(m->arena, pm, std::string(name) + ".conv.weight", c, 2 * d, d, 3, L, s);
+    };
+    auto fp = [&](const char* name, const ConvPack& c, int n, int cin, Tf32Layer* L) -> int {
+      tf32_shape_plain(L, n);
+      return tf32_pack_layer(m->arena, pm, std::string(name) + ".weight", c, n, cin, 1, L, s);
+    };
+    auto fd = [&](const char* name, const ConvPack& c, Tf32Layer* L) -> int {
+      const float* w;
+      SSV_TRY(pm.get(std::string(name) + ".weight", (int64_t)D * D * 2, &w));
+      tf32_shape_plain(L, 2 * D);
+      L->rows = 2 * D; L->cin = D; L->cin_p = D; L->k = 1;
+      L->bias = c.bias;
+      SSV_TRY(m->arena.alloc<float>((size_t)2 * D * D, &L->Wh));
+      SSV_TRY(m->arena.alloc<float>((size_t)2 * D * D, &L->Wl));
+      return tf32_pack_deconv_weights(w, D, D, L->Wh, L->Wl, s);
+    };
+    S_TRY(fp("conv1", m->conv1, D, freq_bins, &m->f_conv1));
+    S_TRY(fh("hc1", m->hc1, D, &m->f_hc1));
+    S_TRY(fh("hc2", m->hc2, D, &m->f_hc2));
+    S_TRY(fd("ups1.deconv", m->dc1, &m->f_dc1));
+    S_TRY(fh("ups1.hc1", m->u1h1, D, &m->f_u1h1));
+    S_TRY(fh("ups1.hc2", m->u1h2, D, &m->f_u1h2));
+    S_TRY(fd("ups2.deconv", m->dc2, &m->f_dc2));
+    S_TRY(fh("ups2.hc1", m->u2h1, D, &m->f_u2h1));
+    S_TRY(fh("ups2.hc2", m->u2h2, D, &m->f_u2h2));
+    S_TRY(fp("conv2", m->conv2, 2 * D, D, &m->f_conv2));
+    S_TRY(fh("hc3", m->hc3, 2 * D, &m->f_hc3));
+    S_TRY(fh("hc4", m->hc4, 2 * D, &m->f_hc4));
+    S_TRY(fp("conv3", m->conv3, O, 2 * D, &m->f_conv3));
+    S_TRY(fp("conv4", m->conv4, O, O, &m->f_conv4));
+    S_TRY(fp("conv5", m->conv5, O, O, &m->f_conv5));
+    S_TRY(fp("conv6", m->conv6, O, O, &m->f_conv6));
+  }
 #undef S_TRY
   if (st == kOk && cudaStreamSynchronize(s) != cudaSuccess) {
     set_error("ssrn_create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1493,6 +1538,59 @@ static int ssrn_fwd_f32(ssv_ssrn* m, const float* mel, long sb, long sf, long st
   SSV_TRY(run_conv(m->conv5, EPI_LN_RELU, 1, 0, P, o_ld, 4 * T, B, Q, o_ld, s));
   SSV_TRY(run_conv(m->conv6, EPI_LN_SIGMOID, 1, 0, Q, o_ld, 4 * T, B, P, o_ld, s));
   SSV_TRY(launch_transpose_out(P, o_ld, B, O, 4 * T, out, s));
+  return kOk;
+}
+
+// FP32-accurate SSRN on the tensor cores: all 16 layers on conv_tf32x3_kernel with split operands, activations travelling
+// as (hi, lo) pairs.  The four 513-bin heads run on three-CTA clusters (768 accumulator columns, 255 of them padding with
+// zero weights and zero LayerNorm parameters, so they add nothing to the row statistics).  Same 1e-4 bar as the CUDA-core arm.
+static int ssrn_fwd_tf32(ssv_ssrn* m, const float* mel, long sb, long sf, long st_, int B, int T, float* out, cudaStream_t s) {
+  const int D = m->D, O = m->O;
+  const int o_ld = round_up(O, 64);
+  const int f_ld = m->f_conv1.cin_p;
+  const size_t need = (size_t)B * 4 * T * (o_ld > 2 * D ? o_ld : 2 * D);
+  SSV_TRY(m->ws.ensure((size_t)B * 4 * T * o_ld));
+  if (need > m->fws_floats) {
+    for (float*& p : m->fws) {
+      if (p) cudaFree(p);
+      p = nullptr;
+    }
+    m->fws_floats = 0;
+    for (float*& p : m->fws)
+      if (cudaMalloc((void**)&p, need * sizeof(float) + 256) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("ssrn_fwd: workspace cudaMalloc of %zu bytes failed", need * sizeof(float));
+        return kNoMem;
+      }
+    m->fws_floats = need;
+    m->fplan_B = m->fplan_T = 0;
+  }
+  float *Ah = m->fws[0], *Al = m->fws[1], *Bh = m->fws[2], *Bl = m->fws[3];
+  if (m->fplan_B != B || m->fplan_T != T || m->fplan_out != m->ws.buf[0]) {
+    m->fplan_B = m->fplan_T = 0;
+    Tf32Launch* L = m->fplan;
+    SSV_TRY(tf32_prepare(m->f_conv1, EPI_LN, 1, 0, Ah, Al, f_ld, T, B, Bh, Bl, D, &L[0]));
+    SSV_TRY(tf32_prepare(m->f_hc1, EPI_HIGHWAY, 1, 0, Bh, Bl, D, T, B, Ah, Al, D, &L[1]));
+    SSV_TRY(tf32_prepare(m->f_hc2, EPI_HIGHWAY, 3, 0, Ah, Al, D, T, B, Bh, Bl, D, &L[2]));
+    SSV_TRY(tf32_prepare(m->f_dc1, EPI_NONE, 1, 0, Bh, Bl, D, T, B, Ah, Al, 2 * D, &L[3]));              // (B,T,2D) == (B,2T,D)
+    SSV_TRY(tf32_prepare(m->f_u1h1, EPI_HIGHWAY, 1, 0, Ah, Al, D, 2 * T, B, Bh, Bl, D, &L[4]));
+    SSV_TRY(tf32_prepare(m->f_u1h2, EPI_HIGHWAY, 3, 0, Bh, Bl, D, 2 * T, B, Ah, Al, D, &L[5]));
+    SSV_TRY(tf32_prepare(m->f_dc2, EPI_NONE, 1, 0, Ah, Al, D, 2 * T, B, Bh, Bl, 2 * D, &L[6]));
+    SSV_TRY(tf32_prepare(m->f_u2h1, EPI_HIGHWAY, 1, 0, Bh, Bl, D, 4 * T, B, Ah, Al, D, &L[7]));
+    SSV_TRY(tf32_prepare(m->f_u2h2, EPI_HIGHWAY, 3, 0, Ah, Al, D, 4 * T, B, Bh, Bl, D, &L[8]));
+    SSV_TRY(tf32_prepare(m->f_conv2, EPI_LN, 1, 0, Bh, Bl, D, 4 * T, B, Ah, Al, 2 * D, &L[9]));
+    SSV_TRY(tf32_prepare(m->f_hc3, EPI_HIGHWAY, 1, 0, Ah, Al, 2 * D, 4 * T, B, Bh, Bl, 2 * D, &L[10]));
+    SSV_TRY(tf32_prepare(m->f_hc4, EPI_HIGHWAY, 1, 0, Bh, Bl, 2 * D, 4 * T, B, Ah, Al, 2 * D, &L[11]));
+    SSV_TRY(tf32_prepare(m->f_conv3, EPI_LN, 1, 0, Ah, Al, 2 * D, 4 * T, B, Bh, Bl, o_ld, &L[12]));
+    SSV_TRY(tf32_prepare(m->f_conv4, EPI_LN_RELU, 1, 0, Bh, Bl, o_ld, 4 * T, B, Ah, Al, o_ld, &L[13]));
+    SSV_TRY(tf32_prepare(m->f_conv5, EPI_LN_RELU, 1, 0, Ah, Al, o_ld, 4 * T, B, Bh, Bl, o_ld, &L[14]));
+    SSV_TRY(tf32_prepare(m->f_conv6, EPI_LN_SIGMOID, 1, 0, Bh, Bl, o_ld, 4 * T, B, m->ws.buf[0], nullptr, o_ld, &L[15]));   // plain fp32
+    m->fplan_B = B; m->fplan_T = T; m->fplan_out = m->ws.buf[0];
+  }
+  SSV_TRY(launch_transpose_in(mel, sb, sf, st_, B, m->F, T, Bh, f_ld, s));
+  SSV_TRY(launch_split_tf32(Bh, Ah, Al, (size_t)B * T * f_ld, s));
+  for (int i = 0; i < 16; ++i) SSV_TRY(tf32_run(m->fplan[i], s));
+  SSV_TRY(launch_transpose_out(m->ws.buf[0], o_ld, B, O, 4 * T, out, s));
   return kOk;
 }
 
@@ -1552,7 +1650,8 @@ int ssv_ssrn_fwd(ssv_ssrn* m, const float* mel, long stride_b, long stride_f, lo
   SSV_CHECK(m && mel && out, "ssrn_fwd: null pointer");
   SSV_CHECK(B > 0 && T > 0, "ssrn_fwd: empty input");
   cudaStream_t s = as_stream(stream);
-  if (precision == SSV_PREC_FP32) return ssrn_fwd_f32(m, mel, stride_b, stride_f, stride_t, B, T, out, s);
+  if (precision == SSV_PREC_FP32 && m->F % T32_BK == 0) return ssrn_fwd_tf32(m, mel, stride_b, stride_f, stride_t, B, T, out, s);
+  if (precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA) return ssrn_fwd_f32(m, mel, stride_b, stride_f, stride_t, B, T, out, s);
   if (precision == SSV_PREC_BF16) return ssrn_fwd_bf16(m, mel, stride_b, stride_f, stride_t, B, T, out, s);
   set_error("ssrn_fwd: unknown precision %d", precision);
   return kInval;

@@ -107,11 +107,14 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
     } else if (none) {
       g = 1.f;
       be = 0.f;
-    } else {
+    } else if (gc < a.n_cols) {
       g = a.g1[gc];
       be = a.b1[gc];
+    } else {                                               // padding column of a layer whose width does not fill the cluster
+      g = 0.f;
+      be = 0.f;
     }
-    prm_s[j] = make_float4(a.bias[gc], g, be, 0.f);
+    prm_s[j] = make_float4(gc < a.n_cols ? a.bias[gc] : 0.f, g, be, 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
 
     // pass 2: normalise (+ gate with the residual), into the staging tile
     const int o_ld = hwy ? RES_LD : OUT_LD;
-    const bool relu = a.epi == EPI_LN_RELU;
+    const bool relu = a.epi == EPI_LN_RELU, sigm = a.epi == EPI_LN_SIGMOID;
 #pragma unroll
     for (int cc = 0; cc < 128; cc += 16) {
       if (cc >= c_n) break;
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
           const float4 p1 = prm_s[c + i];
           const float x1 = (__uint_as_float(r0[i]) + __uint_as_float(r1[i])) + p1.x;
           const float h1 = (x1 - m1) * rs1 * p1.y + p1.z;
-          o[i] = none ? x1 : (relu ? fmaxf(h1, 0.f) : h1);          // EPI_NONE: the raw conv output (training keeps it)
+          o[i] = none ? x1 : (relu ? fmaxf(h1, 0.f) : (sigm ? sigmoid_fast(h1) : h1));   // EPI_NONE: the raw conv output (training keeps it)
         }
       }
       float4* dst = reinterpret_cast<float4*>(out_s + (size_t)row * o_ld + c);
@@ -335,6 +338,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
         for (int h = 0; h < 2; ++h) {
           if (h * 32 >= f4_per_row) break;
           const int gc = h == 0 ? w0 + lane * 4 : w1 + lane * 4;
+          if (gc >= a.y_cols) continue;
           if (a.Yl != nullptr) {
             float4 hi, lo;
             split4(v[u][h], hi, lo);
@@ -448,9 +452,9 @@ void tf32_shape_highway(Tf32Layer* L, int d) {
   L->w1_base = d; L->w1_rank = 128;
 }
 
-void tf32_shape_plain(Tf32Layer* L, int n) {
+void tf32_shape_plain(Tf32Layer* L, int n) {          // n need not fill the cluster: 513 -> three CTAs, 255 padding columns
   L->n_real = n;
-  L->cluster_n = n / 256;
+  L->cluster_n = (n + 255) / 256;
   L->w0_base = 0; L->w0_rank = 256;
   L->w1_base = 128; L->w1_rank = 256;
 }
@@ -469,6 +473,26 @@ __global__ void pack_dgrad_w_tf32_kernel(const float* __restrict__ w, int d, int
     hi[i] = h;
     lo[i] = to_tf32(v - h);
   }
+}
+
+// ConvTranspose1d(k = 2, stride 2) weight (cin, cout, 2) as the 1x1 operand [2 cout rows (j, co)][cin], split into hi / lo
+__global__ void pack_deconv_w_tf32_kernel(const float* __restrict__ w, int cin, int cout, float* __restrict__ hi, float* __restrict__ lo) {
+  const long total = (long)2 * cout * cin;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int row = (int)(i / cin);
+    const int j = row / cout, co = row - j * cout;
+    const float v = w[((long)ci * cout + co) * 2 + j];
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(v - h);
+  }
+}
+
+int tf32_pack_deconv_weights(const float* w, int cin, int cout, float* hi, float* lo, cudaStream_t s) {
+  pack_deconv_w_tf32_kernel<<<1024, 256, 0, s>>>(w, cin, cout, hi, lo);
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
 }
 
 int tf32_pack_dgrad_weights(const float* w, int d, int k, float* hi, float* lo, cudaStream_t s) {
@@ -508,8 +532,9 @@ int tf32_check_error() {
 int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
                  float* Yh, float* Yl, int y_ld, Tf32Launch* out) {
   SSV_CHECK(L.cin_p % T32_BK == 0 && x_ld >= L.cin_p && x_ld % 4 == 0, "conv_tf32: bad K padding (cin_p %d, ld %d)", L.cin_p, x_ld);
-  SSV_CHECK(epi == EPI_HIGHWAY || epi == EPI_LN || epi == EPI_LN_RELU || epi == EPI_NONE, "conv_tf32: epilogue %d not built", epi);
-  SSV_CHECK(L.cluster_n == 1 || L.cluster_n == 2 || L.cluster_n == 4, "conv_tf32: cluster_n must be 1, 2 or 4");
+  SSV_CHECK(epi == EPI_HIGHWAY || epi == EPI_LN || epi == EPI_LN_RELU || epi == EPI_LN_SIGMOID || epi == EPI_NONE,
+            "conv_tf32: epilogue %d not built", epi);
+  SSV_CHECK(L.cluster_n >= 1 && L.cluster_n <= 4, "conv_tf32: cluster_n must be 1..4");
   SSV_CHECK(y_ld % 4 == 0, "conv_tf32: output row stride must be a multiple of 4");
   ConvTf32Args& a = out->args;
   memset(&a, 0, sizeof(a));
@@ -538,6 +563,11 @@ int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* 
   a.cluster_n = L.cluster_n;
   a.w0_base = L.w0_base; a.w0_rank = L.w0_rank; a.w1_base = L.w1_base; a.w1_rank = L.w1_rank;
   a.n_real = L.n_real;
+  a.n_cols = L.rows;
+  {
+    const int wide = epi == EPI_HIGHWAY ? L.n_real : L.cluster_n * T32_NL;
+    a.y_cols = y_ld < wide ? y_ld : wide;
+  }
   a.epi = epi;
   a.bias = L.bias;
   a.g1 = L.g1; a.b1 = L.b1; a.g2 = L.g2; a.b2 = L.b2;

@@ -20,11 +20,13 @@ struct alignas(64) ConvTf32Args {
   int tiles_per_b;          // ceil(T / 128) when utt_per_tile == 1
   int kb_per_tap;           // cin_p / 16
   int ktaps, dil, causal;
-  int cluster_n;            // CTAs splitting N: 1, 2 or 4
+  int cluster_n;            // CTAs splitting N: 1..4
   int w0_base, w0_rank;     // weight-row / output-column origin of block 0 = w0_base + rank * w0_rank
   int w1_base, w1_rank;     // same for block 1
   int n_real;               // LayerNorm width
-  int epi;                  // Epilogue (EPI_LN, EPI_LN_RELU, EPI_HIGHWAY; EPI_NONE: raw conv output + bias, plain column layout)
+  int n_cols;               // real weight rows / output columns (columns beyond are padding: zero weights, zero parameters)
+  int y_cols;               // columns stored (multiple of 4)
+  int epi;                  // Epilogue (EPI_LN, EPI_LN_RELU, EPI_LN_SIGMOID, EPI_HIGHWAY; EPI_NONE: raw conv output + bias, plain column layout)
   int nstages;
   const float* bias;        // [N] fp32, indexed by global column
   const float* g1; const float* b1; const float* g2; const float* b2;
@@ -46,10 +48,12 @@ struct Tf32Layer {
 };
 
 void tf32_shape_highway(Tf32Layer* L, int d);     // rows = 2 d, d in {256, 512}
-void tf32_shape_plain(Tf32Layer* L, int n);       // n in {256, 512}
+void tf32_shape_plain(Tf32Layer* L, int n);       // n <= 1024; three CTAs (255 padding columns) for the 513-bin heads
 int tf32_pack_weights(const float* w /*[n][cin][k]*/, int n, int cin, int k, int cin_p, float* hi, float* lo, cudaStream_t s);
 // dgrad operand of a highwayConv weight (2d, d, k): [d][k * 2d], taps mirrored
 int tf32_pack_dgrad_weights(const float* w, int d, int k, float* hi, float* lo, cudaStream_t s);
+// ConvTranspose1d(k = 2, s = 2) weight (cin, cout, 2) as the 1x1 operand [2 cout][cin]
+int tf32_pack_deconv_weights(const float* w, int cin, int cout, float* hi, float* lo, cudaStream_t s);
 // x (fp32, any layout, n elements) -> hi = tf32(x), lo = tf32(x - hi)
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t s);
 // A launch with its TMA descriptors encoded: built once per (layer, buffers, shape) and replayed (encoding four tensor

@@ -72,6 +72,29 @@ def test_ssrn_golden_fp32(golden_dir, cuda_models_k):
     assert _maxabs(lin, _t(z["lin"])) <= FP32_TOL
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp32-ffma"])
+def test_ssrn_both_fp32_arms(prec, golden_dir, cuda_models_k, cuda_models):
+    """"fp32" = 12 of the 16 layers on the tensor cores with split operands (3xTF32), "fp32-ffma" = every layer on the
+    CUDA cores; both hold the 1e-4 bar, on a short (two utterances per tile) and a ragged long input with odd batch."""
+    _, mk, _, _ = cuda_models_k
+    _, m2, _, sd2 = cuda_models
+    old_k, old = mk.precision, m2.precision
+    try:
+        mk.precision = m2.precision = prec
+        z = np.load(golden_dir / "ssrn_seed7.npz")
+        assert _maxabs(mk(_t(z["mel"]).cuda()), _t(z["lin"])) <= FP32_TOL
+        z = np.load(golden_dir / "cfg1_seed0.npz")
+        lin = m2(_t(z["Y"]).cuda())
+        assert _maxabs(lin[:, :, ::4], _t(z["lin_t4"])) <= FP32_TOL
+        mel = torch.rand((3, 80, 131), generator=torch.Generator().manual_seed(3))
+        got = m2(mel.cuda())
+        assert _maxabs(got, O.ssrn(mel, sd2)) <= FP32_TOL
+        one = m2(mel[2:3, :, :9].contiguous().cuda())
+        assert _maxabs(one, O.ssrn(mel[2:3, :, :9], sd2)) <= FP32_TOL
+    finally:
+        mk.precision, m2.precision = old_k, old
+
+
 def test_ssrn_noncontiguous_input_and_cfg1(golden_dir, cuda_models):
     _, m2, _, _ = cuda_models
     z = np.load(golden_dir / "cfg1_seed0.npz")
