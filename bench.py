@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--frames", type=int, default=T_FRAMES)
     ap.add_argument("--ssrn-precision", default="bf16", choices=["fp32", "bf16"],
-                    help="SSRN arm: bf16 = tcgen05 tensor cores (2e-2 rel-L2 bar), fp32 = FFMA (1e-4 max-abs bar); "
+                    help="SSRN arm: bf16 = tcgen05 tensor cores (2e-2 rel-L2 bar), fp32 = 3xTF32 on the tensor cores (1e-4 max-abs bar); "
                          "Text2Mel always runs the fp32 arm (identical alignments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
@@ -627,7 +627,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("fp32 (TextEnc: tcgen05 kind::tf32 with 3xTF32 split operands, FP32-accurate; decode: FFMA)"
-                  + (" + fp32 SSRN (FFMA)" if args.ssrn_precision == "fp32" else " + bf16 SSRN (tcgen05, fp32 accumulate)")),
+                  + (" + fp32 SSRN (3xTF32, tcgen05)" if args.ssrn_precision == "fp32" else " + bf16 SSRN (tcgen05, fp32 accumulate)")),
         "data": "synthetic",
         "config": config_dict(args, B),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
