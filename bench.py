@@ -664,8 +664,13 @@ def main():
                              "note": "achieved counts the three TF32 MMAs per product (hi*hi, hi*lo, lo*hi); peak = half the measured "
                                      "sustained bf16 rate (kind::tf32 issues at half the kind::f16 rate); useful_fp32_tflops is the "
                                      "algorithmic FP32 rate (CUDA-core FP32 peak: 74.4)"},
-        "roofline_ssrn": {"bound": "tensor", "achieved": ssrn_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                          "frac": ssrn_tflops / peaks["bf16_sustained"], "precision": args.ssrn_precision},
+        "roofline_ssrn": ({"bound": "tensor", "achieved": ssrn_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                           "frac": ssrn_tflops / peaks["bf16_sustained"], "precision": args.ssrn_precision}
+                          if args.ssrn_precision == "bf16" else
+                          {"bound": "tensor", "achieved": 3 * ssrn_tflops, "peak": peaks["bf16_sustained"] / 2, "unit": "TFLOP/s",
+                           "frac": 3 * ssrn_tflops / (peaks["bf16_sustained"] / 2), "useful_fp32_tflops": ssrn_tflops,
+                           "precision": "fp32 (3xTF32)",
+                           "note": "achieved counts the three TF32 MMAs per product; peak = half the measured sustained bf16 rate"}),
         "extra": extra,
     }
     if rank == 0 and world == 1 and not args.no_eager:
