@@ -257,6 +257,14 @@ __device__ __forceinline__ float rstd_fast(float var) { return rsqrtf(var + 1e-5
 // per row instead of 4 + 1.  Measured: B = 1 30.0 -> 28.9 us/frame.  With 2 or 4 rows per micro-batch the mat-vec
 // phases are bound by the FMA pipe, where the packed form is ~9 % slower than scalar FFMA (B = 64: 53.7 -> 58
 // us/frame), so those shapes keep scalar FMAs and the plain X layout.
+// (Tried: the accumulators of multi-row micro-batches in 64-bit register pairs holding columns (1, 0) and (3, 2), so that
+// every FFMA reads its accumulator and its weight from registers of opposite parity.  A three-register FFMA whose two
+// fresh operands share a register bank issues at half rate -- tools/micro/ffma_bank_bench.cu: 0.88 FFMA per cycle and
+// scheduler when only the first FFMA of each reuse group conflicts, and ptxas, with all registers in use here, leaves
+// 44 % of this loop's FFMAs conflicting, which is the 0.63 per cycle measured in situ.  The pairs remove those
+// conflicts in the SASS, but the launch does not get faster: B = 64 49.4 -> 49.4 us/frame, 128 89.5 -> 88.4,
+// 192 126 -> 122, 256 164.8 -> 168-170.  The FMA loops are filler between hand-offs, not the bound -- see
+// profiles/r2_decode_ws_knockouts.md: without any FMA the launch is only 14-22 % shorter.)
 
 template <int XS> struct XVecN { using T = float2; };         // one X row: (x, x) | (x0, x1) | (x0, x0, x1, x1) | (x0, x1, x2, x3)
 template <> struct XVecN<4> { using T = float4; };
