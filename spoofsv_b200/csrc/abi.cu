@@ -500,6 +500,43 @@ static int tf32_raw_conv(Arena& ar, float* Wh, float* Wl, const float* bias, int
   return tf32_launch(L, EPI_NONE, dil, causal, xh, xl, x_ld, T, B, Y, nullptr, y_ld, s);
 }
 
+// wgrad of a highwayConv on the tensor cores at FP32 accuracy: a split-K GEMM on conv_tf32x3_kernel (operand layouts in
+// conv_tc32.cuh).  dH (B T x 2d) and X (B T x d) channels-last -> dW (2d, d, k).
+static int tf32_wgrad(Arena& ar, const float* dH, const float* X, int B, int T, int d, int k, int dil, int causal, float* dW,
+                      cudaStream_t s) {
+  const int M = B * T, n2 = 2 * d, n_all = k * d;
+  const int taps_per_launch = n_all <= 1024 ? k : 1;            // N of one launch: at most four 256-column CTAs
+  const int n_launch = taps_per_launch * d;
+  const int per_chunk = (n2 / T32_BM) * ((n_launch + 255) / 256);
+  int chunks = (device_sm_count() + per_chunk / 2) / per_chunk;
+  if (chunks < 1) chunks = 1;
+  const int kc = round_up((M + chunks - 1) / chunks, 32);
+  chunks = (M + kc - 1) / kc;
+  const int k_pad = chunks * kc;
+  float *Ah, *Al, *Wh, *Wl, *P, *zero;
+  SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * kc, &Ah));
+  SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * kc, &Al));
+  SSV_TRY(ar.alloc<float>((size_t)n_all * k_pad, &Wh));
+  SSV_TRY(ar.alloc<float>((size_t)n_all * k_pad, &Wl));
+  SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * n_all, &P));
+  SSV_TRY(ar.alloc<float>(1024, &zero));
+  SSV_CUDA(cudaMemsetAsync(zero, 0, sizeof(float) * 1024, s));
+  const int tap_base = causal ? -(k - 1) : -((k - 1) / 2);
+  SSV_TRY(launch_wgrad_prep_dh(dH, M, n2, kc, chunks, Ah, Al, s));
+  SSV_TRY(launch_wgrad_prep_x(X, d, B, T, d, k, dil, tap_base, k_pad, Wh, Wl, s));
+  for (int j0 = 0; j0 < k; j0 += taps_per_launch) {
+    Tf32Layer L;
+    L.Wh = Wh + (size_t)j0 * d * k_pad;
+    L.Wl = Wl + (size_t)j0 * d * k_pad;
+    L.bias = zero;
+    L.rows = n_launch; L.cin = kc; L.cin_p = kc; L.k = 1;
+    L.w_cols = k_pad; L.w_k_per_b = kc;
+    tf32_shape_plain(&L, n_launch);
+    SSV_TRY(tf32_launch(L, EPI_NONE, 1, 0, Ah, Al, kc, n2, chunks, P + (size_t)j0 * d, nullptr, n_all, s));
+  }
+  return launch_wgrad_tc_reduce(P, chunks, d, k, dW, s);
+}
+
 // Training-time forward of one highwayConv, FP32: also hands back H = conv(x) + b in the library's row layout
 // ((B T) x 2d), which ssv_highway_conv_bwd takes instead of recomputing the conv.
 int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
@@ -572,7 +609,7 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_TRY(ar.alloc<float>((size_t)6 * d, &sums));
   SSV_TRY(ar.alloc<float>((size_t)k * 2 * d * d, &Wd));
   SSV_TRY(ar.alloc<float>((size_t)d, &zero_bias));
-  SSV_TRY(ar.alloc<float>((size_t)wgrad_chunks(M) * k * 2 * d * d, &P));
+  SSV_TRY(ar.alloc<float>(tc ? (size_t)4 : (size_t)wgrad_chunks(M) * k * 2 * d * d, &P));      // CUDA-core wgrad partials
   SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
   SSV_TRY(launch_transpose_in(dy, (long)d * T, T, 1, B, d, T, dyr, d, s));
   // 1. H = conv(X) + b, raw: saved by the training-time forward, or recomputed here
@@ -616,7 +653,8 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_TRY(launch_add_inplace(dxc, dxr, (long)M * d, s));
   SSV_TRY(launch_transpose_out(dxc, d, B, d, T, dx, s));
   // 4. wgrad
-  SSV_TRY(launch_wgrad(dH, xin, M, T, d, k, dilation, causal ? 1 : 0, P, dconv_w, s));
+  if (tc) SSV_TRY(tf32_wgrad(ar, dH, xin, B, T, d, k, dilation, causal ? 1 : 0, dconv_w, s));
+  else SSV_TRY(launch_wgrad(dH, xin, M, T, d, k, dilation, causal ? 1 : 0, P, dconv_w, s));
   return kOk;
 }
 

@@ -142,10 +142,11 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
         tma_load_3d(S + A_HALF_BYTES, &a.tmAl, full_bar + st, c0, tc, b0);
         uint8_t* Bh = S + 2 * A_HALF_BYTES;
         uint8_t* Bl = Bh + B_HALF_BYTES;
-        tma_load_2d(Bh, &a.tmBh, full_bar + st, kb * T32_BK, w0);
-        tma_load_2d(Bh + B_HALF_BYTES / 2, &a.tmBh, full_bar + st, kb * T32_BK, w1);
-        tma_load_2d(Bl, &a.tmBl, full_bar + st, kb * T32_BK, w0);
-        tma_load_2d(Bl + B_HALF_BYTES / 2, &a.tmBl, full_bar + st, kb * T32_BK, w1);
+        const int wk = kb * T32_BK + b0 * a.w_k_per_b;
+        tma_load_2d(Bh, &a.tmBh, full_bar + st, wk, w0);
+        tma_load_2d(Bh + B_HALF_BYTES / 2, &a.tmBh, full_bar + st, wk, w1);
+        tma_load_2d(Bl, &a.tmBl, full_bar + st, wk, w0);
+        tma_load_2d(Bl + B_HALF_BYTES / 2, &a.tmBl, full_bar + st, wk, w1);
       }
     }
   } else if (warp == 1) {
@@ -514,6 +515,94 @@ int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream
   return kOk;
 }
 
+// ---- split-K wgrad operands (see conv_tc32.cuh) ----
+// dH (M x n2 rows, channels-last) -> [chunk][n2][kc], hi / lo; rows past M are zero.  32 x 32 tiles; kc % 32 == 0.
+__global__ void __launch_bounds__(256) wgrad_prep_dh_kernel(const float* __restrict__ dH, int M, int n2, int kc, float* __restrict__ Ah,
+                                                            float* __restrict__ Al) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i;
+    tile[ty + i][tx] = r < M ? dH[(size_t)r * n2 + c0 + tx] : 0.f;
+  }
+  __syncthreads();
+  const int chunk = r0 / kc, kk = r0 - chunk * kc + tx;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int co = c0 + ty + i;
+    const float v = tile[tx][ty + i];
+    const float h = to_tf32(v);
+    const size_t o = ((size_t)chunk * n2 + co) * kc + kk;
+    Ah[o] = h;
+    Al[o] = to_tf32(v - h);
+  }
+}
+// X (B T x x_ld rows, channels-last) -> [(j, ci)][k_pad] with row r = (b, t) holding X[(b, t + (tap_base + j) dil)][ci]
+// (zero outside the utterance and past the last row), hi / lo
+__global__ void __launch_bounds__(256) wgrad_prep_x_kernel(const float* __restrict__ X, int x_ld, int M, int T, int d, int dil, int tap_base,
+                                                           int k_pad, float* __restrict__ Wh, float* __restrict__ Wl) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32, j = blockIdx.z;
+  const int off = (tap_base + j) * dil;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i;
+    float v = 0.f;
+    if (r < M) {
+      const int b = r / T, ts = r - b * T + off;
+      if (ts >= 0 && ts < T) v = X[((size_t)b * T + ts) * x_ld + c0 + tx];
+    }
+    tile[ty + i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int ci = c0 + ty + i;
+    const float v = tile[tx][ty + i];
+    const float h = to_tf32(v);
+    const size_t o = ((size_t)j * d + ci) * k_pad + r0 + tx;
+    Wh[o] = h;
+    Wl[o] = to_tf32(v - h);
+  }
+}
+// partials [chunk][2d][k d] -> dW (2d, d, k)
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ P, int chunks, int d, int k, float* __restrict__ dW) {
+  const long total = (long)2 * d * k * d;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % d);
+    const int j = (int)((i / d) % k);
+    const int co = (int)(i / ((long)d * k));
+    float sum = 0.f;
+    for (int c = 0; c < chunks; ++c) sum += P[(size_t)c * total + i];
+    dW[((size_t)co * d + ci) * k + j] = sum;
+  }
+}
+
+int launch_wgrad_prep_dh(const float* dH, int M, int n2, int kc, int chunks, float* Ah, float* Al, cudaStream_t s) {
+  SSV_CHECK(kc % 32 == 0 && n2 % 32 == 0 && (long)chunks * kc >= M, "wgrad_prep_dh: bad chunking (kc %d, chunks %d, M %d)", kc, chunks, M);
+  wgrad_prep_dh_kernel<<<dim3((unsigned)(chunks * kc / 32), (unsigned)(n2 / 32)), 256, 0, s>>>(dH, M, n2, kc, Ah, Al);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+int launch_wgrad_prep_x(const float* X, int x_ld, int B, int T, int d, int k, int dil, int tap_base, int k_pad, float* Wh, float* Wl,
+                        cudaStream_t s) {
+  SSV_CHECK(k_pad % 32 == 0 && d % 32 == 0 && k_pad >= B * T, "wgrad_prep_x: bad padding");
+  wgrad_prep_x_kernel<<<dim3((unsigned)(k_pad / 32), (unsigned)(d / 32), (unsigned)k), 256, 0, s>>>(X, x_ld, B * T, T, d, dil, tap_base, k_pad, Wh, Wl);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+int launch_wgrad_tc_reduce(const float* P, int chunks, int d, int k, float* dW, cudaStream_t s) {
+  wgrad_tc_reduce_kernel<<<1024, 256, 0, s>>>(P, chunks, d, k, dW);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int* tf32_err_flag_dev() { return tf32_err_flag(); }
 
 int tf32_check_error() {
@@ -550,7 +639,9 @@ int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* 
     SSV_TRY(make_map_f32(&a.tmAh, Xh, 3, dims, strides, box));
     SSV_TRY(make_map_f32(&a.tmAl, Xl, 3, dims, strides, box));
   }
-  const int kp = L.k * L.cin_p;
+  const int kp = L.w_cols ? L.w_cols : L.k * L.cin_p;
+  SSV_CHECK(L.w_k_per_b == 0 || a.utt_per_tile == 1, "conv_tf32: split-K operands need whole 128-row tiles");
+  a.w_k_per_b = L.w_k_per_b;
   {
     cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)L.rows};
     cuuint64_t strides[1] = {(cuuint64_t)kp * 4};

@@ -26,6 +26,7 @@ struct alignas(64) ConvTf32Args {
   int n_real;               // LayerNorm width
   int n_cols;               // real weight rows / output columns (columns beyond are padding: zero weights, zero parameters)
   int y_cols;               // columns stored (multiple of 4)
+  int w_k_per_b;            // weight K origin advances by this much per "utterance" (split-K wgrad: utterance = K chunk); else 0
   int epi;                  // Epilogue (EPI_LN, EPI_LN_RELU, EPI_LN_SIGMOID, EPI_HIGHWAY; EPI_NONE: raw conv output + bias, plain column layout)
   int nstages;
   const float* bias;        // [N] fp32, indexed by global column
@@ -45,6 +46,8 @@ struct Tf32Layer {
   const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
   int rows = 0, cin = 0, cin_p = 0, k = 1;
   int cluster_n = 1, w0_base = 0, w0_rank = 0, w1_base = 0, w1_rank = 0, n_real = 0;
+  int w_cols = 0;           // K extent / row stride of the weight operand when it is not k * cin_p (split-K wgrad)
+  int w_k_per_b = 0;        // see ConvTf32Args
 };
 
 void tf32_shape_highway(Tf32Layer* L, int d);     // rows = 2 d, d in {256, 512}
@@ -54,6 +57,14 @@ int tf32_pack_weights(const float* w /*[n][cin][k]*/, int n, int cin, int k, int
 int tf32_pack_dgrad_weights(const float* w, int d, int k, float* hi, float* lo, cudaStream_t s);
 // ConvTranspose1d(k = 2, s = 2) weight (cin, cout, 2) as the 1x1 operand [2 cout][cin]
 int tf32_pack_deconv_weights(const float* w, int cin, int cout, float* hi, float* lo, cudaStream_t s);
+// wgrad of a highwayConv as a split-K GEMM on the same kernel (dW[co][ci][j] = sum_r dH[r][co] X[r shifted by tap j][ci]):
+//   A operand  = dH^T in K chunks, [chunk][2d][kc]   (the kernel's "activations": utterance = chunk, time step = co)
+//   B operand  = shifted X^T, [(j, ci)][chunks * kc] (the kernel's "weights", K origin advancing with the chunk)
+//   partials   = [chunk][2d][k * d], summed into dW (2d, d, k) by the reduce kernel
+int launch_wgrad_prep_dh(const float* dH, int M, int n2, int kc, int chunks, float* Ah, float* Al, cudaStream_t s);
+int launch_wgrad_prep_x(const float* X, int x_ld, int B, int T, int d, int k, int dil, int tap_base, int k_pad, float* Wh, float* Wl,
+                        cudaStream_t s);
+int launch_wgrad_tc_reduce(const float* P, int chunks, int d, int k, float* dW, cudaStream_t s);
 // x (fp32, any layout, n elements) -> hi = tf32(x), lo = tf32(x - hi)
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t s);
 // A launch with its TMA descriptors encoded: built once per (layer, buffers, shape) and replayed (encoding four tensor
