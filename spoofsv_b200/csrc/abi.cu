@@ -497,7 +497,20 @@ static int tf32_raw_conv(Arena& ar, float* Wh, float* Wl, const float* bias, int
   L.Wh = Wh; L.Wl = Wl; L.bias = bias;
   L.rows = rows; L.cin = cin; L.cin_p = cin; L.k = k;
   tf32_shape_plain(&L, rows);
-  return tf32_launch(L, EPI_NONE, dil, causal, xh, xl, x_ld, T, B, Y, nullptr, y_ld, s);
+  // few row tiles (TextEnc at 64 characters, the dgrad's narrow output): cut the input channels into chunks so that the
+  // launch fills the machine, and add the partial outputs up afterwards
+  const int n_tiles = T <= 64 ? (B + 1) / 2 : B * ((T + T32_BM - 1) / T32_BM);
+  const int room = tf32_max_clusters(L.cluster_n);
+  int ksplit = 1;
+  while (ksplit < 4 && n_tiles * ksplit * 2 <= room && cin % (T32_BK * ksplit * 2) == 0) ksplit *= 2;
+  if (ksplit == 1) return tf32_launch(L, EPI_NONE, dil, causal, xh, xl, x_ld, T, B, Y, nullptr, y_ld, s);
+  const long per = (long)B * T * y_ld;
+  float* P;
+  SSV_TRY(ar.alloc<float>((size_t)ksplit * per, &P));
+  Tf32Launch launch;
+  SSV_TRY(tf32_prepare_split(L, EPI_NONE, dil, causal, xh, xl, x_ld, T, B, P, nullptr, y_ld, ksplit, per, &launch));
+  SSV_TRY(tf32_run(launch, s));
+  return launch_sum_chunks(P, ksplit, per, Y, s);
 }
 
 // wgrad of a highwayConv on the tensor cores at FP32 accuracy: a split-K GEMM on conv_tf32x3_kernel (operand layouts in
@@ -507,8 +520,8 @@ static int tf32_wgrad(Arena& ar, const float* dH, const float* X, int B, int T, 
   const int M = B * T, n2 = 2 * d, n_all = k * d;
   const int taps_per_launch = n_all <= 1024 ? k : 1;            // N of one launch: at most four 256-column CTAs
   const int n_launch = taps_per_launch * d;
-  const int per_chunk = (n2 / T32_BM) * ((n_launch + 255) / 256);
-  int chunks = (device_sm_count() + per_chunk / 2) / per_chunk;
+  const int cluster_n = (n_launch + 255) / 256;
+  int chunks = tf32_max_clusters(cluster_n) / (n2 / T32_BM);      // one wave of clusters (a cluster of three does not fit every GPC)
   if (chunks < 1) chunks = 1;
   const int kc = round_up((M + chunks - 1) / chunks, 32);
   chunks = (M + kc - 1) / kc;

@@ -107,6 +107,8 @@ int launch_hwy_bwd_rows(const float* H, const float* X, const float* dY, int M, 
 int launch_colsum_partials(const float* partial, int nblk, int ncol, float* out, cudaStream_t s);
 int launch_pack_dgrad_w(const float* conv_w /*(2d,d,k)*/, int d, int k, float* dst /*[k*2d][d]*/, cudaStream_t s);
 int launch_add_inplace(float* a, const float* b, long n, cudaStream_t s);
+// out[i] = sum over chunks of P[c * per + i] (split-K partial outputs; per % 4 == 0)
+int launch_sum_chunks(const float* P, int chunks, long per, float* out, cudaStream_t s);
 int wgrad_chunks(int M);
 int launch_wgrad(const float* dH, const float* X, int M, int T, int d, int k, int dil, int causal,
                  float* P /*[chunks][k][2d][d]*/, float* dW /*(2d,d,k)*/, cudaStream_t s);

@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
   long long* prof = a.prof ? a.prof + (size_t)blockIdx.x * 8 : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = a.cluster_n > 1 ? cluster_rank() : 0u;
-  const int tile = blockIdx.x / a.cluster_n;
+  int tile = blockIdx.x / a.cluster_n;
+  int chunk = 0;
+  if (a.ksplit > 1) { chunk = tile % a.ksplit; tile /= a.ksplit; }
   int b0, t0;
   if (a.utt_per_tile > 1) { b0 = tile * a.utt_per_tile; t0 = 0; }
   else { b0 = tile / a.tiles_per_b; t0 = (tile - b0 * a.tiles_per_b) * T32_BM; }
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
       g = 0.f;
       be = 0.f;
     }
-    prm_s[j] = make_float4(gc < a.n_cols ? a.bias[gc] : 0.f, g, be, 0.f);
+    prm_s[j] = make_float4(gc < a.n_cols && chunk == 0 ? a.bias[gc] : 0.f, g, be, 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -136,13 +138,13 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
         uint8_t* S = tiles + (size_t)st * STAGE_BYTES;
         mbar_expect_tx(full_bar + st, STAGE_BYTES);
         const int j = kb / a.kb_per_tap;
-        const int c0 = (kb - j * a.kb_per_tap) * T32_BK;
+        const int c0 = (chunk * a.kb_per_tap + kb - j * a.kb_per_tap) * T32_BK;
         const int tc = t0 + (tap_base + j) * a.dil;
         tma_load_3d(S, &a.tmAh, full_bar + st, c0, tc, b0);
         tma_load_3d(S + A_HALF_BYTES, &a.tmAl, full_bar + st, c0, tc, b0);
         uint8_t* Bh = S + 2 * A_HALF_BYTES;
         uint8_t* Bl = Bh + B_HALF_BYTES;
-        const int wk = kb * T32_BK + b0 * a.w_k_per_b;
+        const int wk = j * a.w_tap_stride + c0 + b0 * a.w_k_per_b;
         tma_load_2d(Bh, &a.tmBh, full_bar + st, wk, w0);
         tma_load_2d(Bh + B_HALF_BYTES / 2, &a.tmBh, full_bar + st, wk, w1);
         tma_load_2d(Bl, &a.tmBl, full_bar + st, wk, w0);
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(NT, 1) conv_tf32x3_kernel(const __grid_constan
             *reinterpret_cast<float4*>(a.Yh + yoff[u] + gc) = hi;
             *reinterpret_cast<float4*>(a.Yl + yoff[u] + gc) = lo;
           } else {
-            *reinterpret_cast<float4*>(a.Yh + yoff[u] + gc) = v[u][h];
+            *reinterpret_cast<float4*>(a.Yh + (size_t)chunk * a.y_chunk_stride + yoff[u] + gc) = v[u][h];
           }
         }
       }
@@ -620,6 +622,43 @@ int tf32_check_error() {
 
 int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
                  float* Yh, float* Yl, int y_ld, Tf32Launch* out) {
+  return tf32_prepare_split(L, epi, dil, causal, Xh, Xl, x_ld, T, B, Yh, Yl, y_ld, 1, 0, out);
+}
+
+int tf32_max_clusters(int cluster_n) {
+  static int cached[5] = {0, 0, 0, 0, 0};
+  if (cluster_n < 1 || cluster_n > 4) return 0;
+  if (cached[cluster_n] == 0) {
+    int sm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    int n = sm / cluster_n;
+    if (cluster_n > 1) {
+      cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(sm / cluster_n * cluster_n));
+      cfg.blockDim = dim3(NT);
+      cfg.dynamicSmemBytes = 1024 + 256 + (size_t)T32_NL * 16 + 6 * T32_BM * 16 + 4 * (size_t)STAGE_BYTES;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)cluster_n;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int q = 0;
+      if (cudaOccupancyMaxActiveClusters(&q, conv_tf32x3_kernel, &cfg) == cudaSuccess && q > 0) n = q;
+      else cudaGetLastError();
+    }
+    cached[cluster_n] = n > 0 ? n : 1;
+  }
+  return cached[cluster_n];
+}
+
+int tf32_prepare_split(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
+                       float* Yh, float* Yl, int y_ld, int ksplit, long y_chunk_stride, Tf32Launch* out) {
+  SSV_CHECK(ksplit >= 1 && (ksplit == 1 || (epi == EPI_NONE && Yl == nullptr && L.cin_p % (T32_BK * ksplit) == 0 && L.w_k_per_b == 0)),
+            "conv_tf32: split-K needs the no-epilogue mode and Cin a multiple of %d", T32_BK * ksplit);
   SSV_CHECK(L.cin_p % T32_BK == 0 && x_ld >= L.cin_p && x_ld % 4 == 0, "conv_tf32: bad K padding (cin_p %d, ld %d)", L.cin_p, x_ld);
   SSV_CHECK(epi == EPI_HIGHWAY || epi == EPI_LN || epi == EPI_LN_RELU || epi == EPI_LN_SIGMOID || epi == EPI_NONE,
             "conv_tf32: epilogue %d not built", epi);
@@ -649,7 +688,10 @@ int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* 
     SSV_TRY(make_map_f32(&a.tmBh, L.Wh, 2, dims, strides, box));
     SSV_TRY(make_map_f32(&a.tmBl, L.Wl, 2, dims, strides, box));
   }
-  a.kb_per_tap = L.cin_p / T32_BK;
+  a.kb_per_tap = L.cin_p / T32_BK / ksplit;
+  a.ksplit = ksplit;
+  a.w_tap_stride = L.cin_p;
+  a.y_chunk_stride = y_chunk_stride;
   a.ktaps = L.k; a.dil = dil; a.causal = causal;
   a.cluster_n = L.cluster_n;
   a.w0_base = L.w0_base; a.w0_rank = L.w0_rank; a.w1_base = L.w1_base; a.w1_rank = L.w1_rank;
@@ -665,7 +707,7 @@ int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* 
   a.Xh = Xh; a.Xl = Xl; a.x_sb = (long)T * x_ld; a.x_st = x_ld;
   a.Yh = Yh; a.Yl = Yl; a.y_sb = (long)T * y_ld; a.y_st = y_ld;
   a.nstages = 4;
-  out->n_ctas = n_tiles * L.cluster_n;
+  out->n_ctas = n_tiles * ksplit * L.cluster_n;
   out->cluster_n = L.cluster_n;
   return kOk;
 }

@@ -27,6 +27,10 @@ struct alignas(64) ConvTf32Args {
   int n_cols;               // real weight rows / output columns (columns beyond are padding: zero weights, zero parameters)
   int y_cols;               // columns stored (multiple of 4)
   int w_k_per_b;            // weight K origin advances by this much per "utterance" (split-K wgrad: utterance = K chunk); else 0
+  int ksplit;               // EPI_NONE only: the input channels are cut into ksplit chunks, one CTA (cluster) per (tile, chunk);
+                            // chunk c writes its partial sums to Yh + c * y_chunk_stride (bias in chunk 0 only)
+  int w_tap_stride;         // K distance of two taps in the weight operand = the full padded Cin
+  long y_chunk_stride;
   int epi;                  // Epilogue (EPI_LN, EPI_LN_RELU, EPI_LN_SIGMOID, EPI_HIGHWAY; EPI_NONE: raw conv output + bias, plain column layout)
   int nstages;
   const float* bias;        // [N] fp32, indexed by global column
@@ -73,6 +77,12 @@ struct Tf32Launch {
   ConvTf32Args args;
   int n_ctas = 0, cluster_n = 1;
 };
+// ksplit > 1 (EPI_NONE, Yl == nullptr): split-K over the input channels; Yh then receives ksplit partial outputs,
+// y_chunk_stride floats apart
+int tf32_prepare_split(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
+                       float* Yh, float* Yl, int y_ld, int ksplit, long y_chunk_stride, Tf32Launch* out);
+// how many clusters of this size the device runs at once (one CTA per SM)
+int tf32_max_clusters(int cluster_n);
 int tf32_prepare(const Tf32Layer& L, int epi, int dil, int causal, const float* Xh, const float* Xl, int x_ld, int T, int B,
                  float* Yh, float* Yl, int y_ld, Tf32Launch* out);
 int tf32_run(const Tf32Launch& L, cudaStream_t s);

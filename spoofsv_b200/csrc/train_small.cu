@@ -196,6 +196,17 @@ __global__ void sum_chunks_kernel(const float* __restrict__ P, int chunks, long 
     out[i] = s;
   }
 }
+// float4 version for the split-K partial outputs of the conv kernels (per % 4 == 0)
+__global__ void sum_chunks4_kernel(const float4* __restrict__ P, int chunks, long per4, float4* __restrict__ out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per4; i += (long)gridDim.x * blockDim.x) {
+    float4 s = P[i];
+    for (int c = 1; c < chunks; ++c) {
+      const float4 v = P[(size_t)c * per4 + i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    out[i] = s;
+  }
+}
 
 // ---- attention backward, train branch: A = softmax_n(K^T q / 16), R = V A.
 // One warp per (b, t): g[n] = dA[n, t] + V[n, :] . dR[t, :];  dS[n] = A[n, t] (g[n] - sum_n' A[n', t] g[n']);
@@ -384,6 +395,14 @@ int wgrad_plain_chunks(int M) {
   int c = (M + 511) / 512;
   return c < 1 ? 1 : (c > 32 ? 32 : c);
 }
+int launch_sum_chunks(const float* P, int chunks, long per, float* out, cudaStream_t s) {
+  SSV_CHECK(per % 4 == 0, "sum_chunks: length must be a multiple of 4");
+  sum_chunks4_kernel<<<grid_for(per / 4), 256, 0, s>>>(reinterpret_cast<const float4*>(P), chunks, per / 4, reinterpret_cast<float4*>(out));
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int launch_wgrad_plain(const float* dH, int ldh, const float* X, int ldx, int M, int n, int cin, float* P, float* dW, cudaStream_t s) {
   const int chunks = wgrad_plain_chunks(M);
   const int rpc = ((M + chunks - 1) / chunks + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
