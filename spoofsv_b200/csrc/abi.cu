@@ -4,9 +4,10 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
-#include <map>
 #include <new>
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -30,13 +31,28 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
+// Per-stream scratch block behind the stream-ordered arenas: the standalone training ops make 10-20 workspace
+// allocations per call and a training step makes ~70 calls; as cudaMallocAsync / cudaFreeAsync pairs that was ~2000
+// driver calls per step on a host-bound path.  Calls on one stream are ordered, so consecutive calls can carve their
+// workspaces out of the same block; the block grows (stream-ordered free + alloc) when a call needed more.
+struct ScratchBlock {
+  void* base = nullptr;
+  size_t cap = 0;
+  bool in_use = false;          // a live Arena owns it (a nested Arena on the same stream falls back to cudaMallocAsync)
+};
+inline std::mutex& scratch_mutex() { static std::mutex m; return m; }
+inline std::map<cudaStream_t, ScratchBlock>& scratch_blocks() { static std::map<cudaStream_t, ScratchBlock> m; return m; }
+
 struct Arena {
   std::vector<void*> ptrs;
   cudaStream_t async_stream = nullptr;
   bool async = false;
+  char* blk = nullptr;          // this stream's scratch block
+  size_t blk_cap = 0, used = 0, wanted = 0;
+  bool owns_blk = false;
   Arena() = default;
-  // Stream-ordered scratch (cudaMallocAsync / cudaFreeAsync on `s`, pool memory kept between calls): for the per-call
-  // workspaces of the standalone ops, which would otherwise pay a cudaMalloc / cudaFree (= device sync) per buffer.
+  // Stream-ordered scratch (a cached block per stream, cudaMallocAsync / cudaFreeAsync on `s` beyond it): for the
+  // per-call workspaces of the standalone ops, which would otherwise pay a cudaMalloc / cudaFree (= device sync) per buffer.
   explicit Arena(cudaStream_t s) : async_stream(s), async(true) {
     static bool pool_configured = false;
     if (!pool_configured) {
@@ -49,17 +65,47 @@ struct Arena {
       cudaGetLastError();
       pool_configured = true;
     }
+    std::lock_guard<std::mutex> lock(scratch_mutex());
+    ScratchBlock& b = scratch_blocks()[s];
+    if (!b.in_use) {
+      b.in_use = owns_blk = true;
+      blk = static_cast<char*>(b.base);
+      blk_cap = b.cap;
+    }
   }
   ~Arena() {
     for (void* p : ptrs) {
       if (async) cudaFreeAsync(p, async_stream);
       else cudaFree(p);
     }
+    if (owns_blk) {
+      std::lock_guard<std::mutex> lock(scratch_mutex());
+      ScratchBlock& b = scratch_blocks()[async_stream];
+      if (wanted > blk_cap) {                  // grow this stream's block for the next call
+        if (b.base) cudaFreeAsync(b.base, async_stream);
+        b.base = nullptr;
+        b.cap = 0;
+        void* p = nullptr;
+        const size_t cap = wanted + wanted / 4;
+        if (cudaMallocAsync(&p, cap, async_stream) == cudaSuccess) { b.base = p; b.cap = cap; }
+        else cudaGetLastError();
+      }
+      b.in_use = false;
+    }
   }
   template <typename T>
   int alloc(size_t count, T** out) {
+    const size_t bytes = (count * sizeof(T) + 256 + 255) & ~size_t(255);
+    if (async) {
+      wanted += bytes;
+      if (used + bytes <= blk_cap) {
+        *out = reinterpret_cast<T*>(blk + used);
+        used += bytes;
+        return kOk;
+      }
+    }
     void* p = nullptr;
-    const cudaError_t e = async ? cudaMallocAsync(&p, count * sizeof(T) + 256, async_stream) : cudaMalloc(&p, count * sizeof(T) + 256);
+    const cudaError_t e = async ? cudaMallocAsync(&p, bytes, async_stream) : cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
       set_error("cudaMalloc of %zu bytes failed", count * sizeof(T));
@@ -513,6 +559,18 @@ static int tf32_raw_conv(Arena& ar, float* Wh, float* Wl, const float* bias, int
   return launch_sum_chunks(P, ksplit, per, Y, s);
 }
 
+// 4096 zero floats for the bias operand of the gradient GEMMs (allocated and cleared once)
+static const float* device_zeros() {
+  static float* z = nullptr;
+  if (!z) {
+    if (cudaMalloc((void**)&z, 4096 * sizeof(float)) != cudaSuccess || cudaMemset(z, 0, 4096 * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      z = nullptr;
+    }
+  }
+  return z;
+}
+
 // wgrad of a highwayConv on the tensor cores at FP32 accuracy: a split-K GEMM on conv_tf32x3_kernel (operand layouts in
 // conv_tc32.cuh).  dH (B T x 2d) and X (B T x d) channels-last -> dW (2d, d, k).
 static int tf32_wgrad(Arena& ar, const float* dH, const float* X, int B, int T, int d, int k, int dil, int causal, float* dW,
@@ -526,14 +584,14 @@ static int tf32_wgrad(Arena& ar, const float* dH, const float* X, int B, int T, 
   const int kc = round_up((M + chunks - 1) / chunks, 32);
   chunks = (M + kc - 1) / kc;
   const int k_pad = chunks * kc;
-  float *Ah, *Al, *Wh, *Wl, *P, *zero;
+  float *Ah, *Al, *Wh, *Wl, *P;
+  const float* zero = device_zeros();
+  SSV_CHECK(zero != nullptr, "wgrad: no memory for the zero bias");
   SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * kc, &Ah));
   SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * kc, &Al));
   SSV_TRY(ar.alloc<float>((size_t)n_all * k_pad, &Wh));
   SSV_TRY(ar.alloc<float>((size_t)n_all * k_pad, &Wl));
   SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * n_all, &P));
-  SSV_TRY(ar.alloc<float>(1024, &zero));
-  SSV_CUDA(cudaMemsetAsync(zero, 0, sizeof(float) * 1024, s));
   const int tap_base = causal ? -(k - 1) : -((k - 1) / 2);
   SSV_TRY(launch_wgrad_prep_dh(dH, M, n2, kc, chunks, Ah, Al, s));
   SSV_TRY(launch_wgrad_prep_x(X, d, B, T, d, k, dil, tap_base, k_pad, Wh, Wl, s));
@@ -611,7 +669,9 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   pm.m["ln2.weight"] = {ln2_w, d};
   pm.m["ln2.bias"] = {ln2_b, d};
   const int M = B * T;
-  float *xin, *dyr, *Hbuf = nullptr, *dH, *dxr, *dxc, *partial, *sums, *Wd, *zero_bias, *P;
+  float *xin, *dyr, *Hbuf = nullptr, *dH, *dxr, *dxc, *partial, *sums, *Wd, *P;
+  const float* zero_bias = device_zeros();
+  SSV_CHECK(zero_bias != nullptr, "highway_conv_bwd: no memory for the zero bias");
   SSV_TRY(ar.alloc<float>((size_t)M * d, &xin));
   SSV_TRY(ar.alloc<float>((size_t)M * d, &dyr));
   if (!h_saved) SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &Hbuf));
@@ -621,7 +681,6 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_TRY(ar.alloc<float>((size_t)hwy_bwd_row_blocks(M) * 6 * d, &partial));
   SSV_TRY(ar.alloc<float>((size_t)6 * d, &sums));
   SSV_TRY(ar.alloc<float>((size_t)k * 2 * d * d, &Wd));
-  SSV_TRY(ar.alloc<float>((size_t)d, &zero_bias));
   SSV_TRY(ar.alloc<float>(tc ? (size_t)4 : (size_t)wgrad_chunks(M) * k * 2 * d * d, &P));      // CUDA-core wgrad partials
   SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
   SSV_TRY(launch_transpose_in(dy, (long)d * T, T, 1, B, d, T, dyr, d, s));
@@ -644,14 +703,14 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   // 2. gate + LayerNorm backward per row, parameter partial sums
   int nblk = 0;
   SSV_TRY(launch_hwy_bwd_rows(H, xin, dyr, M, d, ln1_w, ln1_b, ln2_w, ln2_b, dH, dxr, partial, &nblk, s));
-  SSV_TRY(launch_colsum_partials(partial, nblk, 6 * d, sums, s));
-  SSV_CUDA(cudaMemcpyAsync(dln1_w, sums, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
-  SSV_CUDA(cudaMemcpyAsync(dln1_b, sums + d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
-  SSV_CUDA(cudaMemcpyAsync(dln2_w, sums + 2 * d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
-  SSV_CUDA(cudaMemcpyAsync(dln2_b, sums + 3 * d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
-  SSV_CUDA(cudaMemcpyAsync(dconv_b, sums + 4 * d, sizeof(float) * 2 * d, cudaMemcpyDeviceToDevice, s));
+  {
+    ColSegs sg{};
+    sg.n = 5;
+    float* dst[5] = {dln1_w, dln1_b, dln2_w, dln2_b, dconv_b};
+    for (int i = 0; i < 5; ++i) { sg.dst[i] = dst[i]; sg.begin[i] = i * d; sg.len[i] = i == 4 ? 2 * d : d; }
+    SSV_TRY(launch_colsum_scatter(partial, nblk, 6 * d, sg, s));
+  }
   // 3. dgrad: the forward's conv kernel on dH with time-flipped, transposed weights and mirrored taps
-  SSV_CUDA(cudaMemsetAsync(zero_bias, 0, sizeof(float) * d, s));
   if (tc) {
     float* Wdl;
     SSV_TRY(ar.alloc<float>((size_t)k * 2 * d * d, &Wdl));
@@ -660,7 +719,7 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   } else {
     SSV_TRY(launch_pack_dgrad_w(conv_w, d, k, Wd, s));
     ConvPack g;
-    g.W = Wd; g.bias = zero_bias; g.cin = 2 * d; g.cin_p = 2 * d; g.k = k; g.n = d; g.n_pad = d;
+    g.W = Wd; g.bias = const_cast<float*>(zero_bias); g.cin = 2 * d; g.cin_p = 2 * d; g.k = k; g.n = d; g.n_pad = d;
     SSV_TRY(run_conv(g, EPI_NONE, dilation, causal ? 2 : 0, dH, 2 * d, T, B, dxc, d, s));
   }
   SSV_TRY(launch_add_inplace(dxc, dxr, (long)M * d, s));
@@ -719,9 +778,13 @@ int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float
   SSV_TRY(launch_transpose_in(dy, (long)n * T, T, 1, B, n, T, dyr, n_pad, s));
   // LayerNorm backward per row, parameter sums
   SSV_TRY(launch_ln_rows_bwd(h_saved, n_pad, dyr, n_pad, M, n, ln_w, dH, partial, s));
-  SSV_TRY(launch_colsum_partials(partial, nblk, pc, sums, s));
-  SSV_CUDA(cudaMemcpyAsync(dln_w, sums, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
-  SSV_CUDA(cudaMemcpyAsync(dln_b, sums + pc / 2, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  {
+    ColSegs sg{};
+    sg.n = 2;
+    sg.dst[0] = dln_w; sg.begin[0] = 0; sg.len[0] = n;
+    sg.dst[1] = dln_b; sg.begin[1] = pc / 2; sg.len[1] = n;
+    SSV_TRY(launch_colsum_scatter(partial, nblk, pc, sg, s));
+  }
   // bias gradients: per utterance (the speaker projection's), summed over the utterances for the conv bias
   SSV_TRY(launch_utt_colsum(dH, n_pad, B, T, n, U, s));
   SSV_TRY(launch_colsum_partials(U, B, n, db, s));
@@ -729,14 +792,14 @@ int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float
   // dgrad: dX = dH W through the forward's conv kernel (W as the [K = n][N = cin] operand)
   if (dx) {
     const int k_p = round_up(n, 16);
-    float *Wd, *zero_bias, *dxr;
+    float *Wd, *dxr;
+    const float* zero_bias = device_zeros();
+    SSV_CHECK(zero_bias != nullptr, "conv_ln_bwd: no memory for the zero bias");
     SSV_TRY(ar.alloc<float>((size_t)k_p * x_ld, &Wd));
-    SSV_TRY(ar.alloc<float>((size_t)x_ld, &zero_bias));
     SSV_TRY(ar.alloc<float>((size_t)M * x_ld, &dxr));
     SSV_TRY(launch_pad_matrix(w, n, cin, k_p, x_ld, Wd, s));
-    SSV_CUDA(cudaMemsetAsync(zero_bias, 0, sizeof(float) * x_ld, s));
     ConvPack g;
-    g.W = Wd; g.bias = zero_bias; g.cin = n; g.cin_p = k_p; g.k = 1; g.n = cin; g.n_pad = x_ld;
+    g.W = Wd; g.bias = const_cast<float*>(zero_bias); g.cin = n; g.cin_p = k_p; g.k = 1; g.n = cin; g.n_pad = x_ld;
     SSV_TRY(run_conv(g, EPI_NONE, 1, 0, dH, n_pad, T, B, dxr, x_ld, s));
     if (relu_in) SSV_TRY(launch_relu_mask(dxr, xin, (long)M * x_ld, s));
     SSV_TRY(launch_transpose_out(dxr, x_ld, B, cin, T, dx, s));
@@ -811,11 +874,12 @@ int ssv_text_embedding_bwd(const int64_t* ids, const float* dy, int B, int N, in
   SSV_CHECK(B > 0 && N > 0 && vocab > 0 && E > 0, "text_embedding_bwd: empty input");
   cudaStream_t s = as_stream(stream);
   Arena ar(s);
-  float *rows, *dWt;
+  float *rows, *dWt, *scratch;
   SSV_TRY(ar.alloc<float>((size_t)B * N * E, &rows));
   SSV_TRY(ar.alloc<float>((size_t)vocab * E, &dWt));
+  SSV_TRY(ar.alloc<float>((size_t)embed_bwd_scratch_floats(vocab, E), &scratch));
   SSV_TRY(launch_transpose_in(dy, (long)E * N, N, 1, B, E, N, rows, E, s));
-  SSV_TRY(launch_embed_bwd(ids, B * N, rows, E, vocab, E, dWt, dbias, s));
+  SSV_TRY(launch_embed_bwd(ids, B * N, rows, E, vocab, E, scratch, dWt, dbias, s));
   SSV_TRY(launch_transpose_out(dWt, E, 1, E, vocab, dweight, s));                   // (vocab, E) -> (E, vocab)
   return kOk;
 }

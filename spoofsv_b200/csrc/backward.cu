@@ -157,6 +157,18 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int nb
   out[c] = s;
 }
 
+// the same, with the column range cut into up to 6 segments that go to separate destinations (the parameter gradients
+// of one layer): saves a device-to-device copy per gradient on a host-bound path
+__global__ void colsum_scatter_kernel(const float* __restrict__ partial, int nblk, int ncol, ColSegs segs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * ncol + c];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < segs.n && c >= segs.begin[i] && c < segs.begin[i] + segs.len[i]) segs.dst[i][c - segs.begin[i]] = s;
+}
+
 // dgrad weight: Wd[(j' * 2d + co)][ci] = conv_w[co][ci][k - 1 - j']   (conv_w is (2d, d, k))
 __global__ void pack_dgrad_w_kernel(const float* __restrict__ w, int d, int k, float* __restrict__ dst) {
   const long total = (long)k * 2 * d * d;
@@ -274,6 +286,13 @@ int hwy_bwd_row_blocks(int M) { return (M + BWD_RPB - 1) / BWD_RPB; }
 
 int launch_colsum_partials(const float* partial, int nblk, int ncol, float* out, cudaStream_t s) {
   colsum_partials_kernel<<<(ncol + 255) / 256, 256, 0, s>>>(partial, nblk, ncol, out);
+  SSV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return kOk;
+}
+
+int launch_colsum_scatter(const float* partial, int nblk, int ncol, const ColSegs& segs, cudaStream_t s) {
+  colsum_scatter_kernel<<<(ncol + 255) / 256, 256, 0, s>>>(partial, nblk, ncol, segs);
   SSV_CUDA(cudaGetLastError());
   ++g_launches;
   return kOk;

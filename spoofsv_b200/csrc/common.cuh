@@ -105,6 +105,13 @@ int launch_hwy_bwd_rows(const float* H, const float* X, const float* dY, int M, 
                         const float* g2, const float* b2, float* dH, float* dXres, float* partial /*[blocks][6d]*/,
                         int* nblk_out, cudaStream_t s);
 int launch_colsum_partials(const float* partial, int nblk, int ncol, float* out, cudaStream_t s);
+struct ColSegs {          // column ranges [begin, begin + len) of a column-sum row and where each goes
+  float* dst[6];
+  int begin[6];
+  int len[6];
+  int n;
+};
+int launch_colsum_scatter(const float* partial, int nblk, int ncol, const ColSegs& segs, cudaStream_t s);
 int launch_pack_dgrad_w(const float* conv_w /*(2d,d,k)*/, int d, int k, float* dst /*[k*2d][d]*/, cudaStream_t s);
 int launch_add_inplace(float* a, const float* b, long n, cudaStream_t s);
 // out[i] = sum over chunks of P[c * per + i] (split-K partial outputs; per % 4 == 0)
@@ -129,7 +136,8 @@ int launch_wgrad_plain(const float* dH, int ldh, const float* X, int ldx, int M,
 int launch_att_bwd(const float* Kx /*(B,N,512)*/, const float* Q /*(B,T,256)*/, const float* dR, int ldr, const float* dq_add,
                    const float* A, const float* dA, int B, int N, int T, float* dS /*(B,N,T)*/, float* dq /*(B,T,256)*/,
                    float* dKx /*(B,N,512)*/, cudaStream_t s);
-int launch_embed_bwd(const int64_t* ids, int rows, const float* dX, int ld, int vocab, int E, float* dWt /*[vocab][E]*/, float* dbias,
+int embed_bwd_scratch_floats(int vocab, int E);
+int launch_embed_bwd(const int64_t* ids, int rows, const float* dX, int ld, int vocab, int E, float* scratch, float* dWt, float* dbias,
                      cudaStream_t s);
 int launch_linear_small_bwd(const float* dS, int ds_ld, const float* x, long x_ld, int B, int in_f, int out_f, float* dW, float* db,
                             cudaStream_t s);

@@ -311,8 +311,10 @@ def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, gro
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group)
             terms /= dist.get_world_size(group)
-        t_l1, t_bd, t_att, t_disc = (float(v) for v in terms.tolist())
-        scale = (t_l1 + t_bd + t_att) / abs(t_disc)
+        # the weight stays on the device (a detached 0-d tensor): reading the four values back here, as the reference's
+        # Python floats do, would stall the host between forward and backward and leave the GPU waiting for the
+        # backward kernels to be issued; they are read once, after the optimizer step
+        scale = (terms[0] + terms[1] + terms[2]) / terms[3].abs()
         loss = loss_l1 + loss_bd + loss_att + scale * loss_disc
         if reducer is not None:
             reducer.begin()                      # bucket allreduces start from the gradient hooks, under the backward pass
@@ -322,7 +324,9 @@ def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, gro
     else:
         allreduce_gradients(model.parameters(), group=group)
     opt_syn.step()
-    return {"l1": t_l1, "bin_div": t_bd, "att": t_att, "disc": t_disc, "loss": t_l1 + t_bd + t_att + scale * t_disc}
+    t_l1, t_bd, t_att, t_disc = (float(v) for v in terms.tolist())
+    scale_f = (t_l1 + t_bd + t_att) / abs(t_disc)
+    return {"l1": t_l1, "bin_div": t_bd, "att": t_att, "disc": t_disc, "loss": t_l1 + t_bd + t_att + scale_f * t_disc}
 
 
 def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff=None, group=None, shard_weight: float = 1.0):
@@ -368,12 +372,13 @@ def ssrn_generator_step(model, disc, opt_syn, mel_gt, lin_gt, cfg=None, group=No
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group)
             terms /= dist.get_world_size(group)
-        t_l1, t_bd, t_disc = (float(v) for v in terms.tolist())
-        scale = (t_l1 + t_bd) / abs(t_disc)
+        scale = (terms[0] + terms[1]) / terms[2].abs()           # on the device, see generator_step
         ((loss_l1 + loss_bd + scale * loss_disc) * shard_weight).backward()
     allreduce_gradients(model.parameters(), group=group)
     opt_syn.step()
-    return {"l1": t_l1, "bin_div": t_bd, "disc": t_disc, "loss": t_l1 + t_bd + scale * t_disc}
+    t_l1, t_bd, t_disc = (float(v) for v in terms.tolist())
+    scale_f = (t_l1 + t_bd) / abs(t_disc)
+    return {"l1": t_l1, "bin_div": t_bd, "disc": t_disc, "loss": t_l1 + t_bd + scale_f * t_disc}
 
 
 def ssrn_discriminator_step(model, disc, opt_disc, mel_gt, lin_gt, cfg, coeff=None, group=None, shard_weight: float = 1.0):

@@ -29,7 +29,9 @@ def timeit(fn, n=5):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); t0 = time.perf_counter(); e0.record()
     for _ in range(n): fn()
+    t_issue = time.perf_counter()
     e1.record(); torch.cuda.synchronize()
+    print("   (host issue time %.2f ms per call)" % (1e3 * (t_issue - t0) / n), flush=True)
     return e0.elapsed_time(e1) / n, 1e3 * (time.perf_counter() - t0) / n
 
 print("ours  (fwd+bwd) gpu %.2f ms, wall %.2f ms" % timeit(step_ours), flush=True)
