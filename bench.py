@@ -603,6 +603,22 @@ def main():
                 extra["config5_g_iteration_allreduce_after_backward_ms"] = g_post_ms
             extra["config5_g_iteration_ms"] = g_ms
             extra["config5_d_iteration_ms"] = d_ms
+            if world == 1:
+                # the same two iterations captured in CUDA graphs and replayed (fixed shapes): issued kernel by kernel
+                # the host sets the pace of both (~800 launches / several hundred small autograd ops)
+                try:
+                    m1.layerwise_train_forward = True
+                    gg = TR.GraphedIteration(lambda mel, i, sp: TR.generator_body(m1, disc, og, mel, i, sp, gaw, {"LAMBDA": 10}),
+                                             (mel_g, ids_t, spk_t), parameters=list(m1.parameters()) + list(disc.parameters()))
+                    gd = TR.GraphedIteration(lambda mel, i, sp: TR.discriminator_body(m1, disc, od, mel, i, sp, {"LAMBDA": 10}),
+                                             (mel_g, ids_t, spk_t), parameters=list(m1.parameters()) + list(disc.parameters()))
+                    extra["config5_g_iteration_graph_ms"] = timed(lambda: gg(mel_g, ids_t, spk_t))
+                    extra["config5_d_iteration_graph_ms"] = timed(lambda: gd(mel_g, ids_t, spk_t))
+                    del gg, gd
+                except Exception as exc:
+                    extra["config5_graph_error"] = f"{type(exc).__name__}: {exc}"
+                finally:
+                    m1.layerwise_train_forward = False
             extra["config5"] = {"global_batch": Bg, "per_rank_batch": sl.stop - sl.start, "text_len": Nt, "frames": T, "dtype": "fp32",
                                 "allreduce": "NCCL, 8 MB buckets launched from gradient hooks during backward" if world > 1 else "none (1 rank)",
                                 "g_allreduce_elements": 24_073_584 if world > 1 else 0, "d_allreduce_elements": 119_233 if world > 1 else 0}

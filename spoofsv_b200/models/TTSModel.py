@@ -445,7 +445,12 @@ class melSyn(_Native):
         column is the next input frame -> (Y (B,F,t), A (B,N,t), max_att).  Y and A are views of
         decoder-owned buffers.  ``A_last`` is not read (its columns are already held here)."""
         if self.training:
-            if self.precision in ("fp32", "fp32-ffma") and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # layerwise_train_forward: also without a graph (the discriminator iteration) go layer by layer instead of
+            # through the fused forward, whose packed copy of the weights is rebuilt on the host after every optimizer
+            # step -- a CUDA-graph capture of the iteration (train.GraphedIteration) cannot contain that
+            layerwise = getattr(self, "layerwise_train_forward", False) or (
+                torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
+            if self.precision in ("fp32", "fp32-ffma") and layerwise:
                 return self._train_forward_autograd(melspec, textid, spkemb)
             return self._train_forward(melspec, textid, spkemb)
         _lib.require_cuda(melspec, "melSyn.forward melspec")

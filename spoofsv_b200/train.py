@@ -288,8 +288,22 @@ def fp32_math():
 
 def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group=None, shard_weight: float = 1.0,
                    reducer: "OverlappedGradReducer | None" = None):
+    terms = generator_body(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group, shard_weight, reducer)
+    return generator_terms(terms)
+
+
+def generator_terms(terms) -> dict:
+    """The loss dictionary of a 'G' iteration from the device tensor generator_body returns (one host read)."""
+    t_l1, t_bd, t_att, t_disc = (float(v) for v in terms.tolist())
+    scale_f = (t_l1 + t_bd + t_att) / abs(t_disc)
+    return {"l1": t_l1, "bin_div": t_bd, "att": t_att, "disc": t_disc, "loss": t_l1 + t_bd + t_att + scale_f * t_disc}
+
+
+def generator_body(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, group=None, shard_weight: float = 1.0,
+                   reducer: "OverlappedGradReducer | None" = None):
     """One 'G' iteration (:277-300): teacher-forced forward, L1 + binary divergence + guided attention + adversarial
-    term scaled to the size of the other three, backward, gradient allreduce, Adam step.  Returns the loss terms.
+    term scaled to the size of the other three, backward, gradient allreduce, Adam step.  Returns the four loss terms as a device tensor
+    (no host synchronisation anywhere in the body: it can be captured in a CUDA graph, `GraphedIteration`).
     `reducer` (an OverlappedGradReducer over model.parameters()) overlaps the bucket allreduces with the backward pass;
     without it the buckets are reduced after backward.  `shard_weight` = local_items * world / global_items (1.0 for equal shards): the rank's mean losses and their
     gradients are weighted by it, so that the average over ranks is the mean over the GLOBAL batch even when the
@@ -324,23 +338,36 @@ def generator_step(model, disc, opt_syn, mel_gt, text_id, spk_emb, gaw, cfg, gro
     else:
         allreduce_gradients(model.parameters(), group=group)
     opt_syn.step()
-    t_l1, t_bd, t_att, t_disc = (float(v) for v in terms.tolist())
-    scale_f = (t_l1 + t_bd + t_att) / abs(t_disc)
-    return {"l1": t_l1, "bin_div": t_bd, "att": t_att, "disc": t_disc, "loss": t_l1 + t_bd + t_att + scale_f * t_disc}
+    return terms
 
 
 def discriminator_step(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff=None, group=None, shard_weight: float = 1.0):
     """One 'D' iteration (:302-322): WGAN-GP.  The generator runs without a graph (its output is detached in the
     reference), the gradient penalty differentiates through the discriminator's backward pass (autograd).
     `coeff` (B,) are the interpolation weights (reference: torch.rand(B), one per utterance)."""
+    return wgan_terms(discriminator_body(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff, group, shard_weight))
+
+
+def discriminator_body(model, disc, opt_disc, mel_gt, text_id, spk_emb, cfg, coeff=None, group=None, shard_weight: float = 1.0):
+    """discriminator_step without the host read of the loss values: returns the device tensor (gradient penalty,
+    discriminator loss)."""
     opt_disc.zero_grad(set_to_none=True)
     spec_inputs = torch.cat((torch.zeros_like(mel_gt[:, :, :1]), mel_gt[:, :, :-1]), dim=-1)
     with torch.no_grad():
         pred, _ = model(spec_inputs, text_id, spk_emb)
-    return _wgan_gp_step(disc, opt_disc, mel_gt, pred, cfg, coeff, group, shard_weight)
+    return _wgan_gp_body(disc, opt_disc, mel_gt, pred, cfg, coeff, group, shard_weight)
+
+
+def wgan_terms(t) -> dict:
+    gp, ld = (float(v) for v in t.tolist())
+    return {"gp": gp, "wd": -ld, "loss": ld + gp}
 
 
 def _wgan_gp_step(disc, opt_disc, real, fake, cfg, coeff, group, shard_weight: float = 1.0):
+    return wgan_terms(_wgan_gp_body(disc, opt_disc, real, fake, cfg, coeff, group, shard_weight))
+
+
+def _wgan_gp_body(disc, opt_disc, real, fake, cfg, coeff, group, shard_weight: float = 1.0):
     B = real.shape[0]
     if coeff is None:
         coeff = torch.rand(B, device=real.device)
@@ -355,7 +382,44 @@ def _wgan_gp_step(disc, opt_disc, real, fake, cfg, coeff, group, shard_weight: f
         (loss_d * shard_weight if shard_weight != 1.0 else loss_d).backward()
     allreduce_gradients(disc.parameters(), group=group)
     opt_disc.step()
-    return {"gp": loss_gp.item(), "wd": -loss_d.item(), "loss": loss_d.item() + loss_gp.item()}
+    return torch.stack([loss_gp.detach(), loss_d.detach()])
+
+
+class GraphedIteration:
+    """One training iteration of fixed shapes, captured in a CUDA graph and replayed (single process).
+
+    A generator iteration is ~800 kernel launches and a discriminator iteration several hundred small autograd ops: issued
+    one by one the host, not the GPU, sets the pace (15 ms each at the config-5 shape).  `body(*inputs)` must not read
+    anything back to the host (generator_body / discriminator_body) and its optimizer must be built with
+    `capturable=True`.  The warm-up iterations run on the capture stream (the library's per-stream scratch block and its
+    one-time allocations are in place before the capture starts) and ARE training iterations on the first batch.
+    `__call__` copies the new batch into the static input tensors, replays, and returns the body's (static) output.
+    `parameters`: every parameter whose `.grad` the body writes, including those it does not zero itself (the generator
+    iteration also accumulates into the discriminator's gradients).  Their `.grad` is dropped before the capture so that
+    the graph allocates them in its own pool: a gradient tensor left over from an eager iteration would be captured by
+    address and may be returned to the driver later (the next capture empties the allocator's cache)."""
+
+    def __init__(self, body, inputs, warmup: int = 3, parameters=None):
+        self.inputs = [t.clone() for t in inputs]
+        self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                body(*self.inputs)
+        torch.cuda.current_stream().wait_stream(self.stream)
+        torch.cuda.synchronize()
+        for p in (parameters or ()):
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.out = body(*self.inputs)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
+        self.graph.replay()
+        return self.out
 
 
 def ssrn_generator_step(model, disc, opt_syn, mel_gt, lin_gt, cfg=None, group=None, shard_weight: float = 1.0):

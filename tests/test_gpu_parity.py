@@ -917,3 +917,69 @@ def test_ssrn_adversarial_step_vs_oracle(cuda_models_k):
     with torch.no_grad():
         wd = -float(torch.mean(ref_disc(pred) - ref_disc(lin.double())))
     assert abs(dt["gp"] - gp) <= 1e-4 * max(1.0, abs(gp)) and abs(dt["wd"] - wd) <= 1e-4 * max(1.0, abs(wd))
+
+
+def test_graphed_training_iterations_match_eager(cuda_models_k):
+    """train.GraphedIteration: the G and the D iteration captured in CUDA graphs and replayed give the loss terms and the
+    updated parameters of the eager iterations from the same state (dropout off: the discriminator must be
+    deterministic for the comparison; Adam built capturable)."""
+    from spoofsv_b200 import train as TR
+    from oracle import weights as Wt
+    m1, _, _, _ = cuda_models_k
+    sd0 = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+    B, N, T = 4, 24, 48
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    ids = Wt.synthetic_text(B, N, seed=9).cuda()
+    spk = torch.randn((B, m1.spkemb_dim, 1), device="cuda", generator=gen) * 0.1
+    mel = torch.rand((B, 80, T), device="cuda", generator=gen) * 0.9 + 0.05
+    coeff = torch.rand(B, device="cuda", generator=gen)
+    torch.manual_seed(11)
+    disc = TR.melDisc(80, 128).cuda().train()
+    for mod in disc.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    gaw = TR.guided_attention_mat(186, 325, device="cuda")
+    cfg = {"LAMBDA": 10}
+    og = torch.optim.Adam(m1.parameters(), 2e-4, (0.5, 0.9), 1e-6, capturable=True)
+    od = torch.optim.Adam(disc.parameters(), 2e-4, (0.5, 0.9), 1e-6, capturable=True)
+
+    def snapshot(mod, opt):
+        out = [p.detach().clone() for p in mod.parameters()]
+        for st in opt.state.values():
+            out += [v.clone() for v in st.values() if torch.is_tensor(v)]
+        return out
+
+    def restore(mod, opt, snap):
+        it = iter(snap)
+        with torch.no_grad():
+            for p in mod.parameters():
+                p.copy_(next(it))
+            for st in opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.copy_(next(it))
+
+    was_training = m1.training
+    try:
+        m1.train()
+        m1.layerwise_train_forward = True
+        for body, mod, opt, inputs, to_dict in (
+                (lambda me, i, sp: TR.generator_body(m1, disc, og, me, i, sp, gaw, cfg), m1, og, (mel, ids, spk), TR.generator_terms),
+                (lambda me, i, sp, c: TR.discriminator_body(m1, disc, od, me, i, sp, cfg, coeff=c), disc, od, (mel, ids, spk, coeff),
+                 TR.wgan_terms)):
+            g = TR.GraphedIteration(body, inputs, parameters=list(m1.parameters()) + list(disc.parameters()))
+            snap = snapshot(mod, opt)
+            got = to_dict(g(*inputs))
+            p_graph = [p.detach().clone() for p in mod.parameters()]
+            restore(mod, opt, snap)
+            want = to_dict(body(*inputs))
+            for k in want:
+                assert abs(got[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), (k, got[k], want[k])
+            for a, b in zip(p_graph, mod.parameters()):
+                assert float((a - b).abs().max()) <= 1e-7
+            del g
+    finally:
+        m1.layerwise_train_forward = False
+        m1.train(was_training)
+        m1.zero_grad(set_to_none=True)
+        m1.load_state_dict(sd0)
