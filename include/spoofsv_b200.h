@@ -161,10 +161,12 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
 /* y (B, n, T) = LN(W relu?(x) + b (+ sb per utterance)); h_save: (B T) x round_up(n, 64) floats for the backward. */
 int ssv_conv_ln_fwd_save(const float* x, const float* w, const float* b, const float* sb /* (B, n) or NULL */,
                          const float* ln_w, const float* ln_b, int B, int cin, int n, int T, int relu_in, float* y,
-                         float* h_save, void* stream);
+                         float* h_save, int precision /* SSV_PREC_FP32: conv on the tensor cores (3xTF32); SSV_PREC_FP32_FFMA */,
+                         void* stream);
 int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float* ln_w, const float* h_saved, int B, int cin,
                     int n, int T, int relu_in, float* dx /* or NULL */, float* dw, float* db, float* dsb /* (B, n) or NULL */,
-                    float* dln_w, float* dln_b, void* stream);
+                    float* dln_w, float* dln_b, int precision /* dgrad and wgrad on the tensor cores or the CUDA cores */,
+                    void* stream);
 /* kv (B, 512, N) = [K ; V], q (B, 256, T) -> A (B, N, T) = softmax_n(K^T q / 16), rq (B, 512, T) = [V A ; q] */
 int ssv_attention_train_fwd(const float* kv, const float* q, int B, int N, int T, float* A, float* rq, void* stream);
 int ssv_attention_train_bwd(const float* kv, const float* q, const float* A, const float* dA /* or NULL */, const float* drq,

@@ -81,7 +81,12 @@ struct Arena {
     if (owns_blk) {
       std::lock_guard<std::mutex> lock(scratch_mutex());
       ScratchBlock& b = scratch_blocks()[async_stream];
-      if (wanted > blk_cap) {                  // grow this stream's block for the next call
+      cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+      if (wanted > blk_cap && cudaStreamIsCapturing(async_stream, &cap_status) != cudaSuccess) cudaGetLastError();
+      // grow this stream's block for the next call -- never inside a stream capture: the block must outlive the graph,
+      // and freeing an allocation made outside the capture is not a capturable operation (the fall-back allocations of
+      // this call were captured as the graph's own memory nodes, which is fine)
+      if (wanted > blk_cap && cap_status == cudaStreamCaptureStatusNone) {
         if (b.base) cudaFreeAsync(b.base, async_stream);
         b.base = nullptr;
         b.cap = 0;
@@ -571,15 +576,18 @@ static const float* device_zeros() {
   return z;
 }
 
-// wgrad of a highwayConv on the tensor cores at FP32 accuracy: a split-K GEMM on conv_tf32x3_kernel (operand layouts in
-// conv_tc32.cuh).  dH (B T x 2d) and X (B T x d) channels-last -> dW (2d, d, k).
-static int tf32_wgrad(Arena& ar, const float* dH, const float* X, int B, int T, int d, int k, int dil, int causal, float* dW,
-                      cudaStream_t s) {
-  const int M = B * T, n2 = 2 * d, n_all = k * d;
+// wgrad on the tensor cores at FP32 accuracy: a split-K GEMM on conv_tf32x3_kernel (operand layouts in conv_tc32.cuh).
+// dH (B T x ldh, n_out columns) and X (B T x ldx, cin columns) channels-last -> dW (n_out, cin, k).  A highwayConv has
+// n_out = 2d, cin = d; the 1x1 layers any n_out > 64 and cin.
+static int tf32_wgrad(Arena& ar, const float* dH, int ldh, int n_out, const float* X, int ldx, int cin, int B, int T, int k, int dil,
+                      int causal, float* dW, cudaStream_t s) {
+  SSV_CHECK(n_out > 64 && cin % 4 == 0, "wgrad: shape (n %d, cin %d) not built on the tensor-core arm", n_out, cin);
+  const int M = B * T, n_all = k * cin;
   const int taps_per_launch = n_all <= 1024 ? k : 1;            // N of one launch: at most four 256-column CTAs
-  const int n_launch = taps_per_launch * d;
+  const int n_launch = taps_per_launch * cin;
   const int cluster_n = (n_launch + 255) / 256;
-  int chunks = tf32_max_clusters(cluster_n) / (n2 / T32_BM);      // one wave of clusters (a cluster of three does not fit every GPC)
+  const int tiles = (n_out + T32_BM - 1) / T32_BM;
+  int chunks = tf32_max_clusters(cluster_n) / tiles;             // one wave of clusters (a cluster of three does not fit every GPC)
   if (chunks < 1) chunks = 1;
   const int kc = round_up((M + chunks - 1) / chunks, 32);
   chunks = (M + kc - 1) / kc;
@@ -587,25 +595,25 @@ static int tf32_wgrad(Arena& ar, const float* dH, const float* X, int B, int T, 
   float *Ah, *Al, *Wh, *Wl, *P;
   const float* zero = device_zeros();
   SSV_CHECK(zero != nullptr, "wgrad: no memory for the zero bias");
-  SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * kc, &Ah));
-  SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * kc, &Al));
+  SSV_TRY(ar.alloc<float>((size_t)chunks * n_out * kc, &Ah));
+  SSV_TRY(ar.alloc<float>((size_t)chunks * n_out * kc, &Al));
   SSV_TRY(ar.alloc<float>((size_t)n_all * k_pad, &Wh));
   SSV_TRY(ar.alloc<float>((size_t)n_all * k_pad, &Wl));
-  SSV_TRY(ar.alloc<float>((size_t)chunks * n2 * n_all, &P));
+  SSV_TRY(ar.alloc<float>((size_t)chunks * n_out * n_all, &P));
   const int tap_base = causal ? -(k - 1) : -((k - 1) / 2);
-  SSV_TRY(launch_wgrad_prep_dh(dH, M, n2, kc, chunks, Ah, Al, s));
-  SSV_TRY(launch_wgrad_prep_x(X, d, B, T, d, k, dil, tap_base, k_pad, Wh, Wl, s));
+  SSV_TRY(launch_wgrad_prep_dh(dH, ldh, M, n_out, kc, chunks, Ah, Al, s));
+  SSV_TRY(launch_wgrad_prep_x(X, ldx, B, T, cin, k, dil, tap_base, k_pad, Wh, Wl, s));
   for (int j0 = 0; j0 < k; j0 += taps_per_launch) {
     Tf32Layer L;
-    L.Wh = Wh + (size_t)j0 * d * k_pad;
-    L.Wl = Wl + (size_t)j0 * d * k_pad;
+    L.Wh = Wh + (size_t)j0 * cin * k_pad;
+    L.Wl = Wl + (size_t)j0 * cin * k_pad;
     L.bias = zero;
     L.rows = n_launch; L.cin = kc; L.cin_p = kc; L.k = 1;
     L.w_cols = k_pad; L.w_k_per_b = kc;
     tf32_shape_plain(&L, n_launch);
-    SSV_TRY(tf32_launch(L, EPI_NONE, 1, 0, Ah, Al, kc, n2, chunks, P + (size_t)j0 * d, nullptr, n_all, s));
+    SSV_TRY(tf32_launch(L, EPI_NONE, 1, 0, Ah, Al, kc, n_out, chunks, P + (size_t)j0 * cin, nullptr, n_all, s));
   }
-  return launch_wgrad_tc_reduce(P, chunks, d, k, dW, s);
+  return launch_wgrad_tc_reduce(P, chunks, n_out, cin, k, dW, s);
 }
 
 // Training-time forward of one highwayConv, FP32: also hands back H = conv(x) + b in the library's row layout
@@ -725,7 +733,7 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   SSV_TRY(launch_add_inplace(dxc, dxr, (long)M * d, s));
   SSV_TRY(launch_transpose_out(dxc, d, B, d, T, dx, s));
   // 4. wgrad
-  if (tc) SSV_TRY(tf32_wgrad(ar, dH, xin, B, T, d, k, dilation, causal ? 1 : 0, dconv_w, s));
+  if (tc) SSV_TRY(tf32_wgrad(ar, dH, 2 * d, 2 * d, xin, d, d, B, T, k, dilation, causal ? 1 : 0, dconv_w, s));
   else SSV_TRY(launch_wgrad(dH, xin, M, T, d, k, dilation, causal ? 1 : 0, P, dconv_w, s));
   return kOk;
 }
@@ -736,8 +744,10 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
 // y = LN(W relu?(x) + b (+ sb per utterance)): models/TTSModel.py:128-131, 173-180, 218-230.  h_save receives the raw
 // conv output ((B T) x round_up(n, 64)), which ssv_conv_ln_bwd takes.
 int ssv_conv_ln_fwd_save(const float* x, const float* w, const float* b, const float* sb, const float* ln_w, const float* ln_b,
-                         int B, int cin, int n, int T, int relu_in, float* y, float* h_save, void* stream) {
+                         int B, int cin, int n, int T, int relu_in, float* y, float* h_save, int precision, void* stream) {
   SSV_CHECK(x && w && b && ln_w && ln_b && y && h_save, "conv_ln_fwd_save: null pointer");
+  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "conv_ln_fwd_save: precision must be SSV_PREC_FP32 (tensor cores, 3xTF32) or SSV_PREC_FP32_FFMA");
+  const bool tc = precision == SSV_PREC_FP32 && cin % T32_BK == 0 && n > 64;
   SSV_CHECK(B > 0 && T > 0 && cin > 0 && n > 0 && n <= 512 && cin <= 512, "conv_ln_fwd_save: bad shape (B=%d, cin=%d, n=%d, T=%d)", B, cin, n, T);
   cudaStream_t s = as_stream(stream);
   Arena ar(s);
@@ -752,15 +762,26 @@ int ssv_conv_ln_fwd_save(const float* x, const float* w, const float* b, const f
   SSV_TRY(ar.alloc<float>((size_t)M * n_pad, &yr));
   SSV_TRY(launch_transpose_in(x, (long)cin * T, T, 1, B, cin, T, xin, x_ld, s));
   if (relu_in) SSV_TRY(launch_relu_rows(xin, (long)M * x_ld, s));
-  SSV_TRY(run_conv(c, EPI_NONE, 1, 0, xin, x_ld, T, B, h_save, n_pad, s, sb, n));
+  if (tc) {
+    float *wh, *wl;
+    SSV_TRY(ar.alloc<float>((size_t)n * cin, &wh));
+    SSV_TRY(ar.alloc<float>((size_t)n * cin, &wl));
+    SSV_TRY(tf32_pack_weights(w, n, cin, 1, cin, wh, wl, s));
+    SSV_TRY(tf32_raw_conv(ar, wh, wl, b, n, cin, 1, 1, 0, xin, x_ld, T, B, h_save, n_pad, s));
+    if (sb) SSV_TRY(launch_add_utt_bias(h_save, n_pad, B, T, n, sb, s));
+  } else {
+    SSV_TRY(run_conv(c, EPI_NONE, 1, 0, xin, x_ld, T, B, h_save, n_pad, s, sb, n));
+  }
   SSV_TRY(launch_ln_rows_fwd(h_save, n_pad, M, n, ln_w, ln_b, yr, n_pad, s));
   SSV_TRY(launch_transpose_out(yr, n_pad, B, n, T, y, s));
   return kOk;
 }
 
 int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float* ln_w, const float* h_saved, int B, int cin, int n,
-                    int T, int relu_in, float* dx, float* dw, float* db, float* dsb, float* dln_w, float* dln_b, void* stream) {
+                    int T, int relu_in, float* dx, float* dw, float* db, float* dsb, float* dln_w, float* dln_b, int precision, void* stream) {
   SSV_CHECK(x && dy && w && ln_w && h_saved && dw && db && dln_w && dln_b, "conv_ln_bwd: null pointer");
+  SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "conv_ln_bwd: precision must be SSV_PREC_FP32 (tensor cores, 3xTF32) or SSV_PREC_FP32_FFMA");
+  const bool tc = precision == SSV_PREC_FP32 && cin % T32_BK == 0 && n % T32_BK == 0 && n > 64;
   SSV_CHECK(B > 0 && T > 0 && cin > 0 && n > 0 && n <= 512 && cin <= 512, "conv_ln_bwd: bad shape (B=%d, cin=%d, n=%d, T=%d)", B, cin, n, T);
   cudaStream_t s = as_stream(stream);
   Arena ar(s);
@@ -772,7 +793,7 @@ int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float
   SSV_TRY(ar.alloc<float>((size_t)nblk * pc, &partial));
   SSV_TRY(ar.alloc<float>((size_t)pc, &sums));
   SSV_TRY(ar.alloc<float>((size_t)B * n, &U));
-  SSV_TRY(ar.alloc<float>((size_t)wgrad_plain_chunks(M) * n * cin, &P));
+  SSV_TRY(ar.alloc<float>(tc ? (size_t)4 : (size_t)wgrad_plain_chunks(M) * n * cin, &P));
   SSV_TRY(launch_transpose_in(x, (long)cin * T, T, 1, B, cin, T, xin, x_ld, s));
   if (relu_in) SSV_TRY(launch_relu_rows(xin, (long)M * x_ld, s));
   SSV_TRY(launch_transpose_in(dy, (long)n * T, T, 1, B, n, T, dyr, n_pad, s));
@@ -797,14 +818,23 @@ int ssv_conv_ln_bwd(const float* x, const float* dy, const float* w, const float
     SSV_CHECK(zero_bias != nullptr, "conv_ln_bwd: no memory for the zero bias");
     SSV_TRY(ar.alloc<float>((size_t)k_p * x_ld, &Wd));
     SSV_TRY(ar.alloc<float>((size_t)M * x_ld, &dxr));
-    SSV_TRY(launch_pad_matrix(w, n, cin, k_p, x_ld, Wd, s));
-    ConvPack g;
-    g.W = Wd; g.bias = const_cast<float*>(zero_bias); g.cin = n; g.cin_p = k_p; g.k = 1; g.n = cin; g.n_pad = x_ld;
-    SSV_TRY(run_conv(g, EPI_NONE, 1, 0, dH, n_pad, T, B, dxr, x_ld, s));
+    if (tc) {
+      float *wdh, *wdl;
+      SSV_TRY(ar.alloc<float>((size_t)cin * k_p, &wdh));
+      SSV_TRY(ar.alloc<float>((size_t)cin * k_p, &wdl));
+      SSV_TRY(tf32_pack_transposed(w, n, cin, k_p, wdh, wdl, s));
+      SSV_TRY(tf32_raw_conv(ar, wdh, wdl, zero_bias, cin, k_p, 1, 1, 0, dH, n_pad, T, B, dxr, x_ld, s));
+    } else {
+      SSV_TRY(launch_pad_matrix(w, n, cin, k_p, x_ld, Wd, s));
+      ConvPack g;
+      g.W = Wd; g.bias = const_cast<float*>(zero_bias); g.cin = n; g.cin_p = k_p; g.k = 1; g.n = cin; g.n_pad = x_ld;
+      SSV_TRY(run_conv(g, EPI_NONE, 1, 0, dH, n_pad, T, B, dxr, x_ld, s));
+    }
     if (relu_in) SSV_TRY(launch_relu_mask(dxr, xin, (long)M * x_ld, s));
     SSV_TRY(launch_transpose_out(dxr, x_ld, B, cin, T, dx, s));
   }
-  SSV_TRY(launch_wgrad_plain(dH, n_pad, xin, x_ld, M, n, cin, P, dw, s));
+  if (tc) SSV_TRY(tf32_wgrad(ar, dH, n_pad, n, xin, x_ld, cin, B, T, 1, 1, 0, dw, s));
+  else SSV_TRY(launch_wgrad_plain(dH, n_pad, xin, x_ld, M, n, cin, P, dw, s));
   return kOk;
 }
 

@@ -136,6 +136,7 @@ int launch_wgrad_plain(const float* dH, int ldh, const float* X, int ldx, int M,
 int launch_att_bwd(const float* Kx /*(B,N,512)*/, const float* Q /*(B,T,256)*/, const float* dR, int ldr, const float* dq_add,
                    const float* A, const float* dA, int B, int N, int T, float* dS /*(B,N,T)*/, float* dq /*(B,T,256)*/,
                    float* dKx /*(B,N,512)*/, cudaStream_t s);
+int launch_add_utt_bias(float* h, int ld, int B, int T, int n, const float* sb /*(B, n)*/, cudaStream_t s);
 int embed_bwd_scratch_floats(int vocab, int E);
 int launch_embed_bwd(const int64_t* ids, int rows, const float* dX, int ld, int vocab, int E, float* scratch, float* dWt, float* dbias,
                      cudaStream_t s);

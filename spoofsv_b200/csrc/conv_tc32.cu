@@ -518,32 +518,34 @@ int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream
 }
 
 // ---- split-K wgrad operands (see conv_tc32.cuh) ----
-// dH (M x n2 rows, channels-last) -> [chunk][n2][kc], hi / lo; rows past M are zero.  32 x 32 tiles; kc % 32 == 0.
-__global__ void __launch_bounds__(256) wgrad_prep_dh_kernel(const float* __restrict__ dH, int M, int n2, int kc, float* __restrict__ Ah,
-                                                            float* __restrict__ Al) {
+// dH (M rows x ldh, n_out real columns, channels-last) -> [chunk][n_out][kc], hi / lo; rows past M are zero.  32 x 32 tiles;
+// kc % 32 == 0.
+__global__ void __launch_bounds__(256) wgrad_prep_dh_kernel(const float* __restrict__ dH, int ldh, int M, int n_out, int kc,
+                                                            float* __restrict__ Ah, float* __restrict__ Al) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int r = r0 + ty + i;
-    tile[ty + i][tx] = r < M ? dH[(size_t)r * n2 + c0 + tx] : 0.f;
+    tile[ty + i][tx] = r < M && c0 + tx < n_out ? dH[(size_t)r * ldh + c0 + tx] : 0.f;
   }
   __syncthreads();
   const int chunk = r0 / kc, kk = r0 - chunk * kc + tx;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int co = c0 + ty + i;
+    if (co >= n_out) continue;
     const float v = tile[tx][ty + i];
     const float h = to_tf32(v);
-    const size_t o = ((size_t)chunk * n2 + co) * kc + kk;
+    const size_t o = ((size_t)chunk * n_out + co) * kc + kk;
     Ah[o] = h;
     Al[o] = to_tf32(v - h);
   }
 }
-// X (B T x x_ld rows, channels-last) -> [(j, ci)][k_pad] with row r = (b, t) holding X[(b, t + (tap_base + j) dil)][ci]
-// (zero outside the utterance and past the last row), hi / lo
-__global__ void __launch_bounds__(256) wgrad_prep_x_kernel(const float* __restrict__ X, int x_ld, int M, int T, int d, int dil, int tap_base,
+// X (B T rows x x_ld, cin real columns, channels-last) -> [(j, ci)][k_pad] with row r = (b, t) holding
+// X[(b, t + (tap_base + j) dil)][ci] (zero outside the utterance and past the last row), hi / lo
+__global__ void __launch_bounds__(256) wgrad_prep_x_kernel(const float* __restrict__ X, int x_ld, int M, int T, int cin, int dil, int tap_base,
                                                            int k_pad, float* __restrict__ Wh, float* __restrict__ Wl) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(256) wgrad_prep_x_kernel(const float* __restri
   for (int i = 0; i < 32; i += 8) {
     const int r = r0 + ty + i;
     float v = 0.f;
-    if (r < M) {
+    if (r < M && c0 + tx < cin) {
       const int b = r / T, ts = r - b * T + off;
       if (ts >= 0 && ts < T) v = X[((size_t)b * T + ts) * x_ld + c0 + tx];
     }
@@ -563,43 +565,62 @@ __global__ void __launch_bounds__(256) wgrad_prep_x_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int ci = c0 + ty + i;
+    if (ci >= cin) continue;
     const float v = tile[tx][ty + i];
     const float h = to_tf32(v);
-    const size_t o = ((size_t)j * d + ci) * k_pad + r0 + tx;
+    const size_t o = ((size_t)j * cin + ci) * k_pad + r0 + tx;
     Wh[o] = h;
     Wl[o] = to_tf32(v - h);
   }
 }
-// partials [chunk][2d][k d] -> dW (2d, d, k)
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ P, int chunks, int d, int k, float* __restrict__ dW) {
-  const long total = (long)2 * d * k * d;
+// partials [chunk][n_out][k cin] -> dW (n_out, cin, k)
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ P, int chunks, int n_out, int cin, int k, float* __restrict__ dW) {
+  const long total = (long)n_out * k * cin;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % d);
-    const int j = (int)((i / d) % k);
-    const int co = (int)(i / ((long)d * k));
+    const int ci = (int)(i % cin);
+    const int j = (int)((i / cin) % k);
+    const int co = (int)(i / ((long)cin * k));
     float sum = 0.f;
     for (int c = 0; c < chunks; ++c) sum += P[(size_t)c * total + i];
-    dW[((size_t)co * d + ci) * k + j] = sum;
+    dW[((size_t)co * cin + ci) * k + j] = sum;
+  }
+}
+// w (n, cin) -> the dgrad operand of a 1x1 conv, [cin][k_p] = w^T with zero columns past n, hi / lo
+__global__ void pack_transposed_tf32_kernel(const float* __restrict__ w, int n, int cin, int k_p, float* __restrict__ hi, float* __restrict__ lo) {
+  const long total = (long)cin * k_p;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % k_p);
+    const int ci = (int)(i / k_p);
+    const float v = kk < n ? w[(size_t)kk * cin + ci] : 0.f;
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(v - h);
   }
 }
 
-int launch_wgrad_prep_dh(const float* dH, int M, int n2, int kc, int chunks, float* Ah, float* Al, cudaStream_t s) {
-  SSV_CHECK(kc % 32 == 0 && n2 % 32 == 0 && (long)chunks * kc >= M, "wgrad_prep_dh: bad chunking (kc %d, chunks %d, M %d)", kc, chunks, M);
-  wgrad_prep_dh_kernel<<<dim3((unsigned)(chunks * kc / 32), (unsigned)(n2 / 32)), 256, 0, s>>>(dH, M, n2, kc, Ah, Al);
+int launch_wgrad_prep_dh(const float* dH, int ldh, int M, int n_out, int kc, int chunks, float* Ah, float* Al, cudaStream_t s) {
+  SSV_CHECK(kc % 32 == 0 && (long)chunks * kc >= M, "wgrad_prep_dh: bad chunking (kc %d, chunks %d, M %d)", kc, chunks, M);
+  wgrad_prep_dh_kernel<<<dim3((unsigned)(chunks * kc / 32), (unsigned)((n_out + 31) / 32)), 256, 0, s>>>(dH, ldh, M, n_out, kc, Ah, Al);
   ++g_launches;
   SSV_CUDA(cudaGetLastError());
   return kOk;
 }
-int launch_wgrad_prep_x(const float* X, int x_ld, int B, int T, int d, int k, int dil, int tap_base, int k_pad, float* Wh, float* Wl,
+int launch_wgrad_prep_x(const float* X, int x_ld, int B, int T, int cin, int k, int dil, int tap_base, int k_pad, float* Wh, float* Wl,
                         cudaStream_t s) {
-  SSV_CHECK(k_pad % 32 == 0 && d % 32 == 0 && k_pad >= B * T, "wgrad_prep_x: bad padding");
-  wgrad_prep_x_kernel<<<dim3((unsigned)(k_pad / 32), (unsigned)(d / 32), (unsigned)k), 256, 0, s>>>(X, x_ld, B * T, T, d, dil, tap_base, k_pad, Wh, Wl);
+  SSV_CHECK(k_pad % 32 == 0 && k_pad >= B * T, "wgrad_prep_x: bad padding");
+  wgrad_prep_x_kernel<<<dim3((unsigned)(k_pad / 32), (unsigned)((cin + 31) / 32), (unsigned)k), 256, 0, s>>>(X, x_ld, B * T, T, cin, dil, tap_base, k_pad, Wh, Wl);
   ++g_launches;
   SSV_CUDA(cudaGetLastError());
   return kOk;
 }
-int launch_wgrad_tc_reduce(const float* P, int chunks, int d, int k, float* dW, cudaStream_t s) {
-  wgrad_tc_reduce_kernel<<<1024, 256, 0, s>>>(P, chunks, d, k, dW);
+int launch_wgrad_tc_reduce(const float* P, int chunks, int n_out, int cin, int k, float* dW, cudaStream_t s) {
+  wgrad_tc_reduce_kernel<<<1024, 256, 0, s>>>(P, chunks, n_out, cin, k, dW);
+  ++g_launches;
+  SSV_CUDA(cudaGetLastError());
+  return kOk;
+}
+int tf32_pack_transposed(const float* w, int n, int cin, int k_p, float* hi, float* lo, cudaStream_t s) {
+  pack_transposed_tf32_kernel<<<256, 256, 0, s>>>(w, n, cin, k_p, hi, lo);
   ++g_launches;
   SSV_CUDA(cudaGetLastError());
   return kOk;

@@ -65,10 +65,13 @@ int tf32_pack_deconv_weights(const float* w, int cin, int cout, float* hi, float
 //   A operand  = dH^T in K chunks, [chunk][2d][kc]   (the kernel's "activations": utterance = chunk, time step = co)
 //   B operand  = shifted X^T, [(j, ci)][chunks * kc] (the kernel's "weights", K origin advancing with the chunk)
 //   partials   = [chunk][2d][k * d], summed into dW (2d, d, k) by the reduce kernel
-int launch_wgrad_prep_dh(const float* dH, int M, int n2, int kc, int chunks, float* Ah, float* Al, cudaStream_t s);
-int launch_wgrad_prep_x(const float* X, int x_ld, int B, int T, int d, int k, int dil, int tap_base, int k_pad, float* Wh, float* Wl,
+// (n_out = 2d, cin = d for a highwayConv; any n_out > 64, cin for the 1x1 layers)
+int launch_wgrad_prep_dh(const float* dH, int ldh, int M, int n_out, int kc, int chunks, float* Ah, float* Al, cudaStream_t s);
+int launch_wgrad_prep_x(const float* X, int x_ld, int B, int T, int cin, int k, int dil, int tap_base, int k_pad, float* Wh, float* Wl,
                         cudaStream_t s);
-int launch_wgrad_tc_reduce(const float* P, int chunks, int d, int k, float* dW, cudaStream_t s);
+int launch_wgrad_tc_reduce(const float* P, int chunks, int n_out, int cin, int k, float* dW, cudaStream_t s);
+// w (n, cin) -> [cin][k_p] = w^T (zero past n): the dgrad operand of a 1x1 conv
+int tf32_pack_transposed(const float* w, int n, int cin, int k_p, float* hi, float* lo, cudaStream_t s);
 // x (fp32, any layout, n elements) -> hi = tf32(x), lo = tf32(x - hi)
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t s);
 // A launch with its TMA descriptors encoded: built once per (layer, buffers, shape) and replayed (encoding four tensor

@@ -307,6 +307,16 @@ __global__ void __launch_bounds__(AB_W * 32) att_bwd_kv_kernel(const float* __re
   *reinterpret_cast<float4*>(o + 260) = make_float4(avv[4], avv[5], avv[6], avv[7]);
 }
 
+// h[(b, t)][c] += sb[b][c]: the per-utterance speaker term of AudioEnc's conv1 / conv3 after a tensor-core conv
+__global__ void add_utt_bias_kernel(float* __restrict__ h, int ld, int B, int T, int n, const float* __restrict__ sb) {
+  const long total = (long)B * T * n;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % n);
+    const long r = i / n;
+    h[r * ld + c] += sb[(r / T) * n + c];
+  }
+}
+
 // ---- embedding backward: dWt[v][c] = sum over the positions with id v of dX[pos][c];  block v < vocab, block vocab: d bias.
 // Block (v, chunk): 8 row groups x 128 channel lanes over the chunk's rows, fixed-order sums (deterministic); the chunks'
 // partial sums are added by embed_bwd_sum_kernel.  (One block per v walking all rows serially took 470 us at 2048 rows.)
@@ -446,6 +456,12 @@ int launch_att_bwd(const float* Kx, const float* Q, const float* dR, int ldr, co
   att_bwd_kv_kernel<<<dim3((N + AB_W - 1) / AB_W, B), AB_W * 32, 0, s>>>(Q, dR, ldr, A, dS, N, T, dKx);
   SSV_CUDA(cudaGetLastError());
   g_launches += 2;
+  return kOk;
+}
+int launch_add_utt_bias(float* h, int ld, int B, int T, int n, const float* sb, cudaStream_t s) {
+  add_utt_bias_kernel<<<grid_for((long)B * T * n), 256, 0, s>>>(h, ld, B, T, n, sb);
+  SSV_CUDA(cudaGetLastError());
+  ++g_launches;
   return kOk;
 }
 int embed_bwd_scratch_floats(int vocab, int E) { return EB_CHUNKS * (vocab + 1) * E; }

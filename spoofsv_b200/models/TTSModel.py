@@ -190,7 +190,7 @@ class _ConvLnFn(torch.autograd.Function):
     reference applies to the layer's input."""
 
     @staticmethod
-    def forward(ctx, x, w, b, sb, g, beta, relu_in):
+    def forward(ctx, x, w, b, sb, g, beta, relu_in, prec=_lib.PREC_FP32_FFMA):
         xs = x.detach().to(torch.float32).contiguous()
         ws, bs, gs, betas = (p.detach().contiguous() for p in (w, b, g, beta))
         sbs = None if sb is None else sb.detach().to(torch.float32).contiguous()
@@ -200,14 +200,14 @@ class _ConvLnFn(torch.autograd.Function):
         h = torch.empty((B * T, (n + 63) // 64 * 64), device=xs.device, dtype=torch.float32)
         _lib.check(_lib.load().ssv_conv_ln_fwd_save(
             xs.data_ptr(), ws.data_ptr(), bs.data_ptr(), None if sbs is None else sbs.data_ptr(), gs.data_ptr(), betas.data_ptr(),
-            B, cin, n, T, int(relu_in), y.data_ptr(), h.data_ptr(), _lib.current_stream_ptr()))
+            B, cin, n, T, int(relu_in), y.data_ptr(), h.data_ptr(), int(prec), _lib.current_stream_ptr()))
         ctx.save_for_backward(xs, ws, gs, h)
-        ctx.cfg = (bool(relu_in), sbs is not None, ctx.needs_input_grad[0])
+        ctx.cfg = (bool(relu_in), sbs is not None, ctx.needs_input_grad[0], int(prec))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        relu_in, has_sb, need_dx = ctx.cfg
+        relu_in, has_sb, need_dx, prec = ctx.cfg
         x, w, g, h = ctx.saved_tensors
         B, cin, T = x.shape
         n = w.shape[0]
@@ -220,8 +220,8 @@ class _ConvLnFn(torch.autograd.Function):
         _lib.check(_lib.load().ssv_conv_ln_bwd(
             x.data_ptr(), dy.data_ptr(), w.data_ptr(), g.data_ptr(), h.data_ptr(), B, cin, n, T, int(relu_in),
             None if dx is None else dx.data_ptr(), dw.data_ptr(), db.data_ptr(), None if dsb is None else dsb.data_ptr(),
-            dg.data_ptr(), dbeta.data_ptr(), _lib.current_stream_ptr()))
-        return dx, dw, db, dsb, dg, dbeta, None
+            dg.data_ptr(), dbeta.data_ptr(), prec, _lib.current_stream_ptr()))
+        return dx, dw, db, dsb, dg, dbeta, None, None
 
 
 class _AttentionTrainFn(torch.autograd.Function):
@@ -543,7 +543,7 @@ class melSyn(_Native):
         te, ae, ad = self.text_encoder, self.audio_encoder, self.audio_decoder
 
         def cl(x, conv, lnm, relu_in=False, sb=None):       # 1x1 conv (+ speaker term) + LayerNorm, fwd / bwd in the library
-            return _ConvLnFn.apply(x, conv.weight, conv.bias, sb, lnm.weight, lnm.bias, relu_in)
+            return _ConvLnFn.apply(x, conv.weight, conv.bias, sb, lnm.weight, lnm.bias, relu_in, _prec(self.precision))
 
         prec = _prec(self.precision)        # "fp32": the highway convs' forward and dgrad on the tensor cores (3xTF32)
 

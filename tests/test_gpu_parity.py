@@ -637,12 +637,14 @@ def _grad_close(got, want, tol=2e-5):
 @pytest.mark.parametrize("cin,n,relu_in,with_sb,B,T", [(80, 256, False, True, 3, 37), (256, 256, True, False, 2, 70),
                                                         (512, 256, False, False, 1, 5), (256, 80, True, False, 3, 129),
                                                         (128, 512, False, False, 2, 33), (256, 256, True, True, 4, 9)])
-def test_conv_ln_forward_backward_vs_autograd(cin, n, relu_in, with_sb, B, T):
+@pytest.mark.parametrize("prec", ["fp32", "fp32-ffma"])
+def test_conv_ln_forward_backward_vs_autograd(prec, cin, n, relu_in, with_sb, B, T):
     """ssv_conv_ln_fwd_save / ssv_conv_ln_bwd (the eleven 1x1 conv + LayerNorm layers of Text2Mel,
     models/TTSModel.py:128-131, 173-180, 218-230) against float64 autograd of the same torch statements: output and the
     gradients of the input, the conv, the per-utterance speaker term and the LayerNorm; ragged row counts, the 80-bin
-    layers, a batch of one."""
+    layers, a batch of one; conv / dgrad / wgrad on the tensor cores (3xTF32, "fp32") and on the CUDA cores."""
     import torch.nn.functional as F
+    from spoofsv_b200 import _lib
     from spoofsv_b200.models.TTSModel import _ConvLnFn
     g = torch.Generator().manual_seed(cin + n + T)
     x = torch.randn((B, cin, T), generator=g)
@@ -652,7 +654,8 @@ def test_conv_ln_forward_backward_vs_autograd(cin, n, relu_in, with_sb, B, T):
     gy = torch.randn((B, n, T), generator=g)
     dev = [t.cuda().requires_grad_(True) for t in (x, w, b, gam, bet)]
     sbd = sb.cuda().requires_grad_(True) if with_sb else None
-    y = _ConvLnFn.apply(dev[0], dev[1], dev[2], sbd, dev[3], dev[4], relu_in)
+    y = _ConvLnFn.apply(dev[0], dev[1], dev[2], sbd, dev[3], dev[4], relu_in,
+                        _lib.PREC_FP32 if prec == "fp32" else _lib.PREC_FP32_FFMA)
     y.backward(gy.cuda())
     ref = [t.double().requires_grad_(True) for t in (x, w, b, gam, bet)]
     sbr = sb.double().requires_grad_(True) if with_sb else None
@@ -976,7 +979,7 @@ def test_graphed_training_iterations_match_eager(cuda_models_k):
             for k in want:
                 assert abs(got[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), (k, got[k], want[k])
             for a, b in zip(p_graph, mod.parameters()):
-                assert float((a - b).abs().max()) <= 1e-7
+                assert float((a - b.detach()).abs().max()) <= 1e-7
             del g
     finally:
         m1.layerwise_train_forward = False
