@@ -41,7 +41,14 @@ struct ScratchBlock {
   bool in_use = false;          // a live Arena owns it (a nested Arena on the same stream falls back to cudaMallocAsync)
 };
 inline std::mutex& scratch_mutex() { static std::mutex m; return m; }
-inline std::map<cudaStream_t, ScratchBlock>& scratch_blocks() { static std::map<cudaStream_t, ScratchBlock> m; return m; }
+// keyed by (device, stream): the default stream has the same handle on every device
+using ScratchKey = std::pair<int, cudaStream_t>;
+inline std::map<ScratchKey, ScratchBlock>& scratch_blocks() { static std::map<ScratchKey, ScratchBlock> m; return m; }
+inline ScratchKey scratch_key(cudaStream_t s) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+  return ScratchKey(dev, s);
+}
 
 struct Arena {
   std::vector<void*> ptrs;
@@ -50,6 +57,7 @@ struct Arena {
   char* blk = nullptr;          // this stream's scratch block
   size_t blk_cap = 0, used = 0, wanted = 0;
   bool owns_blk = false;
+  ScratchKey key{0, nullptr};
   Arena() = default;
   // Stream-ordered scratch (a cached block per stream, cudaMallocAsync / cudaFreeAsync on `s` beyond it): for the
   // per-call workspaces of the standalone ops, which would otherwise pay a cudaMalloc / cudaFree (= device sync) per buffer.
@@ -66,7 +74,8 @@ struct Arena {
       pool_configured = true;
     }
     std::lock_guard<std::mutex> lock(scratch_mutex());
-    ScratchBlock& b = scratch_blocks()[s];
+    key = scratch_key(s);
+    ScratchBlock& b = scratch_blocks()[key];
     if (!b.in_use) {
       b.in_use = owns_blk = true;
       blk = static_cast<char*>(b.base);
@@ -80,7 +89,7 @@ struct Arena {
     }
     if (owns_blk) {
       std::lock_guard<std::mutex> lock(scratch_mutex());
-      ScratchBlock& b = scratch_blocks()[async_stream];
+      ScratchBlock& b = scratch_blocks()[key];
       cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
       if (wanted > blk_cap && cudaStreamIsCapturing(async_stream, &cap_status) != cudaSuccess) cudaGetLastError();
       // grow this stream's block for the next call -- never inside a stream capture: the block must outlive the graph,
