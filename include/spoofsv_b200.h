@@ -153,7 +153,8 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
                          int dilation, int causal, const float* h_saved, float* dx, float* dconv_w, float* dconv_b,
                          float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b,
-                         int precision /* as the forward: recomputed H and dgrad on the tensor cores or the CUDA cores */, void* stream);
+                         int precision /* as the forward: recomputed H, dgrad and wgrad on the tensor cores or the CUDA cores */,
+                         int channels_last /* 1: x, dy and dx are (B, T, d) */, void* stream);
 
 /* ---- the small layers of the Text2Mel training graph, FP32 (reference: the autograd of the nn.Conv1d(kernel 1) +
  * nn.LayerNorm pairs, models/TTSModel.py:128-131, 173-180, 218-230; the unmasked attention of the train branch,
@@ -184,7 +185,8 @@ int ssv_linear_small_bwd(const float* x, const float* dy, int B, int in_f, int o
 int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
                               const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
                               int dilation, int causal, float* y, float* h_save,
-                              int precision /* SSV_PREC_FP32: conv on the tensor cores (3xTF32); SSV_PREC_FP32_FFMA */, void* stream);
+                              int precision /* SSV_PREC_FP32: conv on the tensor cores (3xTF32); SSV_PREC_FP32_FFMA */,
+                              int channels_last /* 1: x and y are (B, T, d) instead of the reference's (B, d, T) */, void* stream);
 
 /* ---- waveform stage (next row of the scope table) -------------------------------------------
  * De-emphasis of B waveforms of n samples each, y[n] = x[n] + coeff * y[n-1]: replaces

@@ -56,8 +56,8 @@ SIGNATURES = {
     "ssv_synthesize_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "ssv_decoder_set_lin_output": (C.c_int, [C.c_void_p, C.c_int]),
     "ssv_deemphasis": (C.c_int, [_c_f32p, _c_f32p, C.c_int, C.c_long, C.c_float, C.c_void_p]),
-    "ssv_highway_conv_bwd": (C.c_int, [_c_f32p] * 8 + [C.c_int] * 6 + [_c_f32p] * 8 + [C.c_int, C.c_void_p]),
-    "ssv_highway_conv_fwd_save": (C.c_int, [_c_f32p] * 7 + [C.c_int] * 6 + [_c_f32p] * 2 + [C.c_int, C.c_void_p]),
+    "ssv_highway_conv_bwd": (C.c_int, [_c_f32p] * 8 + [C.c_int] * 6 + [_c_f32p] * 8 + [C.c_int, C.c_int, C.c_void_p]),
+    "ssv_highway_conv_fwd_save": (C.c_int, [_c_f32p] * 7 + [C.c_int] * 6 + [_c_f32p] * 2 + [C.c_int, C.c_int, C.c_void_p]),
     "ssv_conv_ln_fwd_save": (C.c_int, [_c_f32p] * 6 + [C.c_int] * 5 + [_c_f32p] * 2 + [C.c_int, C.c_void_p]),
     "ssv_conv_ln_bwd": (C.c_int, [_c_f32p] * 5 + [C.c_int] * 5 + [_c_f32p] * 6 + [C.c_int, C.c_void_p]),
     "ssv_attention_train_fwd": (C.c_int, [_c_f32p] * 2 + [C.c_int] * 3 + [_c_f32p] * 2 + [C.c_void_p]),

@@ -629,7 +629,7 @@ static int tf32_wgrad(Arena& ar, const float* dH, int ldh, int n_out, const floa
 // ((B T) x 2d), which ssv_highway_conv_bwd takes instead of recomputing the conv.
 int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* conv_b, const float* ln1_w,
                               const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
-                              int dilation, int causal, float* y, float* h_save, int precision, void* stream) {
+                              int dilation, int causal, float* y, float* h_save, int precision, int channels_last, void* stream) {
   SSV_CHECK(x && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b && y && h_save, "highway_conv_fwd_save: null pointer");
   SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "highway_conv_fwd_save: precision must be SSV_PREC_FP32 (tensor cores, 3xTF32) or SSV_PREC_FP32_FFMA");
   const bool tc = precision == SSV_PREC_FP32;
@@ -645,10 +645,17 @@ int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* 
   ConvPack c;
   if (!tc) SSV_TRY(pack_conv(ar, pm, "conv", 2 * d, d, k, &c, s));
   const int M = B * T;
-  float *xin, *yout;
-  SSV_TRY(ar.alloc<float>((size_t)M * d, &xin));
-  SSV_TRY(ar.alloc<float>((size_t)M * d, &yout));
-  SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
+  // channels_last: x and y are (B, T, d), the library's own row layout -- a stack of layers passes its activations on
+  // without the two boundary transposes per call
+  const float* xin = x;
+  float* yout = y;
+  if (!channels_last) {
+    float* xt;
+    SSV_TRY(ar.alloc<float>((size_t)M * d, &xt));
+    SSV_TRY(ar.alloc<float>((size_t)M * d, &yout));
+    SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xt, d, s));
+    xin = xt;
+  }
   if (tc) {
     float *wh, *wl;
     SSV_TRY(ar.alloc<float>((size_t)2 * d * k * d, &wh));
@@ -659,7 +666,7 @@ int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* 
     SSV_TRY(run_conv(c, EPI_NONE, dilation, causal ? 1 : 0, xin, d, T, B, h_save, 2 * d, s));
   }
   SSV_TRY(launch_hwy_fwd_rows(h_save, xin, M, d, ln1_w, ln1_b, ln2_w, ln2_b, yout, s));
-  SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
+  if (!channels_last) SSV_TRY(launch_transpose_out(yout, d, B, d, T, y, s));
   return kOk;
 }
 
@@ -667,7 +674,7 @@ int ssv_highway_conv_fwd_save(const float* x, const float* conv_w, const float* 
 int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, const float* conv_b, const float* ln1_w,
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, int B, int d, int T, int k,
                          int dilation, int causal, const float* h_saved, float* dx, float* dconv_w, float* dconv_b,
-                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, int precision, void* stream) {
+                         float* dln1_w, float* dln1_b, float* dln2_w, float* dln2_b, int precision, int channels_last, void* stream) {
   SSV_CHECK(x && dy && conv_w && conv_b && ln1_w && ln1_b && ln2_w && ln2_b, "highway_conv_bwd: null input pointer");
   SSV_CHECK(precision == SSV_PREC_FP32 || precision == SSV_PREC_FP32_FFMA, "highway_conv_bwd: precision must be SSV_PREC_FP32 (tensor cores, 3xTF32) or SSV_PREC_FP32_FFMA");
   const bool tc = precision == SSV_PREC_FP32;
@@ -686,21 +693,27 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
   pm.m["ln2.weight"] = {ln2_w, d};
   pm.m["ln2.bias"] = {ln2_b, d};
   const int M = B * T;
-  float *xin, *dyr, *Hbuf = nullptr, *dH, *dxr, *dxc, *partial, *sums, *Wd, *P;
+  float *Hbuf = nullptr, *dH, *dxr, *dxc = dx, *partial, *sums, *Wd, *P;
+  const float *xin = x, *dyr = dy;      // channels_last: x, dy and dx are (B, T, d), the library's row layout
   const float* zero_bias = device_zeros();
   SSV_CHECK(zero_bias != nullptr, "highway_conv_bwd: no memory for the zero bias");
-  SSV_TRY(ar.alloc<float>((size_t)M * d, &xin));
-  SSV_TRY(ar.alloc<float>((size_t)M * d, &dyr));
+  if (!channels_last) {
+    float *xt, *dyt;
+    SSV_TRY(ar.alloc<float>((size_t)M * d, &xt));
+    SSV_TRY(ar.alloc<float>((size_t)M * d, &dyt));
+    SSV_TRY(ar.alloc<float>((size_t)M * d, &dxc));
+    SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xt, d, s));
+    SSV_TRY(launch_transpose_in(dy, (long)d * T, T, 1, B, d, T, dyt, d, s));
+    xin = xt;
+    dyr = dyt;
+  }
   if (!h_saved) SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &Hbuf));
   SSV_TRY(ar.alloc<float>((size_t)M * 2 * d, &dH));
   SSV_TRY(ar.alloc<float>((size_t)M * d, &dxr));
-  SSV_TRY(ar.alloc<float>((size_t)M * d, &dxc));
   SSV_TRY(ar.alloc<float>((size_t)hwy_bwd_row_blocks(M) * 6 * d, &partial));
   SSV_TRY(ar.alloc<float>((size_t)6 * d, &sums));
   SSV_TRY(ar.alloc<float>((size_t)k * 2 * d * d, &Wd));
   SSV_TRY(ar.alloc<float>(tc ? (size_t)4 : (size_t)wgrad_chunks(M) * k * 2 * d * d, &P));      // CUDA-core wgrad partials
-  SSV_TRY(launch_transpose_in(x, (long)d * T, T, 1, B, d, T, xin, d, s));
-  SSV_TRY(launch_transpose_in(dy, (long)d * T, T, 1, B, d, T, dyr, d, s));
   // 1. H = conv(X) + b, raw: saved by the training-time forward, or recomputed here
   const float* H = h_saved;
   if (!h_saved) {
@@ -740,7 +753,7 @@ int ssv_highway_conv_bwd(const float* x, const float* dy, const float* conv_w, c
     SSV_TRY(run_conv(g, EPI_NONE, dilation, causal ? 2 : 0, dH, 2 * d, T, B, dxc, d, s));
   }
   SSV_TRY(launch_add_inplace(dxc, dxr, (long)M * d, s));
-  SSV_TRY(launch_transpose_out(dxc, d, B, d, T, dx, s));
+  if (!channels_last) SSV_TRY(launch_transpose_out(dxc, d, B, d, T, dx, s));
   // 4. wgrad
   if (tc) SSV_TRY(tf32_wgrad(ar, dH, 2 * d, 2 * d, xin, d, d, B, T, k, dilation, causal ? 1 : 0, dconv_w, s));
   else SSV_TRY(launch_wgrad(dH, xin, M, T, d, k, dilation, causal ? 1 : 0, P, dconv_w, s));

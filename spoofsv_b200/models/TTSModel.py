@@ -146,10 +146,15 @@ class _HighwayConvFn(torch.autograd.Function):
     save_h = True        # keep H = conv(x) + b for the backward pass (2d floats per row) instead of recomputing it
 
     @staticmethod
-    def forward(ctx, x, w, b, g1, b1, g2, b2, k, dilation, causal, prec=0):
+    def forward(ctx, x, w, b, g1, b1, g2, b2, k, dilation, causal, prec=0, channels_last=False):
+        """channels_last: x and the result are (B, T, d) -- the library's row layout -- so a stack of layers hands its
+        activations on without the boundary transposes."""
         ps = [p.detach().contiguous() for p in (w, b, g1, b1, g2, b2)]
         xs = x.detach().to(torch.float32).contiguous()
-        B, d, T = xs.shape
+        if channels_last:
+            B, T, d = xs.shape
+        else:
+            B, d, T = xs.shape
         h = None
         if xs.numel() == 0:
             y = torch.empty_like(xs)
@@ -158,30 +163,32 @@ class _HighwayConvFn(torch.autograd.Function):
             h = torch.empty((B * T, 2 * d), device=xs.device, dtype=torch.float32)
             _lib.check(_lib.load().ssv_highway_conv_fwd_save(
                 xs.data_ptr(), *[p.data_ptr() for p in ps], B, d, T, k, dilation, int(causal), y.data_ptr(), h.data_ptr(),
-                int(prec), _lib.current_stream_ptr()))
+                int(prec), int(channels_last), _lib.current_stream_ptr()))
         else:
-            y = _highway_fwd(xs, ps, k, dilation, causal, "fp32-ffma" if prec == _lib.PREC_FP32_FFMA else "fp32")
+            xin = xs.transpose(1, 2).contiguous() if channels_last else xs
+            y = _highway_fwd(xin, ps, k, dilation, causal, "fp32-ffma" if prec == _lib.PREC_FP32_FFMA else "fp32")
+            if channels_last:
+                y = y.transpose(1, 2).contiguous()
         ctx.save_for_backward(xs, *ps, *([h] if h is not None else []))
-        ctx.cfg = (k, dilation, causal, h is not None, int(prec))
+        ctx.cfg = (k, dilation, causal, h is not None, int(prec), bool(channels_last), (B, d, T))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        k, dilation, causal, has_h, prec = ctx.cfg
+        k, dilation, causal, has_h, prec, channels_last, (B, d, T) = ctx.cfg
         saved = ctx.saved_tensors
         x, w, b, g1, b1, g2, b2 = saved[:7]
         h = saved[7] if has_h else None
-        B, d, T = x.shape
         dy = dy.detach().to(torch.float32).contiguous()
         dx = torch.empty_like(x)
         grads = [torch.empty_like(p) for p in (w, b, g1, b1, g2, b2)]
         if x.numel() == 0:
-            return (dx, *[torch.zeros_like(p) for p in (w, b, g1, b1, g2, b2)], None, None, None, None)
+            return (dx, *[torch.zeros_like(p) for p in (w, b, g1, b1, g2, b2)], None, None, None, None, None)
         _lib.check(_lib.load().ssv_highway_conv_bwd(
             x.data_ptr(), dy.data_ptr(), w.data_ptr(), b.data_ptr(), g1.data_ptr(), b1.data_ptr(), g2.data_ptr(),
             b2.data_ptr(), B, d, T, k, dilation, int(causal), h.data_ptr() if h is not None else None, dx.data_ptr(),
-            *[g.data_ptr() for g in grads], prec, _lib.current_stream_ptr()))
-        return (dx, *grads, None, None, None, None)
+            *[g.data_ptr() for g in grads], prec, int(channels_last), _lib.current_stream_ptr()))
+        return (dx, *grads, None, None, None, None, None)
 
 
 class _ConvLnFn(torch.autograd.Function):
@@ -547,14 +554,19 @@ class melSyn(_Native):
 
         prec = _prec(self.precision)        # "fp32": the highway convs' forward and dgrad on the tensor cores (3xTF32)
 
-        def hc(x, bag, k, dil, causal):
+        def hc(x, bag, k, dil, causal):                     # x: (B, T, d), see stack()
             return _HighwayConvFn.apply(x, bag.conv.weight, bag.conv.bias, bag.ln1.weight, bag.ln1.bias, bag.ln2.weight,
-                                        bag.ln2.bias, k, dil, causal, prec)
+                                        bag.ln2.bias, k, dil, causal, prec, True)
 
         def hci(x, bag, causal):
             for i, dil in enumerate((1, 3, 9, 27), start=1):
                 x = hc(x, getattr(bag, f"hc{i}"), 3, dil, causal)
             return x
+
+        def stack(x, fn):
+            """A run of highway layers on channels-last activations: one transpose in, one out, instead of two per layer
+            and direction inside the library calls."""
+            return fn(x.transpose(1, 2).contiguous()).transpose(1, 2).contiguous()
 
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -563,10 +575,12 @@ class melSyn(_Native):
             x = _TextEmbeddingFn.apply(ids, te.textemb_layer.W.weight, te.textemb_layer.W.bias)
             x = cl(x, te.conv1, te.ln1)
             x = cl(x, te.conv2, te.ln2, relu_in=True)
-            x = hci(hci(x, te.hci1, False), te.hci2, False)
-            for bag, k in ((te.hc1, 3), (te.hc2, 3), (te.hc3, 1), (te.hc4, 1)):
-                x = hc(x, bag, k, 1, False)
-            kv = x                                          # [K ; V] (B, 2 hidden, N)
+            def te_stack(x):
+                x = hci(hci(x, te.hci1, False), te.hci2, False)
+                for bag, k in ((te.hc1, 3), (te.hc2, 3), (te.hc3, 1), (te.hc4, 1)):
+                    x = hc(x, bag, k, 1, False)
+                return x
+            kv = stack(x, te_stack)                         # [K ; V] (B, 2 hidden, N)
 
             mel = melspec.to(torch.float32)
             spk = spkemb.to(torch.float32)[:, :, 0]
@@ -575,14 +589,12 @@ class melSyn(_Native):
             q = cl(mel, ae.conv1, ae.ln1, sb=s1)
             q = cl(q, ae.conv2, ae.ln2, relu_in=True)
             q = cl(q, ae.conv3, ae.ln3, relu_in=True, sb=s2)
-            q = hci(hci(q, ae.hci1, True), ae.hci2, True)
-            q = hc(hc(q, ae.hc1, 3, 3, True), ae.hc2, 3, 3, True)
+            q = stack(q, lambda z: hc(hc(hci(hci(z, ae.hci1, True), ae.hci2, True), ae.hc1, 3, 3, True), ae.hc2, 3, 3, True))
 
             A, r = _AttentionTrainFn.apply(kv, q)           # r = [V A ; q]
 
             y = cl(r, ad.conv1, ad.ln1)
-            y = hci(y, ad.hci, True)
-            y = hc(hc(y, ad.hc1, 3, 1, True), ad.hc2, 3, 1, True)
+            y = stack(y, lambda z: hc(hc(hci(z, ad.hci, True), ad.hc1, 3, 1, True), ad.hc2, 3, 1, True))
             y = cl(y, ad.conv2, ad.ln2)
             y = cl(y, ad.conv3, ad.ln3, relu_in=True)
             y = cl(y, ad.conv4, ad.ln4, relu_in=True)

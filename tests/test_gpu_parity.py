@@ -628,6 +628,32 @@ def test_highway_conv_backward_vs_autograd(d, k, dil, causal, B, T, save_h, monk
         assert float((g.detach().cpu().double() - w).abs().max()) <= 2e-5 * max(scale, 1.0), (g.shape, scale)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp32-ffma"])
+@pytest.mark.parametrize("d,k,dil,causal,B,T", [(256, 3, 3, True, 3, 50), (512, 3, 1, False, 2, 41)])
+def test_highway_conv_channels_last_matches_channels_first(prec, d, k, dil, causal, B, T):
+    """The (B, T, d) layout of ssv_highway_conv_fwd_save / _bwd (what the training graph's highway stacks use between
+    layers) gives the output and every gradient of the reference's (B, d, T) layout, bit for bit."""
+    from spoofsv_b200 import _lib
+    from spoofsv_b200.models.TTSModel import _HighwayConvFn, highwayConv
+    torch.manual_seed(3 * d + dil)
+    hc = highwayConv(d, k, dil, causal=causal).cuda()
+    ps = [hc.conv.weight, hc.conv.bias, hc.ln1.weight, hc.ln1.bias, hc.ln2.weight, hc.ln2.bias]
+    p = _lib.PREC_FP32 if prec == "fp32" else _lib.PREC_FP32_FFMA
+    x = torch.randn(B, d, T, device="cuda")
+    gy = torch.randn(B, d, T, device="cuda")
+    outs = []
+    for cl in (False, True):
+        for q in ps:
+            q.grad = None
+        xi = (x.transpose(1, 2).contiguous() if cl else x.clone()).requires_grad_(True)
+        y = _HighwayConvFn.apply(xi, *ps, k, dil, causal, p, cl)
+        y.backward(gy.transpose(1, 2).contiguous() if cl else gy)
+        yy, gx = (y.detach().transpose(1, 2), xi.grad.transpose(1, 2)) if cl else (y.detach(), xi.grad)
+        outs.append([yy.contiguous(), gx.contiguous()] + [q.grad.clone() for q in ps])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def _grad_close(got, want, tol=2e-5):
     assert got.shape == want.shape
     scale = max(float(want.abs().max()), 1.0)
